@@ -1,0 +1,95 @@
+"""CPU: the oracle reproduces the fixtures that oracle/gen_golden.py recorded from the unmodified
+reference (bit-exact on the same torch build; tolerances only guard against a different CPU BLAS)."""
+import json
+
+import pytest
+import torch
+from safetensors.torch import load_file
+
+from moshi_b200.config import MimiConfig, tiny_lm_config
+from moshi_b200.synth import synth_lm_state_dict, synth_mimi_state_dict
+from oracle import scenarios
+from oracle.lm import LMOracle, LMSpec
+from oracle.mimi import MimiOracle
+
+
+@pytest.fixture(scope="module")
+def mimi_sd():
+    return synth_mimi_state_dict(MimiConfig(), seed=scenarios.MIMI_SEED)
+
+
+def test_manifest_says_oracle_was_pinned(golden_dir):
+    m = json.loads((golden_dir / "MANIFEST.json").read_text())
+    assert m["mimi_sine"]["oracle_bit_exact"] and m["mimi_masked"]["oracle_bit_exact"]
+    assert m["lm_tiny_sampled"]["oracle_bit_exact_tokens"] and m["lm_tiny_greedy"]["oracle_bit_exact_tokens"]
+
+
+@torch.no_grad()
+def test_mimi_sine_roundtrip(golden_dir, mimi_sd):
+    gold = load_file(golden_dir / "mimi_sine.safetensors")
+    cfg = MimiConfig()
+    orc = MimiOracle(mimi_sd, cfg)
+    orc.streaming(1)
+    sine = scenarios.sine_1s()
+    codes, pcm = [], []
+    for f in range(sine.shape[-1] // cfg.frame_size):
+        c = orc.encode(sine[..., f * 1920:(f + 1) * 1920])
+        codes.append(c)
+        pcm.append(orc.decode(c))
+    codes, pcm = torch.cat(codes, -1), torch.cat(pcm, -1)
+    assert codes.dtype == torch.int64 and codes.shape == (1, 8, 12)
+    assert (codes == gold["codes_stream"]).all()
+    torch.testing.assert_close(pcm, gold["pcm_stream"], rtol=0, atol=1e-5)
+    # the reference's non-streaming call (13 padded frames) agrees with streaming on the common part
+    assert (gold["codes_batch"][..., :12] == codes).all()
+
+
+@torch.no_grad()
+def test_mimi_masked_rows_and_reset(golden_dir, mimi_sd):
+    gold = load_file(golden_dir / "mimi_masked.safetensors")
+    B, frames = scenarios.MIMI_MASK_B, scenarios.MIMI_MASK_FRAMES
+    pcm = scenarios.mimi_noise(B, frames)
+    orc = MimiOracle(mimi_sd, MimiConfig())
+    orc.streaming(B)
+    for f in range(frames):
+        scenarios.mimi_mask_events(orc, f, B)
+        c = orc.encode(pcm[..., f * 1920:(f + 1) * 1920])
+        assert (c == gold["codes"][f]).all(), f
+        torch.testing.assert_close(orc.decode(c), gold["pcm"][f], rtol=0, atol=1e-5)
+
+
+def test_mimi_rejects_partial_frames(mimi_sd):
+    orc = MimiOracle(mimi_sd, MimiConfig())
+    orc.streaming(1)
+    with pytest.raises(RuntimeError):
+        orc.encode(torch.zeros(1, 1, 1000))
+
+
+@pytest.mark.parametrize("name,sampling", [("lm_tiny_sampled", True), ("lm_tiny_greedy", False)])
+def test_lm_tiny_steps(golden_dir, name, sampling):
+    gold = load_file(golden_dir / f"{name}.safetensors")
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    B, steps = scenarios.LM_B, scenarios.LM_STEPS
+    codes = scenarios.lm_input_codes(cfg, B, steps)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=sampling)
+    orc.streaming(B)
+    torch.manual_seed(scenarios.LM_NOISE_SEED)
+    for i in range(steps):
+        scenarios.lm_mask_events(orc, i, B)
+        nt, na = scenarios.lm_noise(cfg, B) if sampling else (None, None)
+        dbg = {}
+        out = orc.step(codes[i], nt, na, debug=dbg)
+        want = gold["tokens"][i]
+        if out is None:
+            assert (want == -3).all(), i
+        else:
+            assert (out == want).all(), i
+        torch.testing.assert_close(dbg["text_logits"].float()[:, 0, 0], gold["text_logits"][i], rtol=0, atol=0)
+
+
+def test_step_outside_streaming_raises():
+    cfg = tiny_lm_config()
+    orc = LMOracle(synth_lm_state_dict(cfg), LMSpec.from_config(cfg))
+    with pytest.raises(RuntimeError):
+        orc.step(torch.zeros(1, 8, 1, dtype=torch.long))
