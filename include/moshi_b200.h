@@ -1,0 +1,223 @@
+/*
+ * moshi_b200 — C ABI of the B200-native (sm_100a) streaming inference path for
+ * Mimi (SEANet + transformer bottleneck + split RVQ) and the Moshi LM decode step.
+ *
+ * The reference (kyutai-labs/moshi) has no native boundary on this path: its Python classes call
+ * ATen/cuBLAS/cuDNN directly.  The closest precedent is the PyO3 module `rustymimi`
+ * (rust/mimi-pyo3/src/lib.rs:103-236: Tokenizer.encode_step / decode_step / reset).  Each entry
+ * point below cites the reference method it stands behind; `moshi_b200/models/*.py` are the
+ * Python shims that keep the reference signatures and call these functions through ctypes.
+ *
+ * Conventions
+ *   - plain C, opaque handles, `int` return code (0 = B200_OK); on failure b200_last_error()
+ *     returns a thread-local message.  No C++/torch types cross this boundary.
+ *   - pointers named *_dev are device pointers on the handle's GPU; *_host are host pointers.
+ *     Device entry points enqueue work on the stream given to *_streaming_begin and do not
+ *     synchronise; *_host entry points copy in/out through pinned staging buffers and return
+ *     after the result is in the caller's buffer (this is the end-to-end path bench.py times).
+ *   - a handle is thread-compatible, not thread-safe (same as the reference modules,
+ *     moshi/moshi/server.py:160 serialises with one asyncio.Lock).
+ *   - masks are one byte per batch row (torch.bool layout), non-zero = true.
+ *   - all streaming state (conv left-context, overlap-add partials, KV rings, token ring,
+ *     per-row offsets) is owned by the handle between streaming_begin and streaming_end.
+ */
+#ifndef MOSHI_B200_H
+#define MOSHI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = 1,   /* bad argument / unknown tensor name / unsupported option      */
+  B200_ERR_SHAPE = 2,     /* shape or dtype mismatch (reference: AssertionError)          */
+  B200_ERR_STATE = 3,     /* call outside streaming, double streaming (reference: RuntimeError / AssertionError) */
+  B200_ERR_CUDA = 4,      /* CUDA runtime/driver failure; message carries the CUDA error   */
+  B200_ERR_MISSING = 5    /* finalize: a required tensor was never loaded                  */
+};
+
+enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_I64 = 3, B200_U8 = 4 };
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py `gpu_launches`). */
+int64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Mimi  (reference: moshi/moshi/models/compression.py:97-433, loaders.py:38-88, 323-363)       */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct b200_mimi b200_mimi;
+
+typedef struct {
+  int sample_rate;            /* 24000 */
+  float frame_rate;           /* 12.5 */
+  int channels;               /* 1 */
+  int dimension;              /* 512 */
+  int n_filters;              /* 64 */
+  int n_residual_layers;      /* 1 */
+  int n_ratios;               /* 4 */
+  int ratios[8];              /* decoder order: 8,6,5,4 */
+  int kernel_size;            /* 7 */
+  int residual_kernel_size;   /* 3 */
+  int last_kernel_size;       /* 3 */
+  int dilation_base;          /* 2 */
+  int compress;               /* 2 */
+  int tr_d_model;             /* 512 */
+  int tr_num_heads;           /* 8 */
+  int tr_num_layers;          /* 8 */
+  int tr_dim_feedforward;     /* 2048 */
+  int tr_context;             /* 250 */
+  float tr_max_period;        /* 10000 */
+  int q_dimension;            /* 256 */
+  int q_bins;                 /* 2048 */
+  int q_n_q;                  /* 32 codebooks stored */
+  int q_n_semantic;           /* 1 */
+  int num_codebooks;          /* 8 active (MimiModel.set_num_codebooks) */
+} b200_mimi_config;
+
+/* loaders.get_mimi (loaders.py:323-363): build, then feed the state dict tensor by tensor using the
+ * reference's key names (legacy names are normalised by the Python shim),
+ * then finalize (derives centroids = embedding_sum / clamp(cluster_usage, 1e-5), core_vq.py:181-183,
+ * and repacks weights into the kernels' HBM layouts).  Source tensors may be freed after each call. */
+int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out);
+int b200_mimi_load_tensor(b200_mimi* h, const char* name, const void* data_dev, int dtype,
+                          int ndim, const int64_t* shape);
+int b200_mimi_finalize(b200_mimi* h);
+int b200_mimi_destroy(b200_mimi* h);
+
+/* MimiModel.set_num_codebooks (compression.py:263-265 -> vq.py:315-317). */
+int b200_mimi_set_num_codebooks(b200_mimi* h, int n);
+
+/* StreamingModule.streaming(batch) enter / exit (streaming.py:131-137). `stream` is a cudaStream_t. */
+int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream);
+int b200_mimi_streaming_end(b200_mimi* h);
+/* reset_streaming(reset_mask) (streaming.py:139-156); NULL = all rows. */
+int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev);
+/* set_exec_mask(mask) (streaming.py:183-211). */
+int b200_mimi_set_exec_mask(b200_mimi* h, const uint8_t* exec_mask_dev);
+
+/* MimiModel.encode in streaming mode (compression.py:376-388): pcm f32 [B,1,1920*n] -> codes i64 [B,K,n]. */
+int b200_mimi_encode(b200_mimi* h, const float* pcm_dev, int n_frames, int64_t* codes_dev);
+/* MimiModel._encode_to_unquantized_latent (compression.py:338-374): -> latent f32 [B,512,n]. */
+int b200_mimi_encode_to_latent(b200_mimi* h, const float* pcm_dev, int n_frames, float* latent_dev);
+/* SplitResidualVectorQuantizer.encode on a caller-provided latent (vq.py:269-279): [B,512,n] -> [B,K,n]. */
+int b200_mimi_quantize(b200_mimi* h, const float* latent_dev, int n_frames, int64_t* codes_dev);
+/* MimiModel.decode in streaming mode (compression.py:406-429): codes i64 [B,K,n] -> pcm f32 [B,1,1920*n]. */
+int b200_mimi_decode(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames, float* pcm_dev);
+/* MimiModel.decode_latent (compression.py:431-433): codes -> quantized latent f32 [B,512,n]. */
+int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames,
+                            float* latent_dev);
+/* Same as encode / decode with HOST buffers (H2D + D2H inside, returns when the result is ready). */
+int b200_mimi_encode_host(b200_mimi* h, const float* pcm_host, int n_frames, int64_t* codes_host);
+int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codebooks, int n_frames,
+                          float* pcm_host);
+/* Debug taps: copies a named fp32 intermediate of the last call into dst_dev (capacity in elements;
+ * pass dst_dev = NULL to query *numel only).  Names: "enc.<i>", "dec.<i>" = output of SEANet module i
+ * ([B,C,T]; the last encoder module is token-major [B,T,C]), "enc.tr", "dec.up", "dec.tr" ([B,T,C]),
+ * "enc.latent", "dec.latent" ([B,C]). */
+int b200_mimi_read_buffer(b200_mimi* h, const char* name, float* dst_dev, int64_t capacity, int64_t* numel);
+/* Bytes of weights + per-step state traffic of one encode+decode frame at the current batch
+ * (the algorithmic-bytes figure of DESIGN.md, used for the roofline line in bench.py). */
+int64_t b200_mimi_algorithmic_bytes(b200_mimi* h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Moshi LM  (reference: moshi/moshi/models/lm.py:49-850, loaders.py:366-446)                   */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct b200_lm b200_lm;
+
+typedef struct {
+  int dim;                    /* 4096 */
+  int text_card;              /* 32000 */
+  int n_q;                    /* 16 */
+  int dep_q;                  /* 8 */
+  int card;                   /* 2048 */
+  int num_heads;              /* 32 */
+  int num_layers;             /* 32 */
+  int ffn_hidden;             /* 11264 = gating.py:52-58 applied to hidden_scale*dim */
+  int context;                /* 3000 (= KV ring capacity, transformer.py:466-470) */
+  float max_period;           /* 10000 */
+  int depformer_dim;          /* 1024 */
+  int depformer_num_heads;    /* 16 */
+  int depformer_num_layers;   /* 6 */
+  int depformer_ffn_hidden;   /* 2816 */
+  int delays[33];             /* n_q + 1 entries */
+} b200_lm_config;
+
+/* loaders.get_moshi_lm (loaders.py:366-446). Tensors are bf16 with the reference's key names. */
+int b200_lm_create(const b200_lm_config* cfg, b200_lm** out);
+int b200_lm_load_tensor(b200_lm* h, const char* name, const void* data_dev, int dtype,
+                        int ndim, const int64_t* shape);
+int b200_lm_finalize(b200_lm* h);
+int b200_lm_destroy(b200_lm* h);
+
+/* LMGen(...) sampling arguments (lm.py:556-571). */
+int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_text, int top_k,
+                         int top_k_text);
+/* LMGen.streaming(batch) enter / exit (lm.py:604-666): allocates token ring, KV rings, offsets. */
+int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream);
+int b200_lm_streaming_end(b200_lm* h);
+/* _LMGenState.reset (lm.py:537-542) incl. the host step counter quirk (offset_cpu = 0). */
+int b200_lm_reset(b200_lm* h, const uint8_t* reset_mask_dev);
+int b200_lm_set_exec_mask(b200_lm* h, const uint8_t* exec_mask_dev);
+/* Floats of Exp(1) noise one step consumes per batch row: min(top_k_text, text_card) +
+ * dep_q * min(top_k, card), in the draw order of the reference (sampling.py:44). */
+int b200_lm_noise_per_row(b200_lm* h);
+
+/* LMGen.step (lm.py:785-791 -> _step :668-783).
+ *   in_codes_dev  i64 [B, n_in] (n_in >= n_q - dep_q; extra columns ignored, lm.py:688-689)
+ *   noise_dev     f32 [B, b200_lm_noise_per_row] or NULL when use_sampling == 0
+ *   out_tokens_dev i64 [B, dep_q + 1] (row 0 text, 1.. audio; -2 = not ready for that row)
+ *   *ready_host   0 while the reference would return None (offset_cpu <= max_delay), else 1
+ *   support_out_of_sync: LMGen(support_out_of_sync=...) (lm.py:774-776) */
+int b200_lm_step(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev,
+                 int64_t* out_tokens_dev, int support_out_of_sync, int* ready_host);
+int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const float* noise_host,
+                      int64_t* out_tokens_host, int support_out_of_sync, int* ready_host);
+/* Hook / debug taps of the last step, copied into dst_dev (capacity in bytes; NULL = query size):
+ * "text_logits" bf16 [B,text_card] (LMGen.on_text_logits_hook), "transformer_out" bf16 [B,dim]
+ * (step_with_extra_heads), "dep_logits" bf16 [dep_q,B,card], "input_tokens" i64 [B,n_q+1],
+ * "text_token" i64 [B], "audio_tokens" i64 [dep_q,B]. */
+int b200_lm_read_buffer(b200_lm* h, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes);
+/* Algorithmic HBM bytes of one step at the current batch and ring fill: weights once
+ * + per-row KV read/append + embeddings + logits. */
+int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill);
+/* Test/bench helper: declare that every row already holds `fill` steps of history (positions and
+ * ring offsets are advanced; ring contents are whatever is in memory) so that the steady-state
+ * full-ring step can be timed without running 3000 warm-up steps. */
+int b200_lm_assume_fill(b200_lm* h, int fill);
+/* 0 = one launch per kernel, 1 = replay the whole step as one CUDA graph (default 1). */
+int b200_lm_set_graph(b200_lm* h, int enable);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Kernel-level entry points (used by the parity tests; same kernels the handles launch)        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* y[M,N] = x[M,K] * w[N,K]^T, bf16 in, fp32 accumulate, bf16 out.  impl: 0 = auto (what the LM
+ * uses for this shape), 1 = SIMT weight-streaming kernel, 2 = tcgen05/TMA kernel. */
+int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K,
+                        int impl, void* stream);
+/* StreamingConv1d.forward on one layer (conv.py:245-274): x [B,Cin,T], w [Cout,Cin,K], state
+ * previous [B,Cin,Keff-S] (updated in place where exec_mask), y [B,Cout,T/S]. elu_in applies ELU to x. */
+int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,
+                   const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
+                   int K, int stride, int dilation, int elu_in, void* stream);
+/* StreamingConvTranspose1d.forward (conv.py:340-362): x [B,Cin,T], w [Cin,Cout,K], partial
+ * [B,Cout,K-S] (updated where exec_mask), y [B,Cout,T*S]. */
+int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
+                     const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
+                     int K, int stride, int elu_in, void* stream);
+/* sample_token (sampling.py:86-106): logits bf16 [B,card], noise f32 [B,min(k,card)] -> i64 [B]. */
+int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B,
+                   int card, int use_sampling, float temp, int top_k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSHI_B200_H */

@@ -225,8 +225,8 @@ MOSHI_7B = LMConfig()
 
 def tiny_lm_config(**over) -> LMConfig:
     """A scaled-down member of the 7B family that the CPU oracle steps in milliseconds."""
-    base = dict(dim=256, text_card=500, n_q=16, dep_q=8, card=64, num_heads=4, num_layers=3,
+    base = dict(dim=256, text_card=500, n_q=16, dep_q=8, card=64, num_heads=2, num_layers=3,
                 hidden_scale=4.125, context=12, depformer_dim=128, depformer_dim_feedforward=528,
-                depformer_num_heads=4, depformer_num_layers=2)
+                depformer_num_heads=2, depformer_num_layers=2)
     base.update(over)
     return LMConfig(**base)

@@ -1,0 +1,71 @@
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int TensorStore::put(const char* name, const void* dev, int dtype, int ndim, const int64_t* shape) {
+  if (!name || !dev || ndim < 0 || ndim > 8) B200_FAIL(B200_ERR_INVALID, "load_tensor: bad arguments");
+  size_t es = dtype_size(dtype);
+  if (es == 0) B200_FAIL(B200_ERR_INVALID, "load_tensor(%s): unknown dtype %d", name, dtype);
+  Tensor t;
+  t.dtype = dtype;
+  t.shape.assign(shape, shape + ndim);
+  size_t bytes = (size_t)t.numel() * es;
+  B200_CUDA(cudaMalloc(&t.data, bytes ? bytes : 1));
+  B200_CUDA(cudaMemcpy(t.data, dev, bytes, cudaMemcpyDeviceToDevice));
+  auto it = items.find(name);
+  if (it != items.end()) {
+    cudaFree(it->second.data);
+    items.erase(it);
+  }
+  items[name] = t;
+  return B200_OK;
+}
+
+const Tensor* TensorStore::find(const std::string& name) const {
+  auto it = items.find(name);
+  return it == items.end() ? nullptr : &it->second;
+}
+
+void TensorStore::release(const std::string& name) {
+  auto it = items.find(name);
+  if (it != items.end()) {
+    cudaFree(it->second.data);
+    items.erase(it);
+  }
+}
+
+void TensorStore::release_all() {
+  for (auto& kv : items) cudaFree(kv.second.data);
+  items.clear();
+}
+
+int Arena::alloc(void** out, size_t bytes, bool zero) {
+  *out = nullptr;
+  B200_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  ptrs.push_back(*out);
+  if (zero) B200_CUDA(cudaMemset(*out, 0, bytes));
+  return B200_OK;
+}
+
+void Arena::free_all() {
+  for (void* p : ptrs) cudaFree(p);
+  ptrs.clear();
+}
+
+}  // namespace b200
+
+extern "C" {
+const char* b200_last_error(void) { return b200::g_err; }
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+int64_t b200_launch_count(void) { return b200::g_launches.load(); }
+}

@@ -1,0 +1,555 @@
+// Moshi LM handle: weights (reference state-dict names), streaming state, and the per-frame decode
+// step (LMGen._step, lm.py:668-783): token ring -> Temporal transformer -> text sample ->
+// Depformer (dep_q dependent sub-steps) -> token ring.
+#include "gemm_tc.cuh"
+#include "lm_kernels.cuh"
+
+using namespace b200;
+using namespace b200::lm;
+
+namespace {
+
+struct TLayer {
+  const bf16 *in_w, *out_w, *n1, *n2, *lin_in, *lin_out;
+  bf16 *kc = nullptr, *vc = nullptr;
+};
+struct DLayer {
+  std::vector<const bf16*> in_w, out_w, lin_in, lin_out;   // one per depformer step
+  const bf16 *n1, *n2;
+  bf16 *kc = nullptr, *vc = nullptr;
+};
+
+}  // namespace
+
+struct b200_lm {
+  b200_lm_config cfg;
+  TensorStore store;
+  Arena weights, state;
+  bool finalized = false;
+  int batch = 0;
+  cudaStream_t stream = nullptr;
+  int Kc = 0, max_delay = 0, CT = 0;
+  // sampling (LMGen defaults, lm.py:556-571)
+  int use_sampling = 1, top_k = 250, top_k_text = 25;
+  float temp = 0.8f, temp_text = 0.7f;
+  int gemm_impl = 0;
+  // weights
+  EmbedTables emb;
+  std::vector<TLayer> layers;
+  std::vector<DLayer> dlayers;
+  const bf16 *out_norm = nullptr, *text_linear = nullptr;
+  bf16* dep_in_all = nullptr;                  // [dep_q * dd][dim]
+  std::vector<const bf16*> dep_tables;         // [0] = depformer_text_emb, [k] = depformer_emb[k-1]
+  std::vector<const bf16*> dep_heads;          // linears[k]
+  int* delays_dev = nullptr;
+  // state
+  long long *cache = nullptr, *offsets = nullptr, *pos = nullptr;
+  uint8_t* exec_mask = nullptr;
+  long long offset_cpu = 0;
+  // activations
+  long long *in_codes = nullptr, *input_tokens = nullptr, *text_token = nullptr, *audio_tokens = nullptr, *out_tokens = nullptr;
+  float* noise = nullptr;
+  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *q = nullptr, *ao = nullptr, *hbuf = nullptr, *tout = nullptr;
+  bf16 *text_logits = nullptr, *din = nullptr, *dx = nullptr, *dxn = nullptr, *dqkv = nullptr, *dq = nullptr, *dao = nullptr,
+       *dh = nullptr, *dep_logits = nullptr;
+  float* attn_part = nullptr;
+  int nsplit = 1;
+  int n_in_static = 0;
+  // graph
+  int graph_enabled = 1;
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t graph_kernels = 0;                   // kernel nodes in the captured step (for b200_launch_count)
+  // host staging
+  long long *pin_in = nullptr, *pin_out = nullptr;
+  float* pin_noise = nullptr;
+  int64_t weight_bytes = 0;
+  tc::GemmPlanCache plans;
+};
+
+namespace {
+
+int get_bf16(b200_lm* h, const std::string& name, std::vector<int64_t> shape, const bf16** out) {
+  const Tensor* t = h->store.find(name);
+  if (!t) B200_FAIL(B200_ERR_MISSING, "lm finalize: tensor '%s' was not loaded", name.c_str());
+  if (t->dtype != B200_BF16) B200_FAIL(B200_ERR_SHAPE, "lm tensor '%s' must be bfloat16", name.c_str());
+  if (t->shape != shape) {
+    std::string got;
+    for (auto s : t->shape) got += std::to_string(s) + ",";
+    B200_FAIL(B200_ERR_SHAPE, "lm tensor '%s' has shape [%s]", name.c_str(), got.c_str());
+  }
+  *out = static_cast<const bf16*>(t->data);
+  h->weight_bytes += t->numel() * 2;
+  return B200_OK;
+}
+
+int noise_per_row(const b200_lm* h) {
+  const int kt = h->top_k_text < h->cfg.text_card ? h->top_k_text : h->cfg.text_card;
+  const int ka = h->top_k < h->cfg.card ? h->top_k : h->cfg.card;
+  return kt + h->cfg.dep_q * ka;
+}
+
+// y[M][N] = epi(x[M][K] . w[N][K]^T)
+int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, const bf16* res,
+           long long ldr, int M, int N, int K, int epi, int gate_rows) {
+  int impl = h->gemm_impl;
+  if (impl == 0) impl = tc::supported(M, N, K, epi) ? 2 : 1;
+  if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->stream);
+  const int grid = ceil_div(N * 32, 256);
+  if (epi == LIN_STORE) {
+    auto k = linear_simt_kernel<LIN_STORE>;
+    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+  } else if (epi == LIN_RESADD) {
+    auto k = linear_simt_kernel<LIN_RESADD>;
+    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+  } else {
+    auto k = linear_simt_kernel<LIN_GATE>;
+    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+  }
+  return check_launch("linear_simt");
+}
+
+int sample(b200_lm* h, const bf16* logits, int card, const float* noise, long long* out, float temp, int top_k) {
+  B200_LAUNCH(sample_kernel, h->batch, SAMPLE_THREADS, 0, h->stream, logits, (long long)card, noise,
+              (long long)noise_per_row(h), out, card, h->use_sampling, temp, top_k);
+  return check_launch("sample");
+}
+
+TokenRing ring(b200_lm* h) {
+  TokenRing r;
+  r.cache = h->cache; r.offsets = h->offsets; r.exec_mask = h->exec_mask; r.delays = h->delays_dev;
+  r.Kc = h->Kc; r.CT = h->CT; r.dep_q = h->cfg.dep_q; r.n_q = h->cfg.n_q; r.card = h->cfg.card;
+  r.text_card = h->cfg.text_card; r.max_delay = h->max_delay;
+  return r;
+}
+
+// The whole frame as a fixed launch sequence over static buffers (captured into one CUDA graph).
+int step_body(b200_lm* h) {
+  const auto& c = h->cfg;
+  const int B = h->batch, d = c.dim, H = c.num_heads, D = d / H, F = c.ffn_hidden;
+  const int dd = c.depformer_dim, dH = c.depformer_num_heads, dD = dd / dH, dF = c.depformer_ffn_hidden;
+  cudaStream_t st = h->stream;
+  const float nl = -logf(c.max_period) * 2.f / (float)D;
+
+  B200_LAUNCH(lm_prepare_kernel, ceil_div(B * h->Kc, 128), 128, 0, st, ring(h), h->in_codes, h->n_in_static,
+              h->input_tokens, B);
+  B200_LAUNCH(lm_embed_sum_kernel, ceil_div(B * d / 2, 256), 256, 0, st, h->emb, h->input_tokens, h->x, B, d);
+  for (auto& L : h->layers) {
+    B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
+    B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0));
+    B200_LAUNCH(rope_append_bf16_kernel, (unsigned)ceil_div64((long long)B * H * D / 2, 256), 256, 0, st, h->qkv, h->q,
+                L.kc, L.vc, h->pos, h->exec_mask, 0, B, H, D, c.context, 1, nl);
+    {
+      dim3 grid(B * H, h->nsplit);
+      B200_LAUNCH(attn_decode_kernel, grid, ATT_THREADS, 0, st, h->q, L.kc, L.vc, h->attn_part, h->pos, h->exec_mask, H,
+                  c.context, h->nsplit);
+      B200_LAUNCH(attn_combine_kernel, B * H, ATT_D, 0, st, h->attn_part, h->ao, h->nsplit);
+    }
+    B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0));
+    B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n2, h->xn, d, 1e-8f);
+    B200_TRY(linear(h, h->xn, d, L.lin_in, h->hbuf, F, nullptr, 0, B, F, d, LIN_GATE, F));
+    B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0));
+  }
+  B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, h->out_norm, h->tout, d, 1e-8f);
+  B200_TRY(linear(h, h->tout, d, h->text_linear, h->text_logits, c.text_card, nullptr, 0, B, c.text_card, d, LIN_STORE, 0));
+  B200_TRY(sample(h, h->text_logits, c.text_card, h->noise, h->text_token, h->temp_text, h->top_k_text));
+
+  // Depformer (lm.py:809-850): fresh KV state every frame, all rows advance together.
+  const int kt = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
+  const int ka = h->top_k < c.card ? h->top_k : c.card;
+  B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, B, c.dep_q * dd, d, LIN_STORE, 0));
+  for (int k = 0; k < c.dep_q; ++k) {
+    const long long* prev = k == 0 ? h->text_token : h->audio_tokens + (long long)(k - 1) * B;
+    B200_LAUNCH(dep_input_kernel, ceil_div(B * dd, 256), 256, 0, st, h->din, (long long)c.dep_q * dd, k * dd,
+                h->dep_tables[k], prev, h->dx, B, dd);
+    for (auto& L : h->dlayers) {
+      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
+      B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0));
+      B200_LAUNCH(rope_append_bf16_kernel, (unsigned)ceil_div64((long long)B * dH * dD / 2, 256), 256, 0, st, h->dqkv,
+                  h->dq, L.kc, L.vc, (const long long*)nullptr, (const uint8_t*)nullptr, k, B, dH, dD, c.dep_q, 0, 0.f);
+      B200_LAUNCH(dep_attn_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dq, L.kc, L.vc, h->dao, B, dH, dD, c.dep_q,
+                  k + 1);
+      B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0));
+      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
+      B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF));
+      B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0));
+    }
+    bf16* logits = h->dep_logits + (long long)k * B * c.card;
+    B200_TRY(linear(h, h->dx, dd, h->dep_heads[k], logits, c.card, nullptr, 0, B, c.card, dd, LIN_STORE, 0));
+    B200_TRY(sample(h, logits, c.card, h->noise + kt + (long long)k * ka, h->audio_tokens + (long long)k * B, h->temp,
+                    h->top_k));
+  }
+  B200_LAUNCH(advance_pos_kernel, ceil_div(B, 128), 128, 0, st, h->pos, h->exec_mask, B);
+  B200_LAUNCH(lm_finish_kernel, ceil_div(B, 128), 128, 0, st, ring(h), h->text_token, h->audio_tokens, h->out_tokens, B);
+  return check_launch("lm step");
+}
+
+int ensure_streaming(b200_lm* h, const char* what) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "%s: null handle", what);
+  if (!h->finalized) B200_FAIL(B200_ERR_STATE, "%s: handle not finalized", what);
+  if (h->batch <= 0) B200_FAIL(B200_ERR_STATE, "%s: not streaming (wrap calls in streaming())", what);   // lm.py:673-676
+  return B200_OK;
+}
+
+void drop_graph(b200_lm* h) {
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
+  if (!cfg || !out) B200_FAIL(B200_ERR_INVALID, "lm_create: null argument");
+  if (cfg->n_q < 1 || cfg->n_q > 32 || cfg->dep_q < 1 || cfg->dep_q > cfg->n_q)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: n_q=%d dep_q=%d unsupported", cfg->n_q, cfg->dep_q);
+  if (cfg->dim % cfg->num_heads || cfg->dim / cfg->num_heads != ATT_D)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: temporal head dim must be %d", ATT_D);
+  if (cfg->depformer_dim % cfg->depformer_num_heads || (cfg->depformer_dim / cfg->depformer_num_heads) % 64)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: depformer head dim must be a multiple of 64");
+  if (cfg->dep_q > 8) B200_FAIL(B200_ERR_INVALID, "lm_create: dep_q > 8 unsupported");
+  if (cfg->dim % 8 || cfg->ffn_hidden % 8 || cfg->depformer_dim % 8 || cfg->depformer_ffn_hidden % 8)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: feature sizes must be multiples of 8");
+  if (cfg->text_card + 1 > 65535 || cfg->card + 1 > 65535)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: vocabularies above 65535 unsupported by the sampler");
+  b200_lm* h = new b200_lm();
+  h->cfg = *cfg;
+  h->Kc = cfg->n_q + 1;
+  h->max_delay = 0;
+  for (int k = 0; k < h->Kc; ++k) h->max_delay = cfg->delays[k] > h->max_delay ? cfg->delays[k] : h->max_delay;
+  h->CT = h->max_delay + 2;     // lm.py:606-611
+  *out = h;
+  return B200_OK;
+}
+
+int b200_lm_load_tensor(b200_lm* h, const char* name, const void* data_dev, int dtype, int ndim, const int64_t* shape) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_load_tensor: null handle");
+  if (h->finalized) B200_FAIL(B200_ERR_STATE, "lm_load_tensor: already finalized");
+  return h->store.put(name, data_dev, dtype, ndim, shape);
+}
+
+int b200_lm_finalize(b200_lm* h) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_finalize: null handle");
+  if (h->finalized) return B200_OK;
+  const auto& c = h->cfg;
+  const int d = c.dim, dd = c.depformer_dim, F = c.ffn_hidden, dF = c.depformer_ffn_hidden;
+  h->emb.n_q = c.n_q;
+  for (int k = 0; k < c.n_q; ++k)
+    B200_TRY(get_bf16(h, "emb." + std::to_string(k) + ".weight", {c.card + 1, d}, &h->emb.audio[k]));
+  B200_TRY(get_bf16(h, "text_emb.weight", {c.text_card + 1, d}, &h->emb.text));
+  B200_TRY(get_bf16(h, "text_linear.weight", {c.text_card, d}, &h->text_linear));
+  B200_TRY(get_bf16(h, "out_norm.alpha", {1, 1, d}, &h->out_norm));
+  h->layers.resize(c.num_layers);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string p = "transformer.layers." + std::to_string(l);
+    TLayer& L = h->layers[l];
+    B200_TRY(get_bf16(h, p + ".self_attn.in_projs.0.weight", {3 * d, d}, &L.in_w));
+    B200_TRY(get_bf16(h, p + ".self_attn.out_projs.0.weight", {d, d}, &L.out_w));
+    B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, d}, &L.n1));
+    B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, d}, &L.n2));
+    B200_TRY(get_bf16(h, p + ".gating.linear_in.weight", {2 * F, d}, &L.lin_in));
+    B200_TRY(get_bf16(h, p + ".gating.linear_out.weight", {d, F}, &L.lin_out));
+  }
+  // depformer_in.{k} stacked so that all dep_q projections of transformer_out are one GEMM
+  B200_TRY(h->weights.alloc_t(&h->dep_in_all, (size_t)c.dep_q * dd * d, false));
+  for (int k = 0; k < c.dep_q; ++k) {
+    const bf16* w = nullptr;
+    const std::string name = "depformer_in." + std::to_string(k) + ".weight";
+    B200_TRY(get_bf16(h, name, {dd, d}, &w));
+    B200_CUDA(cudaMemcpy(h->dep_in_all + (size_t)k * dd * d, w, (size_t)dd * d * 2, cudaMemcpyDeviceToDevice));
+    h->store.release(name);
+  }
+  h->dep_tables.resize(c.dep_q);
+  B200_TRY(get_bf16(h, "depformer_text_emb.weight", {c.text_card + 1, dd}, &h->dep_tables[0]));
+  for (int k = 1; k < c.dep_q; ++k)
+    B200_TRY(get_bf16(h, "depformer_emb." + std::to_string(k - 1) + ".weight", {c.card + 1, dd}, &h->dep_tables[k]));
+  h->dep_heads.resize(c.dep_q);
+  for (int k = 0; k < c.dep_q; ++k)
+    B200_TRY(get_bf16(h, "linears." + std::to_string(k) + ".weight", {c.card, dd}, &h->dep_heads[k]));
+  h->dlayers.resize(c.depformer_num_layers);
+  for (int l = 0; l < c.depformer_num_layers; ++l) {
+    const std::string p = "depformer.layers." + std::to_string(l);
+    DLayer& L = h->dlayers[l];
+    L.in_w.resize(c.dep_q); L.out_w.resize(c.dep_q); L.lin_in.resize(c.dep_q); L.lin_out.resize(c.dep_q);
+    for (int k = 0; k < c.dep_q; ++k) {
+      const std::string ks = std::to_string(k);
+      B200_TRY(get_bf16(h, p + ".self_attn.in_projs." + ks + ".weight", {3 * dd, dd}, &L.in_w[k]));
+      B200_TRY(get_bf16(h, p + ".self_attn.out_projs." + ks + ".weight", {dd, dd}, &L.out_w[k]));
+      B200_TRY(get_bf16(h, p + ".gating." + ks + ".linear_in.weight", {2 * dF, dd}, &L.lin_in[k]));
+      B200_TRY(get_bf16(h, p + ".gating." + ks + ".linear_out.weight", {dd, dF}, &L.lin_out[k]));
+    }
+    B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, dd}, &L.n1));
+    B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, dd}, &L.n2));
+  }
+  B200_TRY(h->weights.alloc_t(&h->delays_dev, h->Kc, false));
+  B200_CUDA(cudaMemcpy(h->delays_dev, c.delays, h->Kc * sizeof(int), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaDeviceSynchronize());
+  h->finalized = true;
+  return B200_OK;
+}
+
+int b200_lm_destroy(b200_lm* h) {
+  if (!h) return B200_OK;
+  b200_lm_streaming_end(h);
+  h->store.release_all();
+  h->weights.free_all();
+  delete h;
+  return B200_OK;
+}
+
+int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_text, int top_k, int top_k_text) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_set_sampling: null handle");
+  if (top_k < 1 || top_k_text < 1 || top_k > SAMPLE_MAX_K || top_k_text > SAMPLE_MAX_K)
+    B200_FAIL(B200_ERR_INVALID, "lm_set_sampling: top_k must be in [1, %d]", SAMPLE_MAX_K);
+  if (h->batch > 0 && (top_k != h->top_k || top_k_text != h->top_k_text))
+    B200_FAIL(B200_ERR_STATE, "lm_set_sampling: top_k cannot change while streaming");
+  h->use_sampling = use_sampling; h->temp = temp; h->temp_text = temp_text; h->top_k = top_k; h->top_k_text = top_k_text;
+  drop_graph(h);
+  return B200_OK;
+}
+
+int b200_lm_noise_per_row(b200_lm* h) { return h ? noise_per_row(h) : 0; }
+
+int b200_lm_set_graph(b200_lm* h, int enable) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_set_graph: null handle");
+  h->graph_enabled = enable;
+  if (!enable) drop_graph(h);
+  return B200_OK;
+}
+
+int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
+  if (!h || !h->finalized) B200_FAIL(B200_ERR_STATE, "lm_streaming_begin: handle not finalized");
+  if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "lm_streaming_begin: already streaming");
+  if (batch < 1) B200_FAIL(B200_ERR_INVALID, "lm_streaming_begin: batch %d", batch);
+  const auto& c = h->cfg;
+  const int B = batch, d = c.dim, H = c.num_heads, D = d / H, dd = c.depformer_dim;
+  h->stream = static_cast<cudaStream_t>(stream);
+  Arena& A = h->state;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t kv_bytes = (size_t)c.num_layers * 2 * B * H * c.context * D * 2;
+  if (kv_bytes + (1ull << 30) > free_b)
+    B200_FAIL(B200_ERR_INVALID, "lm_streaming_begin: %d sessions need %.1f GB of KV ring, %.1f GB free", B, kv_bytes / 1e9,
+              free_b / 1e9);
+  B200_TRY(A.alloc_t(&h->exec_mask, B, false));
+  B200_CUDA(cudaMemset(h->exec_mask, 1, B));
+  B200_TRY(A.alloc_t(&h->cache, (size_t)B * h->Kc * h->CT, false));
+  {
+    std::vector<long long> init((size_t)B * h->Kc * h->CT, -2);   // ungenerated_token_id, lm.py:606-611
+    B200_CUDA(cudaMemcpy(h->cache, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
+  B200_TRY(A.alloc_t(&h->offsets, B));
+  B200_TRY(A.alloc_t(&h->pos, B));
+  h->offset_cpu = 0;
+  for (auto& L : h->layers) {
+    B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.context * D));
+    B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.context * D));
+  }
+  for (auto& L : h->dlayers) {
+    B200_TRY(A.alloc_t(&L.kc, (size_t)B * dd * c.dep_q));
+    B200_TRY(A.alloc_t(&L.vc, (size_t)B * dd * c.dep_q));
+  }
+  const int n_in_max = c.n_q;   // callers may pass more columns than needed (lm.py:688-689)
+  B200_TRY(A.alloc_t(&h->in_codes, (size_t)B * n_in_max));
+  B200_TRY(A.alloc_t(&h->input_tokens, (size_t)B * h->Kc));
+  B200_TRY(A.alloc_t(&h->text_token, B));
+  B200_TRY(A.alloc_t(&h->audio_tokens, (size_t)B * c.dep_q));
+  B200_TRY(A.alloc_t(&h->out_tokens, (size_t)B * (c.dep_q + 1)));
+  B200_TRY(A.alloc_t(&h->noise, (size_t)B * noise_per_row(h), false));
+  {
+    std::vector<float> ones((size_t)B * noise_per_row(h), 1.f);
+    B200_CUDA(cudaMemcpy(h->noise, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+  }
+  B200_TRY(A.alloc_t(&h->x, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->xn, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->qkv, (size_t)B * 3 * d));
+  B200_TRY(A.alloc_t(&h->q, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->ao, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->hbuf, (size_t)B * c.ffn_hidden));
+  B200_TRY(A.alloc_t(&h->tout, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->text_logits, (size_t)B * c.text_card));
+  B200_TRY(A.alloc_t(&h->din, (size_t)B * c.dep_q * dd));
+  B200_TRY(A.alloc_t(&h->dx, (size_t)B * dd));
+  B200_TRY(A.alloc_t(&h->dxn, (size_t)B * dd));
+  B200_TRY(A.alloc_t(&h->dqkv, (size_t)B * 3 * dd));
+  B200_TRY(A.alloc_t(&h->dq, (size_t)B * dd));
+  B200_TRY(A.alloc_t(&h->dao, (size_t)B * dd));
+  B200_TRY(A.alloc_t(&h->dh, (size_t)B * c.depformer_ffn_hidden));
+  B200_TRY(A.alloc_t(&h->dep_logits, (size_t)B * c.dep_q * c.card));
+  // split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
+  int ns = ceil_div(148 * 4, B * H);
+  if (ns < 1) ns = 1;
+  if (ns > 16) ns = 16;
+  if (ns > ceil_div(c.context, 64)) ns = ceil_div(c.context, 64);
+  h->nsplit = ns;
+  B200_TRY(A.alloc_t(&h->attn_part, (size_t)B * H * ns * (ATT_D + 2)));
+  B200_CUDA(cudaMallocHost(&h->pin_in, (size_t)B * n_in_max * 8));
+  B200_CUDA(cudaMallocHost(&h->pin_out, (size_t)B * (c.dep_q + 1) * 8));
+  B200_CUDA(cudaMallocHost(&h->pin_noise, (size_t)B * noise_per_row(h) * 4));
+  B200_CUDA(cudaDeviceSynchronize());
+  h->batch = B;
+  return B200_OK;
+}
+
+int b200_lm_streaming_end(b200_lm* h) {
+  if (!h) return B200_OK;
+  if (h->batch > 0) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
+  h->plans.clear();
+  h->state.free_all();
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->pin_noise) cudaFreeHost(h->pin_noise);
+  h->pin_in = h->pin_out = nullptr;
+  h->pin_noise = nullptr;
+  h->batch = 0;
+  return B200_OK;
+}
+
+int b200_lm_reset(b200_lm* h, const uint8_t* reset_mask_dev) {
+  B200_TRY(ensure_streaming(h, "lm_reset"));
+  const int B = h->batch;
+  // per-row device offsets (lm.py:539, transformer.py:229-234, 331-333) ...
+  B200_LAUNCH(lm_reset_kernel, ceil_div(B, 128), 128, 0, h->stream, h->offsets, h->pos, h->exec_mask,
+              reset_mask_dev, B);
+  // ... and the global host counter (lm.py:540): after any reset, step() reports "not ready" for max_delay calls
+  h->offset_cpu = 0;
+  return check_launch("lm_reset");
+}
+
+int b200_lm_set_exec_mask(b200_lm* h, const uint8_t* exec_mask_dev) {
+  B200_TRY(ensure_streaming(h, "lm_set_exec_mask"));
+  if (!exec_mask_dev) B200_FAIL(B200_ERR_INVALID, "lm_set_exec_mask: null mask");
+  B200_CUDA(cudaMemcpyAsync(h->exec_mask, exec_mask_dev, h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
+int b200_lm_assume_fill(b200_lm* h, int fill) {
+  B200_TRY(ensure_streaming(h, "lm_assume_fill"));
+  if (fill < 0) B200_FAIL(B200_ERR_INVALID, "lm_assume_fill: negative fill");
+  std::vector<long long> v(h->batch, fill);
+  B200_CUDA(cudaMemcpyAsync(h->offsets, v.data(), v.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA(cudaMemcpyAsync(h->pos, v.data(), v.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  h->offset_cpu = fill;
+  return B200_OK;
+}
+
+static int run_step(b200_lm* h, int n_in) {
+  if (n_in != h->n_in_static) {
+    h->n_in_static = n_in;
+    drop_graph(h);
+  }
+  if (!h->graph_enabled) return step_body(h);
+  if (!h->graph_exec) {
+    // make sure every lazily-built resource (TMA descriptors) exists before capture
+    B200_TRY(tc::prepare_plans(h->plans));
+    cudaGraph_t graph = nullptr;
+    const int64_t before = g_launches.load();
+    B200_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = step_body(h);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    h->graph_kernels = g_launches.load() - before;
+    g_launches.fetch_sub(h->graph_kernels);      // recorded, not executed
+    if (rc != B200_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "graph capture of the LM step failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  }
+  B200_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
+  g_launches.fetch_add(h->graph_kernels);
+  return B200_OK;
+}
+
+int b200_lm_step(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev, int64_t* out_tokens_dev,
+                 int support_out_of_sync, int* ready_host) {
+  B200_TRY(ensure_streaming(h, "lm_step"));
+  const auto& c = h->cfg;
+  const int B = h->batch, needed = c.n_q - c.dep_q;
+  if (!in_codes_dev || !out_tokens_dev) B200_FAIL(B200_ERR_SHAPE, "lm_step: null buffers");
+  if (n_in < needed || n_in > c.n_q)   // lm.py:683-686 assertion
+    B200_FAIL(B200_ERR_SHAPE, "lm_step: expected at least %d user codebooks, got %d", needed, n_in);
+  if (h->use_sampling && h->temp > 0.f && !noise_dev) B200_FAIL(B200_ERR_INVALID, "lm_step: sampling needs noise");
+  B200_CUDA(cudaMemcpyAsync(h->in_codes, in_codes_dev, (size_t)B * n_in * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (noise_dev)
+    B200_CUDA(cudaMemcpyAsync(h->noise, noise_dev, (size_t)B * noise_per_row(h) * 4, cudaMemcpyDeviceToDevice, h->stream));
+  B200_TRY(run_step(h, n_in));
+  B200_CUDA(cudaMemcpyAsync(out_tokens_dev, h->out_tokens, (size_t)B * (c.dep_q + 1) * 8, cudaMemcpyDeviceToDevice,
+                            h->stream));
+  h->offset_cpu += 1;
+  if (ready_host) *ready_host = (support_out_of_sync || h->offset_cpu > h->max_delay) ? 1 : 0;   // lm.py:774-776
+  return B200_OK;
+}
+
+int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const float* noise_host,
+                      int64_t* out_tokens_host, int support_out_of_sync, int* ready_host) {
+  B200_TRY(ensure_streaming(h, "lm_step_host"));
+  const auto& c = h->cfg;
+  const int B = h->batch, needed = c.n_q - c.dep_q;
+  if (!in_codes_host || !out_tokens_host) B200_FAIL(B200_ERR_SHAPE, "lm_step_host: null buffers");
+  if (n_in < needed || n_in > c.n_q) B200_FAIL(B200_ERR_SHAPE, "lm_step_host: expected at least %d user codebooks, got %d", needed, n_in);
+  memcpy(h->pin_in, in_codes_host, (size_t)B * n_in * 8);
+  B200_CUDA(cudaMemcpyAsync(h->in_codes, h->pin_in, (size_t)B * n_in * 8, cudaMemcpyHostToDevice, h->stream));
+  if (noise_host) {
+    memcpy(h->pin_noise, noise_host, (size_t)B * noise_per_row(h) * 4);
+    B200_CUDA(cudaMemcpyAsync(h->noise, h->pin_noise, (size_t)B * noise_per_row(h) * 4, cudaMemcpyHostToDevice, h->stream));
+  } else if (h->use_sampling && h->temp > 0.f) {
+    B200_FAIL(B200_ERR_INVALID, "lm_step_host: sampling needs noise");
+  }
+  B200_TRY(run_step(h, n_in));
+  B200_CUDA(cudaMemcpyAsync(h->pin_out, h->out_tokens, (size_t)B * (c.dep_q + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(out_tokens_host, h->pin_out, (size_t)B * (c.dep_q + 1) * 8);
+  h->offset_cpu += 1;
+  if (ready_host) *ready_host = (support_out_of_sync || h->offset_cpu > h->max_delay) ? 1 : 0;
+  return B200_OK;
+}
+
+int b200_lm_read_buffer(b200_lm* h, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes) {
+  B200_TRY(ensure_streaming(h, "lm_read_buffer"));
+  const auto& c = h->cfg;
+  const std::string n = name ? name : "";
+  const int B = h->batch;
+  const void* src = nullptr;
+  int64_t sz = 0;
+  if (n == "text_logits") { src = h->text_logits; sz = (int64_t)B * c.text_card * 2; }
+  else if (n == "transformer_out") { src = h->tout; sz = (int64_t)B * c.dim * 2; }
+  else if (n == "dep_logits") { src = h->dep_logits; sz = (int64_t)c.dep_q * B * c.card * 2; }
+  else if (n == "input_tokens") { src = h->input_tokens; sz = (int64_t)B * h->Kc * 8; }
+  else if (n == "text_token") { src = h->text_token; sz = (int64_t)B * 8; }
+  else if (n == "audio_tokens") { src = h->audio_tokens; sz = (int64_t)c.dep_q * B * 8; }
+  else B200_FAIL(B200_ERR_INVALID, "lm_read_buffer: unknown buffer '%s'", n.c_str());
+  if (nbytes) *nbytes = sz;
+  if (!dst_dev) return B200_OK;
+  if (capacity_bytes < sz) B200_FAIL(B200_ERR_SHAPE, "lm_read_buffer: destination too small");
+  B200_CUDA(cudaMemcpyAsync(dst_dev, src, (size_t)sz, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
+int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill) {
+  if (!h || h->batch <= 0) return 0;
+  const auto& c = h->cfg;
+  const int64_t B = h->batch;
+  if (kv_fill > c.context) kv_fill = c.context;
+  // weights streamed once per step (embedding tables are gathers, counted per row below)
+  int64_t w = 0;
+  w += (int64_t)c.num_layers * ((int64_t)3 * c.dim * c.dim + (int64_t)c.dim * c.dim + (int64_t)3 * c.ffn_hidden * c.dim) * 2;
+  w += (int64_t)c.text_card * c.dim * 2;
+  w += (int64_t)c.dep_q * c.depformer_dim * c.dim * 2;
+  w += (int64_t)c.dep_q * c.depformer_num_layers *
+       ((int64_t)4 * c.depformer_dim * c.depformer_dim + (int64_t)3 * c.depformer_ffn_hidden * c.depformer_dim) * 2;
+  w += (int64_t)c.dep_q * c.card * c.depformer_dim * 2;
+  // per session: KV ring read (valid slots only) + append, embedding rows, logits written + read by the sampler
+  int64_t per = (int64_t)c.num_layers * 2 * kv_fill * c.dim * 2 + (int64_t)c.num_layers * 2 * c.dim * 2;
+  per += (int64_t)(c.n_q + 1) * c.dim * 2 + (int64_t)c.dep_q * c.depformer_dim * 2;
+  per += (int64_t)2 * (c.text_card + (int64_t)c.dep_q * c.card) * 2;
+  return w + per * B;
+}
+
+}  // extern "C"

@@ -1,0 +1,549 @@
+// bf16 kernels of the Moshi LM decode step (one 12.5 Hz frame for B concurrent sessions).
+//
+// Cast points follow the reference exactly: every nn.Linear output is a bf16
+// tensor, RMSNorm / RoPE / softmax / SiLU are evaluated in fp32 on bf16 inputs and rounded once,
+// residual adds and the 17-way embedding sum are bf16 adds.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200 {
+namespace lm {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// token ring (LMGen._step bookkeeping, lm.py:691-702 and :759-783)
+// ---------------------------------------------------------------------------------------------
+struct TokenRing {
+  long long* cache;        // [B][Kc][CT]
+  long long* offsets;      // [B]
+  const uint8_t* exec_mask;
+  const int* delays;       // [Kc]
+  int Kc, CT, dep_q, n_q, card, text_card, max_delay;
+};
+
+// One thread per (b, k): write the user's codes, then build the model input row [B][Kc].
+static __global__ void lm_prepare_kernel(const TokenRing r, const long long* __restrict__ in_codes, int n_in,
+                                  long long* __restrict__ input_tokens, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * r.Kc) return;
+  const int b = i / r.Kc, k = i % r.Kc;
+  const long long off = r.offsets[b];
+  const bool exec = r.exec_mask[b] != 0;
+  long long* row = r.cache + ((long long)b * r.Kc + k) * r.CT;
+  if (k > r.dep_q && exec) {                                    // lm.py:691-696
+    const int pos = (int)((off + r.delays[k]) % r.CT);
+    row[pos] = in_codes[(long long)b * n_in + (k - r.dep_q - 1)];
+  }
+  const bool is_init = off <= r.delays[k] || !exec;             // lm.py:698-699
+  const long long initial = k == 0 ? r.text_card : r.card;      // lm.py:297-311
+  input_tokens[i] = is_init ? initial : row[off % r.CT];
+}
+
+// offsets += exec; store sampled tokens; gather the delay-aligned output (lm.py:759-783)
+static __global__ void lm_finish_kernel(const TokenRing r, const long long* __restrict__ text_token,
+                                 const long long* __restrict__ audio_tokens /*[dep_q][B]*/,
+                                 long long* __restrict__ out /*[B][dep_q+1]*/, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const bool exec = r.exec_mask[b] != 0;
+  long long off = r.offsets[b];
+  if (exec) off += 1;
+  r.offsets[b] = off;
+  const int pos = (int)(off % r.CT);
+  if (exec) {
+    r.cache[((long long)b * r.Kc + 0) * r.CT + pos] = text_token[b];
+    for (int k = 0; k < r.dep_q; ++k)
+      r.cache[((long long)b * r.Kc + 1 + k) * r.CT + pos] = audio_tokens[(long long)k * B + b];
+  }
+  const bool not_ready = off <= r.max_delay || !exec;
+  for (int k = 0; k <= r.dep_q; ++k) {
+    long long idx = (off - r.max_delay + r.delays[k]) % r.CT;
+    if (idx < 0) idx += r.CT;                                    // python modulo
+    const long long v = r.cache[((long long)b * r.Kc + k) * r.CT + idx];
+    out[(long long)b * (r.dep_q + 1) + k] = not_ready ? -2 : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// embeddings (lm.py:390-397; ScaledEmbedding: token -1 -> zero row, lm_utils.py:103-121)
+// ---------------------------------------------------------------------------------------------
+struct EmbedTables {
+  const bf16* audio[32];   // [card+1][dim]
+  const bf16* text;        // [text_card+1][dim]
+  int n_q;
+};
+static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long* __restrict__ tokens /*[B][n_q+1]*/,
+                                    bf16* __restrict__ x /*[B][dim]*/, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (b, pair)
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, c = (i % half) * 2;
+  const long long* tok = tokens + (long long)b * (t.n_q + 1);
+  float s0 = 0.f, s1 = 0.f;
+  for (int k = 0; k < t.n_q; ++k) {
+    const long long id = tok[k + 1];
+    float e0 = 0.f, e1 = 0.f;
+    if (id >= 0) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(t.audio[k] + id * dim + c);
+      e0 = __low2float(v); e1 = __high2float(v);
+    }
+    if (k == 0) { s0 = e0; s1 = e1; }
+    else { s0 = rbf(s0 + e0); s1 = rbf(s1 + e1); }       // bf16 add per table
+  }
+  {
+    const long long id = tok[0];
+    float e0 = 0.f, e1 = 0.f;
+    if (id >= 0) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(t.text + id * dim + c);
+      e0 = __low2float(v); e1 = __high2float(v);
+    }
+    if (t.n_q == 0) { s0 = e0; s1 = e1; }
+    else { s0 = rbf(s0 + e0); s1 = rbf(s1 + e1); }
+  }
+  *reinterpret_cast<__nv_bfloat162*>(x + (long long)b * dim + c) = __floats2bfloat162_rn(s0, s1);
+}
+
+// depformer input: x = depformer_in[k](transformer_out) + emb(prev)   (lm.py:475-486)
+static __global__ void dep_input_kernel(const bf16* __restrict__ din /*[B][ld]*/, long long ld, int col0,
+                                 const bf16* __restrict__ table /*[V][dd]*/, const long long* __restrict__ prev /*[B]*/,
+                                 bf16* __restrict__ x /*[B][dd]*/, int B, int dd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dd) return;
+  const int b = i / dd, c = i % dd;
+  const long long id = prev[b];
+  const float e = id >= 0 ? bf2f(table[id * dd + c]) : 0.f;
+  x[i] = f2bf(bf2f(din[(long long)b * ld + col0 + c]) + e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm with fp32 math, eps 1e-8 (transformer.py:45-58): y = bf16(x * (alpha * rsqrt(eps + mean(x^2))))
+// Optionally fuses the preceding residual add: x <- bf16(x + upd) first (transformer.py:769,777).
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ alpha,
+                                                      bf16* __restrict__ y, int dim, float eps) {
+  const int row = blockIdx.x;
+  const bf16* xr = x + (long long)row * dim;
+  float ss = 0.f;
+  for (int c = threadIdx.x * 2; c < dim; c += blockDim.x * 2) {
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + c));
+    ss += v.x * v.x + v.y * v.y;
+  }
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float r = rsqrtf(eps + red[0] / (float)dim);
+  for (int c = threadIdx.x * 2; c < dim; c += blockDim.x * 2) {
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + c));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(alpha + c));
+    *reinterpret_cast<__nv_bfloat162*>(y + (long long)row * dim + c) =
+        __floats2bfloat162_rn(v.x * (a.x * r), v.y * (a.y * r));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT weight-streaming GEMM for skinny M:  y[m][n] = sum_k x[m][k] * w[n][k]
+// One warp per output feature n (two weight rows when gating); lanes stride K in 16-byte chunks.
+// ---------------------------------------------------------------------------------------------
+enum { LIN_STORE = 0, LIN_RESADD = 1, LIN_GATE = 2 };
+constexpr int SIMT_MB = 8;
+
+template <int EPI>
+static __global__ void __launch_bounds__(256) linear_simt_kernel(const bf16* __restrict__ x, long long ldx,
+                                                          const bf16* __restrict__ w, bf16* __restrict__ y, long long ldy,
+                                                          const bf16* __restrict__ res, long long ldr, int M, int N,
+                                                          int K, int gate_rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const bf16* w0 = w + (long long)warp * K;
+  const bf16* w1 = EPI == LIN_GATE ? w + (long long)(warp + gate_rows) * K : nullptr;
+  for (int m0 = 0; m0 < M; m0 += SIMT_MB) {
+    float acc0[SIMT_MB], acc1[SIMT_MB];
+#pragma unroll
+    for (int i = 0; i < SIMT_MB; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+    for (int k = lane * 8; k < K; k += 256) {
+      float wf0[8], wf1[8];
+      unpack8(*reinterpret_cast<const uint4*>(w0 + k), wf0);
+      if (EPI == LIN_GATE) unpack8(*reinterpret_cast<const uint4*>(w1 + k), wf1);
+#pragma unroll
+      for (int i = 0; i < SIMT_MB; ++i) {
+        if (m0 + i < M) {
+          float xf[8];
+          unpack8(*reinterpret_cast<const uint4*>(x + (long long)(m0 + i) * ldx + k), xf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc0[i] = fmaf(xf[j], wf0[j], acc0[i]);
+            if (EPI == LIN_GATE) acc1[i] = fmaf(xf[j], wf1[j], acc1[i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < SIMT_MB; ++i) {
+      float a0 = warp_sum(acc0[i]);
+      float a1 = EPI == LIN_GATE ? warp_sum(acc1[i]) : 0.f;
+      if (lane == 0 && m0 + i < M) {
+        const int m = m0 + i;
+        float v;
+        if (EPI == LIN_STORE) v = a0;
+        else if (EPI == LIN_RESADD) v = bf2f(res[(long long)m * ldr + warp]) + rbf(a0);
+        else {
+          const float g = rbf(a0), u = rbf(a1);
+          v = rbf(g / (1.f + expf(-g))) * u;          // bf16(silu(gate)) * value   (gating.py:18-20)
+        }
+        y[(long long)m * ldy + warp] = f2bf(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE (interleaved pairs, fp32) + ring KV append for T = 1 (transformer.py:557-569, 247-253)
+//   qkv [B][3*C] bf16 (rows q | k | v, each (h d)) -> q_rot [B][C]; K, V ring [B][H][cap][D]
+// use_rope = 0 for the depformer (depformer_pos_emb = "none").  pos / slot come from per-row
+// `offset` (temporal) or from the scalar `step` (depformer: all rows advance together).
+// ---------------------------------------------------------------------------------------------
+static __global__ void rope_append_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ q_out,
+                                        bf16* __restrict__ kc, bf16* __restrict__ vc,
+                                        const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
+                                        int step, int B, int H, int D, int cap, int use_rope,
+                                        float neg_log_period_2_over_d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, h, pair)
+  const int half = D / 2;
+  if (i >= (long long)B * H * half) return;
+  const int pr = i % half;
+  const int h = (i / half) % H;
+  const int b = i / ((long long)half * H);
+  const int C = H * D;
+  const long long pos = offset ? offset[b] : step;
+  const bf16* base = qkv + (long long)b * 3 * C + h * D + 2 * pr;
+  float qr = bf2f(base[0]), qi = bf2f(base[1]);
+  float kr = bf2f(base[C]), ki = bf2f(base[C + 1]);
+  if (use_rope) {
+    const float freq = expf((float)pr * neg_log_period_2_over_d);
+    float sn, cs;
+    sincosf(freq * (float)pos, &sn, &cs);
+    const float a = qr * cs - qi * sn, bq = qr * sn + qi * cs;
+    const float c2 = kr * cs - ki * sn, d2 = kr * sn + ki * cs;
+    qr = a; qi = bq; kr = c2; ki = d2;
+  }
+  *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * C + h * D + 2 * pr) = __floats2bfloat162_rn(qr, qi);
+  if (exec_mask && !exec_mask[b]) return;
+  const int slot = (int)(pos % cap);
+  const long long o = (((long long)b * H + h) * cap + slot) * D + 2 * pr;
+  *reinterpret_cast<__nv_bfloat162*>(kc + o) = __floats2bfloat162_rn(kr, ki);
+  *reinterpret_cast<__nv_bfloat162*>(vc + o) = *reinterpret_cast<const __nv_bfloat162*>(base + 2 * C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode attention over the ring (T = 1, D = 128): split-KV with online softmax.
+//   grid = (B*H, nsplit); 128 threads; each half-warp owns one key per iteration (16 lanes x 16 B).
+//   Only the slots that hold valid keys are read (n_valid = min(offset + exec, cap)); the
+//   reference reads the whole ring under a mask (transformer.py:574-585) — same result.
+// ---------------------------------------------------------------------------------------------
+constexpr int ATT_D = 128;
+constexpr int ATT_THREADS = 128;
+
+static __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
+                                                                  const bf16* __restrict__ vc, float* __restrict__ part,
+                                                                  const long long* __restrict__ offset,
+                                                                  const uint8_t* __restrict__ exec_mask, int H, int cap,
+                                                                  int nsplit) {
+  const int bh = blockIdx.x, split = blockIdx.y;
+  const int b = bh / H;
+  const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15;
+  const int hw = tid >> 4;                          // half-warp id 0..7
+  long long n_valid = offset[b] + (exec_mask[b] ? 1 : 0);
+  if (n_valid > cap) n_valid = cap;
+  const int per = (int)((n_valid + nsplit - 1) / nsplit);
+  const int s0 = split * per;
+  const int s1 = (int)min((long long)(s0 + per), n_valid);
+
+  float qf[8];
+  unpack8(*reinterpret_cast<const uint4*>(q + (long long)bh * ATT_D + l16 * 8), qf);
+  const float scale = 0.08838834764831845f;         // 1/sqrt(128)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qf[i] *= scale;
+
+  const bf16* kb = kc + (long long)bh * cap * ATT_D + l16 * 8;
+  const bf16* vb = vc + (long long)bh * cap * ATT_D + l16 * 8;
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  constexpr int U = 4;                              // keys in flight per half-warp
+  for (int base = s0; base < s1; base += 8 * U) {   // warp-uniform trip count (shuffles inside)
+    const int s = base + hw * U;
+    uint4 kr[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ss = s + u < s1 ? s + u : s1 - 1;
+      kr[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * ATT_D);
+      vr[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * ATT_D);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float kf[8];
+      unpack8(kr[u], kf);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      if (s + u < s1) {
+        const float mn = fmaxf(m, d);
+        const float corr = __expf(m - mn), p = __expf(d - mn);
+        float vf[8];
+        unpack8(vr[u], vf);
+        l = l * corr + p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i] * corr);
+        m = mn;
+      }
+    }
+  }
+  // merge the 8 half-warps of the CTA
+  __shared__ float sm_m[8], sm_l[8], sm_acc[8][ATT_D];
+  if (l16 == 0) { sm_m[hw] = m; sm_l[hw] = l; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm_acc[hw][l16 * 8 + i] = acc[i];
+  __syncthreads();
+  if (tid < ATT_D) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - M);
+      L += sm_l[w] * c;
+      A += sm_acc[w][tid] * c;
+    }
+    float* o = part + ((long long)bh * nsplit + split) * (ATT_D + 2);
+    o[tid] = A;
+    if (tid == 0) { o[ATT_D] = M; o[ATT_D + 1] = L; }
+  }
+}
+
+static __global__ void __launch_bounds__(ATT_D) attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out,
+                                                             int nsplit) {
+  const int bh = blockIdx.x, d = threadIdx.x;
+  const float* p = part + (long long)bh * nsplit * (ATT_D + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, p[s * (ATT_D + 2) + ATT_D]);
+  float L = 0.f, A = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = p[s * (ATT_D + 2) + ATT_D];
+    const float c = ms == -INFINITY ? 0.f : __expf(ms - M);
+    L += p[s * (ATT_D + 2) + ATT_D + 1] * c;
+    A += p[s * (ATT_D + 2) + d] * c;
+  }
+  out[(long long)bh * ATT_D + d] = f2bf(L > 0.f ? A / L : 0.f);
+}
+
+// Depformer attention: <= 8 keys, one warp per (b, h), D = 64 (2 dims per lane).
+static __global__ void dep_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                                bf16* __restrict__ out, int B, int H, int D, int cap, int n_keys) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * H) return;
+  const float scale = rsqrtf((float)D);
+  float sc[8];
+  float mx = -INFINITY;
+  for (int j = 0; j < n_keys; ++j) {
+    float d = 0.f;
+    for (int c = lane * 2; c < D; c += 64) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + (long long)warp * D + c));
+      const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kc + ((long long)warp * cap + j) * D + c));
+      d += a.x * kk.x + a.y * kk.y;
+    }
+    d = warp_sum(d) * scale;
+    sc[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < n_keys; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.f / sum;
+  for (int c = lane * 2; c < D; c += 64) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < n_keys; ++j) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vc + ((long long)warp * cap + j) * D + c));
+      a0 = fmaf(sc[j] * inv, v.x, a0);
+      a1 = fmaf(sc[j] * inv, v.y, a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + (long long)warp * D + c) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+
+// _LMGenState.reset / _MHAState.reset / RingKVCache.reset / State.reset for the rows in `mask` (null = all)
+static __global__ void lm_reset_kernel(long long* offsets, long long* pos, uint8_t* exec_mask, const uint8_t* mask, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (mask != nullptr && !mask[b]) return;
+  offsets[b] = 0;
+  pos[b] = 0;
+  exec_mask[b] = 1;
+}
+
+static __global__ void advance_pos_kernel(long long* pos, const uint8_t* exec_mask, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && exec_mask[b]) pos[b] += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_token (sampling.py:86-106): softmax(logits/temp) -> top-k -> argmax(p / Exp(1) noise).
+// Candidates are ranked by (logit desc, index asc); the noise is indexed by rank like the
+// reference indexes it by the position in torch.topk's sorted output.
+// ---------------------------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_MAX_K = 1024;
+
+__device__ __forceinline__ unsigned sample_key(const bf16* logits, int i) {
+  const unsigned short raw = __bfloat16_as_ushort(logits[i]);
+  const unsigned short mono = (raw & 0x8000u) ? (unsigned short)~raw : (unsigned short)(raw | 0x8000u);
+  return ((unsigned)mono << 16) | (unsigned)(0xFFFFu - (unsigned)i);
+}
+
+static __device__ float block_reduce(float v, bool is_max, float* red) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = is_max ? -INFINITY : 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = is_max ? fmaxf(t, red[w]) : t + red[w];
+  return t;
+}
+
+static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf16* __restrict__ logits_all, long long ld,
+                                                                const float* __restrict__ noise, long long noise_ld,
+                                                                long long* __restrict__ out, int card, int use_sampling,
+                                                                float temp, int top_k) {
+  __shared__ float red[SAMPLE_THREADS / 32];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_remaining, s_count;
+  __shared__ unsigned sel[SAMPLE_MAX_K];
+  __shared__ float s_best[SAMPLE_THREADS / 32];
+  __shared__ int s_brank[SAMPLE_THREADS / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const bf16* logits = logits_all + (long long)row * ld;
+
+  if (!(use_sampling && temp > 0.f)) {        // greedy: argmax, first maximum (sampling.py:102-103)
+    unsigned best = 0;
+    for (int i = tid; i < card; i += SAMPLE_THREADS) best = max(best, sample_key(logits, i));
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) hist[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned bb = 0;
+      for (int w = 0; w < SAMPLE_THREADS / 32; ++w) bb = max(bb, hist[w]);
+      out[row] = 0xFFFFu - (bb & 0xFFFFu);
+    }
+    return;
+  }
+  const int k = min(min(top_k, card), SAMPLE_MAX_K);
+  // softmax statistics in fp32 on logits / temp
+  float mx = -INFINITY;
+  for (int i = tid; i < card; i += SAMPLE_THREADS) mx = fmaxf(mx, bf2f(logits[i]) / temp);
+  mx = block_reduce(mx, true, red);
+  float sum = 0.f;
+  for (int i = tid; i < card; i += SAMPLE_THREADS) sum += expf(bf2f(logits[i]) / temp - mx);
+  sum = block_reduce(sum, false, red);
+
+  // radix select of the k-th largest 32-bit key (keys are unique)
+  if (tid == 0) { s_prefix = 0; s_remaining = (unsigned)k; }
+  __syncthreads();
+  for (int pass = 3; pass >= 0; --pass) {
+    hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned mask = pass == 3 ? 0u : (0xFFFFFFFFu << ((pass + 1) * 8));
+    for (int i = tid; i < card; i += SAMPLE_THREADS) {
+      const unsigned key = sample_key(logits, i);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> (pass * 8)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned rem = s_remaining, cum = 0;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (cum + hist[bin] >= rem) break;
+        cum += hist[bin];
+      }
+      s_remaining = rem - cum;
+      s_prefix = prefix | ((unsigned)bin << (pass * 8));
+    }
+    __syncthreads();
+  }
+  const unsigned thr = s_prefix;               // exactly k keys are >= thr
+  if (tid == 0) s_count = 0;
+  // pad the sort buffer
+  int p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  for (int i = tid; i < p2; i += SAMPLE_THREADS) sel[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < card; i += SAMPLE_THREADS) {
+    const unsigned key = sample_key(logits, i);
+    if (key >= thr) {
+      const unsigned slot = atomicAdd(&s_count, 1u);
+      if (slot < (unsigned)p2) sel[slot] = key;
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < p2 / 2; i += SAMPLE_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned a = sel[lo], b = sel[hi];
+        if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // argmax over ranks of p / q (first maximum wins, like torch.argmax)
+  float best = -INFINITY;
+  int brank = 0x7fffffff;
+  for (int j = tid; j < k; j += SAMPLE_THREADS) {
+    const int idx = 0xFFFF - (int)(sel[j] & 0xFFFFu);
+    const float p = expf(bf2f(logits[idx]) / temp - mx) / sum;
+    const float s = p / noise[(long long)row * noise_ld + j];
+    if (s > best || (s == best && j < brank)) { best = s; brank = j; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, brank, o);
+    if (ob > best || (ob == best && oj < brank)) { best = ob; brank = oj; }
+  }
+  if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_brank[tid >> 5] = brank; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+      if (s_best[w] > best || (s_best[w] == best && s_brank[w] < brank)) { best = s_best[w]; brank = s_brank[w]; }
+    if (brank == 0x7fffffff) brank = 0;
+    out[row] = 0xFFFF - (int)(sel[brank] & 0xFFFFu);
+  }
+}
+
+}  // namespace lm
+}  // namespace b200

@@ -1,0 +1,860 @@
+// Mimi handle: weight ingestion (reference state-dict names), streaming state, encode / decode.
+// Reference orchestration: moshi/moshi/models/compression.py:338-433.
+#include "mimi_kernels.cuh"
+
+using namespace b200;
+using namespace b200::mimi;
+
+namespace {
+
+struct ConvLayer {
+  int kind = 0;              // 0 = StreamingConv1d, 1 = StreamingConvTranspose1d
+  std::string key;           // state-dict prefix of the nn.Conv1d / nn.ConvTranspose1d
+  int cin = 0, cout = 0, k = 0, stride = 1, dil = 1;
+  bool elu_in = false, replicate = false, has_bias = true;
+  int res_from = -1;         // buffer index added in the epilogue (residual block second conv)
+  int in_buf = -1, out_buf = -1;
+  int t_in = 0, t_out = 0;   // samples per frame at this layer
+  float* w = nullptr;        // packed
+  float* bias = nullptr;
+  // streaming state
+  int P = 0;                 // conv: carried samples; convtr: K - S
+  float* state = nullptr;    // conv: previous [B][Cin][P]; convtr: partial [B][Cout][S]
+  float* scratch = nullptr;  // convtr candidate partial
+  uint8_t* first = nullptr;  // replicate flag [B]
+  std::string tap;           // debug name of the output buffer
+};
+
+struct Buf {
+  float* p = nullptr;
+  int c = 0, t = 0;
+  bool token_major = false;  // [B][T][C] instead of [B][C][T]
+  long long sb(int) const { return (long long)c * t; }
+  long long sc() const { return token_major ? 1 : t; }
+  long long st() const { return token_major ? c : 1; }
+};
+
+struct TrLayer {
+  const float *in_w, *out_w, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2;
+  float *kc = nullptr, *vc = nullptr;
+};
+
+struct Transformer {
+  std::vector<TrLayer> layers;
+  long long* offset = nullptr;   // [B] tokens seen (== RingKVCache.end_offset == _MHAState.offset)
+};
+
+}  // namespace
+
+struct b200_mimi {
+  b200_mimi_config cfg;
+  TensorStore store;
+  Arena weights, state;
+  bool finalized = false;
+  int batch = 0;
+  int num_codebooks = 8;
+  cudaStream_t stream = nullptr;
+  int frame_size = 0, hop = 0, rs = 0;       // rs = resample stride (2)
+
+  std::vector<ConvLayer> enc, dec;
+  ConvLayer down;
+  std::vector<Buf> enc_bufs, dec_bufs;
+  // up-sampling (depth-wise convtr)
+  float *up_w = nullptr, *up_partial = nullptr, *up_scratch = nullptr;
+  Transformer enc_tr, dec_tr;
+  // quantizer
+  float *wT[2] = {nullptr, nullptr}, *woT[2] = {nullptr, nullptr};
+  float *cb[2] = {nullptr, nullptr}, *cbT[2] = {nullptr, nullptr}, *cnorm[2] = {nullptr, nullptr};
+  int stored_levels[2] = {0, 0};
+  // per-batch buffers
+  float* in_frame = nullptr;                   // [B][1920]
+  float *tok_in_enc = nullptr, *tok_enc = nullptr, *latent = nullptr;     // [B][T][C], [B][T][C], [B][C]
+  float *latent_q = nullptr, *tok_in_dec = nullptr, *tok_dec = nullptr;
+  float *tr_xn = nullptr, *tr_qkv = nullptr, *tr_q = nullptr, *tr_ao = nullptr, *tr_h = nullptr;
+  uint8_t* exec_mask = nullptr;
+  uint8_t* first_flags = nullptr; int n_first = 0;
+  ConvCommit *enc_commits = nullptr, *dec_commits = nullptr;
+  int n_enc_commits = 0, n_dec_commits = 0, max_enc_rows = 0, max_dec_rows = 0;
+  ConvTrCommit* dec_tr_commits = nullptr; int n_dec_tr_commits = 0; long long max_tr_rows = 0;
+  long long* scratch_codes = nullptr;          // [B][K][1] for the host variants
+  float *pin_pcm = nullptr; long long* pin_codes = nullptr; size_t pin_pcm_n = 0, pin_codes_n = 0;
+  float* dev_pcm = nullptr; long long* dev_codes = nullptr; size_t dev_pcm_n = 0, dev_codes_n = 0;
+  std::map<std::string, std::pair<const float*, int64_t>> taps;
+  int64_t weight_bytes = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// structure (seanet.py:170-236, 323-388; resample.py; loaders.py:38-88)
+// ---------------------------------------------------------------------------------------------
+void plan_seanet(b200_mimi* h) {
+  const auto& c = h->cfg;
+  h->enc.clear();
+  h->dec.clear();
+  auto conv = [](const std::string& key, int cin, int cout, int k, int stride, int dil, bool elu) {
+    ConvLayer l;
+    l.kind = 0; l.key = key; l.cin = cin; l.cout = cout; l.k = k; l.stride = stride; l.dil = dil; l.elu_in = elu;
+    return l;
+  };
+  int idx = 0, mult = 1;
+  {
+    auto l = conv("encoder.model.0.conv.conv", c.channels, mult * c.n_filters, c.kernel_size, 1, 1, false);
+    l.tap = "enc.0";
+    h->enc.push_back(l);
+  }
+  idx = 1;
+  for (int ri = c.n_ratios - 1; ri >= 0; --ri) {
+    const int ratio = c.ratios[ri];
+    const int ch = mult * c.n_filters;
+    for (int j = 0; j < c.n_residual_layers; ++j) {
+      int dil = 1;
+      for (int q = 0; q < j; ++q) dil *= c.dilation_base;
+      const std::string base = "encoder.model." + std::to_string(idx);
+      auto a = conv(base + ".block.1.conv.conv", ch, ch / c.compress, c.residual_kernel_size, 1, dil, true);
+      auto b = conv(base + ".block.3.conv.conv", ch / c.compress, ch, 1, 1, 1, true);
+      b.res_from = -2;  // resolved below: input of the block
+      b.tap = "enc." + std::to_string(idx);
+      h->enc.push_back(a);
+      h->enc.push_back(b);
+      ++idx;
+    }
+    ++idx;  // ELU
+    auto l = conv("encoder.model." + std::to_string(idx) + ".conv.conv", ch, ch * 2, 2 * ratio, ratio, 1, true);
+    l.tap = "enc." + std::to_string(idx);
+    h->enc.push_back(l);
+    ++idx;
+    mult *= 2;
+  }
+  ++idx;  // ELU
+  {
+    auto l = conv("encoder.model." + std::to_string(idx) + ".conv.conv", mult * c.n_filters, c.dimension,
+                  c.last_kernel_size, 1, 1, true);
+    l.tap = "enc." + std::to_string(idx);
+    h->enc.push_back(l);
+  }
+
+  idx = 0;
+  mult = 1 << c.n_ratios;
+  {
+    auto l = conv("decoder.model.0.conv.conv", c.dimension, mult * c.n_filters, c.kernel_size, 1, 1, false);
+    l.tap = "dec.0";
+    h->dec.push_back(l);
+  }
+  idx = 1;
+  for (int ri = 0; ri < c.n_ratios; ++ri) {
+    const int ratio = c.ratios[ri];
+    const int ch = mult * c.n_filters;
+    ++idx;  // ELU
+    ConvLayer t;
+    t.kind = 1; t.key = "decoder.model." + std::to_string(idx) + ".convtr.convtr";
+    t.cin = ch; t.cout = ch / 2; t.k = 2 * ratio; t.stride = ratio; t.elu_in = true;
+    t.tap = "dec." + std::to_string(idx);
+    h->dec.push_back(t);
+    ++idx;
+    for (int j = 0; j < c.n_residual_layers; ++j) {
+      int dil = 1;
+      for (int q = 0; q < j; ++q) dil *= c.dilation_base;
+      const std::string base = "decoder.model." + std::to_string(idx);
+      auto a = conv(base + ".block.1.conv.conv", ch / 2, ch / 2 / c.compress, c.residual_kernel_size, 1, dil, true);
+      auto b = conv(base + ".block.3.conv.conv", ch / 2 / c.compress, ch / 2, 1, 1, 1, true);
+      b.res_from = -2;
+      b.tap = "dec." + std::to_string(idx);
+      h->dec.push_back(a);
+      h->dec.push_back(b);
+      ++idx;
+    }
+    mult /= 2;
+  }
+  ++idx;  // ELU
+  {
+    auto l = conv("decoder.model." + std::to_string(idx) + ".conv.conv", c.n_filters, c.channels,
+                  c.last_kernel_size, 1, 1, true);
+    l.tap = "dec." + std::to_string(idx);
+    h->dec.push_back(l);
+  }
+  h->down = conv("downsample.conv.conv.conv", c.dimension, c.dimension, 2 * h->rs, h->rs, 1, false);
+  h->down.replicate = true;
+  h->down.has_bias = false;
+}
+
+int get_f32(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, const float** out) {
+  const Tensor* t = h->store.find(name);
+  if (!t) B200_FAIL(B200_ERR_MISSING, "mimi finalize: tensor '%s' was not loaded", name.c_str());
+  if (t->dtype != B200_F32) B200_FAIL(B200_ERR_SHAPE, "mimi tensor '%s' must be float32", name.c_str());
+  if (!shape.empty() && t->shape != shape) {
+    std::string got;
+    for (auto s : t->shape) got += std::to_string(s) + ",";
+    B200_FAIL(B200_ERR_SHAPE, "mimi tensor '%s' has shape [%s]", name.c_str(), got.c_str());
+  }
+  *out = static_cast<const float*>(t->data);
+  return B200_OK;
+}
+
+int pack_conv(b200_mimi* h, ConvLayer& l) {
+  const float* w = nullptr;
+  if (l.kind == 0) {
+    B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
+    const long long n = (long long)l.cout * l.cin * l.k;
+    B200_TRY(h->weights.alloc_t(&l.w, n, false));
+    B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cout, l.cin, l.k);
+    h->weight_bytes += n * 4;
+  } else {
+    if (l.k != 2 * l.stride) B200_FAIL(B200_ERR_INVALID, "convtr %s: kernel must be 2*stride", l.key.c_str());
+    B200_TRY(get_f32(h, l.key + ".weight", {l.cin, l.cout, l.k}, &w));
+    const long long n = (long long)l.cin * l.cout * l.k;
+    B200_TRY(h->weights.alloc_t(&l.w, n, false));
+    B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cin, l.cout, l.stride);
+    h->weight_bytes += n * 4;
+  }
+  if (l.has_bias) {
+    const float* b = nullptr;
+    B200_TRY(get_f32(h, l.key + ".bias", {l.cout}, &b));
+    B200_TRY(h->weights.alloc_t(&l.bias, l.cout, false));
+    B200_CUDA(cudaMemcpy(l.bias, b, l.cout * 4, cudaMemcpyDeviceToDevice));
+    h->weight_bytes += l.cout * 4;
+  }
+  h->store.release(l.key + ".weight");
+  h->store.release(l.key + ".bias");
+  return check_launch("pack_conv");
+}
+
+int keep(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, const float** out) {
+  const float* src = nullptr;
+  B200_TRY(get_f32(h, name, shape, &src));
+  long long n = 1;
+  for (auto s : shape) n *= s;
+  float* dst = nullptr;
+  B200_TRY(h->weights.alloc_t(&dst, n, false));
+  B200_CUDA(cudaMemcpy(dst, src, n * 4, cudaMemcpyDeviceToDevice));
+  h->store.release(name);
+  h->weight_bytes += n * 4;
+  *out = dst;
+  return B200_OK;
+}
+
+int pack_transformer(b200_mimi* h, const std::string& prefix, Transformer& tr) {
+  const auto& c = h->cfg;
+  const int d = c.tr_d_model, ff = c.tr_dim_feedforward;
+  tr.layers.resize(c.tr_num_layers);
+  for (int li = 0; li < c.tr_num_layers; ++li) {
+    const std::string p = prefix + ".transformer.layers." + std::to_string(li);
+    TrLayer& L = tr.layers[li];
+    B200_TRY(keep(h, p + ".self_attn.in_projs.0.weight", {3 * d, d}, &L.in_w));
+    B200_TRY(keep(h, p + ".self_attn.out_projs.0.weight", {d, d}, &L.out_w));
+    B200_TRY(keep(h, p + ".norm1.weight", {d}, &L.n1w));
+    B200_TRY(keep(h, p + ".norm1.bias", {d}, &L.n1b));
+    B200_TRY(keep(h, p + ".norm2.weight", {d}, &L.n2w));
+    B200_TRY(keep(h, p + ".norm2.bias", {d}, &L.n2b));
+    B200_TRY(keep(h, p + ".linear1.weight", {ff, d}, &L.l1));
+    B200_TRY(keep(h, p + ".linear2.weight", {d, ff}, &L.l2));
+    B200_TRY(keep(h, p + ".layer_scale_1.scale", {d}, &L.ls1));
+    B200_TRY(keep(h, p + ".layer_scale_2.scale", {d}, &L.ls2));
+  }
+  return B200_OK;
+}
+
+int pack_quantizer(b200_mimi* h) {
+  const auto& c = h->cfg;
+  const char* names[2] = {"rvq_first", "rvq_rest"};
+  h->stored_levels[0] = c.q_n_semantic;
+  h->stored_levels[1] = c.q_n_q - c.q_n_semantic;
+  for (int w = 0; w < 2; ++w) {
+    const std::string p = std::string("quantizer.") + names[w];
+    const float* src = nullptr;
+    B200_TRY(get_f32(h, p + ".input_proj.weight", {c.q_dimension, c.dimension, 1}, &src));
+    B200_TRY(h->weights.alloc_t(&h->wT[w], (size_t)c.q_dimension * c.dimension, false));
+    B200_LAUNCH(transpose_kernel, (unsigned)ceil_div64((long long)c.q_dimension * c.dimension, 256), 256, 0, 0, src,
+                h->wT[w], c.q_dimension, c.dimension);
+    B200_TRY(get_f32(h, p + ".output_proj.weight", {c.dimension, c.q_dimension, 1}, &src));
+    B200_TRY(h->weights.alloc_t(&h->woT[w], (size_t)c.q_dimension * c.dimension, false));
+    B200_LAUNCH(transpose_kernel, (unsigned)ceil_div64((long long)c.q_dimension * c.dimension, 256), 256, 0, 0, src,
+                h->woT[w], c.dimension, c.q_dimension);
+    const int L = h->stored_levels[w];
+    const size_t per = (size_t)c.q_bins * c.q_dimension;
+    B200_TRY(h->weights.alloc_t(&h->cb[w], per * L, false));
+    B200_TRY(h->weights.alloc_t(&h->cbT[w], per * L, false));
+    B200_TRY(h->weights.alloc_t(&h->cnorm[w], (size_t)c.q_bins * L, false));
+    for (int l = 0; l < L; ++l) {
+      const std::string cbp = p + ".vq.layers." + std::to_string(l) + "._codebook";
+      const float *es = nullptr, *us = nullptr;
+      B200_TRY(get_f32(h, cbp + ".embedding_sum", {c.q_bins, c.q_dimension}, &es));
+      B200_TRY(get_f32(h, cbp + ".cluster_usage", {c.q_bins}, &us));
+      B200_LAUNCH(build_codebook_kernel, c.q_bins, 128, 0, 0, es, us, h->cb[w] + per * l, h->cbT[w] + per * l,
+                  h->cnorm[w] + (size_t)c.q_bins * l, c.q_bins, c.q_dimension);
+    }
+    B200_CUDA(cudaDeviceSynchronize());
+    for (int l = 0; l < L; ++l) {
+      const std::string cbp = p + ".vq.layers." + std::to_string(l) + "._codebook";
+      h->store.release(cbp + ".embedding_sum");
+      h->store.release(cbp + ".cluster_usage");
+      h->store.release(cbp + "._initialized");
+    }
+    h->store.release(p + ".input_proj.weight");
+    h->store.release(p + ".output_proj.weight");
+  }
+  return check_launch("pack_quantizer");
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, long long xc, long long xt,
+                float* y, long long yb, long long yc, long long yt, const float* res, long long rb, long long rc,
+                long long rt) {
+  const int B = h->batch;
+  if (l.kind == 0) {
+    ConvP p;
+    p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.Tin = l.t_in;
+    p.st = l.state; p.P = l.P; p.first = l.first;
+    p.w = l.w; p.bias = l.bias;
+    p.y = y; p.yb = yb; p.yc = yc; p.yt = yt;
+    p.res = res; p.rb = rb; p.rc = rc; p.rt = rt;
+    p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.K = l.k; p.stride = l.stride; p.dil = l.dil; p.Tout = l.t_out;
+    p.elu_in = l.elu_in;
+    p.M = l.cout; p.N = B * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->stream, p);
+  } else {
+    ConvTrP p;
+    p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.T = l.t_in;
+    p.partial = l.state; p.scratch = l.scratch; p.w = l.w; p.bias = l.bias;
+    p.y = y; p.yb = yb; p.yc = yc; p.yt = yt;
+    p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.S = l.stride; p.elu_in = l.elu_in;
+    p.M = l.cout * l.stride; p.N = B * (l.t_in + 1); p.Kd = 2 * l.cin; p.cin_aligned = (l.cin % BK) == 0;
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+    B200_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->stream, p);
+  }
+  return check_launch(l.key.c_str());
+}
+
+int launch_linear(b200_mimi* h, const float* x, int K, const float* w, float* y, int M, int ntok, int epi,
+                  const float* res, const float* scale) {
+  LinP p;
+  p.x = x; p.ldx = K; p.w = w; p.y = y; p.ldy = M; p.res = res; p.scale = scale; p.epi = epi;
+  p.M = M; p.N = ntok; p.Kd = K;
+  dim3 grid(ceil_div(ntok, BN), ceil_div(M, BM));
+  B200_LAUNCH((igemm_f32_kernel<LinP, true>), grid, 256, 0, h->stream, p);
+  return check_launch("mimi linear");
+}
+
+// StreamingTransformer.forward for T tokens per row (transformer.py:894-929, layer :752-802)
+int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, int T) {
+  const auto& c = h->cfg;
+  const int B = h->batch, ntok = B * T, d = c.tr_d_model, H = c.tr_num_heads, D = d / H, ff = c.tr_dim_feedforward;
+  const float nl = -logf(c.tr_max_period) * 2.f / (float)D;
+  const size_t attn_smem = (size_t)(T * D + T * c.tr_context) * sizeof(float);
+  for (size_t li = 0; li < tr.layers.size(); ++li) {
+    TrLayer& L = tr.layers[li];
+    const float* cur = li == 0 ? x_in : x;
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->stream, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
+    B200_TRY(launch_linear(h, h->tr_xn, d, L.in_w, h->tr_qkv, 3 * d, ntok, EPI_NONE, nullptr, nullptr));
+    {
+      const long long total = (long long)B * T * H * (D / 2);
+      B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->stream, h->tr_qkv, h->tr_q, L.kc,
+                  L.vc, tr.offset, h->exec_mask, B, T, H, D, c.tr_context, nl);
+    }
+    B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->stream, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
+                h->exec_mask, T, H, c.tr_context, c.tr_context);
+    B200_TRY(launch_linear(h, h->tr_ao, d, L.out_w, x, d, ntok, EPI_RES_SCALE, cur, L.ls1));
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->stream, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
+    B200_TRY(launch_linear(h, h->tr_xn, d, L.l1, h->tr_h, ff, ntok, EPI_GELU, nullptr, nullptr));
+    B200_TRY(launch_linear(h, h->tr_h, ff, L.l2, x, d, ntok, EPI_RES_SCALE, x, L.ls2));
+  }
+  B200_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->stream, tr.offset, h->exec_mask, B, T);
+  return check_launch("mimi transformer");
+}
+
+int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, const float* x0, long long xb,
+               long long xc, long long xt, float* last_out, long long lb, long long lc, long long lt) {
+  // bufs[i] is the output of layers[i]; layer 0 reads (x0, strides); the last layer writes last_out.
+  for (size_t i = 0; i < layers.size(); ++i) {
+    ConvLayer& l = layers[i];
+    const float* x; long long sb, sc, st;
+    if (i == 0) { x = x0; sb = xb; sc = xc; st = xt; }
+    else { const Buf& b = bufs[i - 1]; x = b.p; sb = b.sb(0); sc = b.sc(); st = b.st(); }
+    float* y; long long yb, yc, yt;
+    if (i + 1 == layers.size() && last_out) { y = last_out; yb = lb; yc = lc; yt = lt; }
+    else { const Buf& b = bufs[i]; y = b.p; yb = b.sb(0); yc = b.sc(); yt = b.st(); }
+    const float* res = nullptr; long long rb = 0, rc = 0, rt = 0;
+    if (l.res_from == -2) {   // residual block: skip connection is the input of the first conv of the block
+      if (i < 2) B200_FAIL(B200_ERR_INVALID, "bad residual plan");
+      const Buf& b = bufs[i - 2];
+      res = b.p; rb = b.sb(0); rc = b.sc(); rt = b.st();
+    }
+    B200_TRY(launch_conv(h, l, x, sb, sc, st, y, yb, yc, yt, res, rb, rc, rt));
+  }
+  return B200_OK;
+}
+
+int commit_states(b200_mimi* h, bool encoder) {
+  const int B = h->batch;
+  if (encoder) {
+    dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
+    B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
+    B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->stream, h->enc_commits,
+                h->n_enc_commits, h->exec_mask, B);
+  } else {
+    dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
+    B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+    dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);
+    B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->stream, h->dec_tr_commits, h->exec_mask, B);
+  }
+  return check_launch("commit_states");
+}
+
+int encode_frame_to_latent(b200_mimi* h, const float* pcm, int n_frames, int f) {
+  const int B = h->batch, fs = h->frame_size, d = h->cfg.dimension;
+  const int T = fs / h->hop;   // encoder tokens per frame (2)
+  B200_CUDA(cudaMemcpy2DAsync(h->in_frame, (size_t)fs * 4, pcm + (size_t)f * fs, (size_t)fs * n_frames * 4,
+                              (size_t)fs * 4, B, cudaMemcpyDeviceToDevice, h->stream));
+  // SEANet encoder; the last conv writes token-major [B][T][C] for the transformer
+  B200_TRY(run_seanet(h, h->enc, h->enc_bufs, h->in_frame, fs, 0, 1, h->tok_in_enc, (long long)T * d, 1, d));
+  B200_TRY(run_transformer(h, h->enc_tr, h->tok_in_enc, h->tok_enc, T));
+  // learnt down-sampling conv reads token-major, writes latent [B][C][1]
+  B200_TRY(launch_conv(h, h->down, h->tok_enc, (long long)T * d, 1, d, h->latent, d, 1, 1, nullptr, 0, 0, 0));
+  B200_TRY(commit_states(h, true));
+  return B200_OK;
+}
+
+int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, long long lt, int n_cols,
+                  long long* codes, long long cs_b, long long cs_k, long long cs_f) {
+  const auto& c = h->cfg;
+  RvqEncArgs a;
+  a.lat = lat; a.lb = lb; a.lc = lc; a.lt = lt; a.n_frames = n_cols;
+  for (int w = 0; w < 2; ++w) { a.wT[w] = h->wT[w]; a.cbT[w] = h->cbT[w]; a.cb[w] = h->cb[w]; a.cnorm[w] = h->cnorm[w]; }
+  a.levels[0] = c.q_n_semantic < h->num_codebooks ? c.q_n_semantic : h->num_codebooks;
+  a.levels[1] = h->num_codebooks - a.levels[0];
+  a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
+  a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f;
+  a.n_query = h->batch * n_cols; a.Cin = c.dimension; a.Dq = c.q_dimension; a.bins = c.q_bins;
+  dim3 grid(ceil_div(a.n_query, RVQ_Q), 2);
+  const size_t smem = (size_t)RVQ_Q * (c.dimension + c.q_dimension) * sizeof(float);
+  B200_LAUNCH(rvq_encode_kernel, grid, RVQ_THREADS, smem, h->stream, a);
+  return check_launch("rvq_encode");
+}
+
+int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long long cs_k, long long cs_f, int n_codebooks,
+                    int n_cols, float* out, long long ob, long long oc, long long ot) {
+  const auto& c = h->cfg;
+  if (n_codebooks < 1 || n_codebooks > c.q_n_q) B200_FAIL(B200_ERR_SHAPE, "decode: %d codebooks", n_codebooks);
+  RvqDecArgs a;
+  a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f; a.n_frames = n_cols;
+  for (int w = 0; w < 2; ++w) { a.cb[w] = h->cb[w]; a.woT[w] = h->woT[w]; }
+  a.levels[0] = c.q_n_semantic < n_codebooks ? c.q_n_semantic : n_codebooks;
+  a.levels[1] = n_codebooks - a.levels[0];
+  a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
+  a.out = out; a.ob = ob; a.oc = oc; a.ot = ot;
+  a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins;
+  B200_LAUNCH(rvq_decode_kernel, h->batch * n_cols, 256, 2 * c.q_dimension * sizeof(float), h->stream, a);
+  return check_launch("rvq_decode");
+}
+
+int decode_latent_frame(b200_mimi* h, const float* latq /*[B][C]*/, float* pcm, int n_frames, int f) {
+  const int B = h->batch, fs = h->frame_size, d = h->cfg.dimension, S = h->rs;
+  const int T = S;   // tokens per frame after up-sampling
+  {
+    const long long total = (long long)B * 2 * S * d;   // (T_in + 1) * S * C with T_in = 1
+    B200_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->stream, latq, (long long)d, 1LL, 1LL, 1,
+                h->up_w, h->up_partial, h->up_scratch, h->tok_in_dec, B, d, S);
+  }
+  B200_TRY(run_transformer(h, h->dec_tr, h->tok_in_dec, h->tok_dec, T));
+  B200_TRY(run_seanet(h, h->dec, h->dec_bufs, h->tok_dec, (long long)T * d, 1, d, pcm + (size_t)f * fs,
+                      (long long)fs * n_frames, 0, 1));
+  B200_TRY(commit_states(h, false));
+  return B200_OK;
+}
+
+int ensure_streaming(b200_mimi* h, const char* what) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "%s: null handle", what);
+  if (!h->finalized) B200_FAIL(B200_ERR_STATE, "%s: handle not finalized", what);
+  if (h->batch <= 0) B200_FAIL(B200_ERR_STATE, "%s: not streaming (call streaming_begin first)", what);
+  return B200_OK;
+}
+
+void register_tap(b200_mimi* h, const std::string& name, const float* p, int64_t n) { h->taps[name] = {p, n}; }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out) {
+  if (!cfg || !out) B200_FAIL(B200_ERR_INVALID, "mimi_create: null argument");
+  if (cfg->n_ratios < 1 || cfg->n_ratios > 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: n_ratios out of range");
+  if (cfg->channels != 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: only mono audio is on the hot path");
+  if (cfg->q_bins > 8 * RVQ_THREADS) B200_FAIL(B200_ERR_INVALID, "mimi_create: bins > %d unsupported", 8 * RVQ_THREADS);
+  if (cfg->tr_d_model / cfg->tr_num_heads != 64) B200_FAIL(B200_ERR_INVALID, "mimi_create: head dim must be 64");
+  if (cfg->tr_d_model != cfg->dimension) B200_FAIL(B200_ERR_INVALID, "mimi_create: projected transformer unsupported");
+  b200_mimi* h = new b200_mimi();
+  h->cfg = *cfg;
+  h->num_codebooks = cfg->num_codebooks;
+  h->hop = 1;
+  for (int i = 0; i < cfg->n_ratios; ++i) h->hop *= cfg->ratios[i];
+  h->frame_size = (int)(cfg->sample_rate / cfg->frame_rate);
+  const double enc_rate = (double)cfg->sample_rate / h->hop;
+  h->rs = (int)(enc_rate / cfg->frame_rate);
+  if (h->rs < 1 || h->frame_size != h->hop * h->rs) {
+    delete h;
+    B200_FAIL(B200_ERR_INVALID, "mimi_create: frame size %d is not hop*stride", h->frame_size);
+  }
+  plan_seanet(h);
+  *out = h;
+  return B200_OK;
+}
+
+int b200_mimi_load_tensor(b200_mimi* h, const char* name, const void* data_dev, int dtype, int ndim,
+                          const int64_t* shape) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "mimi_load_tensor: null handle");
+  if (h->finalized) B200_FAIL(B200_ERR_STATE, "mimi_load_tensor: already finalized");
+  return h->store.put(name, data_dev, dtype, ndim, shape);
+}
+
+int b200_mimi_finalize(b200_mimi* h) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "mimi_finalize: null handle");
+  if (h->finalized) return B200_OK;
+  for (auto& l : h->enc) B200_TRY(pack_conv(h, l));
+  for (auto& l : h->dec) B200_TRY(pack_conv(h, l));
+  B200_TRY(pack_conv(h, h->down));
+  {
+    const float* w = nullptr;
+    B200_TRY(keep(h, "upsample.convtr.convtr.convtr.weight", {h->cfg.dimension, 1, 2 * h->rs}, &w));
+    h->up_w = const_cast<float*>(w);
+  }
+  B200_TRY(pack_transformer(h, "encoder_transformer", h->enc_tr));
+  B200_TRY(pack_transformer(h, "decoder_transformer", h->dec_tr));
+  B200_TRY(pack_quantizer(h));
+  B200_CUDA(cudaDeviceSynchronize());
+  h->store.release_all();   // anything left is not used on the hot path
+  h->finalized = true;
+  return B200_OK;
+}
+
+int b200_mimi_destroy(b200_mimi* h) {
+  if (!h) return B200_OK;
+  b200_mimi_streaming_end(h);
+  h->store.release_all();
+  h->weights.free_all();
+  if (h->pin_pcm) cudaFreeHost(h->pin_pcm);
+  if (h->pin_codes) cudaFreeHost(h->pin_codes);
+  if (h->dev_pcm) cudaFree(h->dev_pcm);
+  if (h->dev_codes) cudaFree(h->dev_codes);
+  delete h;
+  return B200_OK;
+}
+
+int b200_mimi_set_num_codebooks(b200_mimi* h, int n) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "set_num_codebooks: null handle");
+  if (n < h->cfg.q_n_semantic || n > h->cfg.q_n_q)   // vq.py:315-317 assertion
+    B200_FAIL(B200_ERR_SHAPE, "set_num_codebooks(%d): must be in [%d, %d]", n, h->cfg.q_n_semantic, h->cfg.q_n_q);
+  h->num_codebooks = n;
+  return B200_OK;
+}
+
+int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
+  if (!h || !h->finalized) B200_FAIL(B200_ERR_STATE, "streaming_begin: handle not finalized");
+  if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "streaming_begin: already streaming");   // streaming.py:112
+  if (batch < 1) B200_FAIL(B200_ERR_INVALID, "streaming_begin: batch %d", batch);
+  const auto& c = h->cfg;
+  const int B = batch, d = c.dimension;
+  h->stream = static_cast<cudaStream_t>(stream);
+  h->taps.clear();
+  Arena& A = h->state;
+  B200_TRY(A.alloc_t(&h->exec_mask, B, false));
+  B200_CUDA(cudaMemset(h->exec_mask, 1, B));
+  B200_TRY(A.alloc_t(&h->in_frame, (size_t)B * h->frame_size));
+
+  // flags for replicate-padded convs (only the down-sampling conv in Mimi)
+  h->n_first = 1;
+  B200_TRY(A.alloc_t(&h->first_flags, (size_t)h->n_first * B, false));
+  B200_CUDA(cudaMemset(h->first_flags, 1, (size_t)h->n_first * B));
+
+  std::vector<ConvCommit> enc_c, dec_c;
+  std::vector<ConvTrCommit> dec_t;
+  h->max_enc_rows = h->max_dec_rows = 0;
+  h->max_tr_rows = 0;
+
+  auto setup = [&](std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, int t0, bool last_token_major,
+                   const float* x0, long long x0b, long long x0c, long long x0t, std::vector<ConvCommit>& commits,
+                   const char* tag, bool is_dec) -> int {
+    bufs.assign(layers.size(), Buf());
+    int t = t0;
+    for (size_t i = 0; i < layers.size(); ++i) {
+      ConvLayer& l = layers[i];
+      l.t_in = t;
+      if (l.kind == 0) {
+        if (t % l.stride) B200_FAIL(B200_ERR_INVALID, "%s: %d samples not divisible by stride %d", l.key.c_str(), t, l.stride);
+        l.t_out = t / l.stride;
+        l.P = (l.k - 1) * l.dil + 1 - l.stride;
+        if (l.P > 0) B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
+      } else {
+        l.t_out = t * l.stride;
+        l.P = l.k - l.stride;
+        B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cout * l.P));
+        B200_TRY(A.alloc_t(&l.scratch, (size_t)B * l.cout * l.P));
+      }
+      t = l.t_out;
+      Buf& b = bufs[i];
+      b.c = l.cout; b.t = l.t_out;
+      const bool is_last = i + 1 == layers.size();
+      if (!(is_last && is_dec)) {   // the decoder's last conv writes straight into the caller's PCM buffer
+        b.token_major = is_last && last_token_major;
+        B200_TRY(A.alloc_t(&b.p, (size_t)B * l.cout * l.t_out));
+        if (!l.tap.empty()) register_tap(h, l.tap, b.p, (int64_t)B * l.cout * l.t_out);
+      }
+      // commit descriptor
+      const float* x; long long sb, sc, st;
+      if (i == 0) { x = x0; sb = x0b; sc = x0c; st = x0t; }
+      else { const Buf& pb = bufs[i - 1]; x = pb.p; sb = pb.sb(0); sc = pb.sc(); st = pb.st(); }
+      if (l.kind == 0 && l.P > 0) {
+        ConvCommit cc;
+        cc.x = x; cc.xb = sb; cc.xc = sc; cc.xt = st; cc.Tin = l.t_in; cc.st = l.state; cc.P = l.P; cc.Cin = l.cin;
+        cc.elu_in = l.elu_in; cc.first = nullptr;
+        commits.push_back(cc);
+        int rows = B * l.cin;
+        int& mx = is_dec ? h->max_dec_rows : h->max_enc_rows;
+        if (rows > mx) mx = rows;
+      } else if (l.kind == 1) {
+        ConvTrCommit tc;
+        tc.partial = l.state; tc.scratch = l.scratch; tc.per_row = l.cout * l.P;
+        dec_t.push_back(tc);
+        if ((long long)B * tc.per_row > h->max_tr_rows) h->max_tr_rows = (long long)B * tc.per_row;
+      }
+    }
+    (void)tag;
+    return B200_OK;
+  };
+
+  const int T = h->rs;   // transformer tokens per frame on both sides
+  B200_TRY(A.alloc_t(&h->tok_in_enc, (size_t)B * T * d));   // written by the last encoder conv (token-major)
+  B200_TRY(A.alloc_t(&h->tok_enc, (size_t)B * T * d));
+  B200_TRY(A.alloc_t(&h->latent, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->latent_q, (size_t)B * d));
+  B200_TRY(A.alloc_t(&h->tok_in_dec, (size_t)B * T * d));
+  B200_TRY(A.alloc_t(&h->tok_dec, (size_t)B * T * d));
+  B200_TRY(setup(h->enc, h->enc_bufs, h->frame_size, true, h->in_frame, h->frame_size, 0, 1, enc_c, "enc", false));
+  // the last encoder conv writes tok_in_enc instead of its own buffer
+  register_tap(h, h->enc.back().tap, h->tok_in_enc, (int64_t)B * T * d);
+  if (h->enc.back().t_out != T) B200_FAIL(B200_ERR_INVALID, "encoder yields %d tokens/frame, expected %d", h->enc.back().t_out, T);
+  B200_TRY(setup(h->dec, h->dec_bufs, T, false, h->tok_dec, (long long)T * d, 1, d, dec_c, "dec", true));
+  if (h->dec.back().t_out != h->frame_size) B200_FAIL(B200_ERR_INVALID, "decoder yields %d samples/frame", h->dec.back().t_out);
+  register_tap(h, "enc.tr", h->tok_enc, (int64_t)B * T * d);
+  register_tap(h, "enc.latent", h->latent, (int64_t)B * d);
+  register_tap(h, "dec.latent", h->latent_q, (int64_t)B * d);
+  register_tap(h, "dec.up", h->tok_in_dec, (int64_t)B * T * d);
+  register_tap(h, "dec.tr", h->tok_dec, (int64_t)B * T * d);
+
+  // down-sampling conv (replicate pad): reads tok_enc token-major
+  {
+    ConvLayer& l = h->down;
+    l.t_in = T; l.t_out = T / l.stride; l.P = l.k - l.stride;
+    B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
+    l.first = h->first_flags;
+    ConvCommit cc;
+    cc.x = h->tok_enc; cc.xb = (long long)T * d; cc.xc = 1; cc.xt = d; cc.Tin = T; cc.st = l.state; cc.P = l.P;
+    cc.Cin = l.cin; cc.elu_in = 0; cc.first = l.first;
+    enc_c.push_back(cc);
+    if (B * l.cin > h->max_enc_rows) h->max_enc_rows = B * l.cin;
+  }
+  // up-sampling depth-wise convtr
+  B200_TRY(A.alloc_t(&h->up_partial, (size_t)B * d * h->rs));
+  B200_TRY(A.alloc_t(&h->up_scratch, (size_t)B * d * h->rs));
+  {
+    ConvTrCommit tc;
+    tc.partial = h->up_partial; tc.scratch = h->up_scratch; tc.per_row = d * h->rs;
+    dec_t.push_back(tc);
+    if ((long long)B * tc.per_row > h->max_tr_rows) h->max_tr_rows = (long long)B * tc.per_row;
+  }
+  h->n_enc_commits = (int)enc_c.size();
+  h->n_dec_commits = (int)dec_c.size();
+  h->n_dec_tr_commits = (int)dec_t.size();
+  B200_TRY(A.alloc_t(&h->enc_commits, enc_c.size(), false));
+  B200_TRY(A.alloc_t(&h->dec_commits, dec_c.size() ? dec_c.size() : 1, false));
+  B200_TRY(A.alloc_t(&h->dec_tr_commits, dec_t.size(), false));
+  B200_CUDA(cudaMemcpy(h->enc_commits, enc_c.data(), enc_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
+  if (!dec_c.empty())
+    B200_CUDA(cudaMemcpy(h->dec_commits, dec_c.data(), dec_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(h->dec_tr_commits, dec_t.data(), dec_t.size() * sizeof(ConvTrCommit), cudaMemcpyHostToDevice));
+
+  // transformers
+  const int H = c.tr_num_heads, D = d / H, ff = c.tr_dim_feedforward;
+  for (Transformer* tr : {&h->enc_tr, &h->dec_tr}) {
+    B200_TRY(A.alloc_t(&tr->offset, B));
+    for (auto& L : tr->layers) {
+      B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.tr_context * D));
+      B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.tr_context * D));
+    }
+  }
+  const size_t ntok = (size_t)B * T;
+  B200_TRY(A.alloc_t(&h->tr_xn, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_qkv, ntok * 3 * d));
+  B200_TRY(A.alloc_t(&h->tr_q, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_ao, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_h, ntok * ff));
+  B200_TRY(A.alloc_t(&h->scratch_codes, (size_t)B * c.q_n_q));
+  B200_CUDA(cudaDeviceSynchronize());
+  h->batch = B;
+  return B200_OK;
+}
+
+int b200_mimi_streaming_end(b200_mimi* h) {
+  if (!h) return B200_OK;
+  if (h->batch > 0) cudaStreamSynchronize(h->stream);
+  h->state.free_all();
+  h->batch = 0;
+  h->taps.clear();
+  return B200_OK;
+}
+
+int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_reset"));
+  const int B = h->batch;
+  auto zero = [&](float* buf, long long per_row) {
+    if (!buf || per_row <= 0) return;
+    B200_LAUNCH(zero_rows_kernel, (unsigned)ceil_div64((long long)B * per_row, 256), 256, 0, h->stream, buf, per_row,
+                reset_mask_dev, B);
+  };
+  for (auto* layers : {&h->enc, &h->dec})
+    for (auto& l : *layers) zero(l.state, l.kind == 0 ? (long long)l.cin * l.P : (long long)l.cout * l.P);
+  zero(h->down.state, (long long)h->down.cin * h->down.P);
+  zero(h->up_partial, (long long)h->cfg.dimension * h->rs);
+  B200_LAUNCH(reset_flags_kernel, ceil_div(B, 128), 128, 0, h->stream, h->first_flags, h->n_first, h->enc_tr.offset,
+              h->dec_tr.offset, h->exec_mask, reset_mask_dev, B);
+  return check_launch("mimi_reset");
+}
+
+int b200_mimi_set_exec_mask(b200_mimi* h, const uint8_t* exec_mask_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_set_exec_mask"));
+  if (!exec_mask_dev) B200_FAIL(B200_ERR_INVALID, "mimi_set_exec_mask: null mask");
+  B200_CUDA(cudaMemcpyAsync(h->exec_mask, exec_mask_dev, h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
+int b200_mimi_encode_to_latent(b200_mimi* h, const float* pcm_dev, int n_frames, float* latent_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_encode_to_latent"));
+  if (!pcm_dev || !latent_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_encode_to_latent: bad arguments");
+  const int d = h->cfg.dimension;
+  for (int f = 0; f < n_frames; ++f) {
+    B200_TRY(encode_frame_to_latent(h, pcm_dev, n_frames, f));
+    B200_CUDA(cudaMemcpy2DAsync(latent_dev + f, (size_t)n_frames * 4, h->latent, 4, 4, (size_t)h->batch * d,
+                                cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return B200_OK;
+}
+
+int b200_mimi_quantize(b200_mimi* h, const float* latent_dev, int n_frames, int64_t* codes_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_quantize"));
+  if (!latent_dev || !codes_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_quantize: bad arguments");
+  const int d = h->cfg.dimension, K = h->num_codebooks;
+  return quantize_cols(h, latent_dev, (long long)d * n_frames, n_frames, 1, n_frames,
+                       reinterpret_cast<long long*>(codes_dev), (long long)K * n_frames, n_frames, 1);
+}
+
+int b200_mimi_encode(b200_mimi* h, const float* pcm_dev, int n_frames, int64_t* codes_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_encode"));
+  if (!pcm_dev || !codes_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_encode: bad arguments");
+  const int d = h->cfg.dimension, K = h->num_codebooks;
+  for (int f = 0; f < n_frames; ++f) {
+    B200_TRY(encode_frame_to_latent(h, pcm_dev, n_frames, f));
+    B200_TRY(quantize_cols(h, h->latent, d, 1, 1, 1, reinterpret_cast<long long*>(codes_dev) + f,
+                           (long long)K * n_frames, n_frames, 1));
+  }
+  return B200_OK;
+}
+
+int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames, float* latent_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_decode_latent"));
+  if (!codes_dev || !latent_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_decode_latent: bad arguments");
+  const int d = h->cfg.dimension;
+  return dequantize_cols(h, reinterpret_cast<const long long*>(codes_dev), (long long)n_codebooks * n_frames, n_frames, 1,
+                         n_codebooks, n_frames, latent_dev, (long long)d * n_frames, n_frames, 1);
+}
+
+int b200_mimi_decode(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames, float* pcm_dev) {
+  B200_TRY(ensure_streaming(h, "mimi_decode"));
+  if (!codes_dev || !pcm_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_decode: bad arguments");
+  const int d = h->cfg.dimension;
+  for (int f = 0; f < n_frames; ++f) {
+    B200_TRY(dequantize_cols(h, reinterpret_cast<const long long*>(codes_dev) + f, (long long)n_codebooks * n_frames,
+                             n_frames, 1, n_codebooks, 1, h->latent_q, d, 1, 1));
+    B200_TRY(decode_latent_frame(h, h->latent_q, pcm_dev, n_frames, f));
+  }
+  return B200_OK;
+}
+
+static int ensure_host_staging(b200_mimi* h, size_t pcm_n, size_t codes_n) {
+  if (pcm_n > h->pin_pcm_n) {
+    if (h->pin_pcm) cudaFreeHost(h->pin_pcm);
+    if (h->dev_pcm) cudaFree(h->dev_pcm);
+    B200_CUDA(cudaMallocHost(&h->pin_pcm, pcm_n * 4));
+    B200_CUDA(cudaMalloc(&h->dev_pcm, pcm_n * 4));
+    h->pin_pcm_n = h->dev_pcm_n = pcm_n;
+  }
+  if (codes_n > h->pin_codes_n) {
+    if (h->pin_codes) cudaFreeHost(h->pin_codes);
+    if (h->dev_codes) cudaFree(h->dev_codes);
+    B200_CUDA(cudaMallocHost(&h->pin_codes, codes_n * 8));
+    B200_CUDA(cudaMalloc(&h->dev_codes, codes_n * 8));
+    h->pin_codes_n = h->dev_codes_n = codes_n;
+  }
+  return B200_OK;
+}
+
+int b200_mimi_encode_host(b200_mimi* h, const float* pcm_host, int n_frames, int64_t* codes_host) {
+  B200_TRY(ensure_streaming(h, "mimi_encode_host"));
+  if (!pcm_host || !codes_host || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_encode_host: bad arguments");
+  const size_t pn = (size_t)h->batch * h->frame_size * n_frames, cn = (size_t)h->batch * h->num_codebooks * n_frames;
+  B200_TRY(ensure_host_staging(h, pn, cn));
+  memcpy(h->pin_pcm, pcm_host, pn * 4);
+  B200_CUDA(cudaMemcpyAsync(h->dev_pcm, h->pin_pcm, pn * 4, cudaMemcpyHostToDevice, h->stream));
+  B200_TRY(b200_mimi_encode(h, h->dev_pcm, n_frames, reinterpret_cast<int64_t*>(h->dev_codes)));
+  B200_CUDA(cudaMemcpyAsync(h->pin_codes, h->dev_codes, cn * 8, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(codes_host, h->pin_codes, cn * 8);
+  return B200_OK;
+}
+
+int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codebooks, int n_frames, float* pcm_host) {
+  B200_TRY(ensure_streaming(h, "mimi_decode_host"));
+  if (!pcm_host || !codes_host || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_decode_host: bad arguments");
+  const size_t pn = (size_t)h->batch * h->frame_size * n_frames, cn = (size_t)h->batch * n_codebooks * n_frames;
+  B200_TRY(ensure_host_staging(h, pn, cn));
+  memcpy(h->pin_codes, codes_host, cn * 8);
+  B200_CUDA(cudaMemcpyAsync(h->dev_codes, h->pin_codes, cn * 8, cudaMemcpyHostToDevice, h->stream));
+  B200_TRY(b200_mimi_decode(h, reinterpret_cast<const int64_t*>(h->dev_codes), n_codebooks, n_frames, h->dev_pcm));
+  B200_CUDA(cudaMemcpyAsync(h->pin_pcm, h->dev_pcm, pn * 4, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(pcm_host, h->pin_pcm, pn * 4);
+  return B200_OK;
+}
+
+int b200_mimi_read_buffer(b200_mimi* h, const char* name, float* dst_dev, int64_t capacity, int64_t* numel) {
+  B200_TRY(ensure_streaming(h, "mimi_read_buffer"));
+  auto it = h->taps.find(name ? name : "");
+  if (it == h->taps.end()) B200_FAIL(B200_ERR_INVALID, "mimi_read_buffer: unknown buffer '%s'", name ? name : "(null)");
+  if (numel) *numel = it->second.second;
+  if (!dst_dev) return B200_OK;
+  if (capacity < it->second.second) B200_FAIL(B200_ERR_SHAPE, "mimi_read_buffer: destination too small");
+  B200_CUDA(cudaMemcpyAsync(dst_dev, it->second.first, (size_t)it->second.second * 4, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
+int64_t b200_mimi_algorithmic_bytes(b200_mimi* h) {
+  if (!h || h->batch <= 0) return 0;
+  const auto& c = h->cfg;
+  // weights once per step (encode + decode) + active codebooks (row-major for decode, transposed for encode)
+  int64_t bytes = h->weight_bytes;
+  bytes += (int64_t)2 * h->num_codebooks * c.q_bins * c.q_dimension * 4 + (int64_t)4 * c.q_dimension * c.dimension * 4;
+  // per session: both transformer KV rings read once, conv/convtr carried state read + written, PCM in/out
+  int64_t per_row = (int64_t)2 * c.tr_num_layers * 2 * c.tr_context * c.tr_d_model * 4;
+  int64_t st = 0;
+  for (auto* layers : {&h->enc, &h->dec})
+    for (auto& l : *layers) st += (l.kind == 0 ? (int64_t)l.cin * l.P : (int64_t)l.cout * l.P);
+  st += (int64_t)h->down.cin * h->down.P + (int64_t)c.dimension * h->rs;
+  per_row += 2 * st * 4 + (int64_t)2 * h->frame_size * 4 + h->num_codebooks * 8;
+  return bytes + per_row * h->batch;
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+// fp32 kernels of the Mimi codec path.  Everything on the encode side stays in exact fp32 FMA
+// arithmetic (no TF32 / bf16) because the RVQ indices downstream must match the reference's.
+//
+// Layout conventions
+//   * activations are addressed through explicit (batch, channel, time) strides, so a layer can
+//     read / write either the reference's [B, C, T] layout or the token-major [B, T, C] layout the
+//     transformer kernels use — no transposition kernels (ProjectedTransformer.conv_layout,
+//     transformer.py:972-981, is folded into the neighbouring conv's addressing).
+//   * conv weights are repacked once at load: Conv1d  [Cout][Cin][K] -> [Cout][K*Cin] (tap-major,
+//     channel fastest) so a K-chunk of the implicit GEMM shares one tap;
+//     ConvTranspose1d [Cin][Cout][K=2S] -> [Cout*S][2*Cin] (phase r = output sample modulo S,
+//     tap 0 = current input step, tap 1 = previous input step).
+#pragma once
+
+#include "common.cuh"
+
+namespace b200 {
+namespace mimi {
+
+// ---------------------------------------------------------------------------------------------
+// Tiled fp32 implicit GEMM:  C[m][n] = sum_k A[m][k] * B[k][n]   (64x64 tile, 256 threads, 4x4/thread)
+// A = packed weights (row-major [M][Kd]); B is gathered by the policy; the policy owns the epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16;
+
+struct ConvP {
+  const float* x; long long xb, xc, xt; int Tin;
+  const float* st; int P;            // carried left context [B][Cin][P]
+  const uint8_t* first;              // replicate-pad flags or nullptr
+  const float* w; const float* bias;
+  float* y; long long yb, yc, yt;
+  const float* res; long long rb, rc, rt;
+  int B, Cin, Cout, K, stride, dil, Tout, elu_in;
+  int M, N, Kd, cin_aligned;
+
+  struct Ctx { int valid, b, t; };
+  __device__ __forceinline__ Ctx prepare(int n) const {
+    Ctx c; c.valid = n < N; c.b = c.valid ? n / Tout : 0; c.t = n - c.b * Tout; return c;
+  }
+  __device__ __forceinline__ float ext(int b, int ci, int j) const {
+    // sample j of cat(previous, x) for row b, channel ci   (conv.py:261)
+    if (j < P) {
+      if (first != nullptr && first[b]) {           // conv.py:254-259 (replicate mode, first step)
+        float v = x[b * xb + ci * xc];
+        return elu_in ? elu1(v) : v;
+      }
+      return st[((long long)b * Cin + ci) * P + j];
+    }
+    float v = x[b * xb + ci * xc + (long long)(j - P) * xt];
+    return elu_in ? elu1(v) : v;
+  }
+  __device__ __forceinline__ float loadB(const Ctx& c, int kk, int kw_hint) const {
+    if (!c.valid || kk >= Kd) return 0.f;
+    int kw = cin_aligned ? kw_hint : kk / Cin;
+    int ci = kk - kw * Cin;
+    return ext(c.b, ci, c.t * stride + kw * dil);
+  }
+  __device__ __forceinline__ int chunk_hint(int k0) const { return cin_aligned ? k0 / Cin : 0; }
+  __device__ __forceinline__ float loadBk(int, int) const { return 0.f; }
+  __device__ __forceinline__ void store(int m, int n, float acc) const {
+    if (m >= M || n >= N) return;
+    int b = n / Tout, t = n - b * Tout;
+    float v = acc + (bias ? bias[m] : 0.f);
+    if (res) v = res[b * rb + m * rc + t * rt] + v;   // SEANetResnetBlock: u + v (seanet.py:90-93)
+    y[b * yb + m * yc + t * yt] = v;
+  }
+};
+
+struct ConvTrP {
+  const float* x; long long xb, xc, xt; int T;
+  const float* partial;   // [B][Cout][S] overlap-add carry (conv.py:349-361)
+  float* scratch;         // candidate carry of this step, committed where exec_mask
+  const float* w; const float* bias;
+  float* y; long long yb, yc, yt;
+  int B, Cin, Cout, S, elu_in;
+  int M, N, Kd, cin_aligned;
+
+  struct Ctx { int valid, b, t; };
+  __device__ __forceinline__ Ctx prepare(int n) const {
+    Ctx c; c.valid = n < N; c.b = c.valid ? n / (T + 1) : 0; c.t = n - c.b * (T + 1); return c;
+  }
+  __device__ __forceinline__ float loadB(const Ctx& c, int kk, int tap_hint) const {
+    if (!c.valid || kk >= Kd) return 0.f;
+    int tap = cin_aligned ? tap_hint : kk / Cin;
+    int ci = kk - tap * Cin;
+    int tt = c.t - tap;
+    if (tt < 0 || tt >= T) return 0.f;
+    float v = x[c.b * xb + ci * xc + (long long)tt * xt];
+    return elu_in ? elu1(v) : v;
+  }
+  __device__ __forceinline__ int chunk_hint(int k0) const { return cin_aligned ? k0 / Cin : 0; }
+  __device__ __forceinline__ float loadBk(int, int) const { return 0.f; }
+  __device__ __forceinline__ void store(int m, int n, float acc) const {
+    if (m >= M || n >= N) return;
+    int b = n / (T + 1), t = n - b * (T + 1);
+    int co = m / S, r = m - co * S;
+    long long sidx = ((long long)b * Cout + co) * S + r;
+    if (t == T) { scratch[sidx] = acc; return; }          // tail of y minus bias (conv.py:352-356)
+    float v = acc + (bias ? bias[co] : 0.f);
+    if (t == 0) v += partial[sidx];                       // y[..., :PT] += partial (conv.py:351)
+    y[b * yb + co * yc + (long long)(t * S + r) * yt] = v;
+  }
+};
+
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RES_SCALE = 2 };
+
+struct LinP {   // y[n][m] = epi(sum_k x[n][k] * w[m][k]);  token-major activations
+  const float* x; long long ldx;
+  const float* w;
+  float* y; long long ldy;
+  const float* res; const float* scale; int epi;
+  int M, N, Kd;
+  struct Ctx { int unused; };
+  __device__ __forceinline__ Ctx prepare(int) const { return Ctx{0}; }
+  __device__ __forceinline__ int chunk_hint(int) const { return 0; }
+  __device__ __forceinline__ float loadB(const Ctx&, int, int) const { return 0.f; }
+  __device__ __forceinline__ float loadBk(int kk, int n) const {
+    return (n < N && kk < Kd) ? x[n * ldx + kk] : 0.f;
+  }
+  __device__ __forceinline__ void store(int m, int n, float acc) const {
+    if (m >= M || n >= N) return;
+    float v = acc;
+    if (epi == EPI_GELU) v = gelu_erf(v);
+    else if (epi == EPI_RES_SCALE) v = res[n * ldy + m] + scale[m] * v;   // x + layer_scale(update)
+    y[n * ldy + m] = v;
+  }
+};
+
+template <class P, bool B_K_FAST>
+static __global__ void __launch_bounds__(256) igemm_f32_kernel(const P p) {
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // A loader: 16 consecutive k per row -> coalesced 64 B segments
+  const int a_k = tid & 15, a_m = tid >> 4;               // rows a_m + 16*i
+  // B loader, n-fast (gathers): one column per thread, rows b_k + 4*i
+  const int bn_n = tid & 63, bn_k = tid >> 6;
+  // B loader, k-fast (row-major activations): 16 consecutive k per token
+  const int bk_k = tid & 15, bk_n = tid >> 4;             // cols bk_n + 16*i
+
+  const typename P::Ctx ctx = p.prepare(n0 + bn_n);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + a_m + 16 * i, kk = k0 + a_k;
+      ra[i] = (m < p.M && kk < p.Kd) ? p.w[(long long)m * p.Kd + kk] : 0.f;
+    }
+    if constexpr (B_K_FAST) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rb[i] = p.loadBk(k0 + bk_k, n0 + bk_n + 16 * i);
+    } else {
+      int hint = p.chunk_hint(k0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rb[i] = p.loadB(ctx, k0 + bn_k + 4 * i, hint);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[buf][a_k][a_m + 16 * i] = ra[i];
+    if constexpr (B_K_FAST) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][bk_k][bk_n + 16 * i] = rb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][bn_k + 4 * i][bn_n] = rb[i];
+    }
+  };
+
+  const int nk = (p.Kd + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int it = 0; it < nk; ++it) {
+    const int cur = it & 1;
+    if (it + 1 < nk) fetch((it + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+      const float4 av = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[cur][kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (it + 1 < nk) stash(cur ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p.store(m0 + ty * 4 + i, n0 + tx + 16 * j, acc[i][j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// state commits (run after the layer kernels of a step; only rows with exec_mask change)
+// ---------------------------------------------------------------------------------------------
+struct ConvCommit {   // previous <- last P samples of cat(previous, act(x))   (conv.py:263-267)
+  const float* x; long long xb, xc, xt; int Tin;
+  float* st; int P, Cin, elu_in;
+  uint8_t* first;     // replicate flags (cleared where exec_mask) or nullptr
+};
+struct ConvTrCommit { // partial <- scratch   (conv.py:357-360)
+  float* partial; const float* scratch; int per_row;   // Cout * S
+};
+
+static __global__ void conv_commit_kernel(const ConvCommit* descs, int n_desc, const uint8_t* exec_mask, int B) {
+  const ConvCommit d = descs[blockIdx.y];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;   // (b, ci)
+  if (row >= B * d.Cin) return;
+  const int b = row / d.Cin, ci = row - b * d.Cin;
+  if (!exec_mask[b]) return;
+  const bool rep = d.first != nullptr && d.first[b];
+  float* s = d.st + (long long)row * d.P;
+  for (int j = 0; j < d.P; ++j) {
+    const int e = d.Tin + j;          // index into cat(previous, x); reads run ahead of writes
+    float v;
+    if (e < d.P) {
+      if (rep) { v = d.x[b * d.xb + ci * d.xc]; v = d.elu_in ? elu1(v) : v; }
+      else v = s[e];
+    } else {
+      v = d.x[b * d.xb + ci * d.xc + (long long)(e - d.P) * d.xt];
+      v = d.elu_in ? elu1(v) : v;
+    }
+    s[j] = v;
+  }
+}
+
+// `first` flags are cleared in a second tiny pass so that every (b, ci) thread above saw the old value.
+static __global__ void conv_clear_first_kernel(const ConvCommit* descs, int n_desc, const uint8_t* exec_mask, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_desc * B) return;
+  const ConvCommit d = descs[i / B];
+  const int b = i % B;
+  if (d.first != nullptr && exec_mask[b]) d.first[b] = 0;
+}
+
+static __global__ void convtr_commit_kernel(const ConvTrCommit* descs, const uint8_t* exec_mask, int B) {
+  const ConvTrCommit d = descs[blockIdx.y];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * d.per_row) return;
+  if (exec_mask[i / d.per_row]) d.partial[i] = d.scratch[i];
+}
+
+// reset: zero the state of the rows in reset_mask (conv.py:166-169, 281-286)
+static __global__ void zero_rows_kernel(float* buf, long long per_row, const uint8_t* mask, int B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * per_row) return;
+  if (mask == nullptr || mask[i / per_row]) buf[i] = 0.f;
+}
+static __global__ void reset_flags_kernel(uint8_t* first /*[n_first][B]*/, int n_first, long long* off_a, long long* off_b,
+                                   uint8_t* exec_mask, const uint8_t* mask, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (mask != nullptr && !mask[b]) return;
+  exec_mask[b] = 1;                                       // State.reset (streaming.py:41-42)
+  for (int i = 0; i < n_first; ++i) first[(long long)i * B + b] = 1;
+  if (off_a) off_a[b] = 0;                                // _MHAState.reset / RingKVCache.reset
+  if (off_b) off_b[b] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth-wise ConvTranspose1d up-sampling (resample.py:68-119 with channel_wise=True, k=2S, no bias)
+// latent [B][C] (one frame) -> tokens [B][S][C] (token-major for the decoder transformer)
+// ---------------------------------------------------------------------------------------------
+static __global__ void upsample_dw_kernel(const float* __restrict__ lat, long long lb, long long lc, long long lt, int T,
+                                   const float* __restrict__ w /*[C][2S]*/, const float* __restrict__ partial,
+                                   float* __restrict__ scratch, float* __restrict__ y /*[B][T*S][C]*/,
+                                   int B, int C, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * (T + 1) * S * C;
+  if (i >= total) return;
+  const int c = i % C;
+  long long r0 = i / C;
+  const int r = r0 % S; r0 /= S;
+  const int t = r0 % (T + 1);
+  const int b = r0 / (T + 1);
+  const float* xr = lat + b * lb + c * lc;
+  const long long sidx = ((long long)b * C + c) * S + r;
+  if (t == T) { scratch[sidx] = w[c * 2 * S + r + S] * xr[(long long)(T - 1) * lt]; return; }
+  float v = w[c * 2 * S + r] * xr[(long long)t * lt];
+  if (t == 0) v += partial[sidx];
+  else v += w[c * 2 * S + r + S] * xr[(long long)(t - 1) * lt];
+  y[((long long)b * T * S + (long long)t * S + r) * C + c] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transformer pieces (fp32): LayerNorm(1e-5), RoPE + ring append, ring attention (T tokens/frame)
+// ---------------------------------------------------------------------------------------------
+static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
+                                 float* __restrict__ y, int n_tok, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_tok) return;
+  const float* xr = x + (long long)warp * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = xr[c] - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / C + eps);
+  for (int c = lane; c < C; c += 32) y[(long long)warp * C + c] = (xr[c] - mean) * rstd * g[c] + bta[c];
+}
+
+// qkv [n_tok][3C] (rows q|k|v, each (h d), transformer.py:557-559) -> q_rot [n_tok][C]; K,V ring
+// [B][H][cap][D] written at slot (end_offset[b] + t) % cap.  Masked rows (exec_mask == 0) do not write.
+static __global__ void rope_append_f32_kernel(const float* __restrict__ qkv, float* __restrict__ q_out,
+                                       float* __restrict__ kc, float* __restrict__ vc,
+                                       const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
+                                       int B, int T, int H, int D, int cap, float neg_log_period_2_over_d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, t, h, pair)
+  const int half = D / 2;
+  const long long total = (long long)B * T * H * half;
+  if (i >= total) return;
+  const int pr = i % half;
+  long long r = i / half;
+  const int h = r % H; r /= H;
+  const int t = r % T;
+  const int b = r / T;
+  const int C = H * D;
+  const long long tok = (long long)b * T + t;
+  const float pos = (float)offset[b] + (float)t;               // rope.py:48
+  const float freq = expf((float)pr * neg_log_period_2_over_d);  // rope.py:46
+  float sn, cs;
+  sincosf(freq * pos, &sn, &cs);
+  const float* base = qkv + tok * 3 * C + h * D + 2 * pr;
+  const float qr = base[0], qi = base[1];
+  const float kr = base[C], ki = base[C + 1];
+  q_out[tok * C + h * D + 2 * pr] = qr * cs - qi * sn;
+  q_out[tok * C + h * D + 2 * pr + 1] = qr * sn + qi * cs;
+  if (!exec_mask[b]) return;
+  const int slot = (int)((offset[b] + t) % cap);
+  const long long o = (((long long)b * H + h) * cap + slot) * D + 2 * pr;
+  kc[o] = kr * cs - ki * sn;
+  kc[o + 1] = kr * sn + ki * cs;
+  vc[o] = base[2 * C];
+  vc[o + 1] = base[2 * C + 1];
+}
+
+// One CTA per (b, h); T (<= 4) queries share the K/V stream.  Slot positions follow
+// RingKVCache.complete (transformer.py:255-286) *after* this frame's T keys were written.
+template <int D>
+static __global__ void __launch_bounds__(128) ring_attn_f32_kernel(const float* __restrict__ q, const float* __restrict__ kc,
+                                                            const float* __restrict__ vc, float* __restrict__ out,
+                                                            const long long* __restrict__ offset,
+                                                            const uint8_t* __restrict__ exec_mask,
+                                                            int T, int H, int cap, int context) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int C = H * D;
+  float* sq = sm;                 // [T][D]
+  float* sc = sm + T * D;         // [T][cap]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i % D;
+    sq[i] = q[((long long)b * T + t) * C + h * D + d];
+  }
+  __syncthreads();
+  const long long off = offset[b];
+  // end_offset after the append: only advanced for executing rows (transformer.py:279-284)
+  const long long end_after = exec_mask[b] ? off + T : off;
+  const long long last = off + T - 1;
+  const int end_index = (int)(last % cap);
+  const float scale = rsqrtf((float)D);
+  const float* kb = kc + ((long long)b * H + h) * cap * D;
+  const float* vb = vc + ((long long)b * H + h) * cap * D;
+  for (int s = tid; s < cap; s += blockDim.x) {
+    const int delta = s - end_index;
+    long long pos = delta <= 0 ? last + delta : last + delta - cap;
+    if (s >= end_after) pos = -1;
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pos >= 0) {
+      const float4* kr = reinterpret_cast<const float4*>(kb + (long long)s * D);
+#pragma unroll 4
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kv = kr[d4];
+        for (int t = 0; t < T; ++t) {
+          const float* qq = sq + t * D + d4 * 4;
+          dot[t] += kv.x * qq[0] + kv.y * qq[1] + kv.z * qq[2] + kv.w * qq[3];
+        }
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      const long long dq = (off + t) - pos;
+      const bool ok = pos >= 0 && dq >= 0 && dq < context;     // transformer.py:576-580
+      sc[t * cap + s] = ok ? dot[t] * scale : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // softmax per query: warp t handles query t
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < T) {
+    float* row = sc + warp * cap;
+    float mx = -INFINITY;
+    for (int s = lane; s < cap; s += 32) mx = fmaxf(mx, row[s]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < cap; s += 32) {
+      const float e = (row[s] == -INFINITY) ? 0.f : expf(row[s] - mx);
+      row[s] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    for (int s = lane; s < cap; s += 32) row[s] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i % D;
+    const float* row = sc + t * cap;
+    float acc = 0.f;
+    for (int s = 0; s < cap; ++s) {
+      const float pw = row[s];
+      if (pw != 0.f) acc = fmaf(pw, vb[(long long)s * D + d], acc);
+    }
+    out[((long long)b * T + t) * C + h * D + d] = acc;
+  }
+}
+
+static __global__ void advance_offsets_kernel(long long* off, const uint8_t* exec_mask, int B, int T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && exec_mask[b]) off[b] += T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Residual vector quantizer
+// ---------------------------------------------------------------------------------------------
+constexpr int RVQ_Q = 4;          // queries per CTA
+constexpr int RVQ_THREADS = 256;
+
+// One CTA = RVQ_Q latent vectors x one of the two quantizers (blockIdx.y: 0 = rvq_first, 1 = rvq_rest).
+//   proj:   res[q][m] = sum_k Wt[k][m] * lat[q][k]                       (vq.py:135, 1x1 conv, no bias)
+//   level:  idx = argmin_j (|c_j|^2 - 2 res.c_j)  (first minimum on ties)   (core_vq.py:270-276)
+//           res -= c_idx                                                   (core_vq.py:514-516)
+// cbT is the transposed codebook [level][dim][bins] (coalesced over codes), cb the row-major one.
+struct RvqEncArgs {
+  const float* lat; long long lb, lc, lt; int n_frames;    // latent [B][Cin][n]
+  const float* wT[2];        // [Cin][Dq]
+  const float* cbT[2];       // [levels][Dq][bins]
+  const float* cb[2];        // [levels][bins][Dq]
+  const float* cnorm[2];     // [levels][bins]   |c|^2
+  int levels[2];
+  int level_offset[2];       // first output codebook index
+  long long* codes; long long cs_b, cs_k, cs_f;   // code strides (batch, level, frame)
+  int n_query, Cin, Dq, bins;
+};
+
+static __global__ void __launch_bounds__(RVQ_THREADS) rvq_encode_kernel(const RvqEncArgs a) {
+  extern __shared__ float sm[];
+  const int which = blockIdx.y;
+  if (a.levels[which] <= 0) return;
+  const int q0 = blockIdx.x * RVQ_Q;
+  const int tid = threadIdx.x;
+  float* s_lat = sm;                         // [RVQ_Q][Cin]
+  float* s_res = sm + RVQ_Q * a.Cin;         // [RVQ_Q][Dq]
+  __shared__ float s_best[RVQ_Q][RVQ_THREADS / 32];
+  __shared__ int s_bidx[RVQ_Q][RVQ_THREADS / 32];
+  __shared__ int s_choice[RVQ_Q];
+
+  for (int i = tid; i < RVQ_Q * a.Cin; i += RVQ_THREADS) {
+    const int q = i / a.Cin, c = i % a.Cin;
+    const int qi = q0 + q;
+    float v = 0.f;
+    if (qi < a.n_query) {
+      const int b = qi / a.n_frames, f = qi % a.n_frames;
+      v = a.lat[b * a.lb + c * a.lc + f * a.lt];
+    }
+    s_lat[i] = v;
+  }
+  __syncthreads();
+  for (int m = tid; m < a.Dq; m += RVQ_THREADS) {
+    float acc[RVQ_Q];
+#pragma unroll
+    for (int q = 0; q < RVQ_Q; ++q) acc[q] = 0.f;
+    const float* w = a.wT[which] + m;
+    for (int k = 0; k < a.Cin; ++k) {
+      const float wv = w[(long long)k * a.Dq];
+#pragma unroll
+      for (int q = 0; q < RVQ_Q; ++q) acc[q] = fmaf(wv, s_lat[q * a.Cin + k], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < RVQ_Q; ++q) s_res[q * a.Dq + m] = acc[q];
+  }
+  __syncthreads();
+
+  const int per_thread = (a.bins + RVQ_THREADS - 1) / RVQ_THREADS;   // <= 8 (bins <= 2048)
+  for (int level = 0; level < a.levels[which]; ++level) {
+    const float* cbT = a.cbT[which] + (long long)level * a.Dq * a.bins;
+    const float* cn = a.cnorm[which] + (long long)level * a.bins;
+    float dots[8][RVQ_Q];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < RVQ_Q; ++q) dots[j][q] = 0.f;
+    for (int d = 0; d < a.Dq; ++d) {
+      float xs[RVQ_Q];
+#pragma unroll
+      for (int q = 0; q < RVQ_Q; ++q) xs[q] = s_res[q * a.Dq + d];
+      const float* row = cbT + (long long)d * a.bins;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < per_thread) {
+          const int code = tid + j * RVQ_THREADS;
+          const float cv = code < a.bins ? row[code] : 0.f;
+#pragma unroll
+          for (int q = 0; q < RVQ_Q; ++q) dots[j][q] = fmaf(cv, xs[q], dots[j][q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RVQ_Q; ++q) {
+      float best = INFINITY;
+      int bidx = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < per_thread) {
+          const int code = tid + j * RVQ_THREADS;
+          if (code < a.bins) {
+            const float s = cn[code] - 2.f * dots[j][q];
+            if (s < best) { best = s; bidx = code; }      // ascending code order: first min wins
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+      if ((tid & 31) == 0) { s_best[q][tid >> 5] = best; s_bidx[q][tid >> 5] = bidx; }
+    }
+    __syncthreads();
+    if (tid < RVQ_Q) {
+      float best = s_best[tid][0];
+      int bidx = s_bidx[tid][0];
+      for (int w = 1; w < RVQ_THREADS / 32; ++w) {
+        const float ob = s_best[tid][w];
+        const int oi = s_bidx[tid][w];
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+      s_choice[tid] = bidx;
+      const int qi = q0 + tid;
+      if (qi < a.n_query) {
+        const int b = qi / a.n_frames, f = qi % a.n_frames;
+        a.codes[b * a.cs_b + (a.level_offset[which] + level) * a.cs_k + f * a.cs_f] = bidx;
+      }
+    }
+    __syncthreads();
+    const float* cb = a.cb[which] + (long long)level * a.bins * a.Dq;
+    for (int i = tid; i < RVQ_Q * a.Dq; i += RVQ_THREADS) {
+      const int q = i / a.Dq, d = i % a.Dq;
+      s_res[i] -= cb[(long long)s_choice[q] * a.Dq + d];
+    }
+    __syncthreads();
+  }
+}
+
+// codes [B][K][n] -> latent (vq.py:281-287): out = Wo_first . c0[idx0] + Wo_rest . sum_l c_l[idx_l]
+struct RvqDecArgs {
+  const long long* codes; long long cs_b, cs_k, cs_f; int n_frames;
+  const float* cb[2]; const float* woT[2];   // woT [Dq][Cout]
+  int levels[2]; int level_offset[2];
+  float* out; long long ob, oc, ot;          // [B][Cout][n] via strides
+  int Dq, Cout, bins;
+};
+static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs a) {
+  extern __shared__ float sm[];              // [2][Dq]
+  const int b = blockIdx.x / a.n_frames, f = blockIdx.x % a.n_frames;
+  const int tid = threadIdx.x;
+  for (int which = 0; which < 2; ++which) {
+    for (int d = tid; d < a.Dq; d += blockDim.x) {
+      float s = 0.f;
+      for (int level = 0; level < a.levels[which]; ++level) {
+        const long long idx = a.codes[b * a.cs_b + (a.level_offset[which] + level) * a.cs_k + f * a.cs_f];
+        s += a.cb[which][((long long)level * a.bins + idx) * a.Dq + d];
+      }
+      sm[which * a.Dq + d] = s;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.Cout; c += blockDim.x) {
+    float acc0 = 0.f, acc1 = 0.f;
+    if (a.levels[0] > 0)
+      for (int d = 0; d < a.Dq; ++d) acc0 = fmaf(a.woT[0][(long long)d * a.Cout + c], sm[d], acc0);
+    if (a.levels[1] > 0)
+      for (int d = 0; d < a.Dq; ++d) acc1 = fmaf(a.woT[1][(long long)d * a.Cout + c], sm[a.Dq + d], acc1);
+    a.out[b * a.ob + c * a.oc + f * a.ot] = acc0 + acc1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// load-time repacking
+// ---------------------------------------------------------------------------------------------
+static __global__ void pack_conv_w_kernel(const float* w /*[Cout][Cin][K]*/, float* out /*[Cout][K*Cin]*/, int Cout, int Cin, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * K) return;
+  const int kw = i % K; long long r = i / K;
+  const int ci = r % Cin; const int co = r / Cin;
+  out[((long long)co * K + kw) * Cin + ci] = w[i];
+}
+static __global__ void pack_convtr_w_kernel(const float* w /*[Cin][Cout][2S]*/, float* out /*[Cout*S][2*Cin]*/, int Cin, int Cout, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cin * Cout * 2 * S) return;
+  const int k = i % (2 * S); long long r = i / (2 * S);
+  const int co = r % Cout; const int ci = r / Cout;
+  const int tap = k / S, ph = k % S;
+  out[((long long)co * S + ph) * (2 * Cin) + (long long)tap * Cin + ci] = w[i];
+}
+static __global__ void transpose_kernel(const float* in /*[R][C]*/, float* out /*[C][R]*/, int R, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * C) return;
+  const int c = i % C; const int r = i / C;
+  out[(long long)c * R + r] = in[i];
+}
+// centroids = embedding_sum / clamp(cluster_usage, 1e-5)  (core_vq.py:181-183) + transposed copy + norms
+static __global__ void build_codebook_kernel(const float* esum, const float* usage, float* cb, float* cbT, float* cnorm,
+                                      int bins, int Dq) {
+  const int code = blockIdx.x;
+  const float u = fmaxf(usage[code], 1e-5f);
+  float s = 0.f;
+  for (int d = threadIdx.x; d < Dq; d += blockDim.x) {
+    const float v = esum[(long long)code * Dq + d] / u;
+    cb[(long long)code * Dq + d] = v;
+    cbT[(long long)d * bins + code] = v;
+    s += v * v;
+  }
+  __shared__ float red[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    cnorm[code] = t;
+  }
+}
+
+}  // namespace mimi
+}  // namespace b200

@@ -1,0 +1,109 @@
+// Kernel-level C entry points used by the parity tests (same kernels the handles launch).
+#include "gemm_tc.cuh"
+#include "lm_kernels.cuh"
+#include "mimi_kernels.cuh"
+
+using namespace b200;
+
+extern "C" {
+
+int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K, int impl, void* stream) {
+  using namespace b200::lm;
+  if (!x_dev || !w_dev || !y_dev || M < 1 || N < 1 || K < 8 || K % 8) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16* x = static_cast<const bf16*>(x_dev);
+  const bf16* w = static_cast<const bf16*>(w_dev);
+  bf16* y = static_cast<bf16*>(y_dev);
+  if (impl == 0) impl = tc::supported(M, N, K, LIN_STORE) ? 2 : 1;
+  if (impl == 2) {
+    static tc::GemmPlanCache cache;
+    if (!tc::supported(M, N, K, LIN_STORE)) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: shape unsupported by the tcgen05 kernel");
+    return tc::linear(cache, x, K, w, y, N, nullptr, 0, M, N, K, LIN_STORE, 0, st);
+  }
+  auto k = linear_simt_kernel<LIN_STORE>;
+  B200_LAUNCH(k, ceil_div(N * 32, 256), 256, 0, st, x, (long long)K, w, y, (long long)N, (const bf16*)nullptr, 0LL, M, N, K, 0);
+  return check_launch("op_linear_bf16");
+}
+
+int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,
+                   const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T, int K, int stride,
+                   int dilation, int elu_in, void* stream) {
+  using namespace b200::mimi;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int keff = (K - 1) * dilation + 1, P = keff - stride;
+  if (T % stride || P < 0) B200_FAIL(B200_ERR_SHAPE, "op_conv1d: T %% stride != 0");
+  float* wp = nullptr;
+  ConvCommit* desc = nullptr;
+  B200_CUDA(cudaMalloc(&wp, (size_t)Cout * Cin * K * 4));
+  const long long n = (long long)Cout * Cin * K;
+  B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, st, w_dev, wp, Cout, Cin, K);
+  ConvP p;
+  p.x = x_dev; p.xb = (long long)Cin * T; p.xc = T; p.xt = 1; p.Tin = T;
+  p.st = prev_dev; p.P = P; p.first = nullptr; p.w = wp; p.bias = bias_dev;
+  p.y = y_dev; p.yb = (long long)Cout * (T / stride); p.yc = T / stride; p.yt = 1;
+  p.res = nullptr; p.rb = p.rc = p.rt = 0;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.K = K; p.stride = stride; p.dil = dilation; p.Tout = T / stride; p.elu_in = elu_in;
+  p.M = Cout; p.N = B * (T / stride); p.Kd = Cin * K; p.cin_aligned = (Cin % BK) == 0;
+  auto kern = igemm_f32_kernel<ConvP, false>;
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+  B200_LAUNCH(kern, grid, 256, 0, st, p);
+  if (P > 0) {
+    ConvCommit cc;
+    cc.x = x_dev; cc.xb = p.xb; cc.xc = p.xc; cc.xt = 1; cc.Tin = T; cc.st = prev_dev; cc.P = P; cc.Cin = Cin;
+    cc.elu_in = elu_in; cc.first = nullptr;
+    B200_CUDA(cudaMalloc(&desc, sizeof(ConvCommit)));
+    B200_CUDA(cudaMemcpyAsync(desc, &cc, sizeof(cc), cudaMemcpyHostToDevice, st));
+    dim3 g2(ceil_div(B * Cin, 128), 1);
+    B200_LAUNCH(conv_commit_kernel, g2, 128, 0, st, desc, 1, exec_mask_dev, B);
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  cudaFree(wp);
+  if (desc) cudaFree(desc);
+  return check_launch("op_conv1d");
+}
+
+int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
+                     const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T, int K, int stride,
+                     int elu_in, void* stream) {
+  using namespace b200::mimi;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (K != 2 * stride) B200_FAIL(B200_ERR_SHAPE, "op_convtr1d: kernel must be 2*stride");
+  float *wp = nullptr, *scratch = nullptr;
+  ConvTrCommit* desc = nullptr;
+  const long long n = (long long)Cin * Cout * K;
+  B200_CUDA(cudaMalloc(&wp, n * 4));
+  B200_CUDA(cudaMalloc(&scratch, (size_t)B * Cout * stride * 4));
+  B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, st, w_dev, wp, Cin, Cout, stride);
+  ConvTrP p;
+  p.x = x_dev; p.xb = (long long)Cin * T; p.xc = T; p.xt = 1; p.T = T;
+  p.partial = partial_dev; p.scratch = scratch; p.w = wp; p.bias = bias_dev;
+  p.y = y_dev; p.yb = (long long)Cout * T * stride; p.yc = (long long)T * stride; p.yt = 1;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.S = stride; p.elu_in = elu_in;
+  p.M = Cout * stride; p.N = B * (T + 1); p.Kd = 2 * Cin; p.cin_aligned = (Cin % BK) == 0;
+  auto kern = igemm_f32_kernel<ConvTrP, false>;
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+  B200_LAUNCH(kern, grid, 256, 0, st, p);
+  ConvTrCommit tc_;
+  tc_.partial = partial_dev; tc_.scratch = scratch; tc_.per_row = Cout * stride;
+  B200_CUDA(cudaMalloc(&desc, sizeof(ConvTrCommit)));
+  B200_CUDA(cudaMemcpyAsync(desc, &tc_, sizeof(tc_), cudaMemcpyHostToDevice, st));
+  dim3 g2((unsigned)ceil_div64((long long)B * tc_.per_row, 256), 1);
+  B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, st, desc, exec_mask_dev, B);
+  B200_CUDA(cudaStreamSynchronize(st));
+  cudaFree(wp);
+  cudaFree(scratch);
+  cudaFree(desc);
+  return check_launch("op_convtr1d");
+}
+
+int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B, int card,
+                   int use_sampling, float temp, int top_k, void* stream) {
+  using namespace b200::lm;
+  if (card + 1 > 65535 || top_k < 1 || top_k > SAMPLE_MAX_K) B200_FAIL(B200_ERR_SHAPE, "op_sample: bad card/top_k");
+  const int k = top_k < card ? top_k : card;
+  B200_LAUNCH(sample_kernel, B, SAMPLE_THREADS, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(logits_bf16_dev),
+              (long long)card, noise_dev, (long long)k, reinterpret_cast<long long*>(out_dev), card, use_sampling, temp, top_k);
+  return check_launch("op_sample");
+}
+
+}  // extern "C"

@@ -47,6 +47,7 @@ class MimiOracle:
         self._centroid_cache: dict[str, torch.Tensor] = {}
         self._plan()
         self.batch: int | None = None
+        self.trace: dict[str, torch.Tensor] | None = None   # set to {} to record per-module outputs
 
     # ------------------------------------------------------------------ structure
     def _plan(self) -> None:
@@ -174,11 +175,16 @@ class MimiOracle:
                 h = self._conv(ConvSpec(base + ".block.1.conv.conv", "conv", dilation=dil), F.elu(x))
                 h = self._conv(ConvSpec(base + ".block.3.conv.conv", "conv"), F.elu(h))
                 x = x + h
+                name = base
             else:
                 spec = item[1]
                 if spec.elu_before:
                     x = F.elu(x)
                 x = self._conv(spec, x) if spec.kind == "conv" else self._convtr(spec, x)
+                name = spec.key
+            if self.trace is not None:   # "encoder.model.3.conv.conv" -> "enc.3"
+                side, _, idx = name.split(".")[:3]
+                self.trace[f"{side[:3]}.{idx}"] = x
         return x
 
     # ------------------------------------------------------------------ quantizer
@@ -252,14 +258,22 @@ class MimiOracle:
             raise RuntimeError(f"Invalid input x of length {pcm.shape[-1]}.")
         emb = self._run(self.enc_plan, pcm)
         emb = self._transformer("encoder_transformer", self.enc_tr, emb)
-        return self._conv(self.down_spec, emb)
+        lat = self._conv(self.down_spec, emb)
+        if self.trace is not None:
+            self.trace["enc.tr"] = emb
+            self.trace["enc.latent"] = lat
+        return lat
 
     def encode(self, pcm: torch.Tensor) -> torch.Tensor:
         return self.quantize(self.encode_to_latent(pcm))
 
     def decode_latent(self, latent: torch.Tensor) -> torch.Tensor:
-        emb = self._convtr(self.up_spec, latent)
-        emb = self._transformer("decoder_transformer", self.dec_tr, emb)
+        up = self._convtr(self.up_spec, latent)
+        emb = self._transformer("decoder_transformer", self.dec_tr, up)
+        if self.trace is not None:
+            self.trace["dec.latent"] = latent
+            self.trace["dec.up"] = up
+            self.trace["dec.tr"] = emb
         return self._run(self.dec_plan, emb)
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,149 @@
+"""GPU: kernel-level parity through the C ABI (the same kernels the handles launch)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import cptr, stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from moshi_b200 import _lib
+    return _lib.lib()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(1, 512, 256), (3, 1024, 4096), (8, 12288, 4096), (17, 4096, 11264),
+                                   (96, 4096, 4096), (128, 2048, 1024), (200, 1024, 2816)])
+def test_linear_bf16(lib, impl, M, N, K):
+    from moshi_b200 import _lib
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    y = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    rc = lib.b200_op_linear_bf16(cptr(x), cptr(w), cptr(y), M, N, K, impl, _stream())
+    if impl == 2 and rc != 0:
+        pytest.skip("tcgen05 path does not cover this shape: " + lib.b200_last_error().decode())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    want = (x.float() @ w.float().t())
+    print(stats(f"linear impl={impl} {M}x{N}x{K}", y, want))
+    # bf16 output rounding: half an ulp of the result plus fp32 accumulation-order noise
+    torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=2e-2)
+    # exactness up to one bf16 ulp for almost all entries
+    ulp_off = ((y.float() - want.bfloat16().float()).abs() > 0).float().mean().item()
+    assert ulp_off < 0.05, ulp_off
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,elu", [(1, 64, 7, 1, 1, 0), (64, 32, 3, 1, 1, 1), (32, 64, 1, 1, 1, 1),
+                                                       (64, 128, 8, 4, 1, 1), (128, 64, 3, 1, 2, 1), (512, 1024, 16, 8, 1, 1),
+                                                       (20, 24, 4, 2, 1, 0)])
+def test_streaming_conv1d_matches_batch_conv(lib, cin, cout, k, stride, dil, elu):
+    """conv_test.py:63-110 pattern: chunked streaming == one causal convolution over the whole signal."""
+    from moshi_b200 import _lib
+    torch.manual_seed(41)
+    B, chunks, T = 3, 4, 8 * stride
+    keff = (k - 1) * dil + 1
+    P = keff - stride
+    x = torch.randn(B, cin, chunks * T)
+    w = torch.randn(cout, cin, k) / (cin * k) ** 0.5
+    bias = torch.randn(cout)
+    xin = F.elu(x) if elu else x
+    want = F.conv1d(F.pad(xin, (P, 0)), w, bias, stride=stride, dilation=dil)
+    prev = torch.zeros(B, cin, max(P, 1), device="cuda")
+    mask = torch.ones(B, dtype=torch.bool, device="cuda")
+    outs = []
+    for c in range(chunks):
+        xc = x[..., c * T:(c + 1) * T].contiguous().cuda()
+        y = torch.empty(B, cout, T // stride, device="cuda")
+        _lib.check(lib.b200_op_conv1d(cptr(xc), cptr(w.cuda()), cptr(bias.cuda()), cptr(prev), cptr(mask), cptr(y),
+                                      B, cin, cout, T, k, stride, dil, elu, _stream()))
+        outs.append(y.cpu())
+    got = torch.cat(outs, -1)
+    print(stats(f"conv1d {cin}->{cout} k{k} s{stride} d{dil}", got, want))
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_streaming_conv1d_exec_mask_freezes_state(lib):
+    from moshi_b200 import _lib
+    torch.manual_seed(0)
+    B, cin, cout, k, T = 2, 16, 16, 3, 8
+    w, bias = torch.randn(cout, cin, k).cuda(), torch.randn(cout).cuda()
+    prev = torch.randn(B, cin, k - 1, device="cuda")
+    before = prev.clone()
+    mask = torch.tensor([True, False], device="cuda")
+    x = torch.randn(B, cin, T, device="cuda")
+    y = torch.empty(B, cout, T, device="cuda")
+    _lib.check(lib.b200_op_conv1d(cptr(x), cptr(w), cptr(bias), cptr(prev), cptr(mask), cptr(y), B, cin, cout, T, k, 1, 1, 0,
+                                  _stream()))
+    assert torch.equal(prev[1], before[1])
+    assert torch.equal(prev[0], x[0, :, -2:])
+
+
+@pytest.mark.parametrize("cin,cout,stride,elu", [(64, 32, 4, 1), (1024, 512, 8, 1), (32, 16, 5, 0)])
+def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
+    from moshi_b200 import _lib
+    torch.manual_seed(41)
+    B, chunks, T, k = 2, 3, 3, 2 * stride
+    x = torch.randn(B, cin, chunks * T)
+    w = torch.randn(cin, cout, k) / (2 * cin) ** 0.5
+    bias = torch.randn(cout)
+    xin = F.elu(x) if elu else x
+    want = F.conv_transpose1d(xin, w, bias, stride=stride)[..., :chunks * T * stride]
+    partial = torch.zeros(B, cout, stride, device="cuda")
+    mask = torch.ones(B, dtype=torch.bool, device="cuda")
+    outs = []
+    for c in range(chunks):
+        xc = x[..., c * T:(c + 1) * T].contiguous().cuda()
+        y = torch.empty(B, cout, T * stride, device="cuda")
+        _lib.check(lib.b200_op_convtr1d(cptr(xc), cptr(w.cuda()), cptr(bias.cuda()), cptr(partial), cptr(mask), cptr(y),
+                                        B, cin, cout, T, k, stride, elu, _stream()))
+        outs.append(y.cpu())
+    got = torch.cat(outs, -1)
+    print(stats(f"convtr {cin}->{cout} s{stride}", got, want))
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("card,k,temp", [(2048, 250, 0.8), (32000, 25, 0.7), (64, 250, 0.8), (500, 25, 0.7)])
+def test_sampler_matches_oracle(lib, card, k, temp):
+    """sample_token with shared Exp(1) noise; logits are made tie-free so that ranks are unambiguous."""
+    from moshi_b200 import _lib
+    from oracle.lm import sample_token
+    torch.manual_seed(3)
+    B = 33
+    # distinct bf16 values per row: a random permutation of an exactly-representable grid
+    grid = (torch.arange(card, dtype=torch.float32) - card / 2) * (2.0 ** -5 if card <= 4096 else 2.0 ** -9)
+    grid = grid.bfloat16()
+    assert grid.unique().numel() == card
+    logits = torch.stack([grid[torch.randperm(card)] for _ in range(B)])
+    kk = min(k, card)
+    noise = torch.empty(B, kk).exponential_(1)
+    want = sample_token(logits.float()[:, None, None, :], True, temp, k, noise)[:, 0, 0]
+    out = torch.empty(B, dtype=torch.int64, device="cuda")
+    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), cptr(noise.cuda()), cptr(out), B, card, 1, temp, k, _stream()))
+    torch.cuda.synchronize()
+    agree = (out.cpu() == want).float().mean().item()
+    print(f"sampler card={card} k={k}: agreement {agree:.3f}")
+    assert agree == 1.0
+    # greedy
+    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), None, cptr(out), B, card, 0, temp, k, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), logits.float().argmax(-1))
+
+
+def test_sampler_ties_pick_lowest_index(lib):
+    from moshi_b200 import _lib
+    logits = torch.zeros(2, 100).bfloat16()
+    logits[1, 40:] = 1.0
+    out = torch.empty(2, dtype=torch.int64, device="cuda")
+    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), None, cptr(out), 2, 100, 0, 1.0, 5, _stream()))
+    torch.cuda.synchronize()
+    assert out.tolist() == [0, 40]
