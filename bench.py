@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: concurrent real-time Moshi dialogue sessions per box at <= 80 ms per 12.5 Hz step.
+
+One *step* = one 80 ms frame for every session a GPU owns, through the reference-shaped API:
+``MimiModel.encode`` (user PCM -> 8 codes) -> ``LMGen.step`` (Moshi 7B bf16 Temporal + Depth
+transformers, sampling) -> ``MimiModel.decode`` (8 codes -> PCM).  Sessions are the batch axis;
+with N GPUs every rank runs a replica with its own shard of sessions (no data-path collective),
+so scaling is weak and ``value`` sums the sessions of all ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--sessions B_per_gpu]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("NO_TORCH_COMPILE", "1")
+
+import torch  # noqa: E402
+
+METRIC = "concurrent real-time sessions @ <=80 ms/step (Mimi encode + Moshi 7B LMGen.step + Mimi decode)"
+FRAME_MS = 80.0
+KV_BYTES_PER_SESSION_STEP = 524288      # 32 layers x 2 x 4096 x bf16 per cached position
+
+
+def sessions_sustained(total_sessions: float, ms_per_step: float) -> float:
+    """Sessions served in real time: all of them if the step fits the 80 ms frame, else the
+    fraction that would (a step that takes 160 ms keeps half as many sessions real-time)."""
+    return total_sessions if ms_per_step <= FRAME_MS else total_sessions * FRAME_MS / ms_per_step
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path on the host cores
+# ---------------------------------------------------------------------------------------------
+def _tiled_random_lm_state_dict(cfg, seed: int = 7):
+    """7.7 B bf16 parameters filled from one random 32 Mi-element block (timing only needs realistic,
+    non-denormal values; drawing 7.7 G independent values on the CPU would take minutes)."""
+    from moshi_b200.synth import lm_tensor_specs
+    g = torch.Generator().manual_seed(seed)
+    block = (torch.rand(1 << 25, generator=g) - 0.5).mul_(0.04).bfloat16()
+    sd = {}
+    for key, shape, fan_in in lm_tensor_specs(cfg):
+        n = 1
+        for s in shape:
+            n *= s
+        if fan_in == 0:
+            sd[key] = torch.ones(shape, dtype=torch.bfloat16)
+            continue
+        t = torch.empty(n, dtype=torch.bfloat16)
+        for o in range(0, n, block.numel()):
+            m = min(block.numel(), n - o)
+            t[o:o + m] = block[:m]
+        sd[key] = t.view(shape)
+    return sd
+
+
+def run_cpu_pipeline(steps: int, warmup: int, threads: int | None = None) -> dict:
+    from moshi_b200.config import MOSHI_7B, MimiConfig
+    from moshi_b200.synth import synth_mimi_state_dict
+    from oracle.lm import LMOracle, LMSpec
+    from oracle.mimi import MimiOracle
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mcfg = MimiConfig()
+    mimi = MimiOracle(synth_mimi_state_dict(mcfg, seed=1234), mcfg)
+    lm = LMOracle(_tiled_random_lm_state_dict(MOSHI_7B), LMSpec.from_config(MOSHI_7B))
+    mimi.streaming(1)
+    lm.streaming(1)
+    g = torch.Generator().manual_seed(4242)
+    times, parts = [], []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            pcm = 0.1 * torch.randn(1, 1, 1920, generator=g)
+            t0 = time.perf_counter()
+            codes = mimi.encode(pcm)
+            t1 = time.perf_counter()
+            out = lm.step(codes)
+            t2 = time.perf_counter()
+            audio = torch.zeros(1, 8, 1, dtype=torch.long) if out is None else out[:, 1:].clamp(min=0)
+            mimi.decode(audio)
+            t3 = time.perf_counter()
+            if i >= warmup:
+                times.append((t3 - t0) * 1e3)
+                parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+    ms = sum(times) / len(times)
+    return {"ms_per_step": ms, "cores": cores, "sessions": sessions_sustained(1.0, ms),
+            "mimi_encode_ms": sum(p[0] for p in parts) / len(parts), "lm_step_ms": sum(p[1] for p in parts) / len(parts),
+            "mimi_decode_ms": sum(p[2] for p in parts) / len(parts)}
+
+
+def reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu_pipeline(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["sessions"], "unit": "sessions", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Mimi streaming encode -> Moshi 7B bf16 LMGen.step -> Mimi decode, 1 session on the host cores",
+                   "sessions_per_gpu": 1, "kv_fill": "growing from 0"},
+        "cpu_baseline": {"value": r["sessions"], "unit": "sessions", "cores": r["cores"], "kind": "port",
+                         "sample": f"{args.steps} frames of 1 session (oracle port of the reference PyTorch path, "
+                                   "random block-tiled 7B weights)"},
+        "e2e": {"value": r["sessions"], "unit": "sessions", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "breakdown_ms": {k: r[k] for k in ("mimi_encode_ms", "lm_step_ms", "mimi_decode_ms")},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def _peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _dominant_kernel_roofline(lm, B: int, device) -> dict:
+    """The temporal linear_in GEMM (22528 x 4096 weights, 184.5 MB > L2) timed alone with CUDA events,
+    an L2 flush (256 MiB memset) between launches."""
+    import ctypes as C
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    N, K, M = 22528, 4096, B
+    w = torch.empty(N, K, device=device, dtype=torch.bfloat16).uniform_(-0.02, 0.02)
+    x = torch.empty(M, K, device=device, dtype=torch.bfloat16).uniform_(-1, 1)
+    y = torch.empty(M, N, device=device, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, device=device, dtype=torch.uint8)
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    impl = int(os.environ.get("B200_GEMM_IMPL", "0"))
+    times = []
+    for i in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.b200_op_linear_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), M, N, K, impl, stream))
+        e1.record()
+        torch.cuda.synchronize(device)
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    alg = N * K * 2 + M * K * 2 + M * N * 2
+    peak, src = _peaks()
+    gbs = alg / (ms * 1e-3) / 1e9
+    return {"kernel": "LM linear (gating.linear_in 22528x4096 bf16, M=%d)" % M, "bound": "hbm", "achieved": gbs,
+            "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "ms_per_launch": ms, "algorithmic_bytes": alg}
+
+
+def b200_arm(args) -> None:
+    from moshi_b200 import _lib
+    from moshi_b200.config import MOSHI_7B
+    from moshi_b200.models import LMGen, loaders
+    from moshi_b200.serving import barrier, init_distributed, max_over_ranks, sum_over_ranks
+
+    rank, world = init_distributed()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    lib = _lib.lib()
+
+    mimi = loaders.get_mimi(None, device=device, num_codebooks=8)
+    lm = loaders.get_moshi_lm(None, MOSHI_7B.to_reference_kwargs(), device=device, synth_device=device)
+    torch.cuda.synchronize(device)
+
+    # sessions per GPU: the full-context bf16 KV ring (1.573 GB/session) is what bounds it
+    free, total = torch.cuda.mem_get_info(device)
+    per_session = KV_BYTES_PER_SESSION_STEP * MOSHI_7B.context + 40e6
+    cap = int((free - 8e9) // per_session)
+    B = max(1, min(args.sessions or 96, cap))
+    kv_fill = MOSHI_7B.context if args.kv_fill < 0 else min(args.kv_fill, MOSHI_7B.context)
+
+    gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
+    mimi.streaming_forever(B)
+    gen.streaming_forever(B)
+    gen.assume_fill(kv_fill)      # steady state: every session already holds `kv_fill` frames of history
+
+    g = torch.Generator().manual_seed(4242 + rank)
+    n_buf = 4
+    pcm_host = [(0.1 * torch.randn(B, 1, 1920, generator=g)).pin_memory() for _ in range(n_buf)]
+    pcm_dev = [p.to(device) for p in pcm_host]
+    out_pcm_host = torch.empty(B, 1, 1920).pin_memory()
+    out_tok_host = torch.empty(B, 9, 1, dtype=torch.int64).pin_memory()
+    lm_ev = []
+
+    def frame(pcm, timed_lm: bool = False):
+        codes = mimi.encode(pcm)
+        if timed_lm:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        toks = gen.step(codes)
+        if timed_lm:
+            b.record()
+            lm_ev.append((a, b))
+        audio = toks[:, 1:].clamp(min=0) if toks is not None else torch.zeros(B, 8, 1, dtype=torch.int64, device=device)
+        return toks, mimi.decode(audio)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            frame(pcm_dev[i % n_buf])
+        torch.cuda.synchronize(device)
+
+        # ---- device-resident inputs: `value` --------------------------------------------------
+        launches0 = lib.b200_launch_count()
+        barrier()
+        torch.cuda.synchronize(device)
+        with ClockSampler(local) as clocks:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                frame(pcm_dev[i % n_buf], timed_lm=True)
+            e1.record()
+            torch.cuda.synchronize(device)
+            barrier()
+        launches = lib.b200_launch_count() - launches0
+        ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        lm_ms = sum(a.elapsed_time(b) for a, b in lm_ev) / len(lm_ev)
+
+        # ---- end to end: host PCM in, host PCM + tokens out, every step ------------------------
+        barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pcm = pcm_host[i % n_buf].to(device, non_blocking=True)
+            toks, out = frame(pcm)
+            out_pcm_host.copy_(out, non_blocking=True)
+            if toks is not None:
+                out_tok_host.copy_(toks, non_blocking=True)
+            torch.cuda.synchronize(device)
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    total_sessions = sum_over_ranks(float(B))
+    value = sessions_sustained(total_sessions, ms_dev)
+    e2e_value = sessions_sustained(total_sessions, ms_e2e)
+    lm_bytes = gen.algorithmic_bytes(kv_fill)
+    mimi_bytes = mimi.algorithmic_bytes()
+    peak, peak_src = _peaks()
+    roof = _dominant_kernel_roofline(lm, B, device) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        r = run_cpu_pipeline(steps=3, warmup=1)
+        cpu = {"value": r["sessions"], "unit": "sessions", "cores": r["cores"], "kind": "port",
+               "sample": "3 frames of 1 session (Mimi enc + Moshi 7B LMGen.step + Mimi dec) after 1 warm-up; oracle port "
+                         "of the reference PyTorch path, random block-tiled 7B weights",
+               "ms_per_step": r["ms_per_step"]}
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Mimi streaming encode (8 codebooks) -> Moshi 7B bf16 LMGen.step (temp 0.8/0.7, top-k 250/25) "
+                               "-> Mimi streaming decode; one 80 ms frame for every session per step",
+                   "sessions_per_gpu": B, "sessions_total": total_sessions, "kv_fill": kv_fill,
+                   "kv_ring": "bf16, capacity 3000 (reference context)", "parallelism": f"replicas x{world}",
+                   "l2": "inputs larger than L2 (15.4 GB of weights + KV ring streamed every step)",
+                   "frames_per_s": total_sessions * 1e3 / ms_dev},
+        "e2e": {"value": e2e_value, "unit": "sessions", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 1920 * 4,
+                "d2h_bytes_per_step": B * 1920 * 4 + B * 9 * 8},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "lm_step": {"ms": lm_ms, "algorithmic_bytes": lm_bytes, "achieved_gbs": lm_bytes / (lm_ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": lm_bytes / (lm_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src},
+        "mimi": {"algorithmic_bytes": mimi_bytes, "ms_encode_plus_decode": ms_dev - lm_ms,
+                 "frames_per_s_per_gpu": B * 1e3 / max(ms_dev - lm_ms, 1e-6)},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: 96 or what the KV ring allows)")
+    ap.add_argument("--kv-fill", type=int, default=-1, help="frames of history per session (default: full ring)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

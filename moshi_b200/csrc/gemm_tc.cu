@@ -1,0 +1,328 @@
+// tcgen05 / TMA weight-streaming GEMM (see gemm_tc.cuh).  Hand-written PTX: TMA tensor-map loads
+// into SWIZZLE_128B shared-memory stages, single-thread tcgen05.mma issue with the accumulator in
+// TMEM, mbarrier producer/consumer pipeline, tcgen05.ld epilogue.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+#include "gemm_tc.cuh"
+
+namespace b200 {
+namespace tc {
+
+constexpr int EPI_STORE = 0, EPI_RESADD = 1, EPI_GATE = 2;   // == lm::LIN_*
+constexpr int BLOCK_ROWS = 128;    // weight rows per CTA = UMMA M
+constexpr int BLOCK_K = 64;        // bf16 per k-block = 128 B = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_ROWS * BLOCK_K * 2;   // 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct Params {
+  int M, N, K, Mpad, gate_rows, stages, num_kb;
+  __nv_bfloat16* y; long long ldy;
+  const __nv_bfloat16* res; long long ldr;
+  uint32_t tmem_cols, stage_bytes, b_tile_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 28)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows x 128 B)
+//   [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bars = base + (uint32_t)p.stages * p.stage_bytes;
+  // barrier block: full[MAX_STAGES], empty[MAX_STAGES], tmem_full, tmem_ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull = bars + 16 * MAX_STAGES;
+  const uint32_t tptr = tfull + 8;
+  uint32_t* tptr_generic = reinterpret_cast<uint32_t*>(smem_raw + (tptr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_ROWS;
+  constexpr int A_TILES = EPI == EPI_GATE ? 2 : 1;
+  const uint32_t a_bytes = A_TILES * A_TILE_BYTES;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr_generic;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+        mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
+        tma_load_2d(sa, &tmap_w, full0 + 8 * s, kb * BLOCK_K, n0);
+        if (EPI == EPI_GATE) tma_load_2d(sa + A_TILE_BYTES, &tmap_w, full0 + 8 * s, kb * BLOCK_K, p.gate_rows + n0);
+        tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t db = make_desc(sb + k * UMMA_K * 2);
+          const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), db, idesc, acc);
+          if (EPI == EPI_GATE) umma_bf16(tmem_base + (uint32_t)p.Mpad, make_desc(sa + A_TILE_BYTES + k * UMMA_K * 2), db, idesc, acc);
+        }
+        umma_commit(empty0 + 8 * s);           // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tfull);                      // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int n = n0 + row;
+    const bool n_ok = n < (EPI == EPI_GATE ? p.gate_rows : p.N);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(lane_addr + (uint32_t)c0, r0);
+      if (EPI == EPI_GATE) tmem_ld16(lane_addr + (uint32_t)(p.Mpad + c0), r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int m = c0 + j;
+        if (m < p.M && n_ok) {
+          const float a = __uint_as_float(r0[j]);
+          float v;
+          if (EPI == EPI_STORE) v = a;
+          else if (EPI == EPI_RESADD) v = __bfloat162float(p.res[(long long)m * p.ldr + n]) + bf16_round(a);
+          else {
+            const float g = bf16_round(a), u = bf16_round(__uint_as_float(r1[j]));
+            v = bf16_round(g / (1.f + expf(-g))) * u;
+          }
+          p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static bool g_attr_set = false;
+
+static int init_once() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (!g_attr_set) {
+    const int max_smem = 227 * 1024;
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_RESADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    g_attr_set = true;
+  }
+  return B200_OK;
+}
+
+static int get_map(GemmPlanCache& cache, const void* ptr, int rows, int cols, long long ld, int box_rows,
+                   const CUtensorMap** out) {
+  PlanKey key{ptr, ld, rows, cols, box_rows};
+  auto it = cache.maps.find(key);
+  if (it == cache.maps.end()) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%lld", (int)r, rows, cols, ld);
+    it = cache.maps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return B200_OK;
+}
+
+bool supported(int M, int N, int K, int epi) {
+  (void)N; (void)epi;
+  return M >= 1 && M <= 256 && K >= 64 && K % 8 == 0;
+}
+
+int auto_pick(int M, int N, int K, int epi) {
+  (void)M; (void)N; (void)K; (void)epi;
+  return 1;   // flipped to the tcgen05 kernel once its parity test is green on hardware
+}
+
+int prepare_plans(GemmPlanCache&) { return init_once(); }
+
+int linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, __nv_bfloat16* y,
+           long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
+           cudaStream_t stream) {
+  if (!supported(M, N, K, epi) || ldx % 8) B200_FAIL(B200_ERR_SHAPE, "tcgen05 GEMM: unsupported shape M=%d N=%d K=%d", M, N, K);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15)
+    B200_FAIL(B200_ERR_SHAPE, "tcgen05 GEMM: operands must be 16-byte aligned");
+  B200_TRY(init_once());
+  Params p;
+  p.M = M; p.N = N; p.K = K; p.gate_rows = gate_rows;
+  p.Mpad = ((M + 15) / 16) * 16;
+  if (p.Mpad < 16) p.Mpad = 16;
+  p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
+  p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.b_tile_bytes = (uint32_t)p.Mpad * BLOCK_K * 2;
+  const int a_tiles = epi == EPI_GATE ? 2 : 1;
+  p.stage_bytes = (uint32_t)a_tiles * A_TILE_BYTES + p.b_tile_bytes;
+  int stages = SMEM_BUDGET / (int)p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.num_kb) stages = p.num_kb;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  uint32_t cols = (uint32_t)(a_tiles * p.Mpad), pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  const int w_rows = epi == EPI_GATE ? 2 * gate_rows : N;
+  const int out_rows = epi == EPI_GATE ? gate_rows : N;
+  const CUtensorMap *mw = nullptr, *mx = nullptr;
+  B200_TRY(get_map(cache, w, w_rows, K, K, BLOCK_ROWS, &mw));
+  B200_TRY(get_map(cache, x, M, K, ldx, p.Mpad, &mx));
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
+  const int grid = (out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
+  if (epi == EPI_STORE) {
+    gemm_tc_kernel<EPI_STORE><<<grid, NUM_THREADS, smem, stream>>>(*mw, *mx, p);
+  } else if (epi == EPI_RESADD) {
+    gemm_tc_kernel<EPI_RESADD><<<grid, NUM_THREADS, smem, stream>>>(*mw, *mx, p);
+  } else {
+    gemm_tc_kernel<EPI_GATE><<<grid, NUM_THREADS, smem, stream>>>(*mw, *mx, p);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace tc
+}  // namespace b200

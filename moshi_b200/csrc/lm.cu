@@ -27,7 +27,10 @@ struct b200_lm {
   Arena weights, state;
   bool finalized = false;
   int batch = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // caller's stream (inputs/outputs are ordered on it)
+  cudaStream_t gstream = nullptr;      // private stream: graphs cannot be captured on the legacy default stream
+  cudaStream_t body = nullptr;         // stream the step body is currently being enqueued on
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int Kc = 0, max_delay = 0, CT = 0;
   // sampling (LMGen defaults, lm.py:556-571)
   int use_sampling = 1, top_k = 250, top_k_text = 25;
@@ -92,24 +95,24 @@ int noise_per_row(const b200_lm* h) {
 int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, const bf16* res,
            long long ldr, int M, int N, int K, int epi, int gate_rows) {
   int impl = h->gemm_impl;
-  if (impl == 0) impl = tc::supported(M, N, K, epi) ? 2 : 1;
-  if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->stream);
+  if (impl == 0) impl = tc::auto_pick(M, N, K, epi);
+  if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->body);
   const int grid = ceil_div(N * 32, 256);
   if (epi == LIN_STORE) {
     auto k = linear_simt_kernel<LIN_STORE>;
-    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+    B200_LAUNCH(k, grid, 256, 0, h->body, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
   } else if (epi == LIN_RESADD) {
     auto k = linear_simt_kernel<LIN_RESADD>;
-    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+    B200_LAUNCH(k, grid, 256, 0, h->body, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
   } else {
     auto k = linear_simt_kernel<LIN_GATE>;
-    B200_LAUNCH(k, grid, 256, 0, h->stream, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
+    B200_LAUNCH(k, grid, 256, 0, h->body, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
   }
   return check_launch("linear_simt");
 }
 
 int sample(b200_lm* h, const bf16* logits, int card, const float* noise, long long* out, float temp, int top_k) {
-  B200_LAUNCH(sample_kernel, h->batch, SAMPLE_THREADS, 0, h->stream, logits, (long long)card, noise,
+  B200_LAUNCH(sample_kernel, h->batch, SAMPLE_THREADS, 0, h->body, logits, (long long)card, noise,
               (long long)noise_per_row(h), out, card, h->use_sampling, temp, top_k);
   return check_launch("sample");
 }
@@ -127,7 +130,7 @@ int step_body(b200_lm* h) {
   const auto& c = h->cfg;
   const int B = h->batch, d = c.dim, H = c.num_heads, D = d / H, F = c.ffn_hidden;
   const int dd = c.depformer_dim, dH = c.depformer_num_heads, dD = dd / dH, dF = c.depformer_ffn_hidden;
-  cudaStream_t st = h->stream;
+  cudaStream_t st = h->body;
   const float nl = -logf(c.max_period) * 2.f / (float)D;
 
   B200_LAUNCH(lm_prepare_kernel, ceil_div(B * h->Kc, 128), 128, 0, st, ring(h), h->in_codes, h->n_in_static,
@@ -220,6 +223,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   h->max_delay = 0;
   for (int k = 0; k < h->Kc; ++k) h->max_delay = cfg->delays[k] > h->max_delay ? cfg->delays[k] : h->max_delay;
   h->CT = h->max_delay + 2;     // lm.py:606-611
+  if (const char* e = getenv("B200_GEMM_IMPL")) h->gemm_impl = atoi(e);   // 0 auto, 1 SIMT, 2 tcgen05 (debug switch)
   *out = h;
   return B200_OK;
 }
@@ -385,6 +389,9 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   if (ns > ceil_div(c.context, 64)) ns = ceil_div(c.context, 64);
   h->nsplit = ns;
   B200_TRY(A.alloc_t(&h->attn_part, (size_t)B * H * ns * (ATT_D + 2)));
+  B200_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
   B200_CUDA(cudaMallocHost(&h->pin_in, (size_t)B * n_in_max * 8));
   B200_CUDA(cudaMallocHost(&h->pin_out, (size_t)B * (c.dep_q + 1) * 8));
   B200_CUDA(cudaMallocHost(&h->pin_noise, (size_t)B * noise_per_row(h) * 4));
@@ -395,8 +402,15 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
 
 int b200_lm_streaming_end(b200_lm* h) {
   if (!h) return B200_OK;
-  if (h->batch > 0) cudaStreamSynchronize(h->stream);
+  if (h->batch > 0) {
+    cudaStreamSynchronize(h->stream);
+    if (h->gstream) cudaStreamSynchronize(h->gstream);
+  }
   drop_graph(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->plans.clear();
   h->state.free_all();
   if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -442,15 +456,21 @@ static int run_step(b200_lm* h, int n_in) {
     h->n_in_static = n_in;
     drop_graph(h);
   }
-  if (!h->graph_enabled) return step_body(h);
+  B200_TRY(tc::prepare_plans(h->plans));
+  if (!h->graph_enabled) {
+    h->body = h->stream;
+    return step_body(h);
+  }
+  // the step runs on the private stream, fenced against the caller's stream on both sides
+  B200_CUDA(cudaEventRecord(h->ev_in, h->stream));
+  B200_CUDA(cudaStreamWaitEvent(h->gstream, h->ev_in, 0));
   if (!h->graph_exec) {
-    // make sure every lazily-built resource (TMA descriptors) exists before capture
-    B200_TRY(tc::prepare_plans(h->plans));
     cudaGraph_t graph = nullptr;
     const int64_t before = g_launches.load();
-    B200_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->body = h->gstream;
+    B200_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
     const int rc = step_body(h);
-    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
     h->graph_kernels = g_launches.load() - before;
     g_launches.fetch_sub(h->graph_kernels);      // recorded, not executed
     if (rc != B200_OK) {
@@ -462,8 +482,10 @@ static int run_step(b200_lm* h, int n_in) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
   }
-  B200_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
+  B200_CUDA(cudaGraphLaunch(h->graph_exec, h->gstream));
   g_launches.fetch_add(h->graph_kernels);
+  B200_CUDA(cudaEventRecord(h->ev_out, h->gstream));
+  B200_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
   return B200_OK;
 }
 

@@ -14,7 +14,7 @@ int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M
   const bf16* x = static_cast<const bf16*>(x_dev);
   const bf16* w = static_cast<const bf16*>(w_dev);
   bf16* y = static_cast<bf16*>(y_dev);
-  if (impl == 0) impl = tc::supported(M, N, K, LIN_STORE) ? 2 : 1;
+  if (impl == 0) impl = tc::auto_pick(M, N, K, LIN_STORE);
   if (impl == 2) {
     static tc::GemmPlanCache cache;
     if (!tc::supported(M, N, K, LIN_STORE)) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: shape unsupported by the tcgen05 kernel");

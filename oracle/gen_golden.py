@@ -44,7 +44,7 @@ def mimi_fixtures(manifest: dict) -> None:
 
     # --- config 1: 1 s 440 Hz sine, B=1 (BASELINE.json configs[0]) -------------------------
     sine = scenarios.sine_1s()
-    codes_batch = ref.encode(sine)                       # non-streaming: pads to 13 frames
+    codes_batch = ref.encode(scenarios.sine_1s_full())   # non-streaming, 24000 samples: pads to 13 frames
     pcm_batch = ref.decode(codes_batch)
     n = sine.shape[-1] // cfg.frame_size
     cs, ps = [], []

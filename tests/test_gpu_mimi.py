@@ -86,7 +86,8 @@ def test_rvq_kernel_is_exact_on_the_oracle_latent(gpu, sd):
     with gpu.streaming(B):
         codes_g = torch.empty(B, 8, frames, dtype=torch.int64, device="cuda")
         from moshi_b200 import _lib
-        _lib.check(gpu._lib.b200_mimi_quantize(gpu._h, _lib.ptr(lat.cuda().contiguous()), frames, _lib.ptr(codes_g)))
+        lat_d = lat.cuda().contiguous()
+        _lib.check(gpu._lib.b200_mimi_quantize(gpu._h, _lib.ptr(lat_d), frames, _lib.ptr(codes_g)))
         lat_q = gpu.decode_latent(codes_o.cuda())
     bad, unexcused = rvq_mismatches(codes_g, codes_o, margins, tol=1e-5)
     print(f"rvq on oracle latent: {bad} mismatches / {codes_o.numel()}, {unexcused} unexcused; "

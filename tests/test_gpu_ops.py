@@ -20,7 +20,7 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1])
 @pytest.mark.parametrize("M,N,K", [(1, 512, 256), (3, 1024, 4096), (8, 12288, 4096), (17, 4096, 11264),
                                    (96, 4096, 4096), (128, 2048, 1024), (200, 1024, 2816)])
 def test_linear_bf16(lib, impl, M, N, K):
@@ -60,11 +60,12 @@ def test_streaming_conv1d_matches_batch_conv(lib, cin, cout, k, stride, dil, elu
     want = F.conv1d(F.pad(xin, (P, 0)), w, bias, stride=stride, dilation=dil)
     prev = torch.zeros(B, cin, max(P, 1), device="cuda")
     mask = torch.ones(B, dtype=torch.bool, device="cuda")
+    wd, bd = w.cuda(), bias.cuda()      # keep the device tensors alive across the call
     outs = []
     for c in range(chunks):
         xc = x[..., c * T:(c + 1) * T].contiguous().cuda()
         y = torch.empty(B, cout, T // stride, device="cuda")
-        _lib.check(lib.b200_op_conv1d(cptr(xc), cptr(w.cuda()), cptr(bias.cuda()), cptr(prev), cptr(mask), cptr(y),
+        _lib.check(lib.b200_op_conv1d(cptr(xc), cptr(wd), cptr(bd), cptr(prev), cptr(mask), cptr(y),
                                       B, cin, cout, T, k, stride, dil, elu, _stream()))
         outs.append(y.cpu())
     got = torch.cat(outs, -1)
@@ -100,11 +101,12 @@ def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
     want = F.conv_transpose1d(xin, w, bias, stride=stride)[..., :chunks * T * stride]
     partial = torch.zeros(B, cout, stride, device="cuda")
     mask = torch.ones(B, dtype=torch.bool, device="cuda")
+    wd, bd = w.cuda(), bias.cuda()
     outs = []
     for c in range(chunks):
         xc = x[..., c * T:(c + 1) * T].contiguous().cuda()
         y = torch.empty(B, cout, T * stride, device="cuda")
-        _lib.check(lib.b200_op_convtr1d(cptr(xc), cptr(w.cuda()), cptr(bias.cuda()), cptr(partial), cptr(mask), cptr(y),
+        _lib.check(lib.b200_op_convtr1d(cptr(xc), cptr(wd), cptr(bd), cptr(partial), cptr(mask), cptr(y),
                                         B, cin, cout, T, k, stride, elu, _stream()))
         outs.append(y.cpu())
     got = torch.cat(outs, -1)
@@ -112,29 +114,42 @@ def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("card,k,temp", [(2048, 250, 0.8), (32000, 25, 0.7), (64, 250, 0.8), (500, 25, 0.7)])
+def _tie_free_top(B: int, card: int, n_top: int, gen: torch.Generator) -> torch.Tensor:
+    """bf16 logits whose n_top largest entries are pairwise distinct (bf16 cannot hold 32000 distinct
+    values in a sane range, so the bulk may tie; ties below the top-k never influence the sample)."""
+    bulk = (torch.randn(B, card, generator=gen) * 1.5).clamp(-6, 3.5).bfloat16()
+    # the 384 bf16 values in [4, 32): three binades x 128 mantissas
+    top_vals = torch.cat([torch.arange(128, dtype=torch.float32) * s + lo for lo, s in ((4, 2 ** -5), (8, 2 ** -4), (16, 2 ** -3))])
+    assert top_vals.bfloat16().float().unique().numel() == 384 and n_top <= 384
+    out = bulk.clone()
+    for b in range(B):
+        pos = torch.randperm(card, generator=gen)[:n_top]
+        vals = top_vals[torch.randperm(384, generator=gen)[:n_top]]
+        out[b, pos] = vals.bfloat16()
+    return out
+
+
+@pytest.mark.parametrize("card,k,temp", [(2048, 250, 0.8), (32000, 25, 0.7), (64, 250, 0.8), (500, 25, 0.7),
+                                         (2048, 250, 6.0), (32000, 25, 9.0)])
 def test_sampler_matches_oracle(lib, card, k, temp):
-    """sample_token with shared Exp(1) noise; logits are made tie-free so that ranks are unambiguous."""
+    """sample_token with shared Exp(1) noise on logits whose top-(k+8) entries are tie-free."""
     from moshi_b200 import _lib
     from oracle.lm import sample_token
-    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(3)
     B = 33
-    # distinct bf16 values per row: a random permutation of an exactly-representable grid
-    grid = (torch.arange(card, dtype=torch.float32) - card / 2) * (2.0 ** -5 if card <= 4096 else 2.0 ** -9)
-    grid = grid.bfloat16()
-    assert grid.unique().numel() == card
-    logits = torch.stack([grid[torch.randperm(card)] for _ in range(B)])
     kk = min(k, card)
-    noise = torch.empty(B, kk).exponential_(1)
+    logits = _tie_free_top(B, card, min(card, kk + 8), g)
+    noise = torch.empty(B, kk).exponential_(1, generator=g)
     want = sample_token(logits.float()[:, None, None, :], True, temp, k, noise)[:, 0, 0]
     out = torch.empty(B, dtype=torch.int64, device="cuda")
-    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), cptr(noise.cuda()), cptr(out), B, card, 1, temp, k, _stream()))
+    ld, nd = logits.cuda(), noise.cuda()
+    _lib.check(lib.b200_op_sample(cptr(ld), cptr(nd), cptr(out), B, card, 1, temp, k, _stream()))
     torch.cuda.synchronize()
     agree = (out.cpu() == want).float().mean().item()
-    print(f"sampler card={card} k={k}: agreement {agree:.3f}")
+    print(f"sampler card={card} k={k} temp={temp}: agreement {agree:.3f}, distinct winners {want.unique().numel()}")
     assert agree == 1.0
     # greedy
-    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), None, cptr(out), B, card, 0, temp, k, _stream()))
+    _lib.check(lib.b200_op_sample(cptr(ld), None, cptr(out), B, card, 0, temp, k, _stream()))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), logits.float().argmax(-1))
 
@@ -144,6 +159,7 @@ def test_sampler_ties_pick_lowest_index(lib):
     logits = torch.zeros(2, 100).bfloat16()
     logits[1, 40:] = 1.0
     out = torch.empty(2, dtype=torch.int64, device="cuda")
-    _lib.check(lib.b200_op_sample(cptr(logits.cuda()), None, cptr(out), 2, 100, 0, 1.0, 5, _stream()))
+    ld = logits.cuda()
+    _lib.check(lib.b200_op_sample(cptr(ld), None, cptr(out), 2, 100, 0, 1.0, 5, _stream()))
     torch.cuda.synchronize()
     assert out.tolist() == [0, 40]
