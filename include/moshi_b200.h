@@ -213,6 +213,12 @@ int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev
 int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
                      const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
                      int K, int stride, int elu_in, void* stream);
+/* Ring-cache decode attention for T = 1, head dim 128 (transformer.py:574-585): q bf16 [B,H,128],
+ * K/V rings bf16 [B,H,cap,128], offsets i64 [B] (keys already appended: slots < min(offset+exec, cap)
+ * are attended), out bf16 [B,H,128].  nsplit = KV splits per (b,h) (0 = what the LM would pick). */
+int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev,
+                        const int64_t* offsets_dev, const uint8_t* exec_mask_dev, int B, int H, int cap,
+                        int nsplit, void* stream);
 /* sample_token (sampling.py:86-106): logits bf16 [B,card], noise f32 [B,min(k,card)] -> i64 [B]. */
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B,
                    int card, int use_sampling, float temp, int top_k, void* stream);

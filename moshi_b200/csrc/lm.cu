@@ -382,11 +382,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->dao, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dh, (size_t)B * c.depformer_ffn_hidden));
   B200_TRY(A.alloc_t(&h->dep_logits, (size_t)B * c.dep_q * c.card));
-  // split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
-  int ns = ceil_div(148 * 4, B * H);
-  if (ns < 1) ns = 1;
-  if (ns > 16) ns = 16;
-  if (ns > ceil_div(c.context, 64)) ns = ceil_div(c.context, 64);
+  const int ns = attn_pick_splits(B, H, c.context);
   h->nsplit = ns;
   B200_TRY(A.alloc_t(&h->attn_part, (size_t)B * H * ns * (ATT_D + 2)));
   B200_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));

@@ -262,6 +262,16 @@ static __global__ void rope_append_bf16_kernel(const bf16* __restrict__ qkv, bf1
 constexpr int ATT_D = 128;
 constexpr int ATT_THREADS = 128;
 
+// split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
+inline int attn_pick_splits(int B, int H, int cap) {
+  int ns = (148 * 4 + B * H - 1) / (B * H);
+  if (ns < 1) ns = 1;
+  if (ns > 16) ns = 16;
+  const int max_by_len = (cap + 63) / 64;
+  if (ns > max_by_len) ns = max_by_len;
+  return ns;
+}
+
 static __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
                                                                   const bf16* __restrict__ vc, float* __restrict__ part,
                                                                   const long long* __restrict__ offset,

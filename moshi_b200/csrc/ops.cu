@@ -96,6 +96,29 @@ int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_d
   return check_launch("op_convtr1d");
 }
 
+int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev,
+                        const int64_t* offsets_dev, const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit,
+                        void* stream) {
+  using namespace b200::lm;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || H < 1 || cap < 1) B200_FAIL(B200_ERR_SHAPE, "op_attn_decode: bad shape");
+  if (nsplit <= 0) nsplit = attn_pick_splits(B, H, cap);
+  static float* part = nullptr;
+  static size_t part_n = 0;
+  const size_t need = (size_t)B * H * nsplit * (ATT_D + 2);
+  if (need > part_n) {
+    if (part) cudaFree(part);
+    B200_CUDA(cudaMalloc(&part, need * sizeof(float)));
+    part_n = need;
+  }
+  dim3 grid(B * H, nsplit);
+  B200_LAUNCH(attn_decode_kernel, grid, ATT_THREADS, 0, st, static_cast<const bf16*>(q_dev), static_cast<const bf16*>(k_dev),
+              static_cast<const bf16*>(v_dev), part, reinterpret_cast<const long long*>(offsets_dev), exec_mask_dev, H, cap,
+              nsplit);
+  B200_LAUNCH(attn_combine_kernel, B * H, ATT_D, 0, st, part, static_cast<bf16*>(out_dev), nsplit);
+  return check_launch("op_attn_decode");
+}
+
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B, int card,
                    int use_sampling, float temp, int top_k, void* stream) {
   using namespace b200::lm;

@@ -87,15 +87,25 @@ def scaled_embedding(sd: dict, prefix: str, tokens: torch.Tensor) -> torch.Tenso
 
 
 def sample_token(logits: torch.Tensor, use_sampling: bool, temp: float, top_k: int,
-                 noise: torch.Tensor | None = None) -> torch.Tensor:
+                 noise: torch.Tensor | None = None, tie_break: str = "torch") -> torch.Tensor:
     """sampling.py:86-106 (top-k branch).  ``noise`` replaces the Exp(1) draw of sampling.py:44
     ([N, k], one row per flattened leading index); when None it is drawn from torch's global
-    generator exactly like the reference, so that a seeded reference run is reproduced."""
+    generator exactly like the reference, so that a seeded reference run is reproduced.
+
+    ``tie_break``: the reference ranks candidates with ``torch.topk`` (sampling.py:62), whose order
+    among *equal* probabilities is unspecified (and differs between torch's CPU and CUDA kernels);
+    the noise is indexed by rank, so tied bf16 logits make the sample depend on that order.
+    "torch" keeps torch.topk (bit-exact with a CPU reference run); "index" ranks ties by ascending
+    token id, which is the order the CUDA sampler defines (tolerances)."""
     if not (use_sampling and temp > 0.0):
         return torch.argmax(logits, dim=-1)
     probs = torch.softmax(logits / temp, dim=-1)
     k = min(top_k, probs.shape[-1])
-    top, idx = torch.topk(probs, k, dim=-1)
+    if tie_break == "index":
+        idx = torch.sort(logits, dim=-1, descending=True, stable=True).indices[..., :k]
+        top = probs.gather(-1, idx)
+    else:
+        top, idx = torch.topk(probs, k, dim=-1)
     flat = top.reshape(-1, k)
     q = torch.empty_like(flat).exponential_(1) if noise is None else noise.reshape(-1, k).to(flat)
     choice = (flat / q).argmax(dim=-1, keepdim=True).reshape(*top.shape[:-1], 1)
@@ -104,7 +114,9 @@ def sample_token(logits: torch.Tensor, use_sampling: bool, temp: float, top_k: i
 
 class LMOracle:
     def __init__(self, sd: tp.Dict[str, torch.Tensor], spec: LMSpec, use_sampling: bool = True,
-                 temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25):
+                 temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25,
+                 tie_break: str = "torch"):
+        self.tie_break = tie_break
         self.sd = sd
         self.spec = spec
         self.use_sampling, self.temp, self.temp_text = use_sampling, temp, temp_text
@@ -191,7 +203,7 @@ class LMOracle:
             if logits_out is not None:
                 logits_out.append(logits)
             nxt = sample_token(logits.float(), self.use_sampling, self.temp, self.top_k,
-                               None if noise is None else noise[k])[:, 0, 0]
+                               None if noise is None else noise[k], self.tie_break)[:, 0, 0]
             toks.append(nxt)
             prev = nxt
         return torch.stack(toks, dim=1)
@@ -228,7 +240,7 @@ class LMOracle:
         # 3./4. temporal transformer + text sampling (lm.py:734-747)
         transformer_out, text_logits = self.forward_text(inp)
         text_token = sample_token(text_logits.float(), self.use_sampling, self.temp_text,
-                                  self.top_k_text, noise_text)[:, 0, 0]
+                                  self.top_k_text, noise_text, self.tie_break)[:, 0, 0]
         # 5. depformer
         dep_logits: list = []
         audio = self.depformer_step(text_token, transformer_out, noise_audio, dep_logits)

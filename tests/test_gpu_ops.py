@@ -114,6 +114,28 @@ def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,H,cap,nsplit", [(1, 32, 3000, 0), (5, 4, 3000, 1), (3, 2, 12, 0), (7, 8, 250, 3), (2, 32, 3000, 16)])
+def test_ring_attention_decode(lib, B, H, cap, nsplit):
+    """Attention over the valid part of the ring == masked SDPA over the whole ring (transformer.py:574-585)."""
+    from moshi_b200 import _lib
+    g = torch.Generator().manual_seed(B * 100 + cap)
+    q = torch.randn(B, H, 128, generator=g).bfloat16().cuda()
+    k = torch.randn(B, H, cap, 128, generator=g).bfloat16().cuda()
+    v = torch.randn(B, H, cap, 128, generator=g).bfloat16().cuda()
+    offs = torch.tensor([0, 1, cap - 1, cap, 3 * cap + 5, 17, cap // 2][:B], dtype=torch.int64)
+    n_valid = (offs + 1).clamp(max=cap)
+    out = torch.empty(B, H, 128, dtype=torch.bfloat16, device="cuda")
+    mask = torch.ones(B, dtype=torch.bool, device="cuda")
+    offs_d = offs.cuda()
+    _lib.check(lib.b200_op_attn_decode(cptr(q), cptr(k), cptr(v), cptr(out), cptr(offs_d), cptr(mask), B, H, cap, nsplit,
+                                       _stream()))
+    torch.cuda.synchronize()
+    allowed = (torch.arange(cap)[None, :] < n_valid[:, None]).cuda()
+    want = F.scaled_dot_product_attention(q.float()[:, :, None], k.float(), v.float(), allowed[:, None, None, :])[:, :, 0]
+    print(stats(f"attn B={B} H={H} cap={cap} nsplit={nsplit}", out, want))
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
 def _tie_free_top(B: int, card: int, n_top: int, gen: torch.Generator) -> torch.Tensor:
     """bf16 logits whose n_top largest entries are pairwise distinct (bf16 cannot hold 32000 distinct
     values in a sane range, so the bulk may tie; ties below the top-k never influence the sample)."""

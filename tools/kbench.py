@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks (CUDA events) of the hot-path kernels through the C ABI.
+
+Every timed launch reads operands that are not L2-resident: weights / KV rings are rotated through
+enough copies to exceed the 126 MB L2.  Prints one JSON object per line; run under gpurun, e.g.
+
+    python tools/kbench.py --what gemm,attn,mimi > gpurun_out/kbench.jsonl
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+from moshi_b200 import _lib  # noqa: E402
+
+PEAK = 6576.1
+p = ROOT / "MEASURED_PEAKS.json"
+if p.exists():
+    PEAK = float(json.loads(p.read_text())["hbm_gbs"])
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def time_ms(fn, n_rot: int, iters: int = 20, warm: int = 3) -> float:
+    for i in range(warm):
+        fn(i % n_rot)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_rot)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_gemm(lib, Ms):
+    shapes = [  # (name, N, K)
+        ("temporal.in_proj", 12288, 4096), ("temporal.out_proj", 4096, 4096), ("temporal.linear_in", 22528, 4096),
+        ("temporal.linear_out", 4096, 11264), ("text_linear", 32000, 4096), ("depformer_in_all", 8192, 4096),
+        ("dep.in_proj", 3072, 1024), ("dep.out_proj", 1024, 1024), ("dep.linear_in", 5632, 1024),
+        ("dep.linear_out", 1024, 2816), ("dep.head", 2048, 1024),
+    ]
+    for name, N, K in shapes:
+        wbytes = N * K * 2
+        n_rot = max(2, -(-(400 << 20) // wbytes))
+        ws = [torch.empty(N, K, device="cuda", dtype=torch.bfloat16).uniform_(-0.02, 0.02) for _ in range(n_rot)]
+        for M in Ms:
+            x = torch.empty(M, K, device="cuda", dtype=torch.bfloat16).uniform_(-1, 1)
+            y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            for impl in (1, 2):
+                def fn(i):
+                    _lib.check(lib.b200_op_linear_bf16(_lib.ptr(x), _lib.ptr(ws[i]), _lib.ptr(y), M, N, K, impl, stream()))
+                try:
+                    ms = time_ms(fn, n_rot)
+                except Exception as e:  # unsupported shape
+                    print(json.dumps({"kernel": "linear", "name": name, "M": M, "impl": impl, "error": str(e)[:80]}), flush=True)
+                    continue
+                alg = wbytes + M * K * 2 + M * N * 2
+                gbs = alg / ms / 1e6
+                print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": impl, "ms": round(ms, 4),
+                                  "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+        del ws
+
+
+def bench_attn(lib, Bs, cap=3000, H=32):
+    for B in Bs:
+        per = B * H * cap * 128 * 2
+        n_rot = max(2, -(-(300 << 20) // (2 * per)))
+        n_rot = min(n_rot, 8)
+        ks = [torch.empty(B, H, cap, 128, device="cuda", dtype=torch.bfloat16).normal_() for _ in range(n_rot)]
+        vs = [torch.empty(B, H, cap, 128, device="cuda", dtype=torch.bfloat16).normal_() for _ in range(n_rot)]
+        q = torch.randn(B, H, 128, device="cuda").bfloat16()
+        out = torch.empty_like(q)
+        mask = torch.ones(B, dtype=torch.bool, device="cuda")
+        for fill in (cap, cap // 4):
+            offs = torch.full((B,), fill + 7 * cap if fill == cap else fill - 1, dtype=torch.int64, device="cuda")
+            for ns in (0,):
+                def fn(i):
+                    _lib.check(lib.b200_op_attn_decode(_lib.ptr(q), _lib.ptr(ks[i]), _lib.ptr(vs[i]), _lib.ptr(out),
+                                                       _lib.ptr(offs), _lib.ptr(mask), B, H, cap, ns, stream()))
+                ms = time_ms(fn, n_rot)
+                alg = 2 * B * H * min(fill, cap) * 128 * 2
+                gbs = alg / ms / 1e6
+                print(json.dumps({"kernel": "attn_decode", "B": B, "H": H, "cap": cap, "fill": fill, "nsplit": ns,
+                                  "ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+        del ks, vs
+
+
+def bench_mimi(Bs):
+    from moshi_b200.models import loaders
+    mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
+    for B in Bs:
+        g = torch.Generator().manual_seed(1)
+        pcm = (0.1 * torch.randn(B, 1, 1920, generator=g)).cuda()
+        with mimi.streaming(B), torch.no_grad():
+            codes = None
+            for _ in range(260):      # fill both 250-slot transformer rings
+                codes = mimi.encode(pcm)
+                mimi.decode(codes)
+            enc = time_ms(lambda i: mimi.encode(pcm), 1, iters=20)
+            dec = time_ms(lambda i: mimi.decode(codes), 1, iters=20)
+            alg = mimi.algorithmic_bytes()
+        print(json.dumps({"kernel": "mimi", "B": B, "encode_ms": round(enc, 4), "decode_ms": round(dec, 4),
+                          "frames_per_s": round(B * 1e3 / (enc + dec), 1), "alg_bytes": alg,
+                          "GBps": round(alg / (enc + dec) / 1e6, 1),
+                          "gflops": round(B * 0.9 / (enc + dec) * 1e3, 1)}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="gemm,attn,mimi")
+    ap.add_argument("--M", default="1,16,96")
+    ap.add_argument("--B", default="1,16,96")
+    args = ap.parse_args()
+    lib = _lib.lib()
+    torch.cuda.set_device(0)
+    Ms = [int(v) for v in args.M.split(",")]
+    Bs = [int(v) for v in args.B.split(",")]
+    what = args.what.split(",")
+    if "attn" in what:
+        bench_attn(lib, Bs)
+    if "gemm" in what:
+        bench_gemm(lib, Ms)
+    if "mimi" in what:
+        bench_mimi(Bs)
+
+
+if __name__ == "__main__":
+    main()
