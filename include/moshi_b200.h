@@ -203,6 +203,15 @@ int b200_lm_set_graph(b200_lm* h, int enable);
  * uses for this shape), 1 = SIMT weight-streaming kernel, 2 = tcgen05/TMA kernel. */
 int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K,
                         int impl, void* stream);
+/* Stream-K tcgen05 GEMM over pre-tiled weights (the LM's linear kernel; csrc/gemm_sk.cu).
+ *   b200_op_packed_bytes / b200_op_pack_tiles: repack w bf16 [N,K] (epi 2: [2*gate_rows,K], rows gate|value,
+ *   gating.py:18-20) into 16 KB SWIZZLE_128B tiles.
+ *   b200_op_linear_sk: y = epi(x . W^T); epi 0 store [M,N], 1 residual add (y = res + .), 2 silu(gate)*value
+ *   -> [M,gate_rows].  grid / smem_budget / stream_only are tuning & diagnostics knobs (0 = defaults). */
+int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows);
+int b200_op_pack_tiles(const void* w_dev, void* out_dev, int N, int K, int epi, int gate_rows, void* stream);
+int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N,
+                      int K, int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream);
 /* StreamingConv1d.forward on one layer (conv.py:245-274): x [B,Cin,T], w [Cout,Cin,K], state
  * previous [B,Cin,Keff-S] (updated in place where exec_mask), y [B,Cout,T/S]. elu_in applies ELU to x. */
 int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,

@@ -83,6 +83,9 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_set_graph": (_I, [_P, _I]),
     # kernel-level
     "b200_op_linear_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_op_packed_bytes": (C.c_int64, [_I, _I, _I, _I]),
+    "b200_op_pack_tiles": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200_op_linear_sk": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

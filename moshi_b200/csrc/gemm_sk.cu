@@ -1,0 +1,458 @@
+// Stream-K tcgen05 GEMM for the LM linears (see gemm_tc.cuh):  y[M][N] = epi(x[M][K] . w[N][K]^T), bf16 in,
+// fp32 accumulate in TMEM, bf16 out.  M = concurrent sessions (<= 256), so the kernel is a weight
+// streamer: every weight byte crosses HBM -> SMEM exactly once and the whole chip pulls on it.
+//
+//   * Weights are repacked once at load into UMMA-ready tiles: [n_tile][k_block][A][128 rows x 64 k] bf16,
+//     each 16 KB tile already in the SWIZZLE_128B K-major shared-memory layout.  A pipeline stage is
+//     therefore ONE contiguous `cp.async.bulk` (16 KB, or 32 KB for the gated MLP's gate+value pair).
+//   * Work = the linear sequence of (n_tile, k_block) items, cut into equal contiguous ranges, one per
+//     CTA (persistent, grid = #SMs): every SM streams the same number of bytes whatever N and K are
+//     (out_proj has 32 n-tiles, the text head 250).  A tile whose k-range is cut across CTAs is
+//     finished by whichever CTA arrives last: partial accumulators go to an L2-resident workspace and
+//     are summed in CTA order, so the result is bit-reproducible and independent of arrival order.
+//   * Warp roles (192 threads): warp 0 = bulk-copy/TMA producer, warp 1 = TMEM owner + single-thread
+//     tcgen05.mma issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).  Two TMEM accumulator
+//     stages let the epilogue of one segment overlap the MMAs of the next.
+#include "gemm_tc.cuh"
+
+namespace b200 {
+namespace tc {
+
+namespace {
+
+constexpr int EPI_STORE = 0, EPI_RESADD = 1, EPI_GATE = 2;   // == lm::LIN_*
+constexpr int BLOCK_ROWS = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int TILE_BYTES = BLOCK_ROWS * BLOCK_K * 2;   // 16 KB
+constexpr int MAX_STAGES = 12;
+
+struct SkParams {
+  int M, N, K, Mpad, gate_rows, out_rows;
+  int stages, num_kb, n_tiles, n_acc, acc_cols;
+  long long total_items;
+  const uint8_t* wt;            // pre-tiled weights
+  __nv_bfloat16* y; long long ldy;
+  const __nv_bfloat16* res; long long ldr;
+  float* ws;                    // partial slots: [2 * grid][A][Mpad][128] fp32
+  int* counters;                // [n_tiles], zero between launches
+  uint32_t tmem_cols, stage_bytes;
+  int stream_only;              // diagnostics: skip the MMAs (measures the copy pipeline alone)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    if (++spins > (1u << 22)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major SWIZZLE_128B smem matrix descriptor (see gemm_tc.cu) and the kind::f16 instruction descriptor
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ long long item_begin(long long total, int c, int G) { return total * c / G; }
+// CTA whose item range [item_begin(c), item_begin(c + 1)) holds item j
+__device__ __forceinline__ int item_owner(long long total, long long j, int G) {
+  int c = (int)(j * G / total);
+  while (c + 1 < G && item_begin(total, c + 1, G) <= j) ++c;
+  while (c > 0 && item_begin(total, c, G) > j) --c;
+  return c;
+}
+
+template <int EPI>
+__device__ __forceinline__ float epilogue_value(const SkParams& p, float a, float b, int m, int n) {
+  if (EPI == EPI_STORE) return a;
+  if (EPI == EPI_RESADD) return __bfloat162float(p.res[(long long)m * p.ldr + n]) + bf16_round(a);
+  const float g = bf16_round(a), u = bf16_round(b);
+  return bf16_round(g / (1.f + expf(-g))) * u;     // bf16(silu(gate)) * value   (gating.py:18-20)
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_last;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bars = base + (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tptr = tempty0 + 16;
+  uint32_t* tptr_generic = reinterpret_cast<uint32_t*>(smem_raw + (tptr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int A_TILES = EPI == EPI_GATE ? 2 : 1;
+  constexpr uint32_t a_bytes = A_TILES * TILE_BYTES;
+  const int G = gridDim.x, c = blockIdx.x;
+  const long long i0 = item_begin(p.total_items, c, G), i1 = item_begin(p.total_items, c + 1, G);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);       // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr_generic;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== producer: one contiguous bulk copy of the weight tile(s) + one TMA box of activations per item =====
+      int s = 0; uint32_t ph = 0;
+      for (long long i = i0; i < i1; ++i) {
+        const int kb = (int)(i % p.num_kb);
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+        mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
+        bulk_load(sa, p.wt + (size_t)i * a_bytes, a_bytes, full0 + 8 * s);
+        tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_bits = 0u;       // bit a = phase parity of accumulator stage a
+      long long i = i0;
+      while (i < i1) {
+        const int kb0 = (int)(i % p.num_kb);
+        const long long seg_end = (i - kb0 + p.num_kb) < i1 ? (i - kb0 + p.num_kb) : i1;
+        mbar_wait(tempty0 + 8 * acc, ((acc_bits >> acc) & 1u) ^ 1u);        // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_cols);
+        bool first = true;
+        for (; i < seg_end; ++i) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (!p.stream_only) {
+            const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+            const uint32_t sb = sa + a_bytes;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t db = make_desc(sb + k * UMMA_K * 2);
+              const uint32_t accum = (first && k == 0) ? 0u : 1u;
+              umma_bf16(d0, make_desc(sa + k * UMMA_K * 2), db, idesc, accum);
+              if (EPI == EPI_GATE) umma_bf16(d0 + (uint32_t)p.Mpad, make_desc(sa + TILE_BYTES + k * UMMA_K * 2), db, idesc, accum);
+            }
+          }
+          first = false;
+          umma_commit(empty0 + 8 * s);           // frees the smem stage once these MMAs have read it
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull0 + 8 * acc);           // segment accumulated
+        acc_bits ^= 1u << acc;
+        if (p.n_acc == 2) acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> (global | workspace + last-arriver reduction) =====
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;           // 0..127
+    int acc = 0; uint32_t acc_bits = 0u;       // bit a = phase parity of accumulator stage a
+    long long i = i0;
+    int seg_idx = 0;
+    while (i < i1) {
+      const int tile = (int)(i / p.num_kb);
+      const int kb0 = (int)(i % p.num_kb);
+      const long long tile_end = i - kb0 + p.num_kb;
+      const long long seg_end = tile_end < i1 ? tile_end : i1;
+      const bool whole = kb0 == 0 && seg_end == tile_end;
+      const int n = tile * BLOCK_ROWS + row;
+      const bool n_ok = n < p.out_rows;
+      mbar_wait(tfull0 + 8 * acc, (acc_bits >> acc) & 1u);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      if (whole) {
+        for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(lane_addr + (uint32_t)c0, r0);
+          if (EPI == EPI_GATE) tmem_ld16(lane_addr + (uint32_t)(p.Mpad + c0), r1);
+          tmem_ld_wait();
+          if (!p.stream_only) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = c0 + j;
+              if (m < p.M && n_ok)
+                p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(
+                    epilogue_value<EPI>(p, __uint_as_float(r0[j]), EPI == EPI_GATE ? __uint_as_float(r1[j]) : 0.f, m, n));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      } else {
+        // partial accumulator -> workspace slot (2 * cta + segment parity), layout [A][Mpad][128]
+        const int slot = 2 * c + (seg_idx == 0 ? 0 : 1);
+        float* ws = p.ws + (size_t)slot * A_TILES * p.Mpad * BLOCK_ROWS;
+        for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(lane_addr + (uint32_t)c0, r0);
+          if (EPI == EPI_GATE) tmem_ld16(lane_addr + (uint32_t)(p.Mpad + c0), r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __stcg(ws + (size_t)(c0 + j) * BLOCK_ROWS + row, __uint_as_float(r0[j]));
+            if (EPI == EPI_GATE) __stcg(ws + (size_t)(p.Mpad + c0 + j) * BLOCK_ROWS + row, __uint_as_float(r1[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        // publish, count arrivals; the last arriver of this tile reduces in CTA order
+        __threadfence();
+        epi_bar_sync();
+        const int first_c = item_owner(p.total_items, (long long)tile * p.num_kb, G);
+        const int last_c = item_owner(p.total_items, (long long)(tile + 1) * p.num_kb - 1, G);
+        const int nseg = last_c - first_c + 1;
+        if (et == 0) {
+          const int old = atomicAdd(p.counters + tile, 1);
+          s_last = (old == nseg - 1) ? 1 : 0;
+          if (old == nseg - 1) p.counters[tile] = 0;           // ready for the next launch
+        }
+        epi_bar_sync();
+        if (s_last) {
+          __threadfence();
+          for (int m = 0; m < p.M; ++m) {
+            float a = 0.f, b = 0.f;
+            for (int cc = first_c; cc <= last_c; ++cc) {
+              const long long ci0 = item_begin(p.total_items, cc, G);
+              const int sl = 2 * cc + ((int)(ci0 / p.num_kb) == tile ? 0 : 1);
+              const float* w2 = p.ws + (size_t)sl * A_TILES * p.Mpad * BLOCK_ROWS;
+              a += __ldcg(w2 + (size_t)m * BLOCK_ROWS + row);
+              if (EPI == EPI_GATE) b += __ldcg(w2 + (size_t)(p.Mpad + m) * BLOCK_ROWS + row);
+            }
+            if (n_ok && !p.stream_only) p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, a, b, m, n));
+          }
+        }
+      }
+      acc_bits ^= 1u << acc;
+      if (p.n_acc == 2) acc ^= 1;
+      i = seg_end;
+      ++seg_idx;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// load-time repack: w [rows][K] row-major -> tiles [n_tile][kb][A][128 x 64] in the SWIZZLE_128B layout
+// (16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)); rows/cols beyond the tensor are zero.
+__global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ w, uint4* __restrict__ out, int rows, int K, int n_tiles,
+                                  int num_kb, int a_tiles, int gate_rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // one 16-byte chunk each
+  const long long total = (long long)n_tiles * num_kb * a_tiles * (TILE_BYTES / 16);
+  if (idx >= total) return;
+  const int chunk = (int)(idx % (TILE_BYTES / 16));
+  long long t = idx / (TILE_BYTES / 16);
+  const int a = (int)(t % a_tiles); t /= a_tiles;
+  const int kb = (int)(t % num_kb);
+  const int tile = (int)(t / num_kb);
+  const int r = chunk >> 3, cpos = chunk & 7;
+  const int csrc = cpos ^ (r & 7);                               // logical chunk stored at this position
+  const int limit = a_tiles == 2 ? gate_rows : rows;
+  const int rr = tile * BLOCK_ROWS + r;
+  const int k = kb * BLOCK_K + csrc * 8;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (rr < limit && k < K) v = *reinterpret_cast<const uint4*>(w + (long long)(rr + a * gate_rows) * K + k);
+  out[idx] = v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_attr_set = false;
+int g_sms = 0;
+
+int init_once() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (!g_attr_set) {
+    const int max_smem = 227 * 1024;
+    B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_RESADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_attr_set = true;
+  }
+  return B200_OK;
+}
+
+}  // namespace
+
+int sk_num_sms() { return init_once() == B200_OK ? g_sms : 0; }
+
+size_t sk_packed_bytes(int N, int K, int epi, int gate_rows) {
+  const int a = epi == EPI_GATE ? 2 : 1;
+  const int rows = epi == EPI_GATE ? gate_rows : N;
+  return (size_t)((rows + BLOCK_ROWS - 1) / BLOCK_ROWS) * ((K + BLOCK_K - 1) / BLOCK_K) * a * TILE_BYTES;
+}
+
+int sk_pack_weights(const __nv_bfloat16* w, void* out, int N, int K, int epi, int gate_rows, cudaStream_t stream) {
+  const int a = epi == EPI_GATE ? 2 : 1;
+  const int rows = epi == EPI_GATE ? gate_rows : N;
+  const int n_tiles = (rows + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (K % 8) B200_FAIL(B200_ERR_SHAPE, "sk_pack_weights: K must be a multiple of 8");
+  const long long total = (long long)n_tiles * num_kb * a * (TILE_BYTES / 16);
+  pack_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, static_cast<uint4*>(out), epi == EPI_GATE ? 2 * gate_rows : N,
+                                                                       K, n_tiles, num_kb, a, epi == EPI_GATE ? gate_rows : 0);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("pack_tiles");
+}
+
+size_t sk_workspace_bytes(int max_M) {
+  const int Mpad = ((max_M + 15) / 16) * 16;
+  return (size_t)2 * SK_MAX_GRID * 2 * Mpad * BLOCK_ROWS * 4;  // 2 slots per CTA, gate + value accumulators
+}
+
+bool sk_supported(int M, int N, int K, int epi) {
+  (void)N; (void)epi;
+  return M >= 1 && M <= 256 && K >= 8 && K % 8 == 0;
+}
+
+// y = epi(x . W^T) with W given as packed tiles.  ws / counters: sk_workspace_bytes(M) and >= 1024 ints, zeroed once.
+int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y,
+              long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
+              float* ws, int* counters, const SkTuning& tune, cudaStream_t stream) {
+  if (!sk_supported(M, N, K, epi) || ldx % 8) B200_FAIL(B200_ERR_SHAPE, "sk GEMM: unsupported shape M=%d N=%d K=%d", M, N, K);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tiles)) & 15)
+    B200_FAIL(B200_ERR_SHAPE, "sk GEMM: operands must be 16-byte aligned");
+  B200_TRY(init_once());
+  SkParams p;
+  p.M = M; p.N = N; p.K = K; p.gate_rows = gate_rows;
+  p.out_rows = epi == EPI_GATE ? gate_rows : N;
+  p.Mpad = ((M + 15) / 16) * 16;
+  p.wt = static_cast<const uint8_t*>(w_tiles);
+  p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
+  p.ws = ws; p.counters = counters;
+  p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.n_tiles = (p.out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
+  if (p.n_tiles > 1024) B200_FAIL(B200_ERR_SHAPE, "sk GEMM: more than 1024 row tiles");
+  p.total_items = (long long)p.n_tiles * p.num_kb;
+  const int a_tiles = epi == EPI_GATE ? 2 : 1;
+  p.stage_bytes = (uint32_t)(a_tiles * TILE_BYTES + p.Mpad * BLOCK_K * 2);
+  int stages = (tune.smem_budget > 0 ? tune.smem_budget : 200 * 1024) / (int)p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.acc_cols = a_tiles * p.Mpad;
+  p.n_acc = 2 * p.acc_cols <= 512 ? 2 : 1;
+  uint32_t cols = (uint32_t)(p.n_acc * p.acc_cols), pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  p.stream_only = tune.stream_only;
+  int grid = tune.grid > 0 ? tune.grid : g_sms;
+  if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
+  if ((long long)grid > p.total_items) grid = (int)p.total_items;
+  // every CTA must own >= 1 item and a tile may not be cut into more pieces than the workspace indexes
+  const CUtensorMap* mx = nullptr;
+  {
+    PlanKey key{x, ldx, M, K, p.Mpad};
+    auto it = cache.maps.find(key);
+    if (it == cache.maps.end()) {
+      CUtensorMap m;
+      cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+      cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+      cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.Mpad};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) M=%d K=%d ld=%lld", (int)r, M, K, ldx);
+      it = cache.maps.emplace(key, m).first;
+    }
+    mx = &it->second;
+  }
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
+  if (epi == EPI_STORE) gemm_sk_kernel<EPI_STORE><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
+  else if (epi == EPI_RESADD) gemm_sk_kernel<EPI_RESADD><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
+  else gemm_sk_kernel<EPI_GATE><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("gemm_sk");
+}
+
+}  // namespace tc
+}  // namespace b200

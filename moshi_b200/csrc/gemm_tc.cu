@@ -41,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 22)) __trap();
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -38,5 +38,22 @@ int linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const __
            long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
            cudaStream_t stream);
 
+// ---- stream-K kernel over pre-tiled weights (gemm_sk.cu) --------------------------------------
+struct SkTuning {
+  int grid = 0;          // CTAs (0 = one per SM)
+  int smem_budget = 0;   // bytes of pipeline stages per CTA (0 = 200 KB)
+  int stream_only = 0;   // diagnostics: run the copy pipeline without MMAs / stores
+};
+int sk_num_sms();
+bool sk_supported(int M, int N, int K, int epi);
+size_t sk_packed_bytes(int N, int K, int epi, int gate_rows);
+int sk_pack_weights(const __nv_bfloat16* w, void* out, int N, int K, int epi, int gate_rows, cudaStream_t stream);
+size_t sk_workspace_bytes(int max_M);
+constexpr int SK_MAX_GRID = 304;     // 2 CTAs per SM at most
+constexpr int SK_MAX_TILES = 1024;   // ints in the arrival-counter array
+int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y,
+              long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
+              float* ws, int* counters, const SkTuning& tune, cudaStream_t stream);
+
 }  // namespace tc
 }  // namespace b200

@@ -35,7 +35,9 @@ struct b200_lm {
   // sampling (LMGen defaults, lm.py:556-571)
   int use_sampling = 1, top_k = 250, top_k_text = 25;
   float temp = 0.8f, temp_text = 0.7f;
-  int gemm_impl = 0;
+  int gemm_impl = 3;                           // 3 = stream-K tcgen05 over packed tiles (default)
+  float* sk_ws = nullptr;                      // stream-K partial-accumulator slots (L2-resident)
+  int* sk_counters = nullptr;                  // per-tile arrival counters (zero between launches)
   // weights
   EmbedTables emb;
   std::vector<TLayer> layers;
@@ -91,11 +93,15 @@ int noise_per_row(const b200_lm* h) {
   return kt + h->cfg.dep_q * ka;
 }
 
-// y[M][N] = epi(x[M][K] . w[N][K]^T)
+// y[M][N] = epi(x[M][K] . w[N][K]^T).  `w` is the packed-tile form (gemm_sk.cu) unless a legacy kernel was
+// selected with B200_GEMM_IMPL (1 = SIMT, 2 = one-tile-per-CTA tcgen05), in which case it is row-major.
 int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, const bf16* res,
            long long ldr, int M, int N, int K, int epi, int gate_rows) {
-  int impl = h->gemm_impl;
-  if (impl == 0) impl = tc::auto_pick(M, N, K, epi);
+  const int impl = h->gemm_impl;
+  if (impl == 3) {
+    tc::SkTuning t;
+    return tc::sk_linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->sk_ws, h->sk_counters, t, h->body);
+  }
   if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->body);
   const int grid = ceil_div(N * 32, 256);
   if (epi == LIN_STORE) {
@@ -109,6 +115,21 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
     B200_LAUNCH(k, grid, 256, 0, h->body, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
   }
   return check_launch("linear_simt");
+}
+
+// Linear weight from the store -> the layout the selected GEMM reads.  Packed tiles replace the row-major
+// tensor (which is released), so the 15.4 GB checkpoint is resident once.
+int get_linear(b200_lm* h, const std::string& name, int N, int K, int epi, int gate_rows, const bf16** out) {
+  const bf16* w = nullptr;
+  B200_TRY(get_bf16(h, name, {epi == LIN_GATE ? 2 * gate_rows : N, K}, &w));
+  if (h->gemm_impl != 3) { *out = w; return B200_OK; }
+  void* packed = nullptr;
+  B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(N, K, epi, gate_rows), false));
+  B200_TRY(tc::sk_pack_weights(w, packed, N, K, epi, gate_rows, nullptr));
+  B200_CUDA(cudaStreamSynchronize(nullptr));
+  h->store.release(name);
+  *out = static_cast<const bf16*>(packed);
+  return B200_OK;
 }
 
 int sample(b200_lm* h, const bf16* logits, int card, const float* noise, long long* out, float temp, int top_k) {
@@ -223,7 +244,10 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   h->max_delay = 0;
   for (int k = 0; k < h->Kc; ++k) h->max_delay = cfg->delays[k] > h->max_delay ? cfg->delays[k] : h->max_delay;
   h->CT = h->max_delay + 2;     // lm.py:606-611
-  if (const char* e = getenv("B200_GEMM_IMPL")) h->gemm_impl = atoi(e);   // 0 auto, 1 SIMT, 2 tcgen05 (debug switch)
+  if (const char* e = getenv("B200_GEMM_IMPL")) {   // debug switch: 1 SIMT, 2 one-tile tcgen05, 3 stream-K tcgen05
+    const int v = atoi(e);
+    if (v >= 1 && v <= 3) h->gemm_impl = v;
+  }
   *out = h;
   return B200_OK;
 }
@@ -243,27 +267,41 @@ int b200_lm_finalize(b200_lm* h) {
   for (int k = 0; k < c.n_q; ++k)
     B200_TRY(get_bf16(h, "emb." + std::to_string(k) + ".weight", {c.card + 1, d}, &h->emb.audio[k]));
   B200_TRY(get_bf16(h, "text_emb.weight", {c.text_card + 1, d}, &h->emb.text));
-  B200_TRY(get_bf16(h, "text_linear.weight", {c.text_card, d}, &h->text_linear));
+  B200_TRY(get_linear(h, "text_linear.weight", c.text_card, d, LIN_STORE, 0, &h->text_linear));
   B200_TRY(get_bf16(h, "out_norm.alpha", {1, 1, d}, &h->out_norm));
   h->layers.resize(c.num_layers);
   for (int l = 0; l < c.num_layers; ++l) {
     const std::string p = "transformer.layers." + std::to_string(l);
     TLayer& L = h->layers[l];
-    B200_TRY(get_bf16(h, p + ".self_attn.in_projs.0.weight", {3 * d, d}, &L.in_w));
-    B200_TRY(get_bf16(h, p + ".self_attn.out_projs.0.weight", {d, d}, &L.out_w));
+    B200_TRY(get_linear(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, LIN_STORE, 0, &L.in_w));
+    B200_TRY(get_linear(h, p + ".self_attn.out_projs.0.weight", d, d, LIN_RESADD, 0, &L.out_w));
     B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, d}, &L.n1));
     B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, d}, &L.n2));
-    B200_TRY(get_bf16(h, p + ".gating.linear_in.weight", {2 * F, d}, &L.lin_in));
-    B200_TRY(get_bf16(h, p + ".gating.linear_out.weight", {d, F}, &L.lin_out));
+    B200_TRY(get_linear(h, p + ".gating.linear_in.weight", 2 * F, d, LIN_GATE, F, &L.lin_in));
+    B200_TRY(get_linear(h, p + ".gating.linear_out.weight", d, F, LIN_RESADD, 0, &L.lin_out));
   }
   // depformer_in.{k} stacked so that all dep_q projections of transformer_out are one GEMM
-  B200_TRY(h->weights.alloc_t(&h->dep_in_all, (size_t)c.dep_q * dd * d, false));
-  for (int k = 0; k < c.dep_q; ++k) {
-    const bf16* w = nullptr;
-    const std::string name = "depformer_in." + std::to_string(k) + ".weight";
-    B200_TRY(get_bf16(h, name, {dd, d}, &w));
-    B200_CUDA(cudaMemcpy(h->dep_in_all + (size_t)k * dd * d, w, (size_t)dd * d * 2, cudaMemcpyDeviceToDevice));
-    h->store.release(name);
+  {
+    bf16* stacked = nullptr;
+    B200_CUDA(cudaMalloc(&stacked, (size_t)c.dep_q * dd * d * 2));
+    for (int k = 0; k < c.dep_q; ++k) {
+      const bf16* w = nullptr;
+      const std::string name = "depformer_in." + std::to_string(k) + ".weight";
+      B200_TRY(get_bf16(h, name, {dd, d}, &w));
+      B200_CUDA(cudaMemcpy(stacked + (size_t)k * dd * d, w, (size_t)dd * d * 2, cudaMemcpyDeviceToDevice));
+      h->store.release(name);
+    }
+    if (h->gemm_impl == 3) {
+      void* packed = nullptr;
+      B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(c.dep_q * dd, d, LIN_STORE, 0), false));
+      B200_TRY(tc::sk_pack_weights(stacked, packed, c.dep_q * dd, d, LIN_STORE, 0, nullptr));
+      B200_CUDA(cudaStreamSynchronize(nullptr));
+      cudaFree(stacked);
+      h->dep_in_all = static_cast<bf16*>(packed);
+    } else {
+      h->dep_in_all = stacked;
+      h->weights.ptrs.push_back(stacked);
+    }
   }
   h->dep_tables.resize(c.dep_q);
   B200_TRY(get_bf16(h, "depformer_text_emb.weight", {c.text_card + 1, dd}, &h->dep_tables[0]));
@@ -271,7 +309,7 @@ int b200_lm_finalize(b200_lm* h) {
     B200_TRY(get_bf16(h, "depformer_emb." + std::to_string(k - 1) + ".weight", {c.card + 1, dd}, &h->dep_tables[k]));
   h->dep_heads.resize(c.dep_q);
   for (int k = 0; k < c.dep_q; ++k)
-    B200_TRY(get_bf16(h, "linears." + std::to_string(k) + ".weight", {c.card, dd}, &h->dep_heads[k]));
+    B200_TRY(get_linear(h, "linears." + std::to_string(k) + ".weight", c.card, dd, LIN_STORE, 0, &h->dep_heads[k]));
   h->dlayers.resize(c.depformer_num_layers);
   for (int l = 0; l < c.depformer_num_layers; ++l) {
     const std::string p = "depformer.layers." + std::to_string(l);
@@ -279,10 +317,10 @@ int b200_lm_finalize(b200_lm* h) {
     L.in_w.resize(c.dep_q); L.out_w.resize(c.dep_q); L.lin_in.resize(c.dep_q); L.lin_out.resize(c.dep_q);
     for (int k = 0; k < c.dep_q; ++k) {
       const std::string ks = std::to_string(k);
-      B200_TRY(get_bf16(h, p + ".self_attn.in_projs." + ks + ".weight", {3 * dd, dd}, &L.in_w[k]));
-      B200_TRY(get_bf16(h, p + ".self_attn.out_projs." + ks + ".weight", {dd, dd}, &L.out_w[k]));
-      B200_TRY(get_bf16(h, p + ".gating." + ks + ".linear_in.weight", {2 * dF, dd}, &L.lin_in[k]));
-      B200_TRY(get_bf16(h, p + ".gating." + ks + ".linear_out.weight", {dd, dF}, &L.lin_out[k]));
+      B200_TRY(get_linear(h, p + ".self_attn.in_projs." + ks + ".weight", 3 * dd, dd, LIN_STORE, 0, &L.in_w[k]));
+      B200_TRY(get_linear(h, p + ".self_attn.out_projs." + ks + ".weight", dd, dd, LIN_RESADD, 0, &L.out_w[k]));
+      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_in.weight", 2 * dF, dd, LIN_GATE, dF, &L.lin_in[k]));
+      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_out.weight", dd, dF, LIN_RESADD, 0, &L.lin_out[k]));
     }
     B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, dd}, &L.n1));
     B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, dd}, &L.n2));
@@ -382,6 +420,8 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->dao, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dh, (size_t)B * c.depformer_ffn_hidden));
   B200_TRY(A.alloc_t(&h->dep_logits, (size_t)B * c.dep_q * c.card));
+  B200_TRY(A.alloc(reinterpret_cast<void**>(&h->sk_ws), tc::sk_workspace_bytes(B), false));
+  B200_TRY(A.alloc_t(&h->sk_counters, tc::SK_MAX_TILES));
   const int ns = attn_pick_splits(B, H, c.context);
   h->nsplit = ns;
   B200_TRY(A.alloc_t(&h->attn_part, (size_t)B * H * ns * (ATT_D + 2)));

@@ -77,6 +77,10 @@ struct b200_mimi {
   int n_enc_commits = 0, n_dec_commits = 0, max_enc_rows = 0, max_dec_rows = 0;
   ConvTrCommit* dec_tr_commits = nullptr; int n_dec_tr_commits = 0; long long max_tr_rows = 0;
   long long* scratch_codes = nullptr;          // [B][K][1] for the host variants
+  float* rvq_res[2] = {nullptr, nullptr};      // RVQ workspace: residuals, per-chunk partial argmin
+  float* rvq_best[2] = {nullptr, nullptr};
+  int* rvq_idx[2] = {nullptr, nullptr};
+  int rvq_cap = 0;
   float *pin_pcm = nullptr; long long* pin_codes = nullptr; size_t pin_pcm_n = 0, pin_codes_n = 0;
   float* dev_pcm = nullptr; long long* dev_codes = nullptr; size_t dev_pcm_n = 0, dev_codes_n = 0;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
@@ -417,20 +421,56 @@ int encode_frame_to_latent(b200_mimi* h, const float* pcm, int n_frames, int f) 
   return B200_OK;
 }
 
+// RVQ workspace (residuals + per-chunk partial argmin); sized at streaming_begin for Q = batch and
+// grown only by the multi-frame `quantize` entry point.
+int ensure_rvq_workspace(b200_mimi* h, int Q) {
+  if (Q <= h->rvq_cap) return B200_OK;
+  const int Dq = h->cfg.q_dimension, n_chunks = ceil_div(h->cfg.q_bins, RVQ_CHUNK);
+  if (h->stream) B200_CUDA(cudaStreamSynchronize(h->stream));
+  for (int w = 0; w < 2; ++w) {
+    if (h->rvq_res[w]) cudaFree(h->rvq_res[w]);
+    if (h->rvq_best[w]) cudaFree(h->rvq_best[w]);
+    if (h->rvq_idx[w]) cudaFree(h->rvq_idx[w]);
+    B200_CUDA(cudaMalloc(&h->rvq_res[w], (size_t)Q * Dq * 4));
+    B200_CUDA(cudaMalloc(&h->rvq_best[w], (size_t)Q * n_chunks * 4));
+    B200_CUDA(cudaMalloc(&h->rvq_idx[w], (size_t)Q * n_chunks * 4));
+  }
+  h->rvq_cap = Q;
+  return B200_OK;
+}
+
 int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, long long lt, int n_cols,
                   long long* codes, long long cs_b, long long cs_k, long long cs_f) {
   const auto& c = h->cfg;
-  RvqEncArgs a;
-  a.lat = lat; a.lb = lb; a.lc = lc; a.lt = lt; a.n_frames = n_cols;
-  for (int w = 0; w < 2; ++w) { a.wT[w] = h->wT[w]; a.cbT[w] = h->cbT[w]; a.cb[w] = h->cb[w]; a.cnorm[w] = h->cnorm[w]; }
-  a.levels[0] = c.q_n_semantic < h->num_codebooks ? c.q_n_semantic : h->num_codebooks;
-  a.levels[1] = h->num_codebooks - a.levels[0];
-  a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
-  a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f;
-  a.n_query = h->batch * n_cols; a.Cin = c.dimension; a.Dq = c.q_dimension; a.bins = c.q_bins;
-  dim3 grid(ceil_div(a.n_query, RVQ_Q), 2);
-  const size_t smem = (size_t)RVQ_Q * (c.dimension + c.q_dimension) * sizeof(float);
-  B200_LAUNCH(rvq_encode_kernel, grid, RVQ_THREADS, smem, h->stream, a);
+  const int Q = h->batch * n_cols, Dq = c.q_dimension, bins = c.q_bins;
+  const int n_chunks = ceil_div(bins, RVQ_CHUNK);
+  B200_TRY(ensure_rvq_workspace(h, Q));
+  int levels[2];
+  levels[0] = c.q_n_semantic < h->num_codebooks ? c.q_n_semantic : h->num_codebooks;
+  levels[1] = h->num_codebooks - levels[0];
+  {
+    dim3 grid(Q, 2);
+    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->stream, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
+                h->rvq_res[0], h->rvq_res[1], c.dimension, Dq);
+  }
+  const int max_levels = levels[0] > levels[1] ? levels[0] : levels[1];
+  const size_t per = (size_t)bins * Dq;
+  for (int level = 0; level < max_levels; ++level) {
+    RvqLevelArgs a;
+    for (int w = 0; w < 2; ++w) {
+      a.res[w] = h->rvq_res[w];
+      a.cbT[w] = h->cbT[w] + per * level; a.cb[w] = h->cb[w] + per * level; a.cnorm[w] = h->cnorm[w] + (size_t)bins * level;
+      a.part_best[w] = h->rvq_best[w]; a.part_idx[w] = h->rvq_idx[w];
+      a.active[w] = level < levels[w];
+      a.code_index[w] = (w == 0 ? 0 : levels[0]) + level;
+    }
+    a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f;
+    a.n_query = Q; a.n_frames = n_cols; a.Dq = Dq; a.bins = bins; a.n_chunks = n_chunks;
+    dim3 g1(n_chunks, ceil_div(Q, RVQ_QT), 2);
+    B200_LAUNCH(rvq_search_kernel, g1, RVQ_CHUNK, (size_t)RVQ_QT * Dq * 4, h->stream, a);
+    dim3 g2(Q, 2);
+    B200_LAUNCH(rvq_pick_kernel, g2, 128, 0, h->stream, a);
+  }
   return check_launch("rvq_encode");
 }
 
@@ -485,7 +525,7 @@ int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out) {
   if (!cfg || !out) B200_FAIL(B200_ERR_INVALID, "mimi_create: null argument");
   if (cfg->n_ratios < 1 || cfg->n_ratios > 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: n_ratios out of range");
   if (cfg->channels != 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: only mono audio is on the hot path");
-  if (cfg->q_bins > 8 * RVQ_THREADS) B200_FAIL(B200_ERR_INVALID, "mimi_create: bins > %d unsupported", 8 * RVQ_THREADS);
+  if (cfg->q_dimension % 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: codebook dimension must be a multiple of 8");
   if (cfg->tr_d_model / cfg->tr_num_heads != 64) B200_FAIL(B200_ERR_INVALID, "mimi_create: head dim must be 64");
   if (cfg->tr_d_model != cfg->dimension) B200_FAIL(B200_ERR_INVALID, "mimi_create: projected transformer unsupported");
   b200_mimi* h = new b200_mimi();
@@ -541,6 +581,11 @@ int b200_mimi_destroy(b200_mimi* h) {
   if (h->pin_codes) cudaFreeHost(h->pin_codes);
   if (h->dev_pcm) cudaFree(h->dev_pcm);
   if (h->dev_codes) cudaFree(h->dev_codes);
+  for (int w = 0; w < 2; ++w) {
+    if (h->rvq_res[w]) cudaFree(h->rvq_res[w]);
+    if (h->rvq_best[w]) cudaFree(h->rvq_best[w]);
+    if (h->rvq_idx[w]) cudaFree(h->rvq_idx[w]);
+  }
   delete h;
   return B200_OK;
 }
@@ -694,6 +739,7 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->tr_ao, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_h, ntok * ff));
   B200_TRY(A.alloc_t(&h->scratch_codes, (size_t)B * c.q_n_q));
+  B200_TRY(ensure_rvq_workspace(h, B));
   B200_CUDA(cudaDeviceSynchronize());
   h->batch = B;
   return B200_OK;

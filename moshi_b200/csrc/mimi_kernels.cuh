@@ -435,136 +435,139 @@ static __global__ void advance_offsets_kernel(long long* off, const uint8_t* exe
 }
 
 // ---------------------------------------------------------------------------------------------
-// Residual vector quantizer
+// Residual VQ, level-parallel form: the nearest-code search of one level is spread over
+// (code chunks x query tiles x quantizers) CTAs; the sequential dependency between levels is the
+// launch order.  Per level:  rvq_search_kernel -> partial (best score, index) per code chunk;
+// rvq_pick_kernel -> argmin over chunks (first minimum on ties), code written, residual updated.
 // ---------------------------------------------------------------------------------------------
-constexpr int RVQ_Q = 4;          // queries per CTA
-constexpr int RVQ_THREADS = 256;
+constexpr int RVQ_CHUNK = 128;    // codes per CTA (= threads)
+constexpr int RVQ_QT = 8;         // queries per CTA
 
-// One CTA = RVQ_Q latent vectors x one of the two quantizers (blockIdx.y: 0 = rvq_first, 1 = rvq_rest).
-//   proj:   res[q][m] = sum_k Wt[k][m] * lat[q][k]                       (vq.py:135, 1x1 conv, no bias)
-//   level:  idx = argmin_j (|c_j|^2 - 2 res.c_j)  (first minimum on ties)   (core_vq.py:270-276)
-//           res -= c_idx                                                   (core_vq.py:514-516)
-// cbT is the transposed codebook [level][dim][bins] (coalesced over codes), cb the row-major one.
-struct RvqEncArgs {
-  const float* lat; long long lb, lc, lt; int n_frames;    // latent [B][Cin][n]
-  const float* wT[2];        // [Cin][Dq]
-  const float* cbT[2];       // [levels][Dq][bins]
-  const float* cb[2];        // [levels][bins][Dq]
-  const float* cnorm[2];     // [levels][bins]   |c|^2
-  int levels[2];
-  int level_offset[2];       // first output codebook index
-  long long* codes; long long cs_b, cs_k, cs_f;   // code strides (batch, level, frame)
-  int n_query, Cin, Dq, bins;
+struct RvqLevelArgs {
+  float* res[2];             // residuals [Q][Dq] per quantizer
+  const float* cbT[2];       // this level's transposed codebook [Dq][bins]
+  const float* cb[2];        // this level's codebook [bins][Dq]
+  const float* cnorm[2];     // [bins]
+  float* part_best[2];       // [Q][n_chunks]
+  int* part_idx[2];
+  int active[2];             // quantizer has this level
+  int code_index[2];         // output codebook index of this level
+  long long* codes; long long cs_b, cs_k, cs_f;
+  int n_query, n_frames, Dq, bins, n_chunks;
 };
 
-static __global__ void __launch_bounds__(RVQ_THREADS) rvq_encode_kernel(const RvqEncArgs a) {
-  extern __shared__ float sm[];
-  const int which = blockIdx.y;
-  if (a.levels[which] <= 0) return;
-  const int q0 = blockIdx.x * RVQ_Q;
+// res[which][q][m] = sum_k Wt[k][m] * lat[q][k]   (vq.py:135: 1x1 conv, no bias)
+static __global__ void __launch_bounds__(256) rvq_project_kernel(const float* __restrict__ lat, long long lb, long long lc,
+                                                          long long lt, int n_frames, const float* __restrict__ wT0,
+                                                          const float* __restrict__ wT1, float* __restrict__ res0,
+                                                          float* __restrict__ res1, int Cin, int Dq) {
+  extern __shared__ float s_lat[];           // [Cin]
+  const int q = blockIdx.x, which = blockIdx.y;
+  const int b = q / n_frames, f = q % n_frames;
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) s_lat[c] = lat[b * lb + c * lc + f * lt];
+  __syncthreads();
+  const float* wT = which ? wT1 : wT0;
+  float* res = which ? res1 : res0;
+  for (int m = threadIdx.x; m < Dq; m += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < Cin; ++k) acc = fmaf(wT[(long long)k * Dq + m], s_lat[k], acc);
+    res[(long long)q * Dq + m] = acc;
+  }
+}
+
+static __global__ void __launch_bounds__(RVQ_CHUNK) rvq_search_kernel(const RvqLevelArgs a) {
+  const int which = blockIdx.z;
+  if (!a.active[which]) return;
+  extern __shared__ float s_res[];            // [Dq][RVQ_QT]  (queries fastest: two broadcast LDS.128 per dim)
+  __shared__ float s_best[RVQ_QT][RVQ_CHUNK / 32];
+  __shared__ int s_bidx[RVQ_QT][RVQ_CHUNK / 32];
   const int tid = threadIdx.x;
-  float* s_lat = sm;                         // [RVQ_Q][Cin]
-  float* s_res = sm + RVQ_Q * a.Cin;         // [RVQ_Q][Dq]
-  __shared__ float s_best[RVQ_Q][RVQ_THREADS / 32];
-  __shared__ int s_bidx[RVQ_Q][RVQ_THREADS / 32];
-  __shared__ int s_choice[RVQ_Q];
-
-  for (int i = tid; i < RVQ_Q * a.Cin; i += RVQ_THREADS) {
-    const int q = i / a.Cin, c = i % a.Cin;
-    const int qi = q0 + q;
-    float v = 0.f;
-    if (qi < a.n_query) {
-      const int b = qi / a.n_frames, f = qi % a.n_frames;
-      v = a.lat[b * a.lb + c * a.lc + f * a.lt];
-    }
-    s_lat[i] = v;
+  const int q0 = blockIdx.y * RVQ_QT;
+  const int code = blockIdx.x * RVQ_CHUNK + tid;
+  const float* res = a.res[which];
+  for (int i = tid; i < RVQ_QT * a.Dq; i += RVQ_CHUNK) {
+    const int q = i / a.Dq, d = i - q * a.Dq;
+    s_res[d * RVQ_QT + q] = (q0 + q < a.n_query) ? res[(long long)(q0 + q) * a.Dq + d] : 0.f;
   }
   __syncthreads();
-  for (int m = tid; m < a.Dq; m += RVQ_THREADS) {
-    float acc[RVQ_Q];
+  float dots[RVQ_QT];
 #pragma unroll
-    for (int q = 0; q < RVQ_Q; ++q) acc[q] = 0.f;
-    const float* w = a.wT[which] + m;
-    for (int k = 0; k < a.Cin; ++k) {
-      const float wv = w[(long long)k * a.Dq];
+  for (int q = 0; q < RVQ_QT; ++q) dots[q] = 0.f;
+  const bool ok = code < a.bins;
+  const float* col = a.cbT[which] + (ok ? code : 0);
+  for (int d0 = 0; d0 < a.Dq; d0 += 8) {
+    float cv[8];
 #pragma unroll
-      for (int q = 0; q < RVQ_Q; ++q) acc[q] = fmaf(wv, s_lat[q * a.Cin + k], acc[q]);
+    for (int j = 0; j < 8; ++j) cv[j] = col[(long long)(d0 + j) * a.bins];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r0 = *reinterpret_cast<const float4*>(&s_res[(d0 + j) * RVQ_QT]);
+      const float4 r1 = *reinterpret_cast<const float4*>(&s_res[(d0 + j) * RVQ_QT + 4]);
+      dots[0] = fmaf(cv[j], r0.x, dots[0]); dots[1] = fmaf(cv[j], r0.y, dots[1]);
+      dots[2] = fmaf(cv[j], r0.z, dots[2]); dots[3] = fmaf(cv[j], r0.w, dots[3]);
+      dots[4] = fmaf(cv[j], r1.x, dots[4]); dots[5] = fmaf(cv[j], r1.y, dots[5]);
+      dots[6] = fmaf(cv[j], r1.z, dots[6]); dots[7] = fmaf(cv[j], r1.w, dots[7]);
     }
+  }
+  const float cn = ok ? a.cnorm[which][code] : 0.f;
 #pragma unroll
-    for (int q = 0; q < RVQ_Q; ++q) s_res[q * a.Dq + m] = acc[q];
+  for (int q = 0; q < RVQ_QT; ++q) {
+    float best = ok ? cn - 2.f * dots[q] : INFINITY;       // |c|^2 - 2 x.c  (core_vq.py:270-276 without the constant |x|^2)
+    int bidx = ok ? code : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[q][tid >> 5] = best; s_bidx[q][tid >> 5] = bidx; }
   }
   __syncthreads();
-
-  const int per_thread = (a.bins + RVQ_THREADS - 1) / RVQ_THREADS;   // <= 8 (bins <= 2048)
-  for (int level = 0; level < a.levels[which]; ++level) {
-    const float* cbT = a.cbT[which] + (long long)level * a.Dq * a.bins;
-    const float* cn = a.cnorm[which] + (long long)level * a.bins;
-    float dots[8][RVQ_Q];
+  if (tid < RVQ_QT && q0 + tid < a.n_query) {
+    float best = s_best[tid][0];
+    int bidx = s_bidx[tid][0];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int q = 0; q < RVQ_Q; ++q) dots[j][q] = 0.f;
-    for (int d = 0; d < a.Dq; ++d) {
-      float xs[RVQ_Q];
-#pragma unroll
-      for (int q = 0; q < RVQ_Q; ++q) xs[q] = s_res[q * a.Dq + d];
-      const float* row = cbT + (long long)d * a.bins;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < per_thread) {
-          const int code = tid + j * RVQ_THREADS;
-          const float cv = code < a.bins ? row[code] : 0.f;
-#pragma unroll
-          for (int q = 0; q < RVQ_Q; ++q) dots[j][q] = fmaf(cv, xs[q], dots[j][q]);
-        }
-      }
+    for (int w = 1; w < RVQ_CHUNK / 32; ++w) {
+      const float ob = s_best[tid][w];
+      const int oi = s_bidx[tid][w];
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
     }
-#pragma unroll
-    for (int q = 0; q < RVQ_Q; ++q) {
-      float best = INFINITY;
-      int bidx = 0x7fffffff;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < per_thread) {
-          const int code = tid + j * RVQ_THREADS;
-          if (code < a.bins) {
-            const float s = cn[code] - 2.f * dots[j][q];
-            if (s < best) { best = s; bidx = code; }      // ascending code order: first min wins
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-      }
-      if ((tid & 31) == 0) { s_best[q][tid >> 5] = best; s_bidx[q][tid >> 5] = bidx; }
-    }
-    __syncthreads();
-    if (tid < RVQ_Q) {
-      float best = s_best[tid][0];
-      int bidx = s_bidx[tid][0];
-      for (int w = 1; w < RVQ_THREADS / 32; ++w) {
-        const float ob = s_best[tid][w];
-        const int oi = s_bidx[tid][w];
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-      }
-      s_choice[tid] = bidx;
-      const int qi = q0 + tid;
-      if (qi < a.n_query) {
-        const int b = qi / a.n_frames, f = qi % a.n_frames;
-        a.codes[b * a.cs_b + (a.level_offset[which] + level) * a.cs_k + f * a.cs_f] = bidx;
-      }
-    }
-    __syncthreads();
-    const float* cb = a.cb[which] + (long long)level * a.bins * a.Dq;
-    for (int i = tid; i < RVQ_Q * a.Dq; i += RVQ_THREADS) {
-      const int q = i / a.Dq, d = i % a.Dq;
-      s_res[i] -= cb[(long long)s_choice[q] * a.Dq + d];
-    }
-    __syncthreads();
+    a.part_best[which][(long long)(q0 + tid) * a.n_chunks + blockIdx.x] = best;
+    a.part_idx[which][(long long)(q0 + tid) * a.n_chunks + blockIdx.x] = bidx;
   }
+}
+
+// one CTA per (query, quantizer): argmin over the chunk partials, emit the code, res -= c[idx] (core_vq.py:514-516)
+static __global__ void __launch_bounds__(128) rvq_pick_kernel(const RvqLevelArgs a) {
+  const int which = blockIdx.y;
+  if (!a.active[which]) return;
+  const int q = blockIdx.x;
+  __shared__ int s_choice;
+  if (threadIdx.x < 32) {
+    float best = INFINITY;
+    int bidx = 0x7fffffff;
+    for (int c = threadIdx.x; c < a.n_chunks; c += 32) {
+      const float ob = a.part_best[which][(long long)q * a.n_chunks + c];
+      const int oi = a.part_idx[which][(long long)q * a.n_chunks + c];
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (threadIdx.x == 0) {
+      s_choice = bidx;
+      const int b = q / a.n_frames, f = q % a.n_frames;
+      a.codes[b * a.cs_b + a.code_index[which] * a.cs_k + f * a.cs_f] = bidx;
+    }
+  }
+  __syncthreads();
+  const float* c = a.cb[which] + (long long)s_choice * a.Dq;
+  float* r = a.res[which] + (long long)q * a.Dq;
+  for (int d = threadIdx.x; d < a.Dq; d += blockDim.x) r[d] -= c[d];
 }
 
 // codes [B][K][n] -> latent (vq.py:281-287): out = Wo_first . c0[idx0] + Wo_rest . sum_l c_l[idx_l]

@@ -25,6 +25,34 @@ int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M
   return check_launch("op_linear_bf16");
 }
 
+int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows) { return (int64_t)tc::sk_packed_bytes(N, K, epi, gate_rows); }
+
+int b200_op_pack_tiles(const void* w_dev, void* out_dev, int N, int K, int epi, int gate_rows, void* stream) {
+  if (!w_dev || !out_dev) B200_FAIL(B200_ERR_INVALID, "op_pack_tiles: null pointer");
+  return tc::sk_pack_weights(static_cast<const __nv_bfloat16*>(w_dev), out_dev, N, K, epi, gate_rows,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N, int K,
+                      int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream) {
+  if (!x_dev || !w_tiles_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_sk: null pointer");
+  if (!tc::sk_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_sk: unsupported shape");
+  static tc::GemmPlanCache cache;
+  static float* ws = nullptr;
+  static int* counters = nullptr;
+  if (!ws) {
+    B200_CUDA(cudaMalloc(&ws, tc::sk_workspace_bytes(256)));
+    B200_CUDA(cudaMalloc(&counters, tc::SK_MAX_TILES * sizeof(int)));
+    B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
+  }
+  tc::SkTuning t;
+  t.grid = grid; t.smem_budget = smem_budget; t.stream_only = stream_only;
+  const int out_cols = epi == 2 ? gate_rows : N;
+  return tc::sk_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev),
+                       out_cols, static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, ws, counters, t,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,
                    const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T, int K, int stride,
                    int dilation, int elu_in, void* stream) {

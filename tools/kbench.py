@@ -44,33 +44,51 @@ def time_ms(fn, n_rot: int, iters: int = 20, warm: int = 3) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def bench_gemm(lib, Ms):
-    shapes = [  # (name, N, K)
-        ("temporal.in_proj", 12288, 4096), ("temporal.out_proj", 4096, 4096), ("temporal.linear_in", 22528, 4096),
-        ("temporal.linear_out", 4096, 11264), ("text_linear", 32000, 4096), ("depformer_in_all", 8192, 4096),
-        ("dep.in_proj", 3072, 1024), ("dep.out_proj", 1024, 1024), ("dep.linear_in", 5632, 1024),
-        ("dep.linear_out", 1024, 2816), ("dep.head", 2048, 1024),
+def bench_gemm(lib, Ms, legacy=True):
+    shapes = [  # (name, N, K, epi, gate_rows)
+        ("temporal.in_proj", 12288, 4096, 0, 0), ("temporal.out_proj", 4096, 4096, 1, 0),
+        ("temporal.linear_in", 22528, 4096, 2, 11264), ("temporal.linear_out", 4096, 11264, 1, 0),
+        ("text_linear", 32000, 4096, 0, 0), ("depformer_in_all", 8192, 4096, 0, 0),
+        ("dep.in_proj", 3072, 1024, 0, 0), ("dep.out_proj", 1024, 1024, 1, 0), ("dep.linear_in", 5632, 1024, 2, 2816),
+        ("dep.linear_out", 1024, 2816, 1, 0), ("dep.head", 2048, 1024, 0, 0),
     ]
-    for name, N, K in shapes:
+    for name, N, K, epi, gr in shapes:
         wbytes = N * K * 2
         n_rot = max(2, -(-(400 << 20) // wbytes))
         ws = [torch.empty(N, K, device="cuda", dtype=torch.bfloat16).uniform_(-0.02, 0.02) for _ in range(n_rot)]
+        pk = []
+        for w in ws:
+            out = torch.empty(lib.b200_op_packed_bytes(N, K, epi, gr), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.b200_op_pack_tiles(_lib.ptr(w), _lib.ptr(out), N, K, epi, gr, stream()))
+            pk.append(out)
+        cols = gr if epi == 2 else N
         for M in Ms:
             x = torch.empty(M, K, device="cuda", dtype=torch.bfloat16).uniform_(-1, 1)
             y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            res = torch.zeros(M, cols, device="cuda", dtype=torch.bfloat16)
+            alg = wbytes + M * K * 2 + M * cols * 2 * (2 if epi == 1 else 1)
+            variants = [("sk", 0, 0, 0), ("sk.stream_only", 0, 0, 1), ("sk.2cta", 296, 100 << 10, 0),
+                        ("sk.2cta.stream_only", 296, 100 << 10, 1), ("sk.grid74", 74, 0, 0)]
+            for vname, grid, smem, so in variants:
+                def fn(i):
+                    _lib.check(lib.b200_op_linear_sk(_lib.ptr(x), _lib.ptr(pk[i]), _lib.ptr(y), _lib.ptr(res), M, N, K, epi, gr,
+                                                     grid, smem, so, stream()))
+                ms = time_ms(fn, n_rot)
+                gbs = alg / ms / 1e6
+                print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": vname, "ms": round(ms, 4),
+                                  "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+            if not legacy or epi != 0:
+                continue
             for impl in (1, 2):
+                if impl == 1 and M > 1:
+                    continue
                 def fn(i):
                     _lib.check(lib.b200_op_linear_bf16(_lib.ptr(x), _lib.ptr(ws[i]), _lib.ptr(y), M, N, K, impl, stream()))
-                try:
-                    ms = time_ms(fn, n_rot)
-                except Exception as e:  # unsupported shape
-                    print(json.dumps({"kernel": "linear", "name": name, "M": M, "impl": impl, "error": str(e)[:80]}), flush=True)
-                    continue
-                alg = wbytes + M * K * 2 + M * N * 2
+                ms = time_ms(fn, n_rot)
                 gbs = alg / ms / 1e6
                 print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": impl, "ms": round(ms, 4),
                                   "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
-        del ws
+        del ws, pk
 
 
 def bench_attn(lib, Bs, cap=3000, H=32):
