@@ -29,7 +29,7 @@ constexpr int MAX_STAGES = 12;
 struct SkParams {
   int M, N, K, Mpad, gate_rows, out_rows;
   int stages, num_kb, n_tiles, n_acc, acc_cols;
-  long long total_items;
+  int grid, whole_rounds, sk_tile0, sk_items;   // schedule: tiles [0, sk_tile0) whole, the rest stream-K items
   const uint8_t* wt;            // pre-tiled weights
   __nv_bfloat16* y; long long ldy;
   const __nv_bfloat16* res; long long ldr;
@@ -112,13 +112,43 @@ __device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-__device__ __forceinline__ long long item_begin(long long total, int c, int G) { return total * c / G; }
-// CTA whose item range [item_begin(c), item_begin(c + 1)) holds item j
-__device__ __forceinline__ int item_owner(long long total, long long j, int G) {
-  int c = (int)(j * G / total);
-  while (c + 1 < G && item_begin(total, c + 1, G) <= j) ++c;
-  while (c > 0 && item_begin(total, c, G) > j) --c;
+// ---------------------------------------------------------------------------------------------
+// schedule: every CTA first takes its share of the stream-K region (the n_tiles - W*G tiles that do
+// not fill a whole round of the grid, cut by k-blocks into G equal contiguous item ranges), then W
+// whole tiles (tile = w*G + c).  Partial accumulators are therefore written early in the kernel and
+// their reduction overlaps the whole tiles.  All three warp roles walk the same segment list.
+// ---------------------------------------------------------------------------------------------
+struct Seg { int tile, kb0, kb1, slot; };   // slot: -1 = whole tile, else workspace slot of this partial
+
+__device__ __forceinline__ int sk_begin(const SkParams& p, int c) { return (int)((long long)p.sk_items * c / p.grid); }
+// CTA whose stream-K item range holds item j
+__device__ __forceinline__ int sk_owner(const SkParams& p, int j) {
+  int c = (int)((long long)j * p.grid / p.sk_items);
+  while (c + 1 < p.grid && sk_begin(p, c + 1) <= j) ++c;
+  while (c > 0 && sk_begin(p, c) > j) --c;
   return c;
+}
+__device__ __forceinline__ int seg_count(const SkParams& p, int c, int& n_sk) {
+  const int a = sk_begin(p, c), b = sk_begin(p, c + 1);
+  n_sk = a < b ? (b - 1) / p.num_kb - a / p.num_kb + 1 : 0;
+  int n = n_sk;
+  for (int w = 0; w < p.whole_rounds; ++w) n += (w * p.grid + c < p.sk_tile0) ? 1 : 0;
+  return n;
+}
+__device__ __forceinline__ Seg seg_get(const SkParams& p, int c, int n_sk, int idx) {
+  Seg s;
+  if (idx < n_sk) {
+    const int a = sk_begin(p, c), b = sk_begin(p, c + 1);
+    const int first = a / p.num_kb;
+    s.tile = p.sk_tile0 + first + idx;
+    s.kb0 = idx == 0 ? a - first * p.num_kb : 0;
+    s.kb1 = idx == n_sk - 1 ? (b - 1) % p.num_kb + 1 : p.num_kb;
+    s.slot = (s.kb0 == 0 && s.kb1 == p.num_kb) ? -1 : 2 * c + (idx == 0 ? 0 : 1);
+  } else {
+    s.tile = (idx - n_sk) * p.grid + c;      // rounds are dense: a CTA without a tile in the last round has fewer segments
+    s.kb0 = 0; s.kb1 = p.num_kb; s.slot = -1;
+  }
+  return s;
 }
 
 template <int EPI>
@@ -144,8 +174,9 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int A_TILES = EPI == EPI_GATE ? 2 : 1;
   constexpr uint32_t a_bytes = A_TILES * TILE_BYTES;
-  const int G = gridDim.x, c = blockIdx.x;
-  const long long i0 = item_begin(p.total_items, c, G), i1 = item_begin(p.total_items, c + 1, G);
+  const int c = blockIdx.x;
+  int n_sk = 0;
+  const int n_seg = seg_count(p, c, n_sk);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
@@ -167,16 +198,19 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== producer: one contiguous bulk copy of the weight tile(s) + one TMA box of activations per item =====
+      // ===== producer: one contiguous bulk copy of the weight tile(s) + one TMA box of activations per k-block =====
       int s = 0; uint32_t ph = 0;
-      for (long long i = i0; i < i1; ++i) {
-        const int kb = (int)(i % p.num_kb);
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
-        mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
-        bulk_load(sa, p.wt + (size_t)i * a_bytes, a_bytes, full0 + 8 * s);
-        tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      for (int si = 0; si < n_seg; ++si) {
+        const Seg sg = seg_get(p, c, n_sk, si);
+        const uint8_t* src = p.wt + ((size_t)sg.tile * p.num_kb + sg.kb0) * a_bytes;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, src += a_bytes) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+          mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
+          bulk_load(sa, src, a_bytes, full0 + 8 * s);
+          tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -185,15 +219,12 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
       const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_bits = 0u;       // bit a = phase parity of accumulator stage a
-      long long i = i0;
-      while (i < i1) {
-        const int kb0 = (int)(i % p.num_kb);
-        const long long seg_end = (i - kb0 + p.num_kb) < i1 ? (i - kb0 + p.num_kb) : i1;
+      for (int si = 0; si < n_seg; ++si) {
+        const Seg sg = seg_get(p, c, n_sk, si);
         mbar_wait(tempty0 + 8 * acc, ((acc_bits >> acc) & 1u) ^ 1u);        // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_cols);
-        bool first = true;
-        for (; i < seg_end; ++i) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           if (!p.stream_only) {
@@ -202,12 +233,11 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t db = make_desc(sb + k * UMMA_K * 2);
-              const uint32_t accum = (first && k == 0) ? 0u : 1u;
+              const uint32_t accum = (kb == sg.kb0 && k == 0) ? 0u : 1u;
               umma_bf16(d0, make_desc(sa + k * UMMA_K * 2), db, idesc, accum);
               if (EPI == EPI_GATE) umma_bf16(d0 + (uint32_t)p.Mpad, make_desc(sa + TILE_BYTES + k * UMMA_K * 2), db, idesc, accum);
             }
           }
-          first = false;
           umma_commit(empty0 + 8 * s);           // frees the smem stage once these MMAs have read it
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -222,21 +252,16 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;           // 0..127
-    int acc = 0; uint32_t acc_bits = 0u;       // bit a = phase parity of accumulator stage a
-    long long i = i0;
-    int seg_idx = 0;
-    while (i < i1) {
-      const int tile = (int)(i / p.num_kb);
-      const int kb0 = (int)(i % p.num_kb);
-      const long long tile_end = i - kb0 + p.num_kb;
-      const long long seg_end = tile_end < i1 ? tile_end : i1;
-      const bool whole = kb0 == 0 && seg_end == tile_end;
-      const int n = tile * BLOCK_ROWS + row;
+    const size_t slot_floats = (size_t)A_TILES * BLOCK_ROWS * p.Mpad;
+    int acc = 0; uint32_t acc_bits = 0u;
+    for (int si = 0; si < n_seg; ++si) {
+      const Seg sg = seg_get(p, c, n_sk, si);
+      const int n = sg.tile * BLOCK_ROWS + row;
       const bool n_ok = n < p.out_rows;
       mbar_wait(tfull0 + 8 * acc, (acc_bits >> acc) & 1u);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-      if (whole) {
+      if (sg.slot < 0) {
         for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
           uint32_t r0[16], r1[16];
           tmem_ld16(lane_addr + (uint32_t)c0, r0);
@@ -256,54 +281,70 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       } else {
-        // partial accumulator -> workspace slot (2 * cta + segment parity), layout [A][Mpad][128]
-        const int slot = 2 * c + (seg_idx == 0 ? 0 : 1);
-        float* ws = p.ws + (size_t)slot * A_TILES * p.Mpad * BLOCK_ROWS;
+        // partial accumulator -> workspace slot, layout [A][128 rows][Mpad] (a thread owns one contiguous row)
+        float* wrow = p.ws + (size_t)sg.slot * slot_floats + (size_t)row * p.Mpad;
         for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
           uint32_t r0[16], r1[16];
           tmem_ld16(lane_addr + (uint32_t)c0, r0);
           if (EPI == EPI_GATE) tmem_ld16(lane_addr + (uint32_t)(p.Mpad + c0), r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __stcg(ws + (size_t)(c0 + j) * BLOCK_ROWS + row, __uint_as_float(r0[j]));
-            if (EPI == EPI_GATE) __stcg(ws + (size_t)(p.Mpad + c0 + j) * BLOCK_ROWS + row, __uint_as_float(r1[j]));
+          for (int j = 0; j < 16; j += 4) {
+            __stcg(reinterpret_cast<float4*>(wrow + c0 + j),
+                   make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3])));
+            if (EPI == EPI_GATE)
+              __stcg(reinterpret_cast<float4*>(wrow + (size_t)BLOCK_ROWS * p.Mpad + c0 + j),
+                     make_float4(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]), __uint_as_float(r1[j + 2]), __uint_as_float(r1[j + 3])));
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        // publish, count arrivals; the last arriver of this tile reduces in CTA order
+        // publish, count arrivals; the last arriver of this tile reduces all partials in CTA order
         __threadfence();
         epi_bar_sync();
-        const int first_c = item_owner(p.total_items, (long long)tile * p.num_kb, G);
-        const int last_c = item_owner(p.total_items, (long long)(tile + 1) * p.num_kb - 1, G);
-        const int nseg = last_c - first_c + 1;
+        const int rel = sg.tile - p.sk_tile0;
+        const int first_c = sk_owner(p, rel * p.num_kb), last_c = sk_owner(p, (rel + 1) * p.num_kb - 1);
         if (et == 0) {
-          const int old = atomicAdd(p.counters + tile, 1);
-          s_last = (old == nseg - 1) ? 1 : 0;
-          if (old == nseg - 1) p.counters[tile] = 0;           // ready for the next launch
+          const int old = atomicAdd(p.counters + sg.tile, 1);
+          const int last = old == last_c - first_c;
+          s_last = last;
+          if (last) p.counters[sg.tile] = 0;                     // ready for the next launch
         }
         epi_bar_sync();
         if (s_last) {
           __threadfence();
-          for (int m = 0; m < p.M; ++m) {
-            float a = 0.f, b = 0.f;
+          for (int m0 = 0; m0 < p.M; m0 += 8) {
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
             for (int cc = first_c; cc <= last_c; ++cc) {
-              const long long ci0 = item_begin(p.total_items, cc, G);
-              const int sl = 2 * cc + ((int)(ci0 / p.num_kb) == tile ? 0 : 1);
-              const float* w2 = p.ws + (size_t)sl * A_TILES * p.Mpad * BLOCK_ROWS;
-              a += __ldcg(w2 + (size_t)m * BLOCK_ROWS + row);
-              if (EPI == EPI_GATE) b += __ldcg(w2 + (size_t)(p.Mpad + m) * BLOCK_ROWS + row);
+              const int sl = 2 * cc + ((sk_begin(p, cc) / p.num_kb == rel) ? 0 : 1);
+              const float* w2 = p.ws + (size_t)sl * slot_floats + (size_t)row * p.Mpad + m0;
+              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(w2));
+              const float4 v1 = (m0 + 4 < p.Mpad) ? __ldcg(reinterpret_cast<const float4*>(w2 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+              a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+              if (EPI == EPI_GATE) {
+                const float* w3 = w2 + (size_t)BLOCK_ROWS * p.Mpad;
+                const float4 u0 = __ldcg(reinterpret_cast<const float4*>(w3));
+                const float4 u1 = (m0 + 4 < p.Mpad) ? __ldcg(reinterpret_cast<const float4*>(w3 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                b0.x += u0.x; b0.y += u0.y; b0.z += u0.z; b0.w += u0.w;
+                b1.x += u1.x; b1.y += u1.y; b1.z += u1.z; b1.w += u1.w;
+              }
             }
-            if (n_ok && !p.stream_only) p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, a, b, m, n));
+            if (n_ok && !p.stream_only) {
+              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int m = m0 + j;
+                if (m < p.M) p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, av[j], bv[j], m, n));
+              }
+            }
           }
         }
       }
       acc_bits ^= 1u << acc;
       if (p.n_acc == 2) acc ^= 1;
-      i = seg_end;
-      ++seg_idx;
     }
   }
   tc_fence_before();
@@ -349,7 +390,7 @@ int init_once() {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   if (!g_attr_set) {
-    const int max_smem = 227 * 1024;
+    const int max_smem = 220 * 1024;     // the kernel also has a few bytes of static shared memory
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_RESADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -411,7 +452,18 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   p.n_tiles = (p.out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
   if (p.n_tiles > 1024) B200_FAIL(B200_ERR_SHAPE, "sk GEMM: more than 1024 row tiles");
-  p.total_items = (long long)p.n_tiles * p.num_kb;
+  int grid = tune.grid > 0 ? tune.grid : g_sms;
+  if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
+  if (grid > p.n_tiles * p.num_kb) grid = p.n_tiles * p.num_kb;
+  // whole rounds of the grid, then the remainder: stream-K it unless it nearly fills a round anyway (or the
+  // partials would be as large as the weights they save waiting for: M large and few k-blocks)
+  p.grid = grid;
+  p.whole_rounds = p.n_tiles / grid;
+  int rem = p.n_tiles - p.whole_rounds * grid;
+  const bool split = rem > 0 && rem * 8 < grid * 7 && tune.no_split == 0;
+  if (rem > 0 && !split) { p.whole_rounds += 1; rem = 0; }
+  p.sk_tile0 = p.n_tiles - rem;
+  p.sk_items = rem * p.num_kb;
   const int a_tiles = epi == EPI_GATE ? 2 : 1;
   p.stage_bytes = (uint32_t)(a_tiles * TILE_BYTES + p.Mpad * BLOCK_K * 2);
   int stages = (tune.smem_budget > 0 ? tune.smem_budget : 200 * 1024) / (int)p.stage_bytes;
@@ -424,10 +476,6 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   while (pow2 < cols) pow2 <<= 1;
   p.tmem_cols = pow2;
   p.stream_only = tune.stream_only;
-  int grid = tune.grid > 0 ? tune.grid : g_sms;
-  if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
-  if ((long long)grid > p.total_items) grid = (int)p.total_items;
-  // every CTA must own >= 1 item and a tile may not be cut into more pieces than the workspace indexes
   const CUtensorMap* mx = nullptr;
   {
     PlanKey key{x, ldx, M, K, p.Mpad};

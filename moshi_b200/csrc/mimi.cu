@@ -1,6 +1,7 @@
 // Mimi handle: weight ingestion (reference state-dict names), streaming state, encode / decode.
 // Reference orchestration: moshi/moshi/models/compression.py:338-433.
 #include "mimi_kernels.cuh"
+#include "mimi_gemm.cuh"
 
 using namespace b200;
 using namespace b200::mimi;
@@ -23,6 +24,11 @@ struct ConvLayer {
   float* scratch = nullptr;  // convtr candidate partial
   uint8_t* first = nullptr;  // replicate flag [B]
   std::string tap;           // debug name of the output buffer
+  // mimi_gemm.cuh path: k-major weights and the extended input buffer (carried state | frame), see there
+  bool fast = false;
+  float* wk = nullptr;
+  float* ext = nullptr;      // conv: ext [B][Cin][E]; convtr: zero-padded input [B][Cin][E]
+  int E = 0, D0 = 0;         // row length; index of the first sample of the current frame
 };
 
 struct Buf {
@@ -35,7 +41,7 @@ struct Buf {
 };
 
 struct TrLayer {
-  const float *in_w, *out_w, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2;
+  const float *in_w, *out_w, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2;   // linear weights k-major [K][M]
   float *kc = nullptr, *vc = nullptr;
 };
 
@@ -76,6 +82,8 @@ struct b200_mimi {
   ConvCommit *enc_commits = nullptr, *dec_commits = nullptr;
   int n_enc_commits = 0, n_dec_commits = 0, max_enc_rows = 0, max_dec_rows = 0;
   ConvTrCommit* dec_tr_commits = nullptr; int n_dec_tr_commits = 0; long long max_tr_rows = 0;
+  ExtCommit *enc_ext_commits = nullptr, *dec_ext_commits = nullptr;
+  int n_enc_ext = 0, n_dec_ext = 0, max_enc_ext_rows = 0, max_dec_ext_rows = 0;
   long long* scratch_codes = nullptr;          // [B][K][1] for the host variants
   float* rvq_res[2] = {nullptr, nullptr};      // RVQ workspace: residuals, per-chunk partial argmin
   float* rvq_best[2] = {nullptr, nullptr};
@@ -197,18 +205,30 @@ int get_f32(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, c
 
 int pack_conv(b200_mimi* h, ConvLayer& l) {
   const float* w = nullptr;
+  l.fast = !l.replicate && (l.cin % GK) == 0 && (l.kind == 0 ? l.cout % 4 == 0 : (l.cout * l.stride) % 4 == 0);
+  if (getenv("B200_MIMI_LEGACY")) l.fast = false;          // debug switch: first-generation kernels only
   if (l.kind == 0) {
     B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
     const long long n = (long long)l.cout * l.cin * l.k;
-    B200_TRY(h->weights.alloc_t(&l.w, n, false));
-    B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cout, l.cin, l.k);
+    if (l.fast) {
+      B200_TRY(h->weights.alloc_t(&l.wk, n, false));
+      B200_LAUNCH(pack_conv_k_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.wk, l.cout, l.cin, l.k);
+    } else {
+      B200_TRY(h->weights.alloc_t(&l.w, n, false));
+      B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cout, l.cin, l.k);
+    }
     h->weight_bytes += n * 4;
   } else {
     if (l.k != 2 * l.stride) B200_FAIL(B200_ERR_INVALID, "convtr %s: kernel must be 2*stride", l.key.c_str());
     B200_TRY(get_f32(h, l.key + ".weight", {l.cin, l.cout, l.k}, &w));
     const long long n = (long long)l.cin * l.cout * l.k;
-    B200_TRY(h->weights.alloc_t(&l.w, n, false));
-    B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cin, l.cout, l.stride);
+    if (l.fast) {
+      B200_TRY(h->weights.alloc_t(&l.wk, n, false));
+      B200_LAUNCH(pack_convtr_k_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.wk, l.cin, l.cout, l.stride);
+    } else {
+      B200_TRY(h->weights.alloc_t(&l.w, n, false));
+      B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cin, l.cout, l.stride);
+    }
     h->weight_bytes += n * 4;
   }
   if (l.has_bias) {
@@ -218,6 +238,7 @@ int pack_conv(b200_mimi* h, ConvLayer& l) {
     B200_CUDA(cudaMemcpy(l.bias, b, l.cout * 4, cudaMemcpyDeviceToDevice));
     h->weight_bytes += l.cout * 4;
   }
+  B200_CUDA(cudaDeviceSynchronize());
   h->store.release(l.key + ".weight");
   h->store.release(l.key + ".bias");
   return check_launch("pack_conv");
@@ -237,6 +258,20 @@ int keep(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, cons
   return B200_OK;
 }
 
+// nn.Linear weight [M][K] -> k-major [K][M] (A operand of mimi_gemm_kernel)
+int keep_kmajor(b200_mimi* h, const std::string& name, int M, int K, const float** out) {
+  const float* src = nullptr;
+  B200_TRY(get_f32(h, name, {M, K}, &src));
+  float* dst = nullptr;
+  B200_TRY(h->weights.alloc_t(&dst, (size_t)M * K, false));
+  B200_LAUNCH(transpose_kernel, (unsigned)ceil_div64((long long)M * K, 256), 256, 0, 0, src, dst, M, K);
+  B200_CUDA(cudaDeviceSynchronize());
+  h->store.release(name);
+  h->weight_bytes += (int64_t)M * K * 4;
+  *out = dst;
+  return check_launch("keep_kmajor");
+}
+
 int pack_transformer(b200_mimi* h, const std::string& prefix, Transformer& tr) {
   const auto& c = h->cfg;
   const int d = c.tr_d_model, ff = c.tr_dim_feedforward;
@@ -244,14 +279,14 @@ int pack_transformer(b200_mimi* h, const std::string& prefix, Transformer& tr) {
   for (int li = 0; li < c.tr_num_layers; ++li) {
     const std::string p = prefix + ".transformer.layers." + std::to_string(li);
     TrLayer& L = tr.layers[li];
-    B200_TRY(keep(h, p + ".self_attn.in_projs.0.weight", {3 * d, d}, &L.in_w));
-    B200_TRY(keep(h, p + ".self_attn.out_projs.0.weight", {d, d}, &L.out_w));
+    B200_TRY(keep_kmajor(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, &L.in_w));
+    B200_TRY(keep_kmajor(h, p + ".self_attn.out_projs.0.weight", d, d, &L.out_w));
     B200_TRY(keep(h, p + ".norm1.weight", {d}, &L.n1w));
     B200_TRY(keep(h, p + ".norm1.bias", {d}, &L.n1b));
     B200_TRY(keep(h, p + ".norm2.weight", {d}, &L.n2w));
     B200_TRY(keep(h, p + ".norm2.bias", {d}, &L.n2b));
-    B200_TRY(keep(h, p + ".linear1.weight", {ff, d}, &L.l1));
-    B200_TRY(keep(h, p + ".linear2.weight", {d, ff}, &L.l2));
+    B200_TRY(keep_kmajor(h, p + ".linear1.weight", ff, d, &L.l1));
+    B200_TRY(keep_kmajor(h, p + ".linear2.weight", d, ff, &L.l2));
     B200_TRY(keep(h, p + ".layer_scale_1.scale", {d}, &L.ls1));
     B200_TRY(keep(h, p + ".layer_scale_2.scale", {d}, &L.ls2));
   }
@@ -303,10 +338,56 @@ int pack_quantizer(b200_mimi* h) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+// tile choice: the largest tile that still gives every SM a couple of CTAs
+template <int KIND>
+int launch_gemm(b200_mimi* h, const GemmArgs& a) {
+  auto ctas = [&](int bm, int bn) { return (long long)ceil_div(a.M, bm) * ceil_div(a.N, bn); };
+  const long long want = 2 * 148;
+  if (a.M > 64 && ctas(128, 128) >= want) {
+    dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 128));
+    B200_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->stream, a);
+  } else if (ctas(64, 128) >= want) {
+    dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 64));
+    B200_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->stream, a);
+  } else {
+    dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
+    B200_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->stream, a);
+  }
+  return check_launch("mimi_gemm");
+}
+
+// One SEANet layer.  (y, strides) = raw output; `next` (may be null) = the layer that consumes it: when that layer
+// runs on the mimi_gemm.cuh path its activated input is written here, behind its carried state.
 int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, long long xc, long long xt,
                 float* y, long long yb, long long yc, long long yt, const float* res, long long rb, long long rc,
-                long long rt) {
+                long long rt, const ConvLayer* next = nullptr) {
   const int B = h->batch;
+  float* act = nullptr; long long ab = 0, ac = 0; int a_elu = 0;
+  if (next && next->fast) {
+    act = next->ext + next->D0; ab = (long long)next->cin * next->E; ac = next->E; a_elu = next->elu_in;
+  }
+  if (l.fast) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.wk = l.wk; a.in = l.ext; a.in_b = (long long)l.cin * l.E; a.in_E = l.E;
+    a.Cin = l.cin; a.bias = l.bias;
+    a.y = y; a.yb = yb; a.yc = yc; a.yt = yt;
+    a.a = act; a.ab = ab; a.ac = ac; a.at = 1; a.a_elu = a_elu;
+    if (l.kind == 0) {
+      a.in_off = l.D0 - l.P;
+      a.M = l.cout; a.N = B * l.t_out; a.Kd = l.cin * l.k; a.stride = l.stride; a.dil = l.dil; a.T = l.t_out;
+      a.res = res; a.rb = rb; a.rc = rc; a.rt = rt;
+      const bool t4 = l.t_out % 4 == 0;
+      a.vec_y = y && t4 && yt == 1 && yb % 4 == 0 && yc % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+      a.vec_a = act && t4;
+      a.vec_r = res && t4 && rt == 1 && rb % 4 == 0 && rc % 4 == 0;
+      return launch_gemm<G_CONV>(h, a);
+    }
+    a.in_off = l.D0;
+    a.M = l.cout * l.stride; a.N = B * (l.t_in + 1); a.Kd = 2 * l.cin; a.stride = l.stride; a.T = l.t_in;
+    a.partial = l.state; a.scratch = l.scratch;
+    return launch_gemm<G_CONVTR>(h, a);
+  }
   if (l.kind == 0) {
     ConvP p;
     p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.Tin = l.t_in;
@@ -314,12 +395,14 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     p.w = l.w; p.bias = l.bias;
     p.y = y; p.yb = yb; p.yc = yc; p.yt = yt;
     p.res = res; p.rb = rb; p.rc = rc; p.rt = rt;
+    p.a = act; p.ab = ab; p.ac = ac; p.at = 1; p.a_elu = a_elu;
     p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.K = l.k; p.stride = l.stride; p.dil = l.dil; p.Tout = l.t_out;
     p.elu_in = l.elu_in;
     p.M = l.cout; p.N = B * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
     B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->stream, p);
   } else {
+    if (act) B200_FAIL(B200_ERR_INVALID, "first-generation convtr cannot feed a mimi_gemm layer");
     ConvTrP p;
     p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.T = l.t_in;
     p.partial = l.state; p.scratch = l.scratch; p.w = l.w; p.bias = l.bias;
@@ -332,14 +415,15 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
   return check_launch(l.key.c_str());
 }
 
+// y[n][m] = epi(sum_k x[n][k] * w[m][k]) on token-major activations; w is k-major [K][M]
 int launch_linear(b200_mimi* h, const float* x, int K, const float* w, float* y, int M, int ntok, int epi,
                   const float* res, const float* scale) {
-  LinP p;
-  p.x = x; p.ldx = K; p.w = w; p.y = y; p.ldy = M; p.res = res; p.scale = scale; p.epi = epi;
-  p.M = M; p.N = ntok; p.Kd = K;
-  dim3 grid(ceil_div(ntok, BN), ceil_div(M, BM));
-  B200_LAUNCH((igemm_f32_kernel<LinP, true>), grid, 256, 0, h->stream, p);
-  return check_launch("mimi linear");
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.wk = w; a.in = x; a.in_E = K; a.M = M; a.N = ntok; a.Kd = K;
+  a.y = y; a.yb = M; a.res = res; a.scale = scale;
+  a.lin_epi = epi == EPI_GELU ? GL_GELU : epi == EPI_RES_SCALE ? GL_RES_SCALE : GL_NONE;
+  return launch_gemm<G_LIN>(h, a);
 }
 
 // StreamingTransformer.forward for T tokens per row (transformer.py:894-929, layer :752-802)
@@ -372,6 +456,12 @@ int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, 
 int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, const float* x0, long long xb,
                long long xc, long long xt, float* last_out, long long lb, long long lc, long long lt) {
   // bufs[i] is the output of layers[i]; layer 0 reads (x0, strides); the last layer writes last_out.
+  if (layers[0].fast) {   // its input comes from outside the SEANet (transformer output): copy it behind the carried state
+    const ConvLayer& l = layers[0];
+    const long long n = (long long)h->batch * l.cin * l.t_in;
+    B200_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->stream, x0, xb, xc, xt, l.ext + l.D0,
+                (long long)l.cin * l.E, (long long)l.E, 1LL, h->batch, l.cin, l.t_in, (int)l.elu_in);
+  }
   for (size_t i = 0; i < layers.size(); ++i) {
     ConvLayer& l = layers[i];
     const float* x; long long sb, sc, st;
@@ -386,7 +476,8 @@ int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& b
       const Buf& b = bufs[i - 2];
       res = b.p; rb = b.sb(0); rc = b.sc(); rt = b.st();
     }
-    B200_TRY(launch_conv(h, l, x, sb, sc, st, y, yb, yc, yt, res, rb, rc, rt));
+    const ConvLayer* next = i + 1 < layers.size() ? &layers[i + 1] : nullptr;
+    B200_TRY(launch_conv(h, l, x, sb, sc, st, y, yb, yc, yt, res, rb, rc, rt, next));
   }
   return B200_OK;
 }
@@ -394,13 +485,25 @@ int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& b
 int commit_states(b200_mimi* h, bool encoder) {
   const int B = h->batch;
   if (encoder) {
-    dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
-    B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
-    B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->stream, h->enc_commits,
-                h->n_enc_commits, h->exec_mask, B);
+    if (h->n_enc_commits) {
+      dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
+      B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->stream, h->enc_commits,
+                  h->n_enc_commits, h->exec_mask, B);
+    }
+    if (h->n_enc_ext) {
+      dim3 grid(ceil_div(h->max_enc_ext_rows, 128), h->n_enc_ext);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->stream, h->enc_ext_commits, h->exec_mask, B);
+    }
   } else {
-    dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
-    B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+    if (h->n_dec_commits) {
+      dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+    }
+    if (h->n_dec_ext) {
+      dim3 grid(ceil_div(h->max_dec_ext_rows, 128), h->n_dec_ext);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->stream, h->dec_ext_commits, h->exec_mask, B);
+    }
     dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);
     B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->stream, h->dec_tr_commits, h->exec_mask, B);
   }
@@ -617,13 +720,15 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_CUDA(cudaMemset(h->first_flags, 1, (size_t)h->n_first * B));
 
   std::vector<ConvCommit> enc_c, dec_c;
+  std::vector<ExtCommit> enc_e, dec_e;
   std::vector<ConvTrCommit> dec_t;
   h->max_enc_rows = h->max_dec_rows = 0;
+  h->max_enc_ext_rows = h->max_dec_ext_rows = 0;
   h->max_tr_rows = 0;
 
   auto setup = [&](std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, int t0, bool last_token_major,
                    const float* x0, long long x0b, long long x0c, long long x0t, std::vector<ConvCommit>& commits,
-                   const char* tag, bool is_dec) -> int {
+                   std::vector<ExtCommit>& ecommits, bool is_dec) -> int {
     bufs.assign(layers.size(), Buf());
     int t = t0;
     for (size_t i = 0; i < layers.size(); ++i) {
@@ -633,12 +738,23 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
         if (t % l.stride) B200_FAIL(B200_ERR_INVALID, "%s: %d samples not divisible by stride %d", l.key.c_str(), t, l.stride);
         l.t_out = t / l.stride;
         l.P = (l.k - 1) * l.dil + 1 - l.stride;
-        if (l.P > 0) B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
+        if (l.fast) {          // carried samples live inside ext, right in front of the 16-byte aligned frame
+          l.D0 = (l.P + 3) / 4 * 4;
+          l.E = (l.D0 + t + 3) / 4 * 4;
+          B200_TRY(A.alloc_t(&l.ext, (size_t)B * l.cin * l.E));
+        } else if (l.P > 0) {
+          B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
+        }
       } else {
         l.t_out = t * l.stride;
         l.P = l.k - l.stride;
         B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cout * l.P));
         B200_TRY(A.alloc_t(&l.scratch, (size_t)B * l.cout * l.P));
+        if (l.fast) {          // zero column on both sides of the frame: taps that fall outside read 0
+          l.D0 = 4;
+          l.E = (l.D0 + t + 1 + 3) / 4 * 4;
+          B200_TRY(A.alloc_t(&l.ext, (size_t)B * l.cin * l.E));
+        }
       }
       t = l.t_out;
       Buf& b = bufs[i];
@@ -653,7 +769,13 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
       const float* x; long long sb, sc, st;
       if (i == 0) { x = x0; sb = x0b; sc = x0c; st = x0t; }
       else { const Buf& pb = bufs[i - 1]; x = pb.p; sb = pb.sb(0); sc = pb.sc(); st = pb.st(); }
-      if (l.kind == 0 && l.P > 0) {
+      if (l.kind == 0 && l.P > 0 && l.fast) {
+        ExtCommit ec;
+        ec.ext = l.ext + (l.D0 - l.P); ec.P = l.P; ec.T = l.t_in; ec.E = l.E; ec.Cin = l.cin;
+        ecommits.push_back(ec);
+        int& mx = is_dec ? h->max_dec_ext_rows : h->max_enc_ext_rows;
+        if (B * l.cin > mx) mx = B * l.cin;
+      } else if (l.kind == 0 && l.P > 0) {
         ConvCommit cc;
         cc.x = x; cc.xb = sb; cc.xc = sc; cc.xt = st; cc.Tin = l.t_in; cc.st = l.state; cc.P = l.P; cc.Cin = l.cin;
         cc.elu_in = l.elu_in; cc.first = nullptr;
@@ -668,7 +790,6 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
         if ((long long)B * tc.per_row > h->max_tr_rows) h->max_tr_rows = (long long)B * tc.per_row;
       }
     }
-    (void)tag;
     return B200_OK;
   };
 
@@ -679,11 +800,11 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->latent_q, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->tok_in_dec, (size_t)B * T * d));
   B200_TRY(A.alloc_t(&h->tok_dec, (size_t)B * T * d));
-  B200_TRY(setup(h->enc, h->enc_bufs, h->frame_size, true, h->in_frame, h->frame_size, 0, 1, enc_c, "enc", false));
+  B200_TRY(setup(h->enc, h->enc_bufs, h->frame_size, true, h->in_frame, h->frame_size, 0, 1, enc_c, enc_e, false));
   // the last encoder conv writes tok_in_enc instead of its own buffer
   register_tap(h, h->enc.back().tap, h->tok_in_enc, (int64_t)B * T * d);
   if (h->enc.back().t_out != T) B200_FAIL(B200_ERR_INVALID, "encoder yields %d tokens/frame, expected %d", h->enc.back().t_out, T);
-  B200_TRY(setup(h->dec, h->dec_bufs, T, false, h->tok_dec, (long long)T * d, 1, d, dec_c, "dec", true));
+  B200_TRY(setup(h->dec, h->dec_bufs, T, false, h->tok_dec, (long long)T * d, 1, d, dec_c, dec_e, true));
   if (h->dec.back().t_out != h->frame_size) B200_FAIL(B200_ERR_INVALID, "decoder yields %d samples/frame", h->dec.back().t_out);
   register_tap(h, "enc.tr", h->tok_enc, (int64_t)B * T * d);
   register_tap(h, "enc.latent", h->latent, (int64_t)B * d);
@@ -715,13 +836,22 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   h->n_enc_commits = (int)enc_c.size();
   h->n_dec_commits = (int)dec_c.size();
   h->n_dec_tr_commits = (int)dec_t.size();
-  B200_TRY(A.alloc_t(&h->enc_commits, enc_c.size(), false));
+  h->n_enc_ext = (int)enc_e.size();
+  h->n_dec_ext = (int)dec_e.size();
+  B200_TRY(A.alloc_t(&h->enc_commits, enc_c.size() ? enc_c.size() : 1, false));
   B200_TRY(A.alloc_t(&h->dec_commits, dec_c.size() ? dec_c.size() : 1, false));
   B200_TRY(A.alloc_t(&h->dec_tr_commits, dec_t.size(), false));
-  B200_CUDA(cudaMemcpy(h->enc_commits, enc_c.data(), enc_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
+  B200_TRY(A.alloc_t(&h->enc_ext_commits, enc_e.size() ? enc_e.size() : 1, false));
+  B200_TRY(A.alloc_t(&h->dec_ext_commits, dec_e.size() ? dec_e.size() : 1, false));
+  if (!enc_c.empty())
+    B200_CUDA(cudaMemcpy(h->enc_commits, enc_c.data(), enc_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
   if (!dec_c.empty())
     B200_CUDA(cudaMemcpy(h->dec_commits, dec_c.data(), dec_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(h->dec_tr_commits, dec_t.data(), dec_t.size() * sizeof(ConvTrCommit), cudaMemcpyHostToDevice));
+  if (!enc_e.empty())
+    B200_CUDA(cudaMemcpy(h->enc_ext_commits, enc_e.data(), enc_e.size() * sizeof(ExtCommit), cudaMemcpyHostToDevice));
+  if (!dec_e.empty())
+    B200_CUDA(cudaMemcpy(h->dec_ext_commits, dec_e.data(), dec_e.size() * sizeof(ExtCommit), cudaMemcpyHostToDevice));
 
   // transformers
   const int H = c.tr_num_heads, D = d / H, ff = c.tr_dim_feedforward;
@@ -763,7 +893,15 @@ int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev) {
                 reset_mask_dev, B);
   };
   for (auto* layers : {&h->enc, &h->dec})
-    for (auto& l : *layers) zero(l.state, l.kind == 0 ? (long long)l.cin * l.P : (long long)l.cout * l.P);
+    for (auto& l : *layers) {
+      if (l.kind == 0 && l.fast) {
+        if (l.P > 0)
+          B200_LAUNCH(ext_zero_kernel, (unsigned)ceil_div64((long long)B * l.cin * l.P, 256), 256, 0, h->stream,
+                      l.ext + (l.D0 - l.P), l.P, l.E, l.cin, reset_mask_dev, B);
+      } else {
+        zero(l.state, l.kind == 0 ? (long long)l.cin * l.P : (long long)l.cout * l.P);
+      }
+    }
   zero(h->down.state, (long long)h->down.cin * h->down.P);
   zero(h->up_partial, (long long)h->cfg.dimension * h->rs);
   B200_LAUNCH(reset_flags_kernel, ceil_div(B, 128), 128, 0, h->stream, h->first_flags, h->n_first, h->enc_tr.offset,

@@ -30,6 +30,7 @@ struct ConvP {
   const float* w; const float* bias;
   float* y; long long yb, yc, yt;
   const float* res; long long rb, rc, rt;
+  float* a = nullptr; long long ab = 0, ac = 0, at = 0; int a_elu = 0;   // activated copy for a mimi_gemm.cuh consumer
   int B, Cin, Cout, K, stride, dil, Tout, elu_in;
   int M, N, Kd, cin_aligned;
 
@@ -63,6 +64,7 @@ struct ConvP {
     float v = acc + (bias ? bias[m] : 0.f);
     if (res) v = res[b * rb + m * rc + t * rt] + v;   // SEANetResnetBlock: u + v (seanet.py:90-93)
     y[b * yb + m * yc + t * yt] = v;
+    if (a) a[b * ab + m * ac + t * at] = a_elu ? elu1(v) : v;
   }
 };
 

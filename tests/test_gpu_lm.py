@@ -202,7 +202,9 @@ def test_rows_independent_graph_invariant_and_host_path():
         assert (eager[i] >= 0).all() and (eager[i][:, 1:] < cfg.card).all() and (eager[i][:, 0] < cfg.text_card).all()
     # ring wrap-around: positions near the 3000-slot capacity
     wrapped = run(rows, True, fill=2998)
-    assert all(o is not None and (o >= 0).all() for o in wrapped)
+    assert all(o is not None for o in wrapped)
+    # assume_fill leaves the token ring "ungenerated" (-2): the first output re-aligns the previous step's slot
+    assert all((o >= 0).all() for o in wrapped[1:])
     masked = run(rows, True, mask_row=3)
     for i in (2, 3):
         assert (masked[i][3] == -2).all()

@@ -67,8 +67,7 @@ def bench_gemm(lib, Ms, legacy=True):
             y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             res = torch.zeros(M, cols, device="cuda", dtype=torch.bfloat16)
             alg = wbytes + M * K * 2 + M * cols * 2 * (2 if epi == 1 else 1)
-            variants = [("sk", 0, 0, 0), ("sk.stream_only", 0, 0, 1), ("sk.2cta", 296, 100 << 10, 0),
-                        ("sk.2cta.stream_only", 296, 100 << 10, 1), ("sk.grid74", 74, 0, 0)]
+            variants = [("sk", 0, 0, 0), ("sk.stream_only", 0, 0, 1)]
             for vname, grid, smem, so in variants:
                 def fn(i):
                     _lib.check(lib.b200_op_linear_sk(_lib.ptr(x), _lib.ptr(pk[i]), _lib.ptr(y), _lib.ptr(res), M, N, K, epi, gr,
