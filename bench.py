@@ -106,12 +106,33 @@ def _tiled_random_lm_state_dict(cfg, seed: int = 7):
     return sd
 
 
+def _pick_cpu_threads() -> int:
+    """The reference path is many small ops around 32+ large bf16 matvecs; with one thread per core on a
+    100+-core host the per-op fork/join dominates (59 s per step measured on the 128-core GPU box against 2 s
+    on 8 cores).  Time one temporal-layer matvec at a few thread counts and keep the fastest."""
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    w = torch.randn(8192, 4096).bfloat16()
+    x = torch.randn(1, 1, 4096).bfloat16()
+    best, best_t = 1, float("inf")
+    for n in sorted({t for t in (4, 8, 16, 32, 64, cores) if t <= cores}):
+        torch.set_num_threads(n)
+        F.linear(x, w)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.linear(x, w)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    return best
+
+
 def run_cpu_pipeline(steps: int, warmup: int, threads: int | None = None) -> dict:
     from moshi_b200.config import MOSHI_7B, MimiConfig
     from moshi_b200.synth import synth_mimi_state_dict
     from oracle.lm import LMOracle, LMSpec
     from oracle.mimi import MimiOracle
-    cores = threads or os.cpu_count() or 1
+    cores = threads or _pick_cpu_threads()
     torch.set_num_threads(cores)
     mcfg = MimiConfig()
     mimi = MimiOracle(synth_mimi_state_dict(mcfg, seed=1234), mcfg)
@@ -135,7 +156,7 @@ def run_cpu_pipeline(steps: int, warmup: int, threads: int | None = None) -> dic
                 times.append((t3 - t0) * 1e3)
                 parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
     ms = sum(times) / len(times)
-    return {"ms_per_step": ms, "cores": cores, "sessions": sessions_sustained(1.0, ms),
+    return {"ms_per_step": ms, "cores": cores, "host_cores": os.cpu_count(), "sessions": sessions_sustained(1.0, ms),
             "mimi_encode_ms": sum(p[0] for p in parts) / len(parts), "lm_step_ms": sum(p[1] for p in parts) / len(parts),
             "mimi_decode_ms": sum(p[2] for p in parts) / len(parts)}
 
@@ -153,7 +174,8 @@ def reference_arm(args) -> None:
                    "sessions_per_gpu": 1, "kv_fill": "growing from 0"},
         "cpu_baseline": {"value": r["sessions"], "unit": "sessions", "cores": r["cores"], "kind": "port",
                          "sample": f"{args.steps} frames of 1 session (oracle port of the reference PyTorch path, "
-                                   "random block-tiled 7B weights)"},
+                                   f"random block-tiled 7B weights; torch threads = {r['cores']} of {r['host_cores']} "
+                                   "host cores, the fastest of a short sweep)"},
         "e2e": {"value": r["sessions"], "unit": "sessions", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "breakdown_ms": {k: r[k] for k in ("mimi_encode_ms", "lm_step_ms", "mimi_decode_ms")},
     }
@@ -170,36 +192,80 @@ def _peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _dominant_kernel_roofline(lm, B: int, device) -> dict:
-    """The temporal linear_in GEMM (22528 x 4096 weights, 184.5 MB > L2) timed alone with CUDA events,
-    an L2 flush (256 MiB memset) between launches."""
+def _event_time(fn, iters: int = 10, warm: int = 3) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
+    """The dominant kernel of the step at serving batch is the temporal ring-attention decode (32 launches per
+    step, each streaming 2*B*32*fill*128 bf16 of K/V; profiles/ has its share of the step).  Timed here alone
+    with CUDA events on the launching stream, on K/V rings of the bench's own shape (4.7 GB at B=96: far
+    larger than L2, so every launch streams from HBM), same split-KV configuration the LM uses."""
     import ctypes as C
     from moshi_b200 import _lib
     lib = _lib.lib()
-    N, K, M = 22528, 4096, B
-    w = torch.empty(N, K, device=device, dtype=torch.bfloat16).uniform_(-0.02, 0.02)
-    x = torch.empty(M, K, device=device, dtype=torch.bfloat16).uniform_(-1, 1)
-    y = torch.empty(M, N, device=device, dtype=torch.bfloat16)
-    flush = torch.empty(256 << 20, device=device, dtype=torch.uint8)
+    H, cap, D = 32, 3000, 128
+    k = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
+    v = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
+    q = torch.randn(B, H, D, device=device).bfloat16()
+    out = torch.empty_like(q)
+    offs = torch.full((B,), max(kv_fill - 1, 0) + (cap if kv_fill >= cap else 0), dtype=torch.int64, device=device)
+    mask = torch.ones(B, dtype=torch.bool, device=device)
     stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    impl = int(os.environ.get("B200_GEMM_IMPL", "0"))
-    times = []
-    for i in range(8):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.b200_op_linear_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), M, N, K, impl, stream))
-        e1.record()
-        torch.cuda.synchronize(device)
-        if i >= 3:
-            times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
-    alg = N * K * 2 + M * K * 2 + M * N * 2
+
+    def fn():
+        _lib.check(lib.b200_op_attn_decode(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
+                                           _lib.ptr(mask), B, H, cap, 0, stream))
+    ms = _event_time(fn)
+    n_keys = min(max(kv_fill, 1), cap)
+    alg = 2 * B * H * n_keys * D * 2 + 2 * B * H * D * 2
     peak, src = _peaks()
     gbs = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "LM linear (gating.linear_in 22528x4096 bf16, M=%d)" % M, "bound": "hbm", "achieved": gbs,
-            "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-            "ms_per_launch": ms, "algorithmic_bytes": alg}
+    del k, v
+    return {"kernel": "lm::attn_decode_kernel (+combine), temporal ring attention, B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
+            "bound": "hbm", "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak,
+            "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
+
+
+def _gemm_roofline(B: int, device) -> dict:
+    """Second kernel by time: the stream-K tcgen05 GEMM on the gated-MLP input projection (184.5 MB of weights)."""
+    import ctypes as C
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    N, K, H, M = 22528, 4096, 11264, B
+    n_rot = 3
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    packed = []
+    for _ in range(n_rot):
+        w = torch.empty(N, K, device=device, dtype=torch.bfloat16).uniform_(-0.02, 0.02)
+        out = torch.empty(lib.b200_op_packed_bytes(N, K, 2, H), dtype=torch.uint8, device=device)
+        _lib.check(lib.b200_op_pack_tiles(_lib.ptr(w), _lib.ptr(out), N, K, 2, H, stream))
+        packed.append(out)
+        del w
+    x = torch.empty(M, K, device=device, dtype=torch.bfloat16).uniform_(-1, 1)
+    y = torch.empty(M, H, device=device, dtype=torch.bfloat16)
+    i = [0]
+
+    def fn():
+        _lib.check(lib.b200_op_linear_sk(_lib.ptr(x), _lib.ptr(packed[i[0] % n_rot]), _lib.ptr(y), None, M, N, K, 2, H,
+                                         0, 0, 0, stream))
+        i[0] += 1
+    ms = _event_time(fn, iters=12)
+    alg = N * K * 2 + M * K * 2 + M * H * 2
+    peak, src = _peaks()
+    gbs = alg / (ms * 1e-3) / 1e9
+    return {"kernel": "tc::gemm_sk_kernel<GATE> (gating.linear_in 22528x4096 bf16, M=%d)" % M, "bound": "hbm",
+            "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "ms_per_launch": ms,
+            "algorithmic_bytes": alg, "launches_per_step": 32}
 
 
 def b200_arm(args) -> None:
@@ -221,8 +287,8 @@ def b200_arm(args) -> None:
     # sessions per GPU: the full-context bf16 KV ring (1.573 GB/session) is what bounds it
     free, total = torch.cuda.mem_get_info(device)
     per_session = KV_BYTES_PER_SESSION_STEP * MOSHI_7B.context + 40e6
-    cap = int((free - 8e9) // per_session)
-    B = max(1, min(args.sessions or 96, cap))
+    cap = int((free - 6e9) // per_session)
+    B = max(1, min(args.sessions or cap, cap))
     kv_fill = MOSHI_7B.context if args.kv_fill < 0 else min(args.kv_fill, MOSHI_7B.context)
 
     gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
@@ -290,13 +356,21 @@ def b200_arm(args) -> None:
     lm_bytes = gen.algorithmic_bytes(kv_fill)
     mimi_bytes = mimi.algorithmic_bytes()
     peak, peak_src = _peaks()
-    roof = _dominant_kernel_roofline(lm, B, device) if rank == 0 else None
+    roof = gemm_roof = None
+    if rank == 0:
+        # release the sessions' state (150+ GB of KV rings) before allocating the stand-alone kernel operands
+        gen._stop()
+        mimi._stop()
+        torch.cuda.empty_cache()
+        roof = _dominant_kernel_roofline(B, kv_fill, device)
+        gemm_roof = _gemm_roofline(B, device)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         r = run_cpu_pipeline(steps=3, warmup=1)
         cpu = {"value": r["sessions"], "unit": "sessions", "cores": r["cores"], "kind": "port",
                "sample": "3 frames of 1 session (Mimi enc + Moshi 7B LMGen.step + Mimi dec) after 1 warm-up; oracle port "
-                         "of the reference PyTorch path, random block-tiled 7B weights",
+                         f"of the reference PyTorch path, random block-tiled 7B weights; torch threads = {r['cores']} of "
+                         f"{r['host_cores']} host cores (fastest of a short sweep)",
                "ms_per_step": r["ms_per_step"]}
     if rank != 0:
         return
@@ -315,6 +389,7 @@ def b200_arm(args) -> None:
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof,
+        "roofline_gemm": gemm_roof,
         "lm_step": {"ms": lm_ms, "algorithmic_bytes": lm_bytes, "achieved_gbs": lm_bytes / (lm_ms * 1e-3) / 1e9,
                     "frac_of_hbm_peak": lm_bytes / (lm_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src},
         "mimi": {"algorithmic_bytes": mimi_bytes, "ms_encode_plus_decode": ms_dev - lm_ms,
@@ -330,7 +405,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: 96 or what the KV ring allows)")
+    ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: as many as the full-context bf16 KV rings fit in HBM)")
     ap.add_argument("--kv-fill", type=int, default=-1, help="frames of history per session (default: full ring)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()

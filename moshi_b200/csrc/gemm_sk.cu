@@ -96,6 +96,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Programmatic dependent launch: `pdl_wait` blocks until the preceding kernel in the stream has completed and its
+// writes are visible; `pdl_trigger` lets the following kernel start its own prologue (and weight prefetch) early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major SWIZZLE_128B smem matrix descriptor (see gemm_tc.cu) and the kind::f16 instruction descriptor
@@ -195,19 +199,39 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tptr_generic;
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== producer: one contiguous bulk copy of the weight tile(s) + one TMA box of activations per k-block =====
+      // Weights do not depend on the preceding kernel: the first `stages` weight tiles are requested before the
+      // dependency wait, so under programmatic dependent launch the HBM stream starts while the producer of x
+      // is still running.  The activation boxes (and everything the epilogue touches) come after pdl_wait.
       int s = 0; uint32_t ph = 0;
+      int pre = 0;                                   // stages whose weight copy is already in flight
+      {
+        int ps = 0;
+        for (int si = 0; si < n_seg && pre < p.stages; ++si) {
+          const Seg sg = seg_get(p, c, n_sk, si);
+          const uint8_t* src = p.wt + ((size_t)sg.tile * p.num_kb + sg.kb0) * a_bytes;
+          for (int kb = sg.kb0; kb < sg.kb1 && pre < p.stages; ++kb, src += a_bytes, ++pre, ++ps) {
+            mbar_expect_tx(full0 + 8 * ps, p.stage_bytes);
+            bulk_load(base + (uint32_t)ps * p.stage_bytes, src, a_bytes, full0 + 8 * ps);
+          }
+        }
+      }
+      pdl_wait();
+      int item = 0;
       for (int si = 0; si < n_seg; ++si) {
         const Seg sg = seg_get(p, c, n_sk, si);
         const uint8_t* src = p.wt + ((size_t)sg.tile * p.num_kb + sg.kb0) * a_bytes;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb, src += a_bytes) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, src += a_bytes, ++item) {
           const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
-          mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
-          bulk_load(sa, src, a_bytes, full0 + 8 * s);
+          if (item >= pre) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
+            bulk_load(sa, src, a_bytes, full0 + 8 * s);
+          }
           tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -254,6 +278,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
     const int et = threadIdx.x - 64;           // 0..127
     const size_t slot_floats = (size_t)A_TILES * BLOCK_ROWS * p.Mpad;
     int acc = 0; uint32_t acc_bits = 0u;
+    pdl_wait();                                // y / res / workspace / counters may still be in use by the predecessor
     for (int si = 0; si < n_seg; ++si) {
       const Seg sg = seg_get(p, c, n_sk, si);
       const int n = sg.tile * BLOCK_ROWS + row;
@@ -495,9 +520,18 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
     mx = &it->second;
   }
   const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
-  if (epi == EPI_STORE) gemm_sk_kernel<EPI_STORE><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
-  else if (epi == EPI_RESADD) gemm_sk_kernel<EPI_RESADD><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
-  else gemm_sk_kernel<EPI_GATE><<<grid, NUM_THREADS, smem, stream>>>(*mx, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tune.pdl ? 1 : 0;
+  cudaError_t le;
+  if (epi == EPI_STORE) le = cudaLaunchKernelEx(&cfg, gemm_sk_kernel<EPI_STORE>, *mx, p);
+  else if (epi == EPI_RESADD) le = cudaLaunchKernelEx(&cfg, gemm_sk_kernel<EPI_RESADD>, *mx, p);
+  else le = cudaLaunchKernelEx(&cfg, gemm_sk_kernel<EPI_GATE>, *mx, p);
+  if (le != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "gemm_sk launch failed: %s", cudaGetErrorString(le));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_sk");
 }

@@ -36,6 +36,7 @@ struct b200_lm {
   int use_sampling = 1, top_k = 250, top_k_text = 25;
   float temp = 0.8f, temp_text = 0.7f;
   int gemm_impl = 3;                           // 3 = stream-K tcgen05 over packed tiles (default)
+  int pdl = 0;                                 // programmatic dependent launch of the GEMMs (B200_PDL=1)
   float* sk_ws = nullptr;                      // stream-K partial-accumulator slots (L2-resident)
   int* sk_counters = nullptr;                  // per-tile arrival counters (zero between launches)
   // weights
@@ -100,6 +101,7 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
   const int impl = h->gemm_impl;
   if (impl == 3) {
     tc::SkTuning t;
+    t.pdl = h->pdl;
     return tc::sk_linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->sk_ws, h->sk_counters, t, h->body);
   }
   if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->body);
@@ -248,6 +250,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
     const int v = atoi(e);
     if (v >= 1 && v <= 3) h->gemm_impl = v;
   }
+  if (const char* e = getenv("B200_PDL")) h->pdl = atoi(e) != 0;
   *out = h;
   return B200_OK;
 }

@@ -12,6 +12,11 @@ namespace lm {
 
 typedef __nv_bfloat16 bf16;
 
+// The GEMM that follows each of these kernels is launched with programmatic stream serialization
+// (gemm_sk.cu): triggering at entry lets its CTAs take free SM resources and start streaming weights
+// while this kernel runs; the GEMM itself waits (griddepcontrol.wait) before it touches activations.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -36,6 +41,7 @@ struct TokenRing {
 // One thread per (b, k): write the user's codes, then build the model input row [B][Kc].
 static __global__ void lm_prepare_kernel(const TokenRing r, const long long* __restrict__ in_codes, int n_in,
                                   long long* __restrict__ input_tokens, int B) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * r.Kc) return;
   const int b = i / r.Kc, k = i % r.Kc;
@@ -86,6 +92,7 @@ struct EmbedTables {
 };
 static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long* __restrict__ tokens /*[B][n_q+1]*/,
                                     bf16* __restrict__ x /*[B][dim]*/, int B, int dim) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (b, pair)
   const int half = dim / 2;
   if (i >= B * half) return;
@@ -119,6 +126,7 @@ static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long*
 static __global__ void dep_input_kernel(const bf16* __restrict__ din /*[B][ld]*/, long long ld, int col0,
                                  const bf16* __restrict__ table /*[V][dd]*/, const long long* __restrict__ prev /*[B]*/,
                                  bf16* __restrict__ x /*[B][dd]*/, int B, int dd) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dd) return;
   const int b = i / dd, c = i % dd;
@@ -133,6 +141,7 @@ static __global__ void dep_input_kernel(const bf16* __restrict__ din /*[B][ld]*/
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ alpha,
                                                       bf16* __restrict__ y, int dim, float eps) {
+  pdl_trigger();
   const int row = blockIdx.x;
   const bf16* xr = x + (long long)row * dim;
   float ss = 0.f;
@@ -226,6 +235,7 @@ static __global__ void rope_append_bf16_kernel(const bf16* __restrict__ qkv, bf1
                                         const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
                                         int step, int B, int H, int D, int cap, int use_rope,
                                         float neg_log_period_2_over_d) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, h, pair)
   const int half = D / 2;
   if (i >= (long long)B * H * half) return;
@@ -277,6 +287,7 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const b
                                                                   const long long* __restrict__ offset,
                                                                   const uint8_t* __restrict__ exec_mask, int H, int cap,
                                                                   int nsplit) {
+  pdl_trigger();
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / H;
   const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15;
@@ -357,6 +368,7 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const b
 
 static __global__ void __launch_bounds__(ATT_D) attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out,
                                                              int nsplit) {
+  pdl_trigger();
   const int bh = blockIdx.x, d = threadIdx.x;
   const float* p = part + (long long)bh * nsplit * (ATT_D + 2);
   float M = -INFINITY;
@@ -374,6 +386,7 @@ static __global__ void __launch_bounds__(ATT_D) attn_combine_kernel(const float*
 // Depformer attention: <= 8 keys, one warp per (b, h), D = 64 (2 dims per lane).
 static __global__ void dep_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
                                 bf16* __restrict__ out, int B, int H, int D, int cap, int n_keys) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * H) return;
   const float scale = rsqrtf((float)D);
@@ -415,6 +428,7 @@ static __global__ void lm_reset_kernel(long long* offsets, long long* pos, uint8
 }
 
 static __global__ void advance_pos_kernel(long long* pos, const uint8_t* exec_mask, int B) {
+  pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && exec_mask[b]) pos[b] += 1;
 }
@@ -447,6 +461,7 @@ static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf1
                                                                 const float* __restrict__ noise, long long noise_ld,
                                                                 long long* __restrict__ out, int card, int use_sampling,
                                                                 float temp, int top_k) {
+  pdl_trigger();
   __shared__ float red[SAMPLE_THREADS / 32];
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_remaining, s_count;
