@@ -339,28 +339,31 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
         epi_bar_sync();
         if (s_last) {
           __threadfence();
-          for (int m0 = 0; m0 < p.M; m0 += 8) {
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+          // 16 columns per pass: every contribution's 4 (gate: 8) 16-byte loads are issued before the adds
+          for (int m0 = 0; m0 < p.M; m0 += 16) {
+            float av[16], bv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { av[j] = 0.f; bv[j] = 0.f; }
+#pragma unroll 2
             for (int cc = first_c; cc <= last_c; ++cc) {
               const int sl = 2 * cc + ((sk_begin(p, cc) / p.num_kb == rel) ? 0 : 1);
-              const float* w2 = p.ws + (size_t)sl * slot_floats + (size_t)row * p.Mpad + m0;
-              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(w2));
-              const float4 v1 = (m0 + 4 < p.Mpad) ? __ldcg(reinterpret_cast<const float4*>(w2 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-              a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+              const float4* w2 = reinterpret_cast<const float4*>(p.ws + (size_t)sl * slot_floats + (size_t)row * p.Mpad + m0);
+              float4 v[4], u[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = __ldcg(w2 + j);
               if (EPI == EPI_GATE) {
-                const float* w3 = w2 + (size_t)BLOCK_ROWS * p.Mpad;
-                const float4 u0 = __ldcg(reinterpret_cast<const float4*>(w3));
-                const float4 u1 = (m0 + 4 < p.Mpad) ? __ldcg(reinterpret_cast<const float4*>(w3 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                b0.x += u0.x; b0.y += u0.y; b0.z += u0.z; b0.w += u0.w;
-                b1.x += u1.x; b1.y += u1.y; b1.z += u1.z; b1.w += u1.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[j] = __ldcg(w2 + (size_t)BLOCK_ROWS * p.Mpad / 4 + j);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                av[4 * j] += v[j].x; av[4 * j + 1] += v[j].y; av[4 * j + 2] += v[j].z; av[4 * j + 3] += v[j].w;
+                if (EPI == EPI_GATE) { bv[4 * j] += u[j].x; bv[4 * j + 1] += u[j].y; bv[4 * j + 2] += u[j].z; bv[4 * j + 3] += u[j].w; }
               }
             }
             if (n_ok && !p.stream_only) {
-              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 16; ++j) {
                 const int m = m0 + j;
                 if (m < p.M) p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, av[j], bv[j], m, n));
               }
@@ -485,7 +488,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.grid = grid;
   p.whole_rounds = p.n_tiles / grid;
   int rem = p.n_tiles - p.whole_rounds * grid;
-  const bool split = rem > 0 && rem * 8 < grid * 7 && tune.no_split == 0;
+  // cutting tiles pays when the partial accumulators are small (few sessions) or the remainder leaves most SMs idle
+  const bool split = rem > 0 && tune.no_split == 0 && (M <= 32 ? rem * 8 < grid * 7 : rem * 2 <= grid);
   if (rem > 0 && !split) { p.whole_rounds += 1; rem = 0; }
   p.sk_tile0 = p.n_tiles - rem;
   p.sk_items = rem * p.num_kb;
