@@ -117,6 +117,8 @@ int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebo
 int b200_mimi_encode_host(b200_mimi* h, const float* pcm_host, int n_frames, int64_t* codes_host);
 int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codebooks, int n_frames,
                           float* pcm_host);
+/* 0 = one launch per kernel, 1 = replay each one-frame encode / decode as a CUDA graph (default 1). */
+int b200_mimi_set_graph(b200_mimi* h, int enable);
 /* Debug taps: copies a named fp32 intermediate of the last call into dst_dev (capacity in elements;
  * pass dst_dev = NULL to query *numel only).  Names: "enc.<i>", "dec.<i>" = output of SEANet module i
  * ([B,C,T]; the last encoder module is token-major [B,T,C]), "enc.tr", "dec.up", "dec.tr" ([B,T,C]),

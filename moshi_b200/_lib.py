@@ -62,6 +62,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_mimi_decode_latent": (_I, [_P, _P, _I, _I, _P]),
     "b200_mimi_encode_host": (_I, [_P, _P, _I, _P]),
     "b200_mimi_decode_host": (_I, [_P, _P, _I, _I, _P]),
+    "b200_mimi_set_graph": (_I, [_P, _I]),
     "b200_mimi_read_buffer": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "b200_mimi_algorithmic_bytes": (C.c_int64, [_P]),
     # LM

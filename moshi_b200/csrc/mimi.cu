@@ -89,6 +89,17 @@ struct b200_mimi {
   float* rvq_best[2] = {nullptr, nullptr};
   int* rvq_idx[2] = {nullptr, nullptr};
   int rvq_cap = 0;
+  float* splitk_ws = nullptr; size_t splitk_bytes = 0;   // split-K partial sums of the deep / skinny GEMMs
+  // one-frame encode / decode as CUDA graphs over static buffers (in_frame -> enc_codes, dec_codes -> out_frame)
+  cudaStream_t body = nullptr;                 // stream the kernels are being enqueued on (caller's, or gstream in capture)
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t enc_graph = nullptr, dec_graph = nullptr;
+  int64_t enc_graph_kernels = 0, dec_graph_kernels = 0;
+  int dec_graph_ncb = 0;
+  int graph_enabled = 1;
+  long long *enc_codes = nullptr, *dec_codes = nullptr;   // [B][K], [B][q_n_q]
+  float* out_frame = nullptr;                              // [B][frame_size]
   float *pin_pcm = nullptr; long long* pin_codes = nullptr; size_t pin_pcm_n = 0, pin_codes_n = 0;
   float* dev_pcm = nullptr; long long* dev_codes = nullptr; size_t dev_pcm_n = 0, dev_codes_n = 0;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
@@ -338,20 +349,37 @@ int pack_quantizer(b200_mimi* h) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-// tile choice: the largest tile that still gives every SM a couple of CTAs
+// tile choice: the largest tile that still gives every SM a couple of CTAs; layers with a long reduction and few
+// output tiles (deep SEANet convs, transformer linears at small batch) are cut along K as well.
 template <int KIND>
-int launch_gemm(b200_mimi* h, const GemmArgs& a) {
+int launch_gemm(b200_mimi* h, GemmArgs a) {
   auto ctas = [&](int bm, int bn) { return (long long)ceil_div(a.M, bm) * ceil_div(a.N, bn); };
   const long long want = 2 * 148;
+  a.ksplit = 1; a.ws = nullptr;
   if (a.M > 64 && ctas(128, 128) >= want) {
     dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 128));
-    B200_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->stream, a);
+    B200_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->body, a);
   } else if (ctas(64, 128) >= want) {
     dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 64));
-    B200_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->stream, a);
+    B200_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->body, a);
   } else {
-    dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
-    B200_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->stream, a);
+    const long long n64 = ctas(64, 64);
+    const int nk = ceil_div(a.Kd, GK);
+    int ks = 1;
+    if (n64 < 148 && nk >= 32) {
+      ks = (int)(want / n64);
+      if (ks > nk / 8) ks = nk / 8;          // at least 8 k-blocks (128 k) per split
+      if (ks > 16) ks = 16;
+      if (ks < 1) ks = 1;
+      if ((size_t)ks * a.M * a.N * 4 > h->splitk_bytes) ks = 1;
+    }
+    a.ksplit = ks; a.ws = h->splitk_ws;
+    dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64), ks);
+    B200_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->body, a);
+    if (ks > 1) {
+      const long long n = (long long)a.M * a.N;
+      B200_LAUNCH((gemm_splitk_reduce_kernel<KIND>), (unsigned)ceil_div64(n, 256), 256, 0, h->body, a);
+    }
   }
   return check_launch("mimi_gemm");
 }
@@ -400,7 +428,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     p.elu_in = l.elu_in;
     p.M = l.cout; p.N = B * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->stream, p);
+    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
   } else {
     if (act) B200_FAIL(B200_ERR_INVALID, "first-generation convtr cannot feed a mimi_gemm layer");
     ConvTrP p;
@@ -410,7 +438,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.S = l.stride; p.elu_in = l.elu_in;
     p.M = l.cout * l.stride; p.N = B * (l.t_in + 1); p.Kd = 2 * l.cin; p.cin_aligned = (l.cin % BK) == 0;
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    B200_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->stream, p);
+    B200_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->body, p);
   }
   return check_launch(l.key.c_str());
 }
@@ -435,21 +463,21 @@ int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, 
   for (size_t li = 0; li < tr.layers.size(); ++li) {
     TrLayer& L = tr.layers[li];
     const float* cur = li == 0 ? x_in : x;
-    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->stream, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
     B200_TRY(launch_linear(h, h->tr_xn, d, L.in_w, h->tr_qkv, 3 * d, ntok, EPI_NONE, nullptr, nullptr));
     {
       const long long total = (long long)B * T * H * (D / 2);
-      B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->stream, h->tr_qkv, h->tr_q, L.kc,
+      B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->tr_qkv, h->tr_q, L.kc,
                   L.vc, tr.offset, h->exec_mask, B, T, H, D, c.tr_context, nl);
     }
-    B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->stream, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
+    B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
                 h->exec_mask, T, H, c.tr_context, c.tr_context);
     B200_TRY(launch_linear(h, h->tr_ao, d, L.out_w, x, d, ntok, EPI_RES_SCALE, cur, L.ls1));
-    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->stream, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
     B200_TRY(launch_linear(h, h->tr_xn, d, L.l1, h->tr_h, ff, ntok, EPI_GELU, nullptr, nullptr));
     B200_TRY(launch_linear(h, h->tr_h, ff, L.l2, x, d, ntok, EPI_RES_SCALE, x, L.ls2));
   }
-  B200_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->stream, tr.offset, h->exec_mask, B, T);
+  B200_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->body, tr.offset, h->exec_mask, B, T);
   return check_launch("mimi transformer");
 }
 
@@ -459,7 +487,7 @@ int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& b
   if (layers[0].fast) {   // its input comes from outside the SEANet (transformer output): copy it behind the carried state
     const ConvLayer& l = layers[0];
     const long long n = (long long)h->batch * l.cin * l.t_in;
-    B200_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->stream, x0, xb, xc, xt, l.ext + l.D0,
+    B200_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->body, x0, xb, xc, xt, l.ext + l.D0,
                 (long long)l.cin * l.E, (long long)l.E, 1LL, h->batch, l.cin, l.t_in, (int)l.elu_in);
   }
   for (size_t i = 0; i < layers.size(); ++i) {
@@ -487,40 +515,46 @@ int commit_states(b200_mimi* h, bool encoder) {
   if (encoder) {
     if (h->n_enc_commits) {
       dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
-      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
-      B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->stream, h->enc_commits,
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
+      B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->body, h->enc_commits,
                   h->n_enc_commits, h->exec_mask, B);
     }
     if (h->n_enc_ext) {
       dim3 grid(ceil_div(h->max_enc_ext_rows, 128), h->n_enc_ext);
-      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->stream, h->enc_ext_commits, h->exec_mask, B);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->enc_ext_commits, h->exec_mask, B);
     }
   } else {
     if (h->n_dec_commits) {
       dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
-      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->stream, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
     }
     if (h->n_dec_ext) {
       dim3 grid(ceil_div(h->max_dec_ext_rows, 128), h->n_dec_ext);
-      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->stream, h->dec_ext_commits, h->exec_mask, B);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->dec_ext_commits, h->exec_mask, B);
     }
     dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);
-    B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->stream, h->dec_tr_commits, h->exec_mask, B);
+    B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->body, h->dec_tr_commits, h->exec_mask, B);
   }
   return check_launch("commit_states");
 }
 
-int encode_frame_to_latent(b200_mimi* h, const float* pcm, int n_frames, int f) {
-  const int B = h->batch, fs = h->frame_size, d = h->cfg.dimension;
+// in_frame [B][frame] -> latent [B][C]   (static buffers only: this is what gets captured into a graph)
+int encode_body(b200_mimi* h) {
+  const int fs = h->frame_size, d = h->cfg.dimension;
   const int T = fs / h->hop;   // encoder tokens per frame (2)
-  B200_CUDA(cudaMemcpy2DAsync(h->in_frame, (size_t)fs * 4, pcm + (size_t)f * fs, (size_t)fs * n_frames * 4,
-                              (size_t)fs * 4, B, cudaMemcpyDeviceToDevice, h->stream));
   // SEANet encoder; the last conv writes token-major [B][T][C] for the transformer
   B200_TRY(run_seanet(h, h->enc, h->enc_bufs, h->in_frame, fs, 0, 1, h->tok_in_enc, (long long)T * d, 1, d));
   B200_TRY(run_transformer(h, h->enc_tr, h->tok_in_enc, h->tok_enc, T));
   // learnt down-sampling conv reads token-major, writes latent [B][C][1]
   B200_TRY(launch_conv(h, h->down, h->tok_enc, (long long)T * d, 1, d, h->latent, d, 1, 1, nullptr, 0, 0, 0));
   B200_TRY(commit_states(h, true));
+  return B200_OK;
+}
+
+int load_frame(b200_mimi* h, const float* pcm, int n_frames, int f) {
+  const int fs = h->frame_size;
+  B200_CUDA(cudaMemcpy2DAsync(h->in_frame, (size_t)fs * 4, pcm + (size_t)f * fs, (size_t)fs * n_frames * 4,
+                              (size_t)fs * 4, h->batch, cudaMemcpyDeviceToDevice, h->stream));
   return B200_OK;
 }
 
@@ -553,7 +587,7 @@ int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, lo
   levels[1] = h->num_codebooks - levels[0];
   {
     dim3 grid(Q, 2);
-    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->stream, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
+    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->body, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
                 h->rvq_res[0], h->rvq_res[1], c.dimension, Dq);
   }
   const int max_levels = levels[0] > levels[1] ? levels[0] : levels[1];
@@ -570,9 +604,9 @@ int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, lo
     a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f;
     a.n_query = Q; a.n_frames = n_cols; a.Dq = Dq; a.bins = bins; a.n_chunks = n_chunks;
     dim3 g1(n_chunks, ceil_div(Q, RVQ_QT), 2);
-    B200_LAUNCH(rvq_search_kernel, g1, RVQ_CHUNK, (size_t)RVQ_QT * Dq * 4, h->stream, a);
+    B200_LAUNCH(rvq_search_kernel, g1, RVQ_CHUNK, (size_t)RVQ_QT * Dq * 4, h->body, a);
     dim3 g2(Q, 2);
-    B200_LAUNCH(rvq_pick_kernel, g2, 128, 0, h->stream, a);
+    B200_LAUNCH(rvq_pick_kernel, g2, 128, 0, h->body, a);
   }
   return check_launch("rvq_encode");
 }
@@ -589,22 +623,64 @@ int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long l
   a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
   a.out = out; a.ob = ob; a.oc = oc; a.ot = ot;
   a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins;
-  B200_LAUNCH(rvq_decode_kernel, h->batch * n_cols, 256, 2 * c.q_dimension * sizeof(float), h->stream, a);
+  B200_LAUNCH(rvq_decode_kernel, h->batch * n_cols, 256, 2 * c.q_dimension * sizeof(float), h->body, a);
   return check_launch("rvq_decode");
 }
 
-int decode_latent_frame(b200_mimi* h, const float* latq /*[B][C]*/, float* pcm, int n_frames, int f) {
+// latent_q [B][C] -> out_frame [B][frame]   (static buffers only)
+int decode_latent_body(b200_mimi* h) {
   const int B = h->batch, fs = h->frame_size, d = h->cfg.dimension, S = h->rs;
   const int T = S;   // tokens per frame after up-sampling
   {
     const long long total = (long long)B * 2 * S * d;   // (T_in + 1) * S * C with T_in = 1
-    B200_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->stream, latq, (long long)d, 1LL, 1LL, 1,
+    B200_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->latent_q, (long long)d, 1LL, 1LL, 1,
                 h->up_w, h->up_partial, h->up_scratch, h->tok_in_dec, B, d, S);
   }
   B200_TRY(run_transformer(h, h->dec_tr, h->tok_in_dec, h->tok_dec, T));
-  B200_TRY(run_seanet(h, h->dec, h->dec_bufs, h->tok_dec, (long long)T * d, 1, d, pcm + (size_t)f * fs,
-                      (long long)fs * n_frames, 0, 1));
+  B200_TRY(run_seanet(h, h->dec, h->dec_bufs, h->tok_dec, (long long)T * d, 1, d, h->out_frame, (long long)fs, 0, 1));
   B200_TRY(commit_states(h, false));
+  return B200_OK;
+}
+
+void drop_graphs(b200_mimi* h) {
+  if (h->enc_graph) cudaGraphExecDestroy(h->enc_graph);
+  if (h->dec_graph) cudaGraphExecDestroy(h->dec_graph);
+  h->enc_graph = h->dec_graph = nullptr;
+}
+
+// Runs `body` (a fixed launch sequence over static buffers) as one CUDA graph on the private stream, fenced against
+// the caller's stream on both sides; the first call captures it.  With graphs disabled the body runs eagerly.
+template <class F>
+int run_captured(b200_mimi* h, cudaGraphExec_t* exec, int64_t* n_kernels, F body) {
+  if (!h->graph_enabled) {
+    h->body = h->stream;
+    return body();
+  }
+  B200_CUDA(cudaEventRecord(h->ev_in, h->stream));
+  B200_CUDA(cudaStreamWaitEvent(h->gstream, h->ev_in, 0));
+  if (!*exec) {
+    cudaGraph_t graph = nullptr;
+    const int64_t before = g_launches.load();
+    h->body = h->gstream;
+    B200_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
+    const int rc = body();
+    cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
+    *n_kernels = g_launches.load() - before;
+    g_launches.fetch_sub(*n_kernels);      // recorded, not executed
+    h->body = h->stream;
+    if (rc != B200_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "graph capture of a Mimi frame failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  }
+  B200_CUDA(cudaGraphLaunch(*exec, h->gstream));
+  g_launches.fetch_add(*n_kernels);
+  B200_CUDA(cudaEventRecord(h->ev_out, h->gstream));
+  B200_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
   return B200_OK;
 }
 
@@ -698,6 +774,7 @@ int b200_mimi_set_num_codebooks(b200_mimi* h, int n) {
   if (n < h->cfg.q_n_semantic || n > h->cfg.q_n_q)   // vq.py:315-317 assertion
     B200_FAIL(B200_ERR_SHAPE, "set_num_codebooks(%d): must be in [%d, %d]", n, h->cfg.q_n_semantic, h->cfg.q_n_q);
   h->num_codebooks = n;
+  if (h->enc_graph) { cudaGraphExecDestroy(h->enc_graph); h->enc_graph = nullptr; }
   return B200_OK;
 }
 
@@ -869,7 +946,16 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->tr_ao, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_h, ntok * ff));
   B200_TRY(A.alloc_t(&h->scratch_codes, (size_t)B * c.q_n_q));
+  B200_TRY(A.alloc_t(&h->enc_codes, (size_t)B * c.q_n_q));
+  B200_TRY(A.alloc_t(&h->dec_codes, (size_t)B * c.q_n_q));
+  B200_TRY(A.alloc_t(&h->out_frame, (size_t)B * h->frame_size));
+  B200_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  h->body = h->stream;
   B200_TRY(ensure_rvq_workspace(h, B));
+  h->splitk_bytes = (size_t)16 << 20;
+  B200_TRY(A.alloc(reinterpret_cast<void**>(&h->splitk_ws), h->splitk_bytes, false));
   B200_CUDA(cudaDeviceSynchronize());
   h->batch = B;
   return B200_OK;
@@ -877,7 +963,15 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
 
 int b200_mimi_streaming_end(b200_mimi* h) {
   if (!h) return B200_OK;
-  if (h->batch > 0) cudaStreamSynchronize(h->stream);
+  if (h->batch > 0) {
+    cudaStreamSynchronize(h->stream);
+    if (h->gstream) cudaStreamSynchronize(h->gstream);
+  }
+  drop_graphs(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->state.free_all();
   h->batch = 0;
   h->taps.clear();
@@ -921,7 +1015,9 @@ int b200_mimi_encode_to_latent(b200_mimi* h, const float* pcm_dev, int n_frames,
   if (!pcm_dev || !latent_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_encode_to_latent: bad arguments");
   const int d = h->cfg.dimension;
   for (int f = 0; f < n_frames; ++f) {
-    B200_TRY(encode_frame_to_latent(h, pcm_dev, n_frames, f));
+    B200_TRY(load_frame(h, pcm_dev, n_frames, f));
+    h->body = h->stream;
+    B200_TRY(encode_body(h));
     B200_CUDA(cudaMemcpy2DAsync(latent_dev + f, (size_t)n_frames * 4, h->latent, 4, 4, (size_t)h->batch * d,
                                 cudaMemcpyDeviceToDevice, h->stream));
   }
@@ -932,6 +1028,7 @@ int b200_mimi_quantize(b200_mimi* h, const float* latent_dev, int n_frames, int6
   B200_TRY(ensure_streaming(h, "mimi_quantize"));
   if (!latent_dev || !codes_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_quantize: bad arguments");
   const int d = h->cfg.dimension, K = h->num_codebooks;
+  h->body = h->stream;
   return quantize_cols(h, latent_dev, (long long)d * n_frames, n_frames, 1, n_frames,
                        reinterpret_cast<long long*>(codes_dev), (long long)K * n_frames, n_frames, 1);
 }
@@ -941,9 +1038,14 @@ int b200_mimi_encode(b200_mimi* h, const float* pcm_dev, int n_frames, int64_t* 
   if (!pcm_dev || !codes_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_encode: bad arguments");
   const int d = h->cfg.dimension, K = h->num_codebooks;
   for (int f = 0; f < n_frames; ++f) {
-    B200_TRY(encode_frame_to_latent(h, pcm_dev, n_frames, f));
-    B200_TRY(quantize_cols(h, h->latent, d, 1, 1, 1, reinterpret_cast<long long*>(codes_dev) + f,
-                           (long long)K * n_frames, n_frames, 1));
+    B200_TRY(load_frame(h, pcm_dev, n_frames, f));
+    B200_TRY(run_captured(h, &h->enc_graph, &h->enc_graph_kernels, [&]() -> int {
+      B200_TRY(encode_body(h));
+      return quantize_cols(h, h->latent, d, 1, 1, 1, h->enc_codes, K, 1, 1);
+    }));
+    // enc_codes [B][K] -> codes[b][k][f]
+    B200_CUDA(cudaMemcpy2DAsync(reinterpret_cast<long long*>(codes_dev) + f, (size_t)n_frames * 8, h->enc_codes, 8, 8,
+                                (size_t)h->batch * K, cudaMemcpyDeviceToDevice, h->stream));
   }
   return B200_OK;
 }
@@ -952,6 +1054,7 @@ int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebo
   B200_TRY(ensure_streaming(h, "mimi_decode_latent"));
   if (!codes_dev || !latent_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_decode_latent: bad arguments");
   const int d = h->cfg.dimension;
+  h->body = h->stream;
   return dequantize_cols(h, reinterpret_cast<const long long*>(codes_dev), (long long)n_codebooks * n_frames, n_frames, 1,
                          n_codebooks, n_frames, latent_dev, (long long)d * n_frames, n_frames, 1);
 }
@@ -959,12 +1062,31 @@ int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebo
 int b200_mimi_decode(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames, float* pcm_dev) {
   B200_TRY(ensure_streaming(h, "mimi_decode"));
   if (!codes_dev || !pcm_dev || n_frames < 1) B200_FAIL(B200_ERR_SHAPE, "mimi_decode: bad arguments");
-  const int d = h->cfg.dimension;
-  for (int f = 0; f < n_frames; ++f) {
-    B200_TRY(dequantize_cols(h, reinterpret_cast<const long long*>(codes_dev) + f, (long long)n_codebooks * n_frames,
-                             n_frames, 1, n_codebooks, 1, h->latent_q, d, 1, 1));
-    B200_TRY(decode_latent_frame(h, h->latent_q, pcm_dev, n_frames, f));
+  if (n_codebooks < 1 || n_codebooks > h->cfg.q_n_q) B200_FAIL(B200_ERR_SHAPE, "decode: %d codebooks", n_codebooks);
+  const int d = h->cfg.dimension, fs = h->frame_size;
+  if (h->dec_graph && h->dec_graph_ncb != n_codebooks) {
+    cudaGraphExecDestroy(h->dec_graph);
+    h->dec_graph = nullptr;
   }
+  h->dec_graph_ncb = n_codebooks;
+  for (int f = 0; f < n_frames; ++f) {
+    // codes[b][k][f] -> dec_codes [B][n_codebooks]
+    B200_CUDA(cudaMemcpy2DAsync(h->dec_codes, 8, reinterpret_cast<const long long*>(codes_dev) + f, (size_t)n_frames * 8, 8,
+                                (size_t)h->batch * n_codebooks, cudaMemcpyDeviceToDevice, h->stream));
+    B200_TRY(run_captured(h, &h->dec_graph, &h->dec_graph_kernels, [&]() -> int {
+      B200_TRY(dequantize_cols(h, h->dec_codes, n_codebooks, 1, 1, n_codebooks, 1, h->latent_q, d, 1, 1));
+      return decode_latent_body(h);
+    }));
+    B200_CUDA(cudaMemcpy2DAsync(pcm_dev + (size_t)f * fs, (size_t)fs * n_frames * 4, h->out_frame, (size_t)fs * 4,
+                                (size_t)fs * 4, h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return B200_OK;
+}
+
+int b200_mimi_set_graph(b200_mimi* h, int enable) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "mimi_set_graph: null handle");
+  h->graph_enabled = enable;
+  if (!enable) drop_graphs(h);
   return B200_OK;
 }
 

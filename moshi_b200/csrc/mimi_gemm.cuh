@@ -41,6 +41,7 @@ struct GemmArgs {
   const float* partial; float* scratch;      // convtr overlap-add carry and its candidate (conv.py:349-361)
   const float* scale; int lin_epi;           // lin: layer-scale vector, GL_*
   int vec_y, vec_a, vec_r;                   // conv: 4 consecutive t may be moved as one float4
+  int ksplit; float* ws;                     // split-K: blockIdx.z owns k-blocks [z*kchunk, ...); partials [z][M][N] in ws
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -50,6 +51,45 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Epilogue of one output element (used by the split-K reduction; the main kernel has vectorised forms of the same).
+template <int KIND>
+__device__ __forceinline__ void gemm_store_one(const GemmArgs& p, int m, int n, float accv) {
+  if (KIND == G_LIN) {
+    float v = accv;
+    if (p.lin_epi == GL_GELU) v = gelu_erf(v);
+    else if (p.lin_epi == GL_RES_SCALE) v = p.res[(long long)n * p.yb + m] + p.scale[m] * v;
+    p.y[(long long)n * p.yb + m] = v;
+  } else if (KIND == G_CONV) {
+    const int b = n / p.T, t = n - b * p.T;
+    float v = accv + (p.bias ? p.bias[m] : 0.f);
+    if (p.res) v += p.res[b * p.rb + m * p.rc + t * p.rt];
+    if (p.y) p.y[b * p.yb + m * p.yc + t * p.yt] = v;
+    if (p.a) p.a[b * p.ab + m * p.ac + t * p.at] = p.a_elu ? elu1(v) : v;
+  } else {
+    const int S = p.stride;
+    const int b = n / (p.T + 1), t = n - b * (p.T + 1);
+    const int co = m / S, r = m - co * S;
+    const long long sidx = ((long long)b * (p.M / S) + co) * S + r;
+    if (t == p.T) { p.scratch[sidx] = accv; return; }
+    float v = accv + (p.bias ? p.bias[co] : 0.f);
+    if (t == 0) v += p.partial[sidx];
+    const long long to = (long long)t * S + r;
+    if (p.y) p.y[b * p.yb + co * p.yc + to * p.yt] = v;
+    if (p.a) p.a[b * p.ab + co * p.ac + to * p.at] = p.a_elu ? elu1(v) : v;
+  }
+}
+
+// sums the split-K partials in split order (deterministic) and applies the epilogue
+template <int KIND>
+static __global__ void gemm_splitk_reduce_kernel(const GemmArgs p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.M * p.N) return;
+  const int n = i % p.N, m = i / p.N;
+  float v = 0.f;
+  for (int z = 0; z < p.ksplit; ++z) v += p.ws[((long long)z * p.M + m) * p.N + n];
+  gemm_store_one<KIND>(p, m, n, v);
+}
 
 template <int BM, int BN, int KIND>
 static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mimi_gemm_kernel(const GemmArgs p) {
@@ -148,17 +188,22 @@ static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mim
     }
   };
 
-  const int nk = (p.Kd + GK - 1) / GK;
-  load_a(0, 0);
-  fetch_b(0);
-  stash_b(0);
-  cp_async_wait_all();
+  const int nk_all = (p.Kd + GK - 1) / GK;
+  const int per = (nk_all + p.ksplit - 1) / p.ksplit;          // k-blocks per split (ksplit == 1: all of them)
+  const int kb0 = blockIdx.z * per;
+  const int nk = min(per, nk_all - kb0);                          // may be <= 0 for a trailing split: contributes zeros
+  if (nk > 0) {
+    load_a(0, kb0 * GK);
+    fetch_b(kb0 * GK);
+    stash_b(0);
+    cp_async_wait_all();
+  }
   __syncthreads();
   for (int it = 0; it < nk; ++it) {
     const int cur = it & 1;
     if (it + 1 < nk) {
-      load_a(cur ^ 1, (it + 1) * GK);
-      fetch_b((it + 1) * GK);
+      load_a(cur ^ 1, (kb0 + it + 1) * GK);
+      fetch_b((kb0 + it + 1) * GK);
     }
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
@@ -187,6 +232,24 @@ static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mim
 
   // ---- epilogue ------------------------------------------------------------------------------
   // thread owns rows m = m0 + ty*4 + gi*(BM/GM) + ii and columns n = n0 + tx*4 + gj*(BN/GN) + jj
+  if (p.ksplit > 1) {                                             // partial sums only; gemm_splitk_reduce_kernel finishes
+    float* wz = p.ws + (long long)blockIdx.z * p.M * p.N;
+#pragma unroll
+    for (int gj = 0; gj < GN; ++gj)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int n = n0 + tx * 4 + gj * (BN / GN) + jj;
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int gi = 0; gi < GM; ++gi)
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int m = m0 + ty * 4 + gi * (BM / GM) + ii;
+            if (m < p.M) wz[(long long)m * p.N + n] = acc[4 * gi + ii][4 * gj + jj];
+          }
+      }
+    return;
+  }
 #pragma unroll
   for (int gj = 0; gj < GN; ++gj) {
     const int nb = n0 + tx * 4 + gj * (BN / GN);                 // first of 4 consecutive columns

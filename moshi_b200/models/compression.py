@@ -50,6 +50,7 @@ class MimiModel:
         self._h = C.c_void_p()
         self._batch: int | None = None
         self._num_codebooks = cfg.num_codebooks
+        self.use_graph = True      # replay each one-frame encode / decode as a CUDA graph
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200_mimi_create(C.byref(_config_struct(cfg)), C.byref(self._h)))
             for name, t in normalize_mimi_state_dict(state_dict).items():
@@ -118,6 +119,7 @@ class MimiModel:
     def _start(self, batch_size: int) -> None:
         assert self._batch is None, "mimi is already streaming!"          # streaming.py:112
         with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200_mimi_set_graph(self._h, int(self.use_graph)))
             _lib.check(self._lib.b200_mimi_streaming_begin(self._h, int(batch_size), _lib.current_stream(self.device)))
         self._batch = int(batch_size)
 

@@ -204,3 +204,28 @@ def test_host_buffer_entry_points(gpu):
         gpu.decode_host(codes, out)
     assert torch.equal(codes, want.cpu())
     assert torch.equal(out, want_pcm.cpu())
+
+
+@torch.no_grad()
+def test_graph_replay_equals_eager_launches(gpu):
+    """One-frame encode / decode replayed as CUDA graphs == the same kernels launched one by one, bit for bit,
+    including a paused row (exec_mask) and a recycled row (reset) in the middle of the stream."""
+    B, frames = 5, 9
+    pcm = scenarios.mimi_noise(B, frames, seed=23).cuda()
+
+    def run(use_graph):
+        gpu.use_graph = use_graph
+        codes, outs = [], []
+        with gpu.streaming(B):
+            for f in range(frames):
+                scenarios.mimi_mask_events(gpu, f, B)
+                c = gpu.encode(pcm[..., f * 1920:(f + 1) * 1920])
+                codes.append(c.cpu())
+                outs.append(gpu.decode(c).cpu())
+        gpu.use_graph = True
+        return torch.cat(codes, -1), torch.cat(outs, -1)
+
+    c_eager, p_eager = run(False)
+    c_graph, p_graph = run(True)
+    assert torch.equal(c_eager, c_graph)
+    assert torch.equal(p_eager, p_graph)
