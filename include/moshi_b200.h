@@ -117,6 +117,12 @@ int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebo
 int b200_mimi_encode_host(b200_mimi* h, const float* pcm_host, int n_frames, int64_t* codes_host);
 int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codebooks, int n_frames,
                           float* pcm_host);
+/* StreamingModule.get_streaming_state / set_streaming_state (streaming.py:158-181) as one opaque device blob of
+ * b200_mimi_state_bytes() bytes: masks, carried conv samples, overlap-add partials, transformer KV rings, offsets.
+ * A snapshot can only be restored into a session with the same batch size and configuration. */
+int64_t b200_mimi_state_bytes(b200_mimi* h);
+int b200_mimi_get_state(b200_mimi* h, void* dst_dev, int64_t capacity);
+int b200_mimi_set_state(b200_mimi* h, const void* src_dev, int64_t nbytes);
 /* 0 = one launch per kernel, 1 = replay each one-frame encode / decode as a CUDA graph (default 1). */
 int b200_mimi_set_graph(b200_mimi* h, int enable);
 /* Debug taps: copies a named fp32 intermediate of the last call into dst_dev (capacity in elements;
@@ -187,6 +193,11 @@ int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const 
  * (step_with_extra_heads), "dep_logits" bf16 [dep_q,B,card], "input_tokens" i64 [B,n_q+1],
  * "text_token" i64 [B], "audio_tokens" i64 [dep_q,B]. */
 int b200_lm_read_buffer(b200_lm* h, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes);
+/* LMGen.get_streaming_state / set_streaming_state: token ring, per-row offsets, exec mask, the temporal KV rings
+ * (1.573 GB per session at full context) and the host step counter, as one opaque device blob. */
+int64_t b200_lm_state_bytes(b200_lm* h);
+int b200_lm_get_state(b200_lm* h, void* dst_dev, int64_t capacity);
+int b200_lm_set_state(b200_lm* h, const void* src_dev, int64_t nbytes);
 /* Algorithmic HBM bytes of one step at the current batch and ring fill: weights once
  * + per-row KV read/append + embeddings + logits. */
 int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill);

@@ -63,6 +63,9 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_mimi_encode_host": (_I, [_P, _P, _I, _P]),
     "b200_mimi_decode_host": (_I, [_P, _P, _I, _I, _P]),
     "b200_mimi_set_graph": (_I, [_P, _I]),
+    "b200_mimi_state_bytes": (C.c_int64, [_P]),
+    "b200_mimi_get_state": (_I, [_P, _P, C.c_int64]),
+    "b200_mimi_set_state": (_I, [_P, _P, C.c_int64]),
     "b200_mimi_read_buffer": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "b200_mimi_algorithmic_bytes": (C.c_int64, [_P]),
     # LM
@@ -78,6 +81,9 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_noise_per_row": (_I, [_P]),
     "b200_lm_step": (_I, [_P, _P, _I, _P, _P, _I, C.POINTER(_I)]),
     "b200_lm_step_host": (_I, [_P, _P, _I, _P, _P, _I, C.POINTER(_I)]),
+    "b200_lm_state_bytes": (C.c_int64, [_P]),
+    "b200_lm_get_state": (_I, [_P, _P, C.c_int64]),
+    "b200_lm_set_state": (_I, [_P, _P, C.c_int64]),
     "b200_lm_read_buffer": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "b200_lm_algorithmic_bytes": (C.c_int64, [_P, _I]),
     "b200_lm_assume_fill": (_I, [_P, _I]),

@@ -60,6 +60,33 @@ int Arena::alloc(void** out, size_t bytes, bool zero) {
 void Arena::free_all() {
   for (void* p : ptrs) cudaFree(p);
   ptrs.clear();
+  snap.clear();
+}
+
+static size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
+
+size_t Arena::state_bytes() const {
+  size_t n = 0;
+  for (auto& s : snap) n += pad256(s.second);
+  return n;
+}
+
+int Arena::save(void* dst, cudaStream_t st) const {
+  size_t off = 0;
+  for (auto& s : snap) {
+    B200_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, s.first, s.second, cudaMemcpyDeviceToDevice, st));
+    off += pad256(s.second);
+  }
+  return B200_OK;
+}
+
+int Arena::load(const void* src, cudaStream_t st) const {
+  size_t off = 0;
+  for (auto& s : snap) {
+    B200_CUDA(cudaMemcpyAsync(s.first, static_cast<const char*>(src) + off, s.second, cudaMemcpyDeviceToDevice, st));
+    off += pad256(s.second);
+  }
+  return B200_OK;
 }
 
 }  // namespace b200

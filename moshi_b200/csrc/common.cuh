@@ -96,6 +96,12 @@ struct TensorStore {
 // Device allocation bookkeeping for a handle: everything freed in one place.
 struct Arena {
   std::vector<void*> ptrs;
+  // buffers that make up the streaming state (get/set_streaming_state, streaming.py:158-181), in registration order
+  std::vector<std::pair<void*, size_t>> snap;
+  void mark_state(void* p, size_t bytes) { if (p && bytes) snap.push_back({p, bytes}); }
+  size_t state_bytes() const;                 // each segment padded to 256 B
+  int save(void* dst, cudaStream_t st) const;
+  int load(const void* src, cudaStream_t st) const;
   int alloc(void** out, size_t bytes, bool zero = true);
   template <typename T>
   int alloc_t(T** out, size_t count, bool zero = true) {

@@ -434,8 +434,40 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_CUDA(cudaMallocHost(&h->pin_in, (size_t)B * n_in_max * 8));
   B200_CUDA(cudaMallocHost(&h->pin_out, (size_t)B * (c.dep_q + 1) * 8));
   B200_CUDA(cudaMallocHost(&h->pin_noise, (size_t)B * noise_per_row(h) * 4));
+  // streaming-state snapshot (lm.py:527-542 _LMGenState + the temporal transformer's ring caches)
+  A.mark_state(h->exec_mask, B);
+  A.mark_state(h->cache, (size_t)B * h->Kc * h->CT * 8);
+  A.mark_state(h->offsets, (size_t)B * 8);
+  A.mark_state(h->pos, (size_t)B * 8);
+  for (auto& L : h->layers) {
+    A.mark_state(L.kc, (size_t)B * H * c.context * D * 2);
+    A.mark_state(L.vc, (size_t)B * H * c.context * D * 2);
+  }
   B200_CUDA(cudaDeviceSynchronize());
   h->batch = B;
+  return B200_OK;
+}
+
+/* get_streaming_state / set_streaming_state: device blob = marked buffers + the host step counter (last 256 B) */
+int64_t b200_lm_state_bytes(b200_lm* h) { return (h && h->batch > 0) ? (int64_t)h->state.state_bytes() + 256 : 0; }
+
+int b200_lm_get_state(b200_lm* h, void* dst_dev, int64_t capacity) {
+  B200_TRY(ensure_streaming(h, "lm_get_state"));
+  const size_t n = h->state.state_bytes();
+  if (!dst_dev || capacity < (int64_t)n + 256) B200_FAIL(B200_ERR_SHAPE, "lm_get_state: destination too small");
+  B200_TRY(h->state.save(dst_dev, h->stream));
+  B200_CUDA(cudaMemcpyAsync(static_cast<char*>(dst_dev) + n, &h->offset_cpu, 8, cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+
+int b200_lm_set_state(b200_lm* h, const void* src_dev, int64_t nbytes) {
+  B200_TRY(ensure_streaming(h, "lm_set_state"));
+  const size_t n = h->state.state_bytes();
+  if (!src_dev || nbytes != (int64_t)n + 256) B200_FAIL(B200_ERR_SHAPE, "lm_set_state: snapshot does not fit this session layout");
+  B200_TRY(h->state.load(src_dev, h->stream));
+  B200_CUDA(cudaMemcpyAsync(&h->offset_cpu, static_cast<const char*>(src_dev) + n, 8, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200_OK;
 }
 

@@ -953,6 +953,24 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
   h->body = h->stream;
+  // what a streaming-state snapshot holds (streaming.py:158-181): masks, carried conv samples, overlap-add
+  // partials, both transformers' KV rings and offsets
+  A.mark_state(h->exec_mask, B);
+  A.mark_state(h->first_flags, (size_t)h->n_first * B);
+  for (auto* layers : {&h->enc, &h->dec})
+    for (auto& l : *layers) {
+      if (l.ext && l.kind == 0) A.mark_state(l.ext, (size_t)B * l.cin * l.E * 4);
+      if (l.state) A.mark_state(l.state, (size_t)B * (l.kind == 0 ? l.cin : l.cout) * l.P * 4);
+    }
+  A.mark_state(h->down.state, (size_t)B * h->down.cin * h->down.P * 4);
+  A.mark_state(h->up_partial, (size_t)B * d * h->rs * 4);
+  for (Transformer* tr : {&h->enc_tr, &h->dec_tr}) {
+    A.mark_state(tr->offset, (size_t)B * 8);
+    for (auto& L : tr->layers) {
+      A.mark_state(L.kc, (size_t)B * H * c.tr_context * D * 4);
+      A.mark_state(L.vc, (size_t)B * H * c.tr_context * D * 4);
+    }
+  }
   B200_TRY(ensure_rvq_workspace(h, B));
   h->splitk_bytes = (size_t)16 << 20;
   B200_TRY(A.alloc(reinterpret_cast<void**>(&h->splitk_ws), h->splitk_bytes, false));
@@ -1081,6 +1099,23 @@ int b200_mimi_decode(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, in
                                 (size_t)fs * 4, h->batch, cudaMemcpyDeviceToDevice, h->stream));
   }
   return B200_OK;
+}
+
+/* get_streaming_state / set_streaming_state (streaming.py:158-181) as one opaque device blob */
+int64_t b200_mimi_state_bytes(b200_mimi* h) { return (h && h->batch > 0) ? (int64_t)h->state.state_bytes() : 0; }
+
+int b200_mimi_get_state(b200_mimi* h, void* dst_dev, int64_t capacity) {
+  B200_TRY(ensure_streaming(h, "mimi_get_state"));
+  if (!dst_dev || capacity < (int64_t)h->state.state_bytes()) B200_FAIL(B200_ERR_SHAPE, "mimi_get_state: destination too small");
+  return h->state.save(dst_dev, h->stream);
+}
+
+int b200_mimi_set_state(b200_mimi* h, const void* src_dev, int64_t nbytes) {
+  B200_TRY(ensure_streaming(h, "mimi_set_state"));
+  if (!src_dev || nbytes != (int64_t)h->state.state_bytes())
+    B200_FAIL(B200_ERR_SHAPE, "mimi_set_state: snapshot of %lld bytes does not fit this session layout (%lld)",
+              (long long)nbytes, (long long)h->state.state_bytes());
+  return h->state.load(src_dev, h->stream);
 }
 
 int b200_mimi_set_graph(b200_mimi* h, int enable) {

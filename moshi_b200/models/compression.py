@@ -153,11 +153,20 @@ class MimiModel:
         m = self._mask(exec_mask)
         _lib.check(self._lib.b200_mimi_set_exec_mask(self._h, _lib.ptr(m)))
 
-    def get_streaming_state(self):
-        raise NotImplementedError("streaming-state snapshots are not exposed by the B200 path yet")
+    def get_streaming_state(self) -> dict:
+        """Snapshot of all streaming state (streaming.py:158-170) as one device blob."""
+        assert self._batch is not None, "mimi is not streaming"
+        n = int(self._lib.b200_mimi_state_bytes(self._h))
+        blob = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.b200_mimi_get_state(self._h, _lib.ptr(blob), n))
+        return {"batch_size": self._batch, "blob": blob}
 
-    def set_streaming_state(self, state):
-        raise NotImplementedError("streaming-state snapshots are not exposed by the B200 path yet")
+    def set_streaming_state(self, state: dict) -> None:
+        """Restore a snapshot taken by ``get_streaming_state`` (streaming.py:172-181)."""
+        assert self._batch is not None, "mimi is not streaming"
+        assert state["batch_size"] == self._batch, "snapshot was taken with another batch size"
+        blob = state["blob"].to(self.device).contiguous()
+        _lib.check(self._lib.b200_mimi_set_state(self._h, _lib.ptr(blob), blob.numel()))
 
     # ---- data path ------------------------------------------------------------------------------
     def _check_pcm(self, x: torch.Tensor) -> torch.Tensor:

@@ -190,6 +190,20 @@ class LMGen:
         m = self._mask(exec_mask)
         _lib.check(self._lib.b200_lm_set_exec_mask(self._h, _lib.ptr(m)))
 
+    def get_streaming_state(self) -> dict:
+        """Snapshot of the generation state (token ring, offsets, KV rings) as one device blob."""
+        assert self._batch is not None, "lm_gen is not streaming"
+        n = int(self._lib.b200_lm_state_bytes(self._h))
+        blob = torch.empty(n, dtype=torch.uint8, device=self.lm_model.device)
+        _lib.check(self._lib.b200_lm_get_state(self._h, _lib.ptr(blob), n))
+        return {"batch_size": self._batch, "blob": blob}
+
+    def set_streaming_state(self, state: dict) -> None:
+        assert self._batch is not None, "lm_gen is not streaming"
+        assert state["batch_size"] == self._batch, "snapshot was taken with another batch size"
+        blob = state["blob"].to(self.lm_model.device).contiguous()
+        _lib.check(self._lib.b200_lm_set_state(self._h, _lib.ptr(blob), blob.numel()))
+
     # ---- sampling noise --------------------------------------------------------------------------
     def draw_noise(self) -> torch.Tensor | None:
         """Exp(1) draws of one step in the reference's order (lm.py:736 then lm.py:836 x dep_q),

@@ -209,3 +209,23 @@ def test_rows_independent_graph_invariant_and_host_path():
     for i in (2, 3):
         assert (masked[i][3] == -2).all()
         assert torch.equal(masked[i][[0, 1, 2] + list(range(4, B))], eager[i][[0, 1, 2] + list(range(4, B))])
+
+
+@torch.no_grad()
+def test_streaming_state_snapshot_roundtrip(lm, tiny):
+    """LMGen.get_streaming_state / set_streaming_state: the continuation from a snapshot is reproduced exactly."""
+    from moshi_b200.models import LMGen
+    cfg, _ = tiny
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, cfg.card, (8, B, 8, 1), generator=g).cuda()
+    gen = LMGen(lm, use_sampling=False)
+    with gen.streaming(B):
+        for i in range(4):
+            gen.step(codes[i])
+        snap = gen.get_streaming_state()
+        first = [gen.step(codes[i]).cpu() for i in range(4, 8)]
+        gen.set_streaming_state(snap)
+        second = [gen.step(codes[i]).cpu() for i in range(4, 8)]
+    for a, b in zip(first, second):
+        assert torch.equal(a, b)

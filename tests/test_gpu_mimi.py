@@ -229,3 +229,27 @@ def test_graph_replay_equals_eager_launches(gpu):
     c_graph, p_graph = run(True)
     assert torch.equal(c_eager, c_graph)
     assert torch.equal(p_eager, p_graph)
+
+
+@torch.no_grad()
+def test_streaming_state_snapshot_roundtrip(gpu):
+    """get_streaming_state / set_streaming_state (streaming.py:158-181): replaying from a snapshot reproduces the
+    continuation bit for bit (conv carries, overlap-add partials, KV rings, offsets, masks all restored)."""
+    B = 3
+    pcm = scenarios.mimi_noise(B, 6, seed=5).cuda()
+    with gpu.streaming(B):
+        for f in range(3):
+            gpu.decode(gpu.encode(pcm[..., f * 1920:(f + 1) * 1920]))
+        snap = gpu.get_streaming_state()
+
+        def tail():
+            out = []
+            for f in range(3, 6):
+                c = gpu.encode(pcm[..., f * 1920:(f + 1) * 1920])
+                out.append((c.cpu(), gpu.decode(c).cpu()))
+            return out
+        first = tail()
+        gpu.set_streaming_state(snap)
+        second = tail()
+    for (c1, p1), (c2, p2) in zip(first, second):
+        assert torch.equal(c1, c2) and torch.equal(p1, p2)
