@@ -483,13 +483,19 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   int grid = tune.grid > 0 ? tune.grid : g_sms;
   if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
   if (grid > p.n_tiles * p.num_kb) grid = p.n_tiles * p.num_kb;
-  // whole rounds of the grid, then the remainder: stream-K it unless it nearly fills a round anyway (or the
-  // partials would be as large as the weights they save waiting for: M large and few k-blocks)
+  // Cutting a tile into S pieces moves S fp32 partials of [128 x Mpad] through L2 (written + read back): allow it
+  // only while that stays under half of the tile's weight bytes, i.e. S <= 8 * num_kb / Mpad.
+  int s_max = tune.no_split ? 1 : (8 * p.num_kb) / p.Mpad;
+  // measured on B200 (profiles/r01_c_kbench.jsonl): with more than 32 sessions the publish / count / re-read protocol
+  // costs more than the idle SMs it recovers, so tiles stay whole there
+  if (p.Mpad > 32 && tune.force_split == 0) s_max = 1;
+  if (s_max < 1) s_max = 1;
+  if (p.n_tiles < grid && (long long)p.n_tiles * s_max < grid) grid = p.n_tiles * s_max;   // fewer CTAs, fewer pieces
+  // whole rounds of the grid, then the remainder as a stream-K region shared by all CTAs
   p.grid = grid;
   p.whole_rounds = p.n_tiles / grid;
   int rem = p.n_tiles - p.whole_rounds * grid;
-  // cutting tiles pays when the partial accumulators are small (few sessions) or the remainder leaves most SMs idle
-  const bool split = rem > 0 && tune.no_split == 0 && (M <= 32 ? rem * 8 < grid * 7 : rem * 2 <= grid);
+  const bool split = rem > 0 && s_max > 1 && rem * 8 < grid * 7 && (long long)rem * s_max >= grid;
   if (rem > 0 && !split) { p.whole_rounds += 1; rem = 0; }
   p.sk_tile0 = p.n_tiles - rem;
   p.sk_items = rem * p.num_kb;

@@ -44,6 +44,7 @@ struct SkTuning {
   int smem_budget = 0;   // bytes of pipeline stages per CTA (0 = 200 KB)
   int stream_only = 0;   // diagnostics: run the copy pipeline without MMAs / stores
   int no_split = 0;      // never cut a tile across CTAs (whole tiles only)
+  int force_split = 0;   // tests: cut tiles even where the default policy keeps them whole
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
 };
 int sk_num_sms();
