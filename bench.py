@@ -216,22 +216,22 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
     H, cap, D = 32, 3000, 128
     k = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
     v = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
-    q = torch.randn(B, H, D, device=device).bfloat16()
-    out = torch.empty_like(q)
+    qkv = torch.randn(B, 3 * H * D, device=device).bfloat16()
+    out = torch.empty(B, H * D, device=device, dtype=torch.bfloat16)
     offs = torch.full((B,), max(kv_fill - 1, 0) + (cap if kv_fill >= cap else 0), dtype=torch.int64, device=device)
     mask = torch.ones(B, dtype=torch.bool, device=device)
     stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     def fn():
-        _lib.check(lib.b200_op_attn_decode(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
-                                           _lib.ptr(mask), B, H, cap, 0, stream))
+        _lib.check(lib.b200_op_attn_step(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
+                                         _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
     ms = _event_time(fn)
     n_keys = min(max(kv_fill, 1), cap)
-    alg = 2 * B * H * n_keys * D * 2 + 2 * B * H * D * 2
+    alg = 2 * B * H * n_keys * D * 2 + 6 * B * H * D * 2      # K,V rings once + qkv in, K/V append and output out
     peak, src = _peaks()
     gbs = alg / (ms * 1e-3) / 1e9
     del k, v
-    return {"kernel": "lm::attn_decode_kernel (+combine), temporal ring attention, B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
+    return {"kernel": "lm::attn_step_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
             "bound": "hbm", "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak,
             "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
 

@@ -241,6 +241,11 @@ int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_d
 int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev,
                         const int64_t* offsets_dev, const uint8_t* exec_mask_dev, int B, int H, int cap,
                         int nsplit, void* stream);
+/* One temporal attention step, as the LM launches it (transformer.py:557-597): qkv bf16 [B,3*H*128] (rows q|k|v),
+ * RoPE(q,k) at pos[b], K/V appended to the rings [B,H,cap,128] at pos % cap for rows with exec_mask, attention over
+ * the min(pos + exec, cap) valid slots, out bf16 [B,H*128].  One kernel (rope + append + split-KV + merge). */
+int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_dev, const int64_t* pos_dev,
+                      const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period, void* stream);
 /* sample_token (sampling.py:86-106): logits bf16 [B,card], noise f32 [B,min(k,card)] -> i64 [B]. */
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B,
                    int card, int use_sampling, float temp, int top_k, void* stream);

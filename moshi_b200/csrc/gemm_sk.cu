@@ -483,6 +483,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   int grid = tune.grid > 0 ? tune.grid : g_sms;
   if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
   if (grid > p.n_tiles * p.num_kb) grid = p.n_tiles * p.num_kb;
+  // a CTA should stream at least ~8 k-blocks (128-256 KB): below that the per-CTA set-up and the partial exchange dominate
+  if (tune.grid == 0 && grid > (p.n_tiles * p.num_kb) / 8) grid = (p.n_tiles * p.num_kb) / 8 > 0 ? (p.n_tiles * p.num_kb) / 8 : 1;
   // Cutting a tile into S pieces moves S fp32 partials of [128 x Mpad] through L2 (written + read back): allow it
   // only while that stays under half of the tile's weight bytes, i.e. S <= 8 * num_kb / Mpad.
   int s_max = tune.no_split ? 1 : (8 * p.num_kb) / p.Mpad;

@@ -59,6 +59,7 @@ struct b200_lm {
   bf16 *text_logits = nullptr, *din = nullptr, *dx = nullptr, *dxn = nullptr, *dqkv = nullptr, *dq = nullptr, *dao = nullptr,
        *dh = nullptr, *dep_logits = nullptr;
   float* attn_part = nullptr;
+  int* attn_counters = nullptr;                // split arrival counters [B*H]
   int nsplit = 1;
   int n_in_static = 0;
   // graph
@@ -162,13 +163,13 @@ int step_body(b200_lm* h) {
   for (auto& L : h->layers) {
     B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
     B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0));
-    B200_LAUNCH(rope_append_bf16_kernel, (unsigned)ceil_div64((long long)B * H * D / 2, 256), 256, 0, st, h->qkv, h->q,
-                L.kc, L.vc, h->pos, h->exec_mask, 0, B, H, D, c.context, 1, nl);
-    {
+    {   // RoPE + ring append + split-KV attention + split merge in one launch
+      AttnStep a;
+      a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
+      a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+      a.neg_log_period_2_over_d = nl;
       dim3 grid(B * H, h->nsplit);
-      B200_LAUNCH(attn_decode_kernel, grid, ATT_THREADS, 0, st, h->q, L.kc, L.vc, h->attn_part, h->pos, h->exec_mask, H,
-                  c.context, h->nsplit);
-      B200_LAUNCH(attn_combine_kernel, B * H, ATT_D, 0, st, h->attn_part, h->ao, h->nsplit);
+      B200_LAUNCH(attn_step_kernel, grid, ATT_THREADS, 0, st, a);
     }
     B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0));
     B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n2, h->xn, d, 1e-8f);
@@ -190,10 +191,7 @@ int step_body(b200_lm* h) {
     for (auto& L : h->dlayers) {
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
       B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0));
-      B200_LAUNCH(rope_append_bf16_kernel, (unsigned)ceil_div64((long long)B * dH * dD / 2, 256), 256, 0, st, h->dqkv,
-                  h->dq, L.kc, L.vc, (const long long*)nullptr, (const uint8_t*)nullptr, k, B, dH, dD, c.dep_q, 0, 0.f);
-      B200_LAUNCH(dep_attn_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dq, L.kc, L.vc, h->dao, B, dH, dD, c.dep_q,
-                  k + 1);
+      B200_LAUNCH(dep_attn_step_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dqkv, L.kc, L.vc, h->dao, B, dH, c.dep_q, k);
       B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0));
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
       B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF));
@@ -233,8 +231,8 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
     B200_FAIL(B200_ERR_INVALID, "lm_create: n_q=%d dep_q=%d unsupported", cfg->n_q, cfg->dep_q);
   if (cfg->dim % cfg->num_heads || cfg->dim / cfg->num_heads != ATT_D)
     B200_FAIL(B200_ERR_INVALID, "lm_create: temporal head dim must be %d", ATT_D);
-  if (cfg->depformer_dim % cfg->depformer_num_heads || (cfg->depformer_dim / cfg->depformer_num_heads) % 64)
-    B200_FAIL(B200_ERR_INVALID, "lm_create: depformer head dim must be a multiple of 64");
+  if (cfg->depformer_dim % cfg->depformer_num_heads || cfg->depformer_dim / cfg->depformer_num_heads != 64)
+    B200_FAIL(B200_ERR_INVALID, "lm_create: depformer head dim must be 64");
   if (cfg->dep_q > 8) B200_FAIL(B200_ERR_INVALID, "lm_create: dep_q > 8 unsupported");
   if (cfg->dim % 8 || cfg->ffn_hidden % 8 || cfg->depformer_dim % 8 || cfg->depformer_ffn_hidden % 8)
     B200_FAIL(B200_ERR_INVALID, "lm_create: feature sizes must be multiples of 8");
@@ -428,6 +426,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   const int ns = attn_pick_splits(B, H, c.context);
   h->nsplit = ns;
   B200_TRY(A.alloc_t(&h->attn_part, (size_t)B * H * ns * (ATT_D + 2)));
+  B200_TRY(A.alloc_t(&h->attn_counters, (size_t)B * H));
   B200_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));

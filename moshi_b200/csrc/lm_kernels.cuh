@@ -383,6 +383,197 @@ static __global__ void __launch_bounds__(ATT_D) attn_combine_kernel(const float*
   out[(long long)bh * ATT_D + d] = f2bf(L > 0.f ? A / L : 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused temporal attention step (T = 1, D = 128): RoPE(q, k) + ring append + split-KV attention +
+// split combine in ONE launch (transformer.py:557-597).
+//   grid = (B*H, nsplit), 128 threads.  qkv [B][3C] bf16 (rows q | k | v, each (h d)).
+//   * the CTA whose key range holds the slot of the new key rotates k, writes K/V there, syncs, and then
+//     reads it back like any other key; no other CTA touches that slot (ranges are disjoint), so the
+//     append needs no separate kernel and the oldest key it replaces is never attended;
+//   * q is rotated in registers (rounded to bf16 like the reference's apply_rope output);
+//   * with nsplit > 1 the last CTA to arrive for a (b, h) merges the partials in split order.
+// ---------------------------------------------------------------------------------------------
+struct AttnStep {
+  const bf16* qkv; bf16* kc; bf16* vc; bf16* out;
+  float* part; int* counters;                  // [B*H][nsplit][ATT_D + 2], [B*H] (zero between launches)
+  const long long* pos; const uint8_t* exec_mask;
+  int H, cap, nsplit; float neg_log_period_2_over_d;
+};
+
+static __global__ void __launch_bounds__(ATT_THREADS) attn_step_kernel(const AttnStep a) {
+  pdl_trigger();
+  const int bh = blockIdx.x, split = blockIdx.y;
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int C = a.H * ATT_D;
+  const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15;
+  const int hw = tid >> 4;                          // half-warp id 0..7
+  const bool exec = a.exec_mask[b] != 0;
+  const long long p = a.pos[b];
+  long long n_valid = p + (exec ? 1 : 0);
+  if (n_valid > a.cap) n_valid = a.cap;
+  const int per = (int)((n_valid + a.nsplit - 1) / a.nsplit);
+  const int s0 = split * per;
+  const int s1 = (int)min((long long)(s0 + per), n_valid);
+  const int slot_new = (int)(p % a.cap);
+  const bf16* base = a.qkv + (long long)b * 3 * C + h * ATT_D;
+  const float fpos = (float)p;
+
+  if (exec && slot_new >= s0 && slot_new < s1) {    // CTA-uniform: this CTA owns the new key's slot
+    if (tid < ATT_D / 2) {
+      const int pr = tid;
+      float kr = bf2f(base[C + 2 * pr]), ki = bf2f(base[C + 2 * pr + 1]);
+      const float freq = expf((float)pr * a.neg_log_period_2_over_d);
+      float sn, cs;
+      sincosf(freq * fpos, &sn, &cs);
+      const float c2 = kr * cs - ki * sn, d2 = kr * sn + ki * cs;
+      const long long o = ((long long)bh * a.cap + slot_new) * ATT_D + 2 * pr;
+      *reinterpret_cast<__nv_bfloat162*>(a.kc + o) = __floats2bfloat162_rn(c2, d2);
+      *reinterpret_cast<__nv_bfloat162*>(a.vc + o) = *reinterpret_cast<const __nv_bfloat162*>(base + 2 * C + 2 * pr);
+    }
+    __syncthreads();
+  }
+
+  float qf[8];
+  {
+    float raw[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + l16 * 8), raw);
+    const float scale = 0.08838834764831845f;       // 1/sqrt(128)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pr = l16 * 4 + j;
+      const float freq = expf((float)pr * a.neg_log_period_2_over_d);
+      float sn, cs;
+      sincosf(freq * fpos, &sn, &cs);
+      const float qr = raw[2 * j], qi = raw[2 * j + 1];
+      qf[2 * j] = rbf(qr * cs - qi * sn) * scale;
+      qf[2 * j + 1] = rbf(qr * sn + qi * cs) * scale;
+    }
+  }
+
+  const bf16* kb = a.kc + (long long)bh * a.cap * ATT_D + l16 * 8;
+  const bf16* vb = a.vc + (long long)bh * a.cap * ATT_D + l16 * 8;
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  constexpr int U = 4;                              // keys in flight per half-warp
+  for (int kb0 = s0; kb0 < s1; kb0 += 8 * U) {      // warp-uniform trip count (shuffles inside)
+    const int s = kb0 + hw * U;
+    uint4 kr[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ss = s + u < s1 ? s + u : s1 - 1;
+      kr[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * ATT_D);
+      vr[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * ATT_D);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float kf[8];
+      unpack8(kr[u], kf);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      if (s + u < s1) {
+        const float mn = fmaxf(m, d);
+        const float corr = __expf(m - mn), pw = __expf(d - mn);
+        float vf[8];
+        unpack8(vr[u], vf);
+        l = l * corr + pw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(pw, vf[i], acc[i] * corr);
+        m = mn;
+      }
+    }
+  }
+  // merge the 8 half-warps of the CTA
+  __shared__ float sm_m[8], sm_l[8], sm_acc[8][ATT_D];
+  __shared__ int s_last;
+  if (l16 == 0) { sm_m[hw] = m; sm_l[hw] = l; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm_acc[hw][l16 * 8 + i] = acc[i];
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
+  float L = 0.f, A = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - M);
+    L += sm_l[w] * c;
+    A += sm_acc[w][tid] * c;
+  }
+  if (a.nsplit == 1) {
+    a.out[(long long)bh * ATT_D + tid] = f2bf(L > 0.f ? A / L : 0.f);
+    return;
+  }
+  float* o = a.part + ((long long)bh * a.nsplit + split) * (ATT_D + 2);
+  __stcg(o + tid, A);
+  if (tid == 0) { __stcg(o + ATT_D, M); __stcg(o + ATT_D + 1, L); }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(a.counters + bh, 1);
+    s_last = old == a.nsplit - 1;
+    if (s_last) a.counters[bh] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pp = a.part + (long long)bh * a.nsplit * (ATT_D + 2);
+  float MM = -INFINITY;
+  for (int s = 0; s < a.nsplit; ++s) MM = fmaxf(MM, __ldcg(pp + s * (ATT_D + 2) + ATT_D));
+  float LL = 0.f, AA = 0.f;
+  for (int s = 0; s < a.nsplit; ++s) {
+    const float ms = __ldcg(pp + s * (ATT_D + 2) + ATT_D);
+    const float c = ms == -INFINITY ? 0.f : __expf(ms - MM);
+    LL += __ldcg(pp + s * (ATT_D + 2) + ATT_D + 1) * c;
+    AA += __ldcg(pp + s * (ATT_D + 2) + tid) * c;
+  }
+  a.out[(long long)bh * ATT_D + tid] = f2bf(LL > 0.f ? AA / LL : 0.f);
+}
+
+// Depformer attention step: the new key/value of sub-step `step` is appended to the per-frame cache and the query
+// attends over step + 1 keys; no positional embedding (depformer_pos_emb = "none").  One warp per (b, h), D = 64.
+static __global__ void dep_attn_step_kernel(const bf16* __restrict__ qkv /*[B][3*H*D]*/, bf16* __restrict__ kc,
+                                     bf16* __restrict__ vc, bf16* __restrict__ out, int B, int H, int cap, int step) {
+  pdl_trigger();
+  constexpr int D = 64;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * H) return;
+  const int b = warp / H, h = warp - b * H;
+  const int C = H * D;
+  const bf16* base = qkv + (long long)b * 3 * C + h * D + 2 * lane;
+  const long long row = (long long)warp * cap;
+  *reinterpret_cast<__nv_bfloat162*>(kc + (row + step) * D + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(base + C);
+  *reinterpret_cast<__nv_bfloat162*>(vc + (row + step) * D + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(base + 2 * C);
+  __syncwarp();
+  const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base));
+  const float scale = 0.125f;                       // 1/sqrt(64)
+  float sc[8];
+  float mx = -INFINITY;
+  const int n_keys = step + 1;
+  for (int j = 0; j < n_keys; ++j) {
+    const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kc + (row + j) * D + 2 * lane));
+    const float d = warp_sum(q.x * kk.x + q.y * kk.y) * scale;
+    sc[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < n_keys; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.f / sum;
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < n_keys; ++j) {
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vc + (row + j) * D + 2 * lane));
+    a0 = fmaf(sc[j] * inv, v.x, a0);
+    a1 = fmaf(sc[j] * inv, v.y, a1);
+  }
+  *reinterpret_cast<__nv_bfloat162*>(out + (long long)warp * D + 2 * lane) = __floats2bfloat162_rn(a0, a1);
+}
+
 // Depformer attention: <= 8 keys, one warp per (b, h), D = 64 (2 dims per lane).
 static __global__ void dep_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
                                 bf16* __restrict__ out, int B, int H, int D, int cap, int n_keys) {

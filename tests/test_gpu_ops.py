@@ -1,5 +1,6 @@
 """GPU: kernel-level parity through the C ABI (the same kernels the handles launch)."""
 import ctypes as C
+import math
 
 import pytest
 import torch
@@ -134,6 +135,60 @@ def test_ring_attention_decode(lib, B, H, cap, nsplit):
     want = F.scaled_dot_product_attention(q.float()[:, :, None], k.float(), v.float(), allowed[:, None, None, :])[:, :, 0]
     print(stats(f"attn B={B} H={H} cap={cap} nsplit={nsplit}", out, want))
     torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
+def _rope_ref(x: torch.Tensor, pos: torch.Tensor, max_period: float = 10000.0) -> torch.Tensor:
+    """rope.py:45-82 on [B, H, D] bf16 for one time step at per-row position ``pos``: interleaved pairs, fp32, -> bf16."""
+    B, H, D = x.shape
+    xf = x.float().view(B, H, D // 2, 2)
+    freqs = torch.exp(torch.arange(D // 2, dtype=torch.float32) * (-math.log(max_period) * 2 / D))
+    theta = freqs[None, :] * pos.float()[:, None]
+    c, s_ = torch.cos(theta)[:, None, :], torch.sin(theta)[:, None, :]
+    xr, xi = xf[..., 0], xf[..., 1]
+    return torch.stack([xr * c - xi * s_, xr * s_ + xi * c], dim=-1).view(B, H, D).bfloat16()
+
+
+@pytest.mark.parametrize("B,H,cap,nsplit", [(1, 32, 3000, 0), (5, 4, 3000, 1), (3, 2, 12, 0), (7, 8, 250, 3), (2, 32, 3000, 16)])
+def test_fused_attention_step(lib, B, H, cap, nsplit):
+    """The LM's one-launch attention step == RoPE + ring append + masked SDPA of the reference
+    (transformer.py:557-597, 247-286), including a paused row and wrapped rings."""
+    from moshi_b200 import _lib
+    g = torch.Generator().manual_seed(B * 131 + cap)
+    C = H * 128
+    qkv = torch.randn(B, 3 * C, generator=g).bfloat16()
+    k = torch.randn(B, H, cap, 128, generator=g).bfloat16()
+    v = torch.randn(B, H, cap, 128, generator=g).bfloat16()
+    pos = torch.tensor([0, 1, cap - 1, cap, 3 * cap + 5, 17, cap // 2][:B], dtype=torch.int64)
+    mask = torch.ones(B, dtype=torch.bool)
+    if B > 1:
+        mask[1] = False                      # a paused row: no append, attends over the keys it already has
+    q_in, k_in, v_in = (qkv[:, i * C:(i + 1) * C].reshape(B, H, 128) for i in range(3))
+    q_rot, k_rot = _rope_ref(q_in, pos), _rope_ref(k_in, pos)
+    k_ref, v_ref = k.clone(), v.clone()
+    for b in range(B):
+        if mask[b]:
+            k_ref[b, :, pos[b] % cap] = k_rot[b]
+            v_ref[b, :, pos[b] % cap] = v_in[b]
+    n_valid = (pos + mask.long()).clamp(max=cap)
+    allowed = torch.arange(cap)[None, :] < n_valid[:, None]
+    want = F.scaled_dot_product_attention(q_rot.float()[:, :, None], k_ref.float(), v_ref.float(),
+                                          allowed[:, None, None, :])[:, :, 0].reshape(B, C)
+    kd, vd, out = k.cuda(), v.cuda(), torch.empty(B, C, dtype=torch.bfloat16, device="cuda")
+    qd, pd, md = qkv.cuda(), pos.cuda(), mask.cuda()
+    _lib.check(lib.b200_op_attn_step(cptr(qd), cptr(kd), cptr(vd), cptr(out), cptr(pd), cptr(md), B, H, cap, nsplit,
+                                     10000.0, _stream()))
+    torch.cuda.synchronize()
+    rows = n_valid > 0                       # a paused row with an empty ring has nothing to attend to
+    print(stats(f"attn step B={B} H={H} cap={cap} nsplit={nsplit}", out[rows.cuda()], want[rows]))
+    torch.testing.assert_close(out.float().cpu()[rows], want[rows], rtol=2e-2, atol=2e-2)
+    # ring contents: the appended key is the rotated k (one bf16 ulp of slack for sincos), untouched slots are identical
+    torch.testing.assert_close(kd.cpu().float(), k_ref.float(), rtol=0, atol=4e-2)
+    same = torch.ones(B, cap, dtype=torch.bool)
+    for b in range(B):
+        if mask[b]:
+            same[b, pos[b] % cap] = False
+    assert torch.equal(kd.cpu()[same[:, None].expand(B, H, cap)], k[same[:, None].expand(B, H, cap)])
+    assert torch.equal(vd.cpu(), v_ref)
 
 
 def _tie_free_top(B: int, card: int, n_top: int, gen: torch.Generator) -> torch.Tensor:

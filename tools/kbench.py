@@ -97,19 +97,19 @@ def bench_attn(lib, Bs, cap=3000, H=32):
         n_rot = min(n_rot, 8)
         ks = [torch.empty(B, H, cap, 128, device="cuda", dtype=torch.bfloat16).normal_() for _ in range(n_rot)]
         vs = [torch.empty(B, H, cap, 128, device="cuda", dtype=torch.bfloat16).normal_() for _ in range(n_rot)]
-        q = torch.randn(B, H, 128, device="cuda").bfloat16()
-        out = torch.empty_like(q)
+        q = torch.randn(B, 3 * H * 128, device="cuda").bfloat16()
+        out = torch.empty(B, H * 128, device="cuda", dtype=torch.bfloat16)
         mask = torch.ones(B, dtype=torch.bool, device="cuda")
         for fill in (cap, cap // 4):
             offs = torch.full((B,), fill + 7 * cap if fill == cap else fill - 1, dtype=torch.int64, device="cuda")
             for ns in (0,):
                 def fn(i):
-                    _lib.check(lib.b200_op_attn_decode(_lib.ptr(q), _lib.ptr(ks[i]), _lib.ptr(vs[i]), _lib.ptr(out),
-                                                       _lib.ptr(offs), _lib.ptr(mask), B, H, cap, ns, stream()))
+                    _lib.check(lib.b200_op_attn_step(_lib.ptr(q), _lib.ptr(ks[i]), _lib.ptr(vs[i]), _lib.ptr(out),
+                                                     _lib.ptr(offs), _lib.ptr(mask), B, H, cap, ns, 10000.0, stream()))
                 ms = time_ms(fn, n_rot)
                 alg = 2 * B * H * min(fill, cap) * 128 * 2
                 gbs = alg / ms / 1e6
-                print(json.dumps({"kernel": "attn_decode", "B": B, "H": H, "cap": cap, "fill": fill, "nsplit": ns,
+                print(json.dumps({"kernel": "attn_step", "B": B, "H": H, "cap": cap, "fill": fill, "nsplit": ns,
                                   "ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
         del ks, vs
 
