@@ -289,6 +289,16 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
       if (sg.slot < 0) {
         for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
           uint32_t r0[16], r1[16];
+          // the 16 residual reads of this column chunk are issued together, ahead of the TMEM load they are added to
+          // (one dependent global load per element would cost a DRAM/L2 latency each: 96 of them per thread at B=96)
+          float rv[16];
+          if (EPI == EPI_RESADD && !p.stream_only) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = c0 + j;
+              rv[j] = (m < p.M && n_ok) ? __bfloat162float(p.res[(long long)m * p.ldr + n]) : 0.f;
+            }
+          }
           tmem_ld16(lane_addr + (uint32_t)c0, r0);
           if (EPI == EPI_GATE) tmem_ld16(lane_addr + (uint32_t)(p.Mpad + c0), r1);
           tmem_ld_wait();
@@ -296,9 +306,12 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int m = c0 + j;
-              if (m < p.M && n_ok)
-                p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(
-                    epilogue_value<EPI>(p, __uint_as_float(r0[j]), EPI == EPI_GATE ? __uint_as_float(r1[j]) : 0.f, m, n));
+              if (m < p.M && n_ok) {
+                float v;
+                if (EPI == EPI_RESADD) v = rv[j] + bf16_round(__uint_as_float(r0[j]));
+                else v = epilogue_value<EPI>(p, __uint_as_float(r0[j]), EPI == EPI_GATE ? __uint_as_float(r1[j]) : 0.f, m, n);
+                p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
+              }
             }
           }
         }

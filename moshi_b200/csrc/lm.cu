@@ -36,7 +36,7 @@ struct b200_lm {
   int use_sampling = 1, top_k = 250, top_k_text = 25;
   float temp = 0.8f, temp_text = 0.7f;
   int gemm_impl = 3;                           // 3 = stream-K tcgen05 over packed tiles (default)
-  int pdl = 0;                                 // programmatic dependent launch of the GEMMs (B200_PDL=1)
+  int pdl = 1;                                 // programmatic dependent launch of the GEMMs (B200_PDL=0 disables)
   float* sk_ws = nullptr;                      // stream-K partial-accumulator slots (L2-resident)
   int* sk_counters = nullptr;                  // per-tile arrival counters (zero between launches)
   // weights

@@ -44,7 +44,7 @@ def time_ms(fn, n_rot: int, iters: int = 20, warm: int = 3) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def bench_gemm(lib, Ms, legacy=True):
+def bench_gemm(lib, Ms, legacy=True, only=""):
     shapes = [  # (name, N, K, epi, gate_rows)
         ("temporal.in_proj", 12288, 4096, 0, 0), ("temporal.out_proj", 4096, 4096, 1, 0),
         ("temporal.linear_in", 22528, 4096, 2, 11264), ("temporal.linear_out", 4096, 11264, 1, 0),
@@ -53,6 +53,8 @@ def bench_gemm(lib, Ms, legacy=True):
         ("dep.linear_out", 1024, 2816, 1, 0), ("dep.head", 2048, 1024, 0, 0),
     ]
     for name, N, K, epi, gr in shapes:
+        if only and only not in name:
+            continue
         wbytes = N * K * 2
         n_rot = max(2, -(-(400 << 20) // wbytes))
         ws = [torch.empty(N, K, device="cuda", dtype=torch.bfloat16).uniform_(-0.02, 0.02) for _ in range(n_rot)]
@@ -139,6 +141,8 @@ def main():
     ap.add_argument("--what", default="gemm,attn,mimi")
     ap.add_argument("--M", default="1,16,96")
     ap.add_argument("--B", default="1,16,96")
+    ap.add_argument("--only", default="", help="GEMM shape name filter")
+    ap.add_argument("--no-legacy", action="store_true")
     args = ap.parse_args()
     lib = _lib.lib()
     torch.cuda.set_device(0)
@@ -148,7 +152,7 @@ def main():
     if "attn" in what:
         bench_attn(lib, Bs)
     if "gemm" in what:
-        bench_gemm(lib, Ms)
+        bench_gemm(lib, Ms, legacy=not args.no_legacy, only=args.only)
     if "mimi" in what:
         bench_mimi(Bs)
 
