@@ -338,16 +338,21 @@ def b200_arm(args) -> None:
         lm_ms = sum(a.elapsed_time(b) for a, b in lm_ev) / len(lm_ev)
 
         # ---- end to end: host PCM in, host PCM + tokens out, every step ------------------------
-        barrier()
-        torch.cuda.synchronize(device)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
+        def e2e_step(i):
             pcm = pcm_host[i % n_buf].to(device, non_blocking=True)
             toks, out = frame(pcm)
             out_pcm_host.copy_(out, non_blocking=True)
             if toks is not None:
                 out_tok_host.copy_(toks, non_blocking=True)
             torch.cuda.synchronize(device)
+
+        for i in range(2):               # first use of the pinned staging buffers / copy engines is not steady state
+            e2e_step(i)
+        barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
 
     total_sessions = sum_over_ranks(float(B))

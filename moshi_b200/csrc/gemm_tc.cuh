@@ -58,5 +58,29 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
               long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
               float* ws, int* counters, const SkTuning& tune, cudaStream_t stream);
 
+// ---- the depformer of one frame as one persistent kernel (dep_fused.cu) ---------------------------
+struct DepFusedConfig {
+  int B, dd, H, F, card, dep_q, L;
+  const void* const* in_w; const void* const* out_w; const void* const* lin_in; const void* const* lin_out;   // [dep_q*L] packed tiles
+  const void* const* heads;        // [dep_q] packed tiles
+  const void* const* tables;       // [dep_q] embedding tables (bf16 [V][dd]); [0] = text
+  const void* const* n1; const void* const* n2;   // [L] RMSNorm alphas (bf16 [dd])
+  void* const* kc; void* const* vc;               // [L] KV [B][H][dep_q][64] bf16
+  const void* din; long long din_ld;              // depformer_in_all output, bf16 [B][dep_q*dd]
+  const long long* text_token;
+  void *x, *xn, *ao, *hbuf;                       // bf16 [B][dd] x3, [B][F]
+  float *part0, *part1;                           // dep_fused_partial_floats() floats each
+  void* logits; long long* audio_tokens;          // bf16 [dep_q][B][card], i64 [dep_q][B]
+  const float* noise; long long noise_ld; int noise_off, ka;
+  int use_sampling, top_k; float temp;
+  unsigned* bar;
+};
+struct DepFused;
+size_t dep_fused_partial_floats(const DepFusedConfig& c);
+int dep_fused_create(const DepFusedConfig& c, DepFused** out);
+void dep_fused_set_sampling(DepFused* d, int use_sampling, float temp, int top_k);
+void dep_fused_destroy(DepFused* d);
+int dep_fused_launch(DepFused* d, cudaStream_t stream);
+
 }  // namespace tc
 }  // namespace b200

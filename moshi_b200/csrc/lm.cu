@@ -60,6 +60,10 @@ struct b200_lm {
        *dh = nullptr, *dep_logits = nullptr;
   float* attn_part = nullptr;
   int* attn_counters = nullptr;                // split arrival counters [B*H]
+  tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
+  int dep_fused = 1;
+  float *dep_part0 = nullptr, *dep_part1 = nullptr;
+  unsigned* dep_bar = nullptr;
   int nsplit = 1;
   int n_in_static = 0;
   // graph
@@ -184,23 +188,27 @@ int step_body(b200_lm* h) {
   const int kt = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
   const int ka = h->top_k < c.card ? h->top_k : c.card;
   B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, B, c.dep_q * dd, d, LIN_STORE, 0));
-  for (int k = 0; k < c.dep_q; ++k) {
-    const long long* prev = k == 0 ? h->text_token : h->audio_tokens + (long long)(k - 1) * B;
-    B200_LAUNCH(dep_input_kernel, ceil_div(B * dd, 256), 256, 0, st, h->din, (long long)c.dep_q * dd, k * dd,
-                h->dep_tables[k], prev, h->dx, B, dd);
-    for (auto& L : h->dlayers) {
-      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
-      B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0));
-      B200_LAUNCH(dep_attn_step_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dqkv, L.kc, L.vc, h->dao, B, dH, c.dep_q, k);
-      B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0));
-      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
-      B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF));
-      B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0));
+  if (h->depf) {
+    B200_TRY(tc::dep_fused_launch(h->depf, st));
+  } else {
+    for (int k = 0; k < c.dep_q; ++k) {
+      const long long* prev = k == 0 ? h->text_token : h->audio_tokens + (long long)(k - 1) * B;
+      B200_LAUNCH(dep_input_kernel, ceil_div(B * dd, 256), 256, 0, st, h->din, (long long)c.dep_q * dd, k * dd,
+                  h->dep_tables[k], prev, h->dx, B, dd);
+      for (auto& L : h->dlayers) {
+        B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
+        B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0));
+        B200_LAUNCH(dep_attn_step_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dqkv, L.kc, L.vc, h->dao, B, dH, c.dep_q, k);
+        B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0));
+        B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
+        B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF));
+        B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0));
+      }
+      bf16* logits = h->dep_logits + (long long)k * B * c.card;
+      B200_TRY(linear(h, h->dx, dd, h->dep_heads[k], logits, c.card, nullptr, 0, B, c.card, dd, LIN_STORE, 0));
+      B200_TRY(sample(h, logits, c.card, h->noise + kt + (long long)k * ka, h->audio_tokens + (long long)k * B, h->temp,
+                      h->top_k));
     }
-    bf16* logits = h->dep_logits + (long long)k * B * c.card;
-    B200_TRY(linear(h, h->dx, dd, h->dep_heads[k], logits, c.card, nullptr, 0, B, c.card, dd, LIN_STORE, 0));
-    B200_TRY(sample(h, logits, c.card, h->noise + kt + (long long)k * ka, h->audio_tokens + (long long)k * B, h->temp,
-                    h->top_k));
   }
   B200_LAUNCH(advance_pos_kernel, ceil_div(B, 128), 128, 0, st, h->pos, h->exec_mask, B);
   B200_LAUNCH(lm_finish_kernel, ceil_div(B, 128), 128, 0, st, ring(h), h->text_token, h->audio_tokens, h->out_tokens, B);
@@ -249,6 +257,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
     if (v >= 1 && v <= 3) h->gemm_impl = v;
   }
   if (const char* e = getenv("B200_PDL")) h->pdl = atoi(e) != 0;
+  if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e) != 0;
   *out = h;
   return B200_OK;
 }
@@ -349,6 +358,7 @@ int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_te
   if (h->batch > 0 && (top_k != h->top_k || top_k_text != h->top_k_text))
     B200_FAIL(B200_ERR_STATE, "lm_set_sampling: top_k cannot change while streaming");
   h->use_sampling = use_sampling; h->temp = temp; h->temp_text = temp_text; h->top_k = top_k; h->top_k_text = top_k_text;
+  tc::dep_fused_set_sampling(h->depf, use_sampling, temp, top_k);
   drop_graph(h);
   return B200_OK;
 }
@@ -433,6 +443,35 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_CUDA(cudaMallocHost(&h->pin_in, (size_t)B * n_in_max * 8));
   B200_CUDA(cudaMallocHost(&h->pin_out, (size_t)B * (c.dep_q + 1) * 8));
   B200_CUDA(cudaMallocHost(&h->pin_noise, (size_t)B * noise_per_row(h) * 4));
+  if (h->dep_fused && h->gemm_impl == 3 && B <= 256 && dd <= 1024 && dd % 64 == 0) {
+    tc::DepFusedConfig fc;
+    memset(&fc, 0, sizeof(fc));
+    fc.B = B; fc.dd = dd; fc.H = c.depformer_num_heads; fc.F = c.depformer_ffn_hidden; fc.card = c.card; fc.dep_q = c.dep_q;
+    fc.L = c.depformer_num_layers;
+    std::vector<const void*> in_w, out_w, lin_in, lin_out, heads, tables, n1, n2;
+    std::vector<void*> kc, vc;
+    for (int k = 0; k < c.dep_q; ++k)
+      for (auto& L : h->dlayers) {
+        in_w.push_back(L.in_w[k]); out_w.push_back(L.out_w[k]); lin_in.push_back(L.lin_in[k]); lin_out.push_back(L.lin_out[k]);
+      }
+    for (int k = 0; k < c.dep_q; ++k) { heads.push_back(h->dep_heads[k]); tables.push_back(h->dep_tables[k]); }
+    for (auto& L : h->dlayers) { n1.push_back(L.n1); n2.push_back(L.n2); kc.push_back(L.kc); vc.push_back(L.vc); }
+    fc.in_w = in_w.data(); fc.out_w = out_w.data(); fc.lin_in = lin_in.data(); fc.lin_out = lin_out.data();
+    fc.heads = heads.data(); fc.tables = tables.data(); fc.n1 = n1.data(); fc.n2 = n2.data(); fc.kc = kc.data(); fc.vc = vc.data();
+    fc.din = h->din; fc.din_ld = (long long)c.dep_q * dd; fc.text_token = h->text_token;
+    fc.x = h->dx; fc.xn = h->dxn; fc.ao = h->dao; fc.hbuf = h->dh;
+    const size_t pf = tc::dep_fused_partial_floats(fc);
+    B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
+    B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
+    B200_TRY(A.alloc_t(&h->dep_bar, 1));
+    fc.part0 = h->dep_part0; fc.part1 = h->dep_part1; fc.bar = h->dep_bar;
+    fc.logits = h->dep_logits; fc.audio_tokens = h->audio_tokens;
+    fc.noise = h->noise; fc.noise_ld = noise_per_row(h);
+    fc.noise_off = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
+    fc.ka = h->top_k < c.card ? h->top_k : c.card;
+    fc.use_sampling = h->use_sampling; fc.top_k = h->top_k; fc.temp = h->temp;
+    B200_TRY(tc::dep_fused_create(fc, &h->depf));
+  }
   // streaming-state snapshot (lm.py:527-542 _LMGenState + the temporal transformer's ring caches)
   A.mark_state(h->exec_mask, B);
   A.mark_state(h->cache, (size_t)B * h->Kc * h->CT * 8);
@@ -482,6 +521,8 @@ int b200_lm_streaming_end(b200_lm* h) {
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->plans.clear();
+  tc::dep_fused_destroy(h->depf);
+  h->depf = nullptr;
   h->state.free_all();
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);

@@ -648,19 +648,16 @@ static __device__ float block_reduce(float v, bool is_max, float* red) {
   return t;
 }
 
-static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf16* __restrict__ logits_all, long long ld,
-                                                                const float* __restrict__ noise, long long noise_ld,
-                                                                long long* __restrict__ out, int card, int use_sampling,
-                                                                float temp, int top_k) {
-  pdl_trigger();
+// One row per call; every thread of a SAMPLE_THREADS-wide CTA must call it (block-wide barriers inside).
+static __device__ void sample_row(const bf16* __restrict__ logits, const float* __restrict__ noise, long long* __restrict__ out,
+                                  int card, int use_sampling, float temp, int top_k) {
   __shared__ float red[SAMPLE_THREADS / 32];
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_remaining, s_count;
   __shared__ unsigned sel[SAMPLE_MAX_K];
   __shared__ float s_best[SAMPLE_THREADS / 32];
   __shared__ int s_brank[SAMPLE_THREADS / 32];
-  const int row = blockIdx.x, tid = threadIdx.x;
-  const bf16* logits = logits_all + (long long)row * ld;
+  const int tid = threadIdx.x;
 
   if (!(use_sampling && temp > 0.f)) {        // greedy: argmax, first maximum (sampling.py:102-103)
     unsigned best = 0;
@@ -671,7 +668,7 @@ static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf1
     if (tid == 0) {
       unsigned bb = 0;
       for (int w = 0; w < SAMPLE_THREADS / 32; ++w) bb = max(bb, hist[w]);
-      out[row] = 0xFFFFu - (bb & 0xFFFFu);
+      *out = 0xFFFFu - (bb & 0xFFFFu);
     }
     return;
   }
@@ -743,7 +740,7 @@ static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf1
   for (int j = tid; j < k; j += SAMPLE_THREADS) {
     const int idx = 0xFFFF - (int)(sel[j] & 0xFFFFu);
     const float p = expf(bf2f(logits[idx]) / temp - mx) / sum;
-    const float s = p / noise[(long long)row * noise_ld + j];
+    const float s = p / noise[j];
     if (s > best || (s == best && j < brank)) { best = s; brank = j; }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -757,8 +754,17 @@ static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf1
     for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
       if (s_best[w] > best || (s_best[w] == best && s_brank[w] < brank)) { best = s_best[w]; brank = s_brank[w]; }
     if (brank == 0x7fffffff) brank = 0;
-    out[row] = 0xFFFF - (int)(sel[brank] & 0xFFFFu);
+    *out = 0xFFFF - (int)(sel[brank] & 0xFFFFu);
   }
+}
+
+static __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const bf16* __restrict__ logits_all, long long ld,
+                                                                const float* __restrict__ noise, long long noise_ld,
+                                                                long long* __restrict__ out, int card, int use_sampling,
+                                                                float temp, int top_k) {
+  pdl_trigger();
+  const int row = blockIdx.x;
+  sample_row(logits_all + (long long)row * ld, noise + (long long)row * noise_ld, out + row, card, use_sampling, temp, top_k);
 }
 
 }  // namespace lm
