@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 2-4 through the reference-shaped API, one JSON object per line.
+
+    python tools/configs.py --config 2              # Mimi streaming encode+decode, B = 1 .. 256
+    python tools/configs.py --config 3              # Moshi 7B LMGen.step, B = 1: p50/p90 latency, xRT (fill 200 and full ring)
+    python tools/configs.py --config 4 [--sessions N]   # one GPU's shard of the 512-session config, all rows / 25 % masked
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import statistics
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+PEAK = 6576.1
+pk = ROOT / "MEASURED_PEAKS.json"
+if pk.exists():
+    PEAK = float(json.loads(pk.read_text())["hbm_gbs"])
+
+
+def config2(batches):
+    from moshi_b200.models import loaders
+    mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
+    g = torch.Generator().manual_seed(4242)
+    for B in batches:
+        pcm = (0.1 * torch.randn(B, 1, 1920, generator=g)).cuda()
+        with mimi.streaming(B), torch.no_grad():
+            codes = None
+            for _ in range(255):                       # >= 250 warm-up frames: both transformer KV rings full
+                codes = mimi.encode(pcm)
+                mimi.decode(codes)
+            torch.cuda.synchronize()
+            n = 100
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                codes = mimi.encode(pcm)
+                mimi.decode(codes)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            alg = mimi.algorithmic_bytes()
+        print(json.dumps({"config": 2, "what": "Mimi streaming encode+decode, 8 codebooks, rings full", "B": B,
+                          "ms_per_frame_pair": round(ms, 4), "frames_per_s": round(B * 1e3 / ms, 1),
+                          "algorithmic_GBps": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / PEAK, 4),
+                          "fp32_TFLOPs": round(B * 0.9 / ms, 2)}), flush=True)
+
+
+def _lm():
+    from moshi_b200.config import MOSHI_7B
+    from moshi_b200.models import loaders
+    return loaders.get_moshi_lm(None, MOSHI_7B.to_reference_kwargs(), device="cuda", synth_device="cuda"), MOSHI_7B
+
+
+def config3():
+    from moshi_b200.models import LMGen
+    lm, cfg = _lm()
+    g = torch.Generator().manual_seed(4242)
+    codes = torch.randint(0, 2048, (1, 8, 1), generator=g).cuda()
+    for fill in (200, cfg.context):
+        gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7, top_k=250, top_k_text=25)
+        out_host = torch.empty(1, 9, 1, dtype=torch.int64).pin_memory()
+        with gen.streaming(1), torch.no_grad():
+            gen.assume_fill(fill)
+            for _ in range(20):
+                gen.step(codes)
+            torch.cuda.synchronize()
+            dev, wall = [], []
+            for _ in range(200):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                o = gen.step(codes)
+                e1.record()
+                out_host.copy_(o, non_blocking=True)
+                torch.cuda.synchronize()
+                wall.append((time.perf_counter() - t0) * 1e3)
+                dev.append(e0.elapsed_time(e1))
+            alg = gen.algorithmic_bytes(fill)
+        q = lambda v, p: sorted(v)[int(p * (len(v) - 1))]
+        p50 = q(dev, 0.5)
+        print(json.dumps({"config": 3, "what": "Moshi 7B bf16 LMGen.step, B=1", "kv_fill": fill,
+                          "p50_ms_device": round(p50, 3), "p90_ms_device": round(q(dev, 0.9), 3),
+                          "p50_ms_wall_incl_d2h": round(q(wall, 0.5), 3), "p90_ms_wall_incl_d2h": round(q(wall, 0.9), 3),
+                          "xRT": round(80.0 / p50, 1), "algorithmic_GBps": round(alg / p50 / 1e6, 1),
+                          "frac_of_hbm_peak": round(alg / p50 / 1e6 / PEAK, 3)}), flush=True)
+
+
+def config4(sessions: int):
+    from moshi_b200.models import LMGen, loaders
+    lm, cfg = _lm()
+    mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
+    free, _ = torch.cuda.mem_get_info()
+    cap = int((free - 6e9) // (524288 * cfg.context + 40e6))
+    B = min(sessions or cap, cap)
+    g = torch.Generator().manual_seed(4242)
+    pcm = (0.1 * torch.randn(B, 1, 1920, generator=g)).cuda()
+    gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
+    with mimi.streaming(B), gen.streaming(B), torch.no_grad():
+        gen.assume_fill(cfg.context)
+        for masked in (0.0, 0.25):
+            m = torch.ones(B, dtype=torch.bool)
+            m[: int(B * masked)] = False
+            mimi.set_exec_mask(m)
+            gen.set_exec_mask(m)
+            times = []
+            for i in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                codes = mimi.encode(pcm)
+                toks = gen.step(codes)
+                audio = toks[:, 1:].clamp(min=0) if toks is not None else torch.zeros(B, 8, 1, dtype=torch.int64, device="cuda")
+                mimi.decode(audio)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    times.append(e0.elapsed_time(e1))
+            ms = statistics.mean(times)
+            print(json.dumps({"config": 4, "what": "one GPU's shard of the 512-session config (512 sessions need >= 5 GPUs at "
+                              "full context: 1.573 GB of bf16 KV per session)", "sessions_on_this_gpu": B,
+                              "max_admissible_sessions_per_gpu": cap, "rows_masked": masked, "kv_fill": cfg.context,
+                              "ms_per_step": round(ms, 2), "p_max_ms": round(max(times), 2), "real_time": ms <= 80.0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True)
+    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256")
+    ap.add_argument("--sessions", type=int, default=0)
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    if args.config == 2:
+        config2([int(v) for v in args.batches.split(",")])
+    elif args.config == 3:
+        config3()
+    elif args.config == 4:
+        config4(args.sessions)
+
+
+if __name__ == "__main__":
+    main()
