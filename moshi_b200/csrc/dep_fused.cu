@@ -143,20 +143,21 @@ struct DepParams {
 
 namespace {
 
-struct Pipe { int s; uint32_t ph; int acc; uint32_t acc_bits; };     // per-role pipeline cursor, carried across phases
+struct Pipe { int s; uint32_t ph; int acc; uint32_t acc_bits; int pre; };   // per-role pipeline cursor, carried across phases
+// (pre: producer only — stages of the upcoming GEMM phase whose weight copy is already in flight)
 
+// Grid barrier: one release-reduction per CTA and acquire polling by one thread (all CTAs are co-resident).
+// The CTA's own writes are ordered before the reduction by __syncthreads (cumulativity of the gpu-scope release).
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     epoch += 1;
     const unsigned target = epoch * gridDim.x;
-    atomicAdd(bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned spins = 0;
     while (ld_acquire(bar) < target) {
       if (++spins > (1u << 24)) __trap();
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -295,8 +296,8 @@ __device__ void sample_phase(const DepParams& p, int S, int k) {
 }
 
 // One GEMM phase: units u = blockIdx.x, += gridDim.x; unit = (tile, split); partial [M x 128] -> part[split][m][tile*128 + row]
-__device__ void gemm_phase(const DepParams& p, const Gemm& g, const CUtensorMap* xmap, uint32_t base, uint32_t full0, uint32_t empty0,
-                           uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, Pipe& pipe) {
+__device__ void gemm_phase(const DepParams& p, const Gemm& g, const Gemm* next, const CUtensorMap* xmap, uint32_t base, uint32_t full0,
+                           uint32_t empty0, uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, Pipe& pipe) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = g.n_tiles * g.S;
   const uint32_t a_bytes = (uint32_t)g.A * TILE_BYTES;
@@ -304,17 +305,39 @@ __device__ void gemm_phase(const DepParams& p, const Gemm& g, const CUtensorMap*
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("fence.proxy.async;" ::: "memory");        // activations were written with generic stores by other CTAs
+      int item = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int tile = u / g.S, sp = u - tile * g.S;
         const int kb0 = sp * g.kbps, kb1 = min(g.num_kb, kb0 + g.kbps);
         const uint8_t* src = g.wt + ((size_t)tile * g.num_kb + kb0) * a_bytes;
-        for (int kb = kb0; kb < kb1; ++kb, src += a_bytes) {
-          mbar_wait(empty0 + 8 * pipe.s, pipe.ph ^ 1u);
+        for (int kb = kb0; kb < kb1; ++kb, src += a_bytes, ++item) {
           const uint32_t sa = base + (uint32_t)pipe.s * p.stage_bytes;
-          mbar_expect_tx(full0 + 8 * pipe.s, a_bytes + x_bytes);
-          bulk_load(sa, src, a_bytes, full0 + 8 * pipe.s);
+          if (item >= pipe.pre) {                              // (else: requested at the end of the previous GEMM phase)
+            mbar_wait(empty0 + 8 * pipe.s, pipe.ph ^ 1u);
+            mbar_expect_tx(full0 + 8 * pipe.s, a_bytes + x_bytes);
+            bulk_load(sa, src, a_bytes, full0 + 8 * pipe.s);
+          }
           tma_load_2d(sa + 2 * TILE_BYTES, xmap, full0 + 8 * pipe.s, kb * BLOCK_K, 0);
           if (++pipe.s == p.stages) { pipe.s = 0; pipe.ph ^= 1u; }
+        }
+      }
+      // Weights never depend on the phases in between: request the next GEMM phase's first tiles now, so its HBM
+      // latency (and, at large batch, most of its stream) overlaps the SIMT phase and the two grid barriers ahead.
+      pipe.pre = 0;
+      if (next != nullptr) {
+        const uint32_t nb = (uint32_t)next->A * TILE_BYTES;
+        int s2 = pipe.s; uint32_t ph2 = pipe.ph;
+        const int nunits = next->n_tiles * next->S;
+        for (int u = blockIdx.x; u < nunits && pipe.pre < p.stages; u += gridDim.x) {
+          const int tile = u / next->S, sp = u - tile * next->S;
+          const int kb0 = sp * next->kbps, kb1 = min(next->num_kb, kb0 + next->kbps);
+          const uint8_t* src = next->wt + ((size_t)tile * next->num_kb + kb0) * nb;
+          for (int kb = kb0; kb < kb1 && pipe.pre < p.stages; ++kb, src += nb, ++pipe.pre) {
+            mbar_wait(empty0 + 8 * s2, ph2 ^ 1u);
+            mbar_expect_tx(full0 + 8 * s2, nb + x_bytes);
+            bulk_load(base + (uint32_t)s2 * p.stage_bytes, src, nb, full0 + 8 * s2);
+            if (++s2 == p.stages) { s2 = 0; ph2 ^= 1u; }
+          }
         }
       }
     }
@@ -419,40 +442,54 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tptr_generic;
 
-  Pipe pipe{0, 0u, 0, 0u};
+  Pipe pipe{0, 0u, 0, 0u, 0};
   unsigned epoch = 0;
+  // GEMM phases in execution order: per sub-step k, per layer l: in_proj, out_proj, linear_in, linear_out; then the head
+  auto gemm_at = [&](int k, int l, int which) -> Gemm {
+    Gemm g;
+    if (which == 4) { g = p.g_head; g.wt = p.heads[k]; return g; }
+    const DepLayerW w = p.w[k * p.L + l];
+    if (which == 0) { g = p.g_in; g.wt = w.in_w; }
+    else if (which == 1) { g = p.g_out; g.wt = w.out_w; }
+    else if (which == 2) { g = p.g_lin_in; g.wt = w.lin_in; }
+    else { g = p.g_lin_out; g.wt = w.lin_out; }
+    return g;
+  };
+  Gemm cur = gemm_at(0, 0, 0);
   for (int k = 0; k < p.dep_q; ++k) {
     input_rows(p, k);
     row_phase(p, 0, nullptr, 0, false, p.n1[0], red);
     grid_sync(p.bar, epoch);
     for (int l = 0; l < p.L; ++l) {
-      const DepLayerW w = p.w[k * p.L + l];
-      Gemm g = p.g_in; g.wt = w.in_w;
-      gemm_phase(p, g, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
+      Gemm nxt = gemm_at(k, l, 1);
+      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      attn_phase(p, g.S, l, k);
+      attn_phase(p, cur.S, l, k);
       grid_sync(p.bar, epoch);
-      g = p.g_out; g.wt = w.out_w;
-      gemm_phase(p, g, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
+      cur = nxt; nxt = gemm_at(k, l, 2);
+      gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      row_phase(p, g.S, p.part0, g.N, true, p.n2[l], red);
+      row_phase(p, cur.S, p.part0, cur.N, true, p.n2[l], red);
       grid_sync(p.bar, epoch);
-      g = p.g_lin_in; g.wt = w.lin_in;
-      gemm_phase(p, g, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
+      cur = nxt; nxt = gemm_at(k, l, 3);
+      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      gate_phase(p, g.S);
+      gate_phase(p, cur.S);
       grid_sync(p.bar, epoch);
-      g = p.g_lin_out; g.wt = w.lin_out;
-      gemm_phase(p, g, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
+      cur = nxt; nxt = l + 1 < p.L ? gemm_at(k, l + 1, 0) : gemm_at(k, 0, 4);
+      gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
       // depformer_norms is Identity (lm.py:197-198): after the last layer the head reads x itself
-      row_phase(p, g.S, p.part0, g.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
+      row_phase(p, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
       grid_sync(p.bar, epoch);
+      cur = nxt;
     }
-    Gemm g = p.g_head; g.wt = p.heads[k];
-    gemm_phase(p, g, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
+    const bool last = k + 1 == p.dep_q;
+    Gemm nxt = last ? cur : gemm_at(k + 1, 0, 0);
+    gemm_phase(p, cur, last ? nullptr : &nxt, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
-    sample_phase(p, g.S, k);       // the next sub-step's input rows are the same rows of the same CTA: no barrier needed
+    sample_phase(p, cur.S, k);       // the next sub-step's input rows are the same rows of the same CTA: no barrier needed
+    cur = nxt;
   }
   tc_fence_before();
   __syncthreads();
