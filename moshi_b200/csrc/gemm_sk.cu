@@ -393,6 +393,194 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster split-K ("ck") for the few-tile GEMMs at more than 32 sessions (out_proj / linear_out: 32 row tiles).
+// A cluster of CS CTAs owns one 128-row tile; rank r streams k-blocks [r*kb_per, (r+1)*kb_per) into its own TMEM
+// accumulator.  The partials are then reduce-scattered over distributed shared memory: rank q is sent columns
+// [q*Wc, (q+1)*Wc) of everybody's accumulator (st.shared::cluster into its receive buffer), one cluster barrier,
+// and every rank sums its column block in rank order (deterministic) and runs the epilogue for it.  No global
+// workspace, no atomics; CS x more SMs pull on the weights and the epilogue is spread over the cluster too.
+// ---------------------------------------------------------------------------------------------
+struct CkParams {
+  int M, N, K, Mpad, CS, Wc, kb_per, num_kb, stages;
+  const uint8_t* wt;
+  __nv_bfloat16* y; long long ldy;
+  const __nv_bfloat16* res; long long ldr;
+  uint32_t tmem_cols, stage_bytes;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int EPI>      // EPI_STORE or EPI_RESADD
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull = bars + 16 * MAX_STAGES;
+  const uint32_t tptr = tfull + 8;
+  uint32_t* tptr_generic = reinterpret_cast<uint32_t*>(smem_raw + (tptr - raw));
+  // receive buffer [CS][128 rows][Wc + 4] fp32 (rows padded against bank conflicts), after the barrier block
+  const int ldw = p.Wc + 4;
+  const uint32_t recv = (tptr + 8 + 15u) & ~15u;
+  float* recv_generic = reinterpret_cast<float*>(smem_raw + (recv - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.CS, me = blockIdx.x - tile * p.CS;
+  const int kb0 = me * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr_generic;
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights first (they do not depend on the preceding kernel), activations after the dependency wait
+      const uint8_t* src = p.wt + ((size_t)tile * p.num_kb + kb0) * TILE_BYTES;
+      const int n_items = kb1 - kb0;
+      const int pre = n_items < p.stages ? n_items : p.stages;
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(full0 + 8 * i, p.stage_bytes);
+        bulk_load(base + (uint32_t)i * p.stage_bytes, src + (size_t)i * TILE_BYTES, TILE_BYTES, full0 + 8 * i);
+      }
+      pdl_wait();
+      int s = 0; uint32_t ph = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+        if (i >= pre) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
+          bulk_load(sa, src + (size_t)i * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
+        }
+        tma_load_2d(sa + TILE_BYTES, &tmap_x, full0 + 8 * s, (kb0 + i) * BLOCK_K, 0);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
+        const uint32_t sb = sa + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, (kb == kb0 && k == 0) ? 0u : 1u);
+        umma_commit(empty0 + 8 * s);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  }
+  float own[64];                               // this rank's column block of its own accumulator (Wc <= 64)
+  const int q4 = warp & 3;
+  const int row = q4 * 32 + lane;
+  if (warp >= 2) {
+    pdl_wait();
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    for (int q = 0; q < p.CS; ++q) {
+      const uint32_t dst = map_to_rank(recv + (uint32_t)((me * BLOCK_ROWS + row) * ldw) * 4u, (uint32_t)q);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        if (c0 < p.Wc) {
+          uint32_t r[8];
+          tmem_ld8(lane_addr + (uint32_t)(q * p.Wc + c0), r);
+          tmem_ld_wait();
+          if (kb1 <= kb0) {                    // a rank without k-blocks contributes zeros
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = 0u;
+          }
+          if (q == me) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) own[c0 + j] = __uint_as_float(r[j]);
+          } else {
+            st_cluster_v4(dst + (uint32_t)c0 * 4u, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            st_cluster_v4(dst + (uint32_t)(c0 + 4) * 4u, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();                          // every partial has landed in its owner's receive buffer
+  if (warp >= 2) {
+    const int n = tile * BLOCK_ROWS + row;
+    const bool n_ok = n < p.N;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      if (c0 < p.Wc) {
+        float rv[8];
+        if (EPI == EPI_RESADD) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int m = me * p.Wc + c0 + j;
+            rv[j] = (m < p.M && n_ok) ? __bfloat162float(p.res[(long long)m * p.ldr + n]) : 0.f;
+          }
+        }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int r = 0; r < p.CS; ++r) {       // rank order: the sum does not depend on which rank does it
+          if (r == me) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += own[c0 + j];
+          } else {
+            const float4 a = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0);
+            const float4 b = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0 + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = me * p.Wc + c0 + j;
+          if (m < p.M && n_ok) {
+            const float v = EPI == EPI_RESADD ? rv[j] + bf16_round(acc[j]) : acc[j];
+            p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 // load-time repack: w [rows][K] row-major -> tiles [n_tile][kb][A][128 x 64] in the SWIZZLE_128B layout
 // (16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)); rows/cols beyond the tensor are zero.
 __global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ w, uint4* __restrict__ out, int rows, int K, int n_tiles,
@@ -435,6 +623,8 @@ int init_once() {
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_RESADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_ck_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    B200_CUDA(cudaFuncSetAttribute(gemm_ck_kernel<EPI_RESADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -475,6 +665,26 @@ bool sk_supported(int M, int N, int K, int epi) {
   return M >= 1 && M <= 256 && K >= 8 && K % 8 == 0;
 }
 
+// 2-D tensor map of the activations x [M][K] (row stride ldx) with a [box_rows x 64] SWIZZLE_128B box
+static int x_map(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, int M, int K, int box_rows, const CUtensorMap** out) {
+  PlanKey key{x, ldx, M, K, box_rows};
+  auto it = cache.maps.find(key);
+  if (it == cache.maps.end()) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) M=%d K=%d ld=%lld", (int)r, M, K, ldx);
+    it = cache.maps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return B200_OK;
+}
+
 // y = epi(x . W^T) with W given as packed tiles.  ws / counters: sk_workspace_bytes(M) and >= 1024 ints, zeroed once.
 int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y,
               long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
@@ -483,6 +693,53 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tiles)) & 15)
     B200_FAIL(B200_ERR_SHAPE, "sk GEMM: operands must be 16-byte aligned");
   B200_TRY(init_once());
+  // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
+  if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {
+    const int n_tiles = (N + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    int cs = 1;
+    while (cs < 8 && n_tiles * cs * 2 <= g_sms && num_kb / (cs * 2) >= 4) cs *= 2;
+    if (tune.cluster > 0) cs = tune.cluster;
+    if (cs > 1) {
+      CkParams p;
+      p.M = M; p.N = N; p.K = K; p.CS = cs;
+      const int quantum = 8 * cs < 16 ? 16 : 8 * cs;       // UMMA N is a multiple of 16; every rank owns whole 8-column groups
+      p.Mpad = ((M + quantum - 1) / quantum) * quantum;
+      p.Wc = p.Mpad / cs;
+      if (p.Mpad <= 256 && p.Wc <= 64) {
+        p.num_kb = num_kb; p.kb_per = (num_kb + cs - 1) / cs;
+        p.wt = static_cast<const uint8_t*>(w_tiles);
+        p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
+        p.stage_bytes = (uint32_t)(TILE_BYTES + p.Mpad * BLOCK_K * 2);
+        const size_t recv_bytes = (size_t)cs * BLOCK_ROWS * (p.Wc + 4) * 4;
+        int stages = (int)((200 * 1024 - recv_bytes) / p.stage_bytes);
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        if (stages > p.kb_per) stages = p.kb_per;
+        if (stages >= 2) {
+          p.stages = stages;
+          uint32_t pow2 = 32;
+          while (pow2 < (uint32_t)p.Mpad) pow2 <<= 1;
+          p.tmem_cols = pow2;
+          const CUtensorMap* mx = nullptr;
+          B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, &mx));
+          const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64 + recv_bytes + 64;
+          cudaLaunchConfig_t cfg;
+          memset(&cfg, 0, sizeof(cfg));
+          cfg.gridDim = dim3(n_tiles * cs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+          cudaLaunchAttribute attr[2];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr; cfg.numAttrs = tune.pdl ? 2 : 1;
+          cudaError_t le = epi == EPI_STORE ? cudaLaunchKernelEx(&cfg, gemm_ck_kernel<EPI_STORE>, *mx, p)
+                                            : cudaLaunchKernelEx(&cfg, gemm_ck_kernel<EPI_RESADD>, *mx, p);
+          if (le != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "gemm_ck launch failed: %s", cudaGetErrorString(le));
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          return check_launch("gemm_ck");
+        }
+      }
+    }
+  }
   SkParams p;
   p.M = M; p.N = N; p.K = K; p.gate_rows = gate_rows;
   p.out_rows = epi == EPI_GATE ? gate_rows : N;
@@ -527,23 +784,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.tmem_cols = pow2;
   p.stream_only = tune.stream_only;
   const CUtensorMap* mx = nullptr;
-  {
-    PlanKey key{x, ldx, M, K, p.Mpad};
-    auto it = cache.maps.find(key);
-    if (it == cache.maps.end()) {
-      CUtensorMap m;
-      cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
-      cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
-      cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.Mpad};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) M=%d K=%d ld=%lld", (int)r, M, K, ldx);
-      it = cache.maps.emplace(key, m).first;
-    }
-    mx = &it->second;
-  }
+  B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, &mx));
   const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

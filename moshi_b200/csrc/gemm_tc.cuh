@@ -45,6 +45,8 @@ struct SkTuning {
   int stream_only = 0;   // diagnostics: run the copy pipeline without MMAs / stores
   int no_split = 0;      // never cut a tile across CTAs (whole tiles only)
   int force_split = 0;   // tests: cut tiles even where the default policy keeps them whole
+  int no_cluster = 0;    // never use the cluster split-K kernel
+  int cluster = 0;       // force a cluster size (tests)
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
 };
 int sk_num_sms();

@@ -46,8 +46,9 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
     B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
   }
   tc::SkTuning t;
-  t.grid = grid; t.smem_budget = smem_budget; t.stream_only = stream_only;
-  t.force_split = grid != 0;     // an explicit grid (parity tests) exercises the tile-cutting path at every M
+  // grid > 0: stream-K with that many CTAs; grid < 0: cluster split-K with |grid| CTAs per tile; 0: the LM's own choice
+  t.grid = grid > 0 ? grid : 0; t.cluster = grid < 0 ? -grid : 0; t.smem_budget = smem_budget; t.stream_only = stream_only;
+  t.force_split = grid > 0;     // an explicit grid (parity tests) exercises the tile-cutting path at every M
   const int out_cols = epi == 2 ? gate_rows : N;
   return tc::sk_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev),
                        out_cols, static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, ws, counters, t,

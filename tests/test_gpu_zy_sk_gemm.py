@@ -104,3 +104,29 @@ def test_sk_gated_silu(M, H, K):
         print(stats(f"sk gate {M}x{H}x{K} grid={grid}", y, want))
         assert not torch.isnan(y.float()).any()
         torch.testing.assert_close(y.float(), want, rtol=2e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(33, 4096, 4096, RESADD), (96, 4096, 11264, RESADD), (130, 1024, 1024, STORE),
+                                        (256, 2048, 1024, STORE), (96, 3072, 1024, STORE), (40, 200, 520, RESADD)])
+def test_cluster_split_k(M, N, K, epi):
+    """Cluster split-K (one 128-row tile per cluster, k-range per rank, DSMEM reduce-scatter): every cluster size gives
+    the same bits as the whole-tile schedule up to fp32 summation order, and repeated launches are bit-identical."""
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M * 3 + N)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    res = torch.randn(M, N, generator=g).bfloat16().cuda() if epi == RESADD else None
+    wt = _pack(lib, w, N, K, epi, 0)
+    acc = (x.float() @ w.float().t())
+    want = (res.float() + acc.bfloat16().float()) if epi == RESADD else acc
+    for cs in (2, 4, 8):
+        if (K + 63) // 64 < cs:
+            continue
+        y = _run(lib, x, wt, res, M, N, K, epi, 0, grid=-cs)
+        print(stats(f"ck {M}x{N}x{K} epi={epi} cluster={cs}", y, want))
+        assert not torch.isnan(y.float()).any()
+        torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=3e-2)
+        assert torch.equal(y, _run(lib, x, wt, res, M, N, K, epi, 0, grid=-cs))
+    auto = _run(lib, x, wt, res, M, N, K, epi, 0, grid=0)          # what the LM launches for this shape
+    torch.testing.assert_close(auto.float(), want, rtol=1e-2, atol=3e-2)
