@@ -414,6 +414,9 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     a.in_off = l.D0;
     a.M = l.cout * l.stride; a.N = B * (l.t_in + 1); a.Kd = 2 * l.cin; a.stride = l.stride; a.T = l.t_in;
     a.partial = l.state; a.scratch = l.scratch;
+    // consecutive GEMM rows of one channel are consecutive output samples: move them as float4 / float2 when S allows
+    const bool al = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && yb % 4 == 0 && yc % 4 == 0;
+    a.vec_y = (l.stride % 4 == 0 && al) ? 4 : (l.stride % 2 == 0 && al) ? 2 : 1;
     return launch_gemm<G_CONVTR>(h, a);
   }
   if (l.kind == 0) {

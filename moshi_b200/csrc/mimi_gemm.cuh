@@ -91,6 +91,54 @@ static __global__ void gemm_splitk_reduce_kernel(const GemmArgs p) {
   gemm_store_one<KIND>(p, m, n, v);
 }
 
+// ConvTranspose epilogue for V consecutive GEMM rows m = co*S + r .. (one channel, V consecutive output samples)
+template <int V>
+__device__ __forceinline__ void convtr_store(const GemmArgs& p, int m, int b, int t, const float* accv) {
+  if (m >= p.M) return;
+  const int S = p.stride;
+  const int co = m / S, r = m - co * S;
+  const long long sidx = ((long long)b * (p.M / S) + co) * S + r;
+  float v[V];
+  if (t == p.T) {                                            // tail of y minus bias: the next frame's carry (conv.py:352-356)
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = accv[i];
+    if (V == 4) *reinterpret_cast<float4*>(p.scratch + sidx) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (V == 2) *reinterpret_cast<float2*>(p.scratch + sidx) = make_float2(v[0], v[1]);
+    else p.scratch[sidx] = v[0];
+    return;
+  }
+  const float bias = p.bias ? p.bias[co] : 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = accv[i] + bias;
+  if (t == 0) {                                              // y[..., :PT] += partial (conv.py:351)
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] += p.partial[sidx + i];
+  }
+  const long long to = (long long)t * S + r;
+  if (p.y) {
+    float* y = p.y + b * p.yb + co * p.yc + to * p.yt;
+    if (V == 4 && p.yt == 1) *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (V == 2 && p.yt == 1) *reinterpret_cast<float2*>(y) = make_float2(v[0], v[1]);
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) y[i * p.yt] = v[i];
+    }
+  }
+  if (p.a) {
+    if (p.a_elu) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = elu1(v[i]);
+    }
+    float* a = p.a + b * p.ab + co * p.ac + to * p.at;
+    if (V == 4 && p.at == 1) *reinterpret_cast<float4*>(a) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (V == 2 && p.at == 1) *reinterpret_cast<float2*>(a) = make_float2(v[0], v[1]);
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i * p.at] = v[i];
+    }
+  }
+}
+
 template <int BM, int BN, int KIND>
 static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mimi_gemm_kernel(const GemmArgs p) {
   constexpr int TM = BM / 16, TN = BN / 16;          // micro-tile, in groups of 4
@@ -329,7 +377,6 @@ static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mim
         }
       }
     } else {   // G_CONVTR: m = co*S + r, n = (b, t), t in [0, T]; t == T is the new carry
-      const int S = p.stride;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int n = nb + jj;
@@ -337,19 +384,17 @@ static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mim
         const int b = n / (p.T + 1), t = n - b * (p.T + 1);
 #pragma unroll
         for (int gi = 0; gi < GM; ++gi) {
+          const int mb = m0 + ty * 4 + gi * (BM / GM);
+          if (mb >= p.M) continue;
+          float v[4];
 #pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const int m = m0 + ty * 4 + gi * (BM / GM) + ii;
-            if (m >= p.M) continue;
-            const int co = m / S, r = m - co * S;
-            const float accv = acc[4 * gi + ii][4 * gj + jj];
-            const long long sidx = ((long long)b * (p.M / S) + co) * S + r;
-            if (t == p.T) { p.scratch[sidx] = accv; continue; }    // tail of y minus bias (conv.py:352-356)
-            float v = accv + (p.bias ? p.bias[co] : 0.f);
-            if (t == 0) v += p.partial[sidx];                        // y[..., :PT] += partial (conv.py:351)
-            const long long to = (long long)t * S + r;
-            if (p.y) p.y[b * p.yb + co * p.yc + to * p.yt] = v;
-            if (p.a) p.a[b * p.ab + co * p.ac + to * p.at] = p.a_elu ? elu1(v) : v;
+          for (int ii = 0; ii < 4; ++ii) v[ii] = acc[4 * gi + ii][4 * gj + jj];
+          // vec_y = how many consecutive m (= consecutive output samples of one channel) go out as one vector: S % vec_y == 0
+          if (p.vec_y == 4) convtr_store<4>(p, mb, b, t, v);
+          else if (p.vec_y == 2) { convtr_store<2>(p, mb, b, t, v); convtr_store<2>(p, mb + 2, b, t, v + 2); }
+          else {
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) convtr_store<1>(p, mb + ii, b, t, v + ii);
           }
         }
       }

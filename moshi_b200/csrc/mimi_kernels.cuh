@@ -597,10 +597,14 @@ static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs
   __syncthreads();
   for (int c = tid; c < a.Cout; c += blockDim.x) {
     float acc0 = 0.f, acc1 = 0.f;
-    if (a.levels[0] > 0)
+    if (a.levels[0] > 0) {
+#pragma unroll 8
       for (int d = 0; d < a.Dq; ++d) acc0 = fmaf(a.woT[0][(long long)d * a.Cout + c], sm[d], acc0);
-    if (a.levels[1] > 0)
+    }
+    if (a.levels[1] > 0) {
+#pragma unroll 8
       for (int d = 0; d < a.Dq; ++d) acc1 = fmaf(a.woT[1][(long long)d * a.Cout + c], sm[a.Dq + d], acc1);
+    }
     a.out[b * a.ob + c * a.oc + f * a.ot] = acc0 + acc1;
   }
 }
