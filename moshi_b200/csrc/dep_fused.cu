@@ -176,13 +176,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // rows handled by this CTA: m = blockIdx.x, blockIdx.x + gridDim.x, ...   (same mapping in every row phase, so a row's
 // sampled token is consumed by the CTA that produced it without a barrier)
 //   x_new = has_sum ? bf16(x + bf16(sum_s part[s][m][:])) : x (already written);  xn = rmsnorm(x_new, alpha)
-__device__ void row_phase(const DepParams& p, int S, const float* part, int N, bool has_sum, const bf16* alpha, float* red) {
-  const int dd = p.dd;
+template <int NV, class P>                                    // dd <= NV * THREADS
+__device__ void row_phase(const P& p, int dd, int S, const float* part, int N, bool has_sum, const bf16* alpha, float* red) {
   for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
-    float vals[4];                                            // dd <= 4 * THREADS (1024)
+    float vals[NV];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int j = threadIdx.x + i * THREADS;
       float v = 0.f;
       if (j < dd) {
@@ -201,7 +201,7 @@ __device__ void row_phase(const DepParams& p, int S, const float* part, int N, b
       const float tot = block_sum(ss, red);
       const float r = rsqrtf(1e-8f + tot / (float)dd);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const int j = threadIdx.x + i * THREADS;
         if (j < dd) p.xn[(long long)m * dd + j] = f2bf(vals[i] * (bf2f(alpha[j]) * r));
       }
@@ -266,7 +266,8 @@ __device__ void attn_phase(const DepParams& p, int S, int layer, int step) {
 }
 
 // h = bf16(bf16(silu(bf16 gate)) * bf16 value)   (gating.py:18-20)
-__device__ void gate_phase(const DepParams& p, int S) {
+template <class P>
+__device__ void gate_phase(const P& p, int S) {
   const long long total = (long long)p.B * p.F;
   for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * THREADS) {
     float g = 0.f, u = 0.f;
@@ -296,7 +297,8 @@ __device__ void sample_phase(const DepParams& p, int S, int k) {
 }
 
 // One GEMM phase: units u = blockIdx.x, += gridDim.x; unit = (tile, split); partial [M x 128] -> part[split][m][tile*128 + row]
-__device__ void gemm_phase(const DepParams& p, const Gemm& g, const Gemm* next, const CUtensorMap* xmap, uint32_t base, uint32_t full0,
+template <class P>
+__device__ void gemm_phase(const P& p, const Gemm& g, const Gemm* next, const CUtensorMap* xmap, uint32_t base, uint32_t full0,
                            uint32_t empty0, uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, Pipe& pipe) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = g.n_tiles * g.S;
@@ -458,7 +460,7 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
   Gemm cur = gemm_at(0, 0, 0);
   for (int k = 0; k < p.dep_q; ++k) {
     input_rows(p, k);
-    row_phase(p, 0, nullptr, 0, false, p.n1[0], red);
+    row_phase<4>(p, p.dd, 0, nullptr, 0, false, p.n1[0], red);
     grid_sync(p.bar, epoch);
     for (int l = 0; l < p.L; ++l) {
       Gemm nxt = gemm_at(k, l, 1);
@@ -469,7 +471,7 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
       cur = nxt; nxt = gemm_at(k, l, 2);
       gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      row_phase(p, cur.S, p.part0, cur.N, true, p.n2[l], red);
+      row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, p.n2[l], red);
       grid_sync(p.bar, epoch);
       cur = nxt; nxt = gemm_at(k, l, 3);
       gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
@@ -480,7 +482,7 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
       gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
       // depformer_norms is Identity (lm.py:197-198): after the last layer the head reads x itself
-      row_phase(p, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
+      row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
       grid_sync(p.bar, epoch);
       cur = nxt;
     }

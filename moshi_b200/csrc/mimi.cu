@@ -216,7 +216,9 @@ int get_f32(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, c
 
 int pack_conv(b200_mimi* h, ConvLayer& l) {
   const float* w = nullptr;
-  l.fast = !l.replicate && (l.cin % GK) == 0 && (l.kind == 0 ? l.cout % 4 == 0 : (l.cout * l.stride) % 4 == 0);
+  // ext-buffer path (mimi_gemm.cuh): GEMM-shaped layers, plus the Cout = 1 tail conv which reduces straight from ext
+  l.fast = !l.replicate && (l.cin % GK) == 0 &&
+           (l.kind == 0 ? (l.cout % 4 == 0 || (l.cout == 1 && l.stride == 1)) : (l.cout * l.stride) % 4 == 0);
   if (getenv("B200_MIMI_LEGACY")) l.fast = false;          // debug switch: first-generation kernels only
   if (l.kind == 0) {
     B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
@@ -393,6 +395,24 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
   float* act = nullptr; long long ab = 0, ac = 0; int a_elu = 0;
   if (next && next->fast) {
     act = next->ext + next->D0; ab = (long long)next->cin * next->E; ac = next->E; a_elu = next->elu_in;
+  }
+  if (l.fast && l.kind == 0 && l.cout == 1) {     // last decoder conv: memory-bound reduction over (ci, kw)
+    ConvCout1 q;
+    q.ext = l.ext; q.eb = (long long)l.cin * l.E; q.E = l.E; q.off = l.D0 - l.P;
+    q.wk = l.wk; q.bias = l.bias; q.y = y; q.yb = yb; q.yt = yt;
+    q.B = B; q.Cin = l.cin; q.K = l.k; q.dil = l.dil; q.T = l.t_out;
+    const long long n = (long long)B * l.t_out;
+    B200_LAUNCH(conv_cout1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)l.k * l.cin * 4, h->body, q);
+    return check_launch(l.key.c_str());
+  }
+  if (!l.fast && l.kind == 0 && l.cin == 1 && l.stride == 1 && l.k <= 8 && !l.first && !l.elu_in && !res && xc == 0 && yt == 1) {
+    ConvCin1 q;                                   // first encoder conv: one thread per sample makes all channels
+    q.x = x; q.xb = xb; q.xt = xt; q.st = l.state; q.P = l.P; q.w = l.w; q.bias = l.bias;
+    q.y = y; q.yb = yb; q.yc = yc; q.a = act; q.ab = ab; q.ac = ac; q.a_elu = a_elu;
+    q.B = B; q.Cout = l.cout; q.K = l.k; q.T = l.t_out;
+    const long long n = (long long)B * l.t_out;
+    B200_LAUNCH(conv_cin1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
+    return check_launch(l.key.c_str());
   }
   if (l.fast) {
     GemmArgs a;

@@ -402,6 +402,70 @@ static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mim
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two degenerate SEANet convolutions, which are memory-bound and do not fit a GEMM tile:
+//   conv_cin1_kernel  : first encoder conv (Cin = 1, K = 7): one thread per (b, t) produces all Cout channels
+//   conv_cout1_kernel : last decoder conv (Cout = 1, K = 3): one thread per (b, t) reduces over (ci, kw) from ext
+// ---------------------------------------------------------------------------------------------
+struct ConvCin1 {
+  const float* x; long long xb, xt;          // input [B][1][T]
+  const float* st; int P;                    // carried left context [B][P]
+  const float* w;                            // [Cout][K]
+  const float* bias;
+  float* y; long long yb, yc;                // raw [B][Cout][T]
+  float* a; long long ab, ac; int a_elu;     // activated copy for the consumer (may be null)
+  int B, Cout, K, T;
+};
+static __global__ void __launch_bounds__(256) conv_cin1_kernel(const ConvCin1 p) {
+  extern __shared__ float sw[];              // [Cout][K] then bias [Cout]
+  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[p.Cout * p.K + i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)p.B * p.T) return;
+  const int b = n / p.T, t = n - (long long)b * p.T;
+  float xin[8];                              // K <= 8
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = t + k;                     // index into cat(previous, x)
+    float v = 0.f;
+    if (k < p.K) v = j < p.P ? p.st[(long long)b * p.P + j] : p.x[b * p.xb + (long long)(j - p.P) * p.xt];
+    xin[k] = v;
+  }
+  for (int co = 0; co < p.Cout; ++co) {
+    float acc = sw[p.Cout * p.K + co];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < p.K) acc = fmaf(sw[co * p.K + k], xin[k], acc);
+    p.y[b * p.yb + co * p.yc + t] = acc;
+    if (p.a) p.a[b * p.ab + co * p.ac + t] = p.a_elu ? elu1(acc) : acc;
+  }
+}
+
+struct ConvCout1 {
+  const float* ext; long long eb; int E, off; // ext[b*eb + ci*E + off + t + kw*dil]  (activation already applied)
+  const float* wk;                            // [K*Cin] (tap-major)
+  const float* bias;
+  float* y; long long yb, yt;                 // [B][1][T] via strides
+  int B, Cin, K, dil, T;
+};
+static __global__ void __launch_bounds__(256) conv_cout1_kernel(const ConvCout1 p) {
+  extern __shared__ float sw[];               // [K*Cin]
+  for (int i = threadIdx.x; i < p.K * p.Cin; i += blockDim.x) sw[i] = p.wk[i];
+  __syncthreads();
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)p.B * p.T) return;
+  const int b = n / p.T, t = n - (long long)b * p.T;
+  const float* e = p.ext + b * p.eb + p.off + t;
+  float acc = p.bias ? p.bias[0] : 0.f;
+  for (int kw = 0; kw < p.K; ++kw) {
+    const float* ek = e + kw * p.dil;
+#pragma unroll 8
+    for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(sw[kw * p.Cin + ci], ek[(long long)ci * p.E], acc);
+  }
+  p.y[b * p.yb + (long long)t * p.yt] = acc;
+}
+
 // ext / xpad filler for layers whose producer is not one of the kernels above (PCM frame, transformer output):
 // dst[b*db + c*dc + t*dt] = act(src[b*sb + c*sc + t*st])
 static __global__ void fill_act_kernel(const float* __restrict__ src, long long sb, long long sc, long long st,
