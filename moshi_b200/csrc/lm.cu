@@ -37,6 +37,7 @@ struct b200_lm {
   float temp = 0.8f, temp_text = 0.7f;
   int gemm_impl = 3;                           // 3 = stream-K tcgen05 over packed tiles (default)
   int pdl = 1;                                 // programmatic dependent launch of the GEMMs (B200_PDL=0 disables)
+  int sk_smem = 0;                             // bytes of pipeline stages per GEMM CTA (B200_SK_SMEM_KB; 0 = 200 KB, one CTA per SM)
   float* sk_ws = nullptr;                      // stream-K partial-accumulator slots (L2-resident)
   int* sk_counters = nullptr;                  // per-tile arrival counters (zero between launches)
   // weights
@@ -55,8 +56,8 @@ struct b200_lm {
   // activations
   long long *in_codes = nullptr, *input_tokens = nullptr, *text_token = nullptr, *audio_tokens = nullptr, *out_tokens = nullptr;
   float* noise = nullptr;
-  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *q = nullptr, *ao = nullptr, *hbuf = nullptr, *tout = nullptr;
-  bf16 *text_logits = nullptr, *din = nullptr, *dx = nullptr, *dxn = nullptr, *dqkv = nullptr, *dq = nullptr, *dao = nullptr,
+  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hbuf = nullptr, *tout = nullptr;
+  bf16 *text_logits = nullptr, *din = nullptr, *dx = nullptr, *dxn = nullptr, *dqkv = nullptr, *dao = nullptr,
        *dh = nullptr, *dep_logits = nullptr;
   float* attn_part = nullptr;
   int* attn_counters = nullptr;                // split arrival counters [B*H]
@@ -109,6 +110,7 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
   if (impl == 3) {
     tc::SkTuning t;
     t.pdl = h->pdl;
+    t.smem_budget = h->sk_smem;
     return tc::sk_linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->sk_ws, h->sk_counters, t, h->body);
   }
   if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->body);
@@ -263,6 +265,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
     if (v >= 1 && v <= 3) h->gemm_impl = v;
   }
   if (const char* e = getenv("B200_PDL")) h->pdl = atoi(e) != 0;
+  if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
   if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e) != 0;
   if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
   *out = h;
@@ -425,7 +428,6 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->x, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->xn, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->qkv, (size_t)B * 3 * d));
-  B200_TRY(A.alloc_t(&h->q, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->ao, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->hbuf, (size_t)B * c.ffn_hidden));
   B200_TRY(A.alloc_t(&h->tout, (size_t)B * d));
@@ -434,7 +436,6 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->dx, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dxn, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dqkv, (size_t)B * 3 * dd));
-  B200_TRY(A.alloc_t(&h->dq, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dao, (size_t)B * dd));
   B200_TRY(A.alloc_t(&h->dh, (size_t)B * c.depformer_ffn_hidden));
   B200_TRY(A.alloc_t(&h->dep_logits, (size_t)B * c.dep_q * c.card));
