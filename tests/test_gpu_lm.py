@@ -260,11 +260,15 @@ def test_fused_depformer_equals_launch_chain(B, monkeypatch):
 
     chain, fused = run("0"), run("1")
     same = total = 0
+    on_track = torch.ones(B, dtype=torch.bool)             # rows whose sampled history is still identical in both runs
     for (tl_c, dl_c, at_c), (tl_f, dl_f, at_f) in zip(chain, fused):
-        assert torch.equal(tl_c, tl_f)                    # the temporal path is the same code in both runs
+        assert on_track.any()
+        assert torch.equal(tl_c[on_track], tl_f[on_track])  # the temporal path is the same code in both runs
         # sub-step 0 sees identical inputs; later sub-steps only where the previously sampled ids agree
-        torch.testing.assert_close(dl_f[0], dl_c[0], rtol=0, atol=LOGIT_ATOL)
-        same += int((at_c == at_f).sum())
-        total += at_c.numel()
-    print(f"fused vs chain, B={B}: greedy ids equal {same}/{total}")
+        torch.testing.assert_close(dl_f[0][on_track], dl_c[0][on_track], rtol=0, atol=LOGIT_ATOL)
+        eq = (at_c == at_f)[:, on_track]
+        same += int(eq.sum())
+        total += eq.numel()
+        on_track &= (at_c == at_f).all(dim=0)
+    print(f"fused vs chain, B={B}: greedy ids equal {same}/{total} on rows with identical history")
     assert same / total > 0.9
