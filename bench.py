@@ -231,9 +231,19 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
     peak, src = _peaks()
     gbs = alg / (ms * 1e-3) / 1e9
     del k, v
-    return {"kernel": "lm::attn_step_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/attn_step_ncu.json: B = 96, full ring);
+    # the kernel reads every session's K/V exactly once, so bytes per launch scale with sessions x keys
+    traffic, traffic_src = None, None
+    cap_file = ROOT / "profiles" / "attn_step_ncu.json"
+    if cap_file.exists():
+        cap_d = json.loads(cap_file.read_text())
+        per_key_session = (cap_d["dram_bytes_read"] + cap_d["dram_bytes_write"]) / (cap_d["B"] * cap_d["keys"])
+        traffic = per_key_session * B * n_keys
+        traffic_src = ("ncu --set full at B=%d, %d keys (%s): dram read+write / launch scaled by sessions x keys"
+                       % (cap_d["B"], cap_d["keys"], cap_d["source"]))
+    return {"traffic": traffic, "traffic_source": traffic_src, "kernel": "lm::attn_step_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
             "bound": "hbm", "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak,
-            "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
+            "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
 
 
 def _gemm_roofline(B: int, device) -> dict:
