@@ -225,6 +225,17 @@ int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows);
 int b200_op_pack_tiles(const void* w_dev, void* out_dev, int N, int K, int epi, int gate_rows, void* stream);
 int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N,
                       int K, int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream);
+/* int8 x int8 linear (QLinear, utils/quantize.py:13-40: bitsandbytes row-wise absmax quantisation of weights and
+ * activations, int32 accumulation, dequantisation by both row scales / 127^2), on tcgen05 kind::i8.
+ *   b200_op_quant_pack_tiles: w bf16 [N,K] -> int8 SWIZZLE_128B tiles (b200_op_packed_bytes_i8 bytes) + scales f32 [N]
+ *   b200_op_quantize_rows:    x bf16 [M,K] -> xq int8 [M,K] + scales f32 [M]
+ *   b200_op_linear_i8:        y bf16 = epi(dequant(xq . Wq^T)), epilogues as b200_op_linear_sk */
+int64_t b200_op_packed_bytes_i8(int N, int K, int epi, int gate_rows);
+int b200_op_quant_pack_tiles(const void* w_dev, void* tiles_dev, float* scales_dev, int N, int K, int epi, int gate_rows,
+                             void* stream);
+int b200_op_quantize_rows(const void* x_dev, void* xq_dev, float* sa_dev, int M, int K, void* stream);
+int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_tiles_dev, const float* sw_dev, void* y_dev,
+                      const void* res_dev, int M, int N, int K, int epi, int gate_rows, void* stream);
 /* StreamingConv1d.forward on one layer (conv.py:245-274): x [B,Cin,T], w [Cout,Cin,K], state
  * previous [B,Cin,Keff-S] (updated in place where exec_mask), y [B,Cout,T/S]. elu_in applies ELU to x. */
 int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,

@@ -37,6 +37,9 @@ struct SkParams {
   int* counters;                // [n_tiles], zero between launches
   uint32_t tmem_cols, stage_bytes;
   int stream_only;              // diagnostics: skip the MMAs (measures the copy pipeline alone)
+  // int8 x int8 -> int32 (QLinear, utils/quantize.py:13-40): activations / weights are row-wise absmax int8, the
+  // accumulator is dequantised as acc * sa[m] * sw[n] / 127^2; whole tiles only (exact integer sums)
+  int i8; const float* sa; const float* sw;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +86,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -113,6 +123,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+// kind::i8: c_format S32 (2 at bit 4), a/b format signed 8 bit (1 at bits 7 / 10), K-major A and B
+__device__ __forceinline__ uint32_t make_idesc_i8(int umma_m, int umma_n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -153,6 +167,12 @@ __device__ __forceinline__ Seg seg_get(const SkParams& p, int c, int n_sk, int i
     s.kb0 = 0; s.kb1 = p.num_kb; s.slot = -1;
   }
   return s;
+}
+
+// accumulator word of output (m, weight row nw) as a float: fp32 bits, or int32 x the two row scales (int8 path)
+__device__ __forceinline__ float acc_value(const SkParams& p, uint32_t bits, int m, int nw) {
+  if (!p.i8) return __uint_as_float(bits);
+  return (float)(int)bits * (p.sa[m] * p.sw[nw] * (1.f / 16129.f));
 }
 
 template <int EPI>
@@ -240,7 +260,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
+      const uint32_t idesc = p.i8 ? make_idesc_i8(BLOCK_ROWS, p.Mpad) : make_idesc(BLOCK_ROWS, p.Mpad);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_bits = 0u;       // bit a = phase parity of accumulator stage a
       for (int si = 0; si < n_seg; ++si) {
@@ -258,8 +278,14 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t db = make_desc(sb + k * UMMA_K * 2);
               const uint32_t accum = (kb == sg.kb0 && k == 0) ? 0u : 1u;
-              umma_bf16(d0, make_desc(sa + k * UMMA_K * 2), db, idesc, accum);
-              if (EPI == EPI_GATE) umma_bf16(d0 + (uint32_t)p.Mpad, make_desc(sa + TILE_BYTES + k * UMMA_K * 2), db, idesc, accum);
+              // one MMA consumes 32 bytes of K per row either way: 16 bf16 or 32 int8
+              if (p.i8) {
+                umma_i8(d0, make_desc(sa + k * UMMA_K * 2), db, idesc, accum);
+                if (EPI == EPI_GATE) umma_i8(d0 + (uint32_t)p.Mpad, make_desc(sa + TILE_BYTES + k * UMMA_K * 2), db, idesc, accum);
+              } else {
+                umma_bf16(d0, make_desc(sa + k * UMMA_K * 2), db, idesc, accum);
+                if (EPI == EPI_GATE) umma_bf16(d0 + (uint32_t)p.Mpad, make_desc(sa + TILE_BYTES + k * UMMA_K * 2), db, idesc, accum);
+              }
             }
           }
           umma_commit(empty0 + 8 * s);           // frees the smem stage once these MMAs have read it
@@ -308,8 +334,8 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
               const int m = c0 + j;
               if (m < p.M && n_ok) {
                 float v;
-                if (EPI == EPI_RESADD) v = rv[j] + bf16_round(__uint_as_float(r0[j]));
-                else v = epilogue_value<EPI>(p, __uint_as_float(r0[j]), EPI == EPI_GATE ? __uint_as_float(r1[j]) : 0.f, m, n);
+                if (EPI == EPI_RESADD) v = rv[j] + bf16_round(acc_value(p, r0[j], m, n));
+                else v = epilogue_value<EPI>(p, acc_value(p, r0[j], m, n), EPI == EPI_GATE ? acc_value(p, r1[j], m, p.gate_rows + n) : 0.f, m, n);
                 p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
               }
             }
@@ -603,6 +629,97 @@ __global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ w, uint4* __
   out[idx] = v;
 }
 
+// ---- int8 quantisation (QLinear: bnb int8_vectorwise_quant, utils/quantize.py:16-20,38) -----------------------------------
+// row-wise absmax of w[rows][K] taken on the fp16 values (the reference quantises weight.to(float16))
+__global__ void row_absmax_f16_kernel(const __nv_bfloat16* __restrict__ w, float* __restrict__ out, int rows, int K) {
+  const int row = blockIdx.x;
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    mx = fmaxf(mx, fabsf(__half2float(__float2half_rn(__bfloat162float(w[(long long)row * K + k])))));
+  __shared__ float red[32];
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) t = fmaxf(t, red[i]);
+    out[row] = t;
+  }
+}
+__device__ __forceinline__ int quant_i8(float v, float inv) {           // round(v * 127 / absmax), ties to even (torch.round)
+  int q = __float2int_rn(v * inv);
+  return q > 127 ? 127 : (q < -127 ? -127 : q);
+}
+// w [rows][K] -> int8 tiles [n_tile][kb][A][128 rows x 128 k] in the SWIZZLE_128B layout (one 16-byte chunk = 16 k per thread)
+__global__ void pack_tiles_i8_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ absmax, uint4* __restrict__ out,
+                                     int rows, int K, int n_tiles, int num_kb, int a_tiles, int gate_rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_tiles * num_kb * a_tiles * (TILE_BYTES / 16);
+  if (idx >= total) return;
+  const int chunk = (int)(idx % (TILE_BYTES / 16));
+  long long t = idx / (TILE_BYTES / 16);
+  const int a = (int)(t % a_tiles); t /= a_tiles;
+  const int kb = (int)(t % num_kb);
+  const int tile = (int)(t / num_kb);
+  const int r = chunk >> 3, cpos = chunk & 7;
+  const int csrc = cpos ^ (r & 7);
+  const int limit = a_tiles == 2 ? gate_rows : rows;
+  const int rr = tile * BLOCK_ROWS + r;
+  const int k0 = kb * 128 + csrc * 16;
+  uint32_t words[4] = {0u, 0u, 0u, 0u};
+  if (rr < limit) {
+    const long long srow = (long long)(rr + a * gate_rows);
+    const float am = absmax[srow];
+    const float inv = am > 0.f ? 127.f / am : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = k0 + j;
+      int q = 0;
+      if (k < K) q = quant_i8(__half2float(__float2half_rn(__bfloat162float(w[srow * K + k]))), inv);
+      words[j >> 2] |= (uint32_t)(q & 0xFF) << (8 * (j & 3));
+    }
+  }
+  out[idx] = make_uint4(words[0], words[1], words[2], words[3]);
+}
+// activations: x [M][K] bf16 (row stride ldx) -> xq int8 [M][K], sa[m] = absmax of the row
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int8_t* __restrict__ xq,
+                                                           float* __restrict__ sa, int K) {
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (long long)row * ldx;
+  float mx = 0.f;
+  for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      mx = fmaxf(mx, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  __shared__ float red[8];
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float am = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) am = fmaxf(am, red[i]);
+  if (threadIdx.x == 0) sa[row] = am;
+  const float inv = am > 0.f ? 127.f / am : 0.f;
+  for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint32_t w0 = 0u, w1 = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      const uint32_t a = (uint32_t)(quant_i8(f.x, inv) & 0xFF), b = (uint32_t)(quant_i8(f.y, inv) & 0xFF);
+      if (i < 2) w0 |= (a | (b << 8)) << (16 * i);
+      else w1 |= (a | (b << 8)) << (16 * (i - 2));
+    }
+    *reinterpret_cast<uint2*>(xq + (long long)row * K + k) = make_uint2(w0, w1);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -655,6 +772,34 @@ int sk_pack_weights(const __nv_bfloat16* w, void* out, int N, int K, int epi, in
   return check_launch("pack_tiles");
 }
 
+size_t sk_packed_bytes_i8(int N, int K, int epi, int gate_rows) {
+  const int a = epi == EPI_GATE ? 2 : 1;
+  const int rows = epi == EPI_GATE ? gate_rows : N;
+  return (size_t)((rows + BLOCK_ROWS - 1) / BLOCK_ROWS) * ((K + 127) / 128) * a * TILE_BYTES;
+}
+
+int sk_quant_pack_weights(const __nv_bfloat16* w, void* out_tiles, float* out_scales, int N, int K, int epi, int gate_rows,
+                          cudaStream_t stream) {
+  if (K % 16) B200_FAIL(B200_ERR_SHAPE, "sk_quant_pack_weights: K must be a multiple of 16");
+  const int a = epi == EPI_GATE ? 2 : 1;
+  const int w_rows = epi == EPI_GATE ? 2 * gate_rows : N;
+  const int rows = epi == EPI_GATE ? gate_rows : N;
+  const int n_tiles = (rows + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + 127) / 128;
+  row_absmax_f16_kernel<<<w_rows, 256, 0, stream>>>(w, out_scales, w_rows, K);
+  const long long total = (long long)n_tiles * num_kb * a * (TILE_BYTES / 16);
+  pack_tiles_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, out_scales, static_cast<uint4*>(out_tiles), w_rows, K,
+                                                                           n_tiles, num_kb, a, epi == EPI_GATE ? gate_rows : 0);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return check_launch("quant_pack_tiles");
+}
+
+int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream) {
+  if (K % 8 || ldx % 8) B200_FAIL(B200_ERR_SHAPE, "sk_quantize_rows: K and the row stride must be multiples of 8");
+  quantize_rows_kernel<<<M, 256, 0, stream>>>(x, ldx, static_cast<int8_t*>(xq), sa, K);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("quantize_rows");
+}
+
 size_t sk_workspace_bytes(int max_M) {
   const int Mpad = ((max_M + 15) / 16) * 16;
   return (size_t)2 * SK_MAX_GRID * 2 * Mpad * BLOCK_ROWS * 4;  // 2 slots per CTA, gate + value accumulators
@@ -665,19 +810,21 @@ bool sk_supported(int M, int N, int K, int epi) {
   return M >= 1 && M <= 256 && K >= 8 && K % 8 == 0;
 }
 
-// 2-D tensor map of the activations x [M][K] (row stride ldx) with a [box_rows x 64] SWIZZLE_128B box
-static int x_map(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, int M, int K, int box_rows, const CUtensorMap** out) {
+// 2-D tensor map of the activations x [M][K] (row stride ldx elements) with a [box_rows x 128 bytes] SWIZZLE_128B box;
+// elem_bytes = 2 (bf16) or 1 (int8)
+static int x_map(GemmPlanCache& cache, const void* x, long long ldx, int M, int K, int box_rows, int elem_bytes,
+                 const CUtensorMap** out) {
   PlanKey key{x, ldx, M, K, box_rows};
   auto it = cache.maps.find(key);
   if (it == cache.maps.end()) {
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldx * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                          const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) M=%d K=%d ld=%lld", (int)r, M, K, ldx);
     it = cache.maps.emplace(key, m).first;
   }
@@ -694,7 +841,9 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
     B200_FAIL(B200_ERR_SHAPE, "sk GEMM: operands must be 16-byte aligned");
   B200_TRY(init_once());
   // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
-  if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {
+  const bool i8 = tune.xq != nullptr;
+  if (i8 && (K % 16 || !tune.sa || !tune.sw)) B200_FAIL(B200_ERR_SHAPE, "int8 GEMM: K must be a multiple of 16 and both scale vectors given");
+  if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32 && !i8) {
     const int n_tiles = (N + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     int cs = 1;
     while (cs < 8 && n_tiles * cs * 2 <= g_sms && num_kb / (cs * 2) >= 4) cs *= 2;
@@ -720,7 +869,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
           while (pow2 < (uint32_t)p.Mpad) pow2 <<= 1;
           p.tmem_cols = pow2;
           const CUtensorMap* mx = nullptr;
-          B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, &mx));
+          B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, 2, &mx));
           const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64 + recv_bytes + 64;
           cudaLaunchConfig_t cfg;
           memset(&cfg, 0, sizeof(cfg));
@@ -747,7 +896,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.wt = static_cast<const uint8_t*>(w_tiles);
   p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
   p.ws = ws; p.counters = counters;
-  p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  p.i8 = i8 ? 1 : 0; p.sa = tune.sa; p.sw = tune.sw;
+  p.num_kb = i8 ? (K + 127) / 128 : (K + BLOCK_K - 1) / BLOCK_K;      // a k-block is 128 bytes of K per row
   p.n_tiles = (p.out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
   if (p.n_tiles > 1024) B200_FAIL(B200_ERR_SHAPE, "sk GEMM: more than 1024 row tiles");
   int grid = tune.grid > 0 ? tune.grid : g_sms;
@@ -757,7 +907,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   if (tune.grid == 0 && grid > (p.n_tiles * p.num_kb) / 8) grid = (p.n_tiles * p.num_kb) / 8 > 0 ? (p.n_tiles * p.num_kb) / 8 : 1;
   // Cutting a tile into S pieces moves S fp32 partials of [128 x Mpad] through L2 (written + read back): allow it
   // only while that stays under half of the tile's weight bytes, i.e. S <= 8 * num_kb / Mpad.
-  int s_max = tune.no_split ? 1 : (8 * p.num_kb) / p.Mpad;
+  int s_max = (tune.no_split || i8) ? 1 : (8 * p.num_kb) / p.Mpad;      // int8: whole tiles (exact integer sums)
   // measured on B200 (profiles/r01_c_kbench.jsonl): with more than 32 sessions the publish / count / re-read protocol
   // costs more than the idle SMs it recovers, so tiles stay whole there
   if (p.Mpad > 32 && tune.force_split == 0) s_max = 1;
@@ -784,7 +934,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.tmem_cols = pow2;
   p.stream_only = tune.stream_only;
   const CUtensorMap* mx = nullptr;
-  B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, &mx));
+  if (i8) B200_TRY(x_map(cache, tune.xq, K, M, K, p.Mpad, 1, &mx));
+  else B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, 2, &mx));
   const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -47,6 +47,8 @@ struct SkTuning {
   int force_split = 0;   // tests: cut tiles even where the default policy keeps them whole
   int no_cluster = 0;    // never use the cluster split-K kernel
   int cluster = 0;       // force a cluster size (tests)
+  // int8 path (QLinear): row-wise absmax int8 activations [M][K] + their scales, and the weight-row scales [N]
+  const void* xq = nullptr; const float* sa = nullptr; const float* sw = nullptr;
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
 };
 int sk_num_sms();
@@ -54,6 +56,11 @@ bool sk_supported(int M, int N, int K, int epi);
 size_t sk_packed_bytes(int N, int K, int epi, int gate_rows);
 int sk_pack_weights(const __nv_bfloat16* w, void* out, int N, int K, int epi, int gate_rows, cudaStream_t stream);
 size_t sk_workspace_bytes(int max_M);
+// int8 (QLinear, utils/quantize.py:13-40): weights -> row-wise absmax int8 tiles + scales; activations -> int8 rows + scales
+size_t sk_packed_bytes_i8(int N, int K, int epi, int gate_rows);
+int sk_quant_pack_weights(const __nv_bfloat16* w, void* out_tiles, float* out_scales, int N, int K, int epi, int gate_rows,
+                          cudaStream_t stream);
+int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream);
 constexpr int SK_MAX_GRID = 304;     // 2 CTAs per SM at most
 constexpr int SK_MAX_TILES = 1024;   // ints in the arrival-counter array
 int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y,

@@ -55,6 +55,40 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
                        static_cast<cudaStream_t>(stream));
 }
 
+int64_t b200_op_packed_bytes_i8(int N, int K, int epi, int gate_rows) { return (int64_t)tc::sk_packed_bytes_i8(N, K, epi, gate_rows); }
+
+int b200_op_quant_pack_tiles(const void* w_dev, void* tiles_dev, float* scales_dev, int N, int K, int epi, int gate_rows,
+                             void* stream) {
+  if (!w_dev || !tiles_dev || !scales_dev) B200_FAIL(B200_ERR_INVALID, "op_quant_pack_tiles: null pointer");
+  return tc::sk_quant_pack_weights(static_cast<const __nv_bfloat16*>(w_dev), tiles_dev, scales_dev, N, K, epi, gate_rows,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int b200_op_quantize_rows(const void* x_dev, void* xq_dev, float* sa_dev, int M, int K, void* stream) {
+  if (!x_dev || !xq_dev || !sa_dev) B200_FAIL(B200_ERR_INVALID, "op_quantize_rows: null pointer");
+  return tc::sk_quantize_rows(static_cast<const __nv_bfloat16*>(x_dev), K, xq_dev, sa_dev, M, K, static_cast<cudaStream_t>(stream));
+}
+
+int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_tiles_dev, const float* sw_dev, void* y_dev,
+                      const void* res_dev, int M, int N, int K, int epi, int gate_rows, void* stream) {
+  if (!xq_dev || !sa_dev || !w_tiles_dev || !sw_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_i8: null pointer");
+  if (!tc::sk_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_i8: unsupported shape");
+  static tc::GemmPlanCache cache;
+  static float* ws = nullptr;
+  static int* counters = nullptr;
+  if (!ws) {
+    B200_CUDA(cudaMalloc(&ws, 1 << 20));
+    B200_CUDA(cudaMalloc(&counters, tc::SK_MAX_TILES * sizeof(int)));
+    B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
+  }
+  tc::SkTuning t;
+  t.xq = xq_dev; t.sa = sa_dev; t.sw = sw_dev;
+  const int out_cols = epi == 2 ? gate_rows : N;
+  return tc::sk_linear(cache, nullptr, K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev), out_cols,
+                       static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, ws, counters, t,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,
                    const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T, int K, int stride,
                    int dilation, int elu_in, void* stream) {

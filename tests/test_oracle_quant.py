@@ -1,0 +1,35 @@
+"""CPU: the int8 QLinear restatement (oracle/quant.py) — quantiser properties and faithfulness to the float linear."""
+import torch
+
+from oracle import quant
+
+
+def test_rowwise_quantiser_properties():
+    g = torch.Generator().manual_seed(0)
+    t = torch.randn(6, 320, generator=g)
+    t[2] = 0.0
+    q, s = quant.quantize_rows(t)
+    assert q.dtype == torch.int8 and s.shape == (6,)
+    assert int(q.abs().max()) == 127 and (q[2] == 0).all() and s[2] == 0
+    # every row attains +-127 at its absmax element, and dequantisation is within half a step
+    for r in (0, 1, 3, 4, 5):
+        assert int(q[r].abs().max()) == 127
+        assert ((q[r].float() * s[r] / 127) - t[r]).abs().max() <= s[r] / 254 * 1.0001
+    # ties go to even (torch.round): 0.5 * step -> 0, 1.5 * step -> 2
+    row = torch.tensor([[127.0, 0.5, 1.5, -0.5, -2.5]])
+    assert quant.quantize_rows(row)[0].tolist() == [[127, 0, 2, 0, -2]]
+
+
+def test_qlinear_is_a_faithful_linear_and_exact_in_integers():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 512, generator=g).bfloat16()
+    w = (torch.randn(64, 512, generator=g) / 512 ** 0.5).bfloat16()
+    y = quant.qlinear_f32(x, w)
+    ref = x.float() @ w.float().t()
+    assert (y - ref).abs().max() < 0.03 * ref.abs().max()
+    qw, sw = quant.quantize_weight(w)
+    qx, sa = quant.quantize_rows(x)
+    acc = (qx.long() @ qw.long().t())
+    assert torch.equal(acc.double(), qx.double() @ qw.double().t())
+    assert torch.equal(y, acc.float() * ((sa[:, None] * sw[None, :]) * torch.tensor(float(quant.INV_127_SQ))))
+    assert quant.qlinear(x, w).dtype == torch.bfloat16
