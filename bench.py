@@ -291,7 +291,9 @@ def b200_arm(args) -> None:
     lib = _lib.lib()
 
     mimi = loaders.get_mimi(None, device=device, num_codebooks=8)
-    lm = loaders.get_moshi_lm(None, MOSHI_7B.to_reference_kwargs(), device=device, synth_device=device)
+    lm_kwargs = MOSHI_7B.to_reference_kwargs()
+    lm_kwargs["quantize"] = bool(args.quantize)
+    lm = loaders.get_moshi_lm(None, lm_kwargs, device=device, synth_device=device)
     torch.cuda.synchronize(device)
 
     # sessions per GPU: the full-context bf16 KV ring (1.573 GB/session) is what bounds it
@@ -378,7 +380,7 @@ def b200_arm(args) -> None:
         mimi._stop()
         torch.cuda.empty_cache()
         roof = _dominant_kernel_roofline(B, kv_fill, device)
-        gemm_roof = _gemm_roofline(B, device)
+        gemm_roof = None if args.quantize else _gemm_roofline(B, device)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         r = run_cpu_pipeline(steps=3, warmup=1)
@@ -392,8 +394,9 @@ def b200_arm(args) -> None:
     line = {
         "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Mimi streaming encode (8 codebooks) -> Moshi 7B bf16 LMGen.step (temp 0.8/0.7, top-k 250/25) "
+        "vs_baseline": None, "dtype": "int8 linears (s32 accumulate), bf16 elsewhere" if args.quantize else "bf16", "data": "synthetic",
+        "config": {"workload": f"Mimi streaming encode (8 codebooks) -> Moshi 7B {'int8 (W8A8 QLinear)' if args.quantize else 'bf16'} "
+                               "LMGen.step (temp 0.8/0.7, top-k 250/25) "
                                "-> Mimi streaming decode; one 80 ms frame for every session per step",
                    "sessions_per_gpu": B, "sessions_total": total_sessions, "kv_fill": kv_fill,
                    "kv_ring": "bf16, capacity 3000 (reference context)", "parallelism": f"replicas x{world}",
@@ -423,6 +426,7 @@ def main() -> None:
     ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: as many as the full-context bf16 KV rings fit in HBM)")
     ap.add_argument("--kv-fill", type=int, default=-1, help="frames of history per session (default: full ring)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--quantize", action="store_true", help="BASELINE config 5: int8 (W8A8 QLinear) Moshi 7B instead of bf16")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -156,6 +156,8 @@ typedef struct {
   int depformer_num_layers;   /* 6 */
   int depformer_ffn_hidden;   /* 2816 */
   int delays[33];             /* n_q + 1 entries */
+  int quantize;               /* LMModel(quantize=True) (lm.py:107,242-243; utils/quantize.py): every linear is an int8 QLinear,
+                                 quantised here from the bf16 weights at load */
 } b200_lm_config;
 
 /* loaders.get_moshi_lm (loaders.py:366-446). Tensors are bf16 with the reference's key names. */

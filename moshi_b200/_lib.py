@@ -36,6 +36,7 @@ class LMConfigC(C.Structure):
         ("num_heads", C.c_int), ("num_layers", C.c_int), ("ffn_hidden", C.c_int), ("context", C.c_int),
         ("max_period", C.c_float), ("depformer_dim", C.c_int), ("depformer_num_heads", C.c_int),
         ("depformer_num_layers", C.c_int), ("depformer_ffn_hidden", C.c_int), ("delays", C.c_int * 33),
+        ("quantize", C.c_int),
     ]
 
 

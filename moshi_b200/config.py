@@ -154,6 +154,7 @@ class LMConfig:
     depformer_gating: str = "silu"
     depformer_pos_emb: str = "none"
     depformer_weights_per_step: bool = True
+    quantize: bool = False       # LMModel(quantize=True), lm.py:107,242-243: every nn.Linear becomes an int8 QLinear
     delays: tp.List[int] = field(
         default_factory=lambda: [0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1])
 
@@ -210,6 +211,8 @@ class LMConfig:
             bad.append("delays")
         if self.dim % self.num_heads or self.depformer_dim % self.depformer_num_heads:
             bad.append("heads")
+        if self.quantize and any(k % 16 for k in (self.dim, self.ffn_hidden, self.depformer_dim, self.depformer_ffn_hidden)):
+            bad.append("quantize (int8 k-extents must be multiples of 16)")
         if bad:
             raise ValueError(f"LM options outside the B200 hot path: {bad}")
 

@@ -252,7 +252,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
             mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
             bulk_load(sa, src, a_bytes, full0 + 8 * s);
           }
-          tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * BLOCK_K, 0);
+          tma_load_2d(sa + a_bytes, &tmap_x, full0 + 8 * s, kb * (p.i8 ? 2 * BLOCK_K : BLOCK_K), 0);   // 128 bytes of K either way
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }

@@ -11,10 +11,12 @@ namespace {
 
 struct TLayer {
   const bf16 *in_w, *out_w, *n1, *n2, *lin_in, *lin_out;
+  const float *in_s = nullptr, *out_s = nullptr, *lin_in_s = nullptr, *lin_out_s = nullptr;   // int8 path: weight-row scales
   bf16 *kc = nullptr, *vc = nullptr;
 };
 struct DLayer {
   std::vector<const bf16*> in_w, out_w, lin_in, lin_out;   // one per depformer step
+  std::vector<const float*> in_s, out_s, lin_in_s, lin_out_s;   // int8 path: weight-row scales
   const bf16 *n1, *n2;
   bf16 *kc = nullptr, *vc = nullptr;
 };
@@ -45,6 +47,9 @@ struct b200_lm {
   std::vector<TLayer> layers;
   std::vector<DLayer> dlayers;
   const bf16 *out_norm = nullptr, *text_linear = nullptr;
+  const float *text_linear_s = nullptr, *dep_in_s = nullptr;
+  std::vector<const float*> dep_heads_s;
+  int8_t* xq = nullptr; float* xq_scale = nullptr;     // int8 path: the current GEMM's quantised activations [B][max K] and row scales
   bf16* dep_in_all = nullptr;                  // [dep_q * dd][dim]
   std::vector<const bf16*> dep_tables;         // [0] = depformer_text_emb, [k] = depformer_emb[k-1]
   std::vector<const bf16*> dep_heads;          // linears[k]
@@ -105,12 +110,18 @@ int noise_per_row(const b200_lm* h) {
 // y[M][N] = epi(x[M][K] . w[N][K]^T).  `w` is the packed-tile form (gemm_sk.cu) unless a legacy kernel was
 // selected with B200_GEMM_IMPL (1 = SIMT, 2 = one-tile-per-CTA tcgen05), in which case it is row-major.
 int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, const bf16* res,
-           long long ldr, int M, int N, int K, int epi, int gate_rows) {
+           long long ldr, int M, int N, int K, int epi, int gate_rows, const float* w_scales = nullptr) {
   const int impl = h->gemm_impl;
   if (impl == 3) {
     tc::SkTuning t;
     t.pdl = h->pdl;
     t.smem_budget = h->sk_smem;
+    if (h->cfg.quantize) {       // QLinear.forward (utils/quantize.py:22-40): row-wise int8 activations, int8 x int8 -> int32
+      if (!w_scales) B200_FAIL(B200_ERR_STATE, "quantised LM: linear without weight scales");
+      B200_TRY(tc::sk_quantize_rows(x, ldx, h->xq, h->xq_scale, M, K, h->body));
+      t.xq = h->xq; t.sa = h->xq_scale; t.sw = w_scales;
+      t.pdl = 0;
+    }
     return tc::sk_linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->sk_ws, h->sk_counters, t, h->body);
   }
   if (impl == 2) return tc::linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->body);
@@ -130,13 +141,26 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
 
 // Linear weight from the store -> the layout the selected GEMM reads.  Packed tiles replace the row-major
 // tensor (which is released), so the 15.4 GB checkpoint is resident once.
-int get_linear(b200_lm* h, const std::string& name, int N, int K, int epi, int gate_rows, const bf16** out) {
+int get_linear(b200_lm* h, const std::string& name, int N, int K, int epi, int gate_rows, const bf16** out,
+               const float** scales_out) {
   const bf16* w = nullptr;
-  B200_TRY(get_bf16(h, name, {epi == LIN_GATE ? 2 * gate_rows : N, K}, &w));
+  const int w_rows = epi == LIN_GATE ? 2 * gate_rows : N;
+  B200_TRY(get_bf16(h, name, {w_rows, K}, &w));
+  *scales_out = nullptr;
   if (h->gemm_impl != 3) { *out = w; return B200_OK; }
   void* packed = nullptr;
-  B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(N, K, epi, gate_rows), false));
-  B200_TRY(tc::sk_pack_weights(w, packed, N, K, epi, gate_rows, nullptr));
+  if (h->cfg.quantize) {        // QLinear.__init__ (utils/quantize.py:16-21): row-wise absmax int8 of weight.to(float16)
+    float* scales = nullptr;
+    B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes_i8(N, K, epi, gate_rows), false));
+    B200_TRY(h->weights.alloc_t(&scales, (size_t)w_rows, false));
+    B200_TRY(tc::sk_quant_pack_weights(w, packed, scales, N, K, epi, gate_rows, nullptr));
+    *scales_out = scales;
+    h->weight_bytes -= (int64_t)w_rows * K;        // one byte per weight instead of two (get_bf16 counted two) ...
+    h->weight_bytes += (int64_t)w_rows * 4;        // ... plus the row scales
+  } else {
+    B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(N, K, epi, gate_rows), false));
+    B200_TRY(tc::sk_pack_weights(w, packed, N, K, epi, gate_rows, nullptr));
+  }
   B200_CUDA(cudaStreamSynchronize(nullptr));
   h->store.release(name);
   *out = static_cast<const bf16*>(packed);
@@ -173,7 +197,7 @@ int step_body(b200_lm* h) {
   } else {
     for (auto& L : h->layers) {
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
-      B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0));
+      B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0, L.in_s));
       {   // RoPE + ring append + split-KV attention + split merge in one launch
         AttnStep a;
         a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
@@ -182,20 +206,20 @@ int step_body(b200_lm* h) {
         dim3 grid(B * H, h->nsplit);
         B200_LAUNCH(attn_step_kernel, grid, ATT_THREADS, 0, st, a);
       }
-      B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0));
+      B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0, L.out_s));
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n2, h->xn, d, 1e-8f);
-      B200_TRY(linear(h, h->xn, d, L.lin_in, h->hbuf, F, nullptr, 0, B, F, d, LIN_GATE, F));
-      B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0));
+      B200_TRY(linear(h, h->xn, d, L.lin_in, h->hbuf, F, nullptr, 0, B, F, d, LIN_GATE, F, L.lin_in_s));
+      B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0, L.lin_out_s));
     }
   }
   B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, h->out_norm, h->tout, d, 1e-8f);
-  B200_TRY(linear(h, h->tout, d, h->text_linear, h->text_logits, c.text_card, nullptr, 0, B, c.text_card, d, LIN_STORE, 0));
+  B200_TRY(linear(h, h->tout, d, h->text_linear, h->text_logits, c.text_card, nullptr, 0, B, c.text_card, d, LIN_STORE, 0, h->text_linear_s));
   B200_TRY(sample(h, h->text_logits, c.text_card, h->noise, h->text_token, h->temp_text, h->top_k_text));
 
   // Depformer (lm.py:809-850): fresh KV state every frame, all rows advance together.
   const int kt = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
   const int ka = h->top_k < c.card ? h->top_k : c.card;
-  B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, B, c.dep_q * dd, d, LIN_STORE, 0));
+  B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, B, c.dep_q * dd, d, LIN_STORE, 0, h->dep_in_s));
   if (h->depf) {
     B200_TRY(tc::dep_fused_launch(h->depf, st));
   } else {
@@ -205,15 +229,15 @@ int step_body(b200_lm* h) {
                   h->dep_tables[k], prev, h->dx, B, dd);
       for (auto& L : h->dlayers) {
         B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
-        B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0));
+        B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0, L.in_s[k]));
         B200_LAUNCH(dep_attn_step_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dqkv, L.kc, L.vc, h->dao, B, dH, c.dep_q, k);
-        B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0));
+        B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0, L.out_s[k]));
         B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
-        B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF));
-        B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0));
+        B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF, L.lin_in_s[k]));
+        B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0, L.lin_out_s[k]));
       }
       bf16* logits = h->dep_logits + (long long)k * B * c.card;
-      B200_TRY(linear(h, h->dx, dd, h->dep_heads[k], logits, c.card, nullptr, 0, B, c.card, dd, LIN_STORE, 0));
+      B200_TRY(linear(h, h->dx, dd, h->dep_heads[k], logits, c.card, nullptr, 0, B, c.card, dd, LIN_STORE, 0, h->dep_heads_s[k]));
       B200_TRY(sample(h, logits, c.card, h->noise + kt + (long long)k * ka, h->audio_tokens + (long long)k * B, h->temp,
                       h->top_k));
     }
@@ -287,18 +311,18 @@ int b200_lm_finalize(b200_lm* h) {
   for (int k = 0; k < c.n_q; ++k)
     B200_TRY(get_bf16(h, "emb." + std::to_string(k) + ".weight", {c.card + 1, d}, &h->emb.audio[k]));
   B200_TRY(get_bf16(h, "text_emb.weight", {c.text_card + 1, d}, &h->emb.text));
-  B200_TRY(get_linear(h, "text_linear.weight", c.text_card, d, LIN_STORE, 0, &h->text_linear));
+  B200_TRY(get_linear(h, "text_linear.weight", c.text_card, d, LIN_STORE, 0, &h->text_linear, &h->text_linear_s));
   B200_TRY(get_bf16(h, "out_norm.alpha", {1, 1, d}, &h->out_norm));
   h->layers.resize(c.num_layers);
   for (int l = 0; l < c.num_layers; ++l) {
     const std::string p = "transformer.layers." + std::to_string(l);
     TLayer& L = h->layers[l];
-    B200_TRY(get_linear(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, LIN_STORE, 0, &L.in_w));
-    B200_TRY(get_linear(h, p + ".self_attn.out_projs.0.weight", d, d, LIN_RESADD, 0, &L.out_w));
+    B200_TRY(get_linear(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, LIN_STORE, 0, &L.in_w, &L.in_s));
+    B200_TRY(get_linear(h, p + ".self_attn.out_projs.0.weight", d, d, LIN_RESADD, 0, &L.out_w, &L.out_s));
     B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, d}, &L.n1));
     B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, d}, &L.n2));
-    B200_TRY(get_linear(h, p + ".gating.linear_in.weight", 2 * F, d, LIN_GATE, F, &L.lin_in));
-    B200_TRY(get_linear(h, p + ".gating.linear_out.weight", d, F, LIN_RESADD, 0, &L.lin_out));
+    B200_TRY(get_linear(h, p + ".gating.linear_in.weight", 2 * F, d, LIN_GATE, F, &L.lin_in, &L.lin_in_s));
+    B200_TRY(get_linear(h, p + ".gating.linear_out.weight", d, F, LIN_RESADD, 0, &L.lin_out, &L.lin_out_s));
   }
   // depformer_in.{k} stacked so that all dep_q projections of transformer_out are one GEMM
   {
@@ -313,8 +337,18 @@ int b200_lm_finalize(b200_lm* h) {
     }
     if (h->gemm_impl == 3) {
       void* packed = nullptr;
-      B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(c.dep_q * dd, d, LIN_STORE, 0), false));
-      B200_TRY(tc::sk_pack_weights(stacked, packed, c.dep_q * dd, d, LIN_STORE, 0, nullptr));
+      if (c.quantize) {
+        float* scales = nullptr;
+        B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes_i8(c.dep_q * dd, d, LIN_STORE, 0), false));
+        B200_TRY(h->weights.alloc_t(&scales, (size_t)c.dep_q * dd, false));
+        B200_TRY(tc::sk_quant_pack_weights(stacked, packed, scales, c.dep_q * dd, d, LIN_STORE, 0, nullptr));
+        h->dep_in_s = scales;
+        h->weight_bytes -= (int64_t)c.dep_q * dd * d;
+        h->weight_bytes += (int64_t)c.dep_q * dd * 4;
+      } else {
+        B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes(c.dep_q * dd, d, LIN_STORE, 0), false));
+        B200_TRY(tc::sk_pack_weights(stacked, packed, c.dep_q * dd, d, LIN_STORE, 0, nullptr));
+      }
       B200_CUDA(cudaStreamSynchronize(nullptr));
       cudaFree(stacked);
       h->dep_in_all = static_cast<bf16*>(packed);
@@ -328,19 +362,21 @@ int b200_lm_finalize(b200_lm* h) {
   for (int k = 1; k < c.dep_q; ++k)
     B200_TRY(get_bf16(h, "depformer_emb." + std::to_string(k - 1) + ".weight", {c.card + 1, dd}, &h->dep_tables[k]));
   h->dep_heads.resize(c.dep_q);
+  h->dep_heads_s.resize(c.dep_q);
   for (int k = 0; k < c.dep_q; ++k)
-    B200_TRY(get_linear(h, "linears." + std::to_string(k) + ".weight", c.card, dd, LIN_STORE, 0, &h->dep_heads[k]));
+    B200_TRY(get_linear(h, "linears." + std::to_string(k) + ".weight", c.card, dd, LIN_STORE, 0, &h->dep_heads[k], &h->dep_heads_s[k]));
   h->dlayers.resize(c.depformer_num_layers);
   for (int l = 0; l < c.depformer_num_layers; ++l) {
     const std::string p = "depformer.layers." + std::to_string(l);
     DLayer& L = h->dlayers[l];
     L.in_w.resize(c.dep_q); L.out_w.resize(c.dep_q); L.lin_in.resize(c.dep_q); L.lin_out.resize(c.dep_q);
+    L.in_s.resize(c.dep_q); L.out_s.resize(c.dep_q); L.lin_in_s.resize(c.dep_q); L.lin_out_s.resize(c.dep_q);
     for (int k = 0; k < c.dep_q; ++k) {
       const std::string ks = std::to_string(k);
-      B200_TRY(get_linear(h, p + ".self_attn.in_projs." + ks + ".weight", 3 * dd, dd, LIN_STORE, 0, &L.in_w[k]));
-      B200_TRY(get_linear(h, p + ".self_attn.out_projs." + ks + ".weight", dd, dd, LIN_RESADD, 0, &L.out_w[k]));
-      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_in.weight", 2 * dF, dd, LIN_GATE, dF, &L.lin_in[k]));
-      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_out.weight", dd, dF, LIN_RESADD, 0, &L.lin_out[k]));
+      B200_TRY(get_linear(h, p + ".self_attn.in_projs." + ks + ".weight", 3 * dd, dd, LIN_STORE, 0, &L.in_w[k], &L.in_s[k]));
+      B200_TRY(get_linear(h, p + ".self_attn.out_projs." + ks + ".weight", dd, dd, LIN_RESADD, 0, &L.out_w[k], &L.out_s[k]));
+      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_in.weight", 2 * dF, dd, LIN_GATE, dF, &L.lin_in[k], &L.lin_in_s[k]));
+      B200_TRY(get_linear(h, p + ".gating." + ks + ".linear_out.weight", dd, dF, LIN_RESADD, 0, &L.lin_out[k], &L.lin_out_s[k]));
     }
     B200_TRY(get_bf16(h, p + ".norm1.alpha", {1, 1, dd}, &L.n1));
     B200_TRY(get_bf16(h, p + ".norm2.alpha", {1, 1, dd}, &L.n2));
@@ -451,7 +487,13 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_CUDA(cudaMallocHost(&h->pin_in, (size_t)B * n_in_max * 8));
   B200_CUDA(cudaMallocHost(&h->pin_out, (size_t)B * (c.dep_q + 1) * 8));
   B200_CUDA(cudaMallocHost(&h->pin_noise, (size_t)B * noise_per_row(h) * 4));
-  if (h->dep_fused && h->gemm_impl == 3 && B <= 256 && dd <= 1024 && dd % 64 == 0) {
+  if (c.quantize) {     // activations are re-quantised row-wise before every linear (QLinear.forward, utils/quantize.py:28-36)
+    if (h->gemm_impl != 3) B200_FAIL(B200_ERR_STATE, "quantize needs the tcgen05 GEMM (B200_GEMM_IMPL=3)");
+    const int kmax = std::max(std::max(d, c.ffn_hidden), std::max(dd, c.depformer_ffn_hidden));
+    B200_TRY(A.alloc_t(&h->xq, (size_t)B * kmax, false));
+    B200_TRY(A.alloc_t(&h->xq_scale, (size_t)B, false));
+  }
+  if (!c.quantize && h->dep_fused && h->gemm_impl == 3 && B <= 256 && dd <= 1024 && dd % 64 == 0) {
     tc::DepFusedConfig fc;
     memset(&fc, 0, sizeof(fc));
     fc.B = B; fc.dd = dd; fc.H = c.depformer_num_heads; fc.F = c.depformer_ffn_hidden; fc.card = c.card; fc.dep_q = c.dep_q;
@@ -712,6 +754,7 @@ int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill) {
   w += (int64_t)c.dep_q * c.depformer_num_layers *
        ((int64_t)4 * c.depformer_dim * c.depformer_dim + (int64_t)3 * c.depformer_ffn_hidden * c.depformer_dim) * 2;
   w += (int64_t)c.dep_q * c.card * c.depformer_dim * 2;
+  if (c.quantize) w /= 2;        // one byte per weight (the fp32 row scales are < 0.1 % of that)
   // per session: KV ring read (valid slots only) + append, embedding rows, logits written + read by the sampler
   int64_t per = (int64_t)c.num_layers * 2 * kv_fill * c.dim * 2 + (int64_t)c.num_layers * 2 * c.dim * 2;
   per += (int64_t)(c.n_q + 1) * c.dim * 2 + (int64_t)c.dep_q * c.depformer_dim * 2;

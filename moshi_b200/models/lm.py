@@ -29,6 +29,7 @@ def _config_struct(cfg: LMConfig) -> _lib.LMConfigC:
     c.depformer_num_layers, c.depformer_ffn_hidden = cfg.depformer_num_layers, cfg.depformer_ffn_hidden
     for i, d in enumerate(cfg.delays):
         c.delays[i] = d
+    c.quantize = int(bool(cfg.quantize))
     return c
 
 

@@ -115,8 +115,9 @@ def sample_token(logits: torch.Tensor, use_sampling: bool, temp: float, top_k: i
 class LMOracle:
     def __init__(self, sd: tp.Dict[str, torch.Tensor], spec: LMSpec, use_sampling: bool = True,
                  temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25,
-                 tie_break: str = "torch"):
+                 tie_break: str = "torch", quantize: bool = False):
         self.tie_break = tie_break
+        self.quantize = quantize          # LMModel(quantize=True): every nn.Linear is a QLinear (lm.py:242-243)
         self.sd = sd
         self.spec = spec
         self.use_sampling, self.temp, self.temp_text = use_sampling, temp, temp_text
@@ -126,13 +127,13 @@ class LMOracle:
         self.main_spec = tr.TransformerSpec(
             d_model=s.dim, num_heads=s.num_heads, num_layers=s.num_layers, context=s.context,
             norm=s.norm, gating=s.gating, positional_embedding=s.positional_embedding,
-            max_period=s.max_period)
+            max_period=s.max_period, quantize=quantize)
         self.dep_spec = tr.TransformerSpec(
             d_model=s.depformer_dim, num_heads=s.depformer_num_heads,
             num_layers=s.depformer_num_layers, context=None, norm=s.norm, gating=s.depformer_gating,
             positional_embedding=s.depformer_pos_emb, max_period=s.depformer_max_period,
             weights_per_step=s.dep_q if s.depformer_weights_per_step else 0,
-            schedule=s.depformer_schedule)
+            schedule=s.depformer_schedule, quantize=quantize)
         self.batch: int | None = None
 
     # ------------------------------------------------------------------ state (lm.py:604-666)
@@ -173,7 +174,10 @@ class LMOracle:
         x = t if x is None else x + t
         out = tr.forward(self.sd, "transformer", self.main_spec, x, self.main_state)
         out = tr.apply_norm(s.norm, out, self.sd, "out_norm")
-        logits = F.linear(out, self.sd["text_linear.weight"], self.sd.get("text_linear.bias"))
+        if self.quantize:
+            logits = tr.linear(out, self.sd["text_linear.weight"], True)
+        else:
+            logits = F.linear(out, self.sd["text_linear.weight"], self.sd.get("text_linear.bias"))
         return out, logits[:, None]
 
     def forward_depformer(self, k: int, prev: torch.Tensor, transformer_out: torch.Tensor,
@@ -183,11 +187,14 @@ class LMOracle:
         in_idx = 0
         if s.depformer_multi_linear:
             in_idx = k if s.depformer_schedule is None else s.depformer_schedule[k]
-        x = F.linear(transformer_out, self.sd[f"depformer_in.{in_idx}.weight"])
+        x = tr.linear(transformer_out, self.sd[f"depformer_in.{in_idx}.weight"], self.quantize)
         emb = scaled_embedding(self.sd, "depformer_text_emb" if k == 0 else f"depformer_emb.{k - 1}", prev)
         x = x + emb
         y = tr.forward(self.sd, "depformer", self.dep_spec, x, dep_state)
-        logits = F.linear(y, self.sd[f"linears.{k}.weight"], self.sd.get(f"linears.{k}.bias"))
+        if self.quantize:
+            logits = tr.linear(y, self.sd[f"linears.{k}.weight"], True)
+        else:
+            logits = F.linear(y, self.sd[f"linears.{k}.weight"], self.sd.get(f"linears.{k}.bias"))
         return logits[:, None]
 
     def depformer_step(self, text_token: torch.Tensor, transformer_out: torch.Tensor,

@@ -31,6 +31,7 @@ class TransformerSpec:
     weights_per_step: int = 0
     schedule: tp.Optional[tp.List[int]] = None
     positional_scale: float = 1.0
+    quantize: bool = False                # every nn.Linear replaced by QLinear (transformer.py:885-888, utils/quantize.py)
 
 
 @dataclass
@@ -164,16 +165,24 @@ def ring_append(ls: LayerState, k: torch.Tensor, v: torch.Tensor, exec_mask: tor
     return torch.where(empty, torch.full_like(positions, -1), positions)
 
 
+def linear(x: torch.Tensor, w: torch.Tensor, quantize: bool = False) -> torch.Tensor:
+    """``nn.Linear`` (bias-free on this path) or, for a quantised LM, ``QLinear.forward`` (oracle/quant.py)."""
+    if quantize:
+        from .quant import qlinear
+        return qlinear(x, w)
+    return F.linear(x, w)
+
+
 def _per_step_linear(sd: dict, fmt: str, spec: TransformerSpec, x: torch.Tensor, offset_cpu: int):
     """``apply_weights_per_step`` (transformer.py:291-318) for F.linear weights named by ``fmt``."""
     if not spec.weights_per_step:
-        return F.linear(x, sd[fmt.format(i=0)])
+        return linear(x, sd[fmt.format(i=0)], spec.quantize)
     outs = []
     for t in range(x.shape[1]):
         i = t + offset_cpu
         if spec.schedule is not None:
             i = spec.schedule[i]
-        outs.append(F.linear(x[:, t:t + 1], sd[fmt.format(i=i)]))
+        outs.append(linear(x[:, t:t + 1], sd[fmt.format(i=i)], spec.quantize))
     return torch.cat(outs, 1)
 
 
@@ -201,12 +210,12 @@ def attention(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, ls: Laye
     return out
 
 
-def gated_ffn(w_in: torch.Tensor, w_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def gated_ffn(w_in: torch.Tensor, w_out: torch.Tensor, x: torch.Tensor, quantize: bool = False) -> torch.Tensor:
     """gating.py:13-22 with SiLU: W_out (silu(h[:H]) * h[H:]), h = W_in x."""
-    h = F.linear(x, w_in)
+    h = linear(x, w_in, quantize)
     B, T, _ = h.shape
     h = h.view(B, T, 2, -1)
-    return F.linear(F.silu(h[..., 0, :]) * h[..., 1, :], w_out)
+    return linear(F.silu(h[..., 0, :]) * h[..., 1, :], w_out, quantize)
 
 
 def feed_forward(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, offset_cpu: int):
@@ -214,14 +223,14 @@ def feed_forward(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, offse
     if spec.gating == "none":
         return F.linear(F.gelu(F.linear(x, sd[p + ".linear1.weight"])), sd[p + ".linear2.weight"])
     if not spec.weights_per_step:
-        return gated_ffn(sd[p + ".gating.linear_in.weight"], sd[p + ".gating.linear_out.weight"], x)
+        return gated_ffn(sd[p + ".gating.linear_in.weight"], sd[p + ".gating.linear_out.weight"], x, spec.quantize)
     outs = []
     for t in range(x.shape[1]):
         i = t + offset_cpu
         if spec.schedule is not None:
             i = spec.schedule[i]
         outs.append(gated_ffn(sd[f"{p}.gating.{i}.linear_in.weight"],
-                              sd[f"{p}.gating.{i}.linear_out.weight"], x[:, t:t + 1]))
+                              sd[f"{p}.gating.{i}.linear_out.weight"], x[:, t:t + 1], spec.quantize))
     return torch.cat(outs, 1)
 
 

@@ -36,7 +36,7 @@ def test_attributes_match_reference(lm):
     assert (lm.zero_token_id, lm.ungenerated_token_id, lm.initial_token_id) == (-1, -2, 64)
 
 
-def _run(lm, tiny, sampling, use_graph, golden):
+def _run(lm, tiny, sampling, use_graph, golden, quantize=False):
     """Teacher-synchronised comparison: the oracle is stepped on the GPU's own token stream, so a
     single near-tie flip does not make every later step incomparable."""
     from moshi_b200.models import LMGen
@@ -46,7 +46,7 @@ def _run(lm, tiny, sampling, use_graph, golden):
     gen = LMGen(lm, use_sampling=sampling, temp=0.8, temp_text=0.7)
     gen.use_graph = use_graph
     # ties among bf16 logits are ranked by token id on the GPU; torch.topk's order is unspecified
-    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=sampling, tie_break="index")
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=sampling, tie_break="index", quantize=quantize)
     orc.streaming(B)
     diverged = torch.zeros(B, dtype=torch.bool)    # rows whose token history left the reference trajectory
     torch.manual_seed(scenarios.LM_NOISE_SEED)

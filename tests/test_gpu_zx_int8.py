@@ -86,3 +86,40 @@ def test_int8_gated_silu(M, H, K):
     # silu goes through expf on the device: one bf16 ulp of slack on a handful of entries
     torch.testing.assert_close(y.float().cpu(), want, rtol=8e-3, atol=1e-3)
     assert (y.float().cpu() != want).float().mean() < 0.02
+
+
+@pytest.mark.parametrize("sampling,use_graph", [(False, False), (True, True)])
+def test_quantized_lm_steps_match_quantized_oracle(sampling, use_graph):
+    """LMModel(quantize=True) (lm.py:107,242-243): every linear of the Temporal and Depth transformers, the depformer
+    input projections and the logit heads run int8 x int8 on the tensor cores.  Each linear is exact given its input,
+    so against the oracle's QLinear restatement the step differs only by the bf16 rounding noise of the other ops,
+    amplified by the activation quantiser (one int8 step = absmax/127 of a row)."""
+    import dataclasses
+
+    from moshi_b200.config import tiny_lm_config
+    from moshi_b200.models import LMModel
+    from moshi_b200.synth import synth_lm_state_dict
+    from oracle import scenarios
+    from tests.test_gpu_lm import _run
+    cfg = dataclasses.replace(tiny_lm_config(), quantize=True)
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    lm = LMModel(cfg, sd, device="cuda")
+    m, t, _, _, worst, sm, st = _run(lm, (cfg, sd), sampling, use_graph, None, quantize=True)
+    assert worst < 0.2, worst
+    if sampling:
+        assert st > 0 and sm >= st - 1          # the sampler itself is exact on the GPU's own logits
+    else:
+        assert m / t > 0.9
+    # quantisation error against the bf16 model stays small on this model (sanity: the int8 path is not garbage)
+    plain = LMModel(tiny_lm_config(), sd, device="cuda")
+    from moshi_b200.models import LMGen
+    outs = []
+    for model in (lm, plain):
+        gen = LMGen(model, use_sampling=False)
+        codes = scenarios.lm_input_codes(cfg, scenarios.LM_B, 1)
+        with gen.streaming(scenarios.LM_B):
+            gen.step(codes[0].cuda())       # first step only: later steps feed back each model's own tokens
+            outs.append(gen.read_buffer("text_logits", torch.bfloat16, (scenarios.LM_B, cfg.text_card)).float().cpu())
+    rel = (outs[0] - outs[1]).abs().max().item() / outs[1].abs().max().item()
+    print(f"int8 vs bf16 text logits, first step: rel-to-max {rel:.3e}")
+    assert rel < 0.08

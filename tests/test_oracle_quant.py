@@ -33,3 +33,24 @@ def test_qlinear_is_a_faithful_linear_and_exact_in_integers():
     assert torch.equal(acc.double(), qx.double() @ qw.double().t())
     assert torch.equal(y, acc.float() * ((sa[:, None] * sw[None, :]) * torch.tensor(float(quant.INV_127_SQ))))
     assert quant.qlinear(x, w).dtype == torch.bfloat16
+
+
+def test_quantized_lm_oracle_steps_close_to_bf16():
+    """LMOracle(quantize=True) routes every linear through QLinear; its first-step logits stay close to the bf16 model's
+    (later steps feed back each model's own greedy tokens and drift apart)."""
+    from moshi_b200.config import tiny_lm_config
+    from moshi_b200.synth import synth_lm_state_dict
+    from oracle import scenarios
+    from oracle.lm import LMOracle, LMSpec
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    codes = scenarios.lm_input_codes(cfg, 2, 3)
+    logits = []
+    for q in (False, True):
+        orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, quantize=q)
+        orc.streaming(2)
+        dbg = {}
+        orc.step(codes[0][:2], None, None, debug=dbg)
+        logits.append(dbg["text_logits"].float())
+    rel = (logits[0] - logits[1]).abs().max() / logits[0].abs().max()
+    assert 0 < rel < 0.08, rel
