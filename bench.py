@@ -282,7 +282,7 @@ def b200_arm(args) -> None:
     from moshi_b200 import _lib
     from moshi_b200.config import MOSHI_7B
     from moshi_b200.models import LMGen, loaders
-    from moshi_b200.serving import barrier, init_distributed, max_over_ranks, sum_over_ranks
+    from moshi_b200.serving import DialogueService, barrier, init_distributed, max_over_ranks, sum_over_ranks
 
     rank, world = init_distributed()
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -303,17 +303,16 @@ def b200_arm(args) -> None:
     B = max(1, min(args.sessions or cap, cap))
     kv_fill = MOSHI_7B.context if args.kv_fill < 0 else min(args.kv_fill, MOSHI_7B.context)
 
-    gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
-    mimi.streaming_forever(B)
-    gen.streaming_forever(B)
+    # the public per-frame API (host buffers in and out): DialogueService.step -> b200_frame_step; its LMGen / Mimi
+    # streaming handles are the ones the device-resident leg drives directly
+    svc = DialogueService(B, lm, mimi, use_sampling=True, temp=0.8, temp_text=0.7)
+    gen = svc.lm_gen
     gen.assume_fill(kv_fill)      # steady state: every session already holds `kv_fill` frames of history
 
     g = torch.Generator().manual_seed(4242 + rank)
     n_buf = 4
     pcm_host = [(0.1 * torch.randn(B, 1, 1920, generator=g)).pin_memory() for _ in range(n_buf)]
     pcm_dev = [p.to(device) for p in pcm_host]
-    out_pcm_host = torch.empty(B, 1, 1920).pin_memory()
-    out_tok_host = torch.empty(B, 9, 1, dtype=torch.int64).pin_memory()
     lm_ev = []
 
     def frame(pcm, timed_lm: bool = False):
@@ -349,17 +348,19 @@ def b200_arm(args) -> None:
         ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         lm_ms = sum(a.elapsed_time(b) for a, b in lm_ev) / len(lm_ev)
 
-        # ---- end to end: host PCM in, host PCM + tokens out, every step ------------------------
+        # ---- end to end: host PCM in, host PCM + tokens out, every step, through the frame service ----
+        import numpy as np
+        pcm_np = [p.reshape(-1).numpy() for p in pcm_host]
+        out_pcm_np = np.zeros((B, 1920), dtype=np.float32)
+        out_tok_np = np.zeros((B, 9), dtype=np.int64)
+        flags_np = np.zeros(B, dtype=np.uint8)
+
         def e2e_step(i):
-            pcm = pcm_host[i % n_buf].to(device, non_blocking=True)
-            toks, out = frame(pcm)
-            out_pcm_host.copy_(out, non_blocking=True)
-            if toks is not None:
-                out_tok_host.copy_(toks, non_blocking=True)
-            torch.cuda.synchronize(device)
+            svc.step(pcm_np[i % n_buf], out_pcm_np, out_tok_np, flags_out=flags_np)    # returns after its one host wait
 
         for i in range(2):               # first use of the pinned staging buffers / copy engines is not steady state
             e2e_step(i)
+        assert flags_np.all(), "every session must have produced a frame"
         barrier()
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
@@ -376,8 +377,7 @@ def b200_arm(args) -> None:
     roof = gemm_roof = None
     if rank == 0:
         # release the sessions' state (150+ GB of KV rings) before allocating the stand-alone kernel operands
-        gen._stop()
-        mimi._stop()
+        svc.close()
         torch.cuda.empty_cache()
         roof = _dominant_kernel_roofline(B, kv_fill, device)
         gemm_roof = None if args.quantize else _gemm_roofline(B, device)
@@ -403,7 +403,8 @@ def b200_arm(args) -> None:
                    "l2": "inputs larger than L2 (15.4 GB of weights + KV ring streamed every step)",
                    "frames_per_s": total_sessions * 1e3 / ms_dev},
         "e2e": {"value": e2e_value, "unit": "sessions", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 1920 * 4,
-                "d2h_bytes_per_step": B * 1920 * 4 + B * 9 * 8},
+                "d2h_bytes_per_step": B * 1920 * 4 + B * 9 * 8 + B,
+                "api": "moshi_b200.serving.DialogueService.step -> b200_frame_step (numpy host buffers, one host wait per frame)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof,

@@ -211,6 +211,33 @@ int b200_lm_assume_fill(b200_lm* h, int fill);
 int b200_lm_set_graph(b200_lm* h, int enable);
 
 /* ------------------------------------------------------------------------------------------ */
+/* One dialogue frame for every session slot: host PCM in, host PCM + tokens out, one host wait  */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces the per-frame body of the reference's callers: moshi/moshi/server.py:120-147 (chunk -> mimi.encode ->
+ * lm_gen.step -> mimi.decode -> main_pcm.cpu(), tokens[0,0,0].item(): two blocking reads per frame, :82-86) and
+ * rust/moshi-server/batched_asr.py:138-215 (ASRService.step: slot updates -> reset / exec masks -> encode -> step ->
+ * host copies), which the Rust server binds through py_basr_module.rs:243-256.  Slot updates use the values of
+ * batched_asr.py:23-30 (UpdateFlags). */
+typedef struct b200_frame b200_frame;
+#define B200_SLOT_IDLE 0      /* UpdateFlags.NODATA: the slot does not execute from this frame on            */
+#define B200_SLOT_ACTIVE (-1) /* UpdateFlags.ACTIVE: the slot executes from this frame on                     */
+#define B200_SLOT_RESET (-2)  /* UpdateFlags.RESET: reset the slot's streaming state, then execute             */
+                              /* > 0 (end-of-stream marker): the slot keeps its current activity               */
+/* Both handles must be streaming with `batch` rows on `stream`; n_codebooks = the codec's codebooks = dep_q. */
+int b200_frame_create(b200_mimi* mimi, b200_lm* lm, int batch, int n_codebooks, int dep_q, int frame_size, void* stream,
+                      b200_frame** out);
+int b200_frame_destroy(b200_frame* f);
+/*   pcm_in_host     f32 [B, frame_size]   one 80 ms frame per slot (idle slots: ignored)
+ *   updates_host    i32 [B] or NULL (= no change; every slot active after create)
+ *   noise_host / noise_dev  f32 [B, b200_lm_noise_per_row] Exp(1) draws, host or device; both NULL = greedy only
+ *   pcm_out_host    f32 [B, frame_size]   decoded frame; silence for rows with ready == 0
+ *   tokens_out_host i64 [B, dep_q + 1]    LMGen.step output (row 0 text); -2 for rows that are not ready
+ *   ready_out_host  u8  [B] or NULL       1 = the row executed and is past its max_delay warm-up (lm.py:774-782)
+ * The decoder only advances for ready rows (server.py:139-142 skips mimi.decode while step() returns None). */
+int b200_frame_step(b200_frame* f, const float* pcm_in_host, const int32_t* updates_host, const float* noise_host,
+                    const float* noise_dev, float* pcm_out_host, int64_t* tokens_out_host, uint8_t* ready_out_host);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Kernel-level entry points (used by the parity tests; same kernels the handles launch)        */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -89,6 +89,10 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_algorithmic_bytes": (C.c_int64, [_P, _I]),
     "b200_lm_assume_fill": (_I, [_P, _I]),
     "b200_lm_set_graph": (_I, [_P, _I]),
+    # one frame for every session slot, host buffers
+    "b200_frame_create": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_P)]),
+    "b200_frame_destroy": (_I, [_P]),
+    "b200_frame_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     # kernel-level
     "b200_op_linear_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_op_packed_bytes": (C.c_int64, [_I, _I, _I, _I]),

@@ -687,6 +687,8 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const __nv_bfloat16*
   const int row = blockIdx.x;
   const __nv_bfloat16* xr = x + (long long)row * ldx;
   float mx = 0.f;
+  pdl_wait();          // x comes from the preceding kernel; xq / sa may still be read by the GEMM before that one
+  pdl_trigger();       // the GEMM that follows starts streaming its weight tiles while the rows are quantised
   for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
     const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -793,9 +795,16 @@ int sk_quant_pack_weights(const __nv_bfloat16* w, void* out_tiles, float* out_sc
   return check_launch("quant_pack_tiles");
 }
 
-int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream) {
+int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream, int pdl) {
   if (K % 8 || ldx % 8) B200_FAIL(B200_ERR_SHAPE, "sk_quantize_rows: K and the row stride must be multiples of 8");
-  quantize_rows_kernel<<<M, 256, 0, stream>>>(x, ldx, static_cast<int8_t*>(xq), sa, K);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)M); cfg.blockDim = dim3(256); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, quantize_rows_kernel, x, ldx, static_cast<int8_t*>(xq), sa, K));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("quantize_rows");
 }

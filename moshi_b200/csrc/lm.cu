@@ -118,9 +118,8 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
     t.smem_budget = h->sk_smem;
     if (h->cfg.quantize) {       // QLinear.forward (utils/quantize.py:22-40): row-wise int8 activations, int8 x int8 -> int32
       if (!w_scales) B200_FAIL(B200_ERR_STATE, "quantised LM: linear without weight scales");
-      B200_TRY(tc::sk_quantize_rows(x, ldx, h->xq, h->xq_scale, M, K, h->body));
+      B200_TRY(tc::sk_quantize_rows(x, ldx, h->xq, h->xq_scale, M, K, h->body, h->pdl));
       t.xq = h->xq; t.sa = h->xq_scale; t.sw = w_scales;
-      t.pdl = 0;
     }
     return tc::sk_linear(h->plans, x, ldx, w, y, ldy, res, ldr, M, N, K, epi, gate_rows, h->sk_ws, h->sk_counters, t, h->body);
   }

@@ -59,3 +59,94 @@ def barrier() -> None:
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------
+# One frame for every session slot of this GPU (the caller's per-frame plumbing)
+# ---------------------------------------------------------------------------------------------------
+NODATA, ACTIVE, RESET = 0, -1, -2      # UpdateFlags of rust/moshi-server/batched_asr.py:23-30
+
+
+class DialogueService:
+    """Batched full-duplex frame step with the calling convention of ``ASRService.step``
+    (``rust/moshi-server/batched_asr.py:100-215``, bound by ``py_basr_module.rs``): numpy host buffers in and
+    out, per-slot update flags, state owned by the service.  The body of the reference's loop
+    (``server.py:120-147``: ``mimi.encode -> lm_gen.step -> mimi.decode -> .cpu()``) runs below the C ABI as one
+    stream-ordered chain with a single host wait (``b200_frame_step``); masks and the "row is past its delay
+    warm-up" decision are built on the device.
+    """
+
+    def __init__(self, batch_size: int, lm, mimi, use_sampling: bool = True, temp: float = 0.8, temp_text: float = 0.7,
+                 top_k: int = 250, top_k_text: int = 25):
+        import ctypes as C
+
+        from . import _lib
+        from .models import LMGen
+        self.batch_size = batch_size
+        self.lm, self.mimi = lm, mimi
+        self.lm_gen = LMGen(lm, use_sampling=use_sampling, temp=temp, temp_text=temp_text, top_k=top_k, top_k_text=top_k_text,
+                            support_out_of_sync=True)
+        self.lm_gen.streaming_forever(batch_size)
+        self.mimi.streaming_forever(batch_size)
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.b200_frame_create(mimi._h, lm._h, batch_size, mimi.num_codebooks, lm.dep_q, mimi.frame_size,
+                                               _lib.current_stream(lm.device), C.byref(self._h)))
+        self.frame_size = mimi.frame_size
+        self.tokens_per_slot = lm.dep_q + 1
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b200_frame_destroy(self._h)
+            self._h = None
+            self.lm_gen._stop()
+            self.mimi._stop()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _np_ptr(a, dtype, numel: int, name: str):
+        import ctypes as C
+
+        import numpy as np
+        if a is None:
+            return C.c_void_p(0)
+        if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"] or a.size != numel:
+            raise AssertionError(f"{name}: expected a C-contiguous {np.dtype(dtype).name} array of {numel} elements")
+        return C.c_void_p(a.ctypes.data)
+
+    def step(self, batch_pcm, pcm_out, tokens_out, updates=None, flags_out=None, noise=None) -> None:
+        """``batch_pcm`` f32 [B * frame_size] (as the Rust harness passes it, ``batched_asr.py:193-196``) -> ``pcm_out``
+        f32 [B, frame_size], ``tokens_out`` i64 [B, dep_q + 1], ``flags_out`` u8 [B] (1 = the slot produced a frame).
+        ``updates``: per-slot NODATA / ACTIVE / RESET (or a positive marker), None = unchanged.
+        ``noise``: f32 [B, noise_per_row] Exp(1) draws (numpy or CUDA tensor); None = drawn on the device."""
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        B = self.batch_size
+        upd = None
+        if updates is not None:
+            upd = np.ascontiguousarray(np.asarray(updates, dtype=np.int32))
+            assert upd.shape == (B,), f"expected {B} slot updates"
+        noise_host = noise_dev = C.c_void_p(0)
+        keep = None
+        if noise is None:
+            keep = self.lm_gen.draw_noise()
+            noise_dev = _lib.ptr(keep)
+        elif isinstance(noise, np.ndarray):
+            noise_host = self._np_ptr(noise, np.float32, B * self._lib.b200_lm_noise_per_row(self.lm._h), "noise")
+        else:
+            keep = noise.to(device=self.lm.device, dtype=__import__("torch").float32).contiguous()
+            noise_dev = _lib.ptr(keep)
+        _lib.check(self._lib.b200_frame_step(
+            self._h, self._np_ptr(batch_pcm, np.float32, B * self.frame_size, "batch_pcm"),
+            self._np_ptr(upd, np.int32, B, "updates"), noise_host, noise_dev,
+            self._np_ptr(pcm_out, np.float32, B * self.frame_size, "pcm_out"),
+            self._np_ptr(tokens_out, np.int64, B * self.tokens_per_slot, "tokens_out"),
+            self._np_ptr(flags_out, np.uint8, B, "flags_out")))
