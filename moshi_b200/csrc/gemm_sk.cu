@@ -175,6 +175,11 @@ __device__ __forceinline__ float acc_value(const SkParams& p, uint32_t bits, int
   return (float)(int)bits * (p.sa[m] * p.sw[nw] * (1.f / 16129.f));
 }
 
+// sum of two partial accumulator words: fp32 values, or (int8 path) int32 bit patterns carried in float registers
+__device__ __forceinline__ float part_add(bool i8, float a, float b) {
+  return i8 ? __int_as_float(__float_as_int(a) + __float_as_int(b)) : a + b;
+}
+
 template <int EPI>
 __device__ __forceinline__ float epilogue_value(const SkParams& p, float a, float b, int m, int n) {
   if (EPI == EPI_STORE) return a;
@@ -396,15 +401,25 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const SkParams p) {
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                av[4 * j] += v[j].x; av[4 * j + 1] += v[j].y; av[4 * j + 2] += v[j].z; av[4 * j + 3] += v[j].w;
-                if (EPI == EPI_GATE) { bv[4 * j] += u[j].x; bv[4 * j + 1] += u[j].y; bv[4 * j + 2] += u[j].z; bv[4 * j + 3] += u[j].w; }
+                const bool q8 = p.i8 != 0;
+                av[4 * j] = part_add(q8, av[4 * j], v[j].x); av[4 * j + 1] = part_add(q8, av[4 * j + 1], v[j].y);
+                av[4 * j + 2] = part_add(q8, av[4 * j + 2], v[j].z); av[4 * j + 3] = part_add(q8, av[4 * j + 3], v[j].w);
+                if (EPI == EPI_GATE) {
+                  bv[4 * j] = part_add(q8, bv[4 * j], u[j].x); bv[4 * j + 1] = part_add(q8, bv[4 * j + 1], u[j].y);
+                  bv[4 * j + 2] = part_add(q8, bv[4 * j + 2], u[j].z); bv[4 * j + 3] = part_add(q8, bv[4 * j + 3], u[j].w);
+                }
               }
             }
             if (n_ok && !p.stream_only) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int m = m0 + j;
-                if (m < p.M) p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, av[j], bv[j], m, n));
+                if (m < p.M) {
+                  // fp32 zero and int32 zero share a bit pattern, so the accumulators start right on both paths
+                  const float a = acc_value(p, __float_as_uint(av[j]), m, n);
+                  const float b = EPI == EPI_GATE ? acc_value(p, __float_as_uint(bv[j]), m, p.gate_rows + n) : 0.f;
+                  p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(epilogue_value<EPI>(p, a, b, m, n));
+                }
               }
             }
           }
@@ -433,6 +448,7 @@ struct CkParams {
   __nv_bfloat16* y; long long ldy;
   const __nv_bfloat16* res; long long ldr;
   uint32_t tmem_cols, stage_bytes;
+  int i8; const float* sa; const float* sw;      // int8 operands: partials are exact int32, scaled once after the reduction
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
@@ -507,13 +523,13 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
           mbar_expect_tx(full0 + 8 * s, p.stage_bytes);
           bulk_load(sa, src + (size_t)i * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
         }
-        tma_load_2d(sa + TILE_BYTES, &tmap_x, full0 + 8 * s, (kb0 + i) * BLOCK_K, 0);
+        tma_load_2d(sa + TILE_BYTES, &tmap_x, full0 + 8 * s, (kb0 + i) * (p.i8 ? 2 * BLOCK_K : BLOCK_K), 0);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_ROWS, p.Mpad);
+      const uint32_t idesc = p.i8 ? make_idesc_i8(BLOCK_ROWS, p.Mpad) : make_idesc(BLOCK_ROWS, p.Mpad);
       int s = 0; uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full0 + 8 * s, ph);
@@ -521,8 +537,11 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
         const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
         const uint32_t sb = sa + TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, (kb == kb0 && k == 0) ? 0u : 1u);
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t accum = (kb == kb0 && k == 0) ? 0u : 1u;
+          if (p.i8) umma_i8(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, accum);
+          else umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, accum);
+        }
         umma_commit(empty0 + 8 * s);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -578,17 +597,40 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
           }
         }
         float acc[8];
+        if (p.i8) {                            // exact: the partials are int32 bit patterns
+          int isum[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int r = 0; r < p.CS; ++r) {       // rank order: the sum does not depend on which rank does it
-          if (r == me) {
+          for (int j = 0; j < 8; ++j) isum[j] = 0;
+          for (int r = 0; r < p.CS; ++r) {
+            if (r == me) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += own[c0 + j];
-          } else {
-            const float4 a = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0);
-            const float4 b = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0 + 4);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+              for (int j = 0; j < 8; ++j) isum[j] += __float_as_int(own[c0 + j]);
+            } else {
+              const int4 a = *reinterpret_cast<const int4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0);
+              const int4 b = *reinterpret_cast<const int4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0 + 4);
+              isum[0] += a.x; isum[1] += a.y; isum[2] += a.z; isum[3] += a.w;
+              isum[4] += b.x; isum[5] += b.y; isum[6] += b.z; isum[7] += b.w;
+            }
+          }
+          const float swn = n_ok ? p.sw[n] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int m = me * p.Wc + c0 + j;
+            acc[j] = m < p.M ? (float)isum[j] * (p.sa[m] * swn * (1.f / 16129.f)) : 0.f;     // same expression as acc_value()
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int r = 0; r < p.CS; ++r) {       // rank order: the sum does not depend on which rank does it
+            if (r == me) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += own[c0 + j];
+            } else {
+              const float4 a = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0);
+              const float4 b = *reinterpret_cast<const float4*>(recv_generic + (size_t)(r * BLOCK_ROWS + row) * ldw + c0 + 4);
+              acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+              acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+            }
           }
         }
 #pragma unroll
@@ -852,8 +894,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
   const bool i8 = tune.xq != nullptr;
   if (i8 && (K % 16 || !tune.sa || !tune.sw)) B200_FAIL(B200_ERR_SHAPE, "int8 GEMM: K must be a multiple of 16 and both scale vectors given");
-  if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32 && !i8) {
-    const int n_tiles = (N + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {
+    const int n_tiles = (N + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = i8 ? (K + 127) / 128 : (K + BLOCK_K - 1) / BLOCK_K;
     int cs = 1;
     while (cs < 8 && n_tiles * cs * 2 <= g_sms && num_kb / (cs * 2) >= 4) cs *= 2;
     if (tune.cluster > 0) cs = tune.cluster;
@@ -867,7 +909,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
         p.num_kb = num_kb; p.kb_per = (num_kb + cs - 1) / cs;
         p.wt = static_cast<const uint8_t*>(w_tiles);
         p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
-        p.stage_bytes = (uint32_t)(TILE_BYTES + p.Mpad * BLOCK_K * 2);
+        p.i8 = i8 ? 1 : 0; p.sa = tune.sa; p.sw = tune.sw;
+        p.stage_bytes = (uint32_t)(TILE_BYTES + p.Mpad * BLOCK_K * 2);      // 128 bytes of K per row, bf16 or int8
         const size_t recv_bytes = (size_t)cs * BLOCK_ROWS * (p.Wc + 4) * 4;
         int stages = (int)((200 * 1024 - recv_bytes) / p.stage_bytes);
         if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -878,7 +921,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
           while (pow2 < (uint32_t)p.Mpad) pow2 <<= 1;
           p.tmem_cols = pow2;
           const CUtensorMap* mx = nullptr;
-          B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, 2, &mx));
+          if (i8) B200_TRY(x_map(cache, tune.xq, K, M, K, p.Mpad, 1, &mx));
+          else B200_TRY(x_map(cache, x, ldx, M, K, p.Mpad, 2, &mx));
           const size_t smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64 + recv_bytes + 64;
           cudaLaunchConfig_t cfg;
           memset(&cfg, 0, sizeof(cfg));
@@ -916,7 +960,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   if (tune.grid == 0 && grid > (p.n_tiles * p.num_kb) / 8) grid = (p.n_tiles * p.num_kb) / 8 > 0 ? (p.n_tiles * p.num_kb) / 8 : 1;
   // Cutting a tile into S pieces moves S fp32 partials of [128 x Mpad] through L2 (written + read back): allow it
   // only while that stays under half of the tile's weight bytes, i.e. S <= 8 * num_kb / Mpad.
-  int s_max = (tune.no_split || i8) ? 1 : (8 * p.num_kb) / p.Mpad;      // int8: whole tiles (exact integer sums)
+  int s_max = tune.no_split ? 1 : (8 * p.num_kb) / p.Mpad;      // int8 partials are int32 and add exactly
   // measured on B200 (profiles/r01_c_kbench.jsonl): with more than 32 sessions the publish / count / re-read protocol
   // costs more than the idle SMs it recovers, so tiles stay whole there
   if (p.Mpad > 32 && tune.force_split == 0) s_max = 1;

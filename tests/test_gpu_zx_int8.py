@@ -58,7 +58,7 @@ def test_int8_linear_store_is_exact(M, N, K):
     assert (y.float().cpu() - ref).abs().max() < 0.05 * ref.abs().max() + 0.05
 
 
-@pytest.mark.parametrize("M,N,K", [(5, 512, 256), (96, 4096, 4096)])
+@pytest.mark.parametrize("M,N,K", [(5, 512, 256), (17, 4096, 4096), (96, 4096, 4096), (104, 4096, 11264), (130, 1024, 2816)])
 def test_int8_linear_residual_add(M, N, K):
     from moshi_b200 import _lib
     lib = _lib.lib()
