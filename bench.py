@@ -205,7 +205,7 @@ def _event_time(fn, iters: int = 10, warm: int = 3) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
+def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: bool = False) -> dict:
     """The dominant kernel of the step at serving batch is the temporal ring-attention decode (32 launches per
     step, each streaming 2*B*32*fill*128 bf16 of K/V; profiles/ has its share of the step).  Timed here alone
     with CUDA events on the launching stream, on K/V rings of the bench's own shape (4.7 GB at B=96: far
@@ -214,8 +214,14 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
     from moshi_b200 import _lib
     lib = _lib.lib()
     H, cap, D = 32, 3000, 128
-    k = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
-    v = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
+    if fp8:
+        k = torch.randint(0, 120, (B, H, cap, D), device=device, dtype=torch.uint8)      # finite positive e4m3 bit patterns
+        v = torch.randint(0, 120, (B, H, cap, D), device=device, dtype=torch.uint8)
+        ks = torch.full((B, H, cap), 0.01, device=device)
+        vs = torch.full((B, H, cap), 0.01, device=device)
+    else:
+        k = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
+        v = torch.empty(B, H, cap, D, device=device, dtype=torch.bfloat16).normal_()
     qkv = torch.randn(B, 3 * H * D, device=device).bfloat16()
     out = torch.empty(B, H * D, device=device, dtype=torch.bfloat16)
     offs = torch.full((B,), max(kv_fill - 1, 0) + (cap if kv_fill >= cap else 0), dtype=torch.int64, device=device)
@@ -223,11 +229,18 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
     stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     def fn():
-        _lib.check(lib.b200_op_attn_step(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
-                                         _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
+        if fp8:
+            _lib.check(lib.b200_op_attn_step_f8(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(ks), _lib.ptr(vs), _lib.ptr(out),
+                                                _lib.ptr(offs), _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
+        else:
+            _lib.check(lib.b200_op_attn_step(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
+                                             _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
     ms = _event_time(fn)
     n_keys = min(max(kv_fill, 1), cap)
-    alg = 2 * B * H * n_keys * D * 2 + 6 * B * H * D * 2      # K,V rings once + qkv in, K/V append and output out
+    if fp8:
+        alg = 2 * B * H * n_keys * (D + 4) + 4 * B * H * D * 2 + 2 * B * H * (D + 4)
+    else:
+        alg = 2 * B * H * n_keys * D * 2 + 6 * B * H * D * 2      # K,V rings once + qkv in, K/V append and output out
     peak, src = _peaks()
     gbs = alg / (ms * 1e-3) / 1e9
     del k, v
@@ -235,13 +248,13 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device) -> dict:
     # the kernel reads every session's K/V exactly once, so bytes per launch scale with sessions x keys
     traffic, traffic_src = None, None
     cap_file = ROOT / "profiles" / "attn_step_ncu.json"
-    if cap_file.exists():
+    if cap_file.exists() and not fp8:
         cap_d = json.loads(cap_file.read_text())
         per_key_session = (cap_d["dram_bytes_read"] + cap_d["dram_bytes_write"]) / (cap_d["B"] * cap_d["keys"])
         traffic = per_key_session * B * n_keys
         traffic_src = ("ncu --set full at B=%d, %d keys (%s): dram read+write / launch scaled by sessions x keys"
                        % (cap_d["B"], cap_d["keys"], cap_d["source"]))
-    return {"traffic": traffic, "traffic_source": traffic_src, "kernel": "lm::attn_step_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 bf16" % (B, n_keys),
+    return {"traffic": traffic, "traffic_source": traffic_src, "kernel": "lm::attn_step%s_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 %s" % ("_f8" if fp8 else "", B, n_keys, "e4m3 + fp32 scale per key" if fp8 else "bf16"),
             "bound": "hbm", "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak,
             "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
 
@@ -298,14 +311,16 @@ def b200_arm(args) -> None:
 
     # sessions per GPU: the full-context bf16 KV ring (1.573 GB/session) is what bounds it
     free, total = torch.cuda.mem_get_info(device)
-    per_session = KV_BYTES_PER_SESSION_STEP * MOSHI_7B.context + 40e6
-    cap = int((free - 6e9) // per_session)
+    fp8 = args.kv_dtype == "fp8_e4m3"
+    kv_step = (32 * 2 * (4096 + 32 * 4)) if fp8 else KV_BYTES_PER_SESSION_STEP     # e4m3 bytes + one fp32 scale per head
+    per_session = kv_step * MOSHI_7B.context + 40e6
+    cap = min(int((free - 6e9) // per_session), 256)      # the GEMM path takes at most 256 activation rows
     B = max(1, min(args.sessions or cap, cap))
     kv_fill = MOSHI_7B.context if args.kv_fill < 0 else min(args.kv_fill, MOSHI_7B.context)
 
     # the public per-frame API (host buffers in and out): DialogueService.step -> b200_frame_step; its LMGen / Mimi
     # streaming handles are the ones the device-resident leg drives directly
-    svc = DialogueService(B, lm, mimi, use_sampling=True, temp=0.8, temp_text=0.7)
+    svc = DialogueService(B, lm, mimi, use_sampling=True, temp=0.8, temp_text=0.7, kv_dtype=args.kv_dtype)
     gen = svc.lm_gen
     gen.assume_fill(kv_fill)      # steady state: every session already holds `kv_fill` frames of history
 
@@ -379,7 +394,7 @@ def b200_arm(args) -> None:
         # release the sessions' state (150+ GB of KV rings) before allocating the stand-alone kernel operands
         svc.close()
         torch.cuda.empty_cache()
-        roof = _dominant_kernel_roofline(B, kv_fill, device)
+        roof = _dominant_kernel_roofline(B, kv_fill, device, fp8)
         gemm_roof = None if args.quantize else _gemm_roofline(B, device)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -399,7 +414,8 @@ def b200_arm(args) -> None:
                                "LMGen.step (temp 0.8/0.7, top-k 250/25) "
                                "-> Mimi streaming decode; one 80 ms frame for every session per step",
                    "sessions_per_gpu": B, "sessions_total": total_sessions, "kv_fill": kv_fill,
-                   "kv_ring": "bf16, capacity 3000 (reference context)", "parallelism": f"replicas x{world}",
+                   "kv_ring": ("e4m3 + one fp32 scale per (head, slot), capacity 3000 -- OPT-IN, not the reference's numerics" if fp8
+                               else "bf16, capacity 3000 (reference context)"), "parallelism": f"replicas x{world}",
                    "l2": "inputs larger than L2 (15.4 GB of weights + KV ring streamed every step)",
                    "frames_per_s": total_sessions * 1e3 / ms_dev},
         "e2e": {"value": e2e_value, "unit": "sessions", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 1920 * 4,
@@ -427,6 +443,9 @@ def main() -> None:
     ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: as many as the full-context bf16 KV rings fit in HBM)")
     ap.add_argument("--kv-fill", type=int, default=-1, help="frames of history per session (default: full ring)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--kv-dtype", choices=["bf16", "fp8_e4m3"], default="bf16",
+                    help="storage of the temporal KV rings; fp8_e4m3 is an opt-in extension outside the reference's numerics "
+                         "(half the ring, twice the sessions per GPU; logit error in tests/test_gpu_zv_kv_fp8.py)")
     ap.add_argument("--quantize", action="store_true", help="BASELINE config 5: int8 (W8A8 QLinear) Moshi 7B instead of bf16")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -89,6 +89,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_algorithmic_bytes": (C.c_int64, [_P, _I]),
     "b200_lm_assume_fill": (_I, [_P, _I]),
     "b200_lm_set_graph": (_I, [_P, _I]),
+    "b200_lm_set_kv_dtype": (_I, [_P, _I]),
     # one frame for every session slot, host buffers
     "b200_frame_create": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_P)]),
     "b200_frame_destroy": (_I, [_P]),
@@ -106,6 +107,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_op_attn_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
+    "b200_op_attn_step_f8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
     "b200_op_sample": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
 }
 

@@ -13,6 +13,8 @@ struct TLayer {
   const bf16 *in_w, *out_w, *n1, *n2, *lin_in, *lin_out;
   const float *in_s = nullptr, *out_s = nullptr, *lin_in_s = nullptr, *lin_out_s = nullptr;   // int8 path: weight-row scales
   bf16 *kc = nullptr, *vc = nullptr;
+  uint8_t *kc8 = nullptr, *vc8 = nullptr;      // opt-in fp8 ring: e4m3 bytes [B][H][cap][D] ...
+  float *ks = nullptr, *vs = nullptr;          // ... and one scale per (session, head, slot)
 };
 struct DLayer {
   std::vector<const bf16*> in_w, out_w, lin_in, lin_out;   // one per depformer step
@@ -70,6 +72,7 @@ struct b200_lm {
   int tmp_fused_max_b = 0;                     // B200_TMP_FUSED_MAX_B
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
   int dep_fused = 1;
+  int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE=fp8: opt-in e4m3 KV ring (not the reference's numerics)
   float *dep_part0 = nullptr, *dep_part1 = nullptr;
   unsigned* dep_bar = nullptr;
   int nsplit = 1;
@@ -197,7 +200,14 @@ int step_body(b200_lm* h) {
     for (auto& L : h->layers) {
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
       B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0, L.in_s));
-      {   // RoPE + ring append + split-KV attention + split merge in one launch
+      if (h->kv_fp8) {
+        AttnStepF8 a;
+        a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
+        a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+        a.neg_log_period_2_over_d = nl;
+        dim3 grid(B * H, h->nsplit);
+        B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+      } else {   // RoPE + ring append + split-KV attention + split merge in one launch
         AttnStep a;
         a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
         a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
@@ -291,6 +301,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
   if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e) != 0;
   if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
+  if (const char* e = getenv("B200_KV_DTYPE")) h->kv_fp8 = std::string(e) == "fp8" || std::string(e) == "fp8_e4m3";
   *out = h;
   return B200_OK;
 }
@@ -442,8 +453,15 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->pos, B));
   h->offset_cpu = 0;
   for (auto& L : h->layers) {
-    B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.context * D));
-    B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.context * D));
+    if (h->kv_fp8) {
+      B200_TRY(A.alloc_t(&L.kc8, (size_t)B * H * c.context * D));
+      B200_TRY(A.alloc_t(&L.vc8, (size_t)B * H * c.context * D));
+      B200_TRY(A.alloc_t(&L.ks, (size_t)B * H * c.context));
+      B200_TRY(A.alloc_t(&L.vs, (size_t)B * H * c.context));
+    } else {
+      B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.context * D));
+      B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.context * D));
+    }
   }
   for (auto& L : h->dlayers) {
     B200_TRY(A.alloc_t(&L.kc, (size_t)B * dd * c.dep_q));
@@ -510,7 +528,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     fc.din = h->din; fc.din_ld = (long long)c.dep_q * dd; fc.text_token = h->text_token;
     fc.x = h->dx; fc.xn = h->dxn; fc.ao = h->dao; fc.hbuf = h->dh;
     size_t pf = tc::dep_fused_partial_floats(fc);
-    const bool want_tmp = B <= h->tmp_fused_max_b;
+    const bool want_tmp = B <= h->tmp_fused_max_b && !h->kv_fp8;
     tc::TmpFusedConfig tcfg;
     memset(&tcfg, 0, sizeof(tcfg));
     if (want_tmp) {
@@ -551,8 +569,15 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   A.mark_state(h->offsets, (size_t)B * 8);
   A.mark_state(h->pos, (size_t)B * 8);
   for (auto& L : h->layers) {
-    A.mark_state(L.kc, (size_t)B * H * c.context * D * 2);
-    A.mark_state(L.vc, (size_t)B * H * c.context * D * 2);
+    if (h->kv_fp8) {
+      A.mark_state(L.kc8, (size_t)B * H * c.context * D);
+      A.mark_state(L.vc8, (size_t)B * H * c.context * D);
+      A.mark_state(L.ks, (size_t)B * H * c.context * 4);
+      A.mark_state(L.vs, (size_t)B * H * c.context * 4);
+    } else {
+      A.mark_state(L.kc, (size_t)B * H * c.context * D * 2);
+      A.mark_state(L.vc, (size_t)B * H * c.context * D * 2);
+    }
   }
   B200_CUDA(cudaDeviceSynchronize());
   h->batch = B;
@@ -623,6 +648,14 @@ int b200_lm_set_exec_mask(b200_lm* h, const uint8_t* exec_mask_dev) {
   B200_TRY(ensure_streaming(h, "lm_set_exec_mask"));
   if (!exec_mask_dev) B200_FAIL(B200_ERR_INVALID, "lm_set_exec_mask: null mask");
   B200_CUDA(cudaMemcpyAsync(h->exec_mask, exec_mask_dev, h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
+int b200_lm_set_kv_dtype(b200_lm* h, int kv_dtype) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: null handle");
+  if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "lm_set_kv_dtype: the rings are allocated at streaming_begin; set the dtype before it");
+  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: unknown dtype %d", kv_dtype);
+  h->kv_fp8 = kv_dtype == B200_KV_FP8_E4M3;
   return B200_OK;
 }
 
@@ -755,7 +788,8 @@ int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill) {
   w += (int64_t)c.dep_q * c.card * c.depformer_dim * 2;
   if (c.quantize) w /= 2;        // one byte per weight (the fp32 row scales are < 0.1 % of that)
   // per session: KV ring read (valid slots only) + append, embedding rows, logits written + read by the sampler
-  int64_t per = (int64_t)c.num_layers * 2 * kv_fill * c.dim * 2 + (int64_t)c.num_layers * 2 * c.dim * 2;
+  const int64_t kv_row = h->kv_fp8 ? (int64_t)c.dim + 4 * c.num_heads : (int64_t)c.dim * 2;      // bytes of one K (or V) row of a layer
+  int64_t per = (int64_t)c.num_layers * 2 * kv_fill * kv_row + (int64_t)c.num_layers * 2 * kv_row;
   per += (int64_t)(c.n_q + 1) * c.dim * 2 + (int64_t)c.dep_q * c.depformer_dim * 2;
   per += (int64_t)2 * (c.text_card + (int64_t)c.dep_q * c.card) * 2;
   return w + per * B;

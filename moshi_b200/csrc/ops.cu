@@ -214,6 +214,38 @@ int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_d
   return check_launch("op_attn_step");
 }
 
+int b200_op_attn_step_f8(const void* qkv_dev, void* k8_dev, void* v8_dev, float* ks_dev, float* vs_dev, void* out_dev,
+                         const int64_t* pos_dev, const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period,
+                         void* stream) {
+  using namespace b200::lm;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || H < 1 || cap < 1) B200_FAIL(B200_ERR_SHAPE, "op_attn_step_f8: bad shape");
+  if (nsplit <= 0) nsplit = attn_pick_splits(B, H, cap);
+  static float* part = nullptr;
+  static int* counters = nullptr;
+  static size_t part_n = 0, cnt_n = 0;
+  const size_t need = (size_t)B * H * nsplit * (ATT_D + 2);
+  if (need > part_n) {
+    if (part) cudaFree(part);
+    B200_CUDA(cudaMalloc(&part, need * sizeof(float)));
+    part_n = need;
+  }
+  if ((size_t)B * H > cnt_n) {
+    if (counters) cudaFree(counters);
+    B200_CUDA(cudaMalloc(&counters, (size_t)B * H * sizeof(int)));
+    B200_CUDA(cudaMemset(counters, 0, (size_t)B * H * sizeof(int)));
+    cnt_n = (size_t)B * H;
+  }
+  AttnStepF8 a;
+  a.qkv = static_cast<const bf16*>(qkv_dev); a.kc = static_cast<uint8_t*>(k8_dev); a.vc = static_cast<uint8_t*>(v8_dev);
+  a.ks = ks_dev; a.vs = vs_dev; a.out = static_cast<bf16*>(out_dev); a.part = part; a.counters = counters;
+  a.pos = reinterpret_cast<const long long*>(pos_dev); a.exec_mask = exec_mask_dev; a.H = H; a.cap = cap; a.nsplit = nsplit;
+  a.neg_log_period_2_over_d = -logf(max_period) * 2.f / (float)ATT_D;
+  dim3 grid(B * H, nsplit);
+  B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+  return check_launch("op_attn_step_f8");
+}
+
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B, int card,
                    int use_sampling, float temp, int top_k, void* stream) {
   using namespace b200::lm;

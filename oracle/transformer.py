@@ -32,6 +32,7 @@ class TransformerSpec:
     schedule: tp.Optional[tp.List[int]] = None
     positional_scale: float = 1.0
     quantize: bool = False                # every nn.Linear replaced by QLinear (transformer.py:885-888, utils/quantize.py)
+    kv_fp8: bool = False                  # NOT a reference option: restates the opt-in e4m3 KV ring of the CUDA path
 
 
 @dataclass
@@ -61,6 +62,8 @@ def init_state(spec: TransformerSpec, batch: int, dtype: torch.dtype) -> Transfo
         capacity = spec.context
     per_row = not spec.weights_per_step
     hd = spec.d_model // spec.num_heads
+    if spec.kv_fp8:
+        dtype = torch.float32            # the ring holds e4m3 values times an fp32 scale; kept dequantised here
     layers = []
     for _ in range(spec.num_layers):
         layers.append(LayerState(
@@ -165,6 +168,16 @@ def ring_append(ls: LayerState, k: torch.Tensor, v: torch.Tensor, exec_mask: tor
     return torch.where(empty, torch.full_like(positions, -1), positions)
 
 
+def fp8_roundtrip(t: torch.Tensor) -> torch.Tensor:
+    """What the opt-in fp8 ring stores for one key / value row of ``D`` entries, dequantised to fp32:
+    ``e4m3(t * (448 / absmax)) * (absmax / 448)``, round to nearest even (csrc/lm_kernels.cuh, attn_step_f8_kernel)."""
+    t = t.float()
+    amax = t.abs().amax(dim=-1, keepdim=True)
+    inv = torch.where(amax > 0, 448.0 / amax, torch.zeros_like(amax))
+    q = (t * inv).to(torch.float8_e4m3fn).float()
+    return q * (amax * (1.0 / 448.0))
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, quantize: bool = False) -> torch.Tensor:
     """``nn.Linear`` (bias-free on this path) or, for a quantised LM, ``QLinear.forward`` (oracle/quant.py)."""
     if quantize:
@@ -196,6 +209,8 @@ def attention(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, ls: Laye
     q, k, v = qkv[0], qkv[1], qkv[2]
     if spec.positional_embedding in ("rope", "sin_rope"):
         q, k = rope(q, k, ls.offset, spec.max_period)
+    if spec.kv_fp8:
+        k, v = fp8_roundtrip(k), fp8_roundtrip(v)
     pos_k = ring_append(ls, k.contiguous(), v.contiguous(), st.exec_mask, st.capacity, st.per_row)
     pos_k = pos_k[:, None]                                                     # [B|1, 1, cap]
     pos_q = ls.offset.view(-1, 1, 1) + torch.arange(T).view(-1, 1)            # [B, T, 1]
@@ -203,7 +218,10 @@ def attention(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, ls: Laye
     allowed = (pos_k >= 0) & (delta >= 0)
     if spec.context is not None:
         allowed = allowed & (delta < spec.context)
-    out = F.scaled_dot_product_attention(q, ls.k, ls.v, allowed[:, None], dropout_p=0.0)
+    if spec.kv_fp8:
+        out = F.scaled_dot_product_attention(q.float(), ls.k, ls.v, allowed[:, None], dropout_p=0.0).to(x.dtype)
+    else:
+        out = F.scaled_dot_product_attention(q, ls.k, ls.v, allowed[:, None], dropout_p=0.0)
     out = out.transpose(1, 2).reshape(B, T, C)
     out = _per_step_linear(sd, p + ".out_projs.{i}.weight", spec, out, ls.offset_cpu)
     ls.offset[:] = torch.where(st.exec_mask, ls.offset + T, ls.offset)
