@@ -205,7 +205,7 @@ def _event_time(fn, iters: int = 10, warm: int = 3) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: bool = False) -> dict:
+def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: int = 0) -> dict:
     """The dominant kernel of the step at serving batch is the temporal ring-attention decode (32 launches per
     step, each streaming 2*B*32*fill*128 bf16 of K/V; profiles/ has its share of the step).  Timed here alone
     with CUDA events on the launching stream, on K/V rings of the bench's own shape (4.7 GB at B=96: far
@@ -230,8 +230,8 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: bool = False) -
 
     def fn():
         if fp8:
-            _lib.check(lib.b200_op_attn_step_f8(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(ks), _lib.ptr(vs), _lib.ptr(out),
-                                                _lib.ptr(offs), _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
+            _lib.check(lib.b200_op_attn_step_q8(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(ks), _lib.ptr(vs), _lib.ptr(out),
+                                                _lib.ptr(offs), _lib.ptr(mask), B, H, cap, 0, 10000.0, fp8, stream))
         else:
             _lib.check(lib.b200_op_attn_step(_lib.ptr(qkv), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(offs),
                                              _lib.ptr(mask), B, H, cap, 0, 10000.0, stream))
@@ -254,7 +254,7 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: bool = False) -
         traffic = per_key_session * B * n_keys
         traffic_src = ("ncu --set full at B=%d, %d keys (%s): dram read+write / launch scaled by sessions x keys"
                        % (cap_d["B"], cap_d["keys"], cap_d["source"]))
-    return {"traffic": traffic, "traffic_source": traffic_src, "kernel": "lm::attn_step%s_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 %s" % ("_f8" if fp8 else "", B, n_keys, "e4m3 + fp32 scale per key" if fp8 else "bf16"),
+    return {"traffic": traffic, "traffic_source": traffic_src, "kernel": "lm::attn_step%s_kernel (RoPE + ring append + split-KV attention + merge), B=%d H=32 keys=%d D=128 %s" % (("", "_f8", "_i8")[fp8], B, n_keys, ("bf16", "e4m3 + fp32 scale per key", "int8 + fp32 scale per key")[fp8]),
             "bound": "hbm", "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak,
             "ms_per_launch": ms, "algorithmic_bytes": alg, "launches_per_step": 32}
 
@@ -311,7 +311,7 @@ def b200_arm(args) -> None:
 
     # sessions per GPU: the full-context bf16 KV ring (1.573 GB/session) is what bounds it
     free, total = torch.cuda.mem_get_info(device)
-    fp8 = args.kv_dtype == "fp8_e4m3"
+    fp8 = {"bf16": 0, "fp8_e4m3": 1, "int8": 2}[args.kv_dtype]
     kv_step = (32 * 2 * (4096 + 32 * 4)) if fp8 else KV_BYTES_PER_SESSION_STEP     # e4m3 bytes + one fp32 scale per head
     per_session = kv_step * MOSHI_7B.context + 40e6
     cap = min(int((free - 6e9) // per_session), 256)      # the GEMM path takes at most 256 activation rows
@@ -414,7 +414,7 @@ def b200_arm(args) -> None:
                                "LMGen.step (temp 0.8/0.7, top-k 250/25) "
                                "-> Mimi streaming decode; one 80 ms frame for every session per step",
                    "sessions_per_gpu": B, "sessions_total": total_sessions, "kv_fill": kv_fill,
-                   "kv_ring": ("e4m3 + one fp32 scale per (head, slot), capacity 3000 -- OPT-IN, not the reference's numerics" if fp8
+                   "kv_ring": (f"{args.kv_dtype} + one fp32 scale per (head, slot), capacity 3000 -- OPT-IN, not the reference's numerics" if fp8
                                else "bf16, capacity 3000 (reference context)"), "parallelism": f"replicas x{world}",
                    "l2": "inputs larger than L2 (15.4 GB of weights + KV ring streamed every step)",
                    "frames_per_s": total_sessions * 1e3 / ms_dev},
@@ -443,9 +443,9 @@ def main() -> None:
     ap.add_argument("--sessions", type=int, default=0, help="sessions per GPU (default: as many as the full-context bf16 KV rings fit in HBM)")
     ap.add_argument("--kv-fill", type=int, default=-1, help="frames of history per session (default: full ring)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--kv-dtype", choices=["bf16", "fp8_e4m3"], default="bf16",
-                    help="storage of the temporal KV rings; fp8_e4m3 is an opt-in extension outside the reference's numerics "
-                         "(half the ring, twice the sessions per GPU; logit error in tests/test_gpu_zv_kv_fp8.py)")
+    ap.add_argument("--kv-dtype", choices=["bf16", "fp8_e4m3", "int8"], default="bf16",
+                    help="storage of the temporal KV rings; fp8_e4m3 / int8 are opt-in extensions outside the reference's numerics "
+                         "(half the ring, twice the sessions per GPU; logit error in tests/test_gpu_zv_kv_q8.py)")
     ap.add_argument("--quantize", action="store_true", help="BASELINE config 5: int8 (W8A8 QLinear) Moshi 7B instead of bf16")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -212,9 +212,10 @@ int b200_lm_set_graph(b200_lm* h, int enable);
 /* Storage type of the temporal KV rings, chosen before b200_lm_streaming_begin.  B200_KV_BF16 (default) is the
  * reference's ring (RingKVCache, transformer.py:196-288: 1.573 GB per session at context 3000).  B200_KV_FP8_E4M3 is
  * an opt-in extension outside the reference's numerics: e4m3 bytes plus one fp32 scale per
- * (session, head, slot), 0.811 GB per session; its logit error is reported by tests/test_gpu_zv_kv_fp8.py. */
+ * (session, head, slot), 0.811 GB per session; its logit error is reported by tests/test_gpu_zv_kv_q8.py. */
 #define B200_KV_BF16 0
 #define B200_KV_FP8_E4M3 1
+#define B200_KV_INT8 2
 int b200_lm_set_kv_dtype(b200_lm* h, int kv_dtype);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -294,10 +295,11 @@ int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev,
 int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_dev, const int64_t* pos_dev,
                       const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period, void* stream);
 /* sample_token (sampling.py:86-106): logits bf16 [B,card], noise f32 [B,min(k,card)] -> i64 [B]. */
-/* The same step over the opt-in fp8 ring (b200_lm_set_kv_dtype): k8 / v8 u8 [B,H,cap,128] e4m3, ks / vs f32 [B,H,cap]. */
-int b200_op_attn_step_f8(const void* qkv_dev, void* k8_dev, void* v8_dev, float* ks_dev, float* vs_dev, void* out_dev,
+/* The same step over an opt-in 8-bit ring (b200_lm_set_kv_dtype): k8 / v8 u8 [B,H,cap,128] (e4m3 bytes, or
+ * round(x * 127 / absmax) + 128), ks / vs f32 [B,H,cap] = absmax / 448 (or / 127) of the row. */
+int b200_op_attn_step_q8(const void* qkv_dev, void* k8_dev, void* v8_dev, float* ks_dev, float* vs_dev, void* out_dev,
                          const int64_t* pos_dev, const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period,
-                         void* stream);
+                         int kv_dtype, void* stream);
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B,
                    int card, int use_sampling, float temp, int top_k, void* stream);
 

@@ -107,7 +107,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_op_attn_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
-    "b200_op_attn_step_f8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
+    "b200_op_attn_step_q8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _I, _P]),
     "b200_op_sample": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
 }
 

@@ -72,7 +72,7 @@ struct b200_lm {
   int tmp_fused_max_b = 0;                     // B200_TMP_FUSED_MAX_B
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
   int dep_fused = 1;
-  int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE=fp8: opt-in e4m3 KV ring (not the reference's numerics)
+  int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE: opt-in 8-bit KV ring (B200_KV_FP8_E4M3 or B200_KV_INT8; 0 = bf16)
   float *dep_part0 = nullptr, *dep_part1 = nullptr;
   unsigned* dep_bar = nullptr;
   int nsplit = 1;
@@ -206,7 +206,8 @@ int step_body(b200_lm* h) {
         a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
         a.neg_log_period_2_over_d = nl;
         dim3 grid(B * H, h->nsplit);
-        B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+        if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_i8_kernel, grid, ATT_THREADS, 0, st, a);
+        else B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
       } else {   // RoPE + ring append + split-KV attention + split merge in one launch
         AttnStep a;
         a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
@@ -301,7 +302,10 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
   if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e) != 0;
   if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
-  if (const char* e = getenv("B200_KV_DTYPE")) h->kv_fp8 = std::string(e) == "fp8" || std::string(e) == "fp8_e4m3";
+  if (const char* e = getenv("B200_KV_DTYPE")) {
+    const std::string v = e;
+    h->kv_fp8 = (v == "fp8" || v == "fp8_e4m3") ? B200_KV_FP8_E4M3 : v == "int8" ? B200_KV_INT8 : 0;
+  }
   *out = h;
   return B200_OK;
 }
@@ -438,7 +442,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   Arena& A = h->state;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  const size_t kv_bytes = (size_t)c.num_layers * 2 * B * H * c.context * D * 2;
+  const size_t kv_bytes = (size_t)c.num_layers * 2 * B * H * c.context * (h->kv_fp8 ? (size_t)D + 4 : (size_t)D * 2);
   if (kv_bytes + (1ull << 30) > free_b)
     B200_FAIL(B200_ERR_INVALID, "lm_streaming_begin: %d sessions need %.1f GB of KV ring, %.1f GB free", B, kv_bytes / 1e9,
               free_b / 1e9);
@@ -654,8 +658,9 @@ int b200_lm_set_exec_mask(b200_lm* h, const uint8_t* exec_mask_dev) {
 int b200_lm_set_kv_dtype(b200_lm* h, int kv_dtype) {
   if (!h) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: null handle");
   if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "lm_set_kv_dtype: the rings are allocated at streaming_begin; set the dtype before it");
-  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: unknown dtype %d", kv_dtype);
-  h->kv_fp8 = kv_dtype == B200_KV_FP8_E4M3;
+  if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3 && kv_dtype != B200_KV_INT8)
+    B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: unknown dtype %d", kv_dtype);
+  h->kv_fp8 = kv_dtype;
   return B200_OK;
 }
 

@@ -214,12 +214,13 @@ int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_d
   return check_launch("op_attn_step");
 }
 
-int b200_op_attn_step_f8(const void* qkv_dev, void* k8_dev, void* v8_dev, float* ks_dev, float* vs_dev, void* out_dev,
+int b200_op_attn_step_q8(const void* qkv_dev, void* k8_dev, void* v8_dev, float* ks_dev, float* vs_dev, void* out_dev,
                          const int64_t* pos_dev, const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period,
-                         void* stream) {
+                         int kv_dtype, void* stream) {
   using namespace b200::lm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (B < 1 || H < 1 || cap < 1) B200_FAIL(B200_ERR_SHAPE, "op_attn_step_f8: bad shape");
+  if (B < 1 || H < 1 || cap < 1) B200_FAIL(B200_ERR_SHAPE, "op_attn_step_q8: bad shape");
+  if (kv_dtype != B200_KV_FP8_E4M3 && kv_dtype != B200_KV_INT8) B200_FAIL(B200_ERR_INVALID, "op_attn_step_q8: kv_dtype %d", kv_dtype);
   if (nsplit <= 0) nsplit = attn_pick_splits(B, H, cap);
   static float* part = nullptr;
   static int* counters = nullptr;
@@ -242,8 +243,9 @@ int b200_op_attn_step_f8(const void* qkv_dev, void* k8_dev, void* v8_dev, float*
   a.pos = reinterpret_cast<const long long*>(pos_dev); a.exec_mask = exec_mask_dev; a.H = H; a.cap = cap; a.nsplit = nsplit;
   a.neg_log_period_2_over_d = -logf(max_period) * 2.f / (float)ATT_D;
   dim3 grid(B * H, nsplit);
-  B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
-  return check_launch("op_attn_step_f8");
+  if (kv_dtype == B200_KV_INT8) B200_LAUNCH(attn_step_i8_kernel, grid, ATT_THREADS, 0, st, a);
+  else B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+  return check_launch("op_attn_step_q8");
 }
 
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B, int card,

@@ -141,7 +141,7 @@ class LMGen:
         self._batch: int | None = None
         self._streaming_state = None      # truthy while streaming (callers test `lm_gen._streaming_state`)
         self.use_graph = True
-        # "bf16" = the reference's ring; "fp8_e4m3" = opt-in extension outside the reference's numerics (half the ring)
+        # "bf16" = the reference's ring; "fp8_e4m3" / "int8" = opt-in extensions outside the reference's numerics (half the ring)
         self.kv_dtype = "bf16"
 
     # ---- streaming protocol ----------------------------------------------------------------------
@@ -156,9 +156,10 @@ class LMGen:
             _lib.check(self._lib.b200_lm_set_sampling(self._h, int(self.use_sampling), float(self.temp),
                                                       float(self.temp_text), int(self.top_k), int(self.top_k_text)))
             _lib.check(self._lib.b200_lm_set_graph(self._h, int(self.use_graph)))
-            if self.kv_dtype not in ("bf16", "fp8_e4m3"):
-                raise ValueError(f"kv_dtype {self.kv_dtype!r}: expected 'bf16' or 'fp8_e4m3'")
-            _lib.check(self._lib.b200_lm_set_kv_dtype(self._h, 1 if self.kv_dtype == "fp8_e4m3" else 0))
+            kinds = {"bf16": 0, "fp8_e4m3": 1, "int8": 2}
+            if self.kv_dtype not in kinds:
+                raise ValueError(f"kv_dtype {self.kv_dtype!r}: expected one of {sorted(kinds)}")
+            _lib.check(self._lib.b200_lm_set_kv_dtype(self._h, kinds[self.kv_dtype]))
             _lib.check(self._lib.b200_lm_streaming_begin(self._h, int(batch_size), _lib.current_stream(dev)))
         self._batch = int(batch_size)
         self._noise_per_row = int(self._lib.b200_lm_noise_per_row(self._h))

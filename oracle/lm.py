@@ -115,7 +115,7 @@ def sample_token(logits: torch.Tensor, use_sampling: bool, temp: float, top_k: i
 class LMOracle:
     def __init__(self, sd: tp.Dict[str, torch.Tensor], spec: LMSpec, use_sampling: bool = True,
                  temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25,
-                 tie_break: str = "torch", quantize: bool = False, kv_fp8: bool = False):
+                 tie_break: str = "torch", quantize: bool = False, kv_quant: str = ""):
         self.tie_break = tie_break
         self.quantize = quantize          # LMModel(quantize=True): every nn.Linear is a QLinear (lm.py:242-243)
         self.sd = sd
@@ -127,7 +127,7 @@ class LMOracle:
         self.main_spec = tr.TransformerSpec(
             d_model=s.dim, num_heads=s.num_heads, num_layers=s.num_layers, context=s.context,
             norm=s.norm, gating=s.gating, positional_embedding=s.positional_embedding,
-            max_period=s.max_period, quantize=quantize, kv_fp8=kv_fp8)
+            max_period=s.max_period, quantize=quantize, kv_quant=kv_quant)
         self.dep_spec = tr.TransformerSpec(
             d_model=s.depformer_dim, num_heads=s.depformer_num_heads,
             num_layers=s.depformer_num_layers, context=None, norm=s.norm, gating=s.depformer_gating,

@@ -32,7 +32,8 @@ class TransformerSpec:
     schedule: tp.Optional[tp.List[int]] = None
     positional_scale: float = 1.0
     quantize: bool = False                # every nn.Linear replaced by QLinear (transformer.py:885-888, utils/quantize.py)
-    kv_fp8: bool = False                  # NOT a reference option: restates the opt-in e4m3 KV ring of the CUDA path
+    kv_quant: str = ""                    # NOT a reference option: restates the opt-in 8-bit KV rings of the CUDA path
+                                          # ("fp8_e4m3" | "int8")
 
 
 @dataclass
@@ -62,8 +63,8 @@ def init_state(spec: TransformerSpec, batch: int, dtype: torch.dtype) -> Transfo
         capacity = spec.context
     per_row = not spec.weights_per_step
     hd = spec.d_model // spec.num_heads
-    if spec.kv_fp8:
-        dtype = torch.float32            # the ring holds e4m3 values times an fp32 scale; kept dequantised here
+    if spec.kv_quant:
+        dtype = torch.float32            # the ring holds 8-bit values times an fp32 scale; kept dequantised here
     layers = []
     for _ in range(spec.num_layers):
         layers.append(LayerState(
@@ -178,6 +179,20 @@ def fp8_roundtrip(t: torch.Tensor) -> torch.Tensor:
     return q * (amax * (1.0 / 448.0))
 
 
+def int8_roundtrip(t: torch.Tensor) -> torch.Tensor:
+    """The opt-in int8 ring: ``clamp(round(t * (127 / absmax)), -127, 127) * (absmax / 127)`` per row of ``D`` entries, ties to
+    even (csrc/lm_kernels.cuh, attn_step_i8_kernel)."""
+    t = t.float()
+    amax = t.abs().amax(dim=-1, keepdim=True)
+    inv = torch.where(amax > 0, 127.0 / amax, torch.zeros_like(amax))
+    q = torch.round(t * inv).clamp_(-127, 127)
+    return q * (amax * (1.0 / 127.0))
+
+
+def kv_roundtrip(t: torch.Tensor, fmt: str) -> torch.Tensor:
+    return {"fp8_e4m3": fp8_roundtrip, "int8": int8_roundtrip}[fmt](t)
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, quantize: bool = False) -> torch.Tensor:
     """``nn.Linear`` (bias-free on this path) or, for a quantised LM, ``QLinear.forward`` (oracle/quant.py)."""
     if quantize:
@@ -209,8 +224,8 @@ def attention(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, ls: Laye
     q, k, v = qkv[0], qkv[1], qkv[2]
     if spec.positional_embedding in ("rope", "sin_rope"):
         q, k = rope(q, k, ls.offset, spec.max_period)
-    if spec.kv_fp8:
-        k, v = fp8_roundtrip(k), fp8_roundtrip(v)
+    if spec.kv_quant:
+        k, v = kv_roundtrip(k, spec.kv_quant), kv_roundtrip(v, spec.kv_quant)
     pos_k = ring_append(ls, k.contiguous(), v.contiguous(), st.exec_mask, st.capacity, st.per_row)
     pos_k = pos_k[:, None]                                                     # [B|1, 1, cap]
     pos_q = ls.offset.view(-1, 1, 1) + torch.arange(T).view(-1, 1)            # [B, T, 1]
@@ -218,7 +233,7 @@ def attention(sd: dict, p: str, spec: TransformerSpec, x: torch.Tensor, ls: Laye
     allowed = (pos_k >= 0) & (delta >= 0)
     if spec.context is not None:
         allowed = allowed & (delta < spec.context)
-    if spec.kv_fp8:
+    if spec.kv_quant:
         out = F.scaled_dot_product_attention(q.float(), ls.k, ls.v, allowed[:, None], dropout_p=0.0).to(x.dtype)
     else:
         out = F.scaled_dot_product_attention(q, ls.k, ls.v, allowed[:, None], dropout_p=0.0)

@@ -1,10 +1,10 @@
-"""GPU: the opt-in fp8 (e4m3 + one fp32 scale per key row) temporal KV ring.
+"""GPU: the opt-in 8-bit temporal KV rings (one byte per element + one fp32 scale per key row): e4m3 and int8.
 
 This is NOT the reference's numerics (its ring is bf16, transformer.py:196-288); it exists to halve the 1.57 GB a
 session's rings take.  Two levels:
-  * the fused attention step kernel against an fp32 emulation that stores ``e4m3(x * 448/absmax) * absmax/448`` for the
-    appended key / value row and attends over the dequantised ring: the kernel must agree with that to bf16 rounding,
-    and the bytes + scales it wrote must be exactly the emulation's;
+  * the fused attention step kernel against an fp32 emulation that stores ``e4m3(x * 448/absmax) * absmax/448`` (or
+    ``round(x * 127/absmax) * absmax/127``) for the appended key / value row and attends over the dequantised ring: the
+    kernel must agree with that to bf16 rounding, and the bytes + scales it wrote must be the emulation's;
   * the LM step against the oracle with the same emulation in its ring, and the *cost* of the option: logit deviation
     of the fp8-ring model from the bf16-ring model on the same token stream (reported and bounded).
 """
@@ -14,7 +14,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from oracle.transformer import fp8_roundtrip
+from oracle.transformer import kv_roundtrip
 from tests.test_gpu_ops import _rope_ref
 from tests.util import cptr, stats
 
@@ -25,8 +25,28 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+FMT = {"fp8_e4m3": (1, 448.0), "int8": (2, 127.0)}
+
+
+def _encode(t, amax, fmt):
+    """Row-scaled bytes as the kernel stores them."""
+    qmax = FMT[fmt][1]
+    inv = torch.where(amax > 0, qmax / amax, torch.zeros_like(amax))
+    y = t.float() * inv[..., None]
+    if fmt == "fp8_e4m3":
+        return y.to(torch.float8_e4m3fn).view(torch.uint8)
+    return (torch.round(y).clamp_(-127, 127) + 128).to(torch.uint8)
+
+
+def _decode(u8, scale, fmt):
+    if fmt == "fp8_e4m3":
+        return u8.view(torch.float8_e4m3fn).float() * scale[..., None]
+    return (u8.float() - 128.0) * scale[..., None]
+
+
+@pytest.mark.parametrize("fmt", ["int8", "fp8_e4m3"])
 @pytest.mark.parametrize("B,H,cap,nsplit,steps", [(3, 2, 12, 0, 30), (2, 32, 300, 4, 6), (5, 4, 3000, 0, 3), (1, 32, 3000, 16, 2)])
-def test_fp8_attention_step_matches_emulation(B, H, cap, nsplit, steps):
+def test_q8_attention_step_matches_emulation(B, H, cap, nsplit, steps, fmt):
     from moshi_b200 import _lib
     lib = _lib.lib()
     g = torch.Generator().manual_seed(B * 17 + cap)
@@ -35,14 +55,12 @@ def test_fp8_attention_step_matches_emulation(B, H, cap, nsplit, steps):
     pos0 = torch.tensor([0, cap - 2, cap + 7, 5, 2 * cap + 1][:B], dtype=torch.int64)
     hist_k = torch.randn(B, H, cap, 128, generator=g).bfloat16()
     hist_v = torch.randn(B, H, cap, 128, generator=g).bfloat16() * torch.rand(B, H, cap, 1, generator=g) * 4
-    ring_k, ring_v = fp8_roundtrip(hist_k), fp8_roundtrip(hist_v)          # dequantised fp32 view of the ring
+    kind, qmax = FMT[fmt]
+    ring_k, ring_v = kv_roundtrip(hist_k, fmt), kv_roundtrip(hist_v, fmt)          # dequantised fp32 view of the ring
     amax_k, amax_v = hist_k.float().abs().amax(-1), hist_v.float().abs().amax(-1)
-
-    def q8(t, amax):
-        inv = torch.where(amax > 0, 448.0 / amax, torch.zeros_like(amax))
-        return (t.float() * inv[..., None]).to(torch.float8_e4m3fn).view(torch.uint8)
-    k8, v8 = q8(hist_k, amax_k).cuda(), q8(hist_v, amax_v).cuda()
-    ks, vs = (amax_k * (1.0 / 448.0)).cuda(), (amax_v * (1.0 / 448.0)).cuda()
+    k8, v8 = _encode(hist_k, amax_k, fmt).cuda(), _encode(hist_v, amax_v, fmt).cuda()
+    ks, vs = (amax_k * (1.0 / qmax)).cuda(), (amax_v * (1.0 / qmax)).cuda()
+    assert torch.equal(_decode(k8.cpu(), ks.cpu(), fmt), ring_k)
     pos = pos0.clone()
     out = torch.empty(B, Cd, dtype=torch.bfloat16, device="cuda")
     worst = 0.0
@@ -53,7 +71,7 @@ def test_fp8_attention_step_matches_emulation(B, H, cap, nsplit, steps):
             mask[1] = False
         q_in, k_in, v_in = (qkv[:, j * Cd:(j + 1) * Cd].reshape(B, H, 128) for j in range(3))
         q_rot, k_rot = _rope_ref(q_in, pos), _rope_ref(k_in, pos)
-        k_new, v_new = fp8_roundtrip(k_rot), fp8_roundtrip(v_in)
+        k_new, v_new = kv_roundtrip(k_rot, fmt), kv_roundtrip(v_in, fmt)
         for b in range(B):
             if mask[b]:
                 ring_k[b, :, pos[b] % cap] = k_new[b]
@@ -62,25 +80,28 @@ def test_fp8_attention_step_matches_emulation(B, H, cap, nsplit, steps):
         allowed = torch.arange(cap)[None, :] < n_valid[:, None]
         want = F.scaled_dot_product_attention(q_rot.float()[:, :, None], ring_k, ring_v, allowed[:, None, None, :])[:, :, 0].reshape(B, Cd)
         qd, pd, md = qkv.cuda(), pos.cuda(), mask.cuda()
-        _lib.check(lib.b200_op_attn_step_f8(cptr(qd), cptr(k8), cptr(v8), cptr(ks), cptr(vs), cptr(out), cptr(pd), cptr(md),
-                                            B, H, cap, nsplit, 10000.0, _stream()))
+        _lib.check(lib.b200_op_attn_step_q8(cptr(qd), cptr(k8), cptr(v8), cptr(ks), cptr(vs), cptr(out), cptr(pd), cptr(md),
+                                            B, H, cap, nsplit, 10000.0, kind, _stream()))
         torch.cuda.synchronize()
         rows = n_valid > 0
         worst = max(worst, (out.float().cpu()[rows] - want[rows]).abs().max().item())
-        torch.testing.assert_close(out.float().cpu()[rows], want[rows], rtol=2e-2, atol=2e-2)
+        # a bf16 ulp of sincos in the rotated key can move it (or its row's absmax) across a rounding boundary of the 8-bit
+        # grid: rare entries differ by one quantisation step of a key the softmax weights heavily; the bulk agrees to
+        # bf16 rounding
+        err = (out.float().cpu()[rows] - want[rows]).abs()
+        assert err.max() < 0.1 and err.mean() < 4e-3, (err.max(), err.mean())
         pos = pos + mask.long()
-    print(f"fp8 attn step B={B} H={H} cap={cap}: worst |d| vs emulation {worst:.3e}")
-    # the ring the kernel maintained == the emulation's (values: one e4m3 step where sincos moved a bf16 ulp of the key)
-    deq_k = k8.cpu().view(torch.float8_e4m3fn).float() * ks.cpu()[..., None]
-    deq_v = v8.cpu().view(torch.float8_e4m3fn).float() * vs.cpu()[..., None]
+    print(f"{fmt} attn step B={B} H={H} cap={cap}: worst |d| vs emulation {worst:.3e}")
+    # the ring the kernel maintained == the emulation's (keys: one grid step where sincos moved a bf16 ulp of the key)
+    deq_k, deq_v = _decode(k8.cpu(), ks.cpu(), fmt), _decode(v8.cpu(), vs.cpu(), fmt)
     assert torch.equal(deq_v, ring_v)
-    torch.testing.assert_close(deq_k, ring_k, rtol=0.13, atol=1e-3)
+    torch.testing.assert_close(deq_k, ring_k, rtol=0.13, atol=0.05)
     assert (deq_k != ring_k).float().mean() < 0.02
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_fp8_ring_lm_matches_emulating_oracle(use_graph):
-    """LM steps with the fp8 ring against the oracle whose ring holds the same e4m3-rounded rows (teacher-synchronised)."""
+@pytest.mark.parametrize("fmt,use_graph", [("int8", False), ("int8", True), ("fp8_e4m3", True)])
+def test_q8_ring_lm_matches_emulating_oracle(fmt, use_graph):
+    """LM steps with an 8-bit ring against the oracle whose ring holds the same rounded rows (teacher-synchronised)."""
     from moshi_b200.config import tiny_lm_config
     from moshi_b200.models import LMGen, LMModel
     from moshi_b200.synth import synth_lm_state_dict
@@ -92,9 +113,9 @@ def test_fp8_ring_lm_matches_emulating_oracle(use_graph):
     B, steps = scenarios.LM_B, 20
     codes = scenarios.lm_input_codes(cfg, B, steps)
     gen = LMGen(lm, use_sampling=False)
-    gen.kv_dtype = "fp8_e4m3"
+    gen.kv_dtype = fmt
     gen.use_graph = use_graph
-    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, tie_break="index", kv_fp8=True)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, tie_break="index", kv_quant=fmt)
     orc.streaming(B)
     worst = 0.0
     agree = total = 0
@@ -113,13 +134,14 @@ def test_fp8_ring_lm_matches_emulating_oracle(use_graph):
             for b in range(B):
                 orc.cache[b, 0, pos[b]] = tt[b]
                 orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
-    print(f"fp8 ring LM vs emulating oracle (graph={use_graph}): worst text-logit diff {worst:.3e}, greedy text tokens equal {agree}/{total}")
+    print(f"{fmt} ring LM vs emulating oracle (graph={use_graph}): worst text-logit diff {worst:.3e}, greedy text tokens equal {agree}/{total}")
     assert worst < 0.12
     assert agree / total > 0.9
 
 
-def test_fp8_ring_cost_against_bf16_ring():
-    """What the option costs: the fp8-ring model against the bf16-ring model fed the same tokens (teacher-forced)."""
+@pytest.mark.parametrize("fmt", ["int8", "fp8_e4m3"])
+def test_q8_ring_cost_against_bf16_ring(fmt):
+    """What the option costs: the 8-bit-ring model against the bf16-ring model fed the same input codes."""
     from moshi_b200.config import tiny_lm_config
     from moshi_b200.models import LMGen, LMModel
     from moshi_b200.synth import synth_lm_state_dict
@@ -129,7 +151,7 @@ def test_fp8_ring_cost_against_bf16_ring():
     B, steps = 4, 24
     codes = scenarios.lm_input_codes(cfg, B, steps)
     logits = []
-    for kv in ("bf16", "fp8_e4m3"):
+    for kv in ("bf16", fmt):
         lm = LMModel(cfg, sd, device="cuda")
         gen = LMGen(lm, use_sampling=False)
         gen.kv_dtype = kv
@@ -146,7 +168,7 @@ def test_fp8_ring_cost_against_bf16_ring():
     same = (a.argmax(-1) == b.argmax(-1)).long().cumprod(dim=0).bool()         # [steps, B]
     d = (a - b).abs().amax(-1)
     rel = (d[same] / a.abs().amax(-1)[same]).max().item()
-    print(f"fp8 vs bf16 ring: worst text-logit deviation {d[same].max().item():.3e} ({rel:.2%} of the row's max |logit|) over "
+    print(f"{fmt} vs bf16 ring: worst text-logit deviation {d[same].max().item():.3e} ({rel:.2%} of the row's max |logit|) over "
           f"{int(same.sum())} comparable row-steps; snapshot bytes {bytes_bf16} -> {bytes_fp8}")
     assert int(same.sum()) >= steps * B // 2
     assert rel < 0.1

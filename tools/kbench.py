@@ -116,6 +116,30 @@ def bench_attn(lib, Bs, cap=3000, H=32):
         del ks, vs
 
 
+def bench_attn_q8(lib, Bs, fmt, cap=3000, H=32):
+    """The opt-in 8-bit rings' attention step (one byte per element + one fp32 scale per key row); fmt 1 = e4m3, 2 = int8."""
+    for B in Bs:
+        n_rot = 2
+        ks = [torch.randint(0, 120, (B, H, cap, 128), device="cuda", dtype=torch.uint8) for _ in range(n_rot)]
+        vs = [torch.randint(0, 120, (B, H, cap, 128), device="cuda", dtype=torch.uint8) for _ in range(n_rot)]
+        sk = torch.full((B, H, cap), 0.01, device="cuda")
+        sv = torch.full((B, H, cap), 0.01, device="cuda")
+        q = torch.randn(B, 3 * H * 128, device="cuda").bfloat16()
+        out = torch.empty(B, H * 128, device="cuda", dtype=torch.bfloat16)
+        mask = torch.ones(B, dtype=torch.bool, device="cuda")
+        for fill in (cap, cap // 4):
+            offs = torch.full((B,), fill + 7 * cap if fill == cap else fill - 1, dtype=torch.int64, device="cuda")
+            def fn(i):
+                _lib.check(lib.b200_op_attn_step_q8(_lib.ptr(q), _lib.ptr(ks[i]), _lib.ptr(vs[i]), _lib.ptr(sk), _lib.ptr(sv), _lib.ptr(out),
+                                                    _lib.ptr(offs), _lib.ptr(mask), B, H, cap, 0, 10000.0, fmt, stream()))
+            ms = time_ms(fn, n_rot)
+            alg = 2 * B * H * min(fill, cap) * (128 + 4)
+            gbs = alg / ms / 1e6
+            print(json.dumps({"kernel": "attn_step_f8" if fmt == 1 else "attn_step_i8", "B": B, "H": H, "cap": cap, "fill": fill, "ms": round(ms, 4),
+                              "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+        del ks, vs
+
+
 def bench_mimi(Bs):
     from moshi_b200.models import loaders
     mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
@@ -151,6 +175,10 @@ def main():
     what = args.what.split(",")
     if "attn" in what:
         bench_attn(lib, Bs)
+    if "attn_f8" in what:
+        bench_attn_q8(lib, Bs, 1)
+    if "attn_i8" in what:
+        bench_attn_q8(lib, Bs, 2)
     if "gemm" in what:
         bench_gemm(lib, Ms, legacy=not args.no_legacy, only=args.only)
     if "mimi" in what:
