@@ -201,13 +201,13 @@ int step_body(b200_lm* h) {
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
       B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0, L.in_s));
       if (h->kv_fp8) {
-        AttnStepF8 a;
+        AttnStepQ8 a;
         a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
         a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
         a.neg_log_period_2_over_d = nl;
         dim3 grid(B * H, h->nsplit);
-        if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_i8_kernel, grid, ATT_THREADS, 0, st, a);
-        else B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+        if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
+        else B200_LAUNCH(attn_step_q8_kernel<KV_E4M3>, grid, ATT_THREADS, 0, st, a);
       } else {   // RoPE + ring append + split-KV attention + split merge in one launch
         AttnStep a;
         a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;

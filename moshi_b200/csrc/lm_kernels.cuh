@@ -540,227 +540,64 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_kernel(const Att
 }
 
 // ---------------------------------------------------------------------------------------------
-// Opt-in fp8 KV ring (NOT the reference's numerics): the same fused step as attn_step_kernel
-// over rings of e4m3 bytes with one fp32 scale per (session, head, slot) = absmax / 448 of the 128 values.
-// Halves the ring (0.81 GB instead of 1.57 GB per session at context 3000), i.e. the sessions a GPU can hold.
-//   * append: the rotated key (rounded to bf16 first, like the bf16 ring) and the value are scaled and rounded
-//     to e4m3 (round to nearest even, |x| / scale <= 448 by construction);
-//   * a half-warp owns one key per slot of an 8-key group: 16 lanes x 8 bytes; the dot product is taken on the
-//     e4m3 values in fp32 and multiplied by the key's scale once; the value's scale is folded into its softmax weight;
-//   * the online softmax is updated once per 8-key group (one rescale of the accumulator instead of eight).
+// Opt-in 8-bit KV rings (NOT the reference's numerics): the same fused step as attn_step_kernel
+// over rings of one byte per element with one fp32 scale per (session, head, slot).  Halves the ring (0.81 GB instead
+// of 1.57 GB per session at context 3000), i.e. doubles the sessions a GPU can hold.  Two encodings of a row x[128]:
+//   KV_E4M3: e4m3(x * 448 / absmax), scale = absmax / 448   (keeps relative precision under outlier channels)
+//   KV_INT8: round(x * 127 / absmax) + 128, scale = absmax / 127   (4x smaller error on smooth rows, cheaper decode:
+//            PRMT places the byte under the fp16 exponent 0x64 (= 1024 + u exactly) and one HADD2 removes 1152)
+// Append: the rotated key (rounded to bf16 first, like the bf16 ring) and the value are scaled and rounded to nearest
+// even.  Attention: a half-warp owns one key (16 lanes x 8 bytes); keys and values are decoded to packed fp16 (exact),
+// the dot product and the per-group weighted value sums run as HFMA2, and everything that accumulates over the ring
+// (softmax statistics, output accumulator) stays fp32; the online softmax is updated once per group of keys.
 // ---------------------------------------------------------------------------------------------
-struct AttnStepF8 {
+constexpr int KV_E4M3 = 1, KV_INT8 = 2;       // = B200_KV_FP8_E4M3, B200_KV_INT8
+
+struct AttnStepQ8 {
   const bf16* qkv; uint8_t* kc; uint8_t* vc; float* ks; float* vs; bf16* out;
   float* part; int* counters;
   const long long* pos; const uint8_t* exec_mask;
   int H, cap, nsplit; float neg_log_period_2_over_d;
 };
 
-__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t two) {
-  const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(two & 0xFFFFu), __NV_E4M3);
+__device__ __forceinline__ __half2 e4m3x2_to_half2(uint32_t two) {
+  const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(two & 0xFFFFu), __NV_E4M3);    // exact
   __half2 h2;
   memcpy(&h2, &hr, sizeof(h2));
-  return __half22float2(h2);
+  return h2;
 }
-__device__ __forceinline__ void unpack8_e4m3(const uint2& v, float* f) {
-  const float2 a = e4m3x2_to_float2(v.x), b = e4m3x2_to_float2(v.x >> 16), c = e4m3x2_to_float2(v.y), d = e4m3x2_to_float2(v.y >> 16);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-
-static __global__ void __launch_bounds__(ATT_THREADS) attn_step_f8_kernel(const AttnStepF8 a) {
-  pdl_trigger();
-  const int bh = blockIdx.x, split = blockIdx.y;
-  const int b = bh / a.H, h = bh - b * a.H;
-  const int C = a.H * ATT_D;
-  const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15;
-  const int hw = tid >> 4;                          // half-warp id 0..7
-  const bool exec = a.exec_mask[b] != 0;
-  const long long p = a.pos[b];
-  long long n_valid = p + (exec ? 1 : 0);
-  if (n_valid > a.cap) n_valid = a.cap;
-  const int per = (int)((n_valid + a.nsplit - 1) / a.nsplit);
-  const int s0 = split * per;
-  const int s1 = (int)min((long long)(s0 + per), n_valid);
-  const int slot_new = (int)(p % a.cap);
-  const bf16* base = a.qkv + (long long)b * 3 * C + h * ATT_D;
-  const float fpos = (float)p;
-
-  if (exec && slot_new >= s0 && slot_new < s1) {    // CTA-uniform: this CTA owns the new key's slot
-    __shared__ float s_amax[2][2];
-    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-    if (tid < ATT_D / 2) {
-      const int pr = tid;
-      const float kr = bf2f(base[C + 2 * pr]), ki = bf2f(base[C + 2 * pr + 1]);
-      const float freq = expf((float)pr * a.neg_log_period_2_over_d);
-      float sn, cs;
-      sincosf(freq * fpos, &sn, &cs);
-      k0 = rbf(kr * cs - ki * sn);
-      k1 = rbf(kr * sn + ki * cs);
-      v0 = bf2f(base[2 * C + 2 * pr]);
-      v1 = bf2f(base[2 * C + 2 * pr + 1]);
-    }
-    const float ak = warp_max(fmaxf(fabsf(k0), fabsf(k1))), av = warp_max(fmaxf(fabsf(v0), fabsf(v1)));
-    if (tid < ATT_D / 2 && lane == 0) { s_amax[tid >> 5][0] = ak; s_amax[tid >> 5][1] = av; }
-    __syncthreads();
-    if (tid < ATT_D / 2) {
-      const float amk = fmaxf(s_amax[0][0], s_amax[1][0]), amv = fmaxf(s_amax[0][1], s_amax[1][1]);
-      const float ik = amk > 0.f ? 448.f / amk : 0.f, iv = amv > 0.f ? 448.f / amv : 0.f;
-      const long long o = ((long long)bh * a.cap + slot_new) * ATT_D + 2 * tid;
-      *reinterpret_cast<__nv_fp8x2_storage_t*>(a.kc + o) = __nv_cvt_float2_to_fp8x2(make_float2(k0 * ik, k1 * ik), __NV_SATFINITE, __NV_E4M3);
-      *reinterpret_cast<__nv_fp8x2_storage_t*>(a.vc + o) = __nv_cvt_float2_to_fp8x2(make_float2(v0 * iv, v1 * iv), __NV_SATFINITE, __NV_E4M3);
-      if (tid == 0) {
-        a.ks[(long long)bh * a.cap + slot_new] = amk * (1.f / 448.f);
-        a.vs[(long long)bh * a.cap + slot_new] = amv * (1.f / 448.f);
-      }
-    }
-    __syncthreads();
-  }
-
-  float qf[8];
-  {
-    float raw[8];
-    unpack8(*reinterpret_cast<const uint4*>(base + l16 * 8), raw);
-    const float scale = 0.08838834764831845f;       // 1/sqrt(128)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pr = l16 * 4 + j;
-      const float freq = expf((float)pr * a.neg_log_period_2_over_d);
-      float sn, cs;
-      sincosf(freq * fpos, &sn, &cs);
-      const float qr = raw[2 * j], qi = raw[2 * j + 1];
-      qf[2 * j] = rbf(qr * cs - qi * sn) * scale;
-      qf[2 * j + 1] = rbf(qr * sn + qi * cs) * scale;
-    }
-  }
-
-  const uint8_t* kb = a.kc + (long long)bh * a.cap * ATT_D + l16 * 8;
-  const uint8_t* vb = a.vc + (long long)bh * a.cap * ATT_D + l16 * 8;
-  const float* ksb = a.ks + (long long)bh * a.cap;
-  const float* vsb = a.vs + (long long)bh * a.cap;
-  float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-  constexpr int U = 8;                              // keys in flight per half-warp (8 bytes per lane each)
-  for (int kb0 = s0; kb0 < s1; kb0 += 8 * U) {      // warp-uniform trip count (shuffles inside)
-    const int s = kb0 + hw * U;
-    uint2 kr[U], vr[U];
-    float ksc[U], vsc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ss = s + u < s1 ? s + u : s1 - 1;
-      kr[u] = *reinterpret_cast<const uint2*>(kb + (long long)ss * ATT_D);
-      vr[u] = *reinterpret_cast<const uint2*>(vb + (long long)ss * ATT_D);
-      ksc[u] = ksb[ss];
-      vsc[u] = vsb[ss];
-    }
-    float d[U];
-    float mn = m;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float kf[8];
-      unpack8_e4m3(kr[u], kf);
-      float t = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t = fmaf(qf[i], kf[i], t);
-      t += __shfl_xor_sync(0xffffffffu, t, 8);
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      d[u] = s + u < s1 ? t * ksc[u] : -INFINITY;
-      mn = fmaxf(mn, d[u]);
-    }
-    if (mn > -INFINITY) {                           // uniform over the half-warp; no shuffles inside
-      const float corr = __expf(m - mn);            // m = -inf -> 0
-      l *= corr;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] *= corr;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float pw = __expf(d[u] - mn);         // padding keys: exp(-inf) = 0
-        l += pw;
-        const float pv = pw * vsc[u];
-        float vf[8];
-        unpack8_e4m3(vr[u], vf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, vf[i], acc[i]);
-      }
-      m = mn;
-    }
-  }
-  // merge the 8 half-warps of the CTA, then the splits (same protocol as attn_step_kernel)
-  __shared__ float sm_m[8], sm_l[8], sm_acc[8][ATT_D];
-  __shared__ int s_last;
-  if (l16 == 0) { sm_m[hw] = m; sm_l[hw] = l; }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sm_acc[hw][l16 * 8 + i] = acc[i];
-  __syncthreads();
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
-  float L = 0.f, A = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - M);
-    L += sm_l[w] * c;
-    A += sm_acc[w][tid] * c;
-  }
-  if (a.nsplit == 1) {
-    a.out[(long long)bh * ATT_D + tid] = f2bf(L > 0.f ? A / L : 0.f);
-    return;
-  }
-  float* o = a.part + ((long long)bh * a.nsplit + split) * (ATT_D + 2);
-  __stcg(o + tid, A);
-  if (tid == 0) { __stcg(o + ATT_D, M); __stcg(o + ATT_D + 1, L); }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int old = atomicAdd(a.counters + bh, 1);
-    s_last = old == a.nsplit - 1;
-    if (s_last) a.counters[bh] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const float* pp = a.part + (long long)bh * a.nsplit * (ATT_D + 2);
-  float MM = -INFINITY;
-  for (int s = 0; s < a.nsplit; ++s) MM = fmaxf(MM, __ldcg(pp + s * (ATT_D + 2) + ATT_D));
-  float LL = 0.f, AA = 0.f;
-  for (int s = 0; s < a.nsplit; ++s) {
-    const float ms = __ldcg(pp + s * (ATT_D + 2) + ATT_D);
-    const float c = ms == -INFINITY ? 0.f : __expf(ms - MM);
-    LL += __ldcg(pp + s * (ATT_D + 2) + ATT_D + 1) * c;
-    AA += __ldcg(pp + s * (ATT_D + 2) + tid) * c;
-  }
-  a.out[(long long)bh * ATT_D + tid] = f2bf(LL > 0.f ? AA / LL : 0.f);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Opt-in int8 KV ring: the same layout as the fp8 ring (one byte per element, one fp32 scale per key row), but the byte
-// is round(x * 127 / absmax) + 128 (offset binary).  Decoding needs no conversion instruction: PRMT places the byte
-// under the fp16 exponent 0x64 (= 1024 + u exactly) and one HADD2 removes 1152, so the dot product and the 8-key
-// partial value sums run as packed fp16 HFMA2 on exact small integers; everything that accumulates over the ring
-// (softmax statistics, output accumulator) stays fp32.
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ __half2 u8x2_to_half2(uint32_t w, uint32_t selector) {
   const uint32_t bits = __byte_perm(w, 0x64646464u, selector);     // [b, 0x64, b', 0x64] = (1024 + b, 1024 + b')
   __half2 h;
   memcpy(&h, &bits, sizeof(h));
   return __hsub2(h, __floats2half2_rn(1152.f, 1152.f));            // exact: values in [-128, 127]
 }
-__device__ __forceinline__ void unpack8_u8(const uint2& v, __half2* h) {
-  h[0] = u8x2_to_half2(v.x, 0x4140u);
-  h[1] = u8x2_to_half2(v.x, 0x4342u);
-  h[2] = u8x2_to_half2(v.y, 0x4140u);
-  h[3] = u8x2_to_half2(v.y, 0x4342u);
+template <int FMT>
+__device__ __forceinline__ void unpack8_q8(const uint2& v, __half2* h) {
+  if (FMT == KV_INT8) {
+    h[0] = u8x2_to_half2(v.x, 0x4140u);
+    h[1] = u8x2_to_half2(v.x, 0x4342u);
+    h[2] = u8x2_to_half2(v.y, 0x4140u);
+    h[3] = u8x2_to_half2(v.y, 0x4342u);
+  } else {
+    h[0] = e4m3x2_to_half2(v.x);
+    h[1] = e4m3x2_to_half2(v.x >> 16);
+    h[2] = e4m3x2_to_half2(v.y);
+    h[3] = e4m3x2_to_half2(v.y >> 16);
+  }
 }
-__device__ __forceinline__ uint32_t quant_u8(float x, float inv) {
-  float r = rintf(x * inv);
-  r = fminf(fmaxf(r, -127.f), 127.f);
-  return (uint32_t)((int)r + 128);
+// two scaled values -> two ring bytes
+template <int FMT>
+__device__ __forceinline__ uint16_t quant2_q8(float x0, float x1) {
+  if (FMT == KV_INT8) {
+    const float r0 = fminf(fmaxf(rintf(x0), -127.f), 127.f), r1 = fminf(fmaxf(rintf(x1), -127.f), 127.f);
+    return (uint16_t)((uint32_t)((int)r0 + 128) | ((uint32_t)((int)r1 + 128) << 8));
+  }
+  return (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(x0, x1), __NV_SATFINITE, __NV_E4M3);
 }
 
-static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const AttnStepF8 a) {
+template <int FMT>
+static __global__ void __launch_bounds__(ATT_THREADS) attn_step_q8_kernel(const AttnStepQ8 a) {
   pdl_trigger();
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / a.H, h = bh - b * a.H;
@@ -797,13 +634,14 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const 
     __syncthreads();
     if (tid < ATT_D / 2) {
       const float amk = fmaxf(s_amax[0][0], s_amax[1][0]), amv = fmaxf(s_amax[0][1], s_amax[1][1]);
-      const float ik = amk > 0.f ? 127.f / amk : 0.f, iv = amv > 0.f ? 127.f / amv : 0.f;
+      constexpr float QMAX = FMT == KV_INT8 ? 127.f : 448.f;
+      const float ik = amk > 0.f ? QMAX / amk : 0.f, iv = amv > 0.f ? QMAX / amv : 0.f;
       const long long o = ((long long)bh * a.cap + slot_new) * ATT_D + 2 * tid;
-      *reinterpret_cast<uint16_t*>(a.kc + o) = (uint16_t)(quant_u8(k0, ik) | (quant_u8(k1, ik) << 8));
-      *reinterpret_cast<uint16_t*>(a.vc + o) = (uint16_t)(quant_u8(v0, iv) | (quant_u8(v1, iv) << 8));
+      *reinterpret_cast<uint16_t*>(a.kc + o) = quant2_q8<FMT>(k0 * ik, k1 * ik);
+      *reinterpret_cast<uint16_t*>(a.vc + o) = quant2_q8<FMT>(v0 * iv, v1 * iv);
       if (tid == 0) {
-        a.ks[(long long)bh * a.cap + slot_new] = amk * (1.f / 127.f);
-        a.vs[(long long)bh * a.cap + slot_new] = amv * (1.f / 127.f);
+        a.ks[(long long)bh * a.cap + slot_new] = amk * (1.f / QMAX);
+        a.vs[(long long)bh * a.cap + slot_new] = amv * (1.f / QMAX);
       }
     }
     __syncthreads();
@@ -833,25 +671,30 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  constexpr int U = 8;                              // keys in flight per half-warp (8 bytes per lane each)
-  for (int kb0 = s0; kb0 < s1; kb0 += 8 * U) {      // warp-uniform trip count (shuffles inside)
+  // Groups of U keys per half-warp, double-buffered in registers: the loads of group i + 1 are in flight while group i is
+  // reduced, so a warp's time per group is max(memory latency, arithmetic) instead of their sum (the bf16 kernel can
+  // afford the sum: it moves twice the bytes per key).
+  constexpr int U = 4;
+  struct Group { uint2 k[U], v[U]; float ks[U], vs[U]; };
+  auto load_group = [&](int kb0, Group& gp) {
     const int s = kb0 + hw * U;
-    uint2 kr[U], vr[U];
-    float ksc[U], vsc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int ss = s + u < s1 ? s + u : s1 - 1;
-      kr[u] = *reinterpret_cast<const uint2*>(kb + (long long)ss * ATT_D);
-      vr[u] = *reinterpret_cast<const uint2*>(vb + (long long)ss * ATT_D);
-      ksc[u] = ksb[ss];
-      vsc[u] = vsb[ss];
+      gp.k[u] = *reinterpret_cast<const uint2*>(kb + (long long)ss * ATT_D);
+      gp.v[u] = *reinterpret_cast<const uint2*>(vb + (long long)ss * ATT_D);
+      gp.ks[u] = ksb[ss];
+      gp.vs[u] = vsb[ss];
     }
+  };
+  auto reduce_group = [&](int kb0, const Group& gp) {
+    const int s = kb0 + hw * U;
     float d[U];
     float mn = m;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       __half2 kh[4];
-      unpack8_u8(kr[u], kh);
+      unpack8_q8<FMT>(gp.k[u], kh);
       __half2 t2 = __hmul2(qh[0], kh[0]);
       t2 = __hfma2(qh[1], kh[1], t2);
       t2 = __hfma2(qh[2], kh[2], t2);
@@ -862,12 +705,12 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const 
       t += __shfl_xor_sync(0xffffffffu, t, 4);
       t += __shfl_xor_sync(0xffffffffu, t, 2);
       t += __shfl_xor_sync(0xffffffffu, t, 1);
-      d[u] = s + u < s1 ? t * ksc[u] : -INFINITY;
+      d[u] = s + u < s1 ? t * gp.ks[u] : -INFINITY;
       mn = fmaxf(mn, d[u]);
     }
     if (mn > -INFINITY) {                           // uniform over the half-warp; no shuffles inside
       const float corr = __expf(m - mn);            // m = -inf -> 0
-      __half2 g[4];                                 // this group's weighted value sum (8 keys), packed fp16
+      __half2 g[4];                                 // this group's weighted value sum, packed fp16
 #pragma unroll
       for (int i = 0; i < 4; ++i) g[i] = __floats2half2_rn(0.f, 0.f);
       float lsum = 0.f;
@@ -875,9 +718,9 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const 
       for (int u = 0; u < U; ++u) {
         const float pw = __expf(d[u] - mn);         // padding keys: exp(-inf) = 0
         lsum += pw;
-        const __half2 pv = __float2half2_rn(pw * vsc[u]);
+        const __half2 pv = __float2half2_rn(pw * gp.vs[u]);
         __half2 vh[4];
-        unpack8_u8(vr[u], vh);
+        unpack8_q8<FMT>(gp.v[u], vh);
 #pragma unroll
         for (int i = 0; i < 4; ++i) g[i] = __hfma2(pv, vh[i], g[i]);
       }
@@ -889,6 +732,17 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_i8_kernel(const 
         acc[2 * i + 1] = fmaf(acc[2 * i + 1], corr, gf.y);
       }
       m = mn;
+    }
+  };
+  Group ga, gb;
+  if (s0 < s1) load_group(s0, ga);
+  for (int kb0 = s0; kb0 < s1; kb0 += 16 * U) {     // CTA-uniform trip count and branches (shuffles inside reduce_group)
+    const int k1 = kb0 + 8 * U, k2 = kb0 + 16 * U;
+    if (k1 < s1) load_group(k1, gb);
+    reduce_group(kb0, ga);
+    if (k1 < s1) {
+      if (k2 < s1) load_group(k2, ga);
+      reduce_group(k1, gb);
     }
   }
   // merge the 8 half-warps of the CTA, then the splits (same protocol as attn_step_kernel)

@@ -237,14 +237,14 @@ int b200_op_attn_step_q8(const void* qkv_dev, void* k8_dev, void* v8_dev, float*
     B200_CUDA(cudaMemset(counters, 0, (size_t)B * H * sizeof(int)));
     cnt_n = (size_t)B * H;
   }
-  AttnStepF8 a;
+  AttnStepQ8 a;
   a.qkv = static_cast<const bf16*>(qkv_dev); a.kc = static_cast<uint8_t*>(k8_dev); a.vc = static_cast<uint8_t*>(v8_dev);
   a.ks = ks_dev; a.vs = vs_dev; a.out = static_cast<bf16*>(out_dev); a.part = part; a.counters = counters;
   a.pos = reinterpret_cast<const long long*>(pos_dev); a.exec_mask = exec_mask_dev; a.H = H; a.cap = cap; a.nsplit = nsplit;
   a.neg_log_period_2_over_d = -logf(max_period) * 2.f / (float)ATT_D;
   dim3 grid(B * H, nsplit);
-  if (kv_dtype == B200_KV_INT8) B200_LAUNCH(attn_step_i8_kernel, grid, ATT_THREADS, 0, st, a);
-  else B200_LAUNCH(attn_step_f8_kernel, grid, ATT_THREADS, 0, st, a);
+  if (kv_dtype == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
+  else B200_LAUNCH(attn_step_q8_kernel<KV_E4M3>, grid, ATT_THREADS, 0, st, a);
   return check_launch("op_attn_step_q8");
 }
 

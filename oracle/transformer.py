@@ -174,7 +174,7 @@ def fp8_roundtrip(t: torch.Tensor) -> torch.Tensor:
     ``e4m3(t * (448 / absmax)) * (absmax / 448)``, round to nearest even (csrc/lm_kernels.cuh, attn_step_f8_kernel)."""
     t = t.float()
     amax = t.abs().amax(dim=-1, keepdim=True)
-    inv = torch.where(amax > 0, 448.0 / amax, torch.zeros_like(amax))
+    inv = torch.where(amax > 0, torch.full_like(amax, 448.0) / amax, torch.zeros_like(amax))   # (scalar / tensor is reciprocal * scalar in torch)
     q = (t * inv).to(torch.float8_e4m3fn).float()
     return q * (amax * (1.0 / 448.0))
 
@@ -184,7 +184,7 @@ def int8_roundtrip(t: torch.Tensor) -> torch.Tensor:
     even (csrc/lm_kernels.cuh, attn_step_i8_kernel)."""
     t = t.float()
     amax = t.abs().amax(dim=-1, keepdim=True)
-    inv = torch.where(amax > 0, 127.0 / amax, torch.zeros_like(amax))
+    inv = torch.where(amax > 0, torch.full_like(amax, 127.0) / amax, torch.zeros_like(amax))
     q = torch.round(t * inv).clamp_(-127, 127)
     return q * (amax * (1.0 / 127.0))
 

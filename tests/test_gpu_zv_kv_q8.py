@@ -31,7 +31,7 @@ FMT = {"fp8_e4m3": (1, 448.0), "int8": (2, 127.0)}
 def _encode(t, amax, fmt):
     """Row-scaled bytes as the kernel stores them."""
     qmax = FMT[fmt][1]
-    inv = torch.where(amax > 0, qmax / amax, torch.zeros_like(amax))
+    inv = torch.where(amax > 0, torch.full_like(amax, qmax) / amax, torch.zeros_like(amax))     # true division, like the kernel
     y = t.float() * inv[..., None]
     if fmt == "fp8_e4m3":
         return y.to(torch.float8_e4m3fn).view(torch.uint8)
@@ -139,37 +139,44 @@ def test_q8_ring_lm_matches_emulating_oracle(fmt, use_graph):
     assert agree / total > 0.9
 
 
-@pytest.mark.parametrize("fmt", ["int8", "fp8_e4m3"])
-def test_q8_ring_cost_against_bf16_ring(fmt):
-    """What the option costs: the 8-bit-ring model against the bf16-ring model fed the same input codes."""
-    from moshi_b200.config import tiny_lm_config
-    from moshi_b200.models import LMGen, LMModel
-    from moshi_b200.synth import synth_lm_state_dict
-    from oracle import scenarios
-    cfg = tiny_lm_config()
-    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
-    B, steps = 4, 24
-    codes = scenarios.lm_input_codes(cfg, B, steps)
-    logits = []
-    for kv in ("bf16", fmt):
-        lm = LMModel(cfg, sd, device="cuda")
-        gen = LMGen(lm, use_sampling=False)
-        gen.kv_dtype = kv
-        per_step = []
-        with gen.streaming(B):
-            for i in range(steps):
-                gen.step(codes[i].cuda())
-                per_step.append(gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).float().cpu())
-                if i == 0:
-                    state_bytes = lm._lib.b200_lm_state_bytes(lm._h)
-        logits.append((torch.stack(per_step), state_bytes))
-    (a, bytes_bf16), (b, bytes_fp8) = logits
-    # greedy feedback differs once a token flips; compare the steps before the first flip per row
-    same = (a.argmax(-1) == b.argmax(-1)).long().cumprod(dim=0).bool()         # [steps, B]
-    d = (a - b).abs().amax(-1)
-    rel = (d[same] / a.abs().amax(-1)[same]).max().item()
-    print(f"{fmt} vs bf16 ring: worst text-logit deviation {d[same].max().item():.3e} ({rel:.2%} of the row's max |logit|) over "
-          f"{int(same.sum())} comparable row-steps; snapshot bytes {bytes_bf16} -> {bytes_fp8}")
-    assert int(same.sum()) >= steps * B // 2
-    assert rel < 0.1
-    assert bytes_fp8 < 0.56 * bytes_bf16
+@pytest.mark.parametrize("fmt,outlier,bound", [("int8", 1.0, 0.02), ("fp8_e4m3", 1.0, 0.05), ("int8", 8.0, 0.08), ("fp8_e4m3", 8.0, 0.06)])
+def test_q8_ring_cost_against_exact_ring(fmt, outlier, bound):
+    """What the option costs: attention over a full 3000-slot 8-bit ring against fp32 attention over the unquantised
+    keys / values (keys with a few large channels, as rotary models have).  Reported as relative RMS error of the head
+    outputs; the bf16 ring's own error on the same data is printed beside it."""
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    kind, qmax = FMT[fmt]
+    B, H, cap = 2, 8, 3000
+    g = torch.Generator().manual_seed(5)
+    Cd = H * 128
+    chan = torch.ones(128)
+    chan[torch.randperm(128, generator=g)[:6]] = outlier                  # outlier channels
+    hist_k = (torch.randn(B, H, cap, 128, generator=g) * chan).bfloat16()
+    hist_v = torch.randn(B, H, cap, 128, generator=g).bfloat16()
+    qkv = torch.randn(B, 3 * Cd, generator=g).bfloat16()
+    pos = torch.full((B,), 2 * cap + 11, dtype=torch.int64)
+    mask = torch.ones(B, dtype=torch.bool)
+    q_in, k_in, v_in = (qkv[:, j * Cd:(j + 1) * Cd].reshape(B, H, 128) for j in range(3))
+    q_rot, k_rot = _rope_ref(q_in, pos), _rope_ref(k_in, pos)
+    ek, ev = hist_k.float().clone(), hist_v.float().clone()
+    for b in range(B):
+        ek[b, :, pos[b] % cap] = k_rot[b].float()
+        ev[b, :, pos[b] % cap] = v_in[b].float()
+    exact = F.scaled_dot_product_attention(q_rot.float()[:, :, None], ek, ev)[:, :, 0].reshape(B, Cd)
+    amax_k, amax_v = hist_k.float().abs().amax(-1), hist_v.float().abs().amax(-1)
+    k8, v8 = _encode(hist_k, amax_k, fmt).cuda(), _encode(hist_v, amax_v, fmt).cuda()
+    ks, vs = (amax_k * (1.0 / qmax)).cuda(), (amax_v * (1.0 / qmax)).cuda()
+    out = torch.empty(B, Cd, dtype=torch.bfloat16, device="cuda")
+    qd, pd, md = qkv.cuda(), pos.cuda(), mask.cuda()
+    _lib.check(lib.b200_op_attn_step_q8(cptr(qd), cptr(k8), cptr(v8), cptr(ks), cptr(vs), cptr(out), cptr(pd), cptr(md),
+                                        B, H, cap, 0, 10000.0, kind, _stream()))
+    kb, vb, out_b = hist_k.cuda(), hist_v.cuda(), torch.empty_like(out)
+    _lib.check(lib.b200_op_attn_step(cptr(qd), cptr(kb), cptr(vb), cptr(out_b), cptr(pd), cptr(md), B, H, cap, 0, 10000.0, _stream()))
+    torch.cuda.synchronize()
+    rms = exact.pow(2).mean().sqrt()
+    e_q8 = ((out.float().cpu() - exact).pow(2).mean().sqrt() / rms).item()
+    e_bf = ((out_b.float().cpu() - exact).pow(2).mean().sqrt() / rms).item()
+    print(f"{fmt} ring, key outlier channels x{outlier:g}: relative RMS error of the attention output {e_q8:.3%} (bf16 ring on the same data: {e_bf:.3%}); "
+          f"ring bytes per session at context 3000, 32 layers: {32 * 2 * 3000 * 32 * (128 + 4) / 1e9:.3f} GB vs 1.573 GB")
+    assert e_q8 < bound
