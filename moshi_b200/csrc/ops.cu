@@ -77,7 +77,7 @@ int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_til
   static float* ws = nullptr;
   static int* counters = nullptr;
   if (!ws) {
-    B200_CUDA(cudaMalloc(&ws, 1 << 20));
+    B200_CUDA(cudaMalloc(&ws, tc::sk_workspace_bytes(256)));      // int32 partials of cut tiles, like the bf16 path
     B200_CUDA(cudaMalloc(&counters, tc::SK_MAX_TILES * sizeof(int)));
     B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
   }
