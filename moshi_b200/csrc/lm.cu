@@ -214,7 +214,8 @@ int step_body(b200_lm* h) {
         a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
         a.neg_log_period_2_over_d = nl;
         dim3 grid(B * H, h->nsplit);
-        B200_LAUNCH(attn_step_kernel, grid, ATT_THREADS, 0, st, a);
+        if (attn_group_keys() == 2) B200_LAUNCH(attn_step_kernel<2>, grid, ATT_THREADS, 0, st, a);
+        else B200_LAUNCH(attn_step_kernel<4>, grid, ATT_THREADS, 0, st, a);
       }
       B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0, L.out_s));
       B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n2, h->xn, d, 1e-8f);

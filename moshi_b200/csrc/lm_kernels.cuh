@@ -276,6 +276,12 @@ constexpr int ATT_D = 128;
 constexpr int ATT_THREADS = 128;
 
 // split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
+// B200_ATT_U=2|4 (diagnostics): register-buffer depth of attn_step_kernel; default 4
+inline int attn_group_keys() {
+  static const int u = [] { const char* e = getenv("B200_ATT_U"); return (e && atoi(e) == 2) ? 2 : 4; }();
+  return u;
+}
+
 inline int attn_pick_splits(int B, int H, int cap) {
   int ns = (148 * 4 + B * H - 1) / (B * H);
   if (ns < 1) ns = 1;
@@ -403,6 +409,7 @@ struct AttnStep {
   int H, cap, nsplit; float neg_log_period_2_over_d;
 };
 
+template <int ATT_U>       // keys per half-warp per register buffer
 static __global__ void __launch_bounds__(ATT_THREADS) attn_step_kernel(const AttnStep a) {
   pdl_trigger();
   const int bh = blockIdx.x, split = blockIdx.y;
@@ -459,20 +466,25 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_kernel(const Att
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  constexpr int U = 4;                              // keys in flight per half-warp
-  for (int kb0 = s0; kb0 < s1; kb0 += 8 * U) {      // warp-uniform trip count (shuffles inside)
+  // Groups of U keys per half-warp, double-buffered in registers: the loads of group i + 1 are in flight while group i
+  // is reduced (same structure as attn_step_q8_kernel below).
+  constexpr int U = ATT_U;
+  struct Group { uint4 k[U], v[U]; };
+  auto load_group = [&](int kb0, Group& gp) {
     const int s = kb0 + hw * U;
-    uint4 kr[U], vr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int ss = s + u < s1 ? s + u : s1 - 1;
-      kr[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * ATT_D);
-      vr[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * ATT_D);
+      gp.k[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * ATT_D);
+      gp.v[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * ATT_D);
     }
+  };
+  auto reduce_group = [&](int kb0, const Group& gp) {
+    const int s = kb0 + hw * U;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float kf[8];
-      unpack8(kr[u], kf);
+      unpack8(gp.k[u], kf);
       float d = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
@@ -484,12 +496,23 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_kernel(const Att
         const float mn = fmaxf(m, d);
         const float corr = __expf(m - mn), pw = __expf(d - mn);
         float vf[8];
-        unpack8(vr[u], vf);
+        unpack8(gp.v[u], vf);
         l = l * corr + pw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(pw, vf[i], acc[i] * corr);
         m = mn;
       }
+    }
+  };
+  Group ga, gb;
+  if (s0 < s1) load_group(s0, ga);
+  for (int kb0 = s0; kb0 < s1; kb0 += 16 * U) {     // CTA-uniform trip count and branches (shuffles inside reduce_group)
+    const int k1 = kb0 + 8 * U, k2 = kb0 + 16 * U;
+    if (k1 < s1) load_group(k1, gb);
+    reduce_group(kb0, ga);
+    if (k1 < s1) {
+      if (k2 < s1) load_group(k2, ga);
+      reduce_group(k1, gb);
     }
   }
   // merge the 8 half-warps of the CTA

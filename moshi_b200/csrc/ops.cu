@@ -210,7 +210,8 @@ int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_d
   a.pos = reinterpret_cast<const long long*>(pos_dev); a.exec_mask = exec_mask_dev; a.H = H; a.cap = cap; a.nsplit = nsplit;
   a.neg_log_period_2_over_d = -logf(max_period) * 2.f / (float)ATT_D;
   dim3 grid(B * H, nsplit);
-  B200_LAUNCH(attn_step_kernel, grid, ATT_THREADS, 0, st, a);
+  if (attn_group_keys() == 2) B200_LAUNCH(attn_step_kernel<2>, grid, ATT_THREADS, 0, st, a);
+  else B200_LAUNCH(attn_step_kernel<4>, grid, ATT_THREADS, 0, st, a);
   return check_launch("op_attn_step");
 }
 

@@ -211,6 +211,60 @@ def test_rows_independent_graph_invariant_and_host_path():
         assert torch.equal(masked[i][[0, 1, 2] + list(range(4, B))], eager[i][[0, 1, 2] + list(range(4, B))])
 
 
+def test_full_size_7b_properties():
+    """BASELINE's own configuration (configs/moshi_7b_202409.json, random block-tiled weights) is too large for the CPU
+    oracle, so the full-size step is checked through size-independent properties: graph replay == eager launches; a
+    session's tokens do not depend on its slot or on its neighbours (no cross-row op anywhere, SURVEY 8e: the batch with
+    its rows permuted gives the permuted tokens, bit for bit); alone in a batch of one the same session gives the same
+    logits up to the fp32 summation order of the split-KV / split-K schedules, which are chosen per batch size; paused
+    rows do not move; outputs in range; the ring wraps at slot 3000."""
+    from moshi_b200.config import MOSHI_7B
+    from moshi_b200.models import LMGen, loaders
+    lm7 = loaders.get_moshi_lm(None, MOSHI_7B.to_reference_kwargs(), device="cuda", synth_device="cuda")
+    cfg = MOSHI_7B
+    B, steps = 5, 5
+    g = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, cfg.card, (steps, B, 8, 1), generator=g).cuda()
+    noise = torch.empty(steps, B, 25 + 8 * 250).exponential_(1, generator=g).cuda()
+
+    def run(rows, use_graph, fill=2997, paused=None, logits=None):
+        gen = LMGen(lm7)
+        gen.use_graph = use_graph
+        outs = []
+        with gen.streaming(len(rows)):
+            gen.assume_fill(fill)                      # steps cross the ring's wrap at 3000
+            for i in range(steps):
+                if paused is not None:
+                    m = torch.ones(len(rows), dtype=torch.bool)
+                    m[paused] = i != 2
+                    gen.set_exec_mask(m)
+                o = gen.step(codes[i][rows], noise=noise[i][rows].contiguous())
+                outs.append(o[:, :, 0].cpu())
+                if logits is not None and i == 0:
+                    logits.append(gen.read_buffer("text_logits", torch.bfloat16, (len(rows), cfg.text_card)).float().cpu())
+        return outs
+
+    rows = list(range(B))
+    perm = [4, 2, 0, 3, 1]
+    la, ls = [], []
+    eager, graph, shuffled = run(rows, False, logits=la), run(rows, True), run(perm, True)
+    run([3], True, logits=ls)
+    paused = run(rows, True, paused=1)
+    d = (la[0][3] - ls[0][0]).abs().max().item()
+    print(f"7B: text logits of session 3 in a batch of {B} vs alone: max |d| = {d:.3e}")
+    assert d < LOGIT_ATOL
+    for i in range(1, steps):
+        assert torch.equal(eager[i], graph[i]), i
+        assert torch.equal(eager[i][perm], shuffled[i]), i
+        assert (eager[i] >= 0).all() and (eager[i][:, 1:] < cfg.card).all() and (eager[i][:, 0] < cfg.text_card).all()
+    assert (paused[2][1] == -2).all()
+    keep = [0, 2, 3, 4]
+    for i in range(1, steps):
+        assert torch.equal(paused[i][keep], eager[i][keep]), i
+    del lm7
+    torch.cuda.empty_cache()
+
+
 @torch.no_grad()
 def test_streaming_state_snapshot_roundtrip(lm, tiny):
     """LMGen.get_streaming_state / set_streaming_state: the continuation from a snapshot is reproduced exactly."""
