@@ -188,6 +188,11 @@ int b200_lm_noise_per_row(b200_lm* h);
  *   support_out_of_sync: LMGen(support_out_of_sync=...) (lm.py:774-776) */
 int b200_lm_step(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev,
                  int64_t* out_tokens_dev, int support_out_of_sync, int* ready_host);
+/* LMGen.step(input_tokens, depformer_replace_tokens) (lm.py:668-669, 751-755: the TTS caller forces the audio tokens of a
+ * frame): replace_audio_dev i64 [B, dep_q] or NULL; when given, the depformer does not run and the text token is still
+ * sampled from the temporal transformer. */
+int b200_lm_step_ex(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev, const int64_t* replace_audio_dev,
+                    int64_t* out_tokens_dev, int support_out_of_sync, int* ready_host);
 int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const float* noise_host,
                       int64_t* out_tokens_host, int support_out_of_sync, int* ready_host);
 /* Hook / debug taps of the last step, copied into dst_dev (capacity in bytes; NULL = query size):

@@ -81,6 +81,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_set_exec_mask": (_I, [_P, _P]),
     "b200_lm_noise_per_row": (_I, [_P]),
     "b200_lm_step": (_I, [_P, _P, _I, _P, _P, _I, C.POINTER(_I)]),
+    "b200_lm_step_ex": (_I, [_P, _P, _I, _P, _P, _P, _I, C.POINTER(_I)]),
     "b200_lm_step_host": (_I, [_P, _P, _I, _P, _P, _I, C.POINTER(_I)]),
     "b200_lm_state_bytes": (C.c_int64, [_P]),
     "b200_lm_get_state": (_I, [_P, _P, C.c_int64]),

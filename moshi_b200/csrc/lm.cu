@@ -77,6 +77,8 @@ struct b200_lm {
   unsigned* dep_bar = nullptr;
   int nsplit = 1;
   int n_in_static = 0;
+  int replace_static = 0;                      // 1: this step's audio tokens are given (depformer_replace_tokens, lm.py:751-755)
+  long long* replace_tokens = nullptr;         // [B][dep_q] staging of those tokens
   // graph
   int graph_enabled = 1;
   cudaGraphExec_t graph_exec = nullptr;
@@ -230,6 +232,13 @@ int step_body(b200_lm* h) {
   // Depformer (lm.py:809-850): fresh KV state every frame, all rows advance together.
   const int kt = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
   const int ka = h->top_k < c.card ? h->top_k : c.card;
+  if (h->replace_static) {
+    // depformer_replace_tokens (lm.py:751-755): the caller supplies this frame's audio tokens, the depformer does not run
+    B200_LAUNCH(replace_audio_kernel, ceil_div(B * c.dep_q, 128), 128, 0, st, h->replace_tokens, h->audio_tokens, B, c.dep_q);
+    B200_LAUNCH(advance_pos_kernel, ceil_div(B, 128), 128, 0, st, h->pos, h->exec_mask, B);
+    B200_LAUNCH(lm_finish_kernel, ceil_div(B, 128), 128, 0, st, ring(h), h->text_token, h->audio_tokens, h->out_tokens, B);
+    return check_launch("lm step (replaced audio tokens)");
+  }
   B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, B, c.dep_q * dd, d, LIN_STORE, 0, h->dep_in_s));
   if (h->depf) {
     B200_TRY(tc::dep_fused_launch(h->depf, st));
@@ -477,6 +486,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->input_tokens, (size_t)B * h->Kc));
   B200_TRY(A.alloc_t(&h->text_token, B));
   B200_TRY(A.alloc_t(&h->audio_tokens, (size_t)B * c.dep_q));
+  B200_TRY(A.alloc_t(&h->replace_tokens, (size_t)B * c.dep_q));
   B200_TRY(A.alloc_t(&h->out_tokens, (size_t)B * (c.dep_q + 1)));
   B200_TRY(A.alloc_t(&h->noise, (size_t)B * noise_per_row(h), false));
   {
@@ -676,9 +686,10 @@ int b200_lm_assume_fill(b200_lm* h, int fill) {
   return B200_OK;
 }
 
-static int run_step(b200_lm* h, int n_in) {
-  if (n_in != h->n_in_static) {
+static int run_step(b200_lm* h, int n_in, int replace = 0) {
+  if (n_in != h->n_in_static || replace != h->replace_static) {     // the captured graph is specific to both
     h->n_in_static = n_in;
+    h->replace_static = replace;
     drop_graph(h);
   }
   B200_TRY(tc::prepare_plans(h->plans));
@@ -716,6 +727,11 @@ static int run_step(b200_lm* h, int n_in) {
 
 int b200_lm_step(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev, int64_t* out_tokens_dev,
                  int support_out_of_sync, int* ready_host) {
+  return b200_lm_step_ex(h, in_codes_dev, n_in, noise_dev, nullptr, out_tokens_dev, support_out_of_sync, ready_host);
+}
+
+int b200_lm_step_ex(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float* noise_dev, const int64_t* replace_audio_dev,
+                    int64_t* out_tokens_dev, int support_out_of_sync, int* ready_host) {
   B200_TRY(ensure_streaming(h, "lm_step"));
   const auto& c = h->cfg;
   const int B = h->batch, needed = c.n_q - c.dep_q;
@@ -726,7 +742,9 @@ int b200_lm_step(b200_lm* h, const int64_t* in_codes_dev, int n_in, const float*
   B200_CUDA(cudaMemcpyAsync(h->in_codes, in_codes_dev, (size_t)B * n_in * 8, cudaMemcpyDeviceToDevice, h->stream));
   if (noise_dev)
     B200_CUDA(cudaMemcpyAsync(h->noise, noise_dev, (size_t)B * noise_per_row(h) * 4, cudaMemcpyDeviceToDevice, h->stream));
-  B200_TRY(run_step(h, n_in));
+  if (replace_audio_dev)
+    B200_CUDA(cudaMemcpyAsync(h->replace_tokens, replace_audio_dev, (size_t)B * c.dep_q * 8, cudaMemcpyDeviceToDevice, h->stream));
+  B200_TRY(run_step(h, n_in, replace_audio_dev ? 1 : 0));
   B200_CUDA(cudaMemcpyAsync(out_tokens_dev, h->out_tokens, (size_t)B * (c.dep_q + 1) * 8, cudaMemcpyDeviceToDevice,
                             h->stream));
   h->offset_cpu += 1;

@@ -897,6 +897,15 @@ static __global__ void lm_reset_kernel(long long* offsets, long long* pos, uint8
   exec_mask[b] = 1;
 }
 
+// depformer_replace_tokens [B][dep_q] -> this frame's audio tokens [dep_q][B] (lm.py:751-755)
+static __global__ void replace_audio_kernel(const long long* __restrict__ given, long long* __restrict__ audio_tokens, int B, int dep_q) {
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dep_q) return;
+  const int b = i / dep_q, k = i - b * dep_q;
+  audio_tokens[(long long)k * B + b] = given[i];
+}
+
 static __global__ void advance_pos_kernel(long long* pos, const uint8_t* exec_mask, int B) {
   pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

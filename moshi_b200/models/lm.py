@@ -240,8 +240,6 @@ class LMGen:
     def _step(self, input_tokens: torch.Tensor, depformer_replace_tokens=None, noise: torch.Tensor | None = None):
         if self._batch is None:
             raise RuntimeError("You should wrap those calls with a `with lm_gen.streaming(): ...`.")   # lm.py:673-676
-        if depformer_replace_tokens is not None:
-            raise ValueError("depformer_replace_tokens (TTS) is outside the B200 hot path")
         lm = self.lm_model
         assert input_tokens.dim() == 3, "Shape should be [B, K, T]."
         B, Ki, S = input_tokens.shape
@@ -254,8 +252,13 @@ class LMGen:
             noise = self.draw_noise()
         out = torch.empty(B, lm.dep_q + 1, device=lm.device, dtype=torch.int64)
         ready = C.c_int(0)
-        _lib.check(self._lib.b200_lm_step(self._h, _lib.ptr(codes), needed, _lib.ptr(noise), _lib.ptr(out),
-                                          int(self.support_out_of_sync), C.byref(ready)))
+        replace = None
+        if depformer_replace_tokens is not None:            # lm.py:751-755
+            assert depformer_replace_tokens.dim() == 3
+            replace = depformer_replace_tokens.squeeze(-1).to(device=lm.device, dtype=torch.int64).contiguous()
+            assert replace.shape == (B, lm.dep_q), f"expected [{B}, {lm.dep_q}, 1] replacement tokens"
+        _lib.check(self._lib.b200_lm_step_ex(self._h, _lib.ptr(codes), needed, _lib.ptr(noise), _lib.ptr(replace), _lib.ptr(out),
+                                             int(self.support_out_of_sync), C.byref(ready)))
         if self.on_text_logits_hook is not None:
             tl = self.read_buffer("text_logits", torch.bfloat16, (B, lm.text_card))
             self.on_text_logits_hook(tl[:, None, None, :])

@@ -218,8 +218,8 @@ class LMOracle:
     @torch.no_grad()
     def step(self, input_tokens: torch.Tensor, noise_text: torch.Tensor | None = None,
              noise_audio: tp.Sequence[torch.Tensor] | None = None,
-             debug: dict | None = None, support_out_of_sync: bool = False
-             ) -> torch.Tensor | None:
+             debug: dict | None = None, support_out_of_sync: bool = False,
+             depformer_replace_tokens: torch.Tensor | None = None) -> torch.Tensor | None:
         """``LMGen._step`` (lm.py:668-783) -> [B, 1 + dep_q, 1] or None while warming up."""
         if self.batch is None:
             raise RuntimeError("call streaming(B) first")
@@ -250,7 +250,11 @@ class LMOracle:
                                   self.top_k_text, noise_text, self.tie_break)[:, 0, 0]
         # 5. depformer
         dep_logits: list = []
-        audio = self.depformer_step(text_token, transformer_out, noise_audio, dep_logits)
+        if depformer_replace_tokens is None:
+            audio = self.depformer_step(text_token, transformer_out, noise_audio, dep_logits)
+        else:                                      # lm.py:751-755: the caller forces this frame's audio tokens
+            assert depformer_replace_tokens.dim() == 3
+            audio = depformer_replace_tokens.squeeze(-1)
         if debug is not None:
             debug.update(input=inp, transformer_out=transformer_out, text_logits=text_logits,
                          text_token=text_token, audio_tokens=audio, dep_logits=dep_logits)

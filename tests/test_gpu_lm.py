@@ -211,6 +211,43 @@ def test_rows_independent_graph_invariant_and_host_path():
         assert torch.equal(masked[i][[0, 1, 2] + list(range(4, B))], eager[i][[0, 1, 2] + list(range(4, B))])
 
 
+def test_depformer_replace_tokens(lm, tiny):
+    """``LMGen.step(codes, depformer_replace_tokens=...)`` (lm.py:751-755, the TTS caller): the given audio tokens enter the
+    ring instead of the depformer's, the text token is still sampled; frames with and without replacement alternate
+    (two captured graphs), and the stream stays on the oracle's trajectory."""
+    from moshi_b200.models import LMGen
+    cfg, sd = tiny
+    B, steps = 3, 10
+    codes = scenarios.lm_input_codes(cfg, B, steps)
+    g = torch.Generator().manual_seed(3)
+    forced = torch.randint(0, cfg.card, (steps, B, cfg.dep_q, 1), generator=g)
+    gen = LMGen(lm, use_sampling=False)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, tie_break="index")
+    orc.streaming(B)
+    agree = total = 0
+    with gen.streaming(B):
+        for i in range(steps):
+            rep = forced[i] if i % 3 != 2 else None
+            dbg = {}
+            want = orc.step(codes[i], None, None, debug=dbg, depformer_replace_tokens=rep)
+            got = gen.step(codes[i].cuda(), depformer_replace_tokens=None if rep is None else rep.cuda())
+            at = gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()
+            tt = gen.read_buffer("text_token", torch.int64, (B,)).cpu()
+            if rep is not None:
+                assert torch.equal(at.t(), rep[:, :, 0])            # forced tokens are what the ring receives
+            assert (want is None) == (got is None)
+            if got is not None:
+                agree += int((got.cpu() == want).sum())
+                total += want.numel()
+            # keep the oracle on the GPU's trajectory (greedy near-ties)
+            pos = (orc.offsets % orc.cache.shape[2])
+            for b in range(B):
+                orc.cache[b, 0, pos[b]] = tt[b]
+                orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
+    print(f"replace tokens: {agree}/{total} output tokens equal to the oracle")
+    assert agree / total > 0.95
+
+
 def test_full_size_7b_properties():
     """BASELINE's own configuration (configs/moshi_7b_202409.json, random block-tiled weights) is too large for the CPU
     oracle, so the full-size step is checked through size-independent properties: graph replay == eager launches; a
