@@ -139,13 +139,6 @@ struct DepParams {
   const float* noise; long long noise_ld; int noise_off, ka; // Exp(1) noise, row stride, offset of sub-step 0, per-step width
   int use_sampling, top_k; float temp;
   unsigned* bar;                                             // grid barrier counter (zero at launch)
-  // Small batches (B <= 8, `red` = 1): every CTA keeps a private copy of the activations ([gridDim.x][Mpad][...]) and runs the
-  // row-wise phases (partial sums + residual + RMSNorm, attention over <= 8 keys, gated SiLU) for ALL rows itself, so a GEMM
-  // phase starts right after them without a grid barrier: 4 barriers per layer instead of 8.  Partials alternate between
-  // two buffer sets (a fast CTA's next GEMM must not overwrite what a slow CTA is still summing).
-  int red;
-  bf16 *x_priv, *xn_priv, *ao_priv, *h_priv;
-  float *partb0, *partb1;
 };
 
 // Temporal transformer (32 layers of one frame) as one persistent kernel, for small batches where the launch chain's
@@ -202,9 +195,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // sampled token is consumed by the CTA that produced it without a barrier)
 //   x_new = has_sum ? bf16(x + bf16(sum_s part[s][m][:])) : x (already written);  xn = rmsnorm(x_new, alpha)
 template <int NV, class P>                                    // dd <= NV * THREADS
-__device__ void row_phase(const P& p, bf16* x, bf16* xn, bool all, int dd, int S, const float* part, int N, bool has_sum,
-                          const bf16* alpha, float* red) {
-  for (int m = all ? 0 : blockIdx.x; m < p.B; m += all ? 1 : gridDim.x) {
+__device__ void row_phase(const P& p, int dd, int S, const float* part, int N, bool has_sum, const bf16* alpha, float* red) {
+  for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
     float vals[NV];
     float ss = 0.f;
 #pragma unroll
@@ -212,12 +204,12 @@ __device__ void row_phase(const P& p, bf16* x, bf16* xn, bool all, int dd, int S
       const int j = threadIdx.x + i * THREADS;
       float v = 0.f;
       if (j < dd) {
-        v = bf2f(x[(long long)m * dd + j]);
+        v = bf2f(p.x[(long long)m * dd + j]);
         if (has_sum) {
           float a = 0.f;
           for (int s = 0; s < S; ++s) a += __ldcg(part + ((long long)s * p.B + m) * N + j);
           v = rbf(v + rbf(a));                                // x_orig + update, both bf16 (transformer.py:769,777)
-          x[(long long)m * dd + j] = f2bf(v);
+          p.x[(long long)m * dd + j] = f2bf(v);
         }
         ss += v * v;
       }
@@ -229,38 +221,37 @@ __device__ void row_phase(const P& p, bf16* x, bf16* xn, bool all, int dd, int S
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int j = threadIdx.x + i * THREADS;
-        if (j < dd) xn[(long long)m * dd + j] = f2bf(vals[i] * (bf2f(alpha[j]) * r));
+        if (j < dd) p.xn[(long long)m * dd + j] = f2bf(vals[i] * (bf2f(alpha[j]) * r));
       }
     }
   }
 }
 
 // x = depformer_in[k](transformer_out) + emb_k(prev)   (lm.py:475-486; token -1 -> zero row, lm_utils.py:103-121)
-__device__ void input_rows(const DepParams& p, int k, bf16* x, bool all) {
+__device__ void input_rows(const DepParams& p, int k) {
   const long long* prev = k == 0 ? p.text_token : p.audio_tokens + (long long)(k - 1) * p.B;
   const bf16* table = p.tables[k];
-  for (int m = all ? 0 : blockIdx.x; m < p.B; m += all ? 1 : gridDim.x) {
+  for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
     const long long id = prev[m];
     for (int j = threadIdx.x; j < p.dd; j += THREADS) {
       const float e = id >= 0 ? bf2f(table[id * p.dd + j]) : 0.f;
-      x[(long long)m * p.dd + j] = f2bf(bf2f(p.din[(long long)m * p.din_ld + (long long)k * p.dd + j]) + e);
+      p.x[(long long)m * p.dd + j] = f2bf(bf2f(p.din[(long long)m * p.din_ld + (long long)k * p.dd + j]) + e);
     }
   }
   __syncthreads();                                            // row_phase re-reads x written by other threads of this CTA
 }
 
 // q,k,v = bf16(sum of in_proj partials); append k,v at slot `step`; attention over step+1 keys (no RoPE in the depformer)
-__device__ void attn_phase(const DepParams& p, int S, int layer, int step, const float* part, bf16* ao, bool all) {
+__device__ void attn_phase(const DepParams& p, int S, int layer, int step) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.dd, N = 3 * C;
   bf16* kc = p.kc[layer];
   bf16* vc = p.vc[layer];
-  // (all: every CTA writes the same K/V values to the per-frame cache; identical concurrent stores)
-  for (int it = all ? warp : blockIdx.x * (THREADS / 32) + warp; it < p.B * p.H; it += all ? THREADS / 32 : gridDim.x * (THREADS / 32)) {
+  for (int it = blockIdx.x * (THREADS / 32) + warp; it < p.B * p.H; it += gridDim.x * (THREADS / 32)) {
     const int b = it / p.H, h = it - b * p.H;
     float q[2] = {0.f, 0.f}, kk[2] = {0.f, 0.f}, vv[2] = {0.f, 0.f};
     for (int s = 0; s < S; ++s) {
-      const float* row = part + ((long long)s * p.B + b) * N + h * DD + 2 * lane;
+      const float* row = p.part0 + ((long long)s * p.B + b) * N + h * DD + 2 * lane;
       const float2 a = __ldcg(reinterpret_cast<const float2*>(row));
       const float2 c = __ldcg(reinterpret_cast<const float2*>(row + C));
       const float2 d = __ldcg(reinterpret_cast<const float2*>(row + 2 * C));
@@ -288,33 +279,32 @@ __device__ void attn_phase(const DepParams& p, int S, int layer, int step, const
       a0 = fmaf(sc[j] * inv, v.x, a0);
       a1 = fmaf(sc[j] * inv, v.y, a1);
     }
-    *reinterpret_cast<__nv_bfloat162*>(ao + (long long)b * C + h * DD + 2 * lane) = __floats2bfloat162_rn(a0, a1);
+    *reinterpret_cast<__nv_bfloat162*>(p.ao + (long long)b * C + h * DD + 2 * lane) = __floats2bfloat162_rn(a0, a1);
   }
 }
 
 // h = bf16(bf16(silu(bf16 gate)) * bf16 value)   (gating.py:18-20)
 template <class P>
-__device__ void gate_phase(const P& p, int S, const float* part0, const float* part1, bf16* hbuf, bool all) {
+__device__ void gate_phase(const P& p, int S) {
   const long long total = (long long)p.B * p.F;
-  for (long long i = all ? (long long)threadIdx.x : (long long)blockIdx.x * THREADS + threadIdx.x; i < total;
-       i += all ? (long long)THREADS : (long long)gridDim.x * THREADS) {
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * THREADS) {
     float g = 0.f, u = 0.f;
     for (int s = 0; s < S; ++s) {
-      g += __ldcg(part0 + (long long)s * total + i);
-      u += __ldcg(part1 + (long long)s * total + i);
+      g += __ldcg(p.part0 + (long long)s * total + i);
+      u += __ldcg(p.part1 + (long long)s * total + i);
     }
     g = rbf(g); u = rbf(u);
-    hbuf[i] = f2bf(rbf(g / (1.f + expf(-g))) * u);
+    p.hbuf[i] = f2bf(rbf(g / (1.f + expf(-g))) * u);
   }
 }
 
 // logits = bf16(sum partials) -> sample -> audio_tokens[k]
-__device__ void sample_phase(const DepParams& p, int S, int k, const float* part) {
+__device__ void sample_phase(const DepParams& p, int S, int k) {
   for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
     bf16* lg = p.logits + ((long long)k * p.B + m) * p.card;
     for (int j = threadIdx.x; j < p.card; j += THREADS) {
       float a = 0.f;
-      for (int s = 0; s < S; ++s) a += __ldcg(part + ((long long)s * p.B + m) * p.card + j);
+      for (int s = 0; s < S; ++s) a += __ldcg(p.part0 + ((long long)s * p.B + m) * p.card + j);
       lg[j] = f2bf(a);
     }
     __syncthreads();
@@ -327,8 +317,7 @@ __device__ void sample_phase(const DepParams& p, int S, int k, const float* part
 // One GEMM phase: units u = blockIdx.x, += gridDim.x; unit = (tile, split); partial [M x 128] -> part[split][m][tile*128 + row]
 template <class P>
 __device__ void gemm_phase(const P& p, const Gemm& g, const Gemm* next, const CUtensorMap* xmap, uint32_t base, uint32_t full0,
-                           uint32_t empty0, uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, Pipe& pipe, float* out0, float* out1,
-                           int xrow) {
+                           uint32_t empty0, uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, Pipe& pipe) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = g.n_tiles * g.S;
   const uint32_t a_bytes = (uint32_t)g.A * TILE_BYTES;
@@ -348,7 +337,7 @@ __device__ void gemm_phase(const P& p, const Gemm& g, const Gemm* next, const CU
             mbar_expect_tx(full0 + 8 * pipe.s, a_bytes + x_bytes);
             bulk_load(sa, src, a_bytes, full0 + 8 * pipe.s);
           }
-          tma_load_2d(sa + 2 * TILE_BYTES, xmap, full0 + 8 * pipe.s, kb * BLOCK_K, xrow);
+          tma_load_2d(sa + 2 * TILE_BYTES, xmap, full0 + 8 * pipe.s, kb * BLOCK_K, 0);
           if (++pipe.s == p.stages) { pipe.s = 0; pipe.ph ^= 1u; }
         }
       }
@@ -411,8 +400,8 @@ __device__ void gemm_phase(const P& p, const Gemm& g, const Gemm* next, const CU
       mbar_wait(tfull0 + 8 * pipe.acc, (pipe.acc_bits >> pipe.acc) & 1u);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pipe.acc * p.acc_cols);
-      float* o0 = out0 + (long long)sp * p.B * g.N + n;
-      float* o1 = out1 + (long long)sp * p.B * g.N + n;
+      float* o0 = p.part0 + (long long)sp * p.B * g.N + n;
+      float* o1 = p.part1 + (long long)sp * p.B * g.N + n;
       for (int c0 = 0; c0 < p.Mpad; c0 += 16) {
         if (c0 >= p.B) break;
         uint32_t r0[16], r1[16];
@@ -487,95 +476,40 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
     return g;
   };
   Gemm cur = gemm_at(0, 0, 0);
-  if (p.red) {
-    // ---- small batch: private activations, row-wise phases for all rows on every CTA, 4 grid barriers per layer ----
-    const long long prow = (long long)blockIdx.x * p.Mpad;
-    bf16* xp = p.x_priv + prow * p.dd;
-    bf16* xnp = p.xn_priv + prow * p.dd;
-    bf16* aop = p.ao_priv + prow * p.dd;
-    bf16* hp = p.h_priv + prow * p.F;
-    const int xrow = (int)prow;
-    int set = 0;                                  // partial buffer set of the GEMM phase that runs next
-    float *o0 = nullptr, *o1 = nullptr;
-    auto next_set = [&]() { o0 = set ? p.partb0 : p.part0; o1 = set ? p.partb1 : p.part1; set ^= 1; };
-    // private activations written with generic stores are read by this CTA's TMA (async proxy)
-    auto publish = [&]() { asm volatile("fence.proxy.async;" ::: "memory"); __syncthreads(); };
-    for (int k = 0; k < p.dep_q; ++k) {
-      input_rows(p, k, xp, true);
-      row_phase<4>(p, xp, xnp, true, p.dd, 0, nullptr, 0, false, p.n1[0], red);
-      publish();
-      for (int l = 0; l < p.L; ++l) {
-        Gemm nxt = gemm_at(k, l, 1);
-        next_set();
-        gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, o0, o1, xrow);
-        grid_sync(p.bar, epoch);
-        attn_phase(p, cur.S, l, k, o0, aop, true);
-        publish();
-        cur = nxt; nxt = gemm_at(k, l, 2);
-        next_set();
-        gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, o0, o1, xrow);
-        grid_sync(p.bar, epoch);
-        row_phase<4>(p, xp, xnp, true, p.dd, cur.S, o0, cur.N, true, p.n2[l], red);
-        publish();
-        cur = nxt; nxt = gemm_at(k, l, 3);
-        next_set();
-        gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, o0, o1, xrow);
-        grid_sync(p.bar, epoch);
-        gate_phase(p, cur.S, o0, o1, hp, true);
-        publish();
-        cur = nxt; nxt = l + 1 < p.L ? gemm_at(k, l + 1, 0) : gemm_at(k, 0, 4);
-        next_set();
-        gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, o0, o1, xrow);
-        grid_sync(p.bar, epoch);
-        row_phase<4>(p, xp, xnp, true, p.dd, cur.S, o0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
-        publish();
-        cur = nxt;
-      }
-      const bool last = k + 1 == p.dep_q;
-      Gemm nxt = last ? cur : gemm_at(k + 1, 0, 0);
-      next_set();
-      gemm_phase(p, cur, last ? nullptr : &nxt, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, o0, o1, xrow);
-      grid_sync(p.bar, epoch);
-      sample_phase(p, cur.S, k, o0);             // rows are spread over the CTAs here (the sampler is the heavy row op)
-      if (!last) grid_sync(p.bar, epoch);        // every CTA reads every row's token in the next sub-step's input_rows
-      cur = nxt;
-    }
-  } else {
   for (int k = 0; k < p.dep_q; ++k) {
-    input_rows(p, k, p.x, false);
-    row_phase<4>(p, p.x, p.xn, false, p.dd, 0, nullptr, 0, false, p.n1[0], red);
+    input_rows(p, k);
+    row_phase<4>(p, p.dd, 0, nullptr, 0, false, p.n1[0], red);
     grid_sync(p.bar, epoch);
     for (int l = 0; l < p.L; ++l) {
       Gemm nxt = gemm_at(k, l, 1);
-      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      attn_phase(p, cur.S, l, k, p.part0, p.ao, false);
+      attn_phase(p, cur.S, l, k);
       grid_sync(p.bar, epoch);
       cur = nxt; nxt = gemm_at(k, l, 2);
-      gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+      gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      row_phase<4>(p, p.x, p.xn, false, p.dd, cur.S, p.part0, cur.N, true, p.n2[l], red);
+      row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, p.n2[l], red);
       grid_sync(p.bar, epoch);
       cur = nxt; nxt = gemm_at(k, l, 3);
-      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+      gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
-      gate_phase(p, cur.S, p.part0, p.part1, p.hbuf, false);
+      gate_phase(p, cur.S);
       grid_sync(p.bar, epoch);
       cur = nxt; nxt = l + 1 < p.L ? gemm_at(k, l + 1, 0) : gemm_at(k, 0, 4);
-      gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+      gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
       grid_sync(p.bar, epoch);
       // depformer_norms is Identity (lm.py:197-198): after the last layer the head reads x itself
-      row_phase<4>(p, p.x, p.xn, false, p.dd, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
+      row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
       grid_sync(p.bar, epoch);
       cur = nxt;
     }
     const bool last = k + 1 == p.dep_q;
     Gemm nxt = last ? cur : gemm_at(k + 1, 0, 0);
-    gemm_phase(p, cur, last ? nullptr : &nxt, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+    gemm_phase(p, cur, last ? nullptr : &nxt, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
-    sample_phase(p, cur.S, k, p.part0);       // the next sub-step's input rows are the same rows of the same CTA: no barrier needed
+    sample_phase(p, cur.S, k);       // the next sub-step's input rows are the same rows of the same CTA: no barrier needed
     cur = nxt;
-  }
   }
   tc_fence_before();
   __syncthreads();
@@ -782,31 +716,31 @@ tmp_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
     else { g = p.g_lin_out; g.wt = w.lin_out; }
     return g;
   };
-  row_phase<16>(p, p.x, p.xn, false, p.d, 0, nullptr, 0, false, p.n1[0], red);        // xn = rmsnorm(x) for layer 0
+  row_phase<16>(p, p.d, 0, nullptr, 0, false, p.n1[0], red);        // xn = rmsnorm(x) for layer 0
   grid_sync(p.bar, epoch);
   Gemm cur = gemm_at(0, 0);
   for (int l = 0; l < p.L; ++l) {
     Gemm nxt = gemm_at(l, 1);
-    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
     ring_attn_phase(p, cur.S, l, sm_acc, sm_ml, s_last);
     grid_sync(p.bar, epoch);
     cur = nxt; nxt = gemm_at(l, 2);
-    gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+    gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
-    row_phase<16>(p, p.x, p.xn, false, p.d, cur.S, p.part0, cur.N, true, p.n2[l], red);
+    row_phase<16>(p, p.d, cur.S, p.part0, cur.N, true, p.n2[l], red);
     grid_sync(p.bar, epoch);
     cur = nxt; nxt = gemm_at(l, 3);
-    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
-    gate_phase(p, cur.S, p.part0, p.part1, p.hbuf, false);
+    gate_phase(p, cur.S);
     grid_sync(p.bar, epoch);
     cur = nxt;
     const bool last = l + 1 == p.L;
     if (!last) nxt = gemm_at(l + 1, 0);
-    gemm_phase(p, cur, last ? nullptr : &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe, p.part0, p.part1, 0);
+    gemm_phase(p, cur, last ? nullptr : &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
     grid_sync(p.bar, epoch);
-    row_phase<16>(p, p.x, p.xn, false, p.d, cur.S, p.part0, cur.N, true, last ? nullptr : p.n1[l + 1], red);   // out_norm is applied outside
+    row_phase<16>(p, p.d, cur.S, p.part0, cur.N, true, last ? nullptr : p.n1[l + 1], red);   // out_norm is applied outside
     grid_sync(p.bar, epoch);
     cur = nxt;
   }
@@ -857,7 +791,6 @@ struct DepFused {
   CUtensorMap map_xn, map_ao, map_h, map_x;
   int grid = 0; size_t smem = 0;
   void* dev_tables = nullptr;     // one allocation holding the pointer tables
-  void* dev_private = nullptr;    // small-batch mode: per-CTA activation copies + the second set of partial buffers
 };
 
 size_t dep_fused_partial_floats(const DepFusedConfig& c) {
@@ -934,32 +867,10 @@ int dep_fused_create(const DepFusedConfig& c, DepFused** out) {
   p.noise = c.noise; p.noise_ld = c.noise_ld; p.noise_off = c.noise_off; p.ka = c.ka;
   p.use_sampling = c.use_sampling; p.top_k = c.top_k; p.temp = c.temp;
   p.bar = c.bar;
-  int red_max_b = 2;      // beyond ~2 rows the 148 redundant re-reads of the partials through L2 cost more than the barriers they save
-  if (const char* e = getenv("B200_DEP_RED_MAX_B")) red_max_b = atoi(e);      // 0 switches the small-batch mode off
-  p.red = c.B <= red_max_b ? 1 : 0;
-  if (p.red) {
-    const size_t rows = (size_t)d->grid * p.Mpad;
-    const size_t act = rows * (size_t)(3 * c.dd + c.F) * sizeof(bf16);
-    const size_t pf = dep_fused_partial_floats(c);
-    if (cudaMalloc(&d->dev_private, act + 2 * pf * sizeof(float)) != cudaSuccess) {
-      dep_fused_destroy(d);
-      B200_FAIL(B200_ERR_CUDA, "fused depformer: cudaMalloc of the private activations failed");
-    }
-    B200_CUDA(cudaMemset(d->dev_private, 0, act + 2 * pf * sizeof(float)));     // rows B..Mpad of every copy stay zero
-    bf16* a = static_cast<bf16*>(d->dev_private);
-    p.x_priv = a; p.xn_priv = a + rows * c.dd; p.ao_priv = a + 2 * rows * c.dd; p.h_priv = a + 3 * rows * c.dd;
-    p.partb0 = reinterpret_cast<float*>(static_cast<uint8_t*>(d->dev_private) + act);
-    p.partb1 = p.partb0 + pf;
-    B200_TRY(make_map(enc, &d->map_xn, p.xn_priv, (int)rows, c.dd, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_ao, p.ao_priv, (int)rows, c.dd, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_h, p.h_priv, (int)rows, c.F, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_x, p.x_priv, (int)rows, c.dd, p.Mpad));
-  } else {
-    B200_TRY(make_map(enc, &d->map_xn, c.xn, c.B, c.dd, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_ao, c.ao, c.B, c.dd, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_h, c.hbuf, c.B, c.F, p.Mpad));
-    B200_TRY(make_map(enc, &d->map_x, c.x, c.B, c.dd, p.Mpad));
-  }
+  B200_TRY(make_map(enc, &d->map_xn, c.xn, c.B, c.dd, p.Mpad));
+  B200_TRY(make_map(enc, &d->map_ao, c.ao, c.B, c.dd, p.Mpad));
+  B200_TRY(make_map(enc, &d->map_h, c.hbuf, c.B, c.F, p.Mpad));
+  B200_TRY(make_map(enc, &d->map_x, c.x, c.B, c.dd, p.Mpad));
   d->smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
   B200_CUDA(cudaFuncSetAttribute(dep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   *out = d;
@@ -974,7 +885,6 @@ void dep_fused_set_sampling(DepFused* d, int use_sampling, float temp, int top_k
 void dep_fused_destroy(DepFused* d) {
   if (!d) return;
   if (d->dev_tables) cudaFree(d->dev_tables);
-  if (d->dev_private) cudaFree(d->dev_private);
   delete d;
 }
 

@@ -363,38 +363,3 @@ def test_fused_depformer_equals_launch_chain(B, monkeypatch):
         on_track &= (at_c == at_f).all(dim=0)
     print(f"fused vs chain, B={B}: greedy ids equal {same}/{total} on rows with identical history")
     assert same / total > 0.9
-
-
-@torch.no_grad()
-@pytest.mark.parametrize("B", [1, 2, 5, 8])
-def test_small_batch_depformer_mode_is_bit_identical(B, monkeypatch):
-    """Below a few sessions the persistent depformer kernel keeps a private copy of the activations per CTA and runs the
-    row-wise phases for all rows on every CTA (4 grid barriers per layer instead of 8).  Same partial sums in the same
-    order: logits and tokens must equal the distributed-rows schedule bit for bit."""
-    from moshi_b200.models import LMGen, LMModel
-    cfg = LMConfig(dim=1024, num_heads=8, num_layers=2, context=64, text_card=4000, card=2048,
-                   depformer_dim=1024, depformer_num_heads=16, depformer_dim_feedforward=4224, depformer_num_layers=3)
-    sd = synth_lm_state_dict(cfg, seed=11, device="cuda")
-    g = torch.Generator().manual_seed(B)
-    codes = torch.randint(0, cfg.card, (4, B, 8, 1), generator=g).cuda()
-    noise = torch.empty(4, B, 25 + 8 * 250).exponential_(1, generator=g).cuda()
-
-    def run(red_max_b: str, sampling: bool):
-        monkeypatch.setenv("B200_DEP_FUSED", "1")
-        monkeypatch.setenv("B200_DEP_RED_MAX_B", red_max_b)
-        lm = LMModel(cfg, sd, device="cuda")
-        gen = LMGen(lm, use_sampling=sampling)
-        outs = []
-        with gen.streaming(B):
-            for i in range(4):
-                gen.step(codes[i], noise=noise[i] if sampling else None)
-                outs.append((gen.read_buffer("dep_logits", torch.bfloat16, (cfg.dep_q, B, cfg.card)).cpu(),
-                             gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()))
-        del gen, lm
-        return outs
-
-    for sampling in (False, True):
-        spread, private = run("0", sampling), run("8", sampling)
-        for i, ((dl_s, at_s), (dl_p, at_p)) in enumerate(zip(spread, private)):
-            assert torch.equal(at_s, at_p), (sampling, i)
-            assert torch.equal(dl_s, dl_p), (sampling, i)
