@@ -649,6 +649,182 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// GEMV path for <= 4 sessions.  With one to four activation rows there is nothing for a tensor core to reuse: the GEMM
+// above is then just a weight stream, and its bulk-copy engine tops out at ~36 GB/s per SM (5.3 TB/s chip-wide, measured).
+// Plain 16-byte loads do not have that ceiling (the attention kernel streams 6.7 TB/s with them), so the same pre-tiled
+// weights are read with LDG.128 here: a CTA owns one 128-row tile (tile pair for the gated MLP) over a k-range, a thread
+// owns one 16-byte chunk position of four rows (the SWIZZLE_128B layout puts logical k-chunk (pos ^ (row & 7)) at position
+// pos, and row & 7 is the same for a thread's four rows, so it multiplies all of them with the same 8 activations), two
+// k-blocks of weights are in flight per thread (register double buffering), fp32 accumulation, 8-lane tree reduction at the
+// end, split partials summed in split order by the last CTA to arrive (deterministic), same epilogues as the GEMM.
+// ---------------------------------------------------------------------------------------------
+constexpr int GV_THREADS = 256;
+constexpr int GV_MAX_M = 4;
+constexpr int GV_MAX_KBPS = 44;            // k-blocks per split: M * 44 * 64 bf16 of activations in shared memory (<= 22.5 KB)
+
+struct GvParams {
+  int M, N, K, out_rows, gate_rows, n_tiles, num_kb, S, kbps;
+  const uint8_t* wt; const __nv_bfloat16* x; long long ldx;
+  __nv_bfloat16* y; long long ldy; const __nv_bfloat16* res; long long ldr;
+  float* ws; int* counters;               // partials [tile][split][A][M][128] fp32, arrival counters [tile] (zero between launches)
+};
+
+__device__ __forceinline__ void gv_unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void gv_store(const GvParams& p, int m, int n, float a, float b) {
+  float v;
+  if (EPI == EPI_STORE) v = a;
+  else if (EPI == EPI_RESADD) v = __bfloat162float(p.res[(long long)m * p.ldr + n]) + bf16_round(a);
+  else { const float g = bf16_round(a), u = bf16_round(b); v = bf16_round(g / (1.f + expf(-g))) * u; }
+  p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
+}
+
+template <int EPI, int M>
+__global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GvParams p) {
+  constexpr int A = EPI == EPI_GATE ? 2 : 1;
+  extern __shared__ __align__(16) uint8_t gv_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gv_smem);          // [M][kbps * 64]
+  __shared__ int s_last;
+  const int t = threadIdx.x;
+  const int tile = blockIdx.x / p.S, sp = blockIdx.x - tile * p.S;
+  const int kb0 = sp * p.kbps, kb1 = min(p.num_kb, kb0 + p.kbps);
+  const int span = p.kbps * BLOCK_K;
+  const int pos = t & 7, r0 = t >> 3;                 // rows r0, r0 + 32, r0 + 64, r0 + 96 of the tile
+  const int kc = (pos ^ (r0 & 7)) * 8;                // the 8 activations this thread multiplies with, inside a k-block
+  const uint4* wbase = reinterpret_cast<const uint4*>(p.wt + ((size_t)tile * p.num_kb + kb0) * (size_t)(A * TILE_BYTES)) + t;
+  pdl_trigger();
+
+  struct Group { uint4 w[A][4]; };
+  auto load_group = [&](int i, Group& g) {            // k-block kb0 + i of this split
+    const uint4* src = wbase + (size_t)i * (A * TILE_BYTES / 16);
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g.w[a][j] = __ldg(src + a * (TILE_BYTES / 16) + j * GV_THREADS);
+  };
+  Group ga, gb;
+  const int n_kb = kb1 - kb0;
+  if (n_kb > 0) load_group(0, ga);                    // weights do not depend on the preceding kernel
+  pdl_wait();
+  // activations of this k-range -> shared memory (zero beyond K)
+  for (int i = t * 8; i < M * span; i += GV_THREADS * 8) {
+    const int m = i / span, k = kb0 * BLOCK_K + (i - m * span);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k < p.K) v = *reinterpret_cast<const uint4*>(p.x + (long long)m * p.ldx + k);     // K % 8 == 0
+    *reinterpret_cast<uint4*>(xs + i) = v;
+  }
+  __syncthreads();
+
+  float acc[A][4][M];
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[a][j][m] = 0.f;
+  auto reduce_group = [&](int i, const Group& g) {
+    float xv[M][8];
+#pragma unroll
+    for (int m = 0; m < M; ++m) gv_unpack8(*reinterpret_cast<const uint4*>(xs + m * span + i * BLOCK_K + kc), xv[m]);
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float wf[8];
+        gv_unpack8(g.w[a][j], wf);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[a][j][m] = fmaf(wf[e], xv[m][e], acc[a][j][m]);
+      }
+  };
+  for (int i = 0; i < n_kb; i += 2) {
+    if (i + 1 < n_kb) load_group(i + 1, gb);
+    reduce_group(i, ga);
+    if (i + 1 < n_kb) {
+      if (i + 2 < n_kb) load_group(i + 2, ga);
+      reduce_group(i + 1, gb);
+    }
+  }
+  // the 8 lanes of a row hold the 8 chunk positions of its k-blocks
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        float v = acc[a][j][m];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        acc[a][j][m] = v;
+      }
+  if (p.S == 1) {
+    if (pos == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = tile * BLOCK_ROWS + r0 + 32 * j;
+        if (n < p.out_rows) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) gv_store<EPI>(p, m, n, acc[0][j][m], A == 2 ? acc[A - 1][j][m] : 0.f);
+        }
+      }
+    }
+    return;
+  }
+  float* slot = p.ws + ((size_t)tile * p.S + sp) * (size_t)(A * M * BLOCK_ROWS);
+  if (pos == 0) {
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < M; ++m) __stcg(slot + (a * M + m) * BLOCK_ROWS + r0 + 32 * j, acc[a][j][m]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const int old = atomicAdd(p.counters + tile, 1);
+    s_last = old == p.S - 1;
+    if (s_last) p.counters[tile] = 0;                // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* tbase = p.ws + (size_t)tile * p.S * (size_t)(A * M * BLOCK_ROWS);
+  for (int idx = t; idx < M * BLOCK_ROWS; idx += GV_THREADS) {
+    const int m = idx / BLOCK_ROWS, r = idx - m * BLOCK_ROWS;
+    const int n = tile * BLOCK_ROWS + r;
+    float a0 = 0.f, a1 = 0.f;
+    for (int s2 = 0; s2 < p.S; ++s2) {               // split order: the sum does not depend on who arrives last
+      const float* sl = tbase + (size_t)s2 * (A * M * BLOCK_ROWS);
+      a0 += __ldcg(sl + m * BLOCK_ROWS + r);
+      if (A == 2) a1 += __ldcg(sl + (M + m) * BLOCK_ROWS + r);
+    }
+    if (n < p.out_rows) gv_store<EPI>(p, m, n, a0, a1);
+  }
+}
+
+template <int EPI>
+static cudaError_t gv_launch(const cudaLaunchConfig_t& cfg, const GvParams& p) {
+  switch (p.M) {
+    case 1: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 1>, p);
+    case 2: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 2>, p);
+    case 3: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 3>, p);
+    default: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 4>, p);
+  }
+}
+
 // load-time repack: w [rows][K] row-major -> tiles [n_tile][kb][A][128 x 64] in the SWIZZLE_128B layout
 // (16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)); rows/cols beyond the tensor are zero.
 __global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ w, uint4* __restrict__ out, int rows, int K, int n_tiles,
@@ -770,6 +946,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 bool g_attr_set = false;
 int g_sms = 0;
+int g_gemv_max_m = GV_MAX_M;     // B200_GEMV_MAX_M (diagnostics): 0 sends every batch size through the tensor-core GEMM
 
 int init_once() {
   if (!g_encode) {
@@ -789,6 +966,7 @@ int init_once() {
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* e = getenv("B200_GEMV_MAX_M")) g_gemv_max_m = atoi(e);
     g_attr_set = true;
   }
   return B200_OK;
@@ -891,8 +1069,44 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tiles)) & 15)
     B200_FAIL(B200_ERR_SHAPE, "sk GEMM: operands must be 16-byte aligned");
   B200_TRY(init_once());
-  // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
   const bool i8 = tune.xq != nullptr;
+  // one to four sessions: stream the tiles with plain loads on the CUDA cores (no bulk-copy engine ceiling)
+  if (!i8 && M <= GV_MAX_M && tune.grid == 0 && tune.cluster == 0 && !tune.stream_only && g_gemv_max_m >= M) {
+    GvParams p;
+    p.M = M; p.N = N; p.K = K; p.gate_rows = gate_rows;
+    p.out_rows = epi == EPI_GATE ? gate_rows : N;
+    p.n_tiles = (p.out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
+    p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    if (p.n_tiles > SK_MAX_TILES) B200_FAIL(B200_ERR_SHAPE, "gemv: more than %d row tiles", SK_MAX_TILES);
+    const int A = epi == EPI_GATE ? 2 : 1;
+    // enough CTAs for ~4 per SM, every CTA streams at least 4 k-blocks, the activation slice fits in shared memory
+    int S = (4 * g_sms + p.n_tiles - 1) / p.n_tiles;
+    if (S > p.num_kb / 4) S = p.num_kb / 4;
+    if (S < 1) S = 1;
+    const int s_min = (p.num_kb + GV_MAX_KBPS - 1) / GV_MAX_KBPS;
+    if (S < s_min) S = s_min;
+    const size_t slot_bytes = (size_t)A * M * BLOCK_ROWS * 4;
+    while (S > s_min && (size_t)p.n_tiles * S * slot_bytes > sk_workspace_bytes(M)) --S;
+    p.kbps = (p.num_kb + S - 1) / S;
+    p.S = (p.num_kb + p.kbps - 1) / p.kbps;
+    if ((size_t)p.n_tiles * p.S * slot_bytes <= sk_workspace_bytes(M)) {
+      p.wt = static_cast<const uint8_t*>(w_tiles); p.x = x; p.ldx = ldx;
+      p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr; p.ws = ws; p.counters = counters;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(p.n_tiles * p.S)); cfg.blockDim = dim3(GV_THREADS);
+      cfg.dynamicSmemBytes = (size_t)M * p.kbps * BLOCK_K * 2; cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = tune.pdl ? 1 : 0;
+      const cudaError_t le = epi == EPI_STORE ? gv_launch<EPI_STORE>(cfg, p) : epi == EPI_RESADD ? gv_launch<EPI_RESADD>(cfg, p) : gv_launch<EPI_GATE>(cfg, p);
+      if (le != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "gemv launch failed: %s", cudaGetErrorString(le));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return check_launch("gemv");
+    }
+  }
+  // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
   if (i8 && (K % 16 || !tune.sa || !tune.sw)) B200_FAIL(B200_ERR_SHAPE, "int8 GEMM: K must be a multiple of 16 and both scale vectors given");
   if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {
     const int n_tiles = (N + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = i8 ? (K + 127) / 128 : (K + BLOCK_K - 1) / BLOCK_K;

@@ -156,8 +156,10 @@ def test_step_outside_streaming_raises(lm):
 @torch.no_grad()
 def test_rows_independent_graph_invariant_and_host_path():
     """Mid-size member of the 7B family at a serving batch, full 3000-slot ring machinery:
-    (1) graph replay == eager launches bit for bit, (2) row b of a batch == the same session alone,
-    (3) the host-buffer entry point returns the same tokens, (4) masked rows do not advance."""
+    (1) graph replay == eager launches bit for bit, (2) a session's tokens do not depend on its slot or its neighbours
+    (the batch with its rows reversed gives the reversed tokens; a *different batch size* may run other kernels — the GEMV
+    path below five sessions, other split points — so "alone" is only equal up to summation order and is checked on the
+    7B model's logits below), (3) the host-buffer entry point returns the same tokens, (4) masked rows do not advance."""
     from moshi_b200.models import LMGen, LMModel
     cfg = LMConfig(dim=1024, num_heads=8, num_layers=4, context=3000, text_card=32000, card=2048,
                    depformer_dim=512, depformer_num_heads=8, depformer_dim_feedforward=2112, depformer_num_layers=2)
@@ -193,12 +195,12 @@ def test_rows_independent_graph_invariant_and_host_path():
     eager = run(rows, False)
     graph = run(rows, True)
     host = run(rows, True, host=True)
-    solo = run([7], True)
+    flipped = run(rows[::-1], True)
     assert eager[0] is None and eager[1] is not None      # max_delay = 1: offset_cpu <= max_delay -> None (lm.py:774-776)
     for i in range(1, steps):
         assert torch.equal(eager[i], graph[i]), i
         assert torch.equal(eager[i], host[i]), i
-        assert torch.equal(eager[i][7:8], solo[i]), i
+        assert torch.equal(eager[i], flipped[i].flip(0)), i
         assert (eager[i] >= 0).all() and (eager[i][:, 1:] < cfg.card).all() and (eager[i][:, 0] < cfg.text_card).all()
     # ring wrap-around: positions near the 3000-slot capacity
     wrapped = run(rows, True, fill=2998)
