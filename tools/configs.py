@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""BASELINE.json configs 2-4 through the reference-shaped API, one JSON object per line.
+"""BASELINE.json configs 2-5 through the reference-shaped API, one JSON object per line.
 
     python tools/configs.py --config 2              # Mimi streaming encode+decode, B = 1 .. 256
     python tools/configs.py --config 3              # Moshi 7B LMGen.step, B = 1: p50/p90 latency, xRT (fill 200 and full ring)
     python tools/configs.py --config 4 [--sessions N]   # one GPU's shard of the 512-session config, all rows / 25 % masked
+    python tools/configs.py --config 5 [--kv-dtype int8]   # int8 (QLinear) weights: sessions swept up to what HBM holds
 """
 from __future__ import annotations
 
@@ -129,11 +130,49 @@ def config4(sessions: int):
                               "ms_per_step": round(ms, 2), "p_max_ms": round(max(times), 2), "real_time": ms <= 80.0}), flush=True)
 
 
+def config5(kv_dtype: str):
+    """int8 weights (row-wise absmax QLinear), 1 GPU: sweep the sessions upward until the step exceeds 80 ms or HBM is full."""
+    from moshi_b200.config import MOSHI_7B
+    from moshi_b200.models import LMGen, loaders
+    kw = MOSHI_7B.to_reference_kwargs()
+    kw["quantize"] = True
+    lm = loaders.get_moshi_lm(None, kw, device="cuda", synth_device="cuda")
+    mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
+    cfg = MOSHI_7B
+    free, _ = torch.cuda.mem_get_info()
+    kv_step = 524288 if kv_dtype == "bf16" else 32 * 2 * (4096 + 32 * 4)
+    cap = min(int((free - 6e9) // (kv_step * cfg.context + 40e6)), 256)
+    g = torch.Generator().manual_seed(4242)
+    for B in sorted({b for b in (16, 32, 64, 96, 128, 160, 192, 224) if b < cap} | {cap}):
+        pcm = (0.1 * torch.randn(B, 1, 1920, generator=g)).cuda()
+        gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
+        gen.kv_dtype = kv_dtype
+        with mimi.streaming(B), gen.streaming(B), torch.no_grad():
+            gen.assume_fill(cfg.context)
+            times = []
+            for i in range(28):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                codes = mimi.encode(pcm)
+                toks = gen.step(codes)
+                audio = toks[:, 1:].clamp(min=0) if toks is not None else torch.zeros(B, 8, 1, dtype=torch.int64, device="cuda")
+                mimi.decode(audio)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    times.append(e0.elapsed_time(e1))
+        times.sort()
+        print(json.dumps({"config": 5, "what": "Moshi 7B int8 linears (W8A8 QLinear) + Mimi, full 3000-frame rings", "kv_ring": kv_dtype,
+                          "sessions": B, "max_sessions_hbm": cap, "ms_per_step_mean": round(statistics.mean(times), 2),
+                          "ms_per_step_p99": round(times[-1], 2), "real_time": times[-1] <= 80.0}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True)
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256")
     ap.add_argument("--sessions", type=int, default=0)
+    ap.add_argument("--kv-dtype", default="bf16", choices=["bf16", "int8", "fp8_e4m3"])
     args = ap.parse_args()
     torch.cuda.set_device(0)
     if args.config == 2:
@@ -142,6 +181,8 @@ def main():
         config3()
     elif args.config == 4:
         config4(args.sessions)
+    elif args.config == 5:
+        config5(args.kv_dtype)
 
 
 if __name__ == "__main__":
