@@ -267,6 +267,9 @@ int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows);
 int b200_op_pack_tiles(const void* w_dev, void* out_dev, int N, int K, int epi, int gate_rows, void* stream);
 int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N,
                       int K, int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream);
+/* Up to how many activation rows the linears take the GEMV path (plain 16-byte loads on the CUDA cores instead of the
+ * tensor-core GEMM; csrc/gemm_sk.cu): 0..4, default 2 (or B200_GEMV_MAX_M).  Returns the previous value. */
+int b200_op_set_gemv_max_rows(int max_rows);
 /* int8 x int8 linear (QLinear, utils/quantize.py:13-40: bitsandbytes row-wise absmax quantisation of weights and
  * activations, int32 accumulation, dequantisation by both row scales / 127^2), on tcgen05 kind::i8.
  *   b200_op_quant_pack_tiles: w bf16 [N,K] -> int8 SWIZZLE_128B tiles (b200_op_packed_bytes_i8 bytes) + scales f32 [N]

@@ -650,7 +650,7 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// GEMV path for <= 4 sessions.  With one to four activation rows there is nothing for a tensor core to reuse: the GEMM
+// GEMV path for one or two sessions (up to four compiled).  With so few activation rows there is nothing for a tensor core to reuse: the GEMM
 // above is then just a weight stream, and its bulk-copy engine tops out at ~36 GB/s per SM (5.3 TB/s chip-wide, measured).
 // Plain 16-byte loads do not have that ceiling (the attention kernel streams 6.7 TB/s with them), so the same pre-tiled
 // weights are read with LDG.128 here: a CTA owns one 128-row tile (tile pair for the gated MLP) over a k-range, a thread
@@ -660,7 +660,7 @@ gemm_ck_kernel(const __grid_constant__ CUtensorMap tmap_x, const CkParams p) {
 // end, split partials summed in split order by the last CTA to arrive (deterministic), same epilogues as the GEMM.
 // ---------------------------------------------------------------------------------------------
 constexpr int GV_THREADS = 256;
-constexpr int GV_MAX_M = 4;
+constexpr int GV_MAX_M = 4;                // compiled for up to 4 rows; used for <= 2 by default (measured: B=1 -14 %, B=2 -11 %, B=4 +1 %)
 constexpr int GV_MAX_KBPS = 44;            // k-blocks per split: M * 44 * 64 bf16 of activations in shared memory (<= 22.5 KB)
 
 struct GvParams {
@@ -946,7 +946,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 bool g_attr_set = false;
 int g_sms = 0;
-int g_gemv_max_m = GV_MAX_M;     // B200_GEMV_MAX_M (diagnostics): 0 sends every batch size through the tensor-core GEMM
+int g_gemv_max_m = 2;            // B200_GEMV_MAX_M (0..4): 0 sends every batch size through the tensor-core GEMM
 
 int init_once() {
   if (!g_encode) {
@@ -975,6 +975,13 @@ int init_once() {
 }  // namespace
 
 int sk_num_sms() { return init_once() == B200_OK ? g_sms : 0; }
+
+int sk_set_gemv_max_m(int max_m) {
+  if (init_once() != B200_OK) return -1;
+  const int before = g_gemv_max_m;
+  g_gemv_max_m = max_m < 0 ? 0 : max_m > GV_MAX_M ? GV_MAX_M : max_m;
+  return before;
+}
 
 size_t sk_packed_bytes(int N, int K, int epi, int gate_rows) {
   const int a = epi == EPI_GATE ? 2 : 1;

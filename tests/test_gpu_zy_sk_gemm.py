@@ -130,3 +130,41 @@ def test_cluster_split_k(M, N, K, epi):
         assert torch.equal(y, _run(lib, x, wt, res, M, N, K, epi, 0, grid=-cs))
     auto = _run(lib, x, wt, res, M, N, K, epi, 0, grid=0)          # what the LM launches for this shape
     torch.testing.assert_close(auto.float(), want, rtol=1e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("N,K,epi", [(4096, 4096, STORE), (12288, 4096, STORE), (4096, 11264, RESADD), (1024, 2816, RESADD),
+                                     (22528, 4096, GATE), (5632, 1024, GATE), (200, 192, STORE)])
+def test_gemv_path_equals_tensor_core_path(M, N, K, epi):
+    """One to four sessions: the same pre-tiled weights streamed with plain loads on the CUDA cores (gemv_kernel) against fp32
+    math and against the tensor-core GEMM (both accumulate in fp32; only the summation order differs)."""
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M * 5 + N)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    rows = N
+    w = (torch.randn(rows, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    gate_rows = N // 2 if epi == GATE else 0
+    res = torch.randn(M, N, generator=g).bfloat16().cuda() if epi == RESADD else None
+    wt = _pack(lib, w, N, K, epi, gate_rows)
+    acc = x.float() @ w.float().t()
+    if epi == STORE:
+        want = acc
+    elif epi == RESADD:
+        want = res.float() + acc.bfloat16().float()
+    else:
+        h = acc.bfloat16()
+        want = (F.silu(h[:, :gate_rows].float()).bfloat16() * h[:, gate_rows:]).float()
+    before = lib.b200_op_set_gemv_max_rows(4)
+    try:
+        y_gemv = _run(lib, x, wt, res, M, N, K, epi, gate_rows)
+        again = _run(lib, x, wt, res, M, N, K, epi, gate_rows)
+        lib.b200_op_set_gemv_max_rows(0)
+        y_mma = _run(lib, x, wt, res, M, N, K, epi, gate_rows)
+    finally:
+        lib.b200_op_set_gemv_max_rows(before)
+    print(stats(f"gemv {M}x{N}x{K} epi={epi}", y_gemv, want), "| vs tensor-core path:", stats("", y_gemv, y_mma.float()))
+    assert not torch.isnan(y_gemv.float()).any()
+    torch.testing.assert_close(y_gemv.float(), want, rtol=2e-2, atol=3e-2)
+    assert torch.equal(y_gemv, again)                                   # split partials are summed in split order
+    assert ((y_gemv.float() - y_mma.float()).abs() > 0).float().mean() < 0.05      # a bf16 ulp apart now and then
