@@ -976,6 +976,8 @@ int init_once() {
 
 int sk_num_sms() { return init_once() == B200_OK ? g_sms : 0; }
 
+int sk_gemv_max_m() { return init_once() == B200_OK ? g_gemv_max_m : 0; }
+
 int sk_set_gemv_max_m(int max_m) {
   if (init_once() != B200_OK) return -1;
   const int before = g_gemv_max_m;

@@ -52,6 +52,7 @@ struct SkTuning {
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
 };
 int sk_num_sms();
+int sk_gemv_max_m();
 int sk_set_gemv_max_m(int max_m);      // rows up to which the GEMV path is taken (0..4); returns the previous value
 bool sk_supported(int M, int N, int K, int epi);
 size_t sk_packed_bytes(int N, int K, int epi, int gate_rows);

@@ -310,7 +310,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   }
   if (const char* e = getenv("B200_PDL")) h->pdl = atoi(e) != 0;
   if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
-  if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e) != 0;
+  if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e);
   if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
   if (const char* e = getenv("B200_KV_DTYPE")) {
     const std::string v = e;
@@ -525,7 +525,10 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     B200_TRY(A.alloc_t(&h->xq, (size_t)B * kmax, false));
     B200_TRY(A.alloc_t(&h->xq_scale, (size_t)B, false));
   }
-  if (!c.quantize && h->dep_fused && h->gemm_impl == 3 && B <= 256 && dd <= 1024 && dd % 64 == 0) {
+  // One or two sessions: the depformer's linears take the GEMV path and the PDL-chained launches beat the persistent kernel
+  // (B=1: 5.5 vs 6.4 ms per LM step, B=2: 6.2 vs 7.1; profiles/r01_r_*).  B200_DEP_FUSED=2 forces the kernel at any batch.
+  const bool dep_small = B <= tc::sk_gemv_max_m() && h->dep_fused != 2;
+  if (!c.quantize && h->dep_fused && !dep_small && h->gemm_impl == 3 && B <= 256 && dd <= 1024 && dd % 64 == 0) {
     tc::DepFusedConfig fc;
     memset(&fc, 0, sizeof(fc));
     fc.B = B; fc.dd = dd; fc.H = c.depformer_num_heads; fc.F = c.depformer_ffn_hidden; fc.card = c.card; fc.dep_q = c.dep_q;
