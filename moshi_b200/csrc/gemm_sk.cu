@@ -668,6 +668,7 @@ struct GvParams {
   const uint8_t* wt; const __nv_bfloat16* x; long long ldx;
   __nv_bfloat16* y; long long ldy; const __nv_bfloat16* res; long long ldr;
   float* ws; int* counters;               // partials [tile][split][A][M][128] fp32, arrival counters [tile] (zero between launches)
+  const __nv_bfloat16* norm_alpha;        // NORM: x is the residual stream, the linear's input is rmsnorm(x, alpha) (transformer.py:45-58)
 };
 
 __device__ __forceinline__ void gv_unpack8(const uint4& v, float* f) {
@@ -689,12 +690,14 @@ __device__ __forceinline__ void gv_store(const GvParams& p, int m, int n, float 
   p.y[(long long)m * p.ldy + n] = __float2bfloat16_rn(v);
 }
 
-template <int EPI, int M>
+template <int EPI, int M, bool NORM>
 __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GvParams p) {
   constexpr int A = EPI == EPI_GATE ? 2 : 1;
   extern __shared__ __align__(16) uint8_t gv_smem[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gv_smem);          // [M][kbps * 64]
   __shared__ int s_last;
+  __shared__ float s_red[GV_THREADS / 32][M];
+  __shared__ float s_rs[M];
   const int t = threadIdx.x;
   const int tile = blockIdx.x / p.S, sp = blockIdx.x - tile * p.S;
   const int kb0 = sp * p.kbps, kb1 = min(p.num_kb, kb0 + p.kbps);
@@ -716,11 +719,54 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GvParams p) {
   const int n_kb = kb1 - kb0;
   if (n_kb > 0) load_group(0, ga);                    // weights do not depend on the preceding kernel
   pdl_wait();
+  if (NORM) {
+    // RMSNorm folded into the staging (the row is 8 KB: every CTA takes the sum of squares of the whole row itself, which
+    // saves a kernel and a dependency per linear): xn = bf16(x * (alpha * rsqrt(eps + mean x^2))), eps 1e-8 (rms_norm_f32)
+    float ss[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ss[m] = 0.f;
+    for (int k = t * 8; k < p.K; k += GV_THREADS * 8) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        float f[8];
+        gv_unpack8(*reinterpret_cast<const uint4*>(p.x + (long long)m * p.ldx + k), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss[m] = fmaf(f[e], f[e], ss[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float v = ss[m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((t & 31) == 0) s_red[t >> 5][m] = v;
+    }
+    __syncthreads();
+    if (t < M) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_THREADS / 32; ++w) tot += s_red[w][t];
+      s_rs[t] = rsqrtf(1e-8f + tot / (float)p.K);
+    }
+    __syncthreads();
+  }
   // activations of this k-range -> shared memory (zero beyond K)
   for (int i = t * 8; i < M * span; i += GV_THREADS * 8) {
     const int m = i / span, k = kb0 * BLOCK_K + (i - m * span);
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (k < p.K) v = *reinterpret_cast<const uint4*>(p.x + (long long)m * p.ldx + k);     // K % 8 == 0
+    if (k < p.K) {
+      v = *reinterpret_cast<const uint4*>(p.x + (long long)m * p.ldx + k);     // K % 8 == 0
+      if (NORM) {
+        float f[8], al[8];
+        gv_unpack8(v, f);
+        gv_unpack8(*reinterpret_cast<const uint4*>(p.norm_alpha + k), al);
+        const float r = s_rs[m];
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(f[2 * e] * (al[2 * e] * r), f[2 * e + 1] * (al[2 * e + 1] * r));
+        v = *reinterpret_cast<const uint4*>(o);
+      }
+    }
     *reinterpret_cast<uint4*>(xs + i) = v;
   }
   __syncthreads();
@@ -815,14 +861,18 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GvParams p) {
   }
 }
 
+template <int EPI, bool NORM>
+static cudaError_t gv_launch_m(const cudaLaunchConfig_t& cfg, const GvParams& p) {
+  switch (p.M) {
+    case 1: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 1, NORM>, p);
+    case 2: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 2, NORM>, p);
+    case 3: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 3, NORM>, p);
+    default: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 4, NORM>, p);
+  }
+}
 template <int EPI>
 static cudaError_t gv_launch(const cudaLaunchConfig_t& cfg, const GvParams& p) {
-  switch (p.M) {
-    case 1: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 1>, p);
-    case 2: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 2>, p);
-    case 3: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 3>, p);
-    default: return cudaLaunchKernelEx(&cfg, gemv_kernel<EPI, 4>, p);
-  }
+  return p.norm_alpha ? gv_launch_m<EPI, true>(cfg, p) : gv_launch_m<EPI, false>(cfg, p);
 }
 
 // load-time repack: w [rows][K] row-major -> tiles [n_tile][kb][A][128 x 64] in the SWIZZLE_128B layout
@@ -1101,6 +1151,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
     if ((size_t)p.n_tiles * p.S * slot_bytes <= sk_workspace_bytes(M)) {
       p.wt = static_cast<const uint8_t*>(w_tiles); p.x = x; p.ldx = ldx;
       p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr; p.ws = ws; p.counters = counters;
+      p.norm_alpha = tune.norm_alpha;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)(p.n_tiles * p.S)); cfg.blockDim = dim3(GV_THREADS);
@@ -1115,6 +1166,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
       return check_launch("gemv");
     }
   }
+  if (tune.norm_alpha) B200_FAIL(B200_ERR_STATE, "sk GEMM: a fused RMSNorm input is only available on the GEMV path (M=%d)", M);
   // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
   if (i8 && (K % 16 || !tune.sa || !tune.sw)) B200_FAIL(B200_ERR_SHAPE, "int8 GEMM: K must be a multiple of 16 and both scale vectors given");
   if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {

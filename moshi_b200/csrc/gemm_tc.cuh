@@ -50,6 +50,8 @@ struct SkTuning {
   // int8 path (QLinear): row-wise absmax int8 activations [M][K] + their scales, and the weight-row scales [N]
   const void* xq = nullptr; const float* sa = nullptr; const float* sw = nullptr;
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
+  // GEMV path only (M <= sk_gemv_max_m()): x is the residual stream and the linear's input is rmsnorm(x, norm_alpha)
+  const __nv_bfloat16* norm_alpha = nullptr;
 };
 int sk_num_sms();
 int sk_gemv_max_m();

@@ -72,6 +72,7 @@ struct b200_lm {
   int tmp_fused_max_b = 0;                     // B200_TMP_FUSED_MAX_B
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
   int dep_fused = 1;
+  int fuse_norm = 1;                           // B200_FUSE_NORM=0: keep rmsnorm_kernel in front of the GEMV path too (diagnostics)
   int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE: opt-in 8-bit KV ring (B200_KV_FP8_E4M3 or B200_KV_INT8; 0 = bf16)
   float *dep_part0 = nullptr, *dep_part1 = nullptr;
   unsigned* dep_bar = nullptr;
@@ -115,12 +116,15 @@ int noise_per_row(const b200_lm* h) {
 // y[M][N] = epi(x[M][K] . w[N][K]^T).  `w` is the packed-tile form (gemm_sk.cu) unless a legacy kernel was
 // selected with B200_GEMM_IMPL (1 = SIMT, 2 = one-tile-per-CTA tcgen05), in which case it is row-major.
 int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, const bf16* res,
-           long long ldr, int M, int N, int K, int epi, int gate_rows, const float* w_scales = nullptr) {
+           long long ldr, int M, int N, int K, int epi, int gate_rows, const float* w_scales = nullptr,
+           const bf16* norm_alpha = nullptr) {
   const int impl = h->gemm_impl;
+  if (impl != 3 && norm_alpha) B200_FAIL(B200_ERR_STATE, "fused RMSNorm input needs the packed-tile GEMM");
   if (impl == 3) {
     tc::SkTuning t;
     t.pdl = h->pdl;
     t.smem_budget = h->sk_smem;
+    t.norm_alpha = norm_alpha;
     if (h->cfg.quantize) {       // QLinear.forward (utils/quantize.py:22-40): row-wise int8 activations, int8 x int8 -> int32
       if (!w_scales) B200_FAIL(B200_ERR_STATE, "quantised LM: linear without weight scales");
       B200_TRY(tc::sk_quantize_rows(x, ldx, h->xq, h->xq_scale, M, K, h->body, h->pdl));
@@ -141,6 +145,16 @@ int linear(b200_lm* h, const bf16* x, long long ldx, const bf16* w, bf16* y, lon
     B200_LAUNCH(k, grid, 256, 0, h->body, x, ldx, w, y, ldy, res, ldr, M, N, K, gate_rows);
   }
   return check_launch("linear_simt");
+}
+
+// y = epi(rmsnorm(x, alpha) . w^T).  One or two sessions: the norm is folded into the GEMV's activation staging (one kernel
+// and one dependency less per linear); otherwise rmsnorm_kernel writes xn and the GEMM reads it.
+int norm_linear(b200_lm* h, const bf16* x, const bf16* alpha, bf16* xn, const bf16* w, bf16* y, long long ldy, int M, int N, int K,
+                int epi, int gate_rows, const float* w_scales) {
+  if (h->gemm_impl == 3 && !h->cfg.quantize && h->fuse_norm && M <= tc::sk_gemv_max_m())
+    return linear(h, x, K, w, y, ldy, nullptr, 0, M, N, K, epi, gate_rows, w_scales, alpha);
+  B200_LAUNCH(rmsnorm_kernel, M, 256, 0, h->body, x, alpha, xn, K, 1e-8f);
+  return linear(h, xn, K, w, y, ldy, nullptr, 0, M, N, K, epi, gate_rows, w_scales);
 }
 
 // Linear weight from the store -> the layout the selected GEMM reads.  Packed tiles replace the row-major
@@ -200,8 +214,7 @@ int step_body(b200_lm* h) {
     B200_TRY(tc::tmp_fused_launch(h->tmpf, st));
   } else {
     for (auto& L : h->layers) {
-      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n1, h->xn, d, 1e-8f);
-      B200_TRY(linear(h, h->xn, d, L.in_w, h->qkv, 3 * d, nullptr, 0, B, 3 * d, d, LIN_STORE, 0, L.in_s));
+      B200_TRY(norm_linear(h, h->x, L.n1, h->xn, L.in_w, h->qkv, 3 * d, B, 3 * d, d, LIN_STORE, 0, L.in_s));
       if (h->kv_fp8) {
         AttnStepQ8 a;
         a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
@@ -220,8 +233,7 @@ int step_body(b200_lm* h) {
         else B200_LAUNCH(attn_step_kernel<4>, grid, ATT_THREADS, 0, st, a);
       }
       B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0, L.out_s));
-      B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, L.n2, h->xn, d, 1e-8f);
-      B200_TRY(linear(h, h->xn, d, L.lin_in, h->hbuf, F, nullptr, 0, B, F, d, LIN_GATE, F, L.lin_in_s));
+      B200_TRY(norm_linear(h, h->x, L.n2, h->xn, L.lin_in, h->hbuf, F, B, F, d, LIN_GATE, F, L.lin_in_s));
       B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0, L.lin_out_s));
     }
   }
@@ -248,12 +260,10 @@ int step_body(b200_lm* h) {
       B200_LAUNCH(dep_input_kernel, ceil_div(B * dd, 256), 256, 0, st, h->din, (long long)c.dep_q * dd, k * dd,
                   h->dep_tables[k], prev, h->dx, B, dd);
       for (auto& L : h->dlayers) {
-        B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n1, h->dxn, dd, 1e-8f);
-        B200_TRY(linear(h, h->dxn, dd, L.in_w[k], h->dqkv, 3 * dd, nullptr, 0, B, 3 * dd, dd, LIN_STORE, 0, L.in_s[k]));
+        B200_TRY(norm_linear(h, h->dx, L.n1, h->dxn, L.in_w[k], h->dqkv, 3 * dd, B, 3 * dd, dd, LIN_STORE, 0, L.in_s[k]));
         B200_LAUNCH(dep_attn_step_kernel, ceil_div(B * dH * 32, 128), 128, 0, st, h->dqkv, L.kc, L.vc, h->dao, B, dH, c.dep_q, k);
         B200_TRY(linear(h, h->dao, dd, L.out_w[k], h->dx, dd, h->dx, dd, B, dd, dd, LIN_RESADD, 0, L.out_s[k]));
-        B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->dx, L.n2, h->dxn, dd, 1e-8f);
-        B200_TRY(linear(h, h->dxn, dd, L.lin_in[k], h->dh, dF, nullptr, 0, B, dF, dd, LIN_GATE, dF, L.lin_in_s[k]));
+        B200_TRY(norm_linear(h, h->dx, L.n2, h->dxn, L.lin_in[k], h->dh, dF, B, dF, dd, LIN_GATE, dF, L.lin_in_s[k]));
         B200_TRY(linear(h, h->dh, dF, L.lin_out[k], h->dx, dd, h->dx, dd, B, dd, dF, LIN_RESADD, 0, L.lin_out_s[k]));
       }
       bf16* logits = h->dep_logits + (long long)k * B * c.card;
@@ -312,6 +322,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
   if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e);
   if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
+  if (const char* e = getenv("B200_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
   if (const char* e = getenv("B200_KV_DTYPE")) {
     const std::string v = e;
     h->kv_fp8 = (v == "fp8" || v == "fp8_e4m3") ? B200_KV_FP8_E4M3 : v == "int8" ? B200_KV_INT8 : 0;

@@ -367,3 +367,40 @@ def test_fused_depformer_equals_launch_chain(B, monkeypatch):
         on_track &= (at_c == at_f).all(dim=0)
     print(f"fused vs chain, B={B}: greedy ids equal {same}/{total} on rows with identical history")
     assert same / total > 0.9
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_one_and_two_sessions_take_the_gemv_path(lm, tiny, B):
+    """Below three sessions every linear runs as gemv_kernel (plain loads, RMSNorm folded into the activation staging) and
+    the depformer as a launch chain: same oracle, same tolerance, teacher-synchronised greedy steps across the ring wrap."""
+    from moshi_b200.models import LMGen
+    cfg, sd = tiny
+    steps = 16
+    codes = scenarios.lm_input_codes(cfg, 3, steps)[:, :B]
+    gen = LMGen(lm, use_sampling=False)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, tie_break="index")
+    orc.streaming(B)
+    worst = 0.0
+    agree = total = 0
+    with gen.streaming(B):
+        for i in range(steps):
+            dbg = {}
+            orc.step(codes[i], None, None, debug=dbg)
+            gen.step(codes[i].cuda())
+            tl = gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).float().cpu()
+            dl = gen.read_buffer("dep_logits", torch.bfloat16, (cfg.dep_q, B, cfg.card)).float().cpu()
+            tt = gen.read_buffer("text_token", torch.int64, (B,)).cpu()
+            at = gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()
+            worst = max(worst, (tl - dbg["text_logits"].float()[:, 0, 0]).abs().max().item())
+            same_text = tt == dbg["text_token"]
+            if same_text.any():
+                worst = max(worst, (dl[0] - dbg["dep_logits"][0].float()[:, 0, 0])[same_text].abs().max().item())
+            agree += int(same_text.sum()) + int((at.t() == dbg["audio_tokens"]).sum())
+            total += B * (1 + cfg.dep_q)
+            pos = (orc.offsets % orc.cache.shape[2])
+            for b in range(B):
+                orc.cache[b, 0, pos[b]] = tt[b]
+                orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
+    print(f"B={B} (GEMV path): worst logit diff {worst:.3e}, greedy tokens equal {agree}/{total}")
+    assert worst < LOGIT_ATOL
+    assert agree / total > 0.95
