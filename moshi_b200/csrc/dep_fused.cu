@@ -141,24 +141,6 @@ struct DepParams {
   unsigned* bar;                                             // grid barrier counter (zero at launch)
 };
 
-// Temporal transformer (32 layers of one frame) as one persistent kernel, for small batches where the launch chain's
-// per-kernel latency dominates (the ring attention runs in-kernel; at large batch the stand-alone attention kernel
-// keeps more bytes in flight and the launch chain is used instead).
-struct TmpParams {
-  int B, Mpad, d, H, F, L, cap, nsplit;
-  int stages; uint32_t stage_bytes, tmem_cols, acc_cols; int n_acc;
-  Gemm g_in, g_out, g_lin_in, g_lin_out;
-  const DepLayerW* w;                                        // [L]
-  const bf16* const* n1; const bf16* const* n2;              // [L]
-  bf16 *x, *xn, *ao, *hbuf;                                  // [B][d] x3, [B][F]
-  bf16* const* kc; bf16* const* vc;                          // [L] rings [B][H][cap][128]
-  float *part0, *part1;
-  float* attn_part; int* attn_counters;                      // split partials [B*H][nsplit][130], arrival counters [B*H]
-  const long long* pos; const uint8_t* exec_mask;
-  float neg_log_period_2_over_d;
-  unsigned* bar;
-};
-
 namespace {
 
 struct Pipe { int s; uint32_t ph; int acc; uint32_t acc_bits; int pre; };   // per-role pipeline cursor, carried across phases
@@ -516,239 +498,6 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// ---- temporal ring attention inside the persistent kernel -------------------------------------------------------------
-// Work item = (b, h, split); a group of 128 threads (two groups per CTA) processes one item exactly like
-// lm::attn_step_kernel: q,k,v = bf16(sum of the in_proj partials), RoPE, the split that owns the new key's slot appends
-// K/V, online-softmax over its key range, last-arriving split merges in split order.
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-
-__device__ void ring_attn_phase(const TmpParams& p, int S, int layer, float (*sm_acc)[8][lm::ATT_D], float (*sm_ml)[16], int* s_last) {
-  constexpr int D = lm::ATT_D;
-  const int g = threadIdx.x >> 7, tid = threadIdx.x & 127, lane = tid & 31, l16 = lane & 15, hw = tid >> 4;
-  const int C = p.H * D, N = 3 * C;
-  bf16* kc = p.kc[layer];
-  bf16* vc = p.vc[layer];
-  const int items = p.B * p.H * p.nsplit;
-  for (int it = blockIdx.x * 2 + g; it < items; it += gridDim.x * 2) {
-    const int bh = it / p.nsplit, split = it - bh * p.nsplit;
-    const int b = bh / p.H, h = bh - b * p.H;
-    const bool exec = p.exec_mask[b] != 0;
-    const long long pos = p.pos[b];
-    long long n_valid = pos + (exec ? 1 : 0);
-    if (n_valid > p.cap) n_valid = p.cap;
-    const int per = (int)((n_valid + p.nsplit - 1) / p.nsplit);
-    const int s0 = split * per;
-    const int s1 = (int)min((long long)(s0 + per), n_valid);
-    const int slot_new = (int)(pos % p.cap);
-    const float fpos = (float)pos;
-    const float* prow = p.part0 + (long long)b * N + h * D;           // + s * B * N per split
-    const long long sstride = (long long)p.B * N;
-
-    if (exec && slot_new >= s0 && slot_new < s1) {                     // group-uniform
-      if (tid < D / 2) {
-        const int pr = tid;
-        float kr = 0.f, ki = 0.f, vr = 0.f, vi = 0.f;
-        for (int s = 0; s < S; ++s) {
-          const float2 kk = __ldcg(reinterpret_cast<const float2*>(prow + s * sstride + C + 2 * pr));
-          const float2 vv = __ldcg(reinterpret_cast<const float2*>(prow + s * sstride + 2 * C + 2 * pr));
-          kr += kk.x; ki += kk.y; vr += vv.x; vi += vv.y;
-        }
-        kr = rbf(kr); ki = rbf(ki);
-        const float freq = expf((float)pr * p.neg_log_period_2_over_d);
-        float sn, cs;
-        sincosf(freq * fpos, &sn, &cs);
-        const long long o = ((long long)bh * p.cap + slot_new) * D + 2 * pr;
-        *reinterpret_cast<__nv_bfloat162*>(kc + o) = __floats2bfloat162_rn(kr * cs - ki * sn, kr * sn + ki * cs);
-        *reinterpret_cast<__nv_bfloat162*>(vc + o) = __floats2bfloat162_rn(vr, vi);
-      }
-      group_sync(g);
-    }
-    float qf[8];
-    {
-      float raw[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = 0.f;
-      for (int s = 0; s < S; ++s) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(prow + s * sstride + l16 * 8));
-        const float4 c = __ldcg(reinterpret_cast<const float4*>(prow + s * sstride + l16 * 8 + 4));
-        raw[0] += a.x; raw[1] += a.y; raw[2] += a.z; raw[3] += a.w; raw[4] += c.x; raw[5] += c.y; raw[6] += c.z; raw[7] += c.w;
-      }
-      const float scale = 0.08838834764831845f;       // 1/sqrt(128)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pr = l16 * 4 + j;
-        const float freq = expf((float)pr * p.neg_log_period_2_over_d);
-        float sn, cs;
-        sincosf(freq * fpos, &sn, &cs);
-        const float qr = rbf(raw[2 * j]), qi = rbf(raw[2 * j + 1]);
-        qf[2 * j] = rbf(qr * cs - qi * sn) * scale;
-        qf[2 * j + 1] = rbf(qr * sn + qi * cs) * scale;
-      }
-    }
-    const bf16* kb = kc + (long long)bh * p.cap * D + l16 * 8;
-    const bf16* vb = vc + (long long)bh * p.cap * D + l16 * 8;
-    float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    constexpr int U = 4;
-    for (int kb0 = s0; kb0 < s1; kb0 += 8 * U) {
-      const int sk = kb0 + hw * U;
-      uint4 kr[U], vr[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ss = sk + u < s1 ? sk + u : s1 - 1;
-        kr[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * D);
-        vr[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * D);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float kf[8];
-        lm::unpack8(kr[u], kf);
-        float dsum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dsum = fmaf(qf[i], kf[i], dsum);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 8);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-        if (sk + u < s1) {
-          const float mn = fmaxf(m, dsum);
-          const float corr = __expf(m - mn), pw = __expf(dsum - mn);
-          float vf[8];
-          lm::unpack8(vr[u], vf);
-          l = l * corr + pw;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(pw, vf[i], acc[i] * corr);
-          m = mn;
-        }
-      }
-    }
-    group_sync(g);                                   // the previous item's readers are done with the merge buffers
-    if (l16 == 0) { sm_ml[g][hw] = m; sm_ml[g][8 + hw] = l; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm_acc[g][hw][l16 * 8 + i] = acc[i];
-    group_sync(g);
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_ml[g][w]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float c = sm_ml[g][w] == -INFINITY ? 0.f : __expf(sm_ml[g][w] - M);
-      L += sm_ml[g][8 + w] * c;
-      A += sm_acc[g][w][tid] * c;
-    }
-    if (p.nsplit == 1) {
-      p.ao[(long long)bh * D + tid] = f2bf(L > 0.f ? A / L : 0.f);
-      continue;
-    }
-    float* o = p.attn_part + ((long long)bh * p.nsplit + split) * (D + 2);
-    __stcg(o + tid, A);
-    if (tid == 0) { __stcg(o + D, M); __stcg(o + D + 1, L); }
-    __threadfence();
-    group_sync(g);
-    if (tid == 0) {
-      const int old = atomicAdd(p.attn_counters + bh, 1);
-      s_last[g] = old == p.nsplit - 1;
-      if (s_last[g]) p.attn_counters[bh] = 0;
-    }
-    group_sync(g);
-    if (s_last[g]) {
-      __threadfence();
-      const float* pp = p.attn_part + (long long)bh * p.nsplit * (D + 2);
-      float MM = -INFINITY;
-      for (int s = 0; s < p.nsplit; ++s) MM = fmaxf(MM, __ldcg(pp + s * (D + 2) + D));
-      float LL = 0.f, AA = 0.f;
-      for (int s = 0; s < p.nsplit; ++s) {
-        const float ms = __ldcg(pp + s * (D + 2) + D);
-        const float c = ms == -INFINITY ? 0.f : __expf(ms - MM);
-        LL += __ldcg(pp + s * (D + 2) + D + 1) * c;
-        AA += __ldcg(pp + s * (D + 2) + tid) * c;
-      }
-      p.ao[(long long)bh * D + tid] = f2bf(LL > 0.f ? AA / LL : 0.f);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
-tmp_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_constant__ CUtensorMap map_ao,
-                 const __grid_constant__ CUtensorMap map_h, const TmpParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ float red[THREADS / 32];
-  __shared__ float sm_acc[2][8][lm::ATT_D];
-  __shared__ float sm_ml[2][16];
-  __shared__ int s_last[2];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bars = base + (uint32_t)p.stages * p.stage_bytes;
-  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
-  const uint32_t tptr = tempty0 + 16;
-  uint32_t* tptr_generic = reinterpret_cast<uint32_t*>(smem_raw + (tptr - raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xn) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ao) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tptr, p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tptr_generic;
-
-  Pipe pipe{0, 0u, 0, 0u, 0};
-  unsigned epoch = 0;
-  auto gemm_at = [&](int l, int which) -> Gemm {
-    const DepLayerW w = p.w[l];
-    Gemm g;
-    if (which == 0) { g = p.g_in; g.wt = w.in_w; }
-    else if (which == 1) { g = p.g_out; g.wt = w.out_w; }
-    else if (which == 2) { g = p.g_lin_in; g.wt = w.lin_in; }
-    else { g = p.g_lin_out; g.wt = w.lin_out; }
-    return g;
-  };
-  row_phase<16>(p, p.d, 0, nullptr, 0, false, p.n1[0], red);        // xn = rmsnorm(x) for layer 0
-  grid_sync(p.bar, epoch);
-  Gemm cur = gemm_at(0, 0);
-  for (int l = 0; l < p.L; ++l) {
-    Gemm nxt = gemm_at(l, 1);
-    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-    grid_sync(p.bar, epoch);
-    ring_attn_phase(p, cur.S, l, sm_acc, sm_ml, s_last);
-    grid_sync(p.bar, epoch);
-    cur = nxt; nxt = gemm_at(l, 2);
-    gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-    grid_sync(p.bar, epoch);
-    row_phase<16>(p, p.d, cur.S, p.part0, cur.N, true, p.n2[l], red);
-    grid_sync(p.bar, epoch);
-    cur = nxt; nxt = gemm_at(l, 3);
-    gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-    grid_sync(p.bar, epoch);
-    gate_phase(p, cur.S);
-    grid_sync(p.bar, epoch);
-    cur = nxt;
-    const bool last = l + 1 == p.L;
-    if (!last) nxt = gemm_at(l + 1, 0);
-    gemm_phase(p, cur, last ? nullptr : &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-    grid_sync(p.bar, epoch);
-    row_phase<16>(p, p.d, cur.S, p.part0, cur.N, true, last ? nullptr : p.n1[l + 1], red);   // out_norm is applied outside
-    grid_sync(p.bar, epoch);
-    cur = nxt;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -893,95 +642,6 @@ int dep_fused_launch(DepFused* d, cudaStream_t stream) {
   dep_fused_kernel<<<d->grid, THREADS, d->smem, stream>>>(d->map_xn, d->map_ao, d->map_h, d->map_x, d->p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("dep_fused");
-}
-
-// ---- temporal fused kernel: host side ---------------------------------------------------------------------------------
-struct TmpFused {
-  TmpParams p;
-  CUtensorMap map_xn, map_ao, map_h;
-  int grid = 0; size_t smem = 0;
-  void* dev_tables = nullptr;
-};
-
-size_t tmp_fused_partial_floats(const TmpFusedConfig& c) {
-  const int grid = sk_num_sms();
-  size_t mx = 0;
-  const Gemm gs[4] = {plan(3 * c.d, c.d, 1, c.B, grid), plan(c.d, c.d, 1, c.B, grid), plan(c.F, c.d, 2, c.B, grid),
-                      plan(c.d, c.F, 1, c.B, grid)};
-  for (const Gemm& g : gs) {
-    const size_t n = (size_t)g.S * c.B * g.N;
-    if (n > mx) mx = n;
-  }
-  return mx;
-}
-
-int tmp_fused_create(const TmpFusedConfig& c, TmpFused** out) {
-  if (c.d > 16 * THREADS || c.d % 64 || c.d / c.H != lm::ATT_D || c.F % 8 || c.B < 1 || c.B > 256)
-    B200_FAIL(B200_ERR_INVALID, "fused temporal transformer: unsupported configuration");
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) B200_FAIL(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
-  TmpFused* d = new TmpFused();
-  TmpParams& p = d->p;
-  memset(&p, 0, sizeof(p));
-  d->grid = sk_num_sms();
-  p.B = c.B; p.Mpad = ((c.B + 15) / 16) * 16; p.d = c.d; p.H = c.H; p.F = c.F; p.L = c.L; p.cap = c.cap; p.nsplit = c.nsplit;
-  p.stage_bytes = (uint32_t)(2 * TILE_BYTES + p.Mpad * BLOCK_K * 2);
-  int stages = (190 * 1024) / (int)p.stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) { delete d; B200_FAIL(B200_ERR_INVALID, "fused temporal transformer: batch too large for the stage ring"); }
-  p.stages = stages;
-  p.acc_cols = 2 * p.Mpad;
-  p.n_acc = 2 * p.acc_cols <= 512 ? 2 : 1;
-  uint32_t cols = (uint32_t)(p.n_acc * p.acc_cols), pow2 = 32;
-  while (pow2 < cols) pow2 <<= 1;
-  p.tmem_cols = pow2;
-  p.g_in = plan(3 * c.d, c.d, 1, c.B, d->grid);
-  p.g_out = plan(c.d, c.d, 1, c.B, d->grid);
-  p.g_lin_in = plan(c.F, c.d, 2, c.B, d->grid);
-  p.g_lin_out = plan(c.d, c.F, 1, c.B, d->grid);
-  const size_t bytes = (size_t)c.L * sizeof(DepLayerW) + (size_t)c.L * 8 * 4;
-  std::vector<uint8_t> host(bytes);
-  size_t off = 0;
-  auto put = [&](const void* src, size_t n) { memcpy(host.data() + off, src, n); const size_t o = off; off += n; return o; };
-  std::vector<DepLayerW> w(c.L);
-  for (int i = 0; i < c.L; ++i) w[i] = DepLayerW{(const uint8_t*)c.in_w[i], (const uint8_t*)c.out_w[i], (const uint8_t*)c.lin_in[i], (const uint8_t*)c.lin_out[i]};
-  const size_t o_w = put(w.data(), (size_t)c.L * sizeof(DepLayerW));
-  const size_t o_n1 = put(c.n1, (size_t)c.L * 8), o_n2 = put(c.n2, (size_t)c.L * 8);
-  const size_t o_kc = put(c.kc, (size_t)c.L * 8), o_vc = put(c.vc, (size_t)c.L * 8);
-  if (cudaMalloc(&d->dev_tables, bytes) != cudaSuccess) { delete d; B200_FAIL(B200_ERR_CUDA, "fused temporal transformer: cudaMalloc failed"); }
-  B200_CUDA(cudaMemcpy(d->dev_tables, host.data(), bytes, cudaMemcpyHostToDevice));
-  uint8_t* dv = static_cast<uint8_t*>(d->dev_tables);
-  p.w = reinterpret_cast<const DepLayerW*>(dv + o_w);
-  p.n1 = reinterpret_cast<const bf16* const*>(dv + o_n1);
-  p.n2 = reinterpret_cast<const bf16* const*>(dv + o_n2);
-  p.kc = reinterpret_cast<bf16* const*>(dv + o_kc);
-  p.vc = reinterpret_cast<bf16* const*>(dv + o_vc);
-  p.x = static_cast<bf16*>(c.x); p.xn = static_cast<bf16*>(c.xn); p.ao = static_cast<bf16*>(c.ao); p.hbuf = static_cast<bf16*>(c.hbuf);
-  p.part0 = c.part0; p.part1 = c.part1; p.attn_part = c.attn_part; p.attn_counters = c.attn_counters;
-  p.pos = c.pos; p.exec_mask = c.exec_mask; p.neg_log_period_2_over_d = c.neg_log_period_2_over_d; p.bar = c.bar;
-  B200_TRY(make_map(enc, &d->map_xn, c.xn, c.B, c.d, p.Mpad));
-  B200_TRY(make_map(enc, &d->map_ao, c.ao, c.B, c.d, p.Mpad));
-  B200_TRY(make_map(enc, &d->map_h, c.hbuf, c.B, c.F, p.Mpad));
-  d->smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
-  B200_CUDA(cudaFuncSetAttribute(tmp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-  *out = d;
-  return B200_OK;
-}
-
-void tmp_fused_destroy(TmpFused* d) {
-  if (!d) return;
-  if (d->dev_tables) cudaFree(d->dev_tables);
-  delete d;
-}
-
-int tmp_fused_launch(TmpFused* d, cudaStream_t stream) {
-  B200_CUDA(cudaMemsetAsync(d->p.bar, 0, sizeof(unsigned), stream));
-  tmp_fused_kernel<<<d->grid, THREADS, d->smem, stream>>>(d->map_xn, d->map_ao, d->map_h, d->p);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return check_launch("tmp_fused");
 }
 
 }  // namespace tc

@@ -95,24 +95,7 @@ void dep_fused_set_sampling(DepFused* d, int use_sampling, float temp, int top_k
 void dep_fused_destroy(DepFused* d);
 int dep_fused_launch(DepFused* d, cudaStream_t stream);
 
-// ---- the temporal transformer of one frame as one persistent kernel, for small batches (dep_fused.cu) ------------
-struct TmpFusedConfig {
-  int B, d, H, F, L, cap, nsplit;
-  const void* const* in_w; const void* const* out_w; const void* const* lin_in; const void* const* lin_out;   // [L] packed tiles
-  const void* const* n1; const void* const* n2;   // [L]
-  void* const* kc; void* const* vc;               // [L] rings [B][H][cap][128] bf16
-  void *x, *xn, *ao, *hbuf;
-  float *part0, *part1;
-  float* attn_part; int* attn_counters;
-  const long long* pos; const uint8_t* exec_mask;
-  float neg_log_period_2_over_d;
-  unsigned* bar;
-};
-struct TmpFused;
-size_t tmp_fused_partial_floats(const TmpFusedConfig& c);
-int tmp_fused_create(const TmpFusedConfig& c, TmpFused** out);
-void tmp_fused_destroy(TmpFused* d);
-int tmp_fused_launch(TmpFused* d, cudaStream_t stream);
+
 
 }  // namespace tc
 }  // namespace b200

@@ -68,8 +68,6 @@ struct b200_lm {
        *dh = nullptr, *dep_logits = nullptr;
   float* attn_part = nullptr;
   int* attn_counters = nullptr;                // split arrival counters [B*H]
-  tc::TmpFused* tmpf = nullptr;                // temporal layers as one persistent kernel when batch <= tmp_fused_max_b
-  int tmp_fused_max_b = 0;                     // B200_TMP_FUSED_MAX_B
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
   int dep_fused = 1;
   int fuse_norm = 1;                           // B200_FUSE_NORM=0: keep rmsnorm_kernel in front of the GEMV path too (diagnostics)
@@ -210,32 +208,28 @@ int step_body(b200_lm* h) {
   B200_LAUNCH(lm_prepare_kernel, ceil_div(B * h->Kc, 128), 128, 0, st, ring(h), h->in_codes, h->n_in_static,
               h->input_tokens, B);
   B200_LAUNCH(lm_embed_sum_kernel, ceil_div(B * d / 2, 256), 256, 0, st, h->emb, h->input_tokens, h->x, B, d);
-  if (h->tmpf) {
-    B200_TRY(tc::tmp_fused_launch(h->tmpf, st));
-  } else {
-    for (auto& L : h->layers) {
-      B200_TRY(norm_linear(h, h->x, L.n1, h->xn, L.in_w, h->qkv, 3 * d, B, 3 * d, d, LIN_STORE, 0, L.in_s));
-      if (h->kv_fp8) {
-        AttnStepQ8 a;
-        a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
-        a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
-        a.neg_log_period_2_over_d = nl;
-        dim3 grid(B * H, h->nsplit);
-        if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
-        else B200_LAUNCH(attn_step_q8_kernel<KV_E4M3>, grid, ATT_THREADS, 0, st, a);
-      } else {   // RoPE + ring append + split-KV attention + split merge in one launch
-        AttnStep a;
-        a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
-        a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
-        a.neg_log_period_2_over_d = nl;
-        dim3 grid(B * H, h->nsplit);
-        if (attn_group_keys() == 2) B200_LAUNCH(attn_step_kernel<2>, grid, ATT_THREADS, 0, st, a);
-        else B200_LAUNCH(attn_step_kernel<4>, grid, ATT_THREADS, 0, st, a);
-      }
-      B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0, L.out_s));
-      B200_TRY(norm_linear(h, h->x, L.n2, h->xn, L.lin_in, h->hbuf, F, B, F, d, LIN_GATE, F, L.lin_in_s));
-      B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0, L.lin_out_s));
+  for (auto& L : h->layers) {
+    B200_TRY(norm_linear(h, h->x, L.n1, h->xn, L.in_w, h->qkv, 3 * d, B, 3 * d, d, LIN_STORE, 0, L.in_s));
+    if (h->kv_fp8) {
+      AttnStepQ8 a;
+      a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
+      a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+      a.neg_log_period_2_over_d = nl;
+      dim3 grid(B * H, h->nsplit);
+      if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
+      else B200_LAUNCH(attn_step_q8_kernel<KV_E4M3>, grid, ATT_THREADS, 0, st, a);
+    } else {   // RoPE + ring append + split-KV attention + split merge in one launch
+      AttnStep a;
+      a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
+      a.pos = h->pos; a.exec_mask = h->exec_mask; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+      a.neg_log_period_2_over_d = nl;
+      dim3 grid(B * H, h->nsplit);
+      if (attn_group_keys() == 2) B200_LAUNCH(attn_step_kernel<2>, grid, ATT_THREADS, 0, st, a);
+      else B200_LAUNCH(attn_step_kernel<4>, grid, ATT_THREADS, 0, st, a);
     }
+    B200_TRY(linear(h, h->ao, d, L.out_w, h->x, d, h->x, d, B, d, d, LIN_RESADD, 0, L.out_s));
+    B200_TRY(norm_linear(h, h->x, L.n2, h->xn, L.lin_in, h->hbuf, F, B, F, d, LIN_GATE, F, L.lin_in_s));
+    B200_TRY(linear(h, h->hbuf, F, L.lin_out, h->x, d, h->x, d, B, d, F, LIN_RESADD, 0, L.lin_out_s));
   }
   B200_LAUNCH(rmsnorm_kernel, B, 256, 0, st, h->x, h->out_norm, h->tout, d, 1e-8f);
   B200_TRY(linear(h, h->tout, d, h->text_linear, h->text_logits, c.text_card, nullptr, 0, B, c.text_card, d, LIN_STORE, 0, h->text_linear_s));
@@ -321,7 +315,6 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
   if (const char* e = getenv("B200_PDL")) h->pdl = atoi(e) != 0;
   if (const char* e = getenv("B200_SK_SMEM_KB")) h->sk_smem = atoi(e) * 1024;
   if (const char* e = getenv("B200_DEP_FUSED")) h->dep_fused = atoi(e);
-  if (const char* e = getenv("B200_TMP_FUSED_MAX_B")) h->tmp_fused_max_b = atoi(e);
   if (const char* e = getenv("B200_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
   if (const char* e = getenv("B200_KV_DTYPE")) {
     const std::string v = e;
@@ -557,33 +550,9 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     fc.din = h->din; fc.din_ld = (long long)c.dep_q * dd; fc.text_token = h->text_token;
     fc.x = h->dx; fc.xn = h->dxn; fc.ao = h->dao; fc.hbuf = h->dh;
     size_t pf = tc::dep_fused_partial_floats(fc);
-    const bool want_tmp = B <= h->tmp_fused_max_b && !h->kv_fp8;
-    tc::TmpFusedConfig tcfg;
-    memset(&tcfg, 0, sizeof(tcfg));
-    if (want_tmp) {
-      tcfg.B = B; tcfg.d = d; tcfg.H = H; tcfg.F = c.ffn_hidden; tcfg.L = c.num_layers; tcfg.cap = c.context; tcfg.nsplit = h->nsplit;
-      const size_t pt = tc::tmp_fused_partial_floats(tcfg);
-      if (pt > pf) pf = pt;
-    }
     B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
     B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
     B200_TRY(A.alloc_t(&h->dep_bar, 1));
-    std::vector<const void*> t_in, t_out, t_lin_in, t_lin_out, t_n1, t_n2;
-    std::vector<void*> t_kc, t_vc;
-    if (want_tmp) {
-      for (auto& L : h->layers) {
-        t_in.push_back(L.in_w); t_out.push_back(L.out_w); t_lin_in.push_back(L.lin_in); t_lin_out.push_back(L.lin_out);
-        t_n1.push_back(L.n1); t_n2.push_back(L.n2); t_kc.push_back(L.kc); t_vc.push_back(L.vc);
-      }
-      tcfg.in_w = t_in.data(); tcfg.out_w = t_out.data(); tcfg.lin_in = t_lin_in.data(); tcfg.lin_out = t_lin_out.data();
-      tcfg.n1 = t_n1.data(); tcfg.n2 = t_n2.data(); tcfg.kc = t_kc.data(); tcfg.vc = t_vc.data();
-      tcfg.x = h->x; tcfg.xn = h->xn; tcfg.ao = h->ao; tcfg.hbuf = h->hbuf;
-      tcfg.part0 = h->dep_part0; tcfg.part1 = h->dep_part1; tcfg.attn_part = h->attn_part; tcfg.attn_counters = h->attn_counters;
-      tcfg.pos = h->pos; tcfg.exec_mask = h->exec_mask;
-      tcfg.neg_log_period_2_over_d = -logf(c.max_period) * 2.f / (float)D;
-      tcfg.bar = h->dep_bar;
-      B200_TRY(tc::tmp_fused_create(tcfg, &h->tmpf));
-    }
     fc.part0 = h->dep_part0; fc.part1 = h->dep_part1; fc.bar = h->dep_bar;
     fc.logits = h->dep_logits; fc.audio_tokens = h->audio_tokens;
     fc.noise = h->noise; fc.noise_ld = noise_per_row(h);
@@ -650,8 +619,6 @@ int b200_lm_streaming_end(b200_lm* h) {
   h->plans.clear();
   tc::dep_fused_destroy(h->depf);
   h->depf = nullptr;
-  tc::tmp_fused_destroy(h->tmpf);
-  h->tmpf = nullptr;
   h->state.free_all();
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
