@@ -646,7 +646,8 @@ int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long l
   a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
   a.out = out; a.ob = ob; a.oc = oc; a.ot = ot;
   a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins;
-  B200_LAUNCH(rvq_decode_kernel, h->batch * n_cols, 256, 2 * c.q_dimension * sizeof(float), h->body, a);
+  dim3 grid(h->batch * n_cols, (c.dimension + 63) / 64);
+  B200_LAUNCH(rvq_decode_kernel, grid, 256, (2 * c.q_dimension + 256) * sizeof(float), h->body, a);
   return check_launch("rvq_decode");
 }
 

@@ -580,10 +580,13 @@ struct RvqDecArgs {
   float* out; long long ob, oc, ot;          // [B][Cout][n] via strides
   int Dq, Cout, bins;
 };
+// grid (B * n_frames, ceil(Cout / 64)), 256 threads = 64 output channels x 4 slices of the Dq-long dot products: the
+// dependent FMA chain per thread is Dq / 2 long instead of 2 * Dq, and a single session still spreads over 8 CTAs.
 static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs a) {
-  extern __shared__ float sm[];              // [2][Dq]
+  extern __shared__ float sm[];              // [2][Dq] summed code vectors, then [4][64] partial dot products
   const int b = blockIdx.x / a.n_frames, f = blockIdx.x % a.n_frames;
   const int tid = threadIdx.x;
+  float* part = sm + 2 * a.Dq;
   for (int which = 0; which < 2; ++which) {
     for (int d = tid; d < a.Dq; d += blockDim.x) {
       float s = 0.f;
@@ -595,18 +598,24 @@ static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs
     }
   }
   __syncthreads();
-  for (int c = tid; c < a.Cout; c += blockDim.x) {
-    float acc0 = 0.f, acc1 = 0.f;
+  const int cl = tid & 63, slice = tid >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  const int d0 = slice * (a.Dq / 4), d1 = slice == 3 ? a.Dq : d0 + a.Dq / 4;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (c < a.Cout) {
     if (a.levels[0] > 0) {
 #pragma unroll 8
-      for (int d = 0; d < a.Dq; ++d) acc0 = fmaf(a.woT[0][(long long)d * a.Cout + c], sm[d], acc0);
+      for (int d = d0; d < d1; ++d) acc0 = fmaf(a.woT[0][(long long)d * a.Cout + c], sm[d], acc0);
     }
     if (a.levels[1] > 0) {
 #pragma unroll 8
-      for (int d = 0; d < a.Dq; ++d) acc1 = fmaf(a.woT[1][(long long)d * a.Cout + c], sm[a.Dq + d], acc1);
+      for (int d = d0; d < d1; ++d) acc1 = fmaf(a.woT[1][(long long)d * a.Cout + c], sm[a.Dq + d], acc1);
     }
-    a.out[b * a.ob + c * a.oc + f * a.ot] = acc0 + acc1;
   }
+  part[slice * 64 + cl] = acc0 + acc1;
+  __syncthreads();
+  if (slice == 0 && c < a.Cout)               // slices in order: the sum does not depend on scheduling
+    a.out[b * a.ob + c * a.oc + f * a.ot] = ((part[cl] + part[64 + cl]) + part[128 + cl]) + part[192 + cl];
 }
 
 // ---------------------------------------------------------------------------------------------
