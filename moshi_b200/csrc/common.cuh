@@ -51,12 +51,6 @@ extern std::atomic<int64_t> g_launches;
     b200::g_launches.fetch_add(1, std::memory_order_relaxed);                  \
   } while (0)
 
-// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled
-// while its predecessor is still running; it must wait here before touching anything the predecessor reads or writes.
-// Without the attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_wait_all() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_next() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

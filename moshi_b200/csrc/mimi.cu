@@ -6,23 +6,6 @@
 using namespace b200;
 using namespace b200::mimi;
 
-// Per-frame kernels are launched with programmatic stream serialization (every Mimi kernel starts with griddepcontrol.wait):
-// the next kernel's launch latency and block scheduling overlap the tail of the current one.  B200_MIMI_PDL=0 switches it off.
-static int g_mimi_pdl = [] { const char* e = getenv("B200_MIMI_PDL"); return e ? atoi(e) != 0 : 1; }();
-#define MIMI_LAUNCH(kernel, grid_, block_, smem_, stream_, ...)                                              \
-  do {                                                                                                   \
-    cudaLaunchConfig_t _cfg;                                                                             \
-    memset(&_cfg, 0, sizeof(_cfg));                                                                      \
-    _cfg.gridDim = dim3(grid_); _cfg.blockDim = dim3(block_); _cfg.dynamicSmemBytes = (smem_); _cfg.stream = (stream_); \
-    cudaLaunchAttribute _attr[1];                                                                        \
-    _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                    \
-    _attr[0].val.programmaticStreamSerializationAllowed = 1;                                             \
-    _cfg.attrs = _attr; _cfg.numAttrs = g_mimi_pdl ? 1 : 0;                                              \
-    (void)cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);      /* errors surface in check_launch() */     \
-    b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
-  } while (0)
-
-
 namespace {
 
 struct ConvLayer {
@@ -377,10 +360,10 @@ int launch_gemm(b200_mimi* h, GemmArgs a) {
   a.ksplit = 1; a.ws = nullptr;
   if (a.M > 64 && ctas(128, 128) >= want) {
     dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 128));
-    MIMI_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->body, a);
+    B200_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->body, a);
   } else if (ctas(64, 128) >= want) {
     dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 64));
-    MIMI_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->body, a);
+    B200_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->body, a);
   } else {
     const long long n64 = ctas(64, 64);
     const int nk = ceil_div(a.Kd, GK);
@@ -394,10 +377,10 @@ int launch_gemm(b200_mimi* h, GemmArgs a) {
     }
     a.ksplit = ks; a.ws = h->splitk_ws;
     dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64), ks);
-    MIMI_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->body, a);
+    B200_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->body, a);
     if (ks > 1) {
       const long long n = (long long)a.M * a.N;
-      MIMI_LAUNCH((gemm_splitk_reduce_kernel<KIND>), (unsigned)ceil_div64(n, 256), 256, 0, h->body, a);
+      B200_LAUNCH((gemm_splitk_reduce_kernel<KIND>), (unsigned)ceil_div64(n, 256), 256, 0, h->body, a);
     }
   }
   return check_launch("mimi_gemm");
@@ -419,7 +402,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     q.wk = l.wk; q.bias = l.bias; q.y = y; q.yb = yb; q.yt = yt;
     q.B = B; q.Cin = l.cin; q.K = l.k; q.dil = l.dil; q.T = l.t_out;
     const long long n = (long long)B * l.t_out;
-    MIMI_LAUNCH(conv_cout1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)l.k * l.cin * 4, h->body, q);
+    B200_LAUNCH(conv_cout1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)l.k * l.cin * 4, h->body, q);
     return check_launch(l.key.c_str());
   }
   if (!l.fast && l.kind == 0 && l.cin == 1 && l.stride == 1 && l.k <= 8 && !l.first && !l.elu_in && !res && xc == 0 && yt == 1) {
@@ -428,7 +411,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     q.y = y; q.yb = yb; q.yc = yc; q.a = act; q.ab = ab; q.ac = ac; q.a_elu = a_elu;
     q.B = B; q.Cout = l.cout; q.K = l.k; q.T = l.t_out;
     const long long n = (long long)B * l.t_out;
-    MIMI_LAUNCH(conv_cin1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
+    B200_LAUNCH(conv_cin1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
     return check_launch(l.key.c_str());
   }
   if (l.fast) {
@@ -468,7 +451,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     p.elu_in = l.elu_in;
     p.M = l.cout; p.N = B * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    MIMI_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
+    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
   } else {
     if (act) B200_FAIL(B200_ERR_INVALID, "first-generation convtr cannot feed a mimi_gemm layer");
     ConvTrP p;
@@ -478,7 +461,7 @@ int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, 
     p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.S = l.stride; p.elu_in = l.elu_in;
     p.M = l.cout * l.stride; p.N = B * (l.t_in + 1); p.Kd = 2 * l.cin; p.cin_aligned = (l.cin % BK) == 0;
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    MIMI_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->body, p);
+    B200_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->body, p);
   }
   return check_launch(l.key.c_str());
 }
@@ -503,21 +486,21 @@ int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, 
   for (size_t li = 0; li < tr.layers.size(); ++li) {
     TrLayer& L = tr.layers[li];
     const float* cur = li == 0 ? x_in : x;
-    MIMI_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
     B200_TRY(launch_linear(h, h->tr_xn, d, L.in_w, h->tr_qkv, 3 * d, ntok, EPI_NONE, nullptr, nullptr));
     {
       const long long total = (long long)B * T * H * (D / 2);
-      MIMI_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->tr_qkv, h->tr_q, L.kc,
+      B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->tr_qkv, h->tr_q, L.kc,
                   L.vc, tr.offset, h->exec_mask, B, T, H, D, c.tr_context, nl);
     }
-    MIMI_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
+    B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
                 h->exec_mask, T, H, c.tr_context, c.tr_context);
     B200_TRY(launch_linear(h, h->tr_ao, d, L.out_w, x, d, ntok, EPI_RES_SCALE, cur, L.ls1));
-    MIMI_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
+    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
     B200_TRY(launch_linear(h, h->tr_xn, d, L.l1, h->tr_h, ff, ntok, EPI_GELU, nullptr, nullptr));
     B200_TRY(launch_linear(h, h->tr_h, ff, L.l2, x, d, ntok, EPI_RES_SCALE, x, L.ls2));
   }
-  MIMI_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->body, tr.offset, h->exec_mask, B, T);
+  B200_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->body, tr.offset, h->exec_mask, B, T);
   return check_launch("mimi transformer");
 }
 
@@ -527,7 +510,7 @@ int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& b
   if (layers[0].fast) {   // its input comes from outside the SEANet (transformer output): copy it behind the carried state
     const ConvLayer& l = layers[0];
     const long long n = (long long)h->batch * l.cin * l.t_in;
-    MIMI_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->body, x0, xb, xc, xt, l.ext + l.D0,
+    B200_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->body, x0, xb, xc, xt, l.ext + l.D0,
                 (long long)l.cin * l.E, (long long)l.E, 1LL, h->batch, l.cin, l.t_in, (int)l.elu_in);
   }
   for (size_t i = 0; i < layers.size(); ++i) {
@@ -555,25 +538,25 @@ int commit_states(b200_mimi* h, bool encoder) {
   if (encoder) {
     if (h->n_enc_commits) {
       dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
-      MIMI_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
-      MIMI_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->body, h->enc_commits,
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
+      B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->body, h->enc_commits,
                   h->n_enc_commits, h->exec_mask, B);
     }
     if (h->n_enc_ext) {
       dim3 grid(ceil_div(h->max_enc_ext_rows, 128), h->n_enc_ext);
-      MIMI_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->enc_ext_commits, h->exec_mask, B);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->enc_ext_commits, h->exec_mask, B);
     }
   } else {
     if (h->n_dec_commits) {
       dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
-      MIMI_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
     }
     if (h->n_dec_ext) {
       dim3 grid(ceil_div(h->max_dec_ext_rows, 128), h->n_dec_ext);
-      MIMI_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->dec_ext_commits, h->exec_mask, B);
+      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->dec_ext_commits, h->exec_mask, B);
     }
     dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);
-    MIMI_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->body, h->dec_tr_commits, h->exec_mask, B);
+    B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->body, h->dec_tr_commits, h->exec_mask, B);
   }
   return check_launch("commit_states");
 }
@@ -627,7 +610,7 @@ int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, lo
   levels[1] = h->num_codebooks - levels[0];
   {
     dim3 grid(Q, 2);
-    MIMI_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->body, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
+    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->body, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
                 h->rvq_res[0], h->rvq_res[1], c.dimension, Dq);
   }
   const int max_levels = levels[0] > levels[1] ? levels[0] : levels[1];
@@ -644,9 +627,9 @@ int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, lo
     a.codes = codes; a.cs_b = cs_b; a.cs_k = cs_k; a.cs_f = cs_f;
     a.n_query = Q; a.n_frames = n_cols; a.Dq = Dq; a.bins = bins; a.n_chunks = n_chunks;
     dim3 g1(n_chunks, ceil_div(Q, RVQ_QT), 2);
-    MIMI_LAUNCH(rvq_search_kernel, g1, RVQ_CHUNK, (size_t)RVQ_QT * Dq * 4, h->body, a);
+    B200_LAUNCH(rvq_search_kernel, g1, RVQ_CHUNK, (size_t)RVQ_QT * Dq * 4, h->body, a);
     dim3 g2(Q, 2);
-    MIMI_LAUNCH(rvq_pick_kernel, g2, 128, 0, h->body, a);
+    B200_LAUNCH(rvq_pick_kernel, g2, 128, 0, h->body, a);
   }
   return check_launch("rvq_encode");
 }
@@ -664,7 +647,7 @@ int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long l
   a.out = out; a.ob = ob; a.oc = oc; a.ot = ot;
   a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins;
   dim3 grid(h->batch * n_cols, (c.dimension + 63) / 64);
-  MIMI_LAUNCH(rvq_decode_kernel, grid, 256, (2 * c.q_dimension + 256) * sizeof(float), h->body, a);
+  B200_LAUNCH(rvq_decode_kernel, grid, 256, (2 * c.q_dimension + 256) * sizeof(float), h->body, a);
   return check_launch("rvq_decode");
 }
 
@@ -674,7 +657,7 @@ int decode_latent_body(b200_mimi* h) {
   const int T = S;   // tokens per frame after up-sampling
   {
     const long long total = (long long)B * 2 * S * d;   // (T_in + 1) * S * C with T_in = 1
-    MIMI_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->latent_q, (long long)d, 1LL, 1LL, 1,
+    B200_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->latent_q, (long long)d, 1LL, 1LL, 1,
                 h->up_w, h->up_partial, h->up_scratch, h->tok_in_dec, B, d, S);
   }
   B200_TRY(run_transformer(h, h->dec_tr, h->tok_in_dec, h->tok_dec, T));

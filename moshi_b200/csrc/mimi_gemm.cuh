@@ -83,7 +83,6 @@ __device__ __forceinline__ void gemm_store_one(const GemmArgs& p, int m, int n, 
 // sums the split-K partials in split order (deterministic) and applies the epilogue
 template <int KIND>
 static __global__ void gemm_splitk_reduce_kernel(const GemmArgs p) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)p.M * p.N) return;
   const int n = i % p.N, m = i / p.N;
@@ -142,7 +141,6 @@ __device__ __forceinline__ void convtr_store(const GemmArgs& p, int m, int b, in
 
 template <int BM, int BN, int KIND>
 static __global__ void __launch_bounds__(256, (BM * BN >= 64 * 128) ? 2 : 3) mimi_gemm_kernel(const GemmArgs p) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   constexpr int TM = BM / 16, TN = BN / 16;          // micro-tile, in groups of 4
   constexpr int GM = TM / 4, GN = TN / 4;
   constexpr int LDA = BM + 4, LDB = BN + 4;
@@ -419,7 +417,6 @@ struct ConvCin1 {
   int B, Cout, K, T;
 };
 static __global__ void __launch_bounds__(256) conv_cin1_kernel(const ConvCin1 p) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   extern __shared__ float sw[];              // [Cout][K] then bias [Cout]
   for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[i] = p.w[i];
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[p.Cout * p.K + i] = p.bias ? p.bias[i] : 0.f;
@@ -453,7 +450,6 @@ struct ConvCout1 {
   int B, Cin, K, dil, T;
 };
 static __global__ void __launch_bounds__(256) conv_cout1_kernel(const ConvCout1 p) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   extern __shared__ float sw[];               // [K*Cin]
   for (int i = threadIdx.x; i < p.K * p.Cin; i += blockDim.x) sw[i] = p.wk[i];
   __syncthreads();
@@ -475,7 +471,6 @@ static __global__ void __launch_bounds__(256) conv_cout1_kernel(const ConvCout1 
 static __global__ void fill_act_kernel(const float* __restrict__ src, long long sb, long long sc, long long st,
                                 float* __restrict__ dst, long long db, long long dc, long long dt, int B, int C, int T,
                                 int elu) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * C * T) return;
   const int t = i % T;
@@ -489,7 +484,6 @@ static __global__ void fill_act_kernel(const float* __restrict__ src, long long 
 // last P of cat(previous, x) = ext[T .. T+P)  ->  ext[0 .. P), for rows with exec_mask.
 struct ExtCommit { float* ext; int P, T, E, Cin; };
 static __global__ void ext_commit_kernel(const ExtCommit* descs, const uint8_t* exec_mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const ExtCommit d = descs[blockIdx.y];
   const int row = blockIdx.x * blockDim.x + threadIdx.x;     // (b, ci)
   if (row >= B * d.Cin) return;
@@ -499,7 +493,6 @@ static __global__ void ext_commit_kernel(const ExtCommit* descs, const uint8_t* 
 }
 // reset: zero the carried samples of the rows in mask (conv.py:166-169)
 static __global__ void ext_zero_kernel(float* ext, int P, int E, int Cin, const uint8_t* mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * Cin * P) return;
   const int j = i % P;
@@ -509,7 +502,6 @@ static __global__ void ext_zero_kernel(float* ext, int P, int E, int Cin, const 
 
 // load-time repacking to k-major
 static __global__ void pack_conv_k_kernel(const float* w /*[Cout][Cin][K]*/, float* out /*[K*Cin][Cout]*/, int Cout, int Cin, int K) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Cin * K) return;
   const int kw = i % K; long long r = i / K;
@@ -517,7 +509,6 @@ static __global__ void pack_conv_k_kernel(const float* w /*[Cout][Cin][K]*/, flo
   out[((long long)kw * Cin + ci) * Cout + co] = w[i];
 }
 static __global__ void pack_convtr_k_kernel(const float* w /*[Cin][Cout][2S]*/, float* out /*[2*Cin][Cout*S]*/, int Cin, int Cout, int S) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cin * Cout * 2 * S) return;
   const int k = i % (2 * S); long long r = i / (2 * S);

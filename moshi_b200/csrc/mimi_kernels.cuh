@@ -130,7 +130,6 @@ struct LinP {   // y[n][m] = epi(sum_k x[n][k] * w[m][k]);  token-major activati
 
 template <class P, bool B_K_FAST>
 static __global__ void __launch_bounds__(256) igemm_f32_kernel(const P p) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -221,7 +220,6 @@ struct ConvTrCommit { // partial <- scratch   (conv.py:357-360)
 };
 
 static __global__ void conv_commit_kernel(const ConvCommit* descs, int n_desc, const uint8_t* exec_mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const ConvCommit d = descs[blockIdx.y];
   const int row = blockIdx.x * blockDim.x + threadIdx.x;   // (b, ci)
   if (row >= B * d.Cin) return;
@@ -245,7 +243,6 @@ static __global__ void conv_commit_kernel(const ConvCommit* descs, int n_desc, c
 
 // `first` flags are cleared in a second tiny pass so that every (b, ci) thread above saw the old value.
 static __global__ void conv_clear_first_kernel(const ConvCommit* descs, int n_desc, const uint8_t* exec_mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_desc * B) return;
   const ConvCommit d = descs[i / B];
@@ -254,7 +251,6 @@ static __global__ void conv_clear_first_kernel(const ConvCommit* descs, int n_de
 }
 
 static __global__ void convtr_commit_kernel(const ConvTrCommit* descs, const uint8_t* exec_mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const ConvTrCommit d = descs[blockIdx.y];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * d.per_row) return;
@@ -263,14 +259,12 @@ static __global__ void convtr_commit_kernel(const ConvTrCommit* descs, const uin
 
 // reset: zero the state of the rows in reset_mask (conv.py:166-169, 281-286)
 static __global__ void zero_rows_kernel(float* buf, long long per_row, const uint8_t* mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * per_row) return;
   if (mask == nullptr || mask[i / per_row]) buf[i] = 0.f;
 }
 static __global__ void reset_flags_kernel(uint8_t* first /*[n_first][B]*/, int n_first, long long* off_a, long long* off_b,
                                    uint8_t* exec_mask, const uint8_t* mask, int B) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (mask != nullptr && !mask[b]) return;
@@ -288,7 +282,6 @@ static __global__ void upsample_dw_kernel(const float* __restrict__ lat, long lo
                                    const float* __restrict__ w /*[C][2S]*/, const float* __restrict__ partial,
                                    float* __restrict__ scratch, float* __restrict__ y /*[B][T*S][C]*/,
                                    int B, int C, int S) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * (T + 1) * S * C;
   if (i >= total) return;
@@ -311,7 +304,6 @@ static __global__ void upsample_dw_kernel(const float* __restrict__ lat, long lo
 // ---------------------------------------------------------------------------------------------
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                                  float* __restrict__ y, int n_tok, int C, float eps) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_tok) return;
   const float* xr = x + (long long)warp * C;
@@ -330,7 +322,6 @@ static __global__ void rope_append_f32_kernel(const float* __restrict__ qkv, flo
                                        float* __restrict__ kc, float* __restrict__ vc,
                                        const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
                                        int B, int T, int H, int D, int cap, float neg_log_period_2_over_d) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, t, h, pair)
   const int half = D / 2;
   const long long total = (long long)B * T * H * half;
@@ -368,7 +359,6 @@ static __global__ void __launch_bounds__(128) ring_attn_f32_kernel(const float* 
                                                             const long long* __restrict__ offset,
                                                             const uint8_t* __restrict__ exec_mask,
                                                             int T, int H, int cap, int context) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   extern __shared__ float sm[];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int C = H * D;
@@ -442,7 +432,6 @@ static __global__ void __launch_bounds__(128) ring_attn_f32_kernel(const float* 
 }
 
 static __global__ void advance_offsets_kernel(long long* off, const uint8_t* exec_mask, int B, int T) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && exec_mask[b]) off[b] += T;
 }
@@ -474,7 +463,6 @@ static __global__ void __launch_bounds__(256) rvq_project_kernel(const float* __
                                                           long long lt, int n_frames, const float* __restrict__ wT0,
                                                           const float* __restrict__ wT1, float* __restrict__ res0,
                                                           float* __restrict__ res1, int Cin, int Dq) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   extern __shared__ float s_lat[];           // [Cin]
   const int q = blockIdx.x, which = blockIdx.y;
   const int b = q / n_frames, f = q % n_frames;
@@ -491,7 +479,6 @@ static __global__ void __launch_bounds__(256) rvq_project_kernel(const float* __
 }
 
 static __global__ void __launch_bounds__(RVQ_CHUNK) rvq_search_kernel(const RvqLevelArgs a) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int which = blockIdx.z;
   if (!a.active[which]) return;
   extern __shared__ float s_res[];            // [Dq][RVQ_QT]  (queries fastest: two broadcast LDS.128 per dim)
@@ -555,7 +542,6 @@ static __global__ void __launch_bounds__(RVQ_CHUNK) rvq_search_kernel(const RvqL
 
 // one CTA per (query, quantizer): argmin over the chunk partials, emit the code, res -= c[idx] (core_vq.py:514-516)
 static __global__ void __launch_bounds__(128) rvq_pick_kernel(const RvqLevelArgs a) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int which = blockIdx.y;
   if (!a.active[which]) return;
   const int q = blockIdx.x;
@@ -597,7 +583,6 @@ struct RvqDecArgs {
 // grid (B * n_frames, ceil(Cout / 64)), 256 threads = 64 output channels x 4 slices of the Dq-long dot products: the
 // dependent FMA chain per thread is Dq / 2 long instead of 2 * Dq, and a single session still spreads over 8 CTAs.
 static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs a) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   extern __shared__ float sm[];              // [2][Dq] summed code vectors, then [4][64] partial dot products
   const int b = blockIdx.x / a.n_frames, f = blockIdx.x % a.n_frames;
   const int tid = threadIdx.x;
@@ -637,7 +622,6 @@ static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs
 // load-time repacking
 // ---------------------------------------------------------------------------------------------
 static __global__ void pack_conv_w_kernel(const float* w /*[Cout][Cin][K]*/, float* out /*[Cout][K*Cin]*/, int Cout, int Cin, int K) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Cin * K) return;
   const int kw = i % K; long long r = i / K;
@@ -645,7 +629,6 @@ static __global__ void pack_conv_w_kernel(const float* w /*[Cout][Cin][K]*/, flo
   out[((long long)co * K + kw) * Cin + ci] = w[i];
 }
 static __global__ void pack_convtr_w_kernel(const float* w /*[Cin][Cout][2S]*/, float* out /*[Cout*S][2*Cin]*/, int Cin, int Cout, int S) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cin * Cout * 2 * S) return;
   const int k = i % (2 * S); long long r = i / (2 * S);
@@ -654,7 +637,6 @@ static __global__ void pack_convtr_w_kernel(const float* w /*[Cin][Cout][2S]*/, 
   out[((long long)co * S + ph) * (2 * Cin) + (long long)tap * Cin + ci] = w[i];
 }
 static __global__ void transpose_kernel(const float* in /*[R][C]*/, float* out /*[C][R]*/, int R, int C) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)R * C) return;
   const int c = i % C; const int r = i / C;
@@ -663,7 +645,6 @@ static __global__ void transpose_kernel(const float* in /*[R][C]*/, float* out /
 // centroids = embedding_sum / clamp(cluster_usage, 1e-5)  (core_vq.py:181-183) + transposed copy + norms
 static __global__ void build_codebook_kernel(const float* esum, const float* usage, float* cb, float* cbT, float* cnorm,
                                       int bins, int Dq) {
-  pdl_wait_all(); pdl_launch_next();     // programmatic dependent launch (mimi.cu: MIMI_LAUNCH)
   const int code = blockIdx.x;
   const float u = fmaxf(usage[code], 1e-5f);
   float s = 0.f;
