@@ -50,6 +50,8 @@ class LMSpec:
     depformer_schedule: tp.Optional[tp.List[int]] = None
     depformer_low_rank: tp.Optional[int] = None
     existing_text_padding_id: int = 3
+    extra_heads_num_heads: int = 0        # lm.py:224-226: nn.Linear(dim, extra_heads_dim) on transformer_out (the STT models)
+    extra_heads_dim: int = 6
 
     @staticmethod
     def from_config(cfg) -> "LMSpec":
@@ -248,9 +250,12 @@ class LMOracle:
         transformer_out, text_logits = self.forward_text(inp)
         text_token = sample_token(text_logits.float(), self.use_sampling, self.temp_text,
                                   self.top_k_text, noise_text, self.tie_break)[:, 0, 0]
-        # 5. depformer
+        # 5. depformer (absent when dep_q == 0: "No-Depformer --- e.g., an ASR model", lm.py:219-222)
         dep_logits: list = []
-        if depformer_replace_tokens is None:
+        self.last_transformer_out = transformer_out
+        if s.dep_q == 0:
+            audio = None
+        elif depformer_replace_tokens is None:
             audio = self.depformer_step(text_token, transformer_out, noise_audio, dep_logits)
         else:                                      # lm.py:751-755: the caller forces this frame's audio tokens
             assert depformer_replace_tokens.dim() == 3
@@ -265,9 +270,10 @@ class LMOracle:
         pos = (self.offsets % CT)[:, None, None]
         tv = self.cache[:, :1]
         tv.scatter_(-1, pos, torch.where(em, text_token[:, None, None], tv.gather(-1, pos)))
-        av = self.cache[:, 1:s.dep_q + 1]
-        apos = pos.expand(-1, s.dep_q, -1)
-        av.scatter_(-1, apos, torch.where(em, audio[:, :, None], av.gather(-1, apos)))
+        if audio is not None:
+            av = self.cache[:, 1:s.dep_q + 1]
+            apos = pos.expand(-1, s.dep_q, -1)
+            av.scatter_(-1, apos, torch.where(em, audio[:, :, None], av.gather(-1, apos)))
 
         # 7. re-aligned output (lm.py:774-783)
         if not support_out_of_sync and self.offset_cpu <= s.max_delay:
@@ -277,3 +283,15 @@ class LMOracle:
         out = self.cache.gather(2, index)
         out[(self.offsets <= s.max_delay) | ~self.exec_mask] = -2
         return out
+
+    @torch.no_grad()
+    def step_with_extra_heads(self, input_tokens: torch.Tensor, noise_text: torch.Tensor | None = None,
+                              noise_audio: tp.Sequence[torch.Tensor] | None = None, **kw):
+        """``LMGen.step_with_extra_heads`` (lm.py:793-807): the step's tokens plus ``softmax(extra_head(transformer_out))``
+        for every extra head ([B, 1, extra_heads_dim] each, in the model dtype like the reference)."""
+        out = self.step(input_tokens, noise_text, noise_audio, **kw)
+        if out is None:
+            return None
+        heads = [torch.softmax(F.linear(self.last_transformer_out, self.sd[f"extra_heads.{i}.weight"]), dim=-1)
+                 for i in range(self.spec.extra_heads_num_heads)]
+        return out, heads

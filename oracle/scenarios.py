@@ -75,3 +75,59 @@ def lm_noise(cfg, batch: int, top_k_text: int = 25, top_k: int = 250):
     nt = torch.empty(batch, kt).exponential_(1)
     na = [torch.empty(batch, ka).exponential_(1) for _ in range(cfg.dep_q)]
     return nt, na
+
+
+# ---- STT-style member of the family: no depformer, extra heads on the temporal output -----------------
+STT_SEED = 777
+STT_B = 2
+STT_STEPS = 14
+STT_KW = dict(dim=128, text_card=200, n_q=8, dep_q=0, card=64, num_heads=1, num_layers=2, hidden_scale=4.125, context=10,
+              delays=[0] * 9, extra_heads_num_heads=2, extra_heads_dim=6)
+
+
+def stt_reference_kwargs() -> dict:
+    """Constructor arguments of the reference's ``LMModel`` for this scenario (7B-family options, dep_q = 0)."""
+    return dict(STT_KW, existing_text_padding_id=3, causal=True, layer_scale=None, max_period=10000, gating="silu",
+                norm="rms_norm_f32", positional_embedding="rope", depformer_dim=64, depformer_dim_feedforward=64,
+                depformer_num_heads=1, depformer_num_layers=1, depformer_layer_scale=None, depformer_multi_linear=True,
+                depformer_context=8, depformer_max_period=10000, depformer_gating="silu", depformer_pos_emb="none",
+                depformer_weights_per_step=True)
+
+
+def stt_state_dict(seed: int = STT_SEED) -> dict:
+    """Seeded bf16 weights under the reference's key names (no depformer tensors; ``extra_heads.{i}.weight``)."""
+    k = STT_KW
+    d = k["dim"]
+    hidden = (2 * int(k["hidden_scale"] * d)) // 3
+    specs = [(f"emb.{i}.weight", (k["card"] + 1, d), d) for i in range(k["n_q"])]
+    specs += [("text_emb.weight", (k["text_card"] + 1, d), d), ("text_linear.weight", (k["text_card"], d), d),
+              ("out_norm.alpha", (1, 1, d), 0)]
+    for layer in range(k["num_layers"]):
+        p = f"transformer.layers.{layer}"
+        specs += [(p + ".self_attn.in_projs.0.weight", (3 * d, d), d), (p + ".self_attn.out_projs.0.weight", (d, d), d),
+                  (p + ".norm1.alpha", (1, 1, d), 0), (p + ".norm2.alpha", (1, 1, d), 0),
+                  (p + ".gating.linear_in.weight", (2 * hidden, d), d), (p + ".gating.linear_out.weight", (d, hidden), hidden)]
+    specs += [(f"extra_heads.{i}.weight", (k["extra_heads_dim"], d), d) for i in range(k["extra_heads_num_heads"])]
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape, fan_in in specs:
+        if fan_in == 0:
+            sd[key] = (1.0 + 0.1 * (2 * torch.rand(shape, generator=g) - 1)).bfloat16()
+        else:
+            bound = math.sqrt(3.0 / fan_in)
+            sd[key] = ((2 * torch.rand(shape, generator=g) - 1) * bound).bfloat16()
+    return sd
+
+
+def stt_spec():
+    from .lm import LMSpec
+    k = STT_KW
+    return LMSpec(dim=k["dim"], text_card=k["text_card"], n_q=k["n_q"], dep_q=0, card=k["card"], num_heads=k["num_heads"],
+                  num_layers=k["num_layers"], hidden_scale=k["hidden_scale"], context=k["context"], delays=list(k["delays"]),
+                  norm="rms_norm_f32", gating="silu", positional_embedding="rope", max_period=10000.0,
+                  extra_heads_num_heads=k["extra_heads_num_heads"], extra_heads_dim=k["extra_heads_dim"])
+
+
+def stt_input_codes(batch: int = STT_B, steps: int = STT_STEPS, seed: int = STT_SEED) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed + 1)
+    return torch.randint(0, STT_KW["card"], (steps, batch, STT_KW["n_q"], 1), generator=g)

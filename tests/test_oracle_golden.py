@@ -93,3 +93,30 @@ def test_step_outside_streaming_raises():
     orc = LMOracle(synth_lm_state_dict(cfg), LMSpec.from_config(cfg))
     with pytest.raises(RuntimeError):
         orc.step(torch.zeros(1, 8, 1, dtype=torch.long))
+
+
+def test_lm_stt_extra_heads(golden_dir):
+    """STT-style member of the family (no depformer, ``extra_heads``; ``LMGen.step_with_extra_heads``, lm.py:793-807 — what
+    ``rust/moshi-server/batched_asr.py:197`` calls): the oracle reproduces the fixture recorded from the unmodified reference
+    bit for bit, including the recycled slot.  Groundwork for SURVEY.md 8(f) item 2; the CUDA path does not build it yet."""
+    import json
+
+    info = json.loads((golden_dir / "lm_stt_tiny.json").read_text())
+    assert info["oracle_bit_exact"] is True
+    gold = load_file(golden_dir / "lm_stt_tiny.safetensors")
+    sd = scenarios.stt_state_dict()
+    codes = scenarios.stt_input_codes()
+    orc = LMOracle(sd, scenarios.stt_spec(), use_sampling=False)
+    orc.streaming(scenarios.STT_B)
+    for i in range(scenarios.STT_STEPS):
+        if i == 6:
+            orc.reset_streaming(torch.tensor([False, True]))
+        got = orc.step_with_extra_heads(codes[i])
+        if (gold["tokens"][i] == info["none_marker"]).all():
+            assert got is None
+            continue
+        toks, heads = got
+        assert torch.equal(toks, gold["tokens"][i])
+        assert toks.shape == (scenarios.STT_B, 1, 1)                  # text stream only
+        assert torch.equal(torch.stack([h[:, 0].float() for h in heads]), gold["extra_heads"][i])
+        assert torch.allclose(torch.stack(heads).float().sum(-1), torch.ones(2, scenarios.STT_B, 1), atol=2e-2)
