@@ -143,7 +143,7 @@ class DialogueService:
         elif isinstance(noise, np.ndarray):
             noise_host = self._np_ptr(noise, np.float32, B * self._lib.b200_lm_noise_per_row(self.lm._h), "noise")
         else:
-            keep = noise.to(device=self.lm.device, dtype=__import__("torch").float32).contiguous()
+            keep = noise.to(device=self.lm.device, dtype=torch.float32).contiguous()
             noise_dev = _lib.ptr(keep)
         _lib.check(self._lib.b200_frame_step(
             self._h, self._np_ptr(batch_pcm, np.float32, B * self.frame_size, "batch_pcm"),
