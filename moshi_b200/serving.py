@@ -151,3 +151,80 @@ class DialogueService:
             self._np_ptr(pcm_out, np.float32, B * self.frame_size, "pcm_out"),
             self._np_ptr(tokens_out, np.int64, B * self.tokens_per_slot, "tokens_out"),
             self._np_ptr(flags_out, np.uint8, B, "flags_out")))
+
+
+class SessionPool:
+    """Slot allocator and PCM framing in front of ``DialogueService.step`` (host logic only; no device work).
+
+    The reference's single-session server accumulates decoded opus PCM in ``all_pcm_data`` and cuts 1920-sample frames off
+    its front (``server.py:116-126``); the batched Rust server keeps one such buffer per slot and tells the Python side every
+    80 ms which slots are ``ACTIVE`` / ``RESET`` / have ``NODATA`` (``batched_asr.py:23-30,146-170``).  This class is that
+    bookkeeping for ``batch_size`` slots:
+
+    * ``open()`` hands out a free slot (the first frame it contributes carries ``RESET``), ``close(slot)`` returns it;
+    * ``push_pcm(slot, samples)`` appends any number of float32 samples to the slot's buffer;
+    * ``next_frame(batch_pcm, updates)`` fills one frame per slot that has >= ``frame_size`` samples buffered (``ACTIVE``, or
+      ``RESET`` for a slot's first frame) and marks the others ``NODATA`` — exactly the arrays ``DialogueService.step`` takes;
+      it returns the slots that contributed a frame;
+    * sessions are independent, so a slot that falls behind simply skips frames (``NODATA``) without stalling the batch.
+    """
+
+    def __init__(self, batch_size: int, frame_size: int = 1920, max_buffered_frames: int = 50):
+        import numpy as np
+        self.batch_size, self.frame_size = batch_size, frame_size
+        self.max_samples = max_buffered_frames * frame_size
+        self._free = list(range(batch_size - 1, -1, -1))            # pop() hands out slot 0 first
+        self._open: dict[int, bool] = {}                            # slot -> still needs its RESET frame
+        self._buf = [np.zeros(0, dtype=np.float32) for _ in range(batch_size)]
+        self.frames_in = [0] * batch_size
+
+    @property
+    def free_slots(self) -> int:
+        return len(self._free)
+
+    def open(self) -> int:
+        if not self._free:
+            raise RuntimeError("no free session slot")
+        slot = self._free.pop()
+        self._open[slot] = True
+        self.frames_in[slot] = 0
+        return slot
+
+    def close(self, slot: int) -> None:
+        import numpy as np
+        if slot not in self._open:
+            raise KeyError(f"slot {slot} is not open")
+        del self._open[slot]
+        self._buf[slot] = np.zeros(0, dtype=np.float32)
+        self._free.append(slot)
+
+    def push_pcm(self, slot: int, samples) -> None:
+        import numpy as np
+        if slot not in self._open:
+            raise KeyError(f"slot {slot} is not open")
+        samples = np.asarray(samples, dtype=np.float32).reshape(-1)
+        if self._buf[slot].size + samples.size > self.max_samples:
+            raise OverflowError(f"slot {slot}: more than {self.max_samples} samples buffered")
+        self._buf[slot] = np.concatenate((self._buf[slot], samples))
+
+    def buffered_frames(self, slot: int) -> int:
+        return self._buf[slot].size // self.frame_size
+
+    def next_frame(self, batch_pcm, updates) -> list[int]:
+        """Fills ``batch_pcm`` f32 [B * frame_size] and ``updates`` i32 [B] in place; returns the slots that contributed."""
+        fs = self.frame_size
+        assert batch_pcm.size == self.batch_size * fs and updates.size == self.batch_size
+        pcm = batch_pcm.reshape(self.batch_size, fs)
+        ready = []
+        for slot in range(self.batch_size):
+            if slot in self._open and self._buf[slot].size >= fs:
+                pcm[slot] = self._buf[slot][:fs]
+                self._buf[slot] = self._buf[slot][fs:]
+                updates[slot] = RESET if self._open[slot] else ACTIVE
+                self._open[slot] = False
+                self.frames_in[slot] += 1
+                ready.append(slot)
+            else:
+                pcm[slot] = 0.0
+                updates[slot] = NODATA
+        return ready

@@ -103,3 +103,39 @@ def test_two_rank_replicas_over_gloo(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line) == {"t": 2.0, "n": 11.0, "world": 2}
+
+
+def test_session_pool_frames_and_slot_updates():
+    """PCM framing and slot bookkeeping in front of DialogueService.step (server.py:116-126, batched_asr.py:146-170)."""
+    import numpy as np
+
+    from moshi_b200.serving import ACTIVE, NODATA, RESET, SessionPool
+    pool = SessionPool(batch_size=3, frame_size=8, max_buffered_frames=4)
+    a, b = pool.open(), pool.open()
+    assert (a, b) == (0, 1) and pool.free_slots == 1
+    pcm = np.full(3 * 8, 7.0, dtype=np.float32)
+    upd = np.zeros(3, dtype=np.int32)
+    pool.push_pcm(a, np.arange(11, dtype=np.float32))          # one frame and three samples
+    pool.push_pcm(b, np.arange(5, dtype=np.float32))           # not a frame yet
+    assert pool.next_frame(pcm, upd) == [a]
+    assert list(upd) == [RESET, NODATA, NODATA]
+    assert np.array_equal(pcm[:8], np.arange(8)) and not pcm[8:].any()
+    pool.push_pcm(a, np.arange(100, 105, dtype=np.float32))    # 3 + 5 = the next frame
+    pool.push_pcm(b, np.arange(5, 16, dtype=np.float32))       # two frames buffered for b
+    assert pool.next_frame(pcm, upd) == [a, b]
+    assert list(upd) == [ACTIVE, RESET, NODATA]
+    assert np.array_equal(pcm[:8], [8, 9, 10, 100, 101, 102, 103, 104]) and np.array_equal(pcm[8:16], np.arange(8))
+    assert pool.next_frame(pcm, upd) == [b] and list(upd) == [NODATA, ACTIVE, NODATA]
+    assert pool.next_frame(pcm, upd) == [] and list(upd) == [NODATA] * 3
+    pool.close(a)
+    c = pool.open()                                            # the freed slot is handed out again and starts with RESET
+    assert c == a
+    pool.push_pcm(c, np.zeros(8, dtype=np.float32))
+    assert pool.next_frame(pcm, upd) == [c] and upd[c] == RESET
+    with pytest.raises(KeyError):
+        pool.push_pcm(2, np.zeros(4, dtype=np.float32))
+    with pytest.raises(OverflowError):
+        pool.push_pcm(b, np.zeros(33, dtype=np.float32))
+    pool.open()
+    with pytest.raises(RuntimeError):
+        pool.open()
