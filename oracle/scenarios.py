@@ -131,3 +131,14 @@ def stt_spec():
 def stt_input_codes(batch: int = STT_B, steps: int = STT_STEPS, seed: int = STT_SEED) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed + 1)
     return torch.randint(0, STT_KW["card"], (steps, batch, STT_KW["n_q"], 1), generator=g)
+
+
+# ---- the 2B configuration's delay pattern (configs/moshi_dev_2b.json: acoustic delay 2) on a tiny member of the family ------
+DELAY2_SEED = 31
+DELAY2_B = 2
+DELAY2_STEPS = 16
+
+
+def delay2_config():
+    from moshi_b200.config import tiny_lm_config
+    return tiny_lm_config(n_q=8, dep_q=4, delays=[0, 0, 2, 2, 2, 0, 2, 1, 2])

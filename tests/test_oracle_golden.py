@@ -120,3 +120,23 @@ def test_lm_stt_extra_heads(golden_dir):
         assert toks.shape == (scenarios.STT_B, 1, 1)                  # text stream only
         assert torch.equal(torch.stack([h[:, 0].float() for h in heads]), gold["extra_heads"][i])
         assert torch.allclose(torch.stack(heads).float().sum(-1), torch.ones(2, scenarios.STT_B, 1), atol=2e-2)
+
+
+def test_lm_delay2_pattern(golden_dir):
+    """The 2B configuration's delay pattern (acoustic streams delayed by up to 2 steps, ``configs/moshi_dev_2b.json``) on a
+    tiny member of the family: ``None`` for the first max_delay steps, then the oracle reproduces the reference's tokens."""
+    info = json.loads((golden_dir / "lm_tiny_delay2.json").read_text())
+    assert info["oracle_bit_exact_tokens"] is True
+    gold = load_file(golden_dir / "lm_tiny_delay2.safetensors")["tokens"]
+    cfg = scenarios.delay2_config()
+    assert cfg.max_delay == 2
+    sd = synth_lm_state_dict(cfg, seed=scenarios.DELAY2_SEED)
+    codes = scenarios.lm_input_codes(cfg, scenarios.DELAY2_B, scenarios.DELAY2_STEPS, seed=scenarios.DELAY2_SEED)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False)
+    orc.streaming(scenarios.DELAY2_B)
+    for i in range(scenarios.DELAY2_STEPS):
+        out = orc.step(codes[i])
+        if i < cfg.max_delay:
+            assert out is None and (gold[i] == info["none_marker"]).all()
+        else:
+            assert torch.equal(out, gold[i]), i
