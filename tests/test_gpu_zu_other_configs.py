@@ -1,10 +1,4 @@
-"""GPU: other members of the model family behind the same kernels.
-
-NOT part of the default suite yet: these cases were written at the end of round 1 after the GPU budget was spent, so they have
-not run on a B200.  Set ``B200_EXPERIMENTAL_TESTS=1`` to run them; once green they lose the gate.
-"""
-import os
-
+"""GPU: other members of the model family behind the same kernels."""
 import pytest
 import torch
 from safetensors.torch import load_file
@@ -13,8 +7,7 @@ from moshi_b200.synth import synth_lm_state_dict
 from oracle import scenarios
 from oracle.lm import LMOracle, LMSpec
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL_TESTS") != "1", reason="not yet validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def test_delay2_pattern_matches_oracle_and_reference(golden_dir):
