@@ -296,7 +296,7 @@ def _gemm_roofline(B: int, device) -> dict:
 def b200_arm(args) -> None:
     from moshi_b200 import _lib
     from moshi_b200.config import MOSHI_7B
-    from moshi_b200.models import LMGen, loaders
+    from moshi_b200.models import loaders
     from moshi_b200.serving import DialogueService, barrier, init_distributed, max_over_ranks, sum_over_ranks
 
     rank, world = init_distributed()

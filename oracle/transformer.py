@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import math
 import typing as tp
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 import torch.nn.functional as F
