@@ -117,7 +117,15 @@ def sample_token(logits: torch.Tensor, use_sampling: bool, temp: float, top_k: i
 class LMOracle:
     def __init__(self, sd: tp.Dict[str, torch.Tensor], spec: LMSpec, use_sampling: bool = True,
                  temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25,
-                 tie_break: str = "torch", quantize: bool = False, kv_quant: str = ""):
+                 tie_break: str = "torch", quantize: bool = False, kv_quant: str = "", cfg_coef: float = 1.0,
+                 cfg_is_no_text: bool = False, cfg_is_masked_until: tp.Sequence[int] | None = None):
+        # classifier-free guidance without a conditioner (lm.py:596-604, 646-662, 714-732, 820-833): the model runs on 2B
+        # rows, the second half with the text stream zeroed (cfg_is_no_text) or every stream zeroed until a per-row step
+        # (cfg_is_masked_until); logits are logits_null + (logits - logits_null) * cfg_coef
+        self.cfg_coef, self.cfg_is_no_text = cfg_coef, cfg_is_no_text
+        self.cfg_is_masked_until = None if cfg_is_masked_until is None else torch.tensor(list(cfg_is_masked_until), dtype=torch.long)
+        if cfg_coef != 1.0:
+            assert cfg_is_no_text or cfg_is_masked_until is not None, "CFG without a conditioner needs one of the two masks"
         self.tie_break = tie_break
         self.quantize = quantize          # LMModel(quantize=True): every nn.Linear is a QLinear (lm.py:242-243)
         self.sd = sd
@@ -146,14 +154,18 @@ class LMOracle:
         self.offsets = torch.zeros(batch, dtype=torch.long)
         self.offset_cpu = 0
         self.exec_mask = torch.ones(batch, dtype=torch.bool)
-        self.main_state = tr.init_state(self.main_spec, batch, self.dtype)
+        self.model_batch = batch * 2 if self.cfg_coef != 1.0 else batch             # lm.py:646-647
+        self.main_state = tr.init_state(self.main_spec, self.model_batch, self.dtype)
         self.initial = torch.cat([torch.full((1, 1, 1), s.text_card, dtype=torch.long),
                                   torch.full((1, s.n_q, 1), s.card, dtype=torch.long)], dim=1)
         self.delays = torch.tensor(s.delays, dtype=torch.long)
 
+    def _model_rows(self, mask: torch.Tensor) -> torch.Tensor:
+        return mask.repeat(2) if self.cfg_coef != 1.0 else mask                     # lm.py:653-661
+
     def set_exec_mask(self, mask: torch.Tensor) -> None:
         self.exec_mask[:] = mask
-        self.main_state.exec_mask[:] = mask
+        self.main_state.exec_mask[:] = self._model_rows(mask)
 
     def reset_streaming(self, reset_mask: torch.Tensor | None = None) -> None:
         """``_LMGenState.reset`` (lm.py:537-542) + the LM's own streaming reset."""
@@ -162,7 +174,7 @@ class LMOracle:
         self.exec_mask |= reset_mask
         self.offsets[reset_mask] = 0
         self.offset_cpu = 0
-        tr.reset_state(self.main_state, reset_mask)
+        tr.reset_state(self.main_state, self._model_rows(reset_mask))
 
     # ------------------------------------------------------------------ model
     def forward_text(self, tokens: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
@@ -204,11 +216,15 @@ class LMOracle:
                        logits_out: list | None = None) -> torch.Tensor:
         """lm.py:809-850 – fresh Depformer state every frame, dep_q sequential sub-steps."""
         B = text_token.shape[0]
-        st = tr.init_state(self.dep_spec, B, self.dtype)
+        cfg = self.cfg_coef != 1.0
+        st = tr.init_state(self.dep_spec, 2 * B if cfg else B, self.dtype)
         prev = text_token
         toks = []
         for k in range(self.spec.dep_q):
-            logits = self.forward_depformer(k, prev[:, None], transformer_out, st)
+            logits = self.forward_depformer(k, (prev.repeat(2) if cfg else prev)[:, None], transformer_out, st)
+            if cfg:                                                                 # lm.py:828-833
+                lg, lg_null = logits.chunk(2)
+                logits = lg_null + (lg - lg_null) * self.cfg_coef
             if logits_out is not None:
                 logits_out.append(logits)
             nxt = sample_token(logits.float(), self.use_sampling, self.temp, self.top_k,
@@ -246,8 +262,21 @@ class LMOracle:
         pos = (self.offsets % CT)[:, None, None].expand_as(is_init)
         inp = torch.where(is_init, self.initial, self.cache.gather(2, pos))
 
+        if self.cfg_coef != 1.0:                                                    # lm.py:714-726
+            zero = torch.full((1,), -1, dtype=torch.long)
+            if self.cfg_is_masked_until is not None:
+                limit = self.delays[:, None] + self.cfg_is_masked_until.view(-1, 1, 1)
+                is_zeroed = self.offsets[:, None, None] <= limit
+                inp = torch.cat([inp, torch.where(is_zeroed & ~is_init, zero, inp)], dim=0)
+            else:
+                inp = inp.repeat(2, 1, 1)
+            if self.cfg_is_no_text:
+                inp[B:, :1] = torch.where(~is_init[:, :1], zero, inp[B:, :1])
         # 3./4. temporal transformer + text sampling (lm.py:734-747)
         transformer_out, text_logits = self.forward_text(inp)
+        if self.cfg_coef != 1.0:                                                    # lm.py:728-732
+            logits, logits_null = text_logits.chunk(2)
+            text_logits = logits if self.cfg_is_no_text else logits_null + (logits - logits_null) * self.cfg_coef
         text_token = sample_token(text_logits.float(), self.use_sampling, self.temp_text,
                                   self.top_k_text, noise_text, self.tie_break)[:, 0, 0]
         # 5. depformer (absent when dep_q == 0: "No-Depformer --- e.g., an ASR model", lm.py:219-222)

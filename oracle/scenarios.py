@@ -142,3 +142,15 @@ DELAY2_STEPS = 16
 def delay2_config():
     from moshi_b200.config import tiny_lm_config
     return tiny_lm_config(n_q=8, dep_q=4, delays=[0, 0, 2, 2, 2, 0, 2, 1, 2])
+
+
+# ---- classifier-free guidance without a conditioner (lm.py:596-604) on the tiny LM -------------------------------------------
+CFG_SEED = 9
+CFG_B = 2
+CFG_STEPS = 14
+CFG_RESET_STEP = 8
+CFG_MODES = {
+    "no_text": dict(cfg_coef=2.0, cfg_is_no_text=True),
+    "masked_until": dict(cfg_coef=1.5, cfg_is_masked_until=[3, 6]),
+    "both": dict(cfg_coef=3.0, cfg_is_no_text=True, cfg_is_masked_until=[2, 2]),
+}

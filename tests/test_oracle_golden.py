@@ -140,3 +140,26 @@ def test_lm_delay2_pattern(golden_dir):
             assert out is None and (gold[i] == info["none_marker"]).all()
         else:
             assert torch.equal(out, gold[i]), i
+
+
+@pytest.mark.parametrize("mode", ["no_text", "masked_until", "both"])
+def test_lm_cfg_without_conditioner(golden_dir, mode):
+    """Classifier-free guidance without a conditioner (``cfg_coef != 1`` with ``cfg_is_no_text`` / ``cfg_is_masked_until``,
+    lm.py:596-604, 646-662, 714-732, 820-833): 2B model rows, guided text and depformer logits; the oracle reproduces the
+    fixture recorded from the unmodified reference, including a slot reset.  Groundwork for SURVEY.md 8(f) item 2."""
+    info = json.loads((golden_dir / "lm_tiny_cfg.json").read_text())
+    assert info["modes"][mode]["oracle_bit_exact_tokens"] is True
+    gold = load_file(golden_dir / "lm_tiny_cfg.safetensors")[mode]
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    codes = scenarios.lm_input_codes(cfg, scenarios.CFG_B, scenarios.CFG_STEPS, seed=scenarios.CFG_SEED)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, **scenarios.CFG_MODES[mode])
+    orc.streaming(scenarios.CFG_B)
+    for i in range(scenarios.CFG_STEPS):
+        if i == scenarios.CFG_RESET_STEP:
+            orc.reset_streaming(torch.tensor([True, False]))
+        out = orc.step(codes[i])
+        if (gold[i] == info["none_marker"]).all():
+            assert out is None
+        else:
+            assert torch.equal(out, gold[i]), i
