@@ -118,14 +118,20 @@ class LMOracle:
     def __init__(self, sd: tp.Dict[str, torch.Tensor], spec: LMSpec, use_sampling: bool = True,
                  temp: float = 0.8, temp_text: float = 0.7, top_k: int = 250, top_k_text: int = 25,
                  tie_break: str = "torch", quantize: bool = False, kv_quant: str = "", cfg_coef: float = 1.0,
-                 cfg_is_no_text: bool = False, cfg_is_masked_until: tp.Sequence[int] | None = None):
+                 cfg_is_no_text: bool = False, cfg_is_masked_until: tp.Sequence[int] | None = None,
+                 condition_sum: torch.Tensor | None = None):
         # classifier-free guidance without a conditioner (lm.py:596-604, 646-662, 714-732, 820-833): the model runs on 2B
         # rows, the second half with the text stream zeroed (cfg_is_no_text) or every stream zeroed until a per-row step
         # (cfg_is_masked_until); logits are logits_null + (logits - logits_null) * cfg_coef
         self.cfg_coef, self.cfg_is_no_text = cfg_coef, cfg_is_no_text
         self.cfg_is_masked_until = None if cfg_is_masked_until is None else torch.tensor(list(cfg_is_masked_until), dtype=torch.long)
+        # fuser.get_sum(condition_tensors) cast to the model dtype (lm.py:616-626): [B (2B with CFG), 1, dim], added to the
+        # summed input embeddings every step (lm.py:398-399).  Evaluating the conditioners themselves happens once per
+        # session outside the step and is not restated here.
+        self.condition_sum = condition_sum
         if cfg_coef != 1.0:
-            assert cfg_is_no_text or cfg_is_masked_until is not None, "CFG without a conditioner needs one of the two masks"
+            assert cfg_is_no_text or cfg_is_masked_until is not None or condition_sum is not None, \
+                "CFG needs condition tensors or one of the two masks"
         self.tie_break = tie_break
         self.quantize = quantize          # LMModel(quantize=True): every nn.Linear is a QLinear (lm.py:242-243)
         self.sd = sd
@@ -186,6 +192,8 @@ class LMOracle:
             x = e if x is None else x + e
         t = scaled_embedding(self.sd, "text_emb", tokens[:, 0])
         x = t if x is None else x + t
+        if self.condition_sum is not None:
+            x = x + self.condition_sum.to(x)
         out = tr.forward(self.sd, "transformer", self.main_spec, x, self.main_state)
         out = tr.apply_norm(s.norm, out, self.sd, "out_norm")
         if self.quantize:

@@ -163,3 +163,27 @@ def test_lm_cfg_without_conditioner(golden_dir, mode):
             assert out is None
         else:
             assert torch.equal(out, gold[i]), i
+
+
+@pytest.mark.parametrize("mode", ["sum", "sum_cfg"])
+def test_lm_condition_sum(golden_dir, mode):
+    """The 2B configuration's conditioning (LUT conditioner fused by ``sum``, ``configs/moshi_dev_2b.json``): ``condition_sum``
+    (computed once per session by the reference's conditioner, stored in the fixture) is added to the summed input embeddings
+    every step (lm.py:398-399); with ``cfg_coef != 1`` the second half of the 2B model rows carries the null condition."""
+    info = json.loads((golden_dir / "lm_tiny_cond.json").read_text())
+    assert info["modes"][mode]["oracle_bit_exact_tokens"] is True
+    gold = load_file(golden_dir / "lm_tiny_cond.safetensors")
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    codes = scenarios.lm_input_codes(cfg, scenarios.CFG_B, scenarios.CFG_STEPS, seed=scenarios.CFG_SEED)
+    csum = gold[mode + ".condition_sum"]
+    assert csum.shape == (scenarios.CFG_B * (2 if mode == "sum_cfg" else 1), 1, cfg.dim)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=False, cfg_coef=info["modes"][mode]["cfg_coef"], condition_sum=csum)
+    orc.streaming(scenarios.CFG_B)
+    for i in range(scenarios.CFG_STEPS):
+        out = orc.step(codes[i])
+        want = gold[mode + ".tokens"][i]
+        if (want == info["none_marker"]).all():
+            assert out is None
+        else:
+            assert torch.equal(out, want), i
