@@ -113,7 +113,8 @@ int b200_mimi_decode(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, in
 /* MimiModel.decode_latent (compression.py:431-433): codes -> quantized latent f32 [B,512,n]. */
 int b200_mimi_decode_latent(b200_mimi* h, const int64_t* codes_dev, int n_codebooks, int n_frames,
                             float* latent_dev);
-/* Same as encode / decode with HOST buffers (H2D + D2H inside, returns when the result is ready). */
+/* Same as encode / decode with HOST buffers (H2D + D2H inside, returns when the result is ready): what the reference's
+ * server does around the two calls, `chunk.to(device)` ... `main_pcm.cpu()` (server.py:80-81, 131-135). */
 int b200_mimi_encode_host(b200_mimi* h, const float* pcm_host, int n_frames, int64_t* codes_host);
 int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codebooks, int n_frames,
                           float* pcm_host);
@@ -123,7 +124,8 @@ int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codeboo
 int64_t b200_mimi_state_bytes(b200_mimi* h);
 int b200_mimi_get_state(b200_mimi* h, void* dst_dev, int64_t capacity);
 int b200_mimi_set_state(b200_mimi* h, const void* src_dev, int64_t nbytes);
-/* 0 = one launch per kernel, 1 = replay each one-frame encode / decode as a CUDA graph (default 1). */
+/* 0 = one launch per kernel, 1 = replay each one-frame encode / decode as a CUDA graph (default 1): the reference's
+ * CUDAGraphed wrappers and its NO_CUDA_GRAPH switch (utils/compile.py:169-175, 190-280; compression.py:151-155). */
 int b200_mimi_set_graph(b200_mimi* h, int enable);
 /* Debug taps: copies a named fp32 intermediate of the last call into dst_dev (capacity in elements;
  * pass dst_dev = NULL to query *numel only).  Names: "enc.<i>", "dec.<i>" = output of SEANet module i
@@ -212,7 +214,8 @@ int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill);
  * ring offsets are advanced; ring contents are whatever is in memory) so that the steady-state
  * full-ring step can be timed without running 3000 warm-up steps. */
 int b200_lm_assume_fill(b200_lm* h, int fill);
-/* 0 = one launch per kernel, 1 = replay the whole step as one CUDA graph (default 1). */
+/* 0 = one launch per kernel, 1 = replay the whole step as one CUDA graph (default 1): the reference graphs forward_text and
+ * depformer_step separately (lm.py:628-634, utils/compile.py:190-280). */
 int b200_lm_set_graph(b200_lm* h, int enable);
 /* Storage type of the temporal KV rings, chosen before b200_lm_streaming_begin.  B200_KV_BF16 (default) is the
  * reference's ring (RingKVCache, transformer.py:196-288: 1.573 GB per session at context 3000).  B200_KV_FP8_E4M3 is
