@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 enum {
   B200_OK = 0,
@@ -160,7 +160,11 @@ typedef struct {
   int delays[33];             /* n_q + 1 entries */
   int quantize;               /* LMModel(quantize=True) (lm.py:107,242-243; utils/quantize.py): every linear is an int8 QLinear,
                                  quantised here from the bf16 weights at load */
+  int extra_heads_num_heads;  /* 0 for the dialogue models; the STT models carry nn.Linear(dim, extra_heads_dim) heads on the   */
+  int extra_heads_dim;        /* temporal output (lm.py:224-226), read by LMGen.step_with_extra_heads (lm.py:793-807)          */
 } b200_lm_config;
+/* Family limits: n_q <= 32, 0 <= dep_q <= 16 (dep_q = 0: no depformer, lm.py:219-222), temporal head dim 128, depformer head
+ * dim 64, vocabularies < 65535: covers configs/moshi_7b_202409.json, configs/moshi_dev_2b.json and the STT checkpoints. */
 
 /* loaders.get_moshi_lm (loaders.py:366-446). Tensors are bf16 with the reference's key names. */
 int b200_lm_create(const b200_lm_config* cfg, b200_lm** out);
@@ -172,6 +176,20 @@ int b200_lm_destroy(b200_lm* h);
 /* LMGen(...) sampling arguments (lm.py:556-571). */
 int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_text, int top_k,
                          int top_k_text);
+/* LMGen(cfg_coef, cfg_is_masked_until, cfg_is_no_text) (lm.py:556-604): classifier-free guidance.  cfg_coef != 1 makes the
+ * model run on 2 * batch rows (lm.py:646-647), the second half with the text stream zeroed (cfg_is_no_text) and / or every
+ * stream zeroed until a per-session step (masked_until_host i64 [n = batch], NULL = not used) (lm.py:714-726); the logits
+ * the samplers read are logits_null + (logits - logits_null) * cfg_coef (lm.py:728-732, 828-833).  Before streaming_begin. */
+int b200_lm_set_cfg(b200_lm* h, float cfg_coef, int cfg_is_no_text, const int64_t* masked_until_host, int n);
+/* _LMGenState.condition_sum (lm.py:616-626 -> forward_text lm.py:398-399): fuser.get_sum(condition_tensors) cast to bf16,
+ * [rows = batch (2 * batch with CFG)][dim], added to the summed input embeddings of every step.  NULL switches it off.
+ * While streaming; the tensor is copied.  (Evaluating the conditioners themselves is per-session work outside the step.) */
+int b200_lm_set_condition_sum(b200_lm* h, const void* sum_bf16_dev, int rows);
+/* Seed of the Exp(1) noise the step draws itself when the caller passes noise = NULL with sampling on (sampling.py:44 draws
+ * it from torch's generator; here a Philox4x32-10 stream keyed by (seed, step counter) inside the step's CUDA graph). */
+int b200_lm_seed_noise(b200_lm* h, uint64_t seed);
+/* Stream the next calls are ordered on (default: the one given to streaming_begin). */
+int b200_lm_set_stream(b200_lm* h, void* stream);
 /* LMGen.streaming(batch) enter / exit (lm.py:604-666): allocates token ring, KV rings, offsets. */
 int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream);
 int b200_lm_streaming_end(b200_lm* h);
@@ -184,7 +202,8 @@ int b200_lm_noise_per_row(b200_lm* h);
 
 /* LMGen.step (lm.py:785-791 -> _step :668-783).
  *   in_codes_dev  i64 [B, n_in] (n_in >= n_q - dep_q; extra columns ignored, lm.py:688-689)
- *   noise_dev     f32 [B, b200_lm_noise_per_row] or NULL when use_sampling == 0
+ *   noise_dev     f32 [B, b200_lm_noise_per_row] Exp(1) draws in the reference's order, or NULL: drawn inside the step
+ *                 (b200_lm_seed_noise); ignored when use_sampling == 0
  *   out_tokens_dev i64 [B, dep_q + 1] (row 0 text, 1.. audio; -2 = not ready for that row)
  *   *ready_host   0 while the reference would return None (offset_cpu <= max_delay), else 1
  *   support_out_of_sync: LMGen(support_out_of_sync=...) (lm.py:774-776) */
@@ -197,16 +216,36 @@ int b200_lm_step_ex(b200_lm* h, const int64_t* in_codes_dev, int n_in, const flo
                     int64_t* out_tokens_dev, int support_out_of_sync, int* ready_host);
 int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const float* noise_host,
                       int64_t* out_tokens_host, int support_out_of_sync, int* ready_host);
-/* Hook / debug taps of the last step, copied into dst_dev (capacity in bytes; NULL = query size):
- * "text_logits" bf16 [B,text_card] (LMGen.on_text_logits_hook), "transformer_out" bf16 [B,dim]
- * (step_with_extra_heads), "dep_logits" bf16 [dep_q,B,card], "input_tokens" i64 [B,n_q+1],
- * "text_token" i64 [B], "audio_tokens" i64 [dep_q,B]. */
+/* Hook / debug taps of the last step, copied into dst_dev (capacity in bytes; NULL = query size); MB = rows the model ran
+ * on (B, or 2B with CFG):  "text_logits" bf16 [B,text_card] (what LMGen.on_text_logits_hook sees: guided under CFG),
+ * "transformer_out" bf16 [MB,dim], "dep_logits" bf16 [dep_q,B,card], "input_tokens" i64 [MB,n_q+1], "text_token" i64 [B],
+ * "audio_tokens" i64 [dep_q,B], "extra_heads" bf16 [n_heads,MB,extra_heads_dim] (softmax(extra_head(transformer_out)),
+ * lm.py:803-806), "model_text_logits" bf16 [MB,text_card], "model_dep_logits" bf16 [dep_q,MB,card]. */
 int b200_lm_read_buffer(b200_lm* h, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes);
 /* LMGen.get_streaming_state / set_streaming_state: token ring, per-row offsets, exec mask, the temporal KV rings
  * (1.573 GB per session at full context) and the host step counter, as one opaque device blob. */
 int64_t b200_lm_state_bytes(b200_lm* h);
 int b200_lm_get_state(b200_lm* h, void* dst_dev, int64_t capacity);
 int b200_lm_set_state(b200_lm* h, const void* src_dev, int64_t nbytes);
+/* The same state entry by entry, so that the Python shim can present the reference's per-module State objects
+ * (streaming.py:158-181; _LMGenState lm.py:523-547, RingKVCache transformer.py:196-288).  Names: "exec_mask" u8 [B], "cache" i64
+ * [B,n_q+1,max_delay+2], "offsets" i64 [B], "model.offset" i64 [MB], "model.exec_mask" u8 [MB] (CFG only), "noise_counter",
+ * "layers.<i>.k" / ".v" bf16 [MB,H,context,128] (8-bit rings: ".k8" / ".v8" u8 + ".k_scale" / ".v_scale" f32 [MB,H,context]).
+ * shape8 receives up to 8 extents.  read / write copy one entry device-to-device on the handle's stream. */
+int b200_lm_state_count(b200_lm* h);
+int b200_lm_state_entry(b200_lm* h, int index, const char** name, int* dtype, int* ndim, int64_t* shape8, int64_t* nbytes);
+int b200_lm_state_read(b200_lm* h, const char* name, void* dst_dev, int64_t nbytes);
+int b200_lm_state_write(b200_lm* h, const char* name, const void* src_dev, int64_t nbytes);
+/* _LMGenState.offset_cpu (lm.py:529): the host step counter behind "step() returns None while offset_cpu <= max_delay". */
+int64_t b200_lm_get_offset_cpu(b200_lm* h);
+int b200_lm_set_offset_cpu(b200_lm* h, int64_t value);
+/* Synchronises the handle's stream, returns and clears the device error flags.  The kernels never read out of bounds:
+ * a token id outside its embedding table (anything but [0, card] and -1; the reference hits a device assert in F.embedding,
+ * lm_utils.py:103-121) embeds as the zero row and raises B200_FLAG_TOKEN_RANGE; the *_host entry points check the flags at
+ * their own synchronisation and return B200_ERR_INVALID. */
+#define B200_FLAG_TOKEN_RANGE 1
+#define B200_FLAG_CODE_RANGE 2
+int b200_lm_error_flags(b200_lm* h, int* flags_out);
 /* Algorithmic HBM bytes of one step at the current batch and ring fill: weights once
  * + per-row KV read/append + embeddings + logits. */
 int64_t b200_lm_algorithmic_bytes(b200_lm* h, int kv_fill);
@@ -253,14 +292,19 @@ int b200_frame_destroy(b200_frame* f);
 int b200_frame_step(b200_frame* f, const float* pcm_in_host, const int32_t* updates_host, const float* noise_host,
                     const float* noise_dev, float* pcm_out_host, int64_t* tokens_out_host, uint8_t* ready_out_host);
 
+/* Hand-offs of the last frame, copied device-to-device into dst_dev (NULL = query size): "codes_in" i64 [B,K] (what
+ * mimi.encode produced and lm_gen.step consumed, server.py:133-138), "tokens" i64 [B,dep_q+1], "codes_out" i64 [B,dep_q] (what
+ * mimi.decode consumed), "exec" / "decoder_exec" u8 [B]. */
+int b200_frame_read_buffer(b200_frame* f, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Kernel-level entry points (used by the parity tests; same kernels the handles launch)        */
 /* ------------------------------------------------------------------------------------------ */
 
-/* y[M,N] = x[M,K] * w[N,K]^T, bf16 in, fp32 accumulate, bf16 out.  impl: 0 = auto (what the LM
- * uses for this shape), 1 = SIMT weight-streaming kernel, 2 = tcgen05/TMA kernel. */
-int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K,
-                        int impl, void* stream);
+/* y[M,N] = x[M,K] * w[N,K]^T, bf16 in, fp32 accumulate, bf16 out, on row-major weights: packs them into tiles and runs
+ * the LM's linear for this shape (GEMV kernel up to 2 rows, tcgen05 stream-K / whole-tile / cluster split-K kernels above);
+ * synchronises the stream (test helper).  Reference op: every nn.Linear of the LM (transformer.py:304-305,554-555,588-589). */
+int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K, void* stream);
 /* Stream-K tcgen05 GEMM over pre-tiled weights (the LM's linear kernel; csrc/gemm_sk.cu).
  *   b200_op_packed_bytes / b200_op_pack_tiles: repack w bf16 [N,K] (epi 2: [2*gate_rows,K], rows gate|value,
  *   gating.py:18-20) into 16 KB SWIZZLE_128B tiles.
@@ -294,12 +338,6 @@ int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev
 int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
                      const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
                      int K, int stride, int elu_in, void* stream);
-/* Ring-cache decode attention for T = 1, head dim 128 (transformer.py:574-585): q bf16 [B,H,128],
- * K/V rings bf16 [B,H,cap,128], offsets i64 [B] (keys already appended: slots < min(offset+exec, cap)
- * are attended), out bf16 [B,H,128].  nsplit = KV splits per (b,h) (0 = what the LM would pick). */
-int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev,
-                        const int64_t* offsets_dev, const uint8_t* exec_mask_dev, int B, int H, int cap,
-                        int nsplit, void* stream);
 /* One temporal attention step, as the LM launches it (transformer.py:557-597): qkv bf16 [B,3*H*128] (rows q|k|v),
  * RoPE(q,k) at pos[b], K/V appended to the rings [B,H,cap,128] at pos % cap for rows with exec_mask, attention over
  * the min(pos + exec, cap) valid slots, out bf16 [B,H*128].  One kernel (rope + append + split-KV + merge). */

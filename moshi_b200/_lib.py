@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "_C" / "libmoshi_b200.so"
 
 B200_OK, B200_ERR_INVALID, B200_ERR_SHAPE, B200_ERR_STATE, B200_ERR_CUDA, B200_ERR_MISSING = range(6)
 B200_F32, B200_BF16, B200_F16, B200_I64, B200_U8 = range(5)
+ABI_VERSION = 2
 
 
 class MimiConfigC(C.Structure):
@@ -36,7 +37,7 @@ class LMConfigC(C.Structure):
         ("num_heads", C.c_int), ("num_layers", C.c_int), ("ffn_hidden", C.c_int), ("context", C.c_int),
         ("max_period", C.c_float), ("depformer_dim", C.c_int), ("depformer_num_heads", C.c_int),
         ("depformer_num_layers", C.c_int), ("depformer_ffn_hidden", C.c_int), ("delays", C.c_int * 33),
-        ("quantize", C.c_int),
+        ("quantize", C.c_int), ("extra_heads_num_heads", C.c_int), ("extra_heads_dim", C.c_int),
     ]
 
 
@@ -91,12 +92,24 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_assume_fill": (_I, [_P, _I]),
     "b200_lm_set_graph": (_I, [_P, _I]),
     "b200_lm_set_kv_dtype": (_I, [_P, _I]),
+    "b200_lm_set_cfg": (_I, [_P, C.c_float, _I, _P, _I]),
+    "b200_lm_set_condition_sum": (_I, [_P, _P, _I]),
+    "b200_lm_seed_noise": (_I, [_P, C.c_uint64]),
+    "b200_lm_set_stream": (_I, [_P, _P]),
+    "b200_lm_state_count": (_I, [_P]),
+    "b200_lm_state_entry": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200_lm_state_read": (_I, [_P, C.c_char_p, _P, C.c_int64]),
+    "b200_lm_state_write": (_I, [_P, C.c_char_p, _P, C.c_int64]),
+    "b200_lm_get_offset_cpu": (C.c_int64, [_P]),
+    "b200_lm_set_offset_cpu": (_I, [_P, C.c_int64]),
+    "b200_lm_error_flags": (_I, [_P, C.POINTER(_I)]),
     # one frame for every session slot, host buffers
     "b200_frame_create": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_P)]),
     "b200_frame_destroy": (_I, [_P]),
     "b200_frame_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_frame_read_buffer": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     # kernel-level
-    "b200_op_linear_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_op_linear_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200_op_packed_bytes": (C.c_int64, [_I, _I, _I, _I]),
     "b200_op_pack_tiles": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_op_linear_sk": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -107,7 +120,6 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_op_linear_i8": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_op_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "b200_op_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_op_attn_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
     "b200_op_attn_step_q8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _I, _P]),
     "b200_op_sample": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
@@ -136,7 +148,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.b200_abi_version() != 1:
+        if handle.b200_abi_version() != ABI_VERSION:
             raise RuntimeError("libmoshi_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -84,6 +84,14 @@ class MimiConfig:
             unsupported.append("transformer.gating/norm")
         if tr.get("positional_embedding", "rope") != "rope":
             unsupported.append("transformer.positional_embedding")
+        if sea.get("activation", "ELU") != "ELU" or sea.get("activation_params", {"alpha": 1.0}).get("alpha", 1.0) != 1.0:
+            unsupported.append("seanet.activation")
+        if not sea.get("causal", True) or not tr.get("causal", True):
+            unsupported.append("causal=False")
+        if sea.get("disable_norm_outer_blocks", 0) != 0:
+            unsupported.append("seanet.disable_norm_outer_blocks")
+        if not tr.get("conv_layout", True):
+            unsupported.append("transformer.conv_layout=False")
         if unsupported:
             raise ValueError(f"Mimi options outside the B200 hot path: {unsupported}")
         return MimiConfig(
@@ -155,6 +163,13 @@ class LMConfig:
     depformer_pos_emb: str = "none"
     depformer_weights_per_step: bool = True
     quantize: bool = False       # LMModel(quantize=True), lm.py:107,242-243: every nn.Linear becomes an int8 QLinear
+    extra_heads_num_heads: int = 0   # lm.py:108-109, 224-226: nn.Linear(dim, extra_heads_dim) heads on the temporal output (STT)
+    extra_heads_dim: int = 6
+    # lm.py:110-118 via loaders.get_conditioner_provider / get_condition_fuser (loaders.py:449-487): the JSON's "conditioners"
+    # and "fuser" sections (configs/moshi_dev_2b.json).  Only LUT conditioners fused by "sum" are on the step path.
+    conditioners: tp.Optional[dict] = None
+    fuser: tp.Optional[dict] = None
+    cross_attention: bool = False
     delays: tp.List[int] = field(
         default_factory=lambda: [0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1])
 
@@ -193,7 +208,12 @@ class LMConfig:
             return LMConfig.from_dict(json.load(f))
 
     def to_reference_kwargs(self) -> dict:
-        return dataclasses.asdict(self)
+        """Keyword arguments of the reference's ``LMModel`` (the ``conditioners`` / ``fuser`` JSON sections are turned into
+        modules by ``loaders.get_conditioner_provider`` / ``get_condition_fuser`` there, so they are not constructor arguments)."""
+        d = dataclasses.asdict(self)
+        d.pop("conditioners")
+        d.pop("fuser")
+        return d
 
     def check_supported(self) -> None:
         bad = []
@@ -209,7 +229,18 @@ class LMConfig:
             bad.append("depformer_multi_linear/weights_per_step")
         if len(self.delays) != self.n_q + 1:
             bad.append("delays")
-        if self.dim % self.num_heads or self.depformer_dim % self.depformer_num_heads:
+        if not self.causal:
+            bad.append("causal=False")
+        if self.dep_q and self.depformer_context < self.dep_q:
+            bad.append("depformer_context < dep_q (the depformer attends over all of a frame's codebooks)")
+        if self.cross_attention or (self.fuser or {}).get("cross") or (self.fuser or {}).get("prepend"):
+            bad.append("cross-attention / prepend conditioning (only fuser.sum is on the step path)")
+        for name, c in (self.conditioners or {}).items():
+            if c.get("type") != "lut":
+                bad.append(f"conditioner {name!r} of type {c.get('type')!r} (only 'lut')")
+        if not 0 <= self.dep_q <= 16 or not 1 <= self.n_q <= 32 or self.dep_q > self.n_q:
+            bad.append("n_q / dep_q (n_q <= 32, 0 <= dep_q <= 16)")
+        if self.dim % self.num_heads or (self.dep_q and self.depformer_dim % self.depformer_num_heads):
             bad.append("heads")
         if self.quantize and any(k % 16 for k in (self.dim, self.ffn_hidden, self.depformer_dim, self.depformer_ffn_hidden)):
             bad.append("quantize (int8 k-extents must be multiples of 16)")

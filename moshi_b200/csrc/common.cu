@@ -67,15 +67,15 @@ static size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
 
 size_t Arena::state_bytes() const {
   size_t n = 0;
-  for (auto& s : snap) n += pad256(s.second);
+  for (auto& s : snap) n += pad256(s.bytes);
   return n;
 }
 
 int Arena::save(void* dst, cudaStream_t st) const {
   size_t off = 0;
   for (auto& s : snap) {
-    B200_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, s.first, s.second, cudaMemcpyDeviceToDevice, st));
-    off += pad256(s.second);
+    B200_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, s.ptr, s.bytes, cudaMemcpyDeviceToDevice, st));
+    off += pad256(s.bytes);
   }
   return B200_OK;
 }
@@ -83,9 +83,30 @@ int Arena::save(void* dst, cudaStream_t st) const {
 int Arena::load(const void* src, cudaStream_t st) const {
   size_t off = 0;
   for (auto& s : snap) {
-    B200_CUDA(cudaMemcpyAsync(s.first, static_cast<const char*>(src) + off, s.second, cudaMemcpyDeviceToDevice, st));
-    off += pad256(s.second);
+    B200_CUDA(cudaMemcpyAsync(s.ptr, static_cast<const char*>(src) + off, s.bytes, cudaMemcpyDeviceToDevice, st));
+    off += pad256(s.bytes);
   }
+  return B200_OK;
+}
+
+int state_entry_info(const Arena& a, int index, const char** name, int* dtype, int* ndim, int64_t* shape8, int64_t* nbytes) {
+  if (index < 0 || index >= (int)a.snap.size()) B200_FAIL(B200_ERR_INVALID, "state_entry: index %d out of range", index);
+  const StateEntry& e = a.snap[index];
+  if (name) *name = e.name.c_str();
+  if (dtype) *dtype = e.dtype;
+  if (ndim) *ndim = (int)e.shape.size();
+  if (shape8) for (size_t i = 0; i < e.shape.size() && i < 8; ++i) shape8[i] = e.shape[i];
+  if (nbytes) *nbytes = (int64_t)e.bytes;
+  return B200_OK;
+}
+
+int state_entry_copy(const Arena& a, const char* name, void* dst_dev, const void* src_dev, int64_t nbytes, cudaStream_t st) {
+  const StateEntry* e = a.find_state(name ? name : "");
+  if (!e) B200_FAIL(B200_ERR_INVALID, "state entry '%s' does not exist", name ? name : "(null)");
+  if (nbytes != (int64_t)e->bytes) B200_FAIL(B200_ERR_SHAPE, "state entry '%s' holds %zu bytes, caller passed %lld", e->name.c_str(), e->bytes, (long long)nbytes);
+  if (dst_dev) B200_CUDA(cudaMemcpyAsync(dst_dev, e->ptr, e->bytes, cudaMemcpyDeviceToDevice, st));
+  else if (src_dev) B200_CUDA(cudaMemcpyAsync(e->ptr, src_dev, e->bytes, cudaMemcpyDeviceToDevice, st));
+  else B200_FAIL(B200_ERR_INVALID, "state entry copy: null buffer");
   return B200_OK;
 }
 

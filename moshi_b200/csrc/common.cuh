@@ -94,11 +94,23 @@ struct TensorStore {
 };
 
 // Device allocation bookkeeping for a handle: everything freed in one place.
+struct StateEntry {
+  std::string name;        // handle-local name; the Python shims map these onto the reference's per-module State fields
+  void* ptr; size_t bytes; int dtype; std::vector<int64_t> shape;
+};
 struct Arena {
   std::vector<void*> ptrs;
   // buffers that make up the streaming state (get/set_streaming_state, streaming.py:158-181), in registration order
-  std::vector<std::pair<void*, size_t>> snap;
-  void mark_state(void* p, size_t bytes) { if (p && bytes) snap.push_back({p, bytes}); }
+  std::vector<StateEntry> snap;
+  void mark_state(void* p, size_t bytes, const std::string& name = "", int dtype = B200_U8, std::vector<int64_t> shape = {}) {
+    if (!p || !bytes) return;
+    if (shape.empty()) shape = {(int64_t)bytes};
+    snap.push_back({name, p, bytes, dtype, shape});
+  }
+  const StateEntry* find_state(const std::string& name) const {
+    for (auto& e : snap) if (e.name == name) return &e;
+    return nullptr;
+  }
   size_t state_bytes() const;                 // each segment padded to 256 B
   int save(void* dst, cudaStream_t st) const;
   int load(const void* src, cudaStream_t st) const;
@@ -109,6 +121,20 @@ struct Arena {
   }
   void free_all();
 };
+
+// Makes the handle's device current for the duration of an entry point (the reference's modules carry their device; a caller
+// whose current device is another GPU must still be able to drive this handle).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// shared body of b200_{lm,mimi}_state_{count,entry,read,write}
+int state_entry_info(const Arena& a, int index, const char** name, int* dtype, int* ndim, int64_t* shape8, int64_t* nbytes);
+int state_entry_copy(const Arena& a, const char* name, void* dst_dev, const void* src_dev, int64_t nbytes, cudaStream_t st);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -4,7 +4,7 @@
 // The depformer is 8 dependent sub-steps x 6 layers of tiny GEMMs (1.23 GB of weights per frame, M = sessions):
 // as separate launches that is ~430 kernels whose launch / set-up / drain latency is 10-20x their HBM time.
 // Here one CTA per SM stays resident for the whole frame and the ~50 phases of a sub-step are separated by
-// grid barriers (all CTAs are co-resident: 1 CTA/SM by shared-memory size, grid <= #SMs):
+// grid barriers (all CTAs are co-resident: cooperative launch, 1 CTA/SM by shared-memory size, grid <= #SMs):
 //
 //   per sub-step k:   [row phase]   x = depformer_in[k](transformer_out) + emb_k(prev token); xn = rmsnorm(x)
 //     per layer l:    [GEMM]        in_proj partials            (tcgen05, split-K units over all CTAs)
@@ -23,7 +23,8 @@
 // activation box by 2-D TMA, single-thread tcgen05.mma into TMEM, tcgen05.ld epilogue); a unit = (128-row weight
 // tile, k-split) and every unit writes its fp32 partial [M x 128] to an L2-resident workspace; the consumer phase
 // sums the splits in split order (deterministic, independent of the batch) and applies the reference's cast points.
-#include "gemm_tc.cuh"
+#include "gemm_sk.cuh"
+#include "tc_prims.cuh"
 #include "lm_kernels.cuh"
 
 namespace b200 {
@@ -45,73 +46,7 @@ struct Gemm {                                // one GEMM phase
   int n_tiles, num_kb, kbps, S, A, N;        // S splits of kbps k-blocks; N = output columns per accumulator
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done, spins = 0;
-  do {
-    if (++spins > (1u << 22)) __trap();      // a pipeline bug must surface as a launch failure, never as a hung GPU
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
-}
+using namespace tcp;
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -122,7 +57,8 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 
 struct DepLayerW { const uint8_t *in_w, *out_w, *lin_in, *lin_out; };
 struct DepParams {
-  int B, Mpad, dd, H, F, card, dep_q, L, n_tables;
+  int B, Mpad, dd, H, F, card, text_card, dep_q, L, n_tables;
+  int* err;                                                  // device error flags (lm::ERR_*)
   int stages; uint32_t stage_bytes, tmem_cols, acc_cols; int n_acc;
   Gemm g_in, g_out, g_lin_in, g_lin_out, g_head;              // shapes (wt filled per (k, l) from the tables below)
   const DepLayerW* w;                                        // [dep_q][L] packed weight pointers (device)
@@ -155,8 +91,13 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
     const unsigned target = epoch * gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned spins = 0;
-    while (ld_acquire(bar) < target) {
-      if (++spins > (1u << 24)) __trap();
+    uint64_t t0 = 0;
+    while (ld_acquire(bar) < target) {               // all CTAs are co-resident (cooperative launch): bounded by wall clock only
+      if ((++spins & 4095u) == 0u) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > WAIT_LIMIT_NS) __trap();
+      }
     }
   }
   __syncthreads();
@@ -215,8 +156,9 @@ __device__ void input_rows(const DepParams& p, int k) {
   const bf16* table = p.tables[k];
   for (int m = blockIdx.x; m < p.B; m += gridDim.x) {
     const long long id = prev[m];
+    const bool ok = lm::embed_id_ok(id, k == 0 ? p.text_card : p.card, p.err);
     for (int j = threadIdx.x; j < p.dd; j += THREADS) {
-      const float e = id >= 0 ? bf2f(table[id * p.dd + j]) : 0.f;
+      const float e = ok ? bf2f(table[id * p.dd + j]) : 0.f;
       p.x[(long long)m * p.dd + j] = f2bf(bf2f(p.din[(long long)m * p.din_ld + (long long)k * p.dd + j]) + e);
     }
   }
@@ -244,7 +186,7 @@ __device__ void attn_phase(const DepParams& p, int S, int layer, int step) {
     *reinterpret_cast<__nv_bfloat162*>(vc + (rowo + step) * DD + 2 * lane) = __floats2bfloat162_rn(vv[0], vv[1]);
     __syncwarp();
     const float qx = rbf(q[0]), qy = rbf(q[1]);
-    float sc[8];
+    float sc[lm::DEP_MAX_Q];
     float mx = -INFINITY;
     for (int j = 0; j <= step; ++j) {
       const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kc + (rowo + j) * DD + 2 * lane));
@@ -555,7 +497,7 @@ size_t dep_fused_partial_floats(const DepFusedConfig& c) {
 }
 
 int dep_fused_create(const DepFusedConfig& c, DepFused** out) {
-  if (c.dd % 64 || c.dd > 4 * THREADS || c.dd / c.H != DD || c.dep_q > 8 || c.F % 8 || c.B < 1 || c.B > 256)
+  if (c.dd % 64 || c.dd > 4 * THREADS || c.dd / c.H != DD || c.dep_q > lm::DEP_MAX_Q || c.dep_q < 1 || c.F % 8 || c.B < 1 || c.B > 256)
     B200_FAIL(B200_ERR_INVALID, "fused depformer: unsupported configuration");
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -566,7 +508,7 @@ int dep_fused_create(const DepFusedConfig& c, DepFused** out) {
   DepParams& p = d->p;
   memset(&p, 0, sizeof(p));
   d->grid = sk_num_sms();
-  p.B = c.B; p.Mpad = ((c.B + 15) / 16) * 16; p.dd = c.dd; p.H = c.H; p.F = c.F; p.card = c.card; p.dep_q = c.dep_q; p.L = c.L;
+  p.B = c.B; p.Mpad = ((c.B + 15) / 16) * 16; p.dd = c.dd; p.H = c.H; p.F = c.F; p.card = c.card; p.text_card = c.text_card; p.err = c.err; p.dep_q = c.dep_q; p.L = c.L;
   p.stage_bytes = (uint32_t)(2 * TILE_BYTES + p.Mpad * BLOCK_K * 2);
   int stages = (200 * 1024) / (int)p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -622,6 +564,14 @@ int dep_fused_create(const DepFusedConfig& c, DepFused** out) {
   B200_TRY(make_map(enc, &d->map_x, c.x, c.B, c.dd, p.Mpad));
   d->smem = (size_t)stages * p.stage_bytes + 1024 + 16 * MAX_STAGES + 64;
   B200_CUDA(cudaFuncSetAttribute(dep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  int per_sm = 0, coop = 0, dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dep_fused_kernel, THREADS, d->smem));
+  if (!coop || per_sm < 1) {
+    dep_fused_destroy(d);
+    B200_FAIL(B200_ERR_CUDA, "fused depformer: the device cannot co-schedule %d CTAs of %zu B shared memory", d->grid, d->smem);
+  }
   *out = d;
   return B200_OK;
 }
@@ -637,9 +587,19 @@ void dep_fused_destroy(DepFused* d) {
   delete d;
 }
 
+// Cooperative launch: the driver guarantees that all CTAs of the grid are co-resident (or fails the launch), so the grid
+// barrier cannot deadlock against another handle's persistent kernel, an MPS neighbour or a second replica on the same GPU.
 int dep_fused_launch(DepFused* d, cudaStream_t stream) {
   B200_CUDA(cudaMemsetAsync(d->p.bar, 0, sizeof(unsigned), stream));
-  dep_fused_kernel<<<d->grid, THREADS, d->smem, stream>>>(d->map_xn, d->map_ao, d->map_h, d->map_x, d->p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)d->grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = d->smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, dep_fused_kernel, d->map_xn, d->map_ao, d->map_h, d->map_x, d->p);
+  if (le != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "fused depformer: cooperative launch failed: %s", cudaGetErrorString(le));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("dep_fused");
 }

@@ -8,6 +8,7 @@
 //     encode -> step -> host copies), the batched form the Rust server binds through py_basr_module.rs.
 // Everything is enqueued on the stream both handles stream on; the only wait is the one before the host reads.
 #include <algorithm>
+#include <string>
 
 #include "common.cuh"
 
@@ -122,6 +123,24 @@ int b200_frame_destroy(b200_frame* f) {
   cudaFreeHost(f->h_updates); cudaFreeHost(f->h_ready);
   if (f->done) cudaEventDestroy(f->done);
   delete f;
+  return B200_OK;
+}
+
+int b200_frame_read_buffer(b200_frame* f, const char* name, void* dst_dev, int64_t capacity_bytes, int64_t* nbytes) {
+  if (!f || !name) B200_FAIL(B200_ERR_INVALID, "frame_read_buffer: null argument");
+  const std::string n = name;
+  const size_t B = (size_t)f->B;
+  const void* src = nullptr; int64_t sz = 0;
+  if (n == "codes_in") { src = f->codes_in; sz = (int64_t)(B * f->n_in * 8); }
+  else if (n == "codes_out") { src = f->codes_out; sz = (int64_t)(B * f->dep_q * 8); }
+  else if (n == "tokens") { src = f->tokens; sz = (int64_t)(B * (f->dep_q + 1) * 8); }
+  else if (n == "exec") { src = f->exec; sz = (int64_t)B; }
+  else if (n == "decoder_exec") { src = f->dec_exec; sz = (int64_t)B; }
+  else B200_FAIL(B200_ERR_INVALID, "frame_read_buffer: unknown buffer '%s'", name);
+  if (nbytes) *nbytes = sz;
+  if (!dst_dev) return B200_OK;
+  if (capacity_bytes < sz) B200_FAIL(B200_ERR_SHAPE, "frame_read_buffer: destination too small");
+  B200_CUDA(cudaMemcpyAsync(dst_dev, src, (size_t)sz, cudaMemcpyDeviceToDevice, f->stream));
   return B200_OK;
 }
 

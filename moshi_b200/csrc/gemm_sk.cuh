@@ -30,13 +30,8 @@ struct GemmPlanCache {
   void clear() { maps.clear(); }
 };
 
-bool supported(int M, int N, int K, int epi);
-// implementation the LM uses for this shape: 1 = SIMT weight-streaming kernel, 2 = tcgen05 kernel
-int auto_pick(int M, int N, int K, int epi);
+// resolves cuTensorMapEncodeTiled and sets the kernels' shared-memory attributes (call before capturing a graph)
 int prepare_plans(GemmPlanCache& cache);
-int linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, __nv_bfloat16* y,
-           long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
-           cudaStream_t stream);
 
 // ---- stream-K kernel over pre-tiled weights (gemm_sk.cu) --------------------------------------
 struct SkTuning {
@@ -73,7 +68,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
 
 // ---- the depformer of one frame as one persistent kernel (dep_fused.cu) ---------------------------
 struct DepFusedConfig {
-  int B, dd, H, F, card, dep_q, L;
+  int B, dd, H, F, card, text_card, dep_q, L;
+  int* err;                                        // device error flags (lm::ERR_*), may be null
   const void* const* in_w; const void* const* out_w; const void* const* lin_in; const void* const* lin_out;   // [dep_q*L] packed tiles
   const void* const* heads;        // [dep_q] packed tiles
   const void* const* tables;       // [dep_q] embedding tables (bf16 [V][dd]); [0] = text

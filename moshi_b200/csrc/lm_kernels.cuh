@@ -39,9 +39,18 @@ struct TokenRing {
   const uint8_t* exec_mask;
   const int* delays;       // [Kc]
   int Kc, CT, dep_q, n_q, card, text_card, max_delay;
+  // classifier-free guidance (lm.py:596-604, 714-726): the model runs on 2B rows, rows [B, 2B) are the "null" copies
+  int cfg;                          // 0 = off, 1 = on
+  int cfg_is_no_text;               // null rows: text stream zeroed
+  const long long* cfg_masked_until;   // [B] or null: null rows: every stream zeroed while offset <= delay + masked_until[b]
+  int* err;                         // device error flags (ERR_*), may be null
 };
 
-// One thread per (b, k): write the user's codes, then build the model input row [B][Kc].
+// device error flags: raised instead of reading out of bounds; surfaced by b200_lm_error_flags / b200_mimi_error_flags and by
+// the host-synchronising entry points
+enum { ERR_TOKEN_RANGE = 1, ERR_CODE_RANGE = 2 };
+
+// One thread per (b, k): write the user's codes, then build the model input row(s) [MB][Kc].
 static __global__ void lm_prepare_kernel(const TokenRing r, const long long* __restrict__ in_codes, int n_in,
                                   long long* __restrict__ input_tokens, int B) {
   pdl_trigger();
@@ -57,14 +66,22 @@ static __global__ void lm_prepare_kernel(const TokenRing r, const long long* __r
   }
   const bool is_init = off <= r.delays[k] || !exec;             // lm.py:698-699
   const long long initial = k == 0 ? r.text_card : r.card;      // lm.py:297-311
-  input_tokens[i] = is_init ? initial : row[off % r.CT];
+  const long long tok = is_init ? initial : row[off % r.CT];
+  input_tokens[i] = tok;
+  if (r.cfg) {                                                  // lm.py:714-726
+    long long t2 = tok;
+    if (r.cfg_masked_until != nullptr && off <= r.delays[k] + r.cfg_masked_until[b] && !is_init) t2 = -1;
+    if (r.cfg_is_no_text && k == 0 && !is_init) t2 = -1;
+    input_tokens[(long long)B * r.Kc + i] = t2;
+  }
 }
 
 // offsets += exec; store sampled tokens; gather the delay-aligned output (lm.py:759-783)
 static __global__ void lm_finish_kernel(const TokenRing r, const long long* __restrict__ text_token,
                                  const long long* __restrict__ audio_tokens /*[dep_q][B]*/,
-                                 long long* __restrict__ out /*[B][dep_q+1]*/, int B) {
+                                 long long* __restrict__ out /*[B][dep_q+1]*/, int B, unsigned long long* noise_ctr) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && noise_ctr != nullptr) *noise_ctr += 1;        // the next step draws fresh Exp(1) noise (lm_noise_kernel)
   if (b >= B) return;
   const bool exec = r.exec_mask[b] != 0;
   long long off = r.offsets[b];
@@ -91,8 +108,17 @@ static __global__ void lm_finish_kernel(const TokenRing r, const long long* __re
 struct EmbedTables {
   const bf16* audio[32];   // [card+1][dim]
   const bf16* text;        // [text_card+1][dim]
-  int n_q;
+  int n_q, card, text_card;
+  const bf16* condition_sum;   // [rows][dim] or null: fuser.get_sum(condition_tensors), added last (lm.py:398-399)
+  int* err;
 };
+// valid ids: [0, vocab] (vocab = the initial token) and -1 (zero row); anything else (-2 "ungenerated", ids past the table)
+// would be a device assert in the reference (F.embedding); here it raises ERR_TOKEN_RANGE and embeds as the zero row
+__device__ __forceinline__ bool embed_id_ok(long long id, int vocab, int* err) {
+  if (id >= 0 && id <= vocab) return true;
+  if (id != -1 && err != nullptr) atomicOr(err, ERR_TOKEN_RANGE);
+  return false;
+}
 static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long* __restrict__ tokens /*[B][n_q+1]*/,
                                     bf16* __restrict__ x /*[B][dim]*/, int B, int dim) {
   pdl_trigger();
@@ -105,7 +131,7 @@ static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long*
   for (int k = 0; k < t.n_q; ++k) {
     const long long id = tok[k + 1];
     float e0 = 0.f, e1 = 0.f;
-    if (id >= 0) {
+    if (embed_id_ok(id, t.card, t.err)) {
       const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(t.audio[k] + id * dim + c);
       e0 = __low2float(v); e1 = __high2float(v);
     }
@@ -115,27 +141,92 @@ static __global__ void lm_embed_sum_kernel(const EmbedTables t, const long long*
   {
     const long long id = tok[0];
     float e0 = 0.f, e1 = 0.f;
-    if (id >= 0) {
+    if (embed_id_ok(id, t.text_card, t.err)) {
       const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(t.text + id * dim + c);
       e0 = __low2float(v); e1 = __high2float(v);
     }
     if (t.n_q == 0) { s0 = e0; s1 = e1; }
     else { s0 = rbf(s0 + e0); s1 = rbf(s1 + e1); }
   }
+  if (t.condition_sum != nullptr) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(t.condition_sum + (long long)b * dim + c);
+    s0 = rbf(s0 + __low2float(v)); s1 = rbf(s1 + __high2float(v));
+  }
   *reinterpret_cast<__nv_bfloat162*>(x + (long long)b * dim + c) = __floats2bfloat162_rn(s0, s1);
 }
 
-// depformer input: x = depformer_in[k](transformer_out) + emb(prev)   (lm.py:475-486)
+// depformer input: x = depformer_in[k](transformer_out) + emb(prev)   (lm.py:475-486); with CFG the rows [Bt, 2*Bt) reuse the
+// tokens of rows [0, Bt) (lm.py:824-826)
 static __global__ void dep_input_kernel(const bf16* __restrict__ din /*[B][ld]*/, long long ld, int col0,
-                                 const bf16* __restrict__ table /*[V][dd]*/, const long long* __restrict__ prev /*[B]*/,
-                                 bf16* __restrict__ x /*[B][dd]*/, int B, int dd) {
+                                 const bf16* __restrict__ table /*[V][dd]*/, const long long* __restrict__ prev /*[Bt]*/,
+                                 bf16* __restrict__ x /*[B][dd]*/, int B, int dd, int Bt, int vocab, int* err) {
   pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dd) return;
   const int b = i / dd, c = i % dd;
-  const long long id = prev[b];
-  const float e = id >= 0 ? bf2f(table[id * dd + c]) : 0.f;
+  const long long id = prev[b % Bt];
+  const float e = embed_id_ok(id, vocab, err) ? bf2f(table[id * dd + c]) : 0.f;
   x[i] = f2bf(bf2f(din[(long long)b * ld + col0 + c]) + e);
+}
+
+// classifier-free guidance on logits (lm.py:728-732, 828-833): out = null + (cond - null) * coef, every operation a bf16
+// tensor op like the reference's; rows [0, B) = conditioned, [B, 2B) = null
+static __global__ void cfg_combine_kernel(const bf16* __restrict__ logits /*[2B][card]*/, bf16* __restrict__ out /*[B][card]*/,
+                                   int B, int card, float coef) {
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * card) return;
+  const float l = bf2f(logits[i]), n = bf2f(logits[(long long)B * card + i]);
+  out[i] = f2bf(n + rbf(rbf(l - n) * coef));
+}
+
+// extra heads of the STT models (lm.py:224-226, 803-806): softmax(extra_head(transformer_out)) in the model dtype.
+// One warp per (head, row); E <= 32 outputs per head.
+static __global__ void extra_heads_kernel(const bf16* __restrict__ tout /*[B][dim]*/, const bf16* const* __restrict__ w /*[n][E][dim]*/,
+                                   bf16* __restrict__ out /*[n][B][E]*/, int B, int dim, int E, int n_heads) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_heads * B) return;
+  const int hd = warp / B, b = warp - hd * B;
+  const bf16* wh = w[hd];
+  float mine = -INFINITY;                      // lane e keeps logit e
+  for (int e = 0; e < E; ++e) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc = fmaf(bf2f(tout[(long long)b * dim + k]), bf2f(wh[(long long)e * dim + k]), acc);
+    acc = rbf(warp_sum(acc));                  // nn.Linear output is a bf16 tensor
+    if (lane == e) mine = acc;
+  }
+  const float mx = warp_max(mine);
+  const float ex = lane < E ? expf(mine - mx) : 0.f;
+  const float sum = warp_sum(ex);
+  if (lane < E) out[((long long)hd * B + b) * E + lane] = f2bf(ex / sum);
+}
+
+// Exp(1) noise for one step's samplers (sampling.py:44: torch.empty_like(probs).exponential_(1)), drawn inside the step's graph:
+// Philox4x32-10 keyed by the session seed, counter = (element / 4, step counter); -log(u), u in (0, 1].
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static __global__ void lm_noise_kernel(float* __restrict__ noise, long long n, unsigned long long seed,
+                                const unsigned long long* __restrict__ step_ctr) {
+  pdl_trigger();
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one Philox block = 4 values
+  if (q * 4 >= n) return;
+  const unsigned long long ctr = *step_ctr;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = q * 4 + j;
+    if (i < n) noise[i] = -__logf(((float)(r[j] >> 8) + 1.0f) * (1.0f / 16777216.0f));     // u in (2^-24, 1]
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,117 +262,19 @@ static __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restr
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// SIMT weight-streaming GEMM for skinny M:  y[m][n] = sum_k x[m][k] * w[n][k]
-// One warp per output feature n (two weight rows when gating); lanes stride K in 16-byte chunks.
-// ---------------------------------------------------------------------------------------------
+// epilogues of the LM linears (gemm_sk.cu): plain store, residual add, gated SiLU (gating.py:18-20)
 enum { LIN_STORE = 0, LIN_RESADD = 1, LIN_GATE = 2 };
-constexpr int SIMT_MB = 8;
 
-template <int EPI>
-static __global__ void __launch_bounds__(256) linear_simt_kernel(const bf16* __restrict__ x, long long ldx,
-                                                          const bf16* __restrict__ w, bf16* __restrict__ y, long long ldy,
-                                                          const bf16* __restrict__ res, long long ldr, int M, int N,
-                                                          int K, int gate_rows) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const bf16* w0 = w + (long long)warp * K;
-  const bf16* w1 = EPI == LIN_GATE ? w + (long long)(warp + gate_rows) * K : nullptr;
-  for (int m0 = 0; m0 < M; m0 += SIMT_MB) {
-    float acc0[SIMT_MB], acc1[SIMT_MB];
-#pragma unroll
-    for (int i = 0; i < SIMT_MB; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
-    for (int k = lane * 8; k < K; k += 256) {
-      float wf0[8], wf1[8];
-      unpack8(*reinterpret_cast<const uint4*>(w0 + k), wf0);
-      if (EPI == LIN_GATE) unpack8(*reinterpret_cast<const uint4*>(w1 + k), wf1);
-#pragma unroll
-      for (int i = 0; i < SIMT_MB; ++i) {
-        if (m0 + i < M) {
-          float xf[8];
-          unpack8(*reinterpret_cast<const uint4*>(x + (long long)(m0 + i) * ldx + k), xf);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc0[i] = fmaf(xf[j], wf0[j], acc0[i]);
-            if (EPI == LIN_GATE) acc1[i] = fmaf(xf[j], wf1[j], acc1[i]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < SIMT_MB; ++i) {
-      float a0 = warp_sum(acc0[i]);
-      float a1 = EPI == LIN_GATE ? warp_sum(acc1[i]) : 0.f;
-      if (lane == 0 && m0 + i < M) {
-        const int m = m0 + i;
-        float v;
-        if (EPI == LIN_STORE) v = a0;
-        else if (EPI == LIN_RESADD) v = bf2f(res[(long long)m * ldr + warp]) + rbf(a0);
-        else {
-          const float g = rbf(a0), u = rbf(a1);
-          v = rbf(g / (1.f + expf(-g))) * u;          // bf16(silu(gate)) * value   (gating.py:18-20)
-        }
-        y[(long long)m * ldy + warp] = f2bf(v);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// RoPE (interleaved pairs, fp32) + ring KV append for T = 1 (transformer.py:557-569, 247-253)
-//   qkv [B][3*C] bf16 (rows q | k | v, each (h d)) -> q_rot [B][C]; K, V ring [B][H][cap][D]
-// use_rope = 0 for the depformer (depformer_pos_emb = "none").  pos / slot come from per-row
-// `offset` (temporal) or from the scalar `step` (depformer: all rows advance together).
-// ---------------------------------------------------------------------------------------------
-static __global__ void rope_append_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ q_out,
-                                        bf16* __restrict__ kc, bf16* __restrict__ vc,
-                                        const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
-                                        int step, int B, int H, int D, int cap, int use_rope,
-                                        float neg_log_period_2_over_d) {
-  pdl_trigger();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, h, pair)
-  const int half = D / 2;
-  if (i >= (long long)B * H * half) return;
-  const int pr = i % half;
-  const int h = (i / half) % H;
-  const int b = i / ((long long)half * H);
-  const int C = H * D;
-  const long long pos = offset ? offset[b] : step;
-  const bf16* base = qkv + (long long)b * 3 * C + h * D + 2 * pr;
-  float qr = bf2f(base[0]), qi = bf2f(base[1]);
-  float kr = bf2f(base[C]), ki = bf2f(base[C + 1]);
-  if (use_rope) {
-    const float freq = expf((float)pr * neg_log_period_2_over_d);
-    float sn, cs;
-    sincosf(freq * (float)pos, &sn, &cs);
-    const float a = qr * cs - qi * sn, bq = qr * sn + qi * cs;
-    const float c2 = kr * cs - ki * sn, d2 = kr * sn + ki * cs;
-    qr = a; qi = bq; kr = c2; ki = d2;
-  }
-  *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * C + h * D + 2 * pr) = __floats2bfloat162_rn(qr, qi);
-  if (exec_mask && !exec_mask[b]) return;
-  const int slot = (int)(pos % cap);
-  const long long o = (((long long)b * H + h) * cap + slot) * D + 2 * pr;
-  *reinterpret_cast<__nv_bfloat162*>(kc + o) = __floats2bfloat162_rn(kr, ki);
-  *reinterpret_cast<__nv_bfloat162*>(vc + o) = *reinterpret_cast<const __nv_bfloat162*>(base + 2 * C);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Decode attention over the ring (T = 1, D = 128): split-KV with online softmax.
-//   grid = (B*H, nsplit); 128 threads; each half-warp owns one key per iteration (16 lanes x 16 B).
-//   Only the slots that hold valid keys are read (n_valid = min(offset + exec, cap)); the
-//   reference reads the whole ring under a mask (transformer.py:574-585) — same result.
-// ---------------------------------------------------------------------------------------------
 constexpr int ATT_D = 128;
 constexpr int ATT_THREADS = 128;
 
-// split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
 // B200_ATT_U=2|4 (diagnostics): register-buffer depth of attn_step_kernel; default 4
 inline int attn_group_keys() {
   static const int u = [] { const char* e = getenv("B200_ATT_U"); return (e && atoi(e) == 2) ? 2 : 4; }();
   return u;
 }
 
+// split-KV so that B*H*nsplit CTAs cover the 148 SMs a few times over even at B = 1
 inline int attn_pick_splits(int B, int H, int cap) {
   int ns = (148 * 4 + B * H - 1) / (B * H);
   if (ns < 1) ns = 1;
@@ -289,107 +282,6 @@ inline int attn_pick_splits(int B, int H, int cap) {
   const int max_by_len = (cap + 63) / 64;
   if (ns > max_by_len) ns = max_by_len;
   return ns;
-}
-
-static __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
-                                                                  const bf16* __restrict__ vc, float* __restrict__ part,
-                                                                  const long long* __restrict__ offset,
-                                                                  const uint8_t* __restrict__ exec_mask, int H, int cap,
-                                                                  int nsplit) {
-  pdl_trigger();
-  const int bh = blockIdx.x, split = blockIdx.y;
-  const int b = bh / H;
-  const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15;
-  const int hw = tid >> 4;                          // half-warp id 0..7
-  long long n_valid = offset[b] + (exec_mask[b] ? 1 : 0);
-  if (n_valid > cap) n_valid = cap;
-  const int per = (int)((n_valid + nsplit - 1) / nsplit);
-  const int s0 = split * per;
-  const int s1 = (int)min((long long)(s0 + per), n_valid);
-
-  float qf[8];
-  unpack8(*reinterpret_cast<const uint4*>(q + (long long)bh * ATT_D + l16 * 8), qf);
-  const float scale = 0.08838834764831845f;         // 1/sqrt(128)
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qf[i] *= scale;
-
-  const bf16* kb = kc + (long long)bh * cap * ATT_D + l16 * 8;
-  const bf16* vb = vc + (long long)bh * cap * ATT_D + l16 * 8;
-  float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-  constexpr int U = 4;                              // keys in flight per half-warp
-  for (int base = s0; base < s1; base += 8 * U) {   // warp-uniform trip count (shuffles inside)
-    const int s = base + hw * U;
-    uint4 kr[U], vr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ss = s + u < s1 ? s + u : s1 - 1;
-      kr[u] = *reinterpret_cast<const uint4*>(kb + (long long)ss * ATT_D);
-      vr[u] = *reinterpret_cast<const uint4*>(vb + (long long)ss * ATT_D);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float kf[8];
-      unpack8(kr[u], kf);
-      float d = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
-      d += __shfl_xor_sync(0xffffffffu, d, 8);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (s + u < s1) {
-        const float mn = fmaxf(m, d);
-        const float corr = __expf(m - mn), p = __expf(d - mn);
-        float vf[8];
-        unpack8(vr[u], vf);
-        l = l * corr + p;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i] * corr);
-        m = mn;
-      }
-    }
-  }
-  // merge the 8 half-warps of the CTA
-  __shared__ float sm_m[8], sm_l[8], sm_acc[8][ATT_D];
-  if (l16 == 0) { sm_m[hw] = m; sm_l[hw] = l; }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sm_acc[hw][l16 * 8 + i] = acc[i];
-  __syncthreads();
-  if (tid < ATT_D) {
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - M);
-      L += sm_l[w] * c;
-      A += sm_acc[w][tid] * c;
-    }
-    float* o = part + ((long long)bh * nsplit + split) * (ATT_D + 2);
-    o[tid] = A;
-    if (tid == 0) { o[ATT_D] = M; o[ATT_D + 1] = L; }
-  }
-}
-
-static __global__ void __launch_bounds__(ATT_D) attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out,
-                                                             int nsplit) {
-  pdl_trigger();
-  const int bh = blockIdx.x, d = threadIdx.x;
-  const float* p = part + (long long)bh * nsplit * (ATT_D + 2);
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, p[s * (ATT_D + 2) + ATT_D]);
-  float L = 0.f, A = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float ms = p[s * (ATT_D + 2) + ATT_D];
-    const float c = ms == -INFINITY ? 0.f : __expf(ms - M);
-    L += p[s * (ATT_D + 2) + ATT_D + 1] * c;
-    A += p[s * (ATT_D + 2) + d] * c;
-  }
-  out[(long long)bh * ATT_D + d] = f2bf(L > 0.f ? A / L : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -815,6 +707,8 @@ static __global__ void __launch_bounds__(ATT_THREADS) attn_step_q8_kernel(const 
   a.out[(long long)bh * ATT_D + tid] = f2bf(LL > 0.f ? AA / LL : 0.f);
 }
 
+constexpr int DEP_MAX_Q = 16;              // dep_q of the largest family member (configs/moshi_dev_2b.json)
+
 // Depformer attention step: the new key/value of sub-step `step` is appended to the per-frame cache and the query
 // attends over step + 1 keys; no positional embedding (depformer_pos_emb = "none").  One warp per (b, h), D = 64.
 static __global__ void dep_attn_step_kernel(const bf16* __restrict__ qkv /*[B][3*H*D]*/, bf16* __restrict__ kc,
@@ -832,7 +726,7 @@ static __global__ void dep_attn_step_kernel(const bf16* __restrict__ qkv /*[B][3
   __syncwarp();
   const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base));
   const float scale = 0.125f;                       // 1/sqrt(64)
-  float sc[8];
+  float sc[DEP_MAX_Q];
   float mx = -INFINITY;
   const int n_keys = step + 1;
   for (int j = 0; j < n_keys; ++j) {
@@ -853,48 +747,18 @@ static __global__ void dep_attn_step_kernel(const bf16* __restrict__ qkv /*[B][3
   *reinterpret_cast<__nv_bfloat162*>(out + (long long)warp * D + 2 * lane) = __floats2bfloat162_rn(a0, a1);
 }
 
-// Depformer attention: <= 8 keys, one warp per (b, h), D = 64 (2 dims per lane).
-static __global__ void dep_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
-                                bf16* __restrict__ out, int B, int H, int D, int cap, int n_keys) {
-  pdl_trigger();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * H) return;
-  const float scale = rsqrtf((float)D);
-  float sc[8];
-  float mx = -INFINITY;
-  for (int j = 0; j < n_keys; ++j) {
-    float d = 0.f;
-    for (int c = lane * 2; c < D; c += 64) {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + (long long)warp * D + c));
-      const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kc + ((long long)warp * cap + j) * D + c));
-      d += a.x * kk.x + a.y * kk.y;
-    }
-    d = warp_sum(d) * scale;
-    sc[j] = d;
-    mx = fmaxf(mx, d);
-  }
-  float sum = 0.f;
-  for (int j = 0; j < n_keys; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-  const float inv = 1.f / sum;
-  for (int c = lane * 2; c < D; c += 64) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < n_keys; ++j) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vc + ((long long)warp * cap + j) * D + c));
-      a0 = fmaf(sc[j] * inv, v.x, a0);
-      a1 = fmaf(sc[j] * inv, v.y, a1);
-    }
-    *reinterpret_cast<__nv_bfloat162*>(out + (long long)warp * D + c) = __floats2bfloat162_rn(a0, a1);
-  }
-}
-
 // _LMGenState.reset / _MHAState.reset / RingKVCache.reset / State.reset for the rows in `mask` (null = all)
-static __global__ void lm_reset_kernel(long long* offsets, long long* pos, uint8_t* exec_mask, const uint8_t* mask, int B) {
+// (with CFG the model rows b and B + b are reset together, lm.py:653-656)
+static __global__ void lm_reset_kernel(long long* offsets, long long* pos, uint8_t* exec_mask, uint8_t* exec_mask_m, const uint8_t* mask,
+                                int B, int cfg) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (mask != nullptr && !mask[b]) return;
   offsets[b] = 0;
   pos[b] = 0;
   exec_mask[b] = 1;
+  exec_mask_m[b] = 1;
+  if (cfg) { pos[B + b] = 0; exec_mask_m[B + b] = 1; }
 }
 
 // depformer_replace_tokens [B][dep_q] -> this frame's audio tokens [dep_q][B] (lm.py:751-755)

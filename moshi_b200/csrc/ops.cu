@@ -1,5 +1,5 @@
 // Kernel-level C entry points used by the parity tests (same kernels the handles launch).
-#include "gemm_tc.cuh"
+#include "gemm_sk.cuh"
 #include "lm_kernels.cuh"
 #include "mimi_kernels.cuh"
 
@@ -7,22 +7,35 @@ using namespace b200;
 
 extern "C" {
 
-int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K, int impl, void* stream) {
-  using namespace b200::lm;
-  if (!x_dev || !w_dev || !y_dev || M < 1 || N < 1 || K < 8 || K % 8) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: bad shape");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bf16* x = static_cast<const bf16*>(x_dev);
-  const bf16* w = static_cast<const bf16*>(w_dev);
-  bf16* y = static_cast<bf16*>(y_dev);
-  if (impl == 0) impl = tc::auto_pick(M, N, K, LIN_STORE);
-  if (impl == 2) {
-    static tc::GemmPlanCache cache;
-    if (!tc::supported(M, N, K, LIN_STORE)) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: shape unsupported by the tcgen05 kernel");
-    return tc::linear(cache, x, K, w, y, N, nullptr, 0, M, N, K, LIN_STORE, 0, st);
+static int sk_scratch(float** ws, int** counters) {
+  static float* g_ws = nullptr;
+  static int* g_counters = nullptr;
+  if (!g_ws) {
+    B200_CUDA(cudaMalloc(&g_ws, tc::sk_workspace_bytes(256)));
+    B200_CUDA(cudaMalloc(&g_counters, tc::SK_MAX_TILES * sizeof(int)));
+    B200_CUDA(cudaMemset(g_counters, 0, tc::SK_MAX_TILES * sizeof(int)));
   }
-  auto k = linear_simt_kernel<LIN_STORE>;
-  B200_LAUNCH(k, ceil_div(N * 32, 256), 256, 0, st, x, (long long)K, w, y, (long long)N, (const bf16*)nullptr, 0LL, M, N, K, 0);
-  return check_launch("op_linear_bf16");
+  *ws = g_ws; *counters = g_counters;
+  return B200_OK;
+}
+
+int b200_op_linear_bf16(const void* x_dev, const void* w_dev, void* y_dev, int M, int N, int K, void* stream) {
+  if (!x_dev || !w_dev || !y_dev || M < 1 || N < 1 || K < 8 || K % 8) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: bad shape");
+  if (!tc::sk_supported(M, N, K, 0)) B200_FAIL(B200_ERR_SHAPE, "op_linear_bf16: unsupported shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static tc::GemmPlanCache cache;
+  float* ws = nullptr; int* counters = nullptr;
+  B200_TRY(sk_scratch(&ws, &counters));
+  void* tiles = nullptr;
+  B200_CUDA(cudaMalloc(&tiles, tc::sk_packed_bytes(N, K, 0, 0)));
+  int rc = tc::sk_pack_weights(static_cast<const __nv_bfloat16*>(w_dev), tiles, N, K, 0, 0, st);
+  tc::SkTuning t;
+  if (rc == B200_OK)
+    rc = tc::sk_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, tiles, static_cast<__nv_bfloat16*>(y_dev), N, nullptr, 0,
+                       M, N, K, 0, 0, ws, counters, t, st);
+  cudaStreamSynchronize(st);
+  cudaFree(tiles);
+  return rc;
 }
 
 int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows) { return (int64_t)tc::sk_packed_bytes(N, K, epi, gate_rows); }
@@ -38,13 +51,8 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
   if (!x_dev || !w_tiles_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_sk: null pointer");
   if (!tc::sk_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_sk: unsupported shape");
   static tc::GemmPlanCache cache;
-  static float* ws = nullptr;
-  static int* counters = nullptr;
-  if (!ws) {
-    B200_CUDA(cudaMalloc(&ws, tc::sk_workspace_bytes(256)));
-    B200_CUDA(cudaMalloc(&counters, tc::SK_MAX_TILES * sizeof(int)));
-    B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
-  }
+  float* ws = nullptr; int* counters = nullptr;
+  B200_TRY(sk_scratch(&ws, &counters));
   tc::SkTuning t;
   // grid > 0: stream-K with that many CTAs; grid < 0: cluster split-K with |grid| CTAs per tile; 0: the LM's own choice
   t.grid = grid > 0 ? grid : 0; t.cluster = grid < 0 ? -grid : 0; t.smem_budget = smem_budget; t.stream_only = stream_only;
@@ -76,13 +84,8 @@ int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_til
   if (!xq_dev || !sa_dev || !w_tiles_dev || !sw_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_i8: null pointer");
   if (!tc::sk_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_i8: unsupported shape");
   static tc::GemmPlanCache cache;
-  static float* ws = nullptr;
-  static int* counters = nullptr;
-  if (!ws) {
-    B200_CUDA(cudaMalloc(&ws, tc::sk_workspace_bytes(256)));      // int32 partials of cut tiles, like the bf16 path
-    B200_CUDA(cudaMalloc(&counters, tc::SK_MAX_TILES * sizeof(int)));
-    B200_CUDA(cudaMemset(counters, 0, tc::SK_MAX_TILES * sizeof(int)));
-  }
+  float* ws = nullptr; int* counters = nullptr;
+  B200_TRY(sk_scratch(&ws, &counters));      // int32 partials of cut tiles share the bf16 path's workspace
   tc::SkTuning t;
   t.xq = xq_dev; t.sa = sa_dev; t.sw = sw_dev;
   const int out_cols = epi == 2 ? gate_rows : N;
@@ -160,29 +163,6 @@ int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_d
   cudaFree(scratch);
   cudaFree(desc);
   return check_launch("op_convtr1d");
-}
-
-int b200_op_attn_decode(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev,
-                        const int64_t* offsets_dev, const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit,
-                        void* stream) {
-  using namespace b200::lm;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (B < 1 || H < 1 || cap < 1) B200_FAIL(B200_ERR_SHAPE, "op_attn_decode: bad shape");
-  if (nsplit <= 0) nsplit = attn_pick_splits(B, H, cap);
-  static float* part = nullptr;
-  static size_t part_n = 0;
-  const size_t need = (size_t)B * H * nsplit * (ATT_D + 2);
-  if (need > part_n) {
-    if (part) cudaFree(part);
-    B200_CUDA(cudaMalloc(&part, need * sizeof(float)));
-    part_n = need;
-  }
-  dim3 grid(B * H, nsplit);
-  B200_LAUNCH(attn_decode_kernel, grid, ATT_THREADS, 0, st, static_cast<const bf16*>(q_dev), static_cast<const bf16*>(k_dev),
-              static_cast<const bf16*>(v_dev), part, reinterpret_cast<const long long*>(offsets_dev), exec_mask_dev, H, cap,
-              nsplit);
-  B200_LAUNCH(attn_combine_kernel, B * H, ATT_D, 0, st, part, static_cast<bf16*>(out_dev), nsplit);
-  return check_launch("op_attn_decode");
 }
 
 int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_dev, const int64_t* pos_dev,

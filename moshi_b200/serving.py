@@ -96,6 +96,17 @@ class DialogueService:
         self.frame_size = mimi.frame_size
         self.tokens_per_slot = lm.dep_q + 1
 
+    def read_buffer(self, name: str, dtype: torch.dtype, shape: tuple) -> torch.Tensor:
+        """Hand-off of the last frame (``b200_frame_read_buffer``): "codes_in", "tokens", "codes_out", "exec", "decoder_exec"."""
+        import ctypes as C
+
+        from . import _lib
+        out = torch.empty(shape, dtype=dtype, device=self.lm.device)
+        n = C.c_int64()
+        _lib.check(self._lib.b200_frame_read_buffer(self._h, name.encode(), _lib.ptr(out), out.numel() * out.element_size(), C.byref(n)))
+        assert n.value == out.numel() * out.element_size(), (name, n.value, shape)
+        return out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.b200_frame_destroy(self._h)
@@ -138,8 +149,7 @@ class DialogueService:
         noise_host = noise_dev = C.c_void_p(0)
         keep = None
         if noise is None:
-            keep = self.lm_gen.draw_noise()
-            noise_dev = _lib.ptr(keep)
+            pass                      # both NULL: the LM step draws its Exp(1) noise itself, inside its CUDA graph
         elif isinstance(noise, np.ndarray):
             noise_host = self._np_ptr(noise, np.float32, B * self._lib.b200_lm_noise_per_row(self.lm._h), "noise")
         else:

@@ -177,6 +177,16 @@ def lm_tensor_specs(cfg: LMConfig) -> list[tuple[str, tuple[int, ...], float]]:
         specs.append((p + ".norm2.alpha", (1, 1, d), 0))
         specs.append((p + ".gating.linear_in.weight", (2 * h, d), d))
         specs.append((p + ".gating.linear_out.weight", (d, h), h))
+    for i in range(cfg.extra_heads_num_heads):                       # lm.py:224-226
+        specs.append((f"extra_heads.{i}.weight", (cfg.extra_heads_dim, d), d))
+    for name, c in (cfg.conditioners or {}).items():                 # conditioners/text.py:106-134, base.py:105-129
+        lut = c["lut"]
+        p = f"condition_provider.conditioners.{name}"
+        specs.append((p + ".embed.weight", (lut["n_bins"] + 1, lut["dim"]), 3.0))
+        specs.append((p + ".output_proj.weight", (d, lut["dim"]), lut["dim"]))
+        specs.append((p + ".learnt_padding", (1, 1, d), 75.0))
+    if cfg.dep_q == 0:                                               # lm.py:219-222: no depformer at all
+        return specs
     for k in range(cfg.dep_q):
         specs.append((f"depformer_in.{k}.weight", (dd, d), d))
     for k in range(cfg.dep_q - 1):
@@ -217,3 +227,40 @@ def iter_synth_lm_tensors(cfg: LMConfig, seed: int = 4242, device: str | torch.d
 def synth_lm_state_dict(cfg: LMConfig, seed: int = 4242, device: str | torch.device = "cpu",
                         dtype: torch.dtype = torch.bfloat16) -> dict[str, torch.Tensor]:
     return dict(iter_synth_lm_tensors(cfg, seed, device, dtype))
+
+
+def tiled_lm_state_dict(cfg: LMConfig, seed: int = 7, block_elems: int = 1 << 25) -> dict[str, torch.Tensor]:
+    """A full-size (7.7 B parameter) bf16 checkpoint on the CPU in seconds: every tensor is cut from one seeded random block
+    of ``block_elems`` values, scaled like ``iter_synth_lm_tensors`` scales it (uniform with the variance of the reference's
+    init, lm_utils.py:44-56; output projections halved so that the bf16 residual stream stays O(1) over 32 layers).  Drawing 7.7 G
+    independent values on the CPU takes minutes; parity and timing only need realistic, seed-reproducible values.  The same
+    dict loads into the CPU oracle and into ``LMModel`` (bench.py's CPU arm, tests/test_gpu_zt_7b_parity.py)."""
+    g = torch.Generator().manual_seed(seed)
+    unit = (2 * torch.rand(block_elems, generator=g) - 1)              # uniform(-1, 1), fp32
+    cache: dict[float, torch.Tensor] = {}
+    sd: dict[str, torch.Tensor] = {}
+    start = 0
+    for key, shape, fan_in in lm_tensor_specs(cfg):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        if fan_in == 0:
+            sd[key] = (1.0 + 0.1 * unit[:n]).to(torch.bfloat16).view(shape)
+            continue
+        bound = math.sqrt(3.0 / fan_in)
+        if ".out_projs." in key or "linear_out" in key:
+            bound *= 0.5
+        blk = cache.get(bound)
+        if blk is None:
+            blk = cache[bound] = (unit * bound).to(torch.bfloat16)
+        t = torch.empty(n, dtype=torch.bfloat16)
+        # successive tensors start at different offsets of the block, so that equal-shaped tensors (the 32 layers) differ
+        o = 0
+        while o < n:
+            m = min(block_elems - start, n - o)
+            t[o:o + m] = blk[start:start + m]
+            o += m
+            start = (start + m) % block_elems
+        start = (start + 9973) % block_elems
+        sd[key] = t.view(shape)
+    return sd

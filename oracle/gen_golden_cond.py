@@ -45,7 +45,9 @@ def main() -> None:
     assert not res.unexpected_keys and all(k.startswith("condition_provider.") for k in res.missing_keys)
     B, steps = scenarios.CFG_B, scenarios.CFG_STEPS
     codes = scenarios.lm_input_codes(cfg, B, steps, seed=scenarios.CFG_SEED)
-    tensors, info = {}, {"generated_by": "oracle/gen_golden_cond.py", "torch": torch.__version__, "B": B, "steps": steps,
+    # the conditioner's weights, under the checkpoint key names, so that moshi_b200.conditioners can be pinned on them
+    cond_sd = {k: v.detach().clone() for k, v in ref.state_dict().items() if k.startswith("condition_provider.")}
+    tensors, info = dict(cond_sd), {"generated_by": "oracle/gen_golden_cond.py", "torch": torch.__version__, "B": B, "steps": steps,
                          "none_marker": -3, "modes": {}}
     for name, cfg_coef in (("sum", 1.0), ("sum_cfg", 2.0)):
         conds = [ConditionAttributes(text={"description": "very_good"}, tensor={})] * B
@@ -65,6 +67,8 @@ def main() -> None:
                 agree &= a is None or bool((a == b).all())
         tensors[name + ".tokens"] = torch.stack(outs)
         tensors[name + ".condition_sum"] = csum.contiguous()
+        tensors[name + ".condition"] = ct["description"].condition.contiguous()          # fp32 [rows, 1, dim]
+        tensors[name + ".mask"] = ct["description"].mask.to(torch.uint8).contiguous()
         info["modes"][name] = {"oracle_bit_exact_tokens": agree, "cfg_coef": cfg_coef}
     golden = ROOT / "tests" / "golden"
     save_file(tensors, golden / "lm_tiny_cond.safetensors")

@@ -34,9 +34,26 @@ def quantize_weight(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return quantize_rows(w.to(torch.float16).float())
 
 
+# QLinear quantises its weight once, at construction (quantize.py:16-21): cache per weight tensor so that stepping a large
+# model does not re-quantise billions of weights every frame.  Keyed by storage address + shape; clear_cache() drops it.
+_QCACHE: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def clear_cache() -> None:
+    _QCACHE.clear()
+
+
+def cached_quantize_weight(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    key = (w.data_ptr(), tuple(w.shape), w.dtype)
+    hit = _QCACHE.get(key)
+    if hit is None:
+        hit = _QCACHE[key] = quantize_weight(w)
+    return hit
+
+
 def qlinear_f32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """Dequantised product in fp32 (before the caller's bf16 rounding): [..., K] x [N, K] -> [..., N]."""
-    qw, sw = quantize_weight(w)
+    qw, sw = cached_quantize_weight(w)
     lead = x.shape[:-1]
     qx, sa = quantize_rows(x.reshape(-1, x.shape[-1]))
     acc = qx.double() @ qw.double().t()                       # exact integers (|acc| < 2^31)

@@ -154,3 +154,20 @@ CFG_MODES = {
     "masked_until": dict(cfg_coef=1.5, cfg_is_masked_until=[3, 6]),
     "both": dict(cfg_coef=3.0, cfg_is_no_text=True, cfg_is_masked_until=[2, 2]),
 }
+
+
+# ---- sampling on peaked distributions (what a trained model produces): text / audio heads of the tiny LM scaled up ----------
+PEAK_GAIN = 4.0
+
+
+def peaked_state_dict(cfg, seed: int = LM_SEED) -> dict:
+    """The tiny LM's seeded weights with ``text_linear`` and ``linears.*`` multiplied by PEAK_GAIN: logits of std ~4 instead
+    of ~1, so that a few candidates carry the probability mass and a sampled token is decided by them rather than by the
+    order of 250 near-tied candidates (random-init heads give near-uniform distributions, where the rank-indexed noise of
+    sampling.py:62-64 is re-dealt by any one-ulp swap)."""
+    from moshi_b200.synth import synth_lm_state_dict
+    sd = synth_lm_state_dict(cfg, seed=seed)
+    for k in list(sd):
+        if k == "text_linear.weight" or k.startswith("linears."):
+            sd[k] = (sd[k].float() * PEAK_GAIN).bfloat16()
+    return sd

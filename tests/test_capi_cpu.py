@@ -34,7 +34,7 @@ def test_header_and_library_agree(built):
 def test_library_reports_version_and_errors_without_gpu(built):
     from moshi_b200 import _lib
     lib = _lib.lib()
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == _lib.ABI_VERSION == 2
     assert lib.b200_launch_count() == 0
     cfg = _lib.MimiConfigC()          # all zero: invalid
     h = C.c_void_p()

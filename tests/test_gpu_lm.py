@@ -404,3 +404,84 @@ def test_one_and_two_sessions_take_the_gemv_path(lm, tiny, B):
     print(f"B={B} (GEMV path): worst logit diff {worst:.3e}, greedy tokens equal {agree}/{total}")
     assert worst < LOGIT_ATOL
     assert agree / total > 0.95
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sampled_tokens_margin_aware_on_peaked_distributions(golden_dir, use_graph):
+    """north_star: "sampled token ids under a fixed seed".  On peaked output distributions (scenarios.peaked_state_dict: what a
+    trained model produces) every sampler decision is compared with the oracle's, fed the same Exp(1) draws: the ids must be
+    EQUAL unless the decision is provably unstable under the logit difference actually observed for that row
+    (tests/util.sample_is_stable: candidates closer than twice that difference may swap ranks and thereby noise values, scores
+    move by at most 2 * diff / temp).  Rows that stay on the reference's trajectory must reproduce the tokens the unmodified
+    reference sampled with torch's seeded CPU generator (tests/golden/lm_tiny_sampled_peaked.safetensors)."""
+    from moshi_b200.models import LMGen, LMModel
+    from tests.util import sample_is_stable
+    cfg = tiny_lm_config()
+    sd = scenarios.peaked_state_dict(cfg)
+    gold = load_file(golden_dir / "lm_tiny_sampled_peaked.safetensors")["tokens"]
+    lm = LMModel(cfg, sd, device="cuda")
+    B, steps = scenarios.LM_B, scenarios.LM_STEPS
+    codes = scenarios.lm_input_codes(cfg, B, steps)
+    gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
+    gen.use_graph = use_graph
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=True, tie_break="index")
+    orc.streaming(B)
+    torch.manual_seed(scenarios.LM_NOISE_SEED)
+    diverged = torch.zeros(B, dtype=torch.bool)
+    decisions = stable = equal = unexcused = 0
+    gold_match = gold_total = 0
+    worst = 0.0
+    with gen.streaming(B):
+        for i in range(steps):
+            scenarios.lm_mask_events(gen, i, B)
+            scenarios.lm_mask_events(orc, i, B)
+            nt, na = scenarios.lm_noise(cfg, B)
+            dbg = {}
+            want = orc.step(codes[i], nt, na, debug=dbg)
+            got = gen.step(codes[i].cuda(), noise=gen.pack_noise(nt, na))
+            assert (want is None) == (got is None), i
+            live = orc.exec_mask.clone()
+            tl = gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).float().cpu()
+            dl = gen.read_buffer("dep_logits", torch.bfloat16, (cfg.dep_q, B, cfg.card)).float().cpu()
+            tt = gen.read_buffer("text_token", torch.int64, (B,)).cpu()
+            at = gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()
+            # sampler by sampler, while the row's inputs to that sampler are identical on both sides
+            same = live.clone()
+            chain = [(tl, dbg["text_logits"].float()[:, 0, 0], 0.7, 25, nt, tt, dbg["text_token"])]
+            for k in range(cfg.dep_q):
+                chain.append((dl[k], dbg["dep_logits"][k].float()[:, 0, 0], 0.8, 250, na[k], at[k], dbg["audio_tokens"][:, k]))
+            for lg, lo, temp, topk, nz, tok_g, tok_o in chain:
+                for b in range(B):
+                    if not same[b]:
+                        continue
+                    d = float((lg[b] - lo[b]).abs().max())
+                    worst = max(worst, d)
+                    ok = bool(sample_is_stable(lo[b:b + 1], temp, topk, nz[b:b + 1], d + 1e-6)[0])
+                    decisions += 1
+                    stable += int(ok)
+                    if tok_g[b] == tok_o[b]:
+                        equal += 1
+                    else:
+                        same[b] = False
+                        unexcused += int(ok)
+            if i == 20:
+                diverged[1] = False
+            diverged |= live & ((tt != dbg["text_token"]) | (at.t() != dbg["audio_tokens"]).any(dim=1))
+            if got is not None:
+                sel = live & ~diverged
+                okg = (got.cpu() == gold[i])[sel]
+                gold_match += int(okg.sum())
+                gold_total += okg.numel()
+            pos = (orc.offsets % orc.cache.shape[2])
+            for b in range(B):
+                if live[b]:
+                    orc.cache[b, 0, pos[b]] = tt[b]
+                    orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
+    print(f"peaked sampling (graph={use_graph}): {decisions} sampler decisions compared, {stable} provably stable under the observed "
+          f"logit difference, {equal} equal, {unexcused} unexcused mismatches; reference fixture {gold_match}/{gold_total}; "
+          f"worst logit diff {worst:.3e}")
+    assert unexcused == 0
+    assert stable > 0.4 * decisions            # the gate is not vacuous
+    assert equal > 0.9 * decisions
+    assert worst < 4 * LOGIT_ATOL              # logits are 4x larger than in the default scenario (bf16 ulp 0.06-0.125 at |x| 8-32)
+    assert gold_total > 0 and gold_match == gold_total

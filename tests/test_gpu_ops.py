@@ -21,22 +21,20 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize("impl", [1])
 @pytest.mark.parametrize("M,N,K", [(1, 512, 256), (3, 1024, 4096), (8, 12288, 4096), (17, 4096, 11264),
-                                   (96, 4096, 4096), (128, 2048, 1024), (200, 1024, 2816)])
-def test_linear_bf16(lib, impl, M, N, K):
+                                   (96, 4096, 4096), (128, 2048, 1024), (200, 1024, 2816), (5, 200, 72)])
+def test_linear_bf16(lib, M, N, K):
+    """The LM's linear on row-major weights (packed on the fly): GEMV kernel at M <= 2, tcgen05 kernels above."""
     from moshi_b200 import _lib
     g = torch.Generator().manual_seed(M * 7 + N)
     x = torch.randn(M, K, generator=g).bfloat16().cuda()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
-    y = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    rc = lib.b200_op_linear_bf16(cptr(x), cptr(w), cptr(y), M, N, K, impl, _stream())
-    if impl == 2 and rc != 0:
-        pytest.skip("tcgen05 path does not cover this shape: " + lib.b200_last_error().decode())
-    _lib.check(rc)
+    y = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.b200_op_linear_bf16(cptr(x), cptr(w), cptr(y), M, N, K, _stream()))
     torch.cuda.synchronize()
     want = (x.float() @ w.float().t())
-    print(stats(f"linear impl={impl} {M}x{N}x{K}", y, want))
+    print(stats(f"linear {M}x{N}x{K}", y, want))
+    assert not torch.isnan(y.float()).any()
     # bf16 output rounding: half an ulp of the result plus fp32 accumulation-order noise
     torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=2e-2)
     # exactness up to one bf16 ulp for almost all entries
@@ -113,28 +111,6 @@ def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
     got = torch.cat(outs, -1)
     print(stats(f"convtr {cin}->{cout} s{stride}", got, want))
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
-
-
-@pytest.mark.parametrize("B,H,cap,nsplit", [(1, 32, 3000, 0), (5, 4, 3000, 1), (3, 2, 12, 0), (7, 8, 250, 3), (2, 32, 3000, 16)])
-def test_ring_attention_decode(lib, B, H, cap, nsplit):
-    """Attention over the valid part of the ring == masked SDPA over the whole ring (transformer.py:574-585)."""
-    from moshi_b200 import _lib
-    g = torch.Generator().manual_seed(B * 100 + cap)
-    q = torch.randn(B, H, 128, generator=g).bfloat16().cuda()
-    k = torch.randn(B, H, cap, 128, generator=g).bfloat16().cuda()
-    v = torch.randn(B, H, cap, 128, generator=g).bfloat16().cuda()
-    offs = torch.tensor([0, 1, cap - 1, cap, 3 * cap + 5, 17, cap // 2][:B], dtype=torch.int64)
-    n_valid = (offs + 1).clamp(max=cap)
-    out = torch.empty(B, H, 128, dtype=torch.bfloat16, device="cuda")
-    mask = torch.ones(B, dtype=torch.bool, device="cuda")
-    offs_d = offs.cuda()
-    _lib.check(lib.b200_op_attn_decode(cptr(q), cptr(k), cptr(v), cptr(out), cptr(offs_d), cptr(mask), B, H, cap, nsplit,
-                                       _stream()))
-    torch.cuda.synchronize()
-    allowed = (torch.arange(cap)[None, :] < n_valid[:, None]).cuda()
-    want = F.scaled_dot_product_attention(q.float()[:, :, None], k.float(), v.float(), allowed[:, None, None, :])[:, :, 0]
-    print(stats(f"attn B={B} H={H} cap={cap} nsplit={nsplit}", out, want))
-    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
 
 
 def _rope_ref(x: torch.Tensor, pos: torch.Tensor, max_period: float = 10000.0) -> torch.Tensor:

@@ -32,8 +32,25 @@ def test_lm_config_rejects_options_outside_hot_path():
     LMConfig.from_dict(d)
     with pytest.raises(ValueError):
         LMConfig.from_dict({**d, "norm": "layer_norm"})
+    with pytest.raises(ValueError):                    # only LUT conditioners fused by sum are on the step path
+        LMConfig.from_dict({**d, "conditioners": {"speaker": {"type": "tensor", "tensor": {"dim": 512}}}})
     with pytest.raises(ValueError):
-        LMConfig.from_dict({**d, "conditioners": {}})
+        LMConfig.from_dict({**d, "fuser": {"cross": ["description"]}})
+    with pytest.raises(ValueError):                    # options that used to load silently
+        LMConfig.from_dict({**d, "causal": False})
+    with pytest.raises(ValueError):
+        LMConfig.from_dict({**d, "depformer_context": 4})
+    import json
+    from pathlib import Path
+    ref = Path("/root/reference/configs/moshi_dev_2b.json")
+    two_b = json.loads(ref.read_text()) if ref.exists() else {
+        **d, "dim": 2560, "n_q": 32, "dep_q": 16, "num_heads": 20, "num_layers": 24, "depformer_context": 16,
+        "delays": [0, 0] + [2] * 15 + [0] + [2] * 15,
+        "conditioners": {"description": {"type": "lut", "lut": {"n_bins": 31, "dim": 16, "tokenizer": "noop"}}},
+        "fuser": {"sum": ["description"]}}
+    c2 = LMConfig.from_dict(two_b)                     # configs/moshi_dev_2b.json is inside the family now
+    assert (c2.n_q, c2.dep_q, c2.max_delay) == (32, 16, 2) and "description" in c2.conditioners
+    assert "conditioners" not in c2.to_reference_kwargs()
 
 
 def test_mimi_config_roundtrip_and_layout():
@@ -43,10 +60,13 @@ def test_mimi_config_roundtrip_and_layout():
     enc, dec = seanet_layout(cfg)
     assert [l[1] for l in enc if l[0] == "conv"] == [0, 3, 6, 9, 12, 14]
     assert [l[1] for l in dec if l[0] == "convtr"] == [2, 5, 8, 11]
-    with pytest.raises(ValueError):
+    for section, key, value in (("seanet", "pad_mode", "reflect"), ("seanet", "activation", "ReLU"), ("seanet", "causal", False),
+                                ("seanet", "disable_norm_outer_blocks", 1), ("transformer", "causal", False),
+                                ("transformer", "conv_layout", False)):
         bad = cfg.to_reference_dict()
-        bad["seanet"]["pad_mode"] = "reflect"
-        MimiConfig.from_reference_dict(bad)
+        bad[section][key] = value
+        with pytest.raises(ValueError):
+            MimiConfig.from_reference_dict(bad)
 
 
 def test_synth_checkpoints_have_reference_keys():

@@ -41,3 +41,49 @@ def rvq_mismatches(codes_got: torch.Tensor, codes_want: torch.Tensor, margins: t
 
 def cptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def greedy_unexcused(got: torch.Tensor, want: torch.Tensor, logits_oracle: torch.Tensor, tol: float) -> tuple[int, int]:
+    """Margin-aware comparison of greedy ids ([N] each) against the oracle's fp32-viewed logits ([N, card]): a mismatch is
+    excused iff the oracle's own top-2 logit gap is below ``2 * tol`` (two logits that each moved by <= tol can swap).
+    Returns (n_mismatch, n_unexcused)."""
+    top2 = logits_oracle.float().topk(2, dim=-1).values
+    gap = top2[:, 0] - top2[:, 1]
+    bad = got.cpu() != want.cpu()
+    return int(bad.sum()), int((bad & (gap > 2 * tol)).sum())
+
+
+def sample_is_stable(logits: torch.Tensor, temp: float, top_k: int, noise: torch.Tensor, tol: float) -> torch.Tensor:
+    """For every row of oracle logits ([N, card], fp32 view of the bf16 tensor) with its Exp(1) noise ([N, k]): is the
+    sampled token (sampling.py:86-106: softmax(l / temp) -> top-k -> argmax(p / q), noise indexed by RANK) the same for
+    every logit vector within ``tol`` (max-norm) of this one?  Conservative test:
+      * a candidate's log-probability moves by at most 2 * tol / temp (its logit and the normaliser);
+      * candidates whose logits lie in one run of the sorted order with adjacent gaps < 2 * tol can exchange ranks, i.e. any
+        of them can receive any noise value of that run (this also covers exact ties, whose torch.topk order is unspecified,
+        and candidates that can cross the top-k boundary).
+    Stable iff the winner's worst-case score exceeds every other candidate's best-case score.  Returns bool [N]."""
+    logits = logits.float().cpu()
+    noise = noise.float().cpu()
+    N, card = logits.shape
+    k = min(top_k, card)
+    out = torch.zeros(N, dtype=torch.bool)
+    for n in range(N):
+        srt, _ = torch.sort(logits[n], descending=True, stable=True)
+        logp = torch.log_softmax(srt / temp, dim=-1)
+        q = torch.cat([noise[n, :k], torch.full((card - k,), float("inf"))])     # ranks beyond k never win
+        score = logp[:k] - torch.log(noise[n, :k])
+        w = int(score.argmax())
+        # runs of the sorted order whose adjacent gaps are all < 2 * tol
+        brk = torch.cat([torch.tensor([True]), (srt[:-1] - srt[1:]) >= 2 * tol])
+        run_id = torch.cumsum(brk.int(), 0) - 1
+        n_runs = int(run_id[-1]) + 1
+        qmin = torch.full((n_runs,), float("inf")).scatter_reduce(0, run_id, q, reduce="amin")
+        qmax = torch.full((n_runs,), 0.0).scatter_reduce(0, run_id, q, reduce="amax")
+        slack = 2 * tol / temp
+        best_case = logp + slack - torch.log(qmin[run_id])          # every candidate, with the smallest noise it could be dealt
+        worst_w = logp[w] - slack - torch.log(qmax[run_id[w]])      # the winner, with the largest noise it could be dealt
+        best_case[w] = -float("inf")
+        if int((run_id == run_id[w]).sum()) > 1:                    # the winner itself can be re-ranked: not stable
+            continue
+        out[n] = bool(worst_w > best_case.max())
+    return out

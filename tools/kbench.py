@@ -78,17 +78,16 @@ def bench_gemm(lib, Ms, legacy=True, only=""):
                 gbs = alg / ms / 1e6
                 print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": vname, "ms": round(ms, 4),
                                   "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
-            if not legacy or epi != 0:
+            if not legacy:
                 continue
-            for impl in (1, 2):
-                if impl == 1 and M > 1:
-                    continue
-                def fn(i):
-                    _lib.check(lib.b200_op_linear_bf16(_lib.ptr(x), _lib.ptr(ws[i]), _lib.ptr(y), M, N, K, impl, stream()))
-                ms = time_ms(fn, n_rot)
-                gbs = alg / ms / 1e6
-                print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": impl, "ms": round(ms, 4),
-                                  "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
+            # same-box library row: cuBLAS through torch.matmul on the row-major weights (the reference's path for every
+            # nn.Linear); GEMM only, i.e. without the residual add / gated SiLU our kernels fuse
+            def fn(i):
+                torch.matmul(x, ws[i].t())
+            ms = time_ms(fn, n_rot)
+            gbs = alg / ms / 1e6
+            print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": "cublas(torch.matmul)", "ms": round(ms, 4),
+                              "GBps": round(gbs, 1), "frac": round(gbs / PEAK, 3)}), flush=True)
         del ws, pk
 
 
