@@ -124,6 +124,19 @@ int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codeboo
 int64_t b200_mimi_state_bytes(b200_mimi* h);
 int b200_mimi_get_state(b200_mimi* h, void* dst_dev, int64_t capacity);
 int b200_mimi_set_state(b200_mimi* h, const void* src_dev, int64_t nbytes);
+/* The same state entry by entry (b200_lm_state_* has the conventions).  Names: "exec_mask" u8 [B]; per SEANet layer
+ * "<encoder|decoder>.model.<i>....ext_hi" / ".ext_lo" f32 [B, P + T, Cin]: the layer's extended input, token-major, whose first P
+ * rows are StreamingConv1d's `previous` (conv.py:161-169; value = hi + lo; P = 1 for a transposed conv: its previous input step,
+ * which determines the reference's `partial`, conv.py:349-361) and whose other T rows are scratch; "downsample.previous" f32
+ * [B, C, 2], "downsample.first" u8 [B], "upsample.partial" f32 [B, C, 2]; "<encoder|decoder>_transformer.offset" i64 [B] and
+ * ".layers.<i>.k" / ".v" f32 [B, 8, 250, 64]. */
+int b200_mimi_state_count(b200_mimi* h);
+int b200_mimi_state_entry(b200_mimi* h, int index, const char** name, int* dtype, int* ndim, int64_t* shape8, int64_t* nbytes);
+int b200_mimi_state_read(b200_mimi* h, const char* name, void* dst_dev, int64_t nbytes);
+int b200_mimi_state_write(b200_mimi* h, const char* name, const void* src_dev, int64_t nbytes);
+/* Synchronises, returns and clears the device error flags: B200_FLAG_CODE_RANGE = MimiModel.decode was given a code outside
+ * [0, bins) (it decodes as the zero vector; the reference indexes out of bounds: "dramatic CUDA crash", vq.py:144-145). */
+int b200_mimi_error_flags(b200_mimi* h, int* flags_out);
 /* 0 = one launch per kernel, 1 = replay each one-frame encode / decode as a CUDA graph (default 1): the reference's
  * CUDAGraphed wrappers and its NO_CUDA_GRAPH switch (utils/compile.py:169-175, 190-280; compression.py:151-155). */
 int b200_mimi_set_graph(b200_mimi* h, int enable);
@@ -338,6 +351,17 @@ int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev
 int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
                      const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
                      int K, int stride, int elu_in, void* stream);
+/* mimi_tc_kernel (TMA + tcgen05 kind::tf32, 3xTF32 split products: fp32-equivalent accuracy) on the reference's layouts;
+ * test scaffolding around the kernel the Mimi handle launches for every conv / convtr / linear (the handle itself keeps all
+ * activations token-major and never transposes).
+ *   b200_op_tc_linear_f32: y[M,N] = x[M,K] . w[N,K]^T  (K % 32 == 0, N % 16 == 0)
+ *   b200_op_tc_conv1d:     same contract as b200_op_conv1d (transposed = 0) / b200_op_convtr1d (transposed = 1, where the
+ *                          carried state is the LAST INPUT STEP previous [B,Cin,1] instead of the overlap-add partial: the same
+ *                          information, conv.py:349-361); Cin % 32 == 0. */
+int b200_op_tc_linear_f32(const float* x_dev, const float* w_dev, float* y_dev, int M, int N, int K, void* stream);
+int b200_op_tc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev, const uint8_t* exec_mask_dev,
+                      float* y_dev, int B, int Cin, int Cout, int T, int K, int stride, int dilation, int elu_in, int transposed,
+                      void* stream);
 /* One temporal attention step, as the LM launches it (transformer.py:557-597): qkv bf16 [B,3*H*128] (rows q|k|v),
  * RoPE(q,k) at pos[b], K/V appended to the rings [B,H,cap,128] at pos % cap for rows with exec_mask, attention over
  * the min(pos + exec, cap) valid slots, out bf16 [B,H*128].  One kernel (rope + append + split-KV + merge). */

@@ -68,6 +68,11 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_mimi_state_bytes": (C.c_int64, [_P]),
     "b200_mimi_get_state": (_I, [_P, _P, C.c_int64]),
     "b200_mimi_set_state": (_I, [_P, _P, C.c_int64]),
+    "b200_mimi_state_count": (_I, [_P]),
+    "b200_mimi_state_entry": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200_mimi_state_read": (_I, [_P, C.c_char_p, _P, C.c_int64]),
+    "b200_mimi_state_write": (_I, [_P, C.c_char_p, _P, C.c_int64]),
+    "b200_mimi_error_flags": (_I, [_P, C.POINTER(_I)]),
     "b200_mimi_read_buffer": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "b200_mimi_algorithmic_bytes": (C.c_int64, [_P]),
     # LM
@@ -120,6 +125,8 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_op_linear_i8": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_op_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_op_tc_linear_f32": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "b200_op_tc_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_attn_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),
     "b200_op_attn_step_q8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _I, _P]),
     "b200_op_sample": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),

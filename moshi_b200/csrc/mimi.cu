@@ -1,47 +1,46 @@
 // Mimi handle: weight ingestion (reference state-dict names), streaming state, encode / decode.
 // Reference orchestration: moshi/moshi/models/compression.py:338-433.
+//
+// Everything between the PCM frame and the latent is TOKEN-MAJOR ([session][step][channel]): every SEANet conv / transposed
+// conv and every transformer linear is one launch of mimi_tc_kernel (TMA + tcgen05 kind::tf32 with 3xTF32 split products,
+// mimi_tc.cuh); a layer's epilogue writes its consumer's activation (ELU applied, hi / lo pair) straight behind the
+// consumer's carried left context, so that `cat(previous, x)` (conv.py:261) is an address, the streaming-state update
+// (conv.py:263-267) is a P-row shift inside that buffer, and ProjectedTransformer.conv_layout (transformer.py:972-981)
+// costs nothing.  The degenerate convs (Cin = 1, Cout = 1), the learnt 2x down-sampling conv (replicate padding), the
+// depth-wise up-sampling, LayerNorm / RoPE / ring attention and the residual VQ are small SIMT kernels.
 #include "mimi_kernels.cuh"
-#include "mimi_gemm.cuh"
+#include "mimi_tc.cuh"
+#include "mimi_tm_kernels.cuh"
 
 using namespace b200;
 using namespace b200::mimi;
 
 namespace {
 
-struct ConvLayer {
+struct SeaLayer {
   int kind = 0;              // 0 = StreamingConv1d, 1 = StreamingConvTranspose1d
   std::string key;           // state-dict prefix of the nn.Conv1d / nn.ConvTranspose1d
+  std::string tap;           // debug name of the raw output (empty: not stored)
   int cin = 0, cout = 0, k = 0, stride = 1, dil = 1;
-  bool elu_in = false, replicate = false, has_bias = true;
-  int res_from = -1;         // buffer index added in the epilogue (residual block second conv)
-  int in_buf = -1, out_buf = -1;
-  int t_in = 0, t_out = 0;   // samples per frame at this layer
-  float* w = nullptr;        // packed
+  bool elu_in = false;
+  int res_from = -1;         // index of the layer whose raw output is added in the epilogue (residual block second conv)
+  bool simt_first = false, simt_last = false;   // Cin = 1 / Cout = 1: memory-bound SIMT kernels
+  // per-frame geometry
+  int t_in = 0, t_out = 0;   // steps per frame in / out
+  int P = 0;                 // carried input rows: conv (k-1)*dil + 1 - stride; convtr 1 (the previous input step)
+  int N = 0;                 // GEMM output features: conv Cout; convtr S * Cout, ordered (phase, channel)
+  // weights
+  float* w_simt = nullptr;   // first conv [Cout][K]; last conv [K][Cin]
   float* bias = nullptr;
-  // streaming state
-  int P = 0;                 // conv: carried samples; convtr: K - S
-  float* state = nullptr;    // conv: previous [B][Cin][P]; convtr: partial [B][Cout][S]
-  float* scratch = nullptr;  // convtr candidate partial
-  uint8_t* first = nullptr;  // replicate flag [B]
-  std::string tap;           // debug name of the output buffer
-  // mimi_gemm.cuh path: k-major weights and the extended input buffer (carried state | frame), see there
-  bool fast = false;
-  float* wk = nullptr;
-  float* ext = nullptr;      // conv: ext [B][Cin][E]; convtr: zero-padded input [B][Cin][E]
-  int E = 0, D0 = 0;         // row length; index of the first sample of the current frame
-};
-
-struct Buf {
-  float* p = nullptr;
-  int c = 0, t = 0;
-  bool token_major = false;  // [B][T][C] instead of [B][C][T]
-  long long sb(int) const { return (long long)c * t; }
-  long long sc() const { return token_major ? 1 : t; }
-  long long st() const { return token_major ? c : 1; }
+  // streaming buffers
+  float *ext_hi = nullptr, *ext_lo = nullptr;   // [B][P + t_in][cin] (SIMT layers: ext_hi is plain fp32, ext_lo null)
+  float* y = nullptr;                           // raw output, token-major [B][t_out * (convtr: S)][cout]
+  mtc::TcLayer tc;
 };
 
 struct TrLayer {
-  const float *in_w, *out_w, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2;   // linear weights k-major [K][M]
+  const float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2;
+  mtc::TcLayer in_proj, out_proj, l1, l2;
   float *kc = nullptr, *vc = nullptr;
 };
 
@@ -50,6 +49,17 @@ struct Transformer {
   long long* offset = nullptr;   // [B] tokens seen (== RingKVCache.end_offset == _MHAState.offset)
 };
 
+struct Tap { const float* p; int C, T; bool transpose; };
+
+struct DownLayer {             // ConvDownsample1d (resample.py:14-65): k = 2 * stride, no bias, replicate padding
+  std::string key;
+  int cin = 0, cout = 0, k = 0, stride = 1;
+  int t_in = 0, t_out = 0, P = 0;
+  float* w = nullptr;          // [Cout][K * Cin]
+  float* state = nullptr;      // previous [B][Cin][P]
+  uint8_t* first = nullptr;    // replicate flags [B]
+};     // transpose: stored [B][T][C], reported [B][C][T]
+
 }  // namespace
 
 struct b200_mimi {
@@ -57,14 +67,15 @@ struct b200_mimi {
   TensorStore store;
   Arena weights, state;
   bool finalized = false;
+  int device = -1;
   int batch = 0;
   int num_codebooks = 8;
   cudaStream_t stream = nullptr;
   int frame_size = 0, hop = 0, rs = 0;       // rs = resample stride (2)
+  int sms = 148;
 
-  std::vector<ConvLayer> enc, dec;
-  ConvLayer down;
-  std::vector<Buf> enc_bufs, dec_bufs;
+  std::vector<SeaLayer> enc, dec;
+  DownLayer down;                            // learnt down-sampling conv (replicate padding): first-generation SIMT kernel
   // up-sampling (depth-wise convtr)
   float *up_w = nullptr, *up_partial = nullptr, *up_scratch = nullptr;
   Transformer enc_tr, dec_tr;
@@ -73,24 +84,23 @@ struct b200_mimi {
   float *cb[2] = {nullptr, nullptr}, *cbT[2] = {nullptr, nullptr}, *cnorm[2] = {nullptr, nullptr};
   int stored_levels[2] = {0, 0};
   // per-batch buffers
-  float* in_frame = nullptr;                   // [B][1920]
   float *tok_in_enc = nullptr, *tok_enc = nullptr, *latent = nullptr;     // [B][T][C], [B][T][C], [B][C]
   float *latent_q = nullptr, *tok_in_dec = nullptr, *tok_dec = nullptr;
-  float *tr_xn = nullptr, *tr_qkv = nullptr, *tr_q = nullptr, *tr_ao = nullptr, *tr_h = nullptr;
+  float *tr_xn_hi = nullptr, *tr_xn_lo = nullptr, *tr_qkv = nullptr, *tr_q = nullptr, *tr_ao = nullptr, *tr_ao_hi = nullptr,
+        *tr_ao_lo = nullptr, *tr_h_hi = nullptr, *tr_h_lo = nullptr;
   uint8_t* exec_mask = nullptr;
   uint8_t* first_flags = nullptr; int n_first = 0;
-  ConvCommit *enc_commits = nullptr, *dec_commits = nullptr;
-  int n_enc_commits = 0, n_dec_commits = 0, max_enc_rows = 0, max_dec_rows = 0;
+  ConvCommit* enc_commits = nullptr; int n_enc_commits = 0, max_enc_rows = 0;
   ConvTrCommit* dec_tr_commits = nullptr; int n_dec_tr_commits = 0; long long max_tr_rows = 0;
-  ExtCommit *enc_ext_commits = nullptr, *dec_ext_commits = nullptr;
-  int n_enc_ext = 0, n_dec_ext = 0, max_enc_ext_rows = 0, max_dec_ext_rows = 0;
+  TmCommit *enc_tm = nullptr, *dec_tm = nullptr; int n_enc_tm = 0, n_dec_tm = 0; long long max_enc_tm = 0, max_dec_tm = 0;
   long long* scratch_codes = nullptr;          // [B][K][1] for the host variants
   float* rvq_res[2] = {nullptr, nullptr};      // RVQ workspace: residuals, per-chunk partial argmin
   float* rvq_best[2] = {nullptr, nullptr};
   int* rvq_idx[2] = {nullptr, nullptr};
   int rvq_cap = 0;
-  float* splitk_ws = nullptr; size_t splitk_bytes = 0;   // split-K partial sums of the deep / skinny GEMMs
-  // one-frame encode / decode as CUDA graphs over static buffers (in_frame -> enc_codes, dec_codes -> out_frame)
+  float* splitk_ws = nullptr; size_t splitk_bytes = 0;   // split-K partial sums of the deep / skinny layers
+  int* err = nullptr;                                     // device error flags (B200_FLAG_CODE_RANGE)
+  // one-frame encode / decode as CUDA graphs over static buffers (frame in enc[0].ext -> enc_codes, dec_codes -> out_frame)
   cudaStream_t body = nullptr;                 // stream the kernels are being enqueued on (caller's, or gstream in capture)
   cudaStream_t gstream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -102,7 +112,8 @@ struct b200_mimi {
   float* out_frame = nullptr;                              // [B][frame_size]
   float *pin_pcm = nullptr; long long* pin_codes = nullptr; size_t pin_pcm_n = 0, pin_codes_n = 0;
   float* dev_pcm = nullptr; long long* dev_codes = nullptr; size_t dev_pcm_n = 0, dev_codes_n = 0;
-  std::map<std::string, std::pair<const float*, int64_t>> taps;
+  float* tap_scratch = nullptr; size_t tap_scratch_n = 0;
+  std::map<std::string, Tap> taps;
   int64_t weight_bytes = 0;
 };
 
@@ -116,7 +127,7 @@ void plan_seanet(b200_mimi* h) {
   h->enc.clear();
   h->dec.clear();
   auto conv = [](const std::string& key, int cin, int cout, int k, int stride, int dil, bool elu) {
-    ConvLayer l;
+    SeaLayer l;
     l.kind = 0; l.key = key; l.cin = cin; l.cout = cout; l.k = k; l.stride = stride; l.dil = dil; l.elu_in = elu;
     return l;
   };
@@ -136,7 +147,7 @@ void plan_seanet(b200_mimi* h) {
       const std::string base = "encoder.model." + std::to_string(idx);
       auto a = conv(base + ".block.1.conv.conv", ch, ch / c.compress, c.residual_kernel_size, 1, dil, true);
       auto b = conv(base + ".block.3.conv.conv", ch / c.compress, ch, 1, 1, 1, true);
-      b.res_from = -2;  // resolved below: input of the block
+      b.res_from = (int)h->enc.size() - 1;      // skip connection: the input of the block = the previous module's raw output
       b.tap = "enc." + std::to_string(idx);
       h->enc.push_back(a);
       h->enc.push_back(b);
@@ -169,7 +180,7 @@ void plan_seanet(b200_mimi* h) {
     const int ratio = c.ratios[ri];
     const int ch = mult * c.n_filters;
     ++idx;  // ELU
-    ConvLayer t;
+    SeaLayer t;
     t.kind = 1; t.key = "decoder.model." + std::to_string(idx) + ".convtr.convtr";
     t.cin = ch; t.cout = ch / 2; t.k = 2 * ratio; t.stride = ratio; t.elu_in = true;
     t.tap = "dec." + std::to_string(idx);
@@ -181,7 +192,7 @@ void plan_seanet(b200_mimi* h) {
       const std::string base = "decoder.model." + std::to_string(idx);
       auto a = conv(base + ".block.1.conv.conv", ch / 2, ch / 2 / c.compress, c.residual_kernel_size, 1, dil, true);
       auto b = conv(base + ".block.3.conv.conv", ch / 2 / c.compress, ch / 2, 1, 1, 1, true);
-      b.res_from = -2;
+      b.res_from = (int)h->dec.size() - 1;
       b.tap = "dec." + std::to_string(idx);
       h->dec.push_back(a);
       h->dec.push_back(b);
@@ -196,9 +207,16 @@ void plan_seanet(b200_mimi* h) {
     l.tap = "dec." + std::to_string(idx);
     h->dec.push_back(l);
   }
-  h->down = conv("downsample.conv.conv.conv", c.dimension, c.dimension, 2 * h->rs, h->rs, 1, false);
-  h->down.replicate = true;
-  h->down.has_bias = false;
+  for (auto* layers : {&h->enc, &h->dec})
+    for (auto& l : *layers) {
+      l.simt_first = l.kind == 0 && l.cin == 1;
+      l.simt_last = l.kind == 0 && l.cout == 1;
+      l.N = l.kind == 1 ? l.stride * l.cout : l.cout;
+      l.P = l.kind == 1 ? 1 : (l.k - 1) * l.dil + 1 - l.stride;
+    }
+  h->down = DownLayer();
+  h->down.key = "downsample.conv.conv.conv"; h->down.cin = c.dimension; h->down.cout = c.dimension;
+  h->down.k = 2 * h->rs; h->down.stride = h->rs;
 }
 
 int get_f32(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, const float** out) {
@@ -214,47 +232,77 @@ int get_f32(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, c
   return B200_OK;
 }
 
-int pack_conv(b200_mimi* h, ConvLayer& l) {
+struct ScratchFree { void* p = nullptr; ~ScratchFree() { if (p) cudaFree(p); } };
+
+// nn.Linear-shaped weight [N][n_taps * Cin] (fp32, device) -> packed hi / lo tiles owned by the handle
+int pack_tc(b200_mimi* h, mtc::TcLayer& L, const float* w_ntc, int N, int Cin, int n_taps) {
+  if (Cin % mtc::TC_KB || N % 16 || (N > mtc::TC_MAX_NT && N % mtc::TC_MAX_NT))
+    B200_FAIL(B200_ERR_INVALID, "mimi: a %d x %d (x %d taps) contraction does not tile on the tensor-core kernel", N, Cin, n_taps);
+  L.Cin = Cin; L.N = N; L.n_taps = n_taps;
+  L.NT = N >= mtc::TC_MAX_NT ? mtc::TC_MAX_NT : N;
+  L.n_tiles_n = (N + L.NT - 1) / L.NT;
+  L.num_kb = n_taps * (Cin / mtc::TC_KB);
+  const size_t bytes = mtc::tc_packed_bytes(N, Cin, n_taps);
+  void* out = nullptr;
+  B200_TRY(h->weights.alloc(&out, bytes, false));
+  B200_TRY(mtc::tc_pack_weights(w_ntc, out, N, Cin, n_taps, nullptr));
+  L.wt = static_cast<uint8_t*>(out);
+  h->weight_bytes += (int64_t)bytes;
+  return B200_OK;
+}
+
+int pack_sea(b200_mimi* h, SeaLayer& l) {
   const float* w = nullptr;
-  // ext-buffer path (mimi_gemm.cuh): GEMM-shaped layers, plus the Cout = 1 tail conv which reduces straight from ext
-  l.fast = !l.replicate && (l.cin % GK) == 0 &&
-           (l.kind == 0 ? (l.cout % 4 == 0 || (l.cout == 1 && l.stride == 1)) : (l.cout * l.stride) % 4 == 0);
-  if (getenv("B200_MIMI_LEGACY")) l.fast = false;          // debug switch: first-generation kernels only
-  if (l.kind == 0) {
-    B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
-    const long long n = (long long)l.cout * l.cin * l.k;
-    if (l.fast) {
-      B200_TRY(h->weights.alloc_t(&l.wk, n, false));
-      B200_LAUNCH(pack_conv_k_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.wk, l.cout, l.cin, l.k);
-    } else {
-      B200_TRY(h->weights.alloc_t(&l.w, n, false));
-      B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cout, l.cin, l.k);
-    }
-    h->weight_bytes += n * 4;
-  } else {
+  const long long n = (long long)l.cout * l.cin * l.k;
+  if (l.kind == 0) B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
+  else {
     if (l.k != 2 * l.stride) B200_FAIL(B200_ERR_INVALID, "convtr %s: kernel must be 2*stride", l.key.c_str());
     B200_TRY(get_f32(h, l.key + ".weight", {l.cin, l.cout, l.k}, &w));
-    const long long n = (long long)l.cin * l.cout * l.k;
-    if (l.fast) {
-      B200_TRY(h->weights.alloc_t(&l.wk, n, false));
-      B200_LAUNCH(pack_convtr_k_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.wk, l.cin, l.cout, l.stride);
-    } else {
-      B200_TRY(h->weights.alloc_t(&l.w, n, false));
-      B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cin, l.cout, l.stride);
-    }
+  }
+  if (l.simt_first) {                       // [Cout][1][K] is already [Cout][K]
+    if (l.k > 8 || l.stride != 1 || l.cout % 4) B200_FAIL(B200_ERR_INVALID, "%s: unsupported first conv", l.key.c_str());
+    B200_TRY(h->weights.alloc_t(&l.w_simt, (size_t)n, false));
+    B200_CUDA(cudaMemcpy(l.w_simt, w, (size_t)n * 4, cudaMemcpyDeviceToDevice));
     h->weight_bytes += n * 4;
+  } else if (l.simt_last) {                 // [1][Cin][K] -> [K][Cin]
+    if (l.stride != 1 || l.cin % 4) B200_FAIL(B200_ERR_INVALID, "%s: unsupported last conv", l.key.c_str());
+    B200_TRY(h->weights.alloc_t(&l.w_simt, (size_t)n, false));
+    B200_LAUNCH(tm_weight_conv_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w_simt, 1, l.cin, l.k);
+    h->weight_bytes += n * 4;
+  } else {
+    ScratchFree tmp;
+    B200_CUDA(cudaMalloc(&tmp.p, (size_t)n * 4));
+    float* wk = static_cast<float*>(tmp.p);
+    if (l.kind == 0) B200_LAUNCH(tm_weight_conv_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, wk, l.cout, l.cin, l.k);
+    else B200_LAUNCH(tm_weight_convtr_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, wk, l.cin, l.cout, l.stride);
+    B200_TRY(pack_tc(h, l.tc, wk, l.N, l.cin, l.kind == 0 ? l.k : 2));
+    B200_CUDA(cudaDeviceSynchronize());
+    l.tc.kind = l.kind; l.tc.dil = l.kind == 0 ? l.dil : 1; l.tc.stride = l.kind == 0 ? l.stride : 1;
+    l.tc.bias_mod = l.cout;
   }
-  if (l.has_bias) {
-    const float* b = nullptr;
-    B200_TRY(get_f32(h, l.key + ".bias", {l.cout}, &b));
-    B200_TRY(h->weights.alloc_t(&l.bias, l.cout, false));
-    B200_CUDA(cudaMemcpy(l.bias, b, l.cout * 4, cudaMemcpyDeviceToDevice));
-    h->weight_bytes += l.cout * 4;
-  }
+  const float* b = nullptr;
+  B200_TRY(get_f32(h, l.key + ".bias", {l.cout}, &b));
+  B200_TRY(h->weights.alloc_t(&l.bias, l.cout, false));
+  B200_CUDA(cudaMemcpy(l.bias, b, l.cout * 4, cudaMemcpyDeviceToDevice));
+  h->weight_bytes += l.cout * 4;
+  l.tc.bias = l.bias;
   B200_CUDA(cudaDeviceSynchronize());
   h->store.release(l.key + ".weight");
   h->store.release(l.key + ".bias");
-  return check_launch("pack_conv");
+  return check_launch("pack_sea");
+}
+
+// the down-sampling conv keeps the first-generation kernel and weight layout ([Cout][K*Cin])
+int pack_down(b200_mimi* h, DownLayer& l) {
+  const float* w = nullptr;
+  B200_TRY(get_f32(h, l.key + ".weight", {l.cout, l.cin, l.k}, &w));
+  const long long n = (long long)l.cout * l.cin * l.k;
+  B200_TRY(h->weights.alloc_t(&l.w, n, false));
+  B200_LAUNCH(pack_conv_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, 0, w, l.w, l.cout, l.cin, l.k);
+  h->weight_bytes += n * 4;
+  B200_CUDA(cudaDeviceSynchronize());
+  h->store.release(l.key + ".weight");
+  return check_launch("pack_down");
 }
 
 int keep(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, const float** out) {
@@ -271,18 +319,14 @@ int keep(b200_mimi* h, const std::string& name, std::vector<int64_t> shape, cons
   return B200_OK;
 }
 
-// nn.Linear weight [M][K] -> k-major [K][M] (A operand of mimi_gemm_kernel)
-int keep_kmajor(b200_mimi* h, const std::string& name, int M, int K, const float** out) {
+int keep_linear(b200_mimi* h, const std::string& name, int M, int K, mtc::TcLayer& L) {
   const float* src = nullptr;
   B200_TRY(get_f32(h, name, {M, K}, &src));
-  float* dst = nullptr;
-  B200_TRY(h->weights.alloc_t(&dst, (size_t)M * K, false));
-  B200_LAUNCH(transpose_kernel, (unsigned)ceil_div64((long long)M * K, 256), 256, 0, 0, src, dst, M, K);
+  B200_TRY(pack_tc(h, L, src, M, K, 1));       // nn.Linear weight [out][in] is already [N][K]
+  L.kind = 2; L.dil = 1; L.stride = 1; L.bias = nullptr; L.bias_mod = M;
   B200_CUDA(cudaDeviceSynchronize());
   h->store.release(name);
-  h->weight_bytes += (int64_t)M * K * 4;
-  *out = dst;
-  return check_launch("keep_kmajor");
+  return B200_OK;
 }
 
 int pack_transformer(b200_mimi* h, const std::string& prefix, Transformer& tr) {
@@ -292,14 +336,14 @@ int pack_transformer(b200_mimi* h, const std::string& prefix, Transformer& tr) {
   for (int li = 0; li < c.tr_num_layers; ++li) {
     const std::string p = prefix + ".transformer.layers." + std::to_string(li);
     TrLayer& L = tr.layers[li];
-    B200_TRY(keep_kmajor(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, &L.in_w));
-    B200_TRY(keep_kmajor(h, p + ".self_attn.out_projs.0.weight", d, d, &L.out_w));
+    B200_TRY(keep_linear(h, p + ".self_attn.in_projs.0.weight", 3 * d, d, L.in_proj));
+    B200_TRY(keep_linear(h, p + ".self_attn.out_projs.0.weight", d, d, L.out_proj));
     B200_TRY(keep(h, p + ".norm1.weight", {d}, &L.n1w));
     B200_TRY(keep(h, p + ".norm1.bias", {d}, &L.n1b));
     B200_TRY(keep(h, p + ".norm2.weight", {d}, &L.n2w));
     B200_TRY(keep(h, p + ".norm2.bias", {d}, &L.n2b));
-    B200_TRY(keep_kmajor(h, p + ".linear1.weight", ff, d, &L.l1));
-    B200_TRY(keep_kmajor(h, p + ".linear2.weight", d, ff, &L.l2));
+    B200_TRY(keep_linear(h, p + ".linear1.weight", ff, d, L.l1));
+    B200_TRY(keep_linear(h, p + ".linear2.weight", d, ff, L.l2));
     B200_TRY(keep(h, p + ".layer_scale_1.scale", {d}, &L.ls1));
     B200_TRY(keep(h, p + ".layer_scale_2.scale", {d}, &L.ls2));
   }
@@ -351,143 +395,19 @@ int pack_quantizer(b200_mimi* h) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-// tile choice: the largest tile that still gives every SM a couple of CTAs; layers with a long reduction and few
-// output tiles (deep SEANet convs, transformer linears at small batch) are cut along K as well.
-template <int KIND>
-int launch_gemm(b200_mimi* h, GemmArgs a) {
-  auto ctas = [&](int bm, int bn) { return (long long)ceil_div(a.M, bm) * ceil_div(a.N, bn); };
-  const long long want = 2 * 148;
-  a.ksplit = 1; a.ws = nullptr;
-  if (a.M > 64 && ctas(128, 128) >= want) {
-    dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 128));
-    B200_LAUNCH((mimi_gemm_kernel<128, 128, KIND>), grid, 256, 0, h->body, a);
-  } else if (ctas(64, 128) >= want) {
-    dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 64));
-    B200_LAUNCH((mimi_gemm_kernel<64, 128, KIND>), grid, 256, 0, h->body, a);
-  } else {
-    const long long n64 = ctas(64, 64);
-    const int nk = ceil_div(a.Kd, GK);
-    int ks = 1;
-    if (n64 < 148 && nk >= 32) {
-      ks = (int)(want / n64);
-      if (ks > nk / 8) ks = nk / 8;          // at least 8 k-blocks (128 k) per split
-      if (ks > 16) ks = 16;
-      if (ks < 1) ks = 1;
-      if ((size_t)ks * a.M * a.N * 4 > h->splitk_bytes) ks = 1;
-    }
-    a.ksplit = ks; a.ws = h->splitk_ws;
-    dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64), ks);
-    B200_LAUNCH((mimi_gemm_kernel<64, 64, KIND>), grid, 256, 0, h->body, a);
-    if (ks > 1) {
-      const long long n = (long long)a.M * a.N;
-      B200_LAUNCH((gemm_splitk_reduce_kernel<KIND>), (unsigned)ceil_div64(n, 256), 256, 0, h->body, a);
-    }
-  }
-  return check_launch("mimi_gemm");
-}
-
-// One SEANet layer.  (y, strides) = raw output; `next` (may be null) = the layer that consumes it: when that layer
-// runs on the mimi_gemm.cuh path its activated input is written here, behind its carried state.
-int launch_conv(b200_mimi* h, const ConvLayer& l, const float* x, long long xb, long long xc, long long xt,
-                float* y, long long yb, long long yc, long long yt, const float* res, long long rb, long long rc,
-                long long rt, const ConvLayer* next = nullptr) {
-  const int B = h->batch;
-  float* act = nullptr; long long ab = 0, ac = 0; int a_elu = 0;
-  if (next && next->fast) {
-    act = next->ext + next->D0; ab = (long long)next->cin * next->E; ac = next->E; a_elu = next->elu_in;
-  }
-  if (l.fast && l.kind == 0 && l.cout == 1) {     // last decoder conv: memory-bound reduction over (ci, kw)
-    ConvCout1 q;
-    q.ext = l.ext; q.eb = (long long)l.cin * l.E; q.E = l.E; q.off = l.D0 - l.P;
-    q.wk = l.wk; q.bias = l.bias; q.y = y; q.yb = yb; q.yt = yt;
-    q.B = B; q.Cin = l.cin; q.K = l.k; q.dil = l.dil; q.T = l.t_out;
-    const long long n = (long long)B * l.t_out;
-    B200_LAUNCH(conv_cout1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)l.k * l.cin * 4, h->body, q);
-    return check_launch(l.key.c_str());
-  }
-  if (!l.fast && l.kind == 0 && l.cin == 1 && l.stride == 1 && l.k <= 8 && !l.first && !l.elu_in && !res && xc == 0 && yt == 1) {
-    ConvCin1 q;                                   // first encoder conv: one thread per sample makes all channels
-    q.x = x; q.xb = xb; q.xt = xt; q.st = l.state; q.P = l.P; q.w = l.w; q.bias = l.bias;
-    q.y = y; q.yb = yb; q.yc = yc; q.a = act; q.ab = ab; q.ac = ac; q.a_elu = a_elu;
-    q.B = B; q.Cout = l.cout; q.K = l.k; q.T = l.t_out;
-    const long long n = (long long)B * l.t_out;
-    B200_LAUNCH(conv_cin1_kernel, (unsigned)ceil_div64(n, 256), 256, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
-    return check_launch(l.key.c_str());
-  }
-  if (l.fast) {
-    GemmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.wk = l.wk; a.in = l.ext; a.in_b = (long long)l.cin * l.E; a.in_E = l.E;
-    a.Cin = l.cin; a.bias = l.bias;
-    a.y = y; a.yb = yb; a.yc = yc; a.yt = yt;
-    a.a = act; a.ab = ab; a.ac = ac; a.at = 1; a.a_elu = a_elu;
-    if (l.kind == 0) {
-      a.in_off = l.D0 - l.P;
-      a.M = l.cout; a.N = B * l.t_out; a.Kd = l.cin * l.k; a.stride = l.stride; a.dil = l.dil; a.T = l.t_out;
-      a.res = res; a.rb = rb; a.rc = rc; a.rt = rt;
-      const bool t4 = l.t_out % 4 == 0;
-      a.vec_y = y && t4 && yt == 1 && yb % 4 == 0 && yc % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
-      a.vec_a = act && t4;
-      a.vec_r = res && t4 && rt == 1 && rb % 4 == 0 && rc % 4 == 0;
-      return launch_gemm<G_CONV>(h, a);
-    }
-    a.in_off = l.D0;
-    a.M = l.cout * l.stride; a.N = B * (l.t_in + 1); a.Kd = 2 * l.cin; a.stride = l.stride; a.T = l.t_in;
-    a.partial = l.state; a.scratch = l.scratch;
-    // consecutive GEMM rows of one channel are consecutive output samples: move them as float4 / float2 when S allows
-    const bool al = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && yb % 4 == 0 && yc % 4 == 0;
-    a.vec_y = (l.stride % 4 == 0 && al) ? 4 : (l.stride % 2 == 0 && al) ? 2 : 1;
-    return launch_gemm<G_CONVTR>(h, a);
-  }
-  if (l.kind == 0) {
-    ConvP p;
-    p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.Tin = l.t_in;
-    p.st = l.state; p.P = l.P; p.first = l.first;
-    p.w = l.w; p.bias = l.bias;
-    p.y = y; p.yb = yb; p.yc = yc; p.yt = yt;
-    p.res = res; p.rb = rb; p.rc = rc; p.rt = rt;
-    p.a = act; p.ab = ab; p.ac = ac; p.at = 1; p.a_elu = a_elu;
-    p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.K = l.k; p.stride = l.stride; p.dil = l.dil; p.Tout = l.t_out;
-    p.elu_in = l.elu_in;
-    p.M = l.cout; p.N = B * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
-  } else {
-    if (act) B200_FAIL(B200_ERR_INVALID, "first-generation convtr cannot feed a mimi_gemm layer");
-    ConvTrP p;
-    p.x = x; p.xb = xb; p.xc = xc; p.xt = xt; p.T = l.t_in;
-    p.partial = l.state; p.scratch = l.scratch; p.w = l.w; p.bias = l.bias;
-    p.y = y; p.yb = yb; p.yc = yc; p.yt = yt;
-    p.B = B; p.Cin = l.cin; p.Cout = l.cout; p.S = l.stride; p.elu_in = l.elu_in;
-    p.M = l.cout * l.stride; p.N = B * (l.t_in + 1); p.Kd = 2 * l.cin; p.cin_aligned = (l.cin % BK) == 0;
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    B200_LAUNCH((igemm_f32_kernel<ConvTrP, false>), grid, 256, 0, h->body, p);
-  }
-  return check_launch(l.key.c_str());
-}
-
-// y[n][m] = epi(sum_k x[n][k] * w[m][k]) on token-major activations; w is k-major [K][M]
-int launch_linear(b200_mimi* h, const float* x, int K, const float* w, float* y, int M, int ntok, int epi,
-                  const float* res, const float* scale) {
-  GemmArgs a;
-  memset(&a, 0, sizeof(a));
-  a.wk = w; a.in = x; a.in_E = K; a.M = M; a.N = ntok; a.Kd = K;
-  a.y = y; a.yb = M; a.res = res; a.scale = scale;
-  a.lin_epi = epi == EPI_GELU ? GL_GELU : epi == EPI_RES_SCALE ? GL_RES_SCALE : GL_NONE;
-  return launch_gemm<G_LIN>(h, a);
-}
+int launch_tc(b200_mimi* h, const mtc::TcLayer& L) { return mtc::tc_launch(L, h->body); }
 
 // StreamingTransformer.forward for T tokens per row (transformer.py:894-929, layer :752-802)
 int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, int T) {
   const auto& c = h->cfg;
-  const int B = h->batch, ntok = B * T, d = c.tr_d_model, H = c.tr_num_heads, D = d / H, ff = c.tr_dim_feedforward;
+  const int B = h->batch, ntok = B * T, d = c.tr_d_model, H = c.tr_num_heads, D = d / H;
   const float nl = -logf(c.tr_max_period) * 2.f / (float)D;
   const size_t attn_smem = (size_t)(T * D + T * c.tr_context) * sizeof(float);
   for (size_t li = 0; li < tr.layers.size(); ++li) {
     TrLayer& L = tr.layers[li];
     const float* cur = li == 0 ? x_in : x;
-    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn, ntok, d, 1e-5f);
-    B200_TRY(launch_linear(h, h->tr_xn, d, L.in_w, h->tr_qkv, 3 * d, ntok, EPI_NONE, nullptr, nullptr));
+    B200_LAUNCH(layernorm_split_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn_hi, h->tr_xn_lo, ntok, d, 1e-5f);
+    B200_TRY(launch_tc(h, L.in_proj));
     {
       const long long total = (long long)B * T * H * (D / 2);
       B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->tr_qkv, h->tr_q, L.kc,
@@ -495,88 +415,97 @@ int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, 
     }
     B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
                 h->exec_mask, T, H, c.tr_context, c.tr_context);
-    B200_TRY(launch_linear(h, h->tr_ao, d, L.out_w, x, d, ntok, EPI_RES_SCALE, cur, L.ls1));
-    B200_LAUNCH(layernorm_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn, ntok, d, 1e-5f);
-    B200_TRY(launch_linear(h, h->tr_xn, d, L.l1, h->tr_h, ff, ntok, EPI_GELU, nullptr, nullptr));
-    B200_TRY(launch_linear(h, h->tr_h, ff, L.l2, x, d, ntok, EPI_RES_SCALE, x, L.ls2));
+    B200_LAUNCH(split_kernel, (unsigned)ceil_div64((long long)ntok * d, 256), 256, 0, h->body, h->tr_ao, h->tr_ao_hi, h->tr_ao_lo,
+                (long long)ntok * d);
+    B200_TRY(launch_tc(h, L.out_proj));       // x = cur + layer_scale_1 * out_proj(attention)
+    B200_LAUNCH(layernorm_split_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn_hi, h->tr_xn_lo, ntok, d, 1e-5f);
+    B200_TRY(launch_tc(h, L.l1));             // h = gelu(linear1(xn)) as a hi / lo pair
+    B200_TRY(launch_tc(h, L.l2));             // x = x + layer_scale_2 * linear2(h)
   }
   B200_LAUNCH(advance_offsets_kernel, ceil_div(B, 128), 128, 0, h->body, tr.offset, h->exec_mask, B, T);
   return check_launch("mimi transformer");
 }
 
-int run_seanet(b200_mimi* h, std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, const float* x0, long long xb,
-               long long xc, long long xt, float* last_out, long long lb, long long lc, long long lt) {
-  // bufs[i] is the output of layers[i]; layer 0 reads (x0, strides); the last layer writes last_out.
-  if (layers[0].fast) {   // its input comes from outside the SEANet (transformer output): copy it behind the carried state
-    const ConvLayer& l = layers[0];
-    const long long n = (long long)h->batch * l.cin * l.t_in;
-    B200_LAUNCH(fill_act_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->body, x0, xb, xc, xt, l.ext + l.D0,
-                (long long)l.cin * l.E, (long long)l.E, 1LL, h->batch, l.cin, l.t_in, (int)l.elu_in);
-  }
+int run_seanet(b200_mimi* h, std::vector<SeaLayer>& layers) {
+  const int B = h->batch;
   for (size_t i = 0; i < layers.size(); ++i) {
-    ConvLayer& l = layers[i];
-    const float* x; long long sb, sc, st;
-    if (i == 0) { x = x0; sb = xb; sc = xc; st = xt; }
-    else { const Buf& b = bufs[i - 1]; x = b.p; sb = b.sb(0); sc = b.sc(); st = b.st(); }
-    float* y; long long yb, yc, yt;
-    if (i + 1 == layers.size() && last_out) { y = last_out; yb = lb; yc = lc; yt = lt; }
-    else { const Buf& b = bufs[i]; y = b.p; yb = b.sb(0); yc = b.sc(); yt = b.st(); }
-    const float* res = nullptr; long long rb = 0, rc = 0, rt = 0;
-    if (l.res_from == -2) {   // residual block: skip connection is the input of the first conv of the block
-      if (i < 2) B200_FAIL(B200_ERR_INVALID, "bad residual plan");
-      const Buf& b = bufs[i - 2];
-      res = b.p; rb = b.sb(0); rc = b.sc(); rt = b.st();
+    SeaLayer& l = layers[i];
+    if (l.simt_first) {
+      const SeaLayer& nx = layers[i + 1];
+      ConvFirst q;
+      q.ext = l.ext_hi; q.E = l.P + l.t_in; q.P = l.P; q.w = l.w_simt; q.bias = l.bias;
+      q.y = l.y; q.y_sb = (long long)l.t_out * l.cout;
+      q.a_hi = nx.ext_hi + (long long)nx.P * nx.cin; q.a_lo = nx.ext_lo + (long long)nx.P * nx.cin;
+      q.a_sb = (long long)(nx.P + nx.t_in) * nx.cin; q.a_elu = nx.elu_in;
+      q.B = B; q.Cout = l.cout; q.K = l.k; q.T = l.t_out;
+      const long long n = (long long)B * l.t_out;
+      B200_LAUNCH(conv_first_tm_kernel, (unsigned)ceil_div64(n, 128), 128, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
+    } else if (l.simt_last) {
+      ConvLast q;
+      q.ext = l.ext_hi; q.e_sb = (long long)(l.P + l.t_in) * l.cin; q.Cin = l.cin; q.w = l.w_simt; q.bias = l.bias;
+      q.y = l.y; q.y_sb = l.t_out; q.B = B; q.K = l.k; q.dil = l.dil; q.T = l.t_out;
+      const long long n = (long long)B * l.t_out;
+      B200_LAUNCH(conv_last_tm_kernel, (unsigned)ceil_div64(n, 128), 128, (size_t)l.k * l.cin * 4, h->body, q);
+    } else {
+      B200_TRY(launch_tc(h, l.tc));
     }
-    const ConvLayer* next = i + 1 < layers.size() ? &layers[i + 1] : nullptr;
-    B200_TRY(launch_conv(h, l, x, sb, sc, st, y, yb, yc, yt, res, rb, rc, rt, next));
   }
-  return B200_OK;
+  return check_launch("mimi seanet");
 }
 
 int commit_states(b200_mimi* h, bool encoder) {
   const int B = h->batch;
   if (encoder) {
-    if (h->n_enc_commits) {
+    if (h->n_enc_commits) {      // the down-sampling conv (first-generation state layout + replicate flags)
       dim3 grid(ceil_div(h->max_enc_rows, 128), h->n_enc_commits);
       B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->enc_commits, h->n_enc_commits, h->exec_mask, B);
       B200_LAUNCH(conv_clear_first_kernel, ceil_div(h->n_enc_commits * B, 128), 128, 0, h->body, h->enc_commits,
                   h->n_enc_commits, h->exec_mask, B);
     }
-    if (h->n_enc_ext) {
-      dim3 grid(ceil_div(h->max_enc_ext_rows, 128), h->n_enc_ext);
-      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->enc_ext_commits, h->exec_mask, B);
+    if (h->n_enc_tm) {
+      dim3 grid((unsigned)ceil_div64(h->max_enc_tm, 128), h->n_enc_tm);
+      B200_LAUNCH(tm_commit_kernel, grid, 128, 0, h->body, h->enc_tm, h->exec_mask, B);
     }
   } else {
-    if (h->n_dec_commits) {
-      dim3 grid(ceil_div(h->max_dec_rows, 128), h->n_dec_commits);
-      B200_LAUNCH(conv_commit_kernel, grid, 128, 0, h->body, h->dec_commits, h->n_dec_commits, h->exec_mask, B);
+    if (h->n_dec_tm) {
+      dim3 grid((unsigned)ceil_div64(h->max_dec_tm, 128), h->n_dec_tm);
+      B200_LAUNCH(tm_commit_kernel, grid, 128, 0, h->body, h->dec_tm, h->exec_mask, B);
     }
-    if (h->n_dec_ext) {
-      dim3 grid(ceil_div(h->max_dec_ext_rows, 128), h->n_dec_ext);
-      B200_LAUNCH(ext_commit_kernel, grid, 128, 0, h->body, h->dec_ext_commits, h->exec_mask, B);
-    }
-    dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);
+    dim3 g2((unsigned)ceil_div64(h->max_tr_rows, 256), h->n_dec_tr_commits);      // the depth-wise up-sampling's overlap-add carry
     B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, h->body, h->dec_tr_commits, h->exec_mask, B);
   }
   return check_launch("commit_states");
 }
 
-// in_frame [B][frame] -> latent [B][C]   (static buffers only: this is what gets captured into a graph)
+// frame in enc[0].ext -> latent [B][C]   (static buffers only: this is what gets captured into a graph)
 int encode_body(b200_mimi* h) {
-  const int fs = h->frame_size, d = h->cfg.dimension;
-  const int T = fs / h->hop;   // encoder tokens per frame (2)
-  // SEANet encoder; the last conv writes token-major [B][T][C] for the transformer
-  B200_TRY(run_seanet(h, h->enc, h->enc_bufs, h->in_frame, fs, 0, 1, h->tok_in_enc, (long long)T * d, 1, d));
+  const int d = h->cfg.dimension;
+  const int T = h->frame_size / h->hop;   // encoder tokens per frame (2)
+  B200_TRY(run_seanet(h, h->enc));        // the last conv's raw output is tok_in_enc, token-major [B][T][C]
   B200_TRY(run_transformer(h, h->enc_tr, h->tok_in_enc, h->tok_enc, T));
-  // learnt down-sampling conv reads token-major, writes latent [B][C][1]
-  B200_TRY(launch_conv(h, h->down, h->tok_enc, (long long)T * d, 1, d, h->latent, d, 1, 1, nullptr, 0, 0, 0));
+  {                                       // learnt down-sampling conv reads token-major, writes latent [B][C][1]
+    const DownLayer& l = h->down;
+    ConvP p;
+    p.x = h->tok_enc; p.xb = (long long)T * d; p.xc = 1; p.xt = d; p.Tin = l.t_in;
+    p.st = l.state; p.P = l.P; p.first = l.first;
+    p.w = l.w; p.bias = nullptr;
+    p.y = h->latent; p.yb = d; p.yc = 1; p.yt = 1;
+    p.res = nullptr; p.rb = p.rc = p.rt = 0;
+    p.B = h->batch; p.Cin = l.cin; p.Cout = l.cout; p.K = l.k; p.stride = l.stride; p.dil = 1; p.Tout = l.t_out;
+    p.elu_in = 0;
+    p.M = l.cout; p.N = h->batch * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
+  }
   B200_TRY(commit_states(h, true));
   return B200_OK;
 }
 
+// the PCM frame lands right behind the first conv's carried samples
 int load_frame(b200_mimi* h, const float* pcm, int n_frames, int f) {
   const int fs = h->frame_size;
-  B200_CUDA(cudaMemcpy2DAsync(h->in_frame, (size_t)fs * 4, pcm + (size_t)f * fs, (size_t)fs * n_frames * 4,
+  const SeaLayer& l = h->enc[0];
+  B200_CUDA(cudaMemcpy2DAsync(l.ext_hi + l.P, (size_t)(l.P + fs) * 4, pcm + (size_t)f * fs, (size_t)fs * n_frames * 4,
                               (size_t)fs * 4, h->batch, cudaMemcpyDeviceToDevice, h->stream));
   return B200_OK;
 }
@@ -645,7 +574,7 @@ int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long l
   a.levels[1] = n_codebooks - a.levels[0];
   a.level_offset[0] = 0; a.level_offset[1] = a.levels[0];
   a.out = out; a.ob = ob; a.oc = oc; a.ot = ot;
-  a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins;
+  a.Dq = c.q_dimension; a.Cout = c.dimension; a.bins = c.q_bins; a.err = h->err;
   dim3 grid(h->batch * n_cols, (c.dimension + 63) / 64);
   B200_LAUNCH(rvq_decode_kernel, grid, 256, (2 * c.q_dimension + 256) * sizeof(float), h->body, a);
   return check_launch("rvq_decode");
@@ -653,15 +582,15 @@ int dequantize_cols(b200_mimi* h, const long long* codes, long long cs_b, long l
 
 // latent_q [B][C] -> out_frame [B][frame]   (static buffers only)
 int decode_latent_body(b200_mimi* h) {
-  const int B = h->batch, fs = h->frame_size, d = h->cfg.dimension, S = h->rs;
+  const int B = h->batch, d = h->cfg.dimension, S = h->rs;
   const int T = S;   // tokens per frame after up-sampling
   {
     const long long total = (long long)B * 2 * S * d;   // (T_in + 1) * S * C with T_in = 1
     B200_LAUNCH(upsample_dw_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->latent_q, (long long)d, 1LL, 1LL, 1,
                 h->up_w, h->up_partial, h->up_scratch, h->tok_in_dec, B, d, S);
   }
-  B200_TRY(run_transformer(h, h->dec_tr, h->tok_in_dec, h->tok_dec, T));
-  B200_TRY(run_seanet(h, h->dec, h->dec_bufs, h->tok_dec, (long long)T * d, 1, d, h->out_frame, (long long)fs, 0, 1));
+  B200_TRY(run_transformer(h, h->dec_tr, h->tok_in_dec, h->tok_dec, T));   // its last linear also fills dec[0]'s ext
+  B200_TRY(run_seanet(h, h->dec));
   B200_TRY(commit_states(h, false));
   return B200_OK;
 }
@@ -715,7 +644,30 @@ int ensure_streaming(b200_mimi* h, const char* what) {
   return B200_OK;
 }
 
-void register_tap(b200_mimi* h, const std::string& name, const float* p, int64_t n) { h->taps[name] = {p, n}; }
+void register_tap(b200_mimi* h, const std::string& name, const float* p, int C, int T, bool transpose) { h->taps[name] = Tap{p, C, T, transpose}; }
+
+// Tile shape of a layer whose sessions produce T GEMM rows per frame: the largest power of two that divides T (<= 128) steps
+// of bb = 128 / tt sessions; strided convolutions also keep the TMA box (tt * stride rows) within 256.
+int tile_shape(int T, int stride, int* tt, int* bb) {
+  int t = 128;
+  while (t > 1 && (T % t || t * stride > 256)) t >>= 1;
+  if (T % t) return B200_ERR_SHAPE;
+  *tt = t; *bb = 128 / t;
+  return B200_OK;
+}
+
+// Plans one tensor-core layer for B sessions of T GEMM rows: A maps over `in_hi / in_lo` ([B][rows][Cin]), epilogue pointers set
+// by the caller in L.p beforehand (y / res / act); this fills geometry, schedule and tensor maps.
+int plan_layer(b200_mimi* h, mtc::TcLayer& L, const float* in_hi, const float* in_lo, int rows_per_session, int row0, int T) {
+  const int B = h->batch;
+  int tt = 0, bb = 0;
+  if (tile_shape(T, L.stride, &tt, &bb) != B200_OK) B200_FAIL(B200_ERR_INVALID, "mimi: %d steps per frame do not tile", T);
+  L.p.tt = tt; L.p.bb = bb; L.p.row0 = row0;
+  L.p.ws = h->splitk_ws;
+  B200_TRY(mtc::tc_make_map(&L.map_hi, in_hi, L.Cin, rows_per_session, (long long)rows_per_session * L.Cin, B, tt, bb, L.stride));
+  B200_TRY(mtc::tc_make_map(&L.map_lo, in_lo, L.Cin, rows_per_session, (long long)rows_per_session * L.Cin, B, tt, bb, L.stride));
+  return mtc::tc_plan(L, B, T, h->sms, h->splitk_bytes);
+}
 
 }  // namespace
 
@@ -731,8 +683,11 @@ int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out) {
   if (cfg->q_dimension % 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: codebook dimension must be a multiple of 8");
   if (cfg->tr_d_model / cfg->tr_num_heads != 64) B200_FAIL(B200_ERR_INVALID, "mimi_create: head dim must be 64");
   if (cfg->tr_d_model != cfg->dimension) B200_FAIL(B200_ERR_INVALID, "mimi_create: projected transformer unsupported");
+  if (cfg->n_filters % 32 || cfg->compress != 2 || cfg->n_filters / cfg->compress % 32)
+    B200_FAIL(B200_ERR_INVALID, "mimi_create: SEANet channel counts must be multiples of 32 (tensor-core k-blocks)");
   b200_mimi* h = new b200_mimi();
   h->cfg = *cfg;
+  cudaGetDevice(&h->device);
   h->num_codebooks = cfg->num_codebooks;
   h->hop = 1;
   for (int i = 0; i < cfg->n_ratios; ++i) h->hop *= cfg->ratios[i];
@@ -752,15 +707,19 @@ int b200_mimi_load_tensor(b200_mimi* h, const char* name, const void* data_dev, 
                           const int64_t* shape) {
   if (!h) B200_FAIL(B200_ERR_INVALID, "mimi_load_tensor: null handle");
   if (h->finalized) B200_FAIL(B200_ERR_STATE, "mimi_load_tensor: already finalized");
+  DeviceGuard g(h->device);
   return h->store.put(name, data_dev, dtype, ndim, shape);
 }
 
 int b200_mimi_finalize(b200_mimi* h) {
   if (!h) B200_FAIL(B200_ERR_INVALID, "mimi_finalize: null handle");
   if (h->finalized) return B200_OK;
-  for (auto& l : h->enc) B200_TRY(pack_conv(h, l));
-  for (auto& l : h->dec) B200_TRY(pack_conv(h, l));
-  B200_TRY(pack_conv(h, h->down));
+  DeviceGuard g(h->device);
+  B200_TRY(mtc::tc_init());
+  B200_CUDA(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
+  for (auto& l : h->enc) B200_TRY(pack_sea(h, l));
+  for (auto& l : h->dec) B200_TRY(pack_sea(h, l));
+  B200_TRY(pack_down(h, h->down));
   {
     const float* w = nullptr;
     B200_TRY(keep(h, "upsample.convtr.convtr.convtr.weight", {h->cfg.dimension, 1, 2 * h->rs}, &w));
@@ -777,6 +736,7 @@ int b200_mimi_finalize(b200_mimi* h) {
 
 int b200_mimi_destroy(b200_mimi* h) {
   if (!h) return B200_OK;
+  DeviceGuard g(h->device);
   b200_mimi_streaming_end(h);
   h->store.release_all();
   h->weights.free_all();
@@ -784,6 +744,7 @@ int b200_mimi_destroy(b200_mimi* h) {
   if (h->pin_codes) cudaFreeHost(h->pin_codes);
   if (h->dev_pcm) cudaFree(h->dev_pcm);
   if (h->dev_codes) cudaFree(h->dev_codes);
+  if (h->tap_scratch) cudaFree(h->tap_scratch);
   for (int w = 0; w < 2; ++w) {
     if (h->rvq_res[w]) cudaFree(h->rvq_res[w]);
     if (h->rvq_best[w]) cudaFree(h->rvq_best[w]);
@@ -806,116 +767,115 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   if (!h || !h->finalized) B200_FAIL(B200_ERR_STATE, "streaming_begin: handle not finalized");
   if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "streaming_begin: already streaming");   // streaming.py:112
   if (batch < 1) B200_FAIL(B200_ERR_INVALID, "streaming_begin: batch %d", batch);
+  DeviceGuard guard_dev(h->device);
   const auto& c = h->cfg;
   const int B = batch, d = c.dimension;
   h->stream = static_cast<cudaStream_t>(stream);
   h->taps.clear();
   Arena& A = h->state;
+  struct Cleanup { b200_mimi* h; bool armed = true; ~Cleanup() { if (armed) h->state.free_all(); } } cleanup{h};
+  h->batch = B;                              // plan_layer reads it (reset below on failure paths by the caller's streaming_end)
+  struct BatchReset { b200_mimi* h; bool armed = true; ~BatchReset() { if (armed) h->batch = 0; } } batch_reset{h};
   B200_TRY(A.alloc_t(&h->exec_mask, B, false));
   B200_CUDA(cudaMemset(h->exec_mask, 1, B));
-  B200_TRY(A.alloc_t(&h->in_frame, (size_t)B * h->frame_size));
+  B200_TRY(A.alloc_t(&h->err, 1));
+  h->splitk_bytes = (size_t)64 << 20;
+  B200_TRY(A.alloc(reinterpret_cast<void**>(&h->splitk_ws), h->splitk_bytes, false));
 
   // flags for replicate-padded convs (only the down-sampling conv in Mimi)
   h->n_first = 1;
   B200_TRY(A.alloc_t(&h->first_flags, (size_t)h->n_first * B, false));
   B200_CUDA(cudaMemset(h->first_flags, 1, (size_t)h->n_first * B));
 
-  std::vector<ConvCommit> enc_c, dec_c;
-  std::vector<ExtCommit> enc_e, dec_e;
-  std::vector<ConvTrCommit> dec_t;
-  h->max_enc_rows = h->max_dec_rows = 0;
-  h->max_enc_ext_rows = h->max_dec_ext_rows = 0;
-  h->max_tr_rows = 0;
-
-  auto setup = [&](std::vector<ConvLayer>& layers, std::vector<Buf>& bufs, int t0, bool last_token_major,
-                   const float* x0, long long x0b, long long x0c, long long x0t, std::vector<ConvCommit>& commits,
-                   std::vector<ExtCommit>& ecommits, bool is_dec) -> int {
-    bufs.assign(layers.size(), Buf());
-    int t = t0;
-    for (size_t i = 0; i < layers.size(); ++i) {
-      ConvLayer& l = layers[i];
-      l.t_in = t;
-      if (l.kind == 0) {
-        if (t % l.stride) B200_FAIL(B200_ERR_INVALID, "%s: %d samples not divisible by stride %d", l.key.c_str(), t, l.stride);
-        l.t_out = t / l.stride;
-        l.P = (l.k - 1) * l.dil + 1 - l.stride;
-        if (l.fast) {          // carried samples live inside ext, right in front of the 16-byte aligned frame
-          l.D0 = (l.P + 3) / 4 * 4;
-          l.E = (l.D0 + t + 3) / 4 * 4;
-          B200_TRY(A.alloc_t(&l.ext, (size_t)B * l.cin * l.E));
-        } else if (l.P > 0) {
-          B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
-        }
-      } else {
-        l.t_out = t * l.stride;
-        l.P = l.k - l.stride;
-        B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cout * l.P));
-        B200_TRY(A.alloc_t(&l.scratch, (size_t)B * l.cout * l.P));
-        if (l.fast) {          // zero column on both sides of the frame: taps that fall outside read 0
-          l.D0 = 4;
-          l.E = (l.D0 + t + 1 + 3) / 4 * 4;
-          B200_TRY(A.alloc_t(&l.ext, (size_t)B * l.cin * l.E));
-        }
-      }
-      t = l.t_out;
-      Buf& b = bufs[i];
-      b.c = l.cout; b.t = l.t_out;
-      const bool is_last = i + 1 == layers.size();
-      if (!(is_last && is_dec)) {   // the decoder's last conv writes straight into the caller's PCM buffer
-        b.token_major = is_last && last_token_major;
-        B200_TRY(A.alloc_t(&b.p, (size_t)B * l.cout * l.t_out));
-        if (!l.tap.empty()) register_tap(h, l.tap, b.p, (int64_t)B * l.cout * l.t_out);
-      }
-      // commit descriptor
-      const float* x; long long sb, sc, st;
-      if (i == 0) { x = x0; sb = x0b; sc = x0c; st = x0t; }
-      else { const Buf& pb = bufs[i - 1]; x = pb.p; sb = pb.sb(0); sc = pb.sc(); st = pb.st(); }
-      if (l.kind == 0 && l.P > 0 && l.fast) {
-        ExtCommit ec;
-        ec.ext = l.ext + (l.D0 - l.P); ec.P = l.P; ec.T = l.t_in; ec.E = l.E; ec.Cin = l.cin;
-        ecommits.push_back(ec);
-        int& mx = is_dec ? h->max_dec_ext_rows : h->max_enc_ext_rows;
-        if (B * l.cin > mx) mx = B * l.cin;
-      } else if (l.kind == 0 && l.P > 0) {
-        ConvCommit cc;
-        cc.x = x; cc.xb = sb; cc.xc = sc; cc.xt = st; cc.Tin = l.t_in; cc.st = l.state; cc.P = l.P; cc.Cin = l.cin;
-        cc.elu_in = l.elu_in; cc.first = nullptr;
-        commits.push_back(cc);
-        int rows = B * l.cin;
-        int& mx = is_dec ? h->max_dec_rows : h->max_enc_rows;
-        if (rows > mx) mx = rows;
-      } else if (l.kind == 1) {
-        ConvTrCommit tc;
-        tc.partial = l.state; tc.scratch = l.scratch; tc.per_row = l.cout * l.P;
-        dec_t.push_back(tc);
-        if ((long long)B * tc.per_row > h->max_tr_rows) h->max_tr_rows = (long long)B * tc.per_row;
-      }
-    }
-    return B200_OK;
-  };
-
   const int T = h->rs;   // transformer tokens per frame on both sides
-  B200_TRY(A.alloc_t(&h->tok_in_enc, (size_t)B * T * d));   // written by the last encoder conv (token-major)
+  B200_TRY(A.alloc_t(&h->tok_in_enc, (size_t)B * T * d));   // written by the last encoder conv
   B200_TRY(A.alloc_t(&h->tok_enc, (size_t)B * T * d));
   B200_TRY(A.alloc_t(&h->latent, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->latent_q, (size_t)B * d));
   B200_TRY(A.alloc_t(&h->tok_in_dec, (size_t)B * T * d));
   B200_TRY(A.alloc_t(&h->tok_dec, (size_t)B * T * d));
-  B200_TRY(setup(h->enc, h->enc_bufs, h->frame_size, true, h->in_frame, h->frame_size, 0, 1, enc_c, enc_e, false));
-  // the last encoder conv writes tok_in_enc instead of its own buffer
-  register_tap(h, h->enc.back().tap, h->tok_in_enc, (int64_t)B * T * d);
+  B200_TRY(A.alloc_t(&h->out_frame, (size_t)B * h->frame_size));
+
+  std::vector<TmCommit> enc_tm, dec_tm;
+  h->max_enc_tm = h->max_dec_tm = 0;
+  // buffers of one SEANet: every layer owns its extended input; raw outputs where something reads them
+  auto setup = [&](std::vector<SeaLayer>& layers, int t0, bool is_dec, std::vector<TmCommit>& commits, long long& max_rows) -> int {
+    int t = t0;
+    for (size_t i = 0; i < layers.size(); ++i) {
+      SeaLayer& l = layers[i];
+      l.t_in = t;
+      if (l.kind == 0) {
+        if (t % l.stride) B200_FAIL(B200_ERR_INVALID, "%s: %d samples not divisible by stride %d", l.key.c_str(), t, l.stride);
+        l.t_out = t / l.stride;
+      } else {
+        l.t_out = t;                            // GEMM rows per session; each row holds `stride` output steps
+      }
+      const size_t ext_n = (size_t)B * (l.P + l.t_in) * l.cin;
+      B200_TRY(A.alloc_t(&l.ext_hi, ext_n));
+      if (!l.simt_first && !l.simt_last) B200_TRY(A.alloc_t(&l.ext_lo, ext_n));
+      else l.ext_lo = nullptr;
+      if (l.P > 0) {
+        TmCommit cm;
+        cm.hi = l.ext_hi; cm.lo = l.ext_lo; cm.P = l.P; cm.T = l.t_in; cm.rowlen = l.cin; cm.sb = (long long)(l.P + l.t_in) * l.cin;
+        commits.push_back(cm);
+        if ((long long)B * l.cin > max_rows) max_rows = (long long)B * l.cin;
+      }
+      const int steps_out = l.kind == 1 ? l.t_out * l.stride : l.t_out;
+      const bool is_last = i + 1 == layers.size();
+      l.y = nullptr;
+      if (is_last && !is_dec) l.y = h->tok_in_enc;                       // transformer input
+      else if (is_last && is_dec) l.y = h->out_frame;
+      else if (!l.tap.empty()) B200_TRY(A.alloc_t(&l.y, (size_t)B * steps_out * l.cout));
+      if (!l.tap.empty() && l.y) register_tap(h, l.tap, l.y, l.cout, steps_out, !(is_last && !is_dec));
+      t = steps_out;
+    }
+    return B200_OK;
+  };
+  B200_TRY(setup(h->enc, h->frame_size, false, enc_tm, h->max_enc_tm));
   if (h->enc.back().t_out != T) B200_FAIL(B200_ERR_INVALID, "encoder yields %d tokens/frame, expected %d", h->enc.back().t_out, T);
-  B200_TRY(setup(h->dec, h->dec_bufs, T, false, h->tok_dec, (long long)T * d, 1, d, dec_c, dec_e, true));
+  B200_TRY(setup(h->dec, T, true, dec_tm, h->max_dec_tm));
   if (h->dec.back().t_out != h->frame_size) B200_FAIL(B200_ERR_INVALID, "decoder yields %d samples/frame", h->dec.back().t_out);
-  register_tap(h, "enc.tr", h->tok_enc, (int64_t)B * T * d);
-  register_tap(h, "enc.latent", h->latent, (int64_t)B * d);
-  register_tap(h, "dec.latent", h->latent_q, (int64_t)B * d);
-  register_tap(h, "dec.up", h->tok_in_dec, (int64_t)B * T * d);
-  register_tap(h, "dec.tr", h->tok_dec, (int64_t)B * T * d);
+  // epilogues + plans: layer i writes its raw output and the activation its consumer i + 1 reads
+  auto wire = [&](std::vector<SeaLayer>& layers) -> int {
+    for (size_t i = 0; i < layers.size(); ++i) {
+      SeaLayer& l = layers[i];
+      if (l.simt_first || l.simt_last) continue;
+      mtc::TcParams& p = l.tc.p;
+      memset(&p, 0, sizeof(p));
+      p.epi = mtc::TC_EPI_CONV;
+      p.y = l.y; p.y_sb = (long long)l.t_out * l.N; p.y_row = l.N;      // convtr: a GEMM row is `stride` consecutive output steps
+      if (l.res_from >= 0) {
+        const SeaLayer& r = layers[l.res_from];
+        if (!r.y) B200_FAIL(B200_ERR_INVALID, "bad residual plan");
+        p.res = r.y; p.r_sb = (long long)l.t_out * l.N; p.r_row = l.N;
+      }
+      if (i + 1 < layers.size()) {
+        const SeaLayer& nx = layers[i + 1];
+        p.act_mode = nx.simt_last ? mtc::TC_ACT_FULL : mtc::TC_ACT_SPLIT;
+        p.act_elu = nx.elu_in ? 1 : 0;
+        p.a_hi = nx.ext_hi + (long long)nx.P * nx.cin;
+        p.a_lo = nx.ext_lo ? nx.ext_lo + (long long)nx.P * nx.cin : nullptr;
+        p.a_sb = (long long)(nx.P + nx.t_in) * nx.cin;
+        p.a_row = l.N;                         // = stride * nx.cin for a convtr: `stride` consumer rows per GEMM row
+      }
+      // conv: GEMM row t reads ext rows t * stride + tap * dil (ext row 0 = oldest carried sample)
+      // convtr: GEMM row t reads ext rows t + slot, slot 0 = x[t-1] (ext row 0 = the carried previous step)
+      B200_TRY(plan_layer(h, l.tc, l.ext_hi, l.ext_lo, l.P + l.t_in, 0, l.t_out));
+    }
+    return B200_OK;
+  };
+  B200_TRY(wire(h->enc));
+  B200_TRY(wire(h->dec));
+  register_tap(h, "enc.tr", h->tok_enc, d, T, false);
+  register_tap(h, "enc.latent", h->latent, d, 1, false);
+  register_tap(h, "dec.latent", h->latent_q, d, 1, false);
+  register_tap(h, "dec.up", h->tok_in_dec, d, T, false);
+  register_tap(h, "dec.tr", h->tok_dec, d, T, false);
 
   // down-sampling conv (replicate pad): reads tok_enc token-major
+  std::vector<ConvCommit> enc_c;
   {
-    ConvLayer& l = h->down;
+    DownLayer& l = h->down;
     l.t_in = T; l.t_out = T / l.stride; l.P = l.k - l.stride;
     B200_TRY(A.alloc_t(&l.state, (size_t)B * l.cin * l.P));
     l.first = h->first_flags;
@@ -923,88 +883,127 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
     cc.x = h->tok_enc; cc.xb = (long long)T * d; cc.xc = 1; cc.xt = d; cc.Tin = T; cc.st = l.state; cc.P = l.P;
     cc.Cin = l.cin; cc.elu_in = 0; cc.first = l.first;
     enc_c.push_back(cc);
-    if (B * l.cin > h->max_enc_rows) h->max_enc_rows = B * l.cin;
+    h->max_enc_rows = B * l.cin;
   }
   // up-sampling depth-wise convtr
+  std::vector<ConvTrCommit> dec_t;
   B200_TRY(A.alloc_t(&h->up_partial, (size_t)B * d * h->rs));
   B200_TRY(A.alloc_t(&h->up_scratch, (size_t)B * d * h->rs));
   {
     ConvTrCommit tc;
     tc.partial = h->up_partial; tc.scratch = h->up_scratch; tc.per_row = d * h->rs;
     dec_t.push_back(tc);
-    if ((long long)B * tc.per_row > h->max_tr_rows) h->max_tr_rows = (long long)B * tc.per_row;
+    h->max_tr_rows = (long long)B * tc.per_row;
   }
   h->n_enc_commits = (int)enc_c.size();
-  h->n_dec_commits = (int)dec_c.size();
   h->n_dec_tr_commits = (int)dec_t.size();
-  h->n_enc_ext = (int)enc_e.size();
-  h->n_dec_ext = (int)dec_e.size();
-  B200_TRY(A.alloc_t(&h->enc_commits, enc_c.size() ? enc_c.size() : 1, false));
-  B200_TRY(A.alloc_t(&h->dec_commits, dec_c.size() ? dec_c.size() : 1, false));
+  h->n_enc_tm = (int)enc_tm.size();
+  h->n_dec_tm = (int)dec_tm.size();
+  B200_TRY(A.alloc_t(&h->enc_commits, enc_c.size(), false));
   B200_TRY(A.alloc_t(&h->dec_tr_commits, dec_t.size(), false));
-  B200_TRY(A.alloc_t(&h->enc_ext_commits, enc_e.size() ? enc_e.size() : 1, false));
-  B200_TRY(A.alloc_t(&h->dec_ext_commits, dec_e.size() ? dec_e.size() : 1, false));
-  if (!enc_c.empty())
-    B200_CUDA(cudaMemcpy(h->enc_commits, enc_c.data(), enc_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
-  if (!dec_c.empty())
-    B200_CUDA(cudaMemcpy(h->dec_commits, dec_c.data(), dec_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
+  B200_TRY(A.alloc_t(&h->enc_tm, enc_tm.size() ? enc_tm.size() : 1, false));
+  B200_TRY(A.alloc_t(&h->dec_tm, dec_tm.size() ? dec_tm.size() : 1, false));
+  B200_CUDA(cudaMemcpy(h->enc_commits, enc_c.data(), enc_c.size() * sizeof(ConvCommit), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(h->dec_tr_commits, dec_t.data(), dec_t.size() * sizeof(ConvTrCommit), cudaMemcpyHostToDevice));
-  if (!enc_e.empty())
-    B200_CUDA(cudaMemcpy(h->enc_ext_commits, enc_e.data(), enc_e.size() * sizeof(ExtCommit), cudaMemcpyHostToDevice));
-  if (!dec_e.empty())
-    B200_CUDA(cudaMemcpy(h->dec_ext_commits, dec_e.data(), dec_e.size() * sizeof(ExtCommit), cudaMemcpyHostToDevice));
+  if (!enc_tm.empty()) B200_CUDA(cudaMemcpy(h->enc_tm, enc_tm.data(), enc_tm.size() * sizeof(TmCommit), cudaMemcpyHostToDevice));
+  if (!dec_tm.empty()) B200_CUDA(cudaMemcpy(h->dec_tm, dec_tm.data(), dec_tm.size() * sizeof(TmCommit), cudaMemcpyHostToDevice));
 
   // transformers
   const int H = c.tr_num_heads, D = d / H, ff = c.tr_dim_feedforward;
-  for (Transformer* tr : {&h->enc_tr, &h->dec_tr}) {
-    B200_TRY(A.alloc_t(&tr->offset, B));
-    for (auto& L : tr->layers) {
-      B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.tr_context * D));
-      B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.tr_context * D));
-    }
-  }
   const size_t ntok = (size_t)B * T;
-  B200_TRY(A.alloc_t(&h->tr_xn, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_xn_hi, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_xn_lo, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_qkv, ntok * 3 * d));
   B200_TRY(A.alloc_t(&h->tr_q, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_ao, ntok * d));
-  B200_TRY(A.alloc_t(&h->tr_h, ntok * ff));
+  B200_TRY(A.alloc_t(&h->tr_ao_hi, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_ao_lo, ntok * d));
+  B200_TRY(A.alloc_t(&h->tr_h_hi, ntok * ff));
+  B200_TRY(A.alloc_t(&h->tr_h_lo, ntok * ff));
+  for (int which = 0; which < 2; ++which) {
+    Transformer* tr = which == 0 ? &h->enc_tr : &h->dec_tr;
+    const float* x_in = which == 0 ? h->tok_in_enc : h->tok_in_dec;
+    float* x = which == 0 ? h->tok_enc : h->tok_dec;
+    B200_TRY(A.alloc_t(&tr->offset, B));
+    for (size_t li = 0; li < tr->layers.size(); ++li) {
+      TrLayer& L = tr->layers[li];
+      B200_TRY(A.alloc_t(&L.kc, (size_t)B * H * c.tr_context * D));
+      B200_TRY(A.alloc_t(&L.vc, (size_t)B * H * c.tr_context * D));
+      const float* cur = li == 0 ? x_in : x;
+      auto lin = [&](mtc::TcLayer& G, const float* in_hi, const float* in_lo, int K, float* y, int N) -> int {
+        memset(&G.p, 0, sizeof(G.p));
+        G.p.epi = mtc::TC_EPI_CONV;
+        G.p.y = y; G.p.y_sb = (long long)T * N; G.p.y_row = N;
+        (void)K;
+        return B200_OK;
+      };
+      // in_proj: qkv = W_in xn
+      B200_TRY(lin(L.in_proj, h->tr_xn_hi, h->tr_xn_lo, d, h->tr_qkv, 3 * d));
+      B200_TRY(plan_layer(h, L.in_proj, h->tr_xn_hi, h->tr_xn_lo, T, 0, T));
+      // out_proj: x = cur + layer_scale_1 * (W_out ao)   (transformer.py:769)
+      B200_TRY(lin(L.out_proj, h->tr_ao_hi, h->tr_ao_lo, d, x, d));
+      L.out_proj.p.epi = mtc::TC_EPI_RES_SCALE; L.out_proj.p.res = cur; L.out_proj.p.r_sb = (long long)T * d; L.out_proj.p.r_row = d;
+      L.out_proj.p.scale = L.ls1;
+      B200_TRY(plan_layer(h, L.out_proj, h->tr_ao_hi, h->tr_ao_lo, T, 0, T));
+      // linear1 + GELU -> h as a hi / lo pair (never stored raw)
+      B200_TRY(lin(L.l1, h->tr_xn_hi, h->tr_xn_lo, d, nullptr, ff));
+      L.l1.p.epi = mtc::TC_EPI_GELU; L.l1.p.act_mode = mtc::TC_ACT_SPLIT; L.l1.p.act_elu = 0;
+      L.l1.p.a_hi = h->tr_h_hi; L.l1.p.a_lo = h->tr_h_lo; L.l1.p.a_sb = (long long)T * ff; L.l1.p.a_row = ff;
+      B200_TRY(plan_layer(h, L.l1, h->tr_xn_hi, h->tr_xn_lo, T, 0, T));
+      // linear2: x = x + layer_scale_2 * (W_2 h)   (transformer.py:777); the decoder's last layer also feeds dec[0]
+      B200_TRY(lin(L.l2, h->tr_h_hi, h->tr_h_lo, ff, x, d));
+      L.l2.p.epi = mtc::TC_EPI_RES_SCALE; L.l2.p.res = x; L.l2.p.r_sb = (long long)T * d; L.l2.p.r_row = d; L.l2.p.scale = L.ls2;
+      if (which == 1 && li + 1 == tr->layers.size()) {
+        const SeaLayer& nx = h->dec[0];
+        L.l2.p.act_mode = mtc::TC_ACT_SPLIT; L.l2.p.act_elu = nx.elu_in ? 1 : 0;
+        L.l2.p.a_hi = nx.ext_hi + (long long)nx.P * nx.cin; L.l2.p.a_lo = nx.ext_lo + (long long)nx.P * nx.cin;
+        L.l2.p.a_sb = (long long)(nx.P + nx.t_in) * nx.cin; L.l2.p.a_row = d;
+      }
+      B200_TRY(plan_layer(h, L.l2, h->tr_h_hi, h->tr_h_lo, T, 0, T));
+    }
+  }
   B200_TRY(A.alloc_t(&h->scratch_codes, (size_t)B * c.q_n_q));
   B200_TRY(A.alloc_t(&h->enc_codes, (size_t)B * c.q_n_q));
   B200_TRY(A.alloc_t(&h->dec_codes, (size_t)B * c.q_n_q));
-  B200_TRY(A.alloc_t(&h->out_frame, (size_t)B * h->frame_size));
   B200_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
   h->body = h->stream;
-  // what a streaming-state snapshot holds (streaming.py:158-181): masks, carried conv samples, overlap-add
-  // partials, both transformers' KV rings and offsets
-  A.mark_state(h->exec_mask, B);
-  A.mark_state(h->first_flags, (size_t)h->n_first * B);
-  for (auto* layers : {&h->enc, &h->dec})
-    for (auto& l : *layers) {
-      if (l.ext && l.kind == 0) A.mark_state(l.ext, (size_t)B * l.cin * l.E * 4);
-      if (l.state) A.mark_state(l.state, (size_t)B * (l.kind == 0 ? l.cin : l.cout) * l.P * 4);
+  // what a streaming-state snapshot holds (streaming.py:158-181): masks, carried conv rows (the transposed convs' carry is
+  // their previous input step), both transformers' KV rings and offsets
+  A.mark_state(h->exec_mask, B, "exec_mask", B200_U8, {B});
+  A.mark_state(h->first_flags, (size_t)h->n_first * B, "downsample.first", B200_U8, {B});
+  for (int which = 0; which < 2; ++which)
+    for (auto& l : which == 0 ? h->enc : h->dec) {
+      const std::string nm = (which == 0 ? "encoder." : "decoder.") + l.key.substr(l.key.find("model."));
+      const int64_t E = l.P + l.t_in;
+      // the whole extended buffer is registered (the frame part is scratch); the shim slices the first P rows out
+      A.mark_state(l.ext_hi, (size_t)B * E * l.cin * 4, nm + ".ext_hi", B200_F32, {B, E, l.cin});
+      if (l.ext_lo) A.mark_state(l.ext_lo, (size_t)B * E * l.cin * 4, nm + ".ext_lo", B200_F32, {B, E, l.cin});
     }
-  A.mark_state(h->down.state, (size_t)B * h->down.cin * h->down.P * 4);
-  A.mark_state(h->up_partial, (size_t)B * d * h->rs * 4);
-  for (Transformer* tr : {&h->enc_tr, &h->dec_tr}) {
-    A.mark_state(tr->offset, (size_t)B * 8);
-    for (auto& L : tr->layers) {
-      A.mark_state(L.kc, (size_t)B * H * c.tr_context * D * 4);
-      A.mark_state(L.vc, (size_t)B * H * c.tr_context * D * 4);
+  A.mark_state(h->down.state, (size_t)B * h->down.cin * h->down.P * 4, "downsample.previous", B200_F32, {B, h->down.cin, h->down.P});
+  A.mark_state(h->up_partial, (size_t)B * d * h->rs * 4, "upsample.partial", B200_F32, {B, d, h->rs});
+  for (int which = 0; which < 2; ++which) {
+    Transformer* tr = which == 0 ? &h->enc_tr : &h->dec_tr;
+    const std::string tp = which == 0 ? "encoder_transformer" : "decoder_transformer";
+    A.mark_state(tr->offset, (size_t)B * 8, tp + ".offset", B200_I64, {B});
+    for (size_t li = 0; li < tr->layers.size(); ++li) {
+      auto& L = tr->layers[li];
+      const std::string p = tp + ".layers." + std::to_string(li);
+      A.mark_state(L.kc, (size_t)B * H * c.tr_context * D * 4, p + ".k", B200_F32, {B, H, c.tr_context, D});
+      A.mark_state(L.vc, (size_t)B * H * c.tr_context * D * 4, p + ".v", B200_F32, {B, H, c.tr_context, D});
     }
   }
   B200_TRY(ensure_rvq_workspace(h, B));
-  h->splitk_bytes = (size_t)16 << 20;
-  B200_TRY(A.alloc(reinterpret_cast<void**>(&h->splitk_ws), h->splitk_bytes, false));
   B200_CUDA(cudaDeviceSynchronize());
-  h->batch = B;
+  cleanup.armed = false;
+  batch_reset.armed = false;
   return B200_OK;
 }
 
 int b200_mimi_streaming_end(b200_mimi* h) {
   if (!h) return B200_OK;
+  DeviceGuard g(h->device);
   if (h->batch > 0) {
     cudaStreamSynchronize(h->stream);
     if (h->gstream) cudaStreamSynchronize(h->gstream);
@@ -1015,6 +1014,7 @@ int b200_mimi_streaming_end(b200_mimi* h) {
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->state.free_all();
+  h->err = nullptr;
   h->batch = 0;
   h->taps.clear();
   return B200_OK;
@@ -1022,6 +1022,7 @@ int b200_mimi_streaming_end(b200_mimi* h) {
 
 int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev) {
   B200_TRY(ensure_streaming(h, "mimi_reset"));
+  DeviceGuard g(h->device);
   const int B = h->batch;
   auto zero = [&](float* buf, long long per_row) {
     if (!buf || per_row <= 0) return;
@@ -1029,15 +1030,10 @@ int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev) {
                 reset_mask_dev, B);
   };
   for (auto* layers : {&h->enc, &h->dec})
-    for (auto& l : *layers) {
-      if (l.kind == 0 && l.fast) {
-        if (l.P > 0)
-          B200_LAUNCH(ext_zero_kernel, (unsigned)ceil_div64((long long)B * l.cin * l.P, 256), 256, 0, h->stream,
-                      l.ext + (l.D0 - l.P), l.P, l.E, l.cin, reset_mask_dev, B);
-      } else {
-        zero(l.state, l.kind == 0 ? (long long)l.cin * l.P : (long long)l.cout * l.P);
-      }
-    }
+    for (auto& l : *layers)
+      if (l.P > 0)
+        B200_LAUNCH(tm_zero_kernel, (unsigned)ceil_div64((long long)B * l.P * l.cin, 256), 256, 0, h->stream, l.ext_hi, l.ext_lo, l.P,
+                    l.cin, (long long)(l.P + l.t_in) * l.cin, reset_mask_dev, B);
   zero(h->down.state, (long long)h->down.cin * h->down.P);
   zero(h->up_partial, (long long)h->cfg.dimension * h->rs);
   B200_LAUNCH(reset_flags_kernel, ceil_div(B, 128), 128, 0, h->stream, h->first_flags, h->n_first, h->enc_tr.offset,
@@ -1047,6 +1043,7 @@ int b200_mimi_reset(b200_mimi* h, const uint8_t* reset_mask_dev) {
 
 int b200_mimi_set_exec_mask(b200_mimi* h, const uint8_t* exec_mask_dev) {
   B200_TRY(ensure_streaming(h, "mimi_set_exec_mask"));
+  DeviceGuard g(h->device);
   if (!exec_mask_dev) B200_FAIL(B200_ERR_INVALID, "mimi_set_exec_mask: null mask");
   B200_CUDA(cudaMemcpyAsync(h->exec_mask, exec_mask_dev, h->batch, cudaMemcpyDeviceToDevice, h->stream));
   return B200_OK;
@@ -1195,28 +1192,66 @@ int b200_mimi_decode_host(b200_mimi* h, const int64_t* codes_host, int n_codeboo
   return B200_OK;
 }
 
+/* the same state entry by entry (names in include/moshi_b200.h) */
+int b200_mimi_state_count(b200_mimi* h) { return (h && h->batch > 0) ? (int)h->state.snap.size() : 0; }
+int b200_mimi_state_entry(b200_mimi* h, int index, const char** name, int* dtype, int* ndim, int64_t* shape8, int64_t* nbytes) {
+  B200_TRY(ensure_streaming(h, "mimi_state_entry"));
+  return state_entry_info(h->state, index, name, dtype, ndim, shape8, nbytes);
+}
+int b200_mimi_state_read(b200_mimi* h, const char* name, void* dst_dev, int64_t nbytes) {
+  B200_TRY(ensure_streaming(h, "mimi_state_read"));
+  DeviceGuard g(h->device);
+  if (!dst_dev) B200_FAIL(B200_ERR_INVALID, "mimi_state_read: null destination");
+  return state_entry_copy(h->state, name, dst_dev, nullptr, nbytes, h->stream);
+}
+int b200_mimi_state_write(b200_mimi* h, const char* name, const void* src_dev, int64_t nbytes) {
+  B200_TRY(ensure_streaming(h, "mimi_state_write"));
+  DeviceGuard g(h->device);
+  if (!src_dev) B200_FAIL(B200_ERR_INVALID, "mimi_state_write: null source");
+  return state_entry_copy(h->state, name, nullptr, src_dev, nbytes, h->stream);
+}
+
+int b200_mimi_error_flags(b200_mimi* h, int* flags_out) {
+  B200_TRY(ensure_streaming(h, "mimi_error_flags"));
+  DeviceGuard g(h->device);
+  int v = 0;
+  B200_CUDA(cudaMemcpyAsync(&v, h->err, 4, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (v) B200_CUDA(cudaMemsetAsync(h->err, 0, 4, h->stream));
+  if (flags_out) *flags_out = v;
+  return B200_OK;
+}
+
 int b200_mimi_read_buffer(b200_mimi* h, const char* name, float* dst_dev, int64_t capacity, int64_t* numel) {
   B200_TRY(ensure_streaming(h, "mimi_read_buffer"));
+  DeviceGuard g(h->device);
   auto it = h->taps.find(name ? name : "");
   if (it == h->taps.end()) B200_FAIL(B200_ERR_INVALID, "mimi_read_buffer: unknown buffer '%s'", name ? name : "(null)");
-  if (numel) *numel = it->second.second;
+  const Tap& t = it->second;
+  const int64_t n = (int64_t)h->batch * t.C * t.T;
+  if (numel) *numel = n;
   if (!dst_dev) return B200_OK;
-  if (capacity < it->second.second) B200_FAIL(B200_ERR_SHAPE, "mimi_read_buffer: destination too small");
-  B200_CUDA(cudaMemcpyAsync(dst_dev, it->second.first, (size_t)it->second.second * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (capacity < n) B200_FAIL(B200_ERR_SHAPE, "mimi_read_buffer: destination too small");
+  if (t.transpose && t.T > 1) {        // stored token-major [B][T][C], reported in the reference's [B][C][T]
+    B200_LAUNCH(tm_to_bct_kernel, (unsigned)ceil_div64(n, 256), 256, 0, h->stream, t.p, dst_dev, h->batch, t.C, t.T);
+    return check_launch("mimi_read_buffer");
+  }
+  B200_CUDA(cudaMemcpyAsync(dst_dev, t.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->stream));
   return B200_OK;
 }
 
 int64_t b200_mimi_algorithmic_bytes(b200_mimi* h) {
   if (!h || h->batch <= 0) return 0;
   const auto& c = h->cfg;
-  // weights once per step (encode + decode) + active codebooks (row-major for decode, transposed for encode)
+  // weights once per step (encode + decode; the tensor-core layers hold a hi and a lo copy: 8 bytes per parameter) + active
+  // codebooks (row-major for decode, transposed for encode)
   int64_t bytes = h->weight_bytes;
   bytes += (int64_t)2 * h->num_codebooks * c.q_bins * c.q_dimension * 4 + (int64_t)4 * c.q_dimension * c.dimension * 4;
-  // per session: both transformer KV rings read once, conv/convtr carried state read + written, PCM in/out
+  // per session: both transformer KV rings read once, carried conv rows read + written (hi and lo), PCM in/out
   int64_t per_row = (int64_t)2 * c.tr_num_layers * 2 * c.tr_context * c.tr_d_model * 4;
   int64_t st = 0;
   for (auto* layers : {&h->enc, &h->dec})
-    for (auto& l : *layers) st += (l.kind == 0 ? (int64_t)l.cin * l.P : (int64_t)l.cout * l.P);
+    for (auto& l : *layers) st += (int64_t)l.cin * l.P * (l.ext_lo ? 2 : 1);
   st += (int64_t)h->down.cin * h->down.P + (int64_t)c.dimension * h->rs;
   per_row += 2 * st * 4 + (int64_t)2 * h->frame_size * 4 + h->num_codebooks * 8;
   return bytes + per_row * h->batch;

@@ -579,6 +579,8 @@ struct RvqDecArgs {
   int levels[2]; int level_offset[2];
   float* out; long long ob, oc, ot;          // [B][Cout][n] via strides
   int Dq, Cout, bins;
+  int* err;                                  // device error flags: a code outside [0, bins) decodes as the zero vector and
+                                             // raises bit 2 (the reference indexes F.embedding: "dramatic CUDA crash", vq.py:144-145)
 };
 // grid (B * n_frames, ceil(Cout / 64)), 256 threads = 64 output channels x 4 slices of the Dq-long dot products: the
 // dependent FMA chain per thread is Dq / 2 long instead of 2 * Dq, and a single session still spreads over 8 CTAs.
@@ -592,7 +594,8 @@ static __global__ void __launch_bounds__(256) rvq_decode_kernel(const RvqDecArgs
       float s = 0.f;
       for (int level = 0; level < a.levels[which]; ++level) {
         const long long idx = a.codes[b * a.cs_b + (a.level_offset[which] + level) * a.cs_k + f * a.cs_f];
-        s += a.cb[which][((long long)level * a.bins + idx) * a.Dq + d];
+        if (idx >= 0 && idx < a.bins) s += a.cb[which][((long long)level * a.bins + idx) * a.Dq + d];
+        else if (a.err != nullptr && d == 0) atomicOr(a.err, 2);
       }
       sm[which * a.Dq + d] = s;
     }

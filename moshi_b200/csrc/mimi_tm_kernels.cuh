@@ -1,0 +1,178 @@
+// Token-major helper kernels around mimi_tc_kernel: the two degenerate SEANet convolutions (Cin = 1 at the encoder's
+// mouth, Cout = 1 at the decoder's), streaming-state commits / resets inside the extended input buffers, LayerNorm with a
+// split (hi / lo) output, load-time weight re-layouts and the layout conversions of the debug taps.
+#pragma once
+
+#include "common.cuh"
+#include "mimi_tc.cuh"
+
+namespace b200 {
+namespace mimi {
+
+// ---------------------------------------------------------------------------------------------
+// First encoder conv (Cin = 1, K <= 8; seanet.py:170-178): memory-bound, one thread per (b, t) produces all Cout channels.
+//   in: ext[b][P + T] fp32 (carried samples | frame);  out: raw y[b][t][co] and the consumer's ELU(y) as a hi / lo pair
+// ---------------------------------------------------------------------------------------------
+struct ConvFirst {
+  const float* ext; int E, P;                // [B][E]
+  const float* w; const float* bias;         // [Cout][K], [Cout]
+  float* y; long long y_sb;                  // [B][T][Cout]
+  float *a_hi, *a_lo; long long a_sb; int a_elu;      // consumer ext (+ its carried rows), row stride Cout
+  int B, Cout, K, T;
+};
+static __global__ void __launch_bounds__(128) conv_first_tm_kernel(const ConvFirst p) {
+  extern __shared__ float sw[];              // [K][Cout] then bias [Cout]
+  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[(i % p.K) * p.Cout + i / p.K] = p.w[i];
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[p.Cout * p.K + i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)p.B * p.T) return;
+  const int b = (int)(n / p.T), t = (int)(n - (long long)b * p.T);
+  float xin[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xin[k] = k < p.K ? p.ext[(long long)b * p.E + t + k] : 0.f;       // cat(previous, x)[t + k]
+  float* y = p.y + (long long)b * p.y_sb + (long long)t * p.Cout;
+  float* ah = p.a_hi + (long long)b * p.a_sb + (long long)t * p.Cout;
+  float* al = p.a_lo + (long long)b * p.a_sb + (long long)t * p.Cout;
+  for (int c0 = 0; c0 < p.Cout; c0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = sw[p.Cout * p.K + c0 + j];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < p.K) acc = fmaf(sw[k * p.Cout + c0 + j], xin[k], acc);
+      v[j] = acc;
+    }
+    *reinterpret_cast<float4*>(y + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mtc::split_tf32(p.a_elu ? elu1(v[j]) : v[j], hi[j], lo[j]);
+    *reinterpret_cast<float4*>(ah + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(al + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Last decoder conv (Cout = 1; seanet.py:380-388): one thread per (b, t) reduces over (tap, ci) from a plain fp32 ext
+struct ConvLast {
+  const float* ext; long long e_sb; int Cin;  // [B][P + T][Cin], activation already applied
+  const float* w;                             // [K][Cin]
+  const float* bias;
+  float* y; long long y_sb;                   // [B][T]
+  int B, K, dil, T;
+};
+static __global__ void __launch_bounds__(128) conv_last_tm_kernel(const ConvLast p) {
+  extern __shared__ float sw[];               // [K * Cin]
+  for (int i = threadIdx.x; i < p.K * p.Cin; i += blockDim.x) sw[i] = p.w[i];
+  __syncthreads();
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)p.B * p.T) return;
+  const int b = (int)(n / p.T), t = (int)(n - (long long)b * p.T);
+  float acc = p.bias ? p.bias[0] : 0.f;
+  for (int kw = 0; kw < p.K; ++kw) {
+    const float4* e = reinterpret_cast<const float4*>(p.ext + (long long)b * p.e_sb + (long long)(t + kw * p.dil) * p.Cin);
+    const float* wk = sw + kw * p.Cin;
+    for (int c4 = 0; c4 < p.Cin / 4; ++c4) {
+      const float4 v = e[c4];
+      acc = fmaf(wk[4 * c4], v.x, acc); acc = fmaf(wk[4 * c4 + 1], v.y, acc);
+      acc = fmaf(wk[4 * c4 + 2], v.z, acc); acc = fmaf(wk[4 * c4 + 3], v.w, acc);
+    }
+  }
+  p.y[(long long)b * p.y_sb + t] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming state inside the extended input buffers.  StreamingConv1d (conv.py:263-267): previous <- the last P rows of
+// cat(previous, x) = rows [T, T + P) -> rows [0, P), for sessions with exec_mask.  StreamingConvTranspose1d's overlap-add carry
+// (conv.py:349-361) is the same thing with P = 1 (the last input step).  Buffers are described once per direction.
+// ---------------------------------------------------------------------------------------------
+struct TmCommit { float* hi; float* lo; int P, T, rowlen; long long sb; };       // rowlen = Cin floats per row
+static __global__ void tm_commit_kernel(const TmCommit* descs, const uint8_t* exec_mask, int B) {
+  const TmCommit d = descs[blockIdx.y];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, ci)
+  if (i >= (long long)B * d.rowlen) return;
+  const int b = (int)(i / d.rowlen), ci = (int)(i - (long long)b * d.rowlen);
+  if (!exec_mask[b]) return;
+  float* h = d.hi + (long long)b * d.sb + ci;
+  for (int j = 0; j < d.P; ++j) h[(long long)j * d.rowlen] = h[(long long)(d.T + j) * d.rowlen];      // ascending: reads stay ahead of writes
+  if (d.lo != nullptr) {
+    float* l = d.lo + (long long)b * d.sb + ci;
+    for (int j = 0; j < d.P; ++j) l[(long long)j * d.rowlen] = l[(long long)(d.T + j) * d.rowlen];
+  }
+}
+// reset (conv.py:166-169, 281-286): zero the carried rows of the sessions in mask (null = all)
+static __global__ void tm_zero_kernel(float* hi, float* lo, int P, int rowlen, long long sb, const uint8_t* mask, int B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)P * rowlen;
+  if (i >= (long long)B * per) return;
+  const int b = (int)(i / per);
+  if (mask != nullptr && !mask[b]) return;
+  const long long o = (long long)b * sb + (i - (long long)b * per);
+  hi[o] = 0.f;
+  if (lo != nullptr) lo[o] = 0.f;
+}
+
+// LayerNorm (eps 1e-5, affine; transformer.py:126) -> the following linear's input as a hi / lo pair
+static __global__ void layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
+                                       float* __restrict__ y_hi, float* __restrict__ y_lo, int n_tok, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_tok) return;
+  const float* xr = x + (long long)warp * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = xr[c] - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float hi, lo;
+    mtc::split_tf32((xr[c] - mean) * rstd * g[c] + bta[c], hi, lo);
+    y_hi[(long long)warp * C + c] = hi;
+    y_lo[(long long)warp * C + c] = lo;
+  }
+}
+
+// x -> (hi, lo), element-wise (attention output in front of out_proj)
+static __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float h, l;
+  mtc::split_tf32(x[i], h, l);
+  hi[i] = h; lo[i] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// load-time weight re-layouts to [N][tap][Cin] (the order mimi_tc's k-blocks walk)
+//   conv   [Cout][Cin][K]  -> [Cout][K][Cin]
+//   convtr [Cin][Cout][2S] -> [(r, co)][slot][Cin], slot 0 = x[t-1] (kernel taps S + r), slot 1 = x[t] (kernel taps r)
+// ---------------------------------------------------------------------------------------------
+static __global__ void tm_weight_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * K) return;
+  const int kw = (int)(i % K);
+  const long long r = i / K;
+  const int ci = (int)(r % Cin), co = (int)(r / Cin);
+  out[((long long)co * K + kw) * Cin + ci] = w[i];
+}
+static __global__ void tm_weight_convtr_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cin * Cout * 2 * S) return;
+  const int k = (int)(i % (2 * S));
+  const long long r = i / (2 * S);
+  const int co = (int)(r % Cout), ci = (int)(r / Cout);
+  const int tap = k / S, ph = k - tap * S;            // kernel tap 0 multiplies x[t], tap 1 multiplies x[t-1]
+  out[((long long)(ph * Cout + co) * 2 + (1 - tap)) * Cin + ci] = w[i];
+}
+
+// debug taps / reference layouts: y[b][c][t] = ytm[b][t][c]
+static __global__ void tm_to_bct_kernel(const float* __restrict__ ytm, float* __restrict__ y, int B, int C, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C * T) return;
+  const int t = (int)(i % T);
+  const long long r = i / T;
+  const int c = (int)(r % C), b = (int)(r / C);
+  y[i] = ytm[((long long)b * T + t) * C + c];
+}
+
+}  // namespace mimi
+}  // namespace b200

@@ -2,6 +2,7 @@
 #include "gemm_sk.cuh"
 #include "lm_kernels.cuh"
 #include "mimi_kernels.cuh"
+#include "mimi_tc.cuh"
 
 using namespace b200;
 
@@ -229,6 +230,174 @@ int b200_op_attn_step_q8(const void* qkv_dev, void* k8_dev, void* v8_dev, float*
   if (kv_dtype == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
   else B200_LAUNCH(attn_step_q8_kernel<KV_E4M3>, grid, ATT_THREADS, 0, st, a);
   return check_launch("op_attn_step_q8");
+}
+
+}  // extern "C"
+
+// ---- mimi_tc_kernel on the reference's [B, C, T] layout (test scaffolding: the handle keeps everything token-major) --------
+namespace {
+
+// ext[b][j][ci] (hi / lo) = cat(previous, act(x))[b][ci][j]  for j < P + T
+__global__ void tm_pack_in_kernel(const float* __restrict__ x, const float* __restrict__ prev, float* __restrict__ hi, float* __restrict__ lo,
+                                  int B, int Cin, int T, int P, int elu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long E = P + T;
+  if (i >= (long long)B * E * Cin) return;
+  const int ci = (int)(i % Cin);
+  const long long r = i / Cin;
+  const int j = (int)(r % E), b = (int)(r / E);
+  float v;
+  if (j < P) v = prev ? prev[((long long)b * Cin + ci) * P + j] : 0.f;
+  else { v = x[((long long)b * Cin + ci) * T + (j - P)]; v = elu ? elu1(v) : v; }
+  float h, l;
+  b200::mtc::split_tf32(v, h, l);
+  hi[i] = h; lo[i] = l;
+}
+// y[b][c][t] = ytm[b][t][c]
+__global__ void tm_unpack_out_kernel(const float* __restrict__ ytm, float* __restrict__ y, int B, int C, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C * T) return;
+  const int t = (int)(i % T);
+  const long long r = i / T;
+  const int c = (int)(r % C), b = (int)(r / C);
+  y[i] = ytm[((long long)b * T + t) * C + c];
+}
+// previous[b][ci][j] <- (hi + lo)[b][T + j][ci] for rows with exec_mask (conv.py:263-267)
+__global__ void tm_commit_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ prev,
+                                 const uint8_t* __restrict__ exec_mask, int B, int Cin, int T, int P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Cin * P) return;
+  const int j = (int)(i % P);
+  const long long r = i / P;
+  const int ci = (int)(r % Cin), b = (int)(r / Cin);
+  if (exec_mask && !exec_mask[b]) return;
+  const long long o = ((long long)b * (P + T) + T + j) * Cin + ci;
+  prev[i] = hi[o] + lo[o];
+}
+// conv [Cout][Cin][K] -> [Cout][K][Cin];  convtr [Cin][Cout][2S] -> [(r, co)][tap'][ci] with tap' = 0: x[t-1] (kernel taps S + r), 1: x[t]
+__global__ void tm_weight_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * K) return;
+  const int kw = (int)(i % K);
+  const long long r = i / K;
+  const int ci = (int)(r % Cin), co = (int)(r / Cin);
+  out[((long long)co * K + kw) * Cin + ci] = w[i];
+}
+__global__ void tm_weight_convtr_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cin * Cout * 2 * S) return;
+  const int k = (int)(i % (2 * S));
+  const long long r = i / (2 * S);
+  const int co = (int)(r % Cout), ci = (int)(r / Cout);
+  const int tap = k / S, ph = k - tap * S;            // tap 0 multiplies x[t], tap 1 multiplies x[t-1]
+  const int n = ph * Cout + co, slot = 1 - tap;       // rows of the A operand: slot 0 = x[t-1], slot 1 = x[t]
+  out[((long long)n * 2 + slot) * Cin + ci] = w[i];
+}
+
+struct DevBufs {
+  std::vector<void*> p;
+  ~DevBufs() { for (void* q : p) cudaFree(q); }
+  template <class T> int get(T** out, size_t n) {
+    void* q = nullptr;
+    B200_CUDA(cudaMalloc(&q, n ? n : 1));
+    p.push_back(q);
+    *out = static_cast<T*>(q);
+    return B200_OK;
+  }
+};
+
+int tc_tile_shape(int T, int* tt, int* bb) {
+  for (int c = 128; c >= 1; c >>= 1)
+    if (T % c == 0) { *tt = c; *bb = 128 / c; return B200_OK; }
+  return B200_ERR_SHAPE;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_op_tc_linear_f32(const float* x_dev, const float* w_dev, float* y_dev, int M, int N, int K, void* stream) {
+  using namespace b200::mtc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!x_dev || !w_dev || !y_dev || M < 1 || K % 32 || N % 16) B200_FAIL(B200_ERR_SHAPE, "op_tc_linear_f32: bad shape");
+  B200_TRY(tc_init());
+  DevBufs d;
+  float *hi, *lo, *ws; uint8_t* wt;
+  B200_TRY(d.get(&hi, (size_t)M * K * 4));
+  B200_TRY(d.get(&lo, (size_t)M * K * 4));
+  B200_TRY(d.get(&wt, tc_packed_bytes(N, K, 1)));
+  const size_t ws_bytes = (size_t)64 << 20;
+  B200_TRY(d.get(&ws, ws_bytes));
+  const long long n = (long long)M * K;
+  // x is already [M][K] token-major: a flat hi/lo split is tm_pack_in with B = M "sessions" of Cin = K, T = 1, P = 0
+  B200_LAUNCH(tm_pack_in_kernel, (unsigned)ceil_div64(n, 256), 256, 0, st, x_dev, (const float*)nullptr, hi, lo, M, K, 1, 0, 0);
+  B200_TRY(tc_pack_weights(w_dev, wt, N, K, 1, st));
+  TcLayer L;
+  L.kind = 2; L.Cin = K; L.N = N; L.n_taps = 1; L.wt = wt;
+  L.NT = N >= TC_MAX_NT ? TC_MAX_NT : N; L.n_tiles_n = (N + L.NT - 1) / L.NT; L.num_kb = K / TC_KB;
+  memset(&L.p, 0, sizeof(L.p));
+  L.p.tt = 128; L.p.bb = 1; L.p.row0 = 0;
+  L.p.epi = TC_EPI_CONV; L.p.y = y_dev; L.p.y_sb = 0; L.p.y_row = N; L.p.ws = ws;
+  B200_TRY(tc_make_map(&L.map_hi, hi, K, M, (long long)M * K, 1, 128, 1, 1));
+  B200_TRY(tc_make_map(&L.map_lo, lo, K, M, (long long)M * K, 1, 128, 1, 1));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  B200_TRY(tc_plan(L, 1, M, sms, ws_bytes));
+  B200_TRY(tc_launch(L, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return B200_OK;
+}
+
+int b200_op_tc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev, const uint8_t* exec_mask_dev,
+                      float* y_dev, int B, int Cin, int Cout, int T, int K, int stride, int dilation, int elu_in, int transposed,
+                      void* stream) {
+  using namespace b200::mtc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_TRY(tc_init());
+  // transposed: ConvTranspose1d with K == 2 * stride as two taps over [x[t-1], x[t]] (P = 1 carried input row, N = S * Cout)
+  const int n_taps = transposed ? 2 : K, S = stride;
+  const int P = transposed ? 1 : (K - 1) * dilation + 1 - stride;
+  const int Tout = transposed ? T : T / stride;               // GEMM rows per session
+  const int N = transposed ? S * Cout : Cout;
+  if (Cin % 32 || N % 16 || (N > 128 && N % 128) || P < 0 || (!transposed && T % stride) || (transposed && K != 2 * S))
+    B200_FAIL(B200_ERR_SHAPE, "op_tc_conv1d: unsupported shape");
+  DevBufs d;
+  float *hi, *lo, *ws, *wk, *ytm; uint8_t* wt;
+  const size_t E = (size_t)P + T;
+  B200_TRY(d.get(&hi, (size_t)B * E * Cin * 4));
+  B200_TRY(d.get(&lo, (size_t)B * E * Cin * 4));
+  B200_TRY(d.get(&wk, (size_t)N * n_taps * Cin * 4));
+  B200_TRY(d.get(&wt, tc_packed_bytes(N, Cin, n_taps)));
+  B200_TRY(d.get(&ytm, (size_t)B * Tout * N * 4));
+  const size_t ws_bytes = (size_t)64 << 20;
+  B200_TRY(d.get(&ws, ws_bytes));
+  const long long n_in = (long long)B * E * Cin, n_w = (long long)N * n_taps * Cin;
+  B200_LAUNCH(tm_pack_in_kernel, (unsigned)ceil_div64(n_in, 256), 256, 0, st, x_dev, (const float*)prev_dev, hi, lo, B, Cin, T, P, elu_in);
+  if (transposed) B200_LAUNCH(tm_weight_convtr_kernel, (unsigned)ceil_div64(n_w, 256), 256, 0, st, w_dev, wk, Cin, Cout, S);
+  else B200_LAUNCH(tm_weight_conv_kernel, (unsigned)ceil_div64(n_w, 256), 256, 0, st, w_dev, wk, Cout, Cin, K);
+  B200_TRY(tc_pack_weights(wk, wt, N, Cin, n_taps, st));
+  TcLayer L;
+  L.kind = transposed ? 1 : 0; L.Cin = Cin; L.N = N; L.n_taps = n_taps; L.dil = transposed ? 1 : dilation; L.stride = transposed ? 1 : stride;
+  L.wt = wt; L.bias = bias_dev; L.bias_mod = Cout;
+  L.NT = N >= TC_MAX_NT ? TC_MAX_NT : N; L.n_tiles_n = (N + L.NT - 1) / L.NT; L.num_kb = n_taps * (Cin / TC_KB);
+  memset(&L.p, 0, sizeof(L.p));
+  if (tc_tile_shape(Tout, &L.p.tt, &L.p.bb) != B200_OK) B200_FAIL(B200_ERR_SHAPE, "op_tc_conv1d: T");
+  while (L.p.tt * L.stride > 256) { L.p.tt /= 2; L.p.bb *= 2; }
+  L.p.row0 = 0;
+  L.p.epi = TC_EPI_CONV; L.p.y = ytm; L.p.y_sb = (long long)Tout * N; L.p.y_row = N; L.p.ws = ws;
+  B200_TRY(tc_make_map(&L.map_hi, hi, Cin, (long long)E, (long long)E * Cin, B, L.p.tt, L.p.bb, L.stride));
+  B200_TRY(tc_make_map(&L.map_lo, lo, Cin, (long long)E, (long long)E * Cin, B, L.p.tt, L.p.bb, L.stride));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  B200_TRY(tc_plan(L, B, Tout, sms, ws_bytes));
+  B200_TRY(tc_launch(L, st));
+  // token-major [B][Tout][N] -> the reference layout: conv [B][Cout][Tout]; convtr [B][Cout][Tout * S] (row t holds S steps of Cout)
+  const int Tr = transposed ? Tout * S : Tout;
+  B200_LAUNCH(tm_unpack_out_kernel, (unsigned)ceil_div64((long long)B * Cout * Tr, 256), 256, 0, st, ytm, y_dev, B, Cout, Tr);
+  if (P > 0 && prev_dev)
+    B200_LAUNCH(tm_commit_kernel, (unsigned)ceil_div64((long long)B * Cin * P, 256), 256, 0, st, hi, lo, prev_dev, exec_mask_dev, B, Cin, T, P);
+  B200_CUDA(cudaStreamSynchronize(st));
+  return check_launch("op_tc_conv1d");
 }
 
 int b200_op_sample(const void* logits_bf16_dev, const float* noise_dev, int64_t* out_dev, int B, int card,

@@ -34,8 +34,9 @@ def main() -> None:
     ref.load_state_dict(sd, strict=True)
     B, steps = scenarios.LM_B, scenarios.LM_STEPS
     codes = scenarios.lm_input_codes(cfg, B, steps)
-    logits_rec = []
-    gen = LMGen(ref, use_sampling=True, temp=0.8, temp_text=0.7, on_text_logits_hook=lambda t: logits_rec.append(t.float().clone()))
+    logits_rec, text_rec, audio_rec = [], [], []
+    gen = LMGen(ref, use_sampling=True, temp=0.8, temp_text=0.7, on_text_logits_hook=lambda t: logits_rec.append(t.float().clone()),
+                on_text_hook=lambda t: text_rec.append(t.clone()), on_audio_hook=lambda t: audio_rec.append(t.clone()))
     outs = []
     torch.manual_seed(scenarios.LM_NOISE_SEED)
     with gen.streaming(B):
@@ -56,7 +57,9 @@ def main() -> None:
     agree = bool((torch.stack(o_outs) == tokens).all())
     tl = torch.stack(logits_rec)[:, :, 0, 0]
     golden = ROOT / "tests" / "golden"
-    save_file({"tokens": tokens, "text_logits": tl}, golden / "lm_tiny_sampled_peaked.safetensors")
+    # the raw decision of every sampler call (lm.py:736-757 hooks): text [steps, B], audio [steps, B, dep_q]
+    save_file({"tokens": tokens, "text_logits": tl, "sampled_text": torch.stack(text_rec), "sampled_audio": torch.stack(audio_rec)},
+              golden / "lm_tiny_sampled_peaked.safetensors")
     info = {"generated_by": "oracle/gen_golden_peaked.py", "torch": torch.__version__, "oracle_bit_exact_tokens": agree, "B": B,
             "steps": steps, "none_marker": -3, "peak_gain": scenarios.PEAK_GAIN, "text_logits_std": float(tl.std()),
             "distinct_text_tokens": int(tokens[:, :, 0].unique().numel())}
