@@ -41,7 +41,7 @@ enum {
   B200_ERR_MISSING = 5    /* finalize: a required tensor was never loaded                  */
 };
 
-enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_I64 = 3, B200_U8 = 4 };
+enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_I64 = 3, B200_U8 = 4, B200_I8 = 5 };
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
@@ -179,7 +179,10 @@ typedef struct {
 /* Family limits: n_q <= 32, 0 <= dep_q <= 16 (dep_q = 0: no depformer, lm.py:219-222), temporal head dim 128, depformer head
  * dim 64, vocabularies < 65535: covers configs/moshi_7b_202409.json, configs/moshi_dev_2b.json and the STT checkpoints. */
 
-/* loaders.get_moshi_lm (loaders.py:366-446). Tensors are bf16 with the reference's key names. */
+/* loaders.get_moshi_lm (loaders.py:366-446). Tensors are bf16 with the reference's key names.  With cfg.quantize a linear may
+ * instead arrive pre-quantised, the way `model.q8.safetensors` stores a QLinear (loaders.py:33; utils/quantize.py:16-21):
+ * "<linear>.weight" B200_I8 [out, in] (CB) + "<linear>.weight_scb" B200_F32 [out] (SCB, the row absmax); such tensors are
+ * tiled as they are, nothing is re-quantised. */
 int b200_lm_create(const b200_lm_config* cfg, b200_lm** out);
 int b200_lm_load_tensor(b200_lm* h, const char* name, const void* data_dev, int dtype,
                         int ndim, const int64_t* shape);

@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "_C" / "libmoshi_b200.so"
 
 B200_OK, B200_ERR_INVALID, B200_ERR_SHAPE, B200_ERR_STATE, B200_ERR_CUDA, B200_ERR_MISSING = range(6)
-B200_F32, B200_BF16, B200_F16, B200_I64, B200_U8 = range(5)
+B200_F32, B200_BF16, B200_F16, B200_I64, B200_U8, B200_I8 = range(6)
 ABI_VERSION = 2
 
 
@@ -181,7 +181,7 @@ def dtype_code(t) -> int:
     if _DTYPES is None:
         import torch
         _DTYPES = {torch.float32: B200_F32, torch.bfloat16: B200_BF16, torch.float16: B200_F16,
-                   torch.int64: B200_I64, torch.uint8: B200_U8, torch.bool: B200_U8}
+                   torch.int64: B200_I64, torch.uint8: B200_U8, torch.bool: B200_U8, torch.int8: B200_I8}
     return _DTYPES[t]
 
 

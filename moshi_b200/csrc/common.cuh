@@ -81,6 +81,7 @@ inline size_t dtype_size(int dtype) {
     case B200_F16: return 2;
     case B200_I64: return 8;
     case B200_U8: return 1;
+    case B200_I8: return 1;
   }
   return 0;
 }

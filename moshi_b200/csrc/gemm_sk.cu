@@ -862,6 +862,34 @@ __global__ void pack_tiles_i8_kernel(const __nv_bfloat16* __restrict__ w, const 
   }
   out[idx] = make_uint4(words[0], words[1], words[2], words[3]);
 }
+// already-quantised weights (a QLinear's CB as stored in model.q8.safetensors): q int8 [rows][K] -> the same int8 tiles
+__global__ void pack_tiles_i8_pre_kernel(const int8_t* __restrict__ q, uint4* __restrict__ out, int rows, int K, int n_tiles, int num_kb,
+                                         int a_tiles, int gate_rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_tiles * num_kb * a_tiles * (TILE_BYTES / 16);
+  if (idx >= total) return;
+  const int chunk = (int)(idx % (TILE_BYTES / 16));
+  long long t = idx / (TILE_BYTES / 16);
+  const int a = (int)(t % a_tiles); t /= a_tiles;
+  const int kb = (int)(t % num_kb);
+  const int tile = (int)(t / num_kb);
+  const int r = chunk >> 3, cpos = chunk & 7;
+  const int csrc = cpos ^ (r & 7);
+  const int limit = a_tiles == 2 ? gate_rows : rows;
+  const int rr = tile * BLOCK_ROWS + r;
+  const int k0 = kb * 128 + csrc * 16;
+  uint32_t words[4] = {0u, 0u, 0u, 0u};
+  if (rr < limit) {
+    const long long srow = (long long)(rr + a * gate_rows);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = k0 + j;
+      const int v = k < K ? (int)q[srow * K + k] : 0;
+      words[j >> 2] |= (uint32_t)(v & 0xFF) << (8 * (j & 3));
+    }
+  }
+  out[idx] = make_uint4(words[0], words[1], words[2], words[3]);
+}
 // activations: x [M][K] bf16 (row stride ldx) -> xq int8 [M][K], sa[m] = absmax of the row
 __global__ void __launch_bounds__(256) quantize_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int8_t* __restrict__ xq,
                                                            float* __restrict__ sa, int K) {
@@ -987,6 +1015,19 @@ int sk_quant_pack_weights(const __nv_bfloat16* w, void* out_tiles, float* out_sc
                                                                            n_tiles, num_kb, a, epi == EPI_GATE ? gate_rows : 0);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return check_launch("quant_pack_tiles");
+}
+
+int sk_pack_weights_i8(const int8_t* q, void* out_tiles, int N, int K, int epi, int gate_rows, cudaStream_t stream) {
+  if (K % 16) B200_FAIL(B200_ERR_SHAPE, "sk_pack_weights_i8: K must be a multiple of 16");
+  const int a = epi == EPI_GATE ? 2 : 1;
+  const int w_rows = epi == EPI_GATE ? 2 * gate_rows : N;
+  const int rows = epi == EPI_GATE ? gate_rows : N;
+  const int n_tiles = (rows + BLOCK_ROWS - 1) / BLOCK_ROWS, num_kb = (K + 127) / 128;
+  const long long total = (long long)n_tiles * num_kb * a * (TILE_BYTES / 16);
+  pack_tiles_i8_pre_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(q, static_cast<uint4*>(out_tiles), w_rows, K, n_tiles, num_kb,
+                                                                              a, epi == EPI_GATE ? gate_rows : 0);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("pack_tiles_i8_pre");
 }
 
 int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream, int pdl) {

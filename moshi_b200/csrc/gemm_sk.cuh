@@ -59,6 +59,8 @@ size_t sk_workspace_bytes(int max_M);
 size_t sk_packed_bytes_i8(int N, int K, int epi, int gate_rows);
 int sk_quant_pack_weights(const __nv_bfloat16* w, void* out_tiles, float* out_scales, int N, int K, int epi, int gate_rows,
                           cudaStream_t stream);
+// weights that arrive already quantised (QLinear CB int8 [N][K] of a q8 checkpoint): tiled as they are
+int sk_pack_weights_i8(const int8_t* q, void* out_tiles, int N, int K, int epi, int gate_rows, cudaStream_t stream);
 int sk_quantize_rows(const __nv_bfloat16* x, long long ldx, void* xq, float* sa, int M, int K, cudaStream_t stream, int pdl = 0);
 constexpr int SK_MAX_GRID = 304;     // 2 CTAs per SM at most
 constexpr int SK_MAX_TILES = 1024;   // ints in the arrival-counter array

@@ -152,15 +152,46 @@ int norm_linear(b200_lm* h, const bf16* x, const bf16* alpha, bf16* xn, const bf
   return linear(h, xn, K, w, y, ldy, nullptr, 0, M, N, K, epi, gate_rows, w_scales);
 }
 
+// A QLinear as model.q8.safetensors stores it (utils/quantize.py:16-21): "<name>" int8 [rows][K] + "<name>_scb" fp32 [rows]
+int get_prequantised(b200_lm* h, const std::string& name, int rows, int K, const int8_t** q, const float** scb) {
+  const Tensor* t = h->store.find(name);
+  const Tensor* s = h->store.find(name + "_scb");
+  if (!h->cfg.quantize) B200_FAIL(B200_ERR_INVALID, "lm tensor '%s' is int8 but the model was not built with quantize=True", name.c_str());
+  if (!s || s->dtype != B200_F32) B200_FAIL(B200_ERR_MISSING, "lm finalize: '%s_scb' (float32 row scales of the int8 weight) was not loaded; "
+                                            "care should be taken not to change its dtype (utils/quantize.py:31-35)", name.c_str());
+  if (t->shape != std::vector<int64_t>{rows, K} || s->shape != std::vector<int64_t>{rows})
+    B200_FAIL(B200_ERR_SHAPE, "lm tensor '%s' / its _scb: expected [%d, %d] / [%d]", name.c_str(), rows, K, rows);
+  *q = static_cast<const int8_t*>(t->data);
+  *scb = static_cast<const float*>(s->data);
+  return B200_OK;
+}
+
 // Linear weight from the store -> packed tiles (gemm_sk.cu), which replace the row-major
 // tensor (which is released), so the 15.4 GB checkpoint is resident once.
 int get_linear(b200_lm* h, const std::string& name, int N, int K, int epi, int gate_rows, const bf16** out,
                const float** scales_out) {
-  const bf16* w = nullptr;
   const int w_rows = epi == LIN_GATE ? 2 * gate_rows : N;
-  B200_TRY(get_bf16(h, name, {w_rows, K}, &w));
   *scales_out = nullptr;
   void* packed = nullptr;
+  const Tensor* t = h->store.find(name);
+  if (t && t->dtype == B200_I8) {      // pre-quantised checkpoint: tile CB as it is, keep SCB
+    const int8_t* q = nullptr; const float* scb = nullptr;
+    B200_TRY(get_prequantised(h, name, w_rows, K, &q, &scb));
+    float* scales = nullptr;
+    B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes_i8(N, K, epi, gate_rows), false));
+    B200_TRY(h->weights.alloc_t(&scales, (size_t)w_rows, false));
+    B200_TRY(tc::sk_pack_weights_i8(q, packed, N, K, epi, gate_rows, nullptr));
+    B200_CUDA(cudaMemcpy(scales, scb, (size_t)w_rows * 4, cudaMemcpyDeviceToDevice));
+    *scales_out = scales;
+    h->weight_bytes += (int64_t)w_rows * K + (int64_t)w_rows * 4;
+    B200_CUDA(cudaStreamSynchronize(nullptr));
+    h->store.release(name);
+    h->store.release(name + "_scb");
+    *out = static_cast<const bf16*>(packed);
+    return B200_OK;
+  }
+  const bf16* w = nullptr;
+  B200_TRY(get_bf16(h, name, {w_rows, K}, &w));
   if (h->cfg.quantize) {        // QLinear.__init__ (utils/quantize.py:16-21): row-wise absmax int8 of weight.to(float16)
     float* scales = nullptr;
     B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes_i8(N, K, epi, gate_rows), false));
@@ -384,7 +415,29 @@ int b200_lm_finalize(b200_lm* h) {
     B200_CUDA(cudaMemcpy(h->extra_w_dev, h->extra_w.data(), h->extra_w.size() * sizeof(void*), cudaMemcpyHostToDevice));
   }
   // depformer_in.{k} stacked so that all dep_q projections of transformer_out are one GEMM
-  if (c.dep_q > 0) {
+  const Tensor* din0 = c.dep_q > 0 ? h->store.find("depformer_in.0.weight") : nullptr;
+  if (din0 && din0->dtype == B200_I8) {          // pre-quantised: stack CB and SCB
+    int8_t* stacked = nullptr; float* scales = nullptr; void* packed = nullptr;
+    B200_CUDA(cudaMalloc(&stacked, (size_t)c.dep_q * dd * d));
+    struct Guard { void* p; ~Guard() { cudaFree(p); } } guard{stacked};
+    B200_TRY(h->weights.alloc_t(&scales, (size_t)c.dep_q * dd, false));
+    for (int k = 0; k < c.dep_q; ++k) {
+      const std::string name = "depformer_in." + std::to_string(k) + ".weight";
+      const int8_t* q = nullptr; const float* scb = nullptr;
+      if (!h->store.find(name)) B200_FAIL(B200_ERR_MISSING, "lm finalize: tensor '%s' was not loaded", name.c_str());
+      B200_TRY(get_prequantised(h, name, dd, d, &q, &scb));
+      B200_CUDA(cudaMemcpy(stacked + (size_t)k * dd * d, q, (size_t)dd * d, cudaMemcpyDeviceToDevice));
+      B200_CUDA(cudaMemcpy(scales + (size_t)k * dd, scb, (size_t)dd * 4, cudaMemcpyDeviceToDevice));
+      h->store.release(name);
+      h->store.release(name + "_scb");
+    }
+    B200_TRY(h->weights.alloc(&packed, tc::sk_packed_bytes_i8(c.dep_q * dd, d, LIN_STORE, 0), false));
+    B200_TRY(tc::sk_pack_weights_i8(stacked, packed, c.dep_q * dd, d, LIN_STORE, 0, nullptr));
+    B200_CUDA(cudaStreamSynchronize(nullptr));
+    h->dep_in_s = scales;
+    h->dep_in_all = static_cast<bf16*>(packed);
+    h->weight_bytes += (int64_t)c.dep_q * dd * d + (int64_t)c.dep_q * dd * 4;
+  } else if (c.dep_q > 0) {
     bf16* stacked = nullptr;
     B200_CUDA(cudaMalloc(&stacked, (size_t)c.dep_q * dd * d * 2));
     struct Guard { void* p; ~Guard() { cudaFree(p); } } guard{stacked};      // released on every path out of this block

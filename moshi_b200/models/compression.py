@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import typing as tp
 from contextlib import ExitStack
+from types import SimpleNamespace
 
 import torch
 
@@ -51,6 +52,20 @@ class MimiModel:
         self._batch: int | None = None
         self._num_codebooks = cfg.num_codebooks
         self.use_graph = True      # replay each one-frame encode / decode as a CUDA graph
+        # carried input rows per SEANet layer (state-dict prefix of its nn.Conv1d / nn.ConvTranspose1d -> P): StreamingConv1d keeps
+        # (k - 1) * dilation + 1 - stride samples (conv.py:233-243), a transposed conv its previous input step
+        from ..synth import seanet_layout
+        self._carried_rows: dict[str, int] = {}
+        for side, layers in zip(("encoder", "decoder"), seanet_layout(cfg)):
+            for kind, idx, cin, cout, k, stride, dil in layers:
+                base = f"{side}.model.{idx}"
+                if kind == "conv":
+                    self._carried_rows[base + ".conv.conv"] = (k - 1) * dil + 1 - stride
+                elif kind == "convtr":
+                    self._carried_rows[base + ".convtr.convtr"] = 1
+                else:
+                    self._carried_rows[base + ".block.1.conv.conv"] = (k - 1) * dil
+                    self._carried_rows[base + ".block.3.conv.conv"] = 0
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200_mimi_create(C.byref(_config_struct(cfg)), C.byref(self._h)))
             for name, t in normalize_mimi_state_dict(state_dict).items():
@@ -153,20 +168,122 @@ class MimiModel:
         m = self._mask(exec_mask)
         _lib.check(self._lib.b200_mimi_set_exec_mask(self._h, _lib.ptr(m)))
 
-    def get_streaming_state(self) -> dict:
-        """Snapshot of all streaming state (streaming.py:158-170) as one device blob."""
-        assert self._batch is not None, "mimi is not streaming"
-        n = int(self._lib.b200_mimi_state_bytes(self._h))
-        blob = torch.empty(n, dtype=torch.uint8, device=self.device)
-        _lib.check(self._lib.b200_mimi_get_state(self._h, _lib.ptr(blob), n))
-        return {"batch_size": self._batch, "blob": blob}
+    # ---- streaming state ------------------------------------------------------------------------------
+    def _state_entries(self) -> list[tuple[str, torch.dtype, tuple[int, ...], int]]:
+        from .lm import _TORCH_DTYPES
+        out = []
+        for i in range(int(self._lib.b200_mimi_state_count(self._h))):
+            name, dt, nd, nb = C.c_char_p(), C.c_int(), C.c_int(), C.c_int64()
+            shape = (C.c_int64 * 8)()
+            _lib.check(self._lib.b200_mimi_state_entry(self._h, i, C.byref(name), C.byref(dt), C.byref(nd), shape, C.byref(nb)))
+            out.append((name.value.decode(), _TORCH_DTYPES[dt.value], tuple(shape[:nd.value]), nb.value))
+        return out
 
-    def set_streaming_state(self, state: dict) -> None:
-        """Restore a snapshot taken by ``get_streaming_state`` (streaming.py:172-181)."""
+    @staticmethod
+    def _split_tf32(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """x = hi + lo with hi = tf32(x), lo = tf32(x - hi), round-to-nearest (ties away): what the kernels' epilogues write."""
+        def rna(t):
+            return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        hi = rna(x.float())
+        return hi, rna(x.float() - hi)
+
+    def get_streaming_state(self) -> dict[str, tp.Any]:
+        """``StreamingModule.get_streaming_state`` (streaming.py:158-166): module path -> state object with the reference's field
+        names.  StreamingConv1d: ``previous [B, Cin, P]``, ``first`` (conv.py:161-169); StreamingConvTranspose1d: the library
+        carries the previous INPUT step instead of the overlap-add ``partial`` (the same information before the last matrix
+        product, conv.py:349-361), reported as ``previous_input [B, Cin, 1]``; ``_MHAState``: ``kv_cache.cache [2, B, H, 250, 64]``,
+        ``kv_cache.end_offset``, ``offset`` (transformer.py:196-288, 321-334); the depth-wise up-sampling keeps ``partial``.
+        Tensors are copies."""
         assert self._batch is not None, "mimi is not streaming"
-        assert state["batch_size"] == self._batch, "snapshot was taken with another batch size"
-        blob = state["blob"].to(self.device).contiguous()
-        _lib.check(self._lib.b200_mimi_set_state(self._h, _lib.ptr(blob), blob.numel()))
+        with torch.cuda.device(self.device):
+            raw = {}
+            for name, dt, shape, nb in self._state_entries():
+                t = torch.empty(shape, dtype=dt, device=self.device)
+                _lib.check(self._lib.b200_mimi_state_read(self._h, name.encode(), _lib.ptr(t), nb))
+                raw[name] = t
+        B = self._batch
+        mask = raw["exec_mask"].bool()
+        state: dict[str, tp.Any] = {"": SimpleNamespace(batch_size=B, device=self.device, exec_mask=mask)}
+        for name in raw:
+            if not name.endswith(".ext_hi"):
+                continue
+            base = name[:-len(".ext_hi")]                          # e.g. encoder.model.3.conv.conv
+            lo = raw.get(base + ".ext_lo")
+            full = raw[name] if lo is None else raw[name] + lo     # [B, P + T, Cin]
+            is_tr = base.endswith(".convtr.convtr")
+            module = base[:-len(".convtr.convtr")] if is_tr else base[:-len(".conv.conv")]
+            P = self._carried_rows[base]
+            prev = full[:, :P].transpose(1, 2).contiguous()        # [B, Cin, P]
+            if is_tr:
+                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous_input=prev)
+            else:
+                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous=prev,
+                                                first=torch.zeros(B, dtype=torch.bool, device=self.device))
+        state["downsample.conv"] = SimpleNamespace(batch_size=B, exec_mask=mask, previous=raw["downsample.previous"],
+                                                   first=raw["downsample.first"].bool())
+        state["upsample.convtr"] = SimpleNamespace(batch_size=B, exec_mask=mask, partial=raw["upsample.partial"])
+        for tr in ("encoder_transformer", "decoder_transformer"):
+            off = raw[tr + ".offset"]
+            state[tr + ".transformer"] = SimpleNamespace(batch_size=B, exec_mask=mask, offsets=off.clone())
+            for i in range(self.cfg.tr_num_layers):
+                kv = SimpleNamespace(cache=torch.stack([raw[f"{tr}.layers.{i}.k"], raw[f"{tr}.layers.{i}.v"]]), end_offset=off.clone())
+                state[f"{tr}.transformer.layers.{i}.self_attn"] = SimpleNamespace(batch_size=B, exec_mask=mask, kv_cache=kv,
+                                                                                 offset=off.clone())
+        return state
+
+    def set_streaming_state(self, state: dict[str, tp.Any]) -> None:
+        """``set_streaming_state`` (streaming.py:168-181): every module state must be present and nothing else."""
+        assert self._batch is not None, "mimi is not streaming"
+        state = dict(state)
+        entries = {name: (dt, shape, nb) for name, dt, shape, nb in self._state_entries()}
+
+        def take(name):
+            if name not in state:
+                raise RuntimeError(f"Expected to find a streaming state for {name}.")
+            return state.pop(name)
+
+        def write(name, t):
+            dt, shape, nb = entries[name]
+            t = t.to(device=self.device, dtype=dt).contiguous()
+            assert tuple(t.shape) == shape, (name, tuple(t.shape), shape)
+            _lib.check(self._lib.b200_mimi_state_write(self._h, name.encode(), _lib.ptr(t), nb))
+
+        with torch.cuda.device(self.device):
+            root = take("")
+            assert root.batch_size == self._batch, "snapshot was taken with another batch size"
+            write("exec_mask", root.exec_mask.to(torch.uint8))
+            for name, (dt, shape, nb) in entries.items():
+                if not name.endswith(".ext_hi"):
+                    continue
+                base = name[:-len(".ext_hi")]
+                is_tr = base.endswith(".convtr.convtr")
+                st = take(base[:-len(".convtr.convtr")] if is_tr else base[:-len(".conv.conv")])
+                prev = (st.previous_input if is_tr else st.previous).to(self.device).float().transpose(1, 2)   # [B, P, Cin]
+                P = self._carried_rows[base]
+                cur = torch.empty(shape, dtype=dt, device=self.device)
+                _lib.check(self._lib.b200_mimi_state_read(self._h, name.encode(), _lib.ptr(cur), nb))
+                if base + ".ext_lo" in entries:
+                    hi, lo = self._split_tf32(prev)
+                    cur_lo = torch.empty(shape, dtype=dt, device=self.device)
+                    _lib.check(self._lib.b200_mimi_state_read(self._h, (base + ".ext_lo").encode(), _lib.ptr(cur_lo), nb))
+                    cur_lo[:, :P] = lo
+                    write(base + ".ext_lo", cur_lo)
+                else:
+                    hi = prev
+                cur[:, :P] = hi
+                write(name, cur)
+            st = take("downsample.conv")
+            write("downsample.previous", st.previous)
+            write("downsample.first", st.first.to(torch.uint8))
+            write("upsample.partial", take("upsample.convtr").partial)
+            for tr in ("encoder_transformer", "decoder_transformer"):
+                write(tr + ".offset", take(tr + ".transformer").offsets.long())
+                for i in range(self.cfg.tr_num_layers):
+                    st = take(f"{tr}.transformer.layers.{i}.self_attn")
+                    write(f"{tr}.layers.{i}.k", st.kv_cache.cache[0])
+                    write(f"{tr}.layers.{i}.v", st.kv_cache.cache[1])
+        if state:
+            raise RuntimeError(f"Some states were not consumed: {list(state.keys())}")
 
     # ---- data path ------------------------------------------------------------------------------
     def _check_pcm(self, x: torch.Tensor) -> torch.Tensor:

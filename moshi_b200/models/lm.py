@@ -80,9 +80,17 @@ class LMModel:
                     host_side[name] = t.detach()
                     continue
                 for n2, t2 in normalize_lm_state_dict({name: t}).items():
-                    t2 = t2.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+                    # a q8 checkpoint stores a QLinear as `weight` int8 + `weight_scb` float32, and the scale must stay float32
+                    # (utils/quantize.py:13-35; the reference's loader casts it with the rest, loaders.py:415-421, and then fails)
+                    if t2.dtype == torch.int8:
+                        want = torch.int8
+                    elif n2.endswith(".weight_scb"):
+                        want = torch.float32
+                    else:
+                        want = torch.bfloat16
+                    t2 = t2.detach().to(device=self.device, dtype=want).contiguous()
                     shape = (C.c_int64 * t2.dim())(*t2.shape)
-                    _lib.check(self._lib.b200_lm_load_tensor(self._h, n2.encode(), _lib.ptr(t2), _lib.B200_BF16,
+                    _lib.check(self._lib.b200_lm_load_tensor(self._h, n2.encode(), _lib.ptr(t2), _lib.dtype_code(want),
                                                              t2.dim(), shape))
                     del t2
             _lib.check(self._lib.b200_lm_finalize(self._h))

@@ -55,7 +55,10 @@ def get_moshi_lm(filename: str | Path | None, lm_kwargs: dict | None = None,
                  lora_weights: str | Path | None = None, fuse_lora: bool = False,
                  lm_kwargs_overrides: dict = {}, synth_seed: int = 4242,
                  synth_device: str | torch.device | None = None) -> LMModel:
-    """``loaders.get_moshi_lm`` (loaders.py:366-446); LoRA / conditioners are outside the hot path."""
+    """``loaders.get_moshi_lm`` (loaders.py:366-446).  Checkpoints: ``model.safetensors`` (bf16), ``model.q8.safetensors``
+    (loaders.py:33: every nn.Linear stored as a QLinear, ``weight`` int8 + ``weight_scb`` float32; needs ``quantize=True`` in the
+    kwargs, like the reference) and legacy ``.pt`` packages; packed ``in_proj_weight`` names are split (transformer.py:422-446).
+    LoRA adapters are fused offline (loaders.py:512-513)."""
     if lora_weights is not None:
         raise ValueError("LoRA checkpoints are fused offline (loaders.py:512-513); pass fused weights")
     kwargs = dict(LMConfig().to_reference_kwargs() if lm_kwargs is None else lm_kwargs)

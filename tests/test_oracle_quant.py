@@ -54,3 +54,25 @@ def test_quantized_lm_oracle_steps_close_to_bf16():
         logits.append(dbg["text_logits"].float())
     rel = (logits[0] - logits[1]).abs().max() / logits[0].abs().max()
     assert 0 < rel < 0.08, rel
+
+
+def test_qlinear_known_answers(golden_dir):
+    """The KAT SURVEY.md 8(c) asks for: ``oracle/quant.py`` against an independent implementation of the published QLinear
+    algorithm (numpy float32 quantiser with half-to-even rounding, exact Python-integer products, float64 dequantisation;
+    ``oracle/gen_qlinear_kat.py``).  It pins the restatement, not bitsandbytes itself (absent: parity stays unpinned)."""
+    import json
+    kat = json.loads((golden_dir / "qlinear_kat.json").read_text())
+    x = torch.tensor(kat["x"], dtype=torch.float32).bfloat16()
+    w = torch.tensor(kat["w"], dtype=torch.float32).bfloat16()
+    assert torch.equal(x.float(), torch.tensor(kat["x"])) and torch.equal(w.float(), torch.tensor(kat["w"]))   # bf16-exact inputs
+    qx, sa = quant.quantize_rows(x)
+    qw, sw = quant.quantize_weight(w)
+    assert qx.tolist() == kat["qx"] and qw.tolist() == kat["qw"]
+    assert qx[2][:6].tolist() == [127, 0, 2, 0, -2, 64]              # ties to even
+    assert torch.equal(sa, torch.tensor(kat["sa"])) and torch.equal(sw, torch.tensor(kat["sw"]))
+    acc = qx.long() @ qw.long().t()
+    assert acc.tolist() == kat["acc"]
+    y = quant.qlinear_f32(x, w)
+    want = torch.tensor(kat["y_float64"], dtype=torch.float64)
+    assert (y.double() - want).abs().max() <= 2.0 ** -22 * want.abs().max()      # fp32 rounding of two multiplies
+    assert (y[1] == 0).all() and (y[:, 4] == 0).all()                # zero activation row, zero weight row
