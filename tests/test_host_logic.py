@@ -159,3 +159,38 @@ def test_session_pool_frames_and_slot_updates():
     pool.open()
     with pytest.raises(RuntimeError):
         pool.open()
+
+
+def test_candle_layout_checkpoint_maps_back_to_reference_names():
+    """``scripts/import_rust.py:45-113`` writes the layout ``rust/moshi-core`` loads (per-step depformer slices); restated here
+    on the synthetic checkpoint and mapped back by ``normalize_lm_state_dict``: every tensor returns under its reference name."""
+    import torch
+    from moshi_b200.models.state_dict import normalize_lm_state_dict
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=3)
+    # the reference-side packed names first (what the .pt checkpoints import_rust.py reads carry)
+    packed = {}
+    for layer in range(cfg.depformer_num_layers):
+        p = f"depformer.layers.{layer}.self_attn."
+        packed[p + "in_proj_weight"] = torch.cat([sd[p + f"in_projs.{k}.weight"] for k in range(cfg.dep_q)])
+        packed[p + "out_proj.weight"] = torch.cat([sd[p + f"out_projs.{k}.weight"] for k in range(cfg.dep_q)])
+    candle = {k: v for k, v in sd.items() if k.startswith(("text_emb", "text_linear", "out_norm", "emb.", "transformer."))}
+    for k in range(cfg.dep_q):
+        base = f"depformer.{k}."
+        candle[base + "linear_in.weight"] = sd[f"depformer_in.{k}.weight"]
+        candle[base + "linear_out.weight"] = sd[f"linears.{k}.weight"]
+        candle[base + "emb.weight"] = sd["depformer_text_emb.weight"] if k == 0 else sd[f"depformer_emb.{k - 1}.weight"]
+        for layer in range(cfg.depformer_num_layers):
+            src, dst = f"depformer.layers.{layer}.", base + f"transformer.layers.{layer}."
+            candle[dst + "self_attn.in_proj_weight"] = packed[src + "self_attn.in_proj_weight"].chunk(cfg.dep_q)[k]
+            candle[dst + "self_attn.out_proj.weight"] = packed[src + "self_attn.out_proj.weight"].chunk(cfg.dep_q)[k]
+            candle[dst + "norm1.alpha"] = sd[src + "norm1.alpha"]
+            candle[dst + "norm2.alpha"] = sd[src + "norm2.alpha"]
+            candle[dst + "gating.linear_in.weight"] = sd[src + f"gating.{k}.linear_in.weight"]
+            candle[dst + "gating.linear_out.weight"] = sd[src + f"gating.{k}.linear_out.weight"]
+    back = normalize_lm_state_dict(candle)
+    assert set(back) == set(sd), set(back) ^ set(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+    # tensor by tensor, the way LMModel streams a checkpoint in
+    one = normalize_lm_state_dict({"depformer.3.transformer.layers.1.gating.linear_out.weight": candle["depformer.3.transformer.layers.1.gating.linear_out.weight"]})
+    assert list(one) == ["depformer.layers.1.gating.3.linear_out.weight"]
