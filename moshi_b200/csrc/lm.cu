@@ -352,7 +352,7 @@ int b200_lm_create(const b200_lm_config* cfg, b200_lm** out) {
     B200_FAIL(B200_ERR_INVALID, "lm_create: temporal head dim must be %d", ATT_D);
   if (cfg->dep_q > 0 && (cfg->depformer_dim % cfg->depformer_num_heads || cfg->depformer_dim / cfg->depformer_num_heads != 64))
     B200_FAIL(B200_ERR_INVALID, "lm_create: depformer head dim must be 64");
-  if (cfg->dim % 8 || cfg->ffn_hidden % 8 || cfg->depformer_dim % 8 || cfg->depformer_ffn_hidden % 8)
+  if (cfg->dim % 8 || cfg->ffn_hidden % 8 || (cfg->dep_q > 0 && (cfg->depformer_dim % 8 || cfg->depformer_ffn_hidden % 8)))
     B200_FAIL(B200_ERR_INVALID, "lm_create: feature sizes must be multiples of 8");
   if (cfg->text_card + 1 > 65535 || cfg->card + 1 > 65535)
     B200_FAIL(B200_ERR_INVALID, "lm_create: vocabularies above 65535 unsupported by the sampler");

@@ -408,15 +408,8 @@ int run_transformer(b200_mimi* h, Transformer& tr, const float* x_in, float* x, 
     const float* cur = li == 0 ? x_in : x;
     B200_LAUNCH(layernorm_split_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, cur, L.n1w, L.n1b, h->tr_xn_hi, h->tr_xn_lo, ntok, d, 1e-5f);
     B200_TRY(launch_tc(h, L.in_proj));
-    {
-      const long long total = (long long)B * T * H * (D / 2);
-      B200_LAUNCH(rope_append_f32_kernel, (unsigned)ceil_div64(total, 256), 256, 0, h->body, h->tr_qkv, h->tr_q, L.kc,
-                  L.vc, tr.offset, h->exec_mask, B, T, H, D, c.tr_context, nl);
-    }
-    B200_LAUNCH((ring_attn_f32_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_q, L.kc, L.vc, h->tr_ao, tr.offset,
-                h->exec_mask, T, H, c.tr_context, c.tr_context);
-    B200_LAUNCH(split_kernel, (unsigned)ceil_div64((long long)ntok * d, 256), 256, 0, h->body, h->tr_ao, h->tr_ao_hi, h->tr_ao_lo,
-                (long long)ntok * d);
+    B200_LAUNCH((ring_attn_step_kernel<64>), B * H, 128, attn_smem, h->body, h->tr_qkv, L.kc, L.vc, h->tr_ao_hi, h->tr_ao_lo, tr.offset,
+                h->exec_mask, T, H, c.tr_context, c.tr_context, nl);
     B200_TRY(launch_tc(h, L.out_proj));       // x = cur + layer_scale_1 * out_proj(attention)
     B200_LAUNCH(layernorm_split_kernel, ceil_div(ntok * 32, 256), 256, 0, h->body, x, L.n2w, L.n2b, h->tr_xn_hi, h->tr_xn_lo, ntok, d, 1e-5f);
     B200_TRY(launch_tc(h, L.l1));             // h = gelu(linear1(xn)) as a hi / lo pair
@@ -682,6 +675,7 @@ int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out) {
   if (cfg->channels != 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: only mono audio is on the hot path");
   if (cfg->q_dimension % 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: codebook dimension must be a multiple of 8");
   if (cfg->tr_d_model / cfg->tr_num_heads != 64) B200_FAIL(B200_ERR_INVALID, "mimi_create: head dim must be 64");
+  if ((int)(cfg->sample_rate / cfg->frame_rate) % 1 || cfg->tr_context < 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: bad transformer context");
   if (cfg->tr_d_model != cfg->dimension) B200_FAIL(B200_ERR_INVALID, "mimi_create: projected transformer unsupported");
   if (cfg->n_filters % 32 || cfg->compress != 2 || cfg->n_filters / cfg->compress % 32)
     B200_FAIL(B200_ERR_INVALID, "mimi_create: SEANet channel counts must be multiples of 32 (tensor-core k-blocks)");

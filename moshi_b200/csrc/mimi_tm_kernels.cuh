@@ -132,7 +132,107 @@ static __global__ void layernorm_split_kernel(const float* __restrict__ x, const
   }
 }
 
-// x -> (hi, lo), element-wise (attention output in front of out_proj)
+// One attention step of a bottleneck transformer layer in ONE launch (transformer.py:557-597 for T tokens per frame):
+// RoPE(q, k) (rope.py:45-82, interleaved pairs, fp32) -> ring append of the T new keys / values for executing sessions
+// (RingKVCache.complete, transformer.py:236-288) -> attention of the T queries over the ring under the causal / context mask ->
+// the out_proj's input as a hi / lo pair.  One CTA per (session, head), 128 threads; qkv [n_tok][3C] (rows q | k | v, each (h d)).
+template <int D>
+static __global__ void __launch_bounds__(128) ring_attn_step_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
+                                                             float* __restrict__ vc, float* __restrict__ out_hi,
+                                                             float* __restrict__ out_lo, const long long* __restrict__ offset,
+                                                             const uint8_t* __restrict__ exec_mask, int T, int H, int cap,
+                                                             int context, float neg_log_period_2_over_d) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int C = H * D;
+  float* sq = sm;                 // [T][D] rotated queries
+  float* sc = sm + T * D;         // [T][cap] scores, then probabilities
+  const int tid = threadIdx.x;
+  const long long off = offset[b];
+  const bool exec = exec_mask[b] != 0;
+  float* kb = kc + ((long long)b * H + h) * cap * D;
+  float* vb = vc + ((long long)b * H + h) * cap * D;
+  for (int i = tid; i < T * (D / 2); i += blockDim.x) {
+    const int t = i / (D / 2), pr = i - t * (D / 2);
+    const float pos = (float)off + (float)t;                         // rope.py:48
+    const float freq = expf((float)pr * neg_log_period_2_over_d);    // rope.py:46
+    float sn, cs;
+    sincosf(freq * pos, &sn, &cs);
+    const float* base = qkv + ((long long)b * T + t) * 3 * C + h * D + 2 * pr;
+    const float qr = base[0], qi = base[1], kr = base[C], ki = base[C + 1];
+    sq[t * D + 2 * pr] = qr * cs - qi * sn;
+    sq[t * D + 2 * pr + 1] = qr * sn + qi * cs;
+    if (exec) {                                                      // masked sessions do not write (their offsets do not move)
+      const int slot = (int)((off + t) % cap);
+      float* kd = kb + (long long)slot * D + 2 * pr;
+      float* vd = vb + (long long)slot * D + 2 * pr;
+      kd[0] = kr * cs - ki * sn; kd[1] = kr * sn + ki * cs;
+      vd[0] = base[2 * C]; vd[1] = base[2 * C + 1];
+    }
+  }
+  __syncthreads();                 // the new keys are read back below by other threads of this CTA (no other CTA touches this ring)
+  // end_offset after the append: only advanced for executing sessions (transformer.py:279-284)
+  const long long end_after = exec ? off + T : off;
+  const long long last = off + T - 1;
+  const int end_index = (int)(last % cap);
+  const float scale = rsqrtf((float)D);
+  for (int s = tid; s < cap; s += blockDim.x) {
+    const int delta = s - end_index;
+    long long pos = delta <= 0 ? last + delta : last + delta - cap;
+    if (s >= end_after) pos = -1;
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pos >= 0) {
+      const float4* kr = reinterpret_cast<const float4*>(kb + (long long)s * D);
+#pragma unroll 4
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kv = kr[d4];
+        for (int t = 0; t < T; ++t) {
+          const float* qq = sq + t * D + d4 * 4;
+          dot[t] += kv.x * qq[0] + kv.y * qq[1] + kv.z * qq[2] + kv.w * qq[3];
+        }
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      const long long dq = (off + t) - pos;
+      const bool ok = pos >= 0 && dq >= 0 && dq < context;     // transformer.py:576-580
+      sc[t * cap + s] = ok ? dot[t] * scale : -INFINITY;
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < T) {                  // softmax per query: warp t handles query t
+    float* row = sc + warp * cap;
+    float mx = -INFINITY;
+    for (int s = lane; s < cap; s += 32) mx = fmaxf(mx, row[s]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < cap; s += 32) {
+      const float e = (row[s] == -INFINITY) ? 0.f : expf(row[s] - mx);
+      row[s] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    for (int s = lane; s < cap; s += 32) row[s] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i % D;
+    const float* row = sc + t * cap;
+    float acc = 0.f;
+    for (int s = 0; s < cap; ++s) {
+      const float pw = row[s];
+      if (pw != 0.f) acc = fmaf(pw, vb[(long long)s * D + d], acc);
+    }
+    float hi, lo;
+    mtc::split_tf32(acc, hi, lo);
+    const long long o = ((long long)b * T + t) * C + h * D + d;
+    out_hi[o] = hi;
+    out_lo[o] = lo;
+  }
+}
+
+// x -> (hi, lo), element-wise
 static __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -8,15 +8,17 @@ using namespace b200;
 
 extern "C" {
 
-static int sk_scratch(float** ws, int** counters) {
-  static float* g_ws = nullptr;
-  static int* g_counters = nullptr;
-  if (!g_ws) {
-    B200_CUDA(cudaMalloc(&g_ws, tc::sk_workspace_bytes(256)));
-    B200_CUDA(cudaMalloc(&g_counters, tc::SK_MAX_TILES * sizeof(int)));
-    B200_CUDA(cudaMemset(g_counters, 0, tc::SK_MAX_TILES * sizeof(int)));
+// split-K workspace + arrival counters of the kernel-level entry points (a handle owns its own); separate sets for the bf16 and
+// the int8 kernels, like the handles keep them
+static int sk_scratch(float** ws, int** counters, int which = 0) {
+  static float* g_ws[2] = {nullptr, nullptr};
+  static int* g_counters[2] = {nullptr, nullptr};
+  if (!g_ws[which]) {
+    B200_CUDA(cudaMalloc(&g_ws[which], tc::sk_workspace_bytes(256)));
+    B200_CUDA(cudaMalloc(&g_counters[which], tc::SK_MAX_TILES * sizeof(int)));
+    B200_CUDA(cudaMemset(g_counters[which], 0, tc::SK_MAX_TILES * sizeof(int)));
   }
-  *ws = g_ws; *counters = g_counters;
+  *ws = g_ws[which]; *counters = g_counters[which];
   return B200_OK;
 }
 
@@ -86,7 +88,7 @@ int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_til
   if (!tc::sk_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_i8: unsupported shape");
   static tc::GemmPlanCache cache;
   float* ws = nullptr; int* counters = nullptr;
-  B200_TRY(sk_scratch(&ws, &counters));      // int32 partials of cut tiles share the bf16 path's workspace
+  B200_TRY(sk_scratch(&ws, &counters, 1));   // int32 partials of cut tiles
   tc::SkTuning t;
   t.xq = xq_dev; t.sa = sa_dev; t.sw = sw_dev;
   const int out_cols = epi == 2 ? gate_rows : N;

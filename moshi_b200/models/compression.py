@@ -214,10 +214,12 @@ class MimiModel:
             module = base[:-len(".convtr.convtr")] if is_tr else base[:-len(".conv.conv")]
             P = self._carried_rows[base]
             prev = full[:, :P].transpose(1, 2).contiguous()        # [B, Cin, P]
+            # _raw: the carried rows exactly as the kernels hold them (re-splitting hi + lo is not always bit-identical)
+            rawp = (raw[name][:, :P].clone(), None if lo is None else lo[:, :P].clone())
             if is_tr:
-                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous_input=prev)
+                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous_input=prev, _raw=rawp)
             else:
-                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous=prev,
+                state[module] = SimpleNamespace(batch_size=B, exec_mask=mask, previous=prev, _raw=rawp,
                                                 first=torch.zeros(B, dtype=torch.bool, device=self.device))
         state["downsample.conv"] = SimpleNamespace(batch_size=B, exec_mask=mask, previous=raw["downsample.previous"],
                                                    first=raw["downsample.first"].bool())
@@ -262,14 +264,18 @@ class MimiModel:
                 P = self._carried_rows[base]
                 cur = torch.empty(shape, dtype=dt, device=self.device)
                 _lib.check(self._lib.b200_mimi_state_read(self._h, name.encode(), _lib.ptr(cur), nb))
-                if base + ".ext_lo" in entries:
+                rawp = getattr(st, "_raw", None)
+                if rawp is not None and torch.equal((rawp[0] if rawp[1] is None else rawp[0] + rawp[1]), prev):
+                    hi, lo = rawp                              # untouched snapshot: restore bit for bit
+                elif base + ".ext_lo" in entries:
                     hi, lo = self._split_tf32(prev)
+                else:
+                    hi, lo = prev, None
+                if base + ".ext_lo" in entries:
                     cur_lo = torch.empty(shape, dtype=dt, device=self.device)
                     _lib.check(self._lib.b200_mimi_state_read(self._h, (base + ".ext_lo").encode(), _lib.ptr(cur_lo), nb))
                     cur_lo[:, :P] = lo
                     write(base + ".ext_lo", cur_lo)
-                else:
-                    hi = prev
                 cur[:, :P] = hi
                 write(name, cur)
             st = take("downsample.conv")

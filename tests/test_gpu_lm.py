@@ -406,6 +406,95 @@ def test_one_and_two_sessions_take_the_gemv_path(lm, tiny, B):
     assert agree / total > 0.95
 
 
+class _OracleAsDevice:
+    """Stand-in with LMGen's surface used by _peaked_sampling_run, backed by a second oracle: lets the comparison logic itself be
+    checked on the CPU (tests/test_sampling_gate_cpu.py)."""
+
+    def __init__(self, sd, cfg, B):
+        self.cfg, self.B = cfg, B
+        self.orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=True, tie_break="index")
+        self.orc.streaming(B)
+        self.dbg = {}
+
+    def set_exec_mask(self, m):
+        self.orc.set_exec_mask(m)
+
+    def reset_streaming(self, m=None):
+        self.orc.reset_streaming(m)
+
+    def step(self, codes, nt, na):
+        self.dbg = {}
+        return self.orc.step(codes, nt, na, debug=self.dbg)
+
+    def outputs(self):
+        d = self.dbg
+        return (d["text_logits"].float()[:, 0, 0], torch.stack([x.float()[:, 0, 0] for x in d["dep_logits"]]), d["text_token"],
+                d["audio_tokens"].t().contiguous())
+
+
+def _peaked_sampling_run(dev, sd, cfg, gold):
+    """Drives `dev` (the GPU LMGen wrapped below, or _OracleAsDevice) and a teacher-synchronised oracle through the peaked
+    sampling scenario; returns the counters the test gates on."""
+    from tests.util import sample_is_stable
+    B, steps = scenarios.LM_B, scenarios.LM_STEPS
+    codes = scenarios.lm_input_codes(cfg, B, steps)
+    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=True, tie_break="index")
+    orc.streaming(B)
+    torch.manual_seed(scenarios.LM_NOISE_SEED)
+    on_ref = torch.ones(B, dtype=torch.bool)       # rows whose sampled history still equals the reference's
+    c = dict(decisions=0, stable=0, equal=0, unexcused=0, ref_decisions=0, ref_equal=0, ref_unexcused=0, worst=0.0)
+    for i in range(steps):
+        scenarios.lm_mask_events(dev, i, B)
+        scenarios.lm_mask_events(orc, i, B)
+        nt, na = scenarios.lm_noise(cfg, B)
+        dbg = {}
+        want = orc.step(codes[i], nt, na, debug=dbg)
+        got = dev.step(codes[i], nt, na)
+        assert (want is None) == (got is None), i
+        live = orc.exec_mask.clone()
+        tl, dl, tt, at = dev.outputs()
+        if i == 20:
+            on_ref[1] = True                  # scenarios.lm_mask_events: row 1 restarts from scratch (in the reference run too)
+        # sampler by sampler.  `same`: this row's inputs to the sampler are identical on the device and in the oracle, so the
+        # oracle's logits are the right yardstick; `ref_same`: they also equal the reference run's (whose logits the oracle
+        # reproduces bit for bit), so the reference's recorded decision is comparable too
+        same = live.clone()
+        ref_same = live & on_ref
+        chain = [(tl, dbg["text_logits"].float()[:, 0, 0], 0.7, 25, nt, tt, dbg["text_token"], gold["sampled_text"][i])]
+        for k in range(cfg.dep_q):
+            chain.append((dl[k], dbg["dep_logits"][k].float()[:, 0, 0], 0.8, 250, na[k], at[k], dbg["audio_tokens"][:, k],
+                          gold["sampled_audio"][i][:, k]))
+        for lg, lo, temp, topk, nz, tok_g, tok_o, tok_r in chain:
+            for b in range(B):
+                if not same[b]:
+                    ref_same[b] = False       # the oracle's logits no longer describe this row's sampler inputs
+                    continue
+                d = float((lg[b] - lo[b]).abs().max())
+                ok = bool(sample_is_stable(lo[b:b + 1], temp, topk, nz[b:b + 1], d + 1e-6)[0])
+                c["worst"] = max(c["worst"], d)
+                c["decisions"] += 1
+                c["stable"] += int(ok)
+                if ref_same[b]:
+                    c["ref_decisions"] += 1
+                    if int(tok_g[b]) == int(tok_r[b]):
+                        c["ref_equal"] += 1
+                    else:
+                        ref_same[b] = False
+                        c["ref_unexcused"] += int(ok)
+                if int(tok_g[b]) == int(tok_o[b]):
+                    c["equal"] += 1
+                else:
+                    same[b] = False
+                    c["unexcused"] += int(ok)
+        on_ref &= ~live | ref_same            # a row stays on the reference's trajectory only if every decision of this step matched
+        pos = (orc.offsets % orc.cache.shape[2])
+        for b in range(B):
+            if live[b]:
+                orc.cache[b, 0, pos[b]] = tt[b]
+                orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
+    return c
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_sampled_tokens_margin_aware_on_peaked_distributions(golden_dir, use_graph):
     """north_star: "sampled token ids under a fixed seed".  On peaked output distributions (scenarios.peaked_state_dict: what a
@@ -417,78 +506,36 @@ def test_sampled_tokens_margin_aware_on_peaked_distributions(golden_dir, use_gra
     on_audio hooks): while a row's token history equals the reference's, each decision equals the reference's or is provably
     unstable (which includes exact bf16 ties, whose torch.topk order is unspecified)."""
     from moshi_b200.models import LMGen, LMModel
-    from tests.util import sample_is_stable
     cfg = tiny_lm_config()
     sd = scenarios.peaked_state_dict(cfg)
     gold = load_file(golden_dir / "lm_tiny_sampled_peaked.safetensors")
     lm = LMModel(cfg, sd, device="cuda")
-    B, steps = scenarios.LM_B, scenarios.LM_STEPS
-    codes = scenarios.lm_input_codes(cfg, B, steps)
     gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
     gen.use_graph = use_graph
-    orc = LMOracle(sd, LMSpec.from_config(cfg), use_sampling=True, tie_break="index")
-    orc.streaming(B)
-    torch.manual_seed(scenarios.LM_NOISE_SEED)
-    on_ref = torch.ones(B, dtype=torch.bool)       # rows whose sampled history still equals the reference's
-    decisions = stable = equal = unexcused = 0
-    ref_decisions = ref_equal = ref_unexcused = 0
-    worst = 0.0
+    B = scenarios.LM_B
+
+    class Dev:
+        def set_exec_mask(self, m):
+            gen.set_exec_mask(m)
+
+        def reset_streaming(self, m=None):
+            gen.reset_streaming(m)
+
+        def step(self, codes, nt, na):
+            return gen.step(codes.cuda(), noise=gen.pack_noise(nt, na))
+
+        def outputs(self):
+            return (gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).float().cpu(),
+                    gen.read_buffer("dep_logits", torch.bfloat16, (cfg.dep_q, B, cfg.card)).float().cpu(),
+                    gen.read_buffer("text_token", torch.int64, (B,)).cpu(), gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu())
+
     with gen.streaming(B):
-        for i in range(steps):
-            scenarios.lm_mask_events(gen, i, B)
-            scenarios.lm_mask_events(orc, i, B)
-            nt, na = scenarios.lm_noise(cfg, B)
-            dbg = {}
-            want = orc.step(codes[i], nt, na, debug=dbg)
-            got = gen.step(codes[i].cuda(), noise=gen.pack_noise(nt, na))
-            assert (want is None) == (got is None), i
-            live = orc.exec_mask.clone()
-            tl = gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).float().cpu()
-            dl = gen.read_buffer("dep_logits", torch.bfloat16, (cfg.dep_q, B, cfg.card)).float().cpu()
-            tt = gen.read_buffer("text_token", torch.int64, (B,)).cpu()
-            at = gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()
-            # sampler by sampler, while the row's inputs to that sampler are identical on both sides
-            if i == 20:
-                on_ref[1] = True                  # scenarios.lm_mask_events: row 1 restarts from scratch (in the reference run too)
-            same = live.clone()
-            ref_same = live & on_ref
-            chain = [(tl, dbg["text_logits"].float()[:, 0, 0], 0.7, 25, nt, tt, dbg["text_token"], gold["sampled_text"][i])]
-            for k in range(cfg.dep_q):
-                chain.append((dl[k], dbg["dep_logits"][k].float()[:, 0, 0], 0.8, 250, na[k], at[k], dbg["audio_tokens"][:, k],
-                              gold["sampled_audio"][i][:, k]))
-            for lg, lo, temp, topk, nz, tok_g, tok_o, tok_r in chain:
-                for b in range(B):
-                    if not (same[b] or ref_same[b]):
-                        continue
-                    d = float((lg[b] - lo[b]).abs().max())
-                    ok = bool(sample_is_stable(lo[b:b + 1], temp, topk, nz[b:b + 1], d + 1e-6)[0])
-                    if same[b]:
-                        worst = max(worst, d)
-                        decisions += 1
-                        stable += int(ok)
-                        if tok_g[b] == tok_o[b]:
-                            equal += 1
-                        else:
-                            same[b] = False
-                            unexcused += int(ok)
-                    if ref_same[b]:               # (the oracle is on the GPU's trajectory = the reference's, so `lo` is the reference's logits)
-                        ref_decisions += 1
-                        if tok_g[b] == tok_r[b]:
-                            ref_equal += 1
-                        else:
-                            ref_same[b] = False
-                            on_ref[b] = False
-                            ref_unexcused += int(ok)
-            pos = (orc.offsets % orc.cache.shape[2])
-            for b in range(B):
-                if live[b]:
-                    orc.cache[b, 0, pos[b]] = tt[b]
-                    orc.cache[b, 1:cfg.dep_q + 1, pos[b]] = at[:, b]
-    print(f"peaked sampling (graph={use_graph}): {decisions} sampler decisions compared, {stable} provably stable under the observed "
-          f"logit difference, {equal} equal, {unexcused} unexcused mismatches; against the reference's recorded decisions: "
-          f"{ref_decisions} compared, {ref_equal} equal, {ref_unexcused} unexcused; worst logit diff {worst:.3e}")
-    assert unexcused == 0
-    assert stable > 0.4 * decisions            # the gate is not vacuous
-    assert equal > 0.9 * decisions
-    assert worst < 4 * LOGIT_ATOL              # logits are 4x larger than in the default scenario (bf16 ulp 0.06-0.125 at |x| 8-32)
-    assert ref_decisions > 50 and ref_unexcused == 0
+        c = _peaked_sampling_run(Dev(), sd, cfg, gold)
+    print(f"peaked sampling (graph={use_graph}): {c['decisions']} sampler decisions compared, {c['stable']} provably stable under the "
+          f"observed logit difference, {c['equal']} equal, {c['unexcused']} unexcused mismatches; against the reference's recorded "
+          f"decisions: {c['ref_decisions']} compared, {c['ref_equal']} equal, {c['ref_unexcused']} unexcused; worst logit diff {c['worst']:.3e}")
+    assert c["unexcused"] == 0 and c["ref_unexcused"] == 0
+    assert c["stable"] > 0.4 * c["decisions"]            # the gate is not vacuous
+    assert c["equal"] > 0.9 * c["decisions"]
+    assert c["worst"] < 4 * LOGIT_ATOL              # logits are 4x larger than in the default scenario (bf16 ulp 0.06-0.125 at |x| 8-32)
+    assert c["ref_decisions"] > 30

@@ -186,7 +186,8 @@ def test_rows_are_independent_and_multiframe_equals_stepwise(gpu):
         c3 = gpu.encode(pcm[5:8])
         o3 = gpu.decode(c3)
     assert torch.equal(c3, codes_all[5:8])
-    torch.testing.assert_close(o3, out_all[5:8], rtol=0, atol=1e-5)
+    # another batch size = another tiling / split-K of the tensor-core GEMMs, i.e. another fp32 summation order (measured 1.5e-5)
+    torch.testing.assert_close(o3, out_all[5:8], rtol=0, atol=5e-5)
     assert codes_all.min() >= 0 and codes_all.max() < 2048 and codes_all.unique().numel() > 500
 
 
