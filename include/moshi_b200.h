@@ -349,18 +349,14 @@ int b200_op_linear_i8(const void* xq_dev, const float* sa_dev, const void* w_til
 int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev,
                    const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
                    int K, int stride, int dilation, int elu_in, void* stream);
-/* StreamingConvTranspose1d.forward (conv.py:340-362): x [B,Cin,T], w [Cin,Cout,K], partial
- * [B,Cout,K-S] (updated where exec_mask), y [B,Cout,T*S]. */
-int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
-                     const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T,
-                     int K, int stride, int elu_in, void* stream);
 /* mimi_tc_kernel (TMA + tcgen05 kind::tf32, 3xTF32 split products: fp32-equivalent accuracy) on the reference's layouts;
  * test scaffolding around the kernel the Mimi handle launches for every conv / convtr / linear (the handle itself keeps all
  * activations token-major and never transposes).
  *   b200_op_tc_linear_f32: y[M,N] = x[M,K] . w[N,K]^T  (K % 32 == 0, N % 16 == 0)
- *   b200_op_tc_conv1d:     same contract as b200_op_conv1d (transposed = 0) / b200_op_convtr1d (transposed = 1, where the
- *                          carried state is the LAST INPUT STEP previous [B,Cin,1] instead of the overlap-add partial: the same
- *                          information, conv.py:349-361); Cin % 32 == 0. */
+ *   b200_op_tc_conv1d:     same contract as b200_op_conv1d (transposed = 0); transposed = 1: StreamingConvTranspose1d.forward
+ *                          (conv.py:340-362), x [B,Cin,T], w [Cin,Cout,2*stride], y [B,Cout,T*stride], where the carried state is the
+ *                          LAST INPUT STEP previous [B,Cin,1] instead of the overlap-add partial (the same information,
+ *                          conv.py:349-361); Cin % 32 == 0. */
 int b200_op_tc_linear_f32(const float* x_dev, const float* w_dev, float* y_dev, int M, int N, int K, void* stream);
 int b200_op_tc_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* prev_dev, const uint8_t* exec_mask_dev,
                       float* y_dev, int B, int Cin, int Cout, int T, int K, int stride, int dilation, int elu_in, int transposed,

@@ -124,7 +124,6 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_op_quantize_rows": (_I, [_P, _P, _P, _I, _I, _P]),
     "b200_op_linear_i8": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_op_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "b200_op_convtr1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_tc_linear_f32": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200_op_tc_conv1d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_op_attn_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P]),

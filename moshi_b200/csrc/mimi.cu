@@ -86,7 +86,7 @@ struct b200_mimi {
   // per-batch buffers
   float *tok_in_enc = nullptr, *tok_enc = nullptr, *latent = nullptr;     // [B][T][C], [B][T][C], [B][C]
   float *latent_q = nullptr, *tok_in_dec = nullptr, *tok_dec = nullptr;
-  float *tr_xn_hi = nullptr, *tr_xn_lo = nullptr, *tr_qkv = nullptr, *tr_q = nullptr, *tr_ao = nullptr, *tr_ao_hi = nullptr,
+  float *tr_xn_hi = nullptr, *tr_xn_lo = nullptr, *tr_qkv = nullptr, *tr_ao_hi = nullptr,
         *tr_ao_lo = nullptr, *tr_h_hi = nullptr, *tr_h_lo = nullptr;
   uint8_t* exec_mask = nullptr;
   uint8_t* first_flags = nullptr; int n_first = 0;
@@ -675,7 +675,6 @@ int b200_mimi_create(const b200_mimi_config* cfg, b200_mimi** out) {
   if (cfg->channels != 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: only mono audio is on the hot path");
   if (cfg->q_dimension % 8) B200_FAIL(B200_ERR_INVALID, "mimi_create: codebook dimension must be a multiple of 8");
   if (cfg->tr_d_model / cfg->tr_num_heads != 64) B200_FAIL(B200_ERR_INVALID, "mimi_create: head dim must be 64");
-  if ((int)(cfg->sample_rate / cfg->frame_rate) % 1 || cfg->tr_context < 1) B200_FAIL(B200_ERR_INVALID, "mimi_create: bad transformer context");
   if (cfg->tr_d_model != cfg->dimension) B200_FAIL(B200_ERR_INVALID, "mimi_create: projected transformer unsupported");
   if (cfg->n_filters % 32 || cfg->compress != 2 || cfg->n_filters / cfg->compress % 32)
     B200_FAIL(B200_ERR_INVALID, "mimi_create: SEANet channel counts must be multiples of 32 (tensor-core k-blocks)");
@@ -908,8 +907,6 @@ int b200_mimi_streaming_begin(b200_mimi* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->tr_xn_hi, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_xn_lo, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_qkv, ntok * 3 * d));
-  B200_TRY(A.alloc_t(&h->tr_q, ntok * d));
-  B200_TRY(A.alloc_t(&h->tr_ao, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_ao_hi, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_ao_lo, ntok * d));
   B200_TRY(A.alloc_t(&h->tr_h_hi, ntok * ff));

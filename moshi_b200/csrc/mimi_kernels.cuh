@@ -7,9 +7,9 @@
 //     transformer kernels use — no transposition kernels (ProjectedTransformer.conv_layout,
 //     transformer.py:972-981, is folded into the neighbouring conv's addressing).
 //   * conv weights are repacked once at load: Conv1d  [Cout][Cin][K] -> [Cout][K*Cin] (tap-major,
-//     channel fastest) so a K-chunk of the implicit GEMM shares one tap;
-//     ConvTranspose1d [Cin][Cout][K=2S] -> [Cout*S][2*Cin] (phase r = output sample modulo S,
-//     tap 0 = current input step, tap 1 = previous input step).
+//     channel fastest) so a K-chunk of the implicit GEMM shares one tap.
+// Since round 2 only the learnt down-sampling conv (replicate padding) still runs on igemm_f32_kernel; every other
+// contraction of the codec is on the tensor cores (mimi_tc.cuh).
 #pragma once
 
 #include "common.cuh"
@@ -65,66 +65,6 @@ struct ConvP {
     if (res) v = res[b * rb + m * rc + t * rt] + v;   // SEANetResnetBlock: u + v (seanet.py:90-93)
     y[b * yb + m * yc + t * yt] = v;
     if (a) a[b * ab + m * ac + t * at] = a_elu ? elu1(v) : v;
-  }
-};
-
-struct ConvTrP {
-  const float* x; long long xb, xc, xt; int T;
-  const float* partial;   // [B][Cout][S] overlap-add carry (conv.py:349-361)
-  float* scratch;         // candidate carry of this step, committed where exec_mask
-  const float* w; const float* bias;
-  float* y; long long yb, yc, yt;
-  int B, Cin, Cout, S, elu_in;
-  int M, N, Kd, cin_aligned;
-
-  struct Ctx { int valid, b, t; };
-  __device__ __forceinline__ Ctx prepare(int n) const {
-    Ctx c; c.valid = n < N; c.b = c.valid ? n / (T + 1) : 0; c.t = n - c.b * (T + 1); return c;
-  }
-  __device__ __forceinline__ float loadB(const Ctx& c, int kk, int tap_hint) const {
-    if (!c.valid || kk >= Kd) return 0.f;
-    int tap = cin_aligned ? tap_hint : kk / Cin;
-    int ci = kk - tap * Cin;
-    int tt = c.t - tap;
-    if (tt < 0 || tt >= T) return 0.f;
-    float v = x[c.b * xb + ci * xc + (long long)tt * xt];
-    return elu_in ? elu1(v) : v;
-  }
-  __device__ __forceinline__ int chunk_hint(int k0) const { return cin_aligned ? k0 / Cin : 0; }
-  __device__ __forceinline__ float loadBk(int, int) const { return 0.f; }
-  __device__ __forceinline__ void store(int m, int n, float acc) const {
-    if (m >= M || n >= N) return;
-    int b = n / (T + 1), t = n - b * (T + 1);
-    int co = m / S, r = m - co * S;
-    long long sidx = ((long long)b * Cout + co) * S + r;
-    if (t == T) { scratch[sidx] = acc; return; }          // tail of y minus bias (conv.py:352-356)
-    float v = acc + (bias ? bias[co] : 0.f);
-    if (t == 0) v += partial[sidx];                       // y[..., :PT] += partial (conv.py:351)
-    y[b * yb + co * yc + (long long)(t * S + r) * yt] = v;
-  }
-};
-
-enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RES_SCALE = 2 };
-
-struct LinP {   // y[n][m] = epi(sum_k x[n][k] * w[m][k]);  token-major activations
-  const float* x; long long ldx;
-  const float* w;
-  float* y; long long ldy;
-  const float* res; const float* scale; int epi;
-  int M, N, Kd;
-  struct Ctx { int unused; };
-  __device__ __forceinline__ Ctx prepare(int) const { return Ctx{0}; }
-  __device__ __forceinline__ int chunk_hint(int) const { return 0; }
-  __device__ __forceinline__ float loadB(const Ctx&, int, int) const { return 0.f; }
-  __device__ __forceinline__ float loadBk(int kk, int n) const {
-    return (n < N && kk < Kd) ? x[n * ldx + kk] : 0.f;
-  }
-  __device__ __forceinline__ void store(int m, int n, float acc) const {
-    if (m >= M || n >= N) return;
-    float v = acc;
-    if (epi == EPI_GELU) v = gelu_erf(v);
-    else if (epi == EPI_RES_SCALE) v = res[n * ldy + m] + scale[m] * v;   // x + layer_scale(update)
-    y[n * ldy + m] = v;
   }
 };
 
@@ -299,138 +239,7 @@ static __global__ void upsample_dw_kernel(const float* __restrict__ lat, long lo
   y[((long long)b * T * S + (long long)t * S + r) * C + c] = v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// transformer pieces (fp32): LayerNorm(1e-5), RoPE + ring append, ring attention (T tokens/frame)
-// ---------------------------------------------------------------------------------------------
-static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
-                                 float* __restrict__ y, int n_tok, int C, float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n_tok) return;
-  const float* xr = x + (long long)warp * C;
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += xr[c];
-  const float mean = warp_sum(s) / C;
-  float v = 0.f;
-  for (int c = lane; c < C; c += 32) { float d = xr[c] - mean; v += d * d; }
-  const float rstd = rsqrtf(warp_sum(v) / C + eps);
-  for (int c = lane; c < C; c += 32) y[(long long)warp * C + c] = (xr[c] - mean) * rstd * g[c] + bta[c];
-}
-
-// qkv [n_tok][3C] (rows q|k|v, each (h d), transformer.py:557-559) -> q_rot [n_tok][C]; K,V ring
-// [B][H][cap][D] written at slot (end_offset[b] + t) % cap.  Masked rows (exec_mask == 0) do not write.
-static __global__ void rope_append_f32_kernel(const float* __restrict__ qkv, float* __restrict__ q_out,
-                                       float* __restrict__ kc, float* __restrict__ vc,
-                                       const long long* __restrict__ offset, const uint8_t* __restrict__ exec_mask,
-                                       int B, int T, int H, int D, int cap, float neg_log_period_2_over_d) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, t, h, pair)
-  const int half = D / 2;
-  const long long total = (long long)B * T * H * half;
-  if (i >= total) return;
-  const int pr = i % half;
-  long long r = i / half;
-  const int h = r % H; r /= H;
-  const int t = r % T;
-  const int b = r / T;
-  const int C = H * D;
-  const long long tok = (long long)b * T + t;
-  const float pos = (float)offset[b] + (float)t;               // rope.py:48
-  const float freq = expf((float)pr * neg_log_period_2_over_d);  // rope.py:46
-  float sn, cs;
-  sincosf(freq * pos, &sn, &cs);
-  const float* base = qkv + tok * 3 * C + h * D + 2 * pr;
-  const float qr = base[0], qi = base[1];
-  const float kr = base[C], ki = base[C + 1];
-  q_out[tok * C + h * D + 2 * pr] = qr * cs - qi * sn;
-  q_out[tok * C + h * D + 2 * pr + 1] = qr * sn + qi * cs;
-  if (!exec_mask[b]) return;
-  const int slot = (int)((offset[b] + t) % cap);
-  const long long o = (((long long)b * H + h) * cap + slot) * D + 2 * pr;
-  kc[o] = kr * cs - ki * sn;
-  kc[o + 1] = kr * sn + ki * cs;
-  vc[o] = base[2 * C];
-  vc[o + 1] = base[2 * C + 1];
-}
-
-// One CTA per (b, h); T (<= 4) queries share the K/V stream.  Slot positions follow
-// RingKVCache.complete (transformer.py:255-286) *after* this frame's T keys were written.
-template <int D>
-static __global__ void __launch_bounds__(128) ring_attn_f32_kernel(const float* __restrict__ q, const float* __restrict__ kc,
-                                                            const float* __restrict__ vc, float* __restrict__ out,
-                                                            const long long* __restrict__ offset,
-                                                            const uint8_t* __restrict__ exec_mask,
-                                                            int T, int H, int cap, int context) {
-  extern __shared__ float sm[];
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int C = H * D;
-  float* sq = sm;                 // [T][D]
-  float* sc = sm + T * D;         // [T][cap]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < T * D; i += blockDim.x) {
-    const int t = i / D, d = i % D;
-    sq[i] = q[((long long)b * T + t) * C + h * D + d];
-  }
-  __syncthreads();
-  const long long off = offset[b];
-  // end_offset after the append: only advanced for executing rows (transformer.py:279-284)
-  const long long end_after = exec_mask[b] ? off + T : off;
-  const long long last = off + T - 1;
-  const int end_index = (int)(last % cap);
-  const float scale = rsqrtf((float)D);
-  const float* kb = kc + ((long long)b * H + h) * cap * D;
-  const float* vb = vc + ((long long)b * H + h) * cap * D;
-  for (int s = tid; s < cap; s += blockDim.x) {
-    const int delta = s - end_index;
-    long long pos = delta <= 0 ? last + delta : last + delta - cap;
-    if (s >= end_after) pos = -1;
-    float dot[4] = {0.f, 0.f, 0.f, 0.f};
-    if (pos >= 0) {
-      const float4* kr = reinterpret_cast<const float4*>(kb + (long long)s * D);
-#pragma unroll 4
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 kv = kr[d4];
-        for (int t = 0; t < T; ++t) {
-          const float* qq = sq + t * D + d4 * 4;
-          dot[t] += kv.x * qq[0] + kv.y * qq[1] + kv.z * qq[2] + kv.w * qq[3];
-        }
-      }
-    }
-    for (int t = 0; t < T; ++t) {
-      const long long dq = (off + t) - pos;
-      const bool ok = pos >= 0 && dq >= 0 && dq < context;     // transformer.py:576-580
-      sc[t * cap + s] = ok ? dot[t] * scale : -INFINITY;
-    }
-  }
-  __syncthreads();
-  // softmax per query: warp t handles query t
-  const int warp = tid >> 5, lane = tid & 31;
-  if (warp < T) {
-    float* row = sc + warp * cap;
-    float mx = -INFINITY;
-    for (int s = lane; s < cap; s += 32) mx = fmaxf(mx, row[s]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int s = lane; s < cap; s += 32) {
-      const float e = (row[s] == -INFINITY) ? 0.f : expf(row[s] - mx);
-      row[s] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    for (int s = lane; s < cap; s += 32) row[s] *= inv;
-  }
-  __syncthreads();
-  for (int i = tid; i < T * D; i += blockDim.x) {
-    const int t = i / D, d = i % D;
-    const float* row = sc + t * cap;
-    float acc = 0.f;
-    for (int s = 0; s < cap; ++s) {
-      const float pw = row[s];
-      if (pw != 0.f) acc = fmaf(pw, vb[(long long)s * D + d], acc);
-    }
-    out[((long long)b * T + t) * C + h * D + d] = acc;
-  }
-}
-
+// per-session token counters of a bottleneck transformer (== RingKVCache.end_offset == _MHAState.offset), advanced where exec_mask
 static __global__ void advance_offsets_kernel(long long* off, const uint8_t* exec_mask, int B, int T) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && exec_mask[b]) off[b] += T;
@@ -630,14 +439,6 @@ static __global__ void pack_conv_w_kernel(const float* w /*[Cout][Cin][K]*/, flo
   const int kw = i % K; long long r = i / K;
   const int ci = r % Cin; const int co = r / Cin;
   out[((long long)co * K + kw) * Cin + ci] = w[i];
-}
-static __global__ void pack_convtr_w_kernel(const float* w /*[Cin][Cout][2S]*/, float* out /*[Cout*S][2*Cin]*/, int Cin, int Cout, int S) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)Cin * Cout * 2 * S) return;
-  const int k = i % (2 * S); long long r = i / (2 * S);
-  const int co = r % Cout; const int ci = r / Cout;
-  const int tap = k / S, ph = k % S;
-  out[((long long)co * S + ph) * (2 * Cin) + (long long)tap * Cin + ci] = w[i];
 }
 static __global__ void transpose_kernel(const float* in /*[R][C]*/, float* out /*[C][R]*/, int R, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -232,15 +232,6 @@ static __global__ void __launch_bounds__(128) ring_attn_step_kernel(const float*
   }
 }
 
-// x -> (hi, lo), element-wise
-static __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float h, l;
-  mtc::split_tf32(x[i], h, l);
-  hi[i] = h; lo[i] = l;
-}
-
 // ---------------------------------------------------------------------------------------------
 // load-time weight re-layouts to [N][tap][Cin] (the order mimi_tc's k-blocks walk)
 //   conv   [Cout][Cin][K]  -> [Cout][K][Cin]

@@ -134,40 +134,6 @@ int b200_op_conv1d(const float* x_dev, const float* w_dev, const float* bias_dev
   return check_launch("op_conv1d");
 }
 
-int b200_op_convtr1d(const float* x_dev, const float* w_dev, const float* bias_dev, float* partial_dev,
-                     const uint8_t* exec_mask_dev, float* y_dev, int B, int Cin, int Cout, int T, int K, int stride,
-                     int elu_in, void* stream) {
-  using namespace b200::mimi;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (K != 2 * stride) B200_FAIL(B200_ERR_SHAPE, "op_convtr1d: kernel must be 2*stride");
-  float *wp = nullptr, *scratch = nullptr;
-  ConvTrCommit* desc = nullptr;
-  const long long n = (long long)Cin * Cout * K;
-  B200_CUDA(cudaMalloc(&wp, n * 4));
-  B200_CUDA(cudaMalloc(&scratch, (size_t)B * Cout * stride * 4));
-  B200_LAUNCH(pack_convtr_w_kernel, (unsigned)ceil_div64(n, 256), 256, 0, st, w_dev, wp, Cin, Cout, stride);
-  ConvTrP p;
-  p.x = x_dev; p.xb = (long long)Cin * T; p.xc = T; p.xt = 1; p.T = T;
-  p.partial = partial_dev; p.scratch = scratch; p.w = wp; p.bias = bias_dev;
-  p.y = y_dev; p.yb = (long long)Cout * T * stride; p.yc = (long long)T * stride; p.yt = 1;
-  p.B = B; p.Cin = Cin; p.Cout = Cout; p.S = stride; p.elu_in = elu_in;
-  p.M = Cout * stride; p.N = B * (T + 1); p.Kd = 2 * Cin; p.cin_aligned = (Cin % BK) == 0;
-  auto kern = igemm_f32_kernel<ConvTrP, false>;
-  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-  B200_LAUNCH(kern, grid, 256, 0, st, p);
-  ConvTrCommit tc_;
-  tc_.partial = partial_dev; tc_.scratch = scratch; tc_.per_row = Cout * stride;
-  B200_CUDA(cudaMalloc(&desc, sizeof(ConvTrCommit)));
-  B200_CUDA(cudaMemcpyAsync(desc, &tc_, sizeof(tc_), cudaMemcpyHostToDevice, st));
-  dim3 g2((unsigned)ceil_div64((long long)B * tc_.per_row, 256), 1);
-  B200_LAUNCH(convtr_commit_kernel, g2, 256, 0, st, desc, exec_mask_dev, B);
-  B200_CUDA(cudaStreamSynchronize(st));
-  cudaFree(wp);
-  cudaFree(scratch);
-  cudaFree(desc);
-  return check_launch("op_convtr1d");
-}
-
 int b200_op_attn_step(const void* qkv_dev, void* k_dev, void* v_dev, void* out_dev, const int64_t* pos_dev,
                       const uint8_t* exec_mask_dev, int B, int H, int cap, int nsplit, float max_period, void* stream) {
   using namespace b200::lm;

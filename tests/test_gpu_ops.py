@@ -88,31 +88,6 @@ def test_streaming_conv1d_exec_mask_freezes_state(lib):
     assert torch.equal(prev[0], x[0, :, -2:])
 
 
-@pytest.mark.parametrize("cin,cout,stride,elu", [(64, 32, 4, 1), (1024, 512, 8, 1), (32, 16, 5, 0)])
-def test_streaming_convtr1d_matches_batch(lib, cin, cout, stride, elu):
-    from moshi_b200 import _lib
-    torch.manual_seed(41)
-    B, chunks, T, k = 2, 3, 3, 2 * stride
-    x = torch.randn(B, cin, chunks * T)
-    w = torch.randn(cin, cout, k) / (2 * cin) ** 0.5
-    bias = torch.randn(cout)
-    xin = F.elu(x) if elu else x
-    want = F.conv_transpose1d(xin, w, bias, stride=stride)[..., :chunks * T * stride]
-    partial = torch.zeros(B, cout, stride, device="cuda")
-    mask = torch.ones(B, dtype=torch.bool, device="cuda")
-    wd, bd = w.cuda(), bias.cuda()
-    outs = []
-    for c in range(chunks):
-        xc = x[..., c * T:(c + 1) * T].contiguous().cuda()
-        y = torch.empty(B, cout, T * stride, device="cuda")
-        _lib.check(lib.b200_op_convtr1d(cptr(xc), cptr(wd), cptr(bd), cptr(partial), cptr(mask), cptr(y),
-                                        B, cin, cout, T, k, stride, elu, _stream()))
-        outs.append(y.cpu())
-    got = torch.cat(outs, -1)
-    print(stats(f"convtr {cin}->{cout} s{stride}", got, want))
-    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
-
-
 def _rope_ref(x: torch.Tensor, pos: torch.Tensor, max_period: float = 10000.0) -> torch.Tensor:
     """rope.py:45-82 on [B, H, D] bf16 for one time step at per-row position ``pos``: interleaved pairs, fp32, -> bf16."""
     B, H, D = x.shape
