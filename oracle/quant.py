@@ -34,9 +34,10 @@ def quantize_weight(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return quantize_rows(w.to(torch.float16).float())
 
 
-# QLinear quantises its weight once, at construction (quantize.py:16-21): cache per weight tensor so that stepping a large
-# model does not re-quantise billions of weights every frame.  Keyed by storage address + shape; clear_cache() drops it.
-_QCACHE: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
+# QLinear quantises its weight once, at construction (quantize.py:16-21): cache per weight tensor OBJECT so that stepping a large
+# model does not re-quantise billions of weights every frame.  Keyed by id() and guarded by a weak reference (a storage address
+# alone is reused by the allocator as soon as a tensor dies); clear_cache() drops everything.
+_QCACHE: dict[int, tuple] = {}
 
 
 def clear_cache() -> None:
@@ -44,11 +45,14 @@ def clear_cache() -> None:
 
 
 def cached_quantize_weight(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-    key = (w.data_ptr(), tuple(w.shape), w.dtype)
-    hit = _QCACHE.get(key)
-    if hit is None:
-        hit = _QCACHE[key] = quantize_weight(w)
-    return hit
+    import weakref
+    hit = _QCACHE.get(id(w))
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
+    val = quantize_weight(w)
+    key = id(w)
+    _QCACHE[key] = (weakref.ref(w, lambda _r, k=key: _QCACHE.pop(k, None)), w._version, val)
+    return val
 
 
 def qlinear_f32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
