@@ -75,6 +75,7 @@ struct DepParams {
   const float* noise; long long noise_ld; int noise_off, ka; // Exp(1) noise, row stride, offset of sub-step 0, per-step width
   int use_sampling, top_k; float temp;
   unsigned* bar;                                             // grid barrier counter (zero at launch)
+  unsigned long long* trace;                                 // optional [DEP_TRACE_SLOTS]: %globaltimer of CTA 0 after every grid barrier
 };
 
 namespace {
@@ -84,7 +85,7 @@ struct Pipe { int s; uint32_t ph; int acc; uint32_t acc_bits; int pre; };   // p
 
 // Grid barrier: one release-reduction per CTA and acquire polling by one thread (all CTAs are co-resident).
 // The CTA's own writes are ordered before the reduction by __syncthreads (cumulativity of the gpu-scope release).
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch, unsigned long long* trace = nullptr) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;
@@ -99,6 +100,7 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
         else if (now - t0 > WAIT_LIMIT_NS) __trap();
       }
     }
+    if (trace != nullptr && blockIdx.x == 0 && epoch < (unsigned)DEP_TRACE_SLOTS) trace[epoch] = global_timer_ns();
   }
   __syncthreads();
 }
@@ -388,6 +390,7 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
 
   Pipe pipe{0, 0u, 0, 0u, 0};
   unsigned epoch = 0;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = global_timer_ns();
   // GEMM phases in execution order: per sub-step k, per layer l: in_proj, out_proj, linear_in, linear_out; then the head
   auto gemm_at = [&](int k, int l, int which) -> Gemm {
     Gemm g;
@@ -403,35 +406,35 @@ dep_fused_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_consta
   for (int k = 0; k < p.dep_q; ++k) {
     input_rows(p, k);
     row_phase<4>(p, p.dd, 0, nullptr, 0, false, p.n1[0], red);
-    grid_sync(p.bar, epoch);
+    grid_sync(p.bar, epoch, p.trace);
     for (int l = 0; l < p.L; ++l) {
       Gemm nxt = gemm_at(k, l, 1);
       gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       attn_phase(p, cur.S, l, k);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       cur = nxt; nxt = gemm_at(k, l, 2);
       gemm_phase(p, cur, &nxt, &map_ao, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, p.n2[l], red);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       cur = nxt; nxt = gemm_at(k, l, 3);
       gemm_phase(p, cur, &nxt, &map_xn, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       gate_phase(p, cur.S);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       cur = nxt; nxt = l + 1 < p.L ? gemm_at(k, l + 1, 0) : gemm_at(k, 0, 4);
       gemm_phase(p, cur, &nxt, &map_h, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       // depformer_norms is Identity (lm.py:197-198): after the last layer the head reads x itself
       row_phase<4>(p, p.dd, cur.S, p.part0, cur.N, true, l + 1 < p.L ? p.n1[l + 1] : nullptr, red);
-      grid_sync(p.bar, epoch);
+      grid_sync(p.bar, epoch, p.trace);
       cur = nxt;
     }
     const bool last = k + 1 == p.dep_q;
     Gemm nxt = last ? cur : gemm_at(k + 1, 0, 0);
     gemm_phase(p, cur, last ? nullptr : &nxt, &map_x, base, full0, empty0, tfull0, tempty0, tmem_base, pipe);
-    grid_sync(p.bar, epoch);
+    grid_sync(p.bar, epoch, p.trace);
     sample_phase(p, cur.S, k);       // the next sub-step's input rows are the same rows of the same CTA: no barrier needed
     cur = nxt;
   }
@@ -557,7 +560,7 @@ int dep_fused_create(const DepFusedConfig& c, DepFused** out) {
   p.logits = static_cast<bf16*>(c.logits); p.audio_tokens = c.audio_tokens;
   p.noise = c.noise; p.noise_ld = c.noise_ld; p.noise_off = c.noise_off; p.ka = c.ka;
   p.use_sampling = c.use_sampling; p.top_k = c.top_k; p.temp = c.temp;
-  p.bar = c.bar;
+  p.bar = c.bar; p.trace = c.trace;
   B200_TRY(make_map(enc, &d->map_xn, c.xn, c.B, c.dd, p.Mpad));
   B200_TRY(make_map(enc, &d->map_ao, c.ao, c.B, c.dd, p.Mpad));
   B200_TRY(make_map(enc, &d->map_h, c.hbuf, c.B, c.F, p.Mpad));

@@ -938,6 +938,7 @@ EncodeTiledFn g_encode = nullptr;
 bool g_attr_set = false;
 int g_sms = 0;
 int g_gemv_max_m = 2;            // B200_GEMV_MAX_M (0..4): 0 sends every batch size through the tensor-core GEMM
+int g_use_ns = 1;                // B200_GEMM_NS=0: keep the swap-AB kernels above 32 sessions (A/B measurements)
 
 int init_once() {
   if (!g_encode) {
@@ -958,6 +959,7 @@ int init_once() {
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("B200_GEMV_MAX_M")) g_gemv_max_m = atoi(e);
+    if (const char* e = getenv("B200_GEMM_NS")) g_use_ns = atoi(e);
     g_attr_set = true;
   }
   return B200_OK;
@@ -965,7 +967,7 @@ int init_once() {
 
 }  // namespace
 
-int prepare_plans(GemmPlanCache&) { return init_once(); }
+int prepare_plans(GemmPlanCache&) { B200_TRY(ns_prepare()); return init_once(); }
 
 int sk_num_sms() { return init_once() == B200_OK ? g_sms : 0; }
 
@@ -1123,6 +1125,10 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
     }
   }
   if (tune.norm_alpha) B200_FAIL(B200_ERR_STATE, "sk GEMM: a fused RMSNorm input is only available on the GEMV path (M=%d)", M);
+  // 33..128 sessions: activations as the A operand, two weight tiles (N = 256) per tcgen05.mma (gemm_ns.cu)
+  if (!i8 && tune.ns >= 0 && (tune.ns > 0 || (g_use_ns && M > 32)) && M <= 128 && tune.grid == 0 && tune.cluster == 0 && !tune.stream_only &&
+      !tune.force_split && ns_supported(M, N, K, epi) && ldy % 8 == 0 && (!res || ldr % 8 == 0))
+    return ns_linear(cache, x, ldx, w_tiles, y, ldy, res, ldr, M, N, K, epi, gate_rows, 0, tune.pdl, stream);
   // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM
   if (i8 && (K % 16 || !tune.sa || !tune.sw)) B200_FAIL(B200_ERR_SHAPE, "int8 GEMM: K must be a multiple of 16 and both scale vectors given");
   if (epi != EPI_GATE && tune.no_cluster == 0 && tune.grid == 0 && M > 32) {

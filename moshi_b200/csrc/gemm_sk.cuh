@@ -45,6 +45,7 @@ struct SkTuning {
   // int8 path (QLinear): row-wise absmax int8 activations [M][K] + their scales, and the weight-row scales [N]
   const void* xq = nullptr; const float* sa = nullptr; const float* sw = nullptr;
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
+  int ns = 0;            // 33..128 sessions: 0 = the non-swapped kernel (gemm_ns.cu) unless B200_GEMM_NS=0, -1 = never, 1 = always (tests)
   // GEMV path only (M <= sk_gemv_max_m()): x is the residual stream and the linear's input is rmsnorm(x, norm_alpha)
   const __nv_bfloat16* norm_alpha = nullptr;
 };
@@ -68,6 +69,15 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
               long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
               float* ws, int* counters, const SkTuning& tune, cudaStream_t stream);
 
+// ---- non-swapped kernel for 33..128 sessions (gemm_ns.cu): A = activations, B = two weight tiles (N = 256) ------------
+bool ns_supported(int M, int N, int K, int epi);
+int ns_prepare();
+int ns_default_cluster(int n_units, int num_kb, int epi);
+// cluster: K-splits (0 = ns_default_cluster); same packed weights and epilogues as sk_linear
+int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y, long long ldy,
+              const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows, int cluster, int pdl,
+              cudaStream_t stream);
+
 // ---- the depformer of one frame as one persistent kernel (dep_fused.cu) ---------------------------
 struct DepFusedConfig {
   int B, dd, H, F, card, text_card, dep_q, L;
@@ -80,18 +90,30 @@ struct DepFusedConfig {
   const void* din; long long din_ld;              // depformer_in_all output, bf16 [B][dep_q*dd]
   const long long* text_token;
   void *x, *xn, *ao, *hbuf;                       // bf16 [B][dd] x3, [B][F]
+  void* qkv; float* ssq;                          // cluster kernel only: bf16 [B][3*dd]; fp32 [ceil(dd/128)][B]
   float *part0, *part1;                           // dep_fused_partial_floats() floats each
   void* logits; long long* audio_tokens;          // bf16 [dep_q][B][card], i64 [dep_q][B]
   const float* noise; long long noise_ld; int noise_off, ka;
   int use_sampling, top_k; float temp;
   unsigned* bar;
+  unsigned long long* trace;                       // optional [DEP_TRACE_SLOTS] barrier timestamps of CTA 0 (diagnostics), may be null
 };
+constexpr int DEP_TRACE_SLOTS = 512;
 struct DepFused;
 size_t dep_fused_partial_floats(const DepFusedConfig& c);
 int dep_fused_create(const DepFusedConfig& c, DepFused** out);
 void dep_fused_set_sampling(DepFused* d, int use_sampling, float temp, int top_k);
 void dep_fused_destroy(DepFused* d);
 int dep_fused_launch(DepFused* d, cudaStream_t stream);
+
+// ---- second generation: clusters of 4 CTAs, split-K reduced over DSMEM, epilogues and RMSNorm fused (dep_cluster.cu) ----
+struct DepCluster;
+bool dep_cluster_supported(const DepFusedConfig& c);
+int dep_cluster_create(const DepFusedConfig& c, DepCluster** out);
+void dep_cluster_set_sampling(DepCluster* d, int use_sampling, float temp, int top_k);
+void dep_cluster_destroy(DepCluster* d);
+int dep_cluster_launch(DepCluster* d, cudaStream_t stream);
+int dep_cluster_info(const DepCluster* d, int* clusters, int* w_stages, int* x_stages);
 
 
 

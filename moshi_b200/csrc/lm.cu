@@ -81,11 +81,14 @@ struct b200_lm {
   float* attn_part = nullptr;
   int* attn_counters = nullptr;                // split arrival counters [B*H]
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
+  tc::DepCluster* depc = nullptr;              // second generation (clusters of 4, DSMEM split-K reduction): <= 128 sessions; B200_DEP_KERNEL=1: off
+  float* dep_ssq = nullptr;
   int dep_fused = 1;
   int fuse_norm = 1;                           // B200_FUSE_NORM=0: keep rmsnorm_kernel in front of the GEMV path too (diagnostics)
   int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE: opt-in 8-bit KV ring (B200_KV_FP8_E4M3 or B200_KV_INT8; 0 = bf16)
   float *dep_part0 = nullptr, *dep_part1 = nullptr;
   unsigned* dep_bar = nullptr;
+  unsigned long long* dep_trace = nullptr;     // B200_DEP_TRACE=1: barrier timestamps of the fused depformer (diagnostics)
   int nsplit = 1;
   int n_in_static = 0;
   int noise_static = 0;                        // 1: the captured step draws its own noise
@@ -299,7 +302,9 @@ int step_body(b200_lm* h) {
     return check_launch("lm step (no depformer)");
   }
   B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, MB, c.dep_q * dd, d, LIN_STORE, 0, h->dep_in_s));
-  if (h->depf) {
+  if (h->depc) {
+    B200_TRY(tc::dep_cluster_launch(h->depc, st));
+  } else if (h->depf) {
     B200_TRY(tc::dep_fused_launch(h->depf, st));
   } else {
     for (int k = 0; k < c.dep_q; ++k) {
@@ -517,6 +522,7 @@ int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_te
     return B200_OK;
   h->use_sampling = use_sampling; h->temp = temp; h->temp_text = temp_text; h->top_k = top_k; h->top_k_text = top_k_text;
   tc::dep_fused_set_sampling(h->depf, use_sampling, temp, top_k);
+  tc::dep_cluster_set_sampling(h->depc, use_sampling, temp, top_k);
   drop_graph(h);         // the sampling parameters are kernel arguments of the captured step
   return B200_OK;
 }
@@ -670,6 +676,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   // Under classifier-free guidance the two halves of the batch meet before every sampler (lm.py:828-833): launch chain.
   const bool dep_small = B <= tc::sk_gemv_max_m() && h->dep_fused != 2;
   h->depf = nullptr;
+  h->depc = nullptr;
   if (c.dep_q > 0 && !cfg && !c.quantize && h->dep_fused && !dep_small && B <= 256 && dd <= 1024 && dd % 64 == 0) {
     tc::DepFusedConfig fc;
     memset(&fc, 0, sizeof(fc));
@@ -687,17 +694,30 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     fc.heads = heads.data(); fc.tables = tables.data(); fc.n1 = n1.data(); fc.n2 = n2.data(); fc.kc = kc.data(); fc.vc = vc.data();
     fc.din = h->din; fc.din_ld = (long long)c.dep_q * dd; fc.text_token = h->text_token;
     fc.x = h->dx; fc.xn = h->dxn; fc.ao = h->dao; fc.hbuf = h->dh;
-    size_t pf = tc::dep_fused_partial_floats(fc);
-    B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
-    B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
+    int dep_kernel = 2;
+    if (const char* e = getenv("B200_DEP_KERNEL")) dep_kernel = atoi(e);
+    const bool use_cluster = dep_kernel == 2 && tc::dep_cluster_supported(fc);
+    if (!use_cluster) {
+      const size_t pf = tc::dep_fused_partial_floats(fc);
+      B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
+      B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
+    } else {
+      B200_TRY(A.alloc_t(&h->dep_ssq, (size_t)((dd + 127) / 128) * B));
+      fc.qkv = h->dqkv; fc.ssq = h->dep_ssq;
+    }
     B200_TRY(A.alloc_t(&h->dep_bar, 1));
     fc.part0 = h->dep_part0; fc.part1 = h->dep_part1; fc.bar = h->dep_bar;
+    if (const char* e = getenv("B200_DEP_TRACE")) {
+      if (atoi(e)) B200_TRY(A.alloc_t(&h->dep_trace, (size_t)tc::DEP_TRACE_SLOTS));
+    }
+    fc.trace = h->dep_trace;
     fc.logits = h->dep_logits; fc.audio_tokens = h->audio_tokens;
     fc.noise = h->noise; fc.noise_ld = noise_per_row(h);
     fc.noise_off = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
     fc.ka = h->top_k < c.card ? h->top_k : c.card;
     fc.use_sampling = h->use_sampling; fc.top_k = h->top_k; fc.temp = h->temp;
-    B200_TRY(tc::dep_fused_create(fc, &h->depf));
+    if (use_cluster) B200_TRY(tc::dep_cluster_create(fc, &h->depc));
+    else B200_TRY(tc::dep_fused_create(fc, &h->depf));
   }
   // streaming-state snapshot (lm.py:527-542 _LMGenState + the temporal transformer's ring caches, transformer.py:196-288)
   A.mark_state(h->exec_mask, B, "exec_mask", B200_U8, {B});
@@ -790,6 +810,8 @@ int b200_lm_streaming_end(b200_lm* h) {
   h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->plans.clear();
   tc::dep_fused_destroy(h->depf);
+  tc::dep_cluster_destroy(h->depc);
+  h->depc = nullptr;
   h->depf = nullptr;
   h->state.free_all();
   h->cfg_until = nullptr; h->noise_ctr = nullptr; h->err = nullptr; h->cond_sum = nullptr; h->cond_on = 0;
@@ -994,6 +1016,7 @@ int b200_lm_read_buffer(b200_lm* h, const char* name, void* dst_dev, int64_t cap
   else if (n == "input_tokens") { src = h->input_tokens; sz = (int64_t)MB * h->Kc * 8; }
   else if (n == "text_token") { src = h->text_token; sz = (int64_t)B * 8; }
   else if (n == "audio_tokens") { src = h->audio_tokens; sz = (int64_t)c.dep_q * B * 8; }
+  else if (n == "dep_trace") { src = h->dep_trace; sz = h->dep_trace ? (int64_t)tc::DEP_TRACE_SLOTS * 8 : 0; }
   else if (n == "extra_heads") { src = h->extra_out; sz = (int64_t)h->extra_w.size() * MB * c.extra_heads_dim * 2; }
   else B200_FAIL(B200_ERR_INVALID, "lm_read_buffer: unknown buffer '%s'", n.c_str());
   if (nbytes) *nbytes = sz;

@@ -846,15 +846,30 @@ static __device__ void sample_row(const bf16* __restrict__ logits, const float* 
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> (pass * 8)) & 0xFFu], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned rem = s_remaining, cum = 0;
-      int bin = 255;
-      for (; bin > 0; --bin) {
-        if (cum + hist[bin] >= rem) break;
-        cum += hist[bin];
+    if (tid < 32) {
+      // the bin of the rem-th largest key, scanning the 256 counts from the top: lane l owns bins 8l .. 8l+7, a suffix sum over
+      // the lanes finds the one lane whose bins contain it (the serial scan by one thread cost ~4 us per pass)
+      const unsigned rem = s_remaining;
+      unsigned h8[8], own = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { h8[i] = hist[tid * 8 + i]; own += h8[i]; }
+      unsigned incl = own;                         // counts in this lane's bins and every higher lane's
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (tid + o < 32) incl += v;
       }
-      s_remaining = rem - cum;
-      s_prefix = prefix | ((unsigned)bin << (pass * 8));
+      unsigned cum = incl - own;                   // counts in bins above this lane's
+      if (cum < rem && rem <= incl) {
+        int bin = tid * 8;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+          if (cum + h8[i] >= rem) { bin = tid * 8 + i; break; }
+          cum += h8[i];
+        }
+        s_remaining = rem - cum;
+        s_prefix = prefix | ((unsigned)bin << (pass * 8));
+      }
     }
     __syncthreads();
   }

@@ -60,9 +60,23 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
   // grid > 0: stream-K with that many CTAs; grid < 0: cluster split-K with |grid| CTAs per tile; 0: the LM's own choice
   t.grid = grid > 0 ? grid : 0; t.cluster = grid < 0 ? -grid : 0; t.smem_budget = smem_budget; t.stream_only = stream_only;
   t.force_split = grid > 0;     // an explicit grid (parity tests) exercises the tile-cutting path at every M
+  t.ns = smem_budget == -1 ? -1 : 0;   // smem_budget -1: the swap-AB kernels at any M (comparison row of tools/kbench.py)
+  if (smem_budget < 0) t.smem_budget = 0;
   const int out_cols = epi == 2 ? gate_rows : N;
   return tc::sk_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev),
                        out_cols, static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, ws, counters, t,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// the non-swapped kernel (33..128 sessions in the LM) at any M <= 128; cluster = K-splits (0 = the LM's own choice)
+int b200_op_linear_ns(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N, int K, int epi,
+                      int gate_rows, int cluster, void* stream) {
+  if (!x_dev || !w_tiles_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_ns: null pointer");
+  if (!tc::ns_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_ns: unsupported shape");
+  static tc::GemmPlanCache cache;
+  const int out_cols = epi == 2 ? gate_rows : N;
+  return tc::ns_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev), out_cols,
+                       static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, cluster, 0,
                        static_cast<cudaStream_t>(stream));
 }
 

@@ -168,3 +168,63 @@ def test_gemv_path_equals_tensor_core_path(M, N, K, epi):
     torch.testing.assert_close(y_gemv.float(), want, rtol=2e-2, atol=3e-2)
     assert torch.equal(y_gemv, again)                                   # split partials are summed in split order
     assert ((y_gemv.float() - y_mma.float()).abs() > 0).float().mean() < 0.05      # a bf16 ulp apart now and then
+
+
+def _run_ns(lib, x, wt, res, M, N, K, epi, gate_rows, cluster=0):
+    from moshi_b200 import _lib
+    cols = gate_rows if epi == GATE else N
+    y = torch.full((M, cols), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.b200_op_linear_ns(cptr(x), cptr(wt), cptr(y), cptr(res), M, N, K, epi, gate_rows, cluster, st))
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(33, 4096, 4096, RESADD), (104, 12288, 4096, STORE), (96, 4096, 11264, RESADD),
+                                        (128, 2048, 1024, STORE), (48, 32000, 4096, STORE), (104, 22528, 4096, GATE),
+                                        (64, 5632, 1024, GATE), (40, 200, 520, RESADD), (5, 384, 72, STORE), (77, 608, 136, GATE),
+                                        (104, 8192, 4096, STORE), (1, 256, 512, STORE)])
+def test_ns_gemm(M, N, K, epi):
+    """The non-swapped kernel (csrc/gemm_ns.cu; the LM's linears at 33..128 sessions: activations = UMMA A, two weight tiles = B,
+    N = 256) against fp32 math for the three epilogues, odd tile counts, ragged N / K, every cluster size (K cut over 1..8 CTAs,
+    DSMEM reduce-scatter by output columns), bit-identical repeats, and against the swap-AB kernels (same weights, same cast
+    points: a bf16 ulp apart now and then from the fp32 summation order)."""
+    from moshi_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M * 3 + N + epi)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    gate_rows = N // 2 if epi == GATE else 0
+    cols = gate_rows if epi == GATE else N
+    res = torch.randn(M, cols, generator=g).bfloat16().cuda() if epi == RESADD else None
+    wt = _pack(lib, w, N, K, epi, gate_rows)
+    acc = x.float() @ w.float().t()
+    if epi == STORE:
+        want = acc
+    elif epi == RESADD:
+        want = res.float() + acc.bfloat16().float()
+    else:
+        h = acc.bfloat16()
+        want = (F.silu(h[:, :gate_rows].float()).bfloat16() * h[:, gate_rows:]).float()
+    n_kb = (K + 63) // 64
+    for cs in ((0, 1) if epi == GATE else (0, 1, 2, 3, 4, 8)):
+        if cs > n_kb:
+            continue
+        y = _run_ns(lib, x, wt, res, M, N, K, epi, gate_rows, cluster=cs)
+        print(stats(f"ns {M}x{N}x{K} epi={epi} cluster={cs}", y, want))
+        assert not torch.isnan(y.float()).any()
+        torch.testing.assert_close(y.float(), want, rtol=2e-2, atol=3e-2)
+        assert torch.equal(y, _run_ns(lib, x, wt, res, M, N, K, epi, gate_rows, cluster=cs))
+    # same result as the swap-AB kernels up to summation order
+    from moshi_b200 import _lib as L
+    y_sw = torch.full((M, cols), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(lib.b200_op_linear_sk(cptr(x), cptr(wt), cptr(y_sw), cptr(res), M, N, K, epi, gate_rows, 0, -1, 0, st))
+    torch.cuda.synchronize()
+    y = _run_ns(lib, x, wt, res, M, N, K, epi, gate_rows)
+    assert ((y.float() - y_sw.float()).abs() > 0).float().mean() < 0.05
+    if epi == RESADD:      # in place, as the LM calls it (y == res)
+        inplace = res.clone()
+        L.check(lib.b200_op_linear_ns(cptr(x), cptr(wt), cptr(inplace), cptr(inplace), M, N, K, epi, gate_rows, 0, st))
+        torch.cuda.synchronize()
+        assert torch.equal(inplace, y)

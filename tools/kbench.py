@@ -44,7 +44,7 @@ def time_ms(fn, n_rot: int, iters: int = 20, warm: int = 3) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def bench_gemm(lib, Ms, legacy=True, only=""):
+def bench_gemm(lib, Ms, legacy=True, only="", ns_sweep=False):
     shapes = [  # (name, N, K, epi, gate_rows)
         ("temporal.in_proj", 12288, 4096, 0, 0), ("temporal.out_proj", 4096, 4096, 1, 0),
         ("temporal.linear_in", 22528, 4096, 2, 11264), ("temporal.linear_out", 4096, 11264, 1, 0),
@@ -69,11 +69,19 @@ def bench_gemm(lib, Ms, legacy=True, only=""):
             y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             res = torch.zeros(M, cols, device="cuda", dtype=torch.bfloat16)
             alg = wbytes + M * K * 2 + M * cols * 2 * (2 if epi == 1 else 1)
-            variants = [("sk", 0, 0, 0), ("sk.stream_only", 0, 0, 1)]
+            # "lm": what the LM launches for this shape (GEMV <= 2 rows, swap-AB stream-K <= 32, non-swapped N=256 kernel 33..128);
+            # "swapAB": the swap-AB kernels at any M; "ns.csN": the non-swapped kernel with K cut over N CTAs
+            variants = [("lm", 0, 0, 0), ("swapAB", 0, -1, 0), ("swapAB.stream_only", 0, -1, 1)]
+            if ns_sweep and M <= 128:
+                variants += [(f"ns.cs{c}", -c, 0, 0) for c in ((1,) if epi == 2 else (1, 2, 3, 4, 8))]
             for vname, grid, smem, so in variants:
                 def fn(i):
-                    _lib.check(lib.b200_op_linear_sk(_lib.ptr(x), _lib.ptr(pk[i]), _lib.ptr(y), _lib.ptr(res), M, N, K, epi, gr,
-                                                     grid, smem, so, stream()))
+                    if vname.startswith("ns."):
+                        _lib.check(lib.b200_op_linear_ns(_lib.ptr(x), _lib.ptr(pk[i]), _lib.ptr(y), _lib.ptr(res), M, N, K, epi, gr,
+                                                         -grid, stream()))
+                    else:
+                        _lib.check(lib.b200_op_linear_sk(_lib.ptr(x), _lib.ptr(pk[i]), _lib.ptr(y), _lib.ptr(res), M, N, K, epi, gr,
+                                                         grid, smem, so, stream()))
                 ms = time_ms(fn, n_rot)
                 gbs = alg / ms / 1e6
                 print(json.dumps({"kernel": "linear", "name": name, "M": M, "N": N, "K": K, "impl": vname, "ms": round(ms, 4),
@@ -166,6 +174,7 @@ def main():
     ap.add_argument("--B", default="1,16,96")
     ap.add_argument("--only", default="", help="GEMM shape name filter")
     ap.add_argument("--no-legacy", action="store_true")
+    ap.add_argument("--ns-sweep", action="store_true", help="time the non-swapped GEMM at every cluster size")
     args = ap.parse_args()
     lib = _lib.lib()
     torch.cuda.set_device(0)
@@ -179,7 +188,7 @@ def main():
     if "attn_i8" in what:
         bench_attn_q8(lib, Bs, 2)
     if "gemm" in what:
-        bench_gemm(lib, Ms, legacy=not args.no_legacy, only=args.only)
+        bench_gemm(lib, Ms, legacy=not args.no_legacy, only=args.only, ns_sweep=args.ns_sweep)
     if "mimi" in what:
         bench_mimi(Bs)
 
