@@ -348,6 +348,49 @@ def _secondary_int8_ring(args, lm, mimi, device, free_bytes: int) -> dict:
             "ms_per_step": ms, "value": sessions_sustained(float(B), ms), "steps": steps, "kv_fill": MOSHI_7B.context}
 
 
+def _kv_fill_sweep(lm, mimi, device, free_bytes: int, fills=(2250, 1500, 750), steps: int = 8) -> list:
+    """SECONDARY lines under the REFERENCE's numerics: sessions younger than the 4-minute context do not need a 3000-slot ring.
+    `kv_capacity` (b200_lm_set_kv_capacity) sizes the bf16 rings to the live history: a ring of fill + 64 slots holds exactly the
+    keys the reference's ring holds until the session is that old (nothing is evicted before position 3000), so a pool of
+    sessions with `kv_fill` frames of history fits context / capacity times as many of them in the same HBM (up to the 256 rows
+    the step's kernels take)."""
+    from moshi_b200.serving import DialogueService
+    out = []
+    for fill in fills:
+        capacity = fill + 64
+        per_session = KV_BYTES_PER_SESSION_STEP * capacity + 40e6
+        B = max(1, min(int((free_bytes - 6e9) // per_session), 256))
+        svc = DialogueService(B, lm, mimi, use_sampling=True, temp=0.8, temp_text=0.7, kv_capacity=capacity)
+        gen = svc.lm_gen
+        gen.assume_fill(fill)
+        g = torch.Generator().manual_seed(7 + fill)
+        pcm = [(0.1 * torch.randn(B, 1, 1920, generator=g)).to(device) for _ in range(2)]
+
+        def frame(x):
+            toks = gen.step(mimi.encode(x))
+            audio = toks[:, 1:].clamp(min=0) if toks is not None else torch.zeros(B, 8, 1, dtype=torch.int64, device=device)
+            mimi.decode(audio)
+
+        with torch.no_grad():
+            for i in range(3):
+                frame(pcm[i % 2])
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                frame(pcm[i % 2])
+            e1.record()
+            torch.cuda.synchronize(device)
+            flags = gen.error_flags()
+        ms = e0.elapsed_time(e1) / steps
+        svc.close()
+        torch.cuda.empty_cache()
+        out.append({"kv_fill": fill, "kv_capacity": capacity, "sessions_per_gpu": B, "ms_per_step": ms,
+                    "value": sessions_sustained(float(B), ms), "steps": steps, "stepped_past_capacity": bool(flags & 4),
+                    "kv_ring": "bf16, reference numerics, %d slots (sessions at most %d frames old)" % (capacity, capacity)})
+    return out
+
+
 def b200_arm(args) -> None:
     from moshi_b200 import _lib
     from moshi_b200.config import MOSHI_7B
@@ -453,11 +496,12 @@ def b200_arm(args) -> None:
         torch.cuda.empty_cache()
         roof = _dominant_kernel_roofline(B, kv_fill, device, fp8)
         gemm_roof = None if args.quantize else _gemm_roofline(B, device)
-    lm_b1 = secondary = None
+    lm_b1 = secondary = kv_sweep = None
     if rank == 0 and world == 1:
         lm_b1 = _lm_single_session(lm, device, peak)
         if not args.quantize and not fp8 and not args.skip_secondary:
             secondary = _secondary_int8_ring(args, lm, mimi, device, free)
+            kv_sweep = _kv_fill_sweep(lm, mimi, device, free)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         r = run_cpu_pipeline(steps=3, warmup=1)
@@ -493,6 +537,7 @@ def b200_arm(args) -> None:
                  "frames_per_s_per_gpu": B * 1e3 / max(ms_dev - lm_ms, 1e-6)},
         "lm_b1": lm_b1,
         "secondary": secondary,
+        "kv_fill_sweep": kv_sweep,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

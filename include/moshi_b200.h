@@ -261,6 +261,7 @@ int b200_lm_set_offset_cpu(b200_lm* h, int64_t value);
  * their own synchronisation and return B200_ERR_INVALID. */
 #define B200_FLAG_TOKEN_RANGE 1
 #define B200_FLAG_CODE_RANGE 2
+#define B200_FLAG_KV_CAPACITY 4
 int b200_lm_error_flags(b200_lm* h, int* flags_out);
 /* Algorithmic HBM bytes of one step at the current batch and ring fill: weights once
  * + per-row KV read/append + embeddings + logits. */
@@ -280,6 +281,12 @@ int b200_lm_set_graph(b200_lm* h, int enable);
 #define B200_KV_FP8_E4M3 1
 #define B200_KV_INT8 2
 int b200_lm_set_kv_dtype(b200_lm* h, int kv_dtype);
+/* Slots per temporal KV ring, chosen before b200_lm_streaming_begin (0 or >= context: the reference's ring of `context` slots,
+ * RingKVCache transformer.py:196-288).  A shorter ring holds the same keys as the reference's for a session's first `slots`
+ * frames (nothing is evicted before position `context`), at slots/context of the 1.573 GB per session: a pool of young sessions
+ * ("rings sized to live fill").  A row that steps past the capacity raises B200_FLAG_KV_CAPACITY; the
+ * caller moves such a session to a full-size handle (get / set streaming state) before that. */
+int b200_lm_set_kv_capacity(b200_lm* h, int slots);
 
 /* ------------------------------------------------------------------------------------------ */
 /* One dialogue frame for every session slot: host PCM in, host PCM + tokens out, one host wait  */
@@ -332,7 +339,8 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
                       int K, int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream);
 /* The LM's linear kernel for 33..128 sessions (csrc/gemm_ns.cu): activations as the UMMA A operand, two pre-tiled weight tiles
  * as B (N = 256 per tcgen05.mma), K cut over a cluster of `cluster` CTAs and reduced over distributed shared memory
- * (0 = the LM's own choice); same packed weights and epilogues as b200_op_linear_sk, any M <= 128.
+ * (0 = the LM's own choice; 100 + n = single-tile units, N = 128 per instruction, n K-splits); same packed weights and
+ * epilogues as b200_op_linear_sk, any M <= 128.
  * (b200_op_linear_sk with smem_budget = -1 keeps the swap-AB kernels at every M: the comparison row of tools/kbench.py.) */
 int b200_op_linear_ns(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N, int K,
                       int epi, int gate_rows, int cluster, void* stream);

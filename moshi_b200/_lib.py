@@ -97,6 +97,7 @@ _PROTOTYPES: dict[str, tuple[tp.Any, list]] = {
     "b200_lm_assume_fill": (_I, [_P, _I]),
     "b200_lm_set_graph": (_I, [_P, _I]),
     "b200_lm_set_kv_dtype": (_I, [_P, _I]),
+    "b200_lm_set_kv_capacity": (_I, [_P, _I]),
     "b200_lm_set_cfg": (_I, [_P, C.c_float, _I, _P, _I]),
     "b200_lm_set_condition_sum": (_I, [_P, _P, _I]),
     "b200_lm_seed_noise": (_I, [_P, C.c_uint64]),

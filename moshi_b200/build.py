@@ -12,7 +12,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT_DIR = HERE / "_C"
 LIB = OUT_DIR / "libmoshi_b200.so"
-SOURCES = ["common.cu", "mimi.cu", "lm.cu", "ops.cu", "gemm_sk.cu", "gemm_ns.cu", "dep_fused.cu", "dep_cluster.cu", "frame.cu", "mimi_tc.cu"]
+SOURCES = ["common.cu", "mimi.cu", "lm.cu", "ops.cu", "gemm_sk.cu", "gemm_ns.cu", "dep_fused.cu", "frame.cu", "mimi_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -36,7 +36,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_CS = 8;
 
 struct NsParams {
-  int M, N, K, out_rows, gate_rows, CS, num_kb, kb_per, stages, n_tiles, ldw;
+  int M, N, K, out_rows, gate_rows, CS, num_kb, kb_per, stages, n_tiles, ldw, unit_tiles;
   const uint8_t* wt;
   __nv_bfloat16* y; long long ldy;
   const __nv_bfloat16* res; long long ldr;
@@ -95,7 +95,8 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 2 * TILE_BYTES + A_BYTES;                 // B (two weight tiles) | A (activation box)
+  const uint32_t a_off = (uint32_t)p.unit_tiles * TILE_BYTES;             // stage = B (one or two weight tiles) | A (activation box)
+  const uint32_t stage_bytes = a_off + A_BYTES;
   const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;
   const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull = bars + 16 * MAX_STAGES;
   const uint32_t tptr = tfull + 8;
@@ -107,7 +108,8 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
   const int kb0 = me * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
   const int n_items = kb1 > kb0 ? kb1 - kb0 : 0;
   // weight tiles of this unit: the (gate, value) pair, or row tiles 2u and 2u+1 (the last unit of an odd count has one)
-  const bool two = EPI == EPI_GATE || 2 * unit + 1 < p.n_tiles;
+  const bool two = EPI == EPI_GATE || (p.unit_tiles == 2 && 2 * unit + 1 < p.n_tiles);
+  const int tile0 = EPI == EPI_GATE ? unit : unit * p.unit_tiles;
   const int width = two ? 256 : 128;                                      // accumulator columns in use
   const uint32_t b_bytes = two ? 2u * TILE_BYTES : (uint32_t)TILE_BYTES;
 
@@ -135,8 +137,8 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
         if (EPI == EPI_GATE) {
           bulk_load(sb, p.wt + ((size_t)unit * p.num_kb + kb) * (2 * TILE_BYTES), 2 * TILE_BYTES, full0 + 8 * s);
         } else {
-          bulk_load(sb, p.wt + ((size_t)(2 * unit) * p.num_kb + kb) * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
-          if (two) bulk_load(sb + TILE_BYTES, p.wt + ((size_t)(2 * unit + 1) * p.num_kb + kb) * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
+          bulk_load(sb, p.wt + ((size_t)tile0 * p.num_kb + kb) * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
+          if (two) bulk_load(sb + TILE_BYTES, p.wt + ((size_t)(tile0 + 1) * p.num_kb + kb) * TILE_BYTES, TILE_BYTES, full0 + 8 * s);
         }
       };
       // weights first (they do not depend on the preceding kernel), activations after the dependency wait
@@ -153,7 +155,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
           mbar_expect_tx(full0 + 8 * s, b_bytes + A_BYTES);
           load_b(i, s);
         }
-        tma_load_2d(base + (uint32_t)s * stage_bytes + 2 * TILE_BYTES, &tmap_x, full0 + 8 * s, (kb0 + i) * BLOCK_K, 0);
+        tma_load_2d(base + (uint32_t)s * stage_bytes + a_off, &tmap_x, full0 + 8 * s, (kb0 + i) * BLOCK_K, 0);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -166,7 +168,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         const uint32_t sb = base + (uint32_t)s * stage_bytes;
-        const uint32_t sa = sb + 2 * TILE_BYTES;
+        const uint32_t sa = sb + a_off;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
           umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, (i == 0 && k == 0) ? 0u : 1u);
@@ -241,7 +243,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
         }
       }
     } else {
-      const int nb = unit * 2 * BLOCK_ROWS;
+      const int nb = tile0 * BLOCK_ROWS;
       for (int c = my_c0; c < my_c1; c += 16) {
         float acc[16];
 #pragma unroll
@@ -322,17 +324,30 @@ bool ns_supported(int M, int N, int K, int epi) {
 int ns_prepare() { return ns_init(); }
 
 // K-splits for a shape: as many as keep every CTA of the grid resident at once (units * cs <= #SMs) with >= 4 k-blocks each
-int ns_default_cluster(int n_units, int num_kb, int epi) {
-  if (epi == EPI_GATE) return 1;
-  int best = 1;
-  for (int cs = 2; cs <= MAX_CS; ++cs)
-    if (n_units * cs <= g_ns_sms && num_kb / cs >= 4) best = cs;
-  return best;
+// The LM's choice of unit and K-split for a shape, from measurements on B200 at 48 / 104 sessions
+// (profiles/r02_c_kbench_ns_sweep.jsonl, profiles/r02_d_kbench_ns_sweep_m104.jsonl):
+//   * >= 40 pairs of tiles (in_proj 48, the gated MLP's input 88, the text head 125): N = 256 units, two K-splits while both CTAs
+//     of every unit are resident at once (in_proj: 96 CTAs), else one;
+//   * fewer (out_proj / linear_out: 32 tiles, depformer_in: 64): single-tile units (N = 128) so that more SMs pull on the
+//     weights, K cut over the largest power of two <= 4 that keeps the grid resident (32 x 4, 64 x 2 = 128 CTAs).
+// Wider clusters lose more to the receive traffic (~10 B/clk per SM over DSMEM) and to cluster placement than they gain.
+void ns_default_plan(int n_tiles, int num_kb, int epi, int* unit_tiles, int* cs) {
+  if (epi == EPI_GATE) { *unit_tiles = 2; *cs = 1; return; }
+  const int pairs = (n_tiles + 1) / 2;
+  if (pairs >= 40) {
+    *unit_tiles = 2;
+    *cs = (2 * pairs <= g_ns_sms && num_kb >= 8) ? 2 : 1;
+    return;
+  }
+  *unit_tiles = 1;
+  int c = 1;
+  while (c < 4 && n_tiles * c * 2 <= g_ns_sms && num_kb / (c * 2) >= 4) c *= 2;
+  *cs = c;
 }
 
 int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y, long long ldy,
               const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows, int cluster, int pdl,
-              cudaStream_t stream) {
+              cudaStream_t stream, int unit_tiles) {
   if (!ns_supported(M, N, K, epi) || ldx % 8) B200_FAIL(B200_ERR_SHAPE, "ns GEMM: unsupported shape M=%d N=%d K=%d", M, N, K);
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_tiles) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res)) & 15)
     B200_FAIL(B200_ERR_SHAPE, "ns GEMM: operands must be 16-byte aligned");
@@ -343,8 +358,13 @@ int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.out_rows = epi == EPI_GATE ? gate_rows : N;
   p.n_tiles = (p.out_rows + BLOCK_ROWS - 1) / BLOCK_ROWS;
   p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  const int n_units = epi == EPI_GATE ? p.n_tiles : (p.n_tiles + 1) / 2;
-  int cs = cluster > 0 ? cluster : ns_default_cluster(n_units, p.num_kb, epi);
+  int def_ut = 2, def_cs = 1;
+  ns_default_plan(p.n_tiles, p.num_kb, epi, &def_ut, &def_cs);
+  if (unit_tiles == 0) unit_tiles = cluster > 0 ? 2 : def_ut;
+  p.unit_tiles = (unit_tiles == 1 && epi != EPI_GATE) ? 1 : 2;
+  const uint32_t stage_bytes = (uint32_t)p.unit_tiles * TILE_BYTES + A_BYTES;
+  const int n_units = (epi == EPI_GATE || p.unit_tiles == 1) ? p.n_tiles : (p.n_tiles + 1) / 2;
+  int cs = cluster > 0 ? cluster : def_cs;
   if (epi == EPI_GATE) cs = 1;
   if (cs > MAX_CS) cs = MAX_CS;
   if (cs > p.num_kb) cs = p.num_kb;
@@ -358,7 +378,6 @@ int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   }
   p.ldw = wmax + 4;
   if (((p.ldw / 4) & 1) == 0) p.ldw += 4;
-  const uint32_t stage_bytes = 2 * TILE_BYTES + A_BYTES;
   int stages = (200 * 1024) / (int)stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.kb_per && p.kb_per >= 2) stages = p.kb_per;

@@ -72,11 +72,11 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
 // ---- non-swapped kernel for 33..128 sessions (gemm_ns.cu): A = activations, B = two weight tiles (N = 256) ------------
 bool ns_supported(int M, int N, int K, int epi);
 int ns_prepare();
-int ns_default_cluster(int n_units, int num_kb, int epi);
-// cluster: K-splits (0 = ns_default_cluster); same packed weights and epilogues as sk_linear
+// cluster: K-splits (0 = the measured choice for the shape); same packed weights and epilogues as sk_linear
+// unit_tiles: weight tiles per CTA as the B operand (2 = N 256; 1 = N 128: twice the units for few-tile shapes; 0 = the LM's choice)
 int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const void* w_tiles, __nv_bfloat16* y, long long ldy,
               const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows, int cluster, int pdl,
-              cudaStream_t stream);
+              cudaStream_t stream, int unit_tiles = 0);
 
 // ---- the depformer of one frame as one persistent kernel (dep_fused.cu) ---------------------------
 struct DepFusedConfig {
@@ -90,7 +90,6 @@ struct DepFusedConfig {
   const void* din; long long din_ld;              // depformer_in_all output, bf16 [B][dep_q*dd]
   const long long* text_token;
   void *x, *xn, *ao, *hbuf;                       // bf16 [B][dd] x3, [B][F]
-  void* qkv; float* ssq;                          // cluster kernel only: bf16 [B][3*dd]; fp32 [ceil(dd/128)][B]
   float *part0, *part1;                           // dep_fused_partial_floats() floats each
   void* logits; long long* audio_tokens;          // bf16 [dep_q][B][card], i64 [dep_q][B]
   const float* noise; long long noise_ld; int noise_off, ka;
@@ -105,16 +104,6 @@ int dep_fused_create(const DepFusedConfig& c, DepFused** out);
 void dep_fused_set_sampling(DepFused* d, int use_sampling, float temp, int top_k);
 void dep_fused_destroy(DepFused* d);
 int dep_fused_launch(DepFused* d, cudaStream_t stream);
-
-// ---- second generation: clusters of 4 CTAs, split-K reduced over DSMEM, epilogues and RMSNorm fused (dep_cluster.cu) ----
-struct DepCluster;
-bool dep_cluster_supported(const DepFusedConfig& c);
-int dep_cluster_create(const DepFusedConfig& c, DepCluster** out);
-void dep_cluster_set_sampling(DepCluster* d, int use_sampling, float temp, int top_k);
-void dep_cluster_destroy(DepCluster* d);
-int dep_cluster_launch(DepCluster* d, cudaStream_t stream);
-int dep_cluster_info(const DepCluster* d, int* clusters, int* w_stages, int* x_stages);
-
 
 
 }  // namespace tc

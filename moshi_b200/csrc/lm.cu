@@ -81,10 +81,9 @@ struct b200_lm {
   float* attn_part = nullptr;
   int* attn_counters = nullptr;                // split arrival counters [B*H]
   tc::DepFused* depf = nullptr;                // the depformer of a frame as one persistent kernel (B200_DEP_FUSED=0: off)
-  tc::DepCluster* depc = nullptr;              // second generation (clusters of 4, DSMEM split-K reduction): <= 128 sessions; B200_DEP_KERNEL=1: off
-  float* dep_ssq = nullptr;
   int dep_fused = 1;
   int fuse_norm = 1;                           // B200_FUSE_NORM=0: keep rmsnorm_kernel in front of the GEMV path too (diagnostics)
+  int kv_cap = 0;                              // b200_lm_set_kv_capacity: slots per ring (0 = cfg.context, the reference's ring)
   int kv_fp8 = 0;                              // b200_lm_set_kv_dtype / B200_KV_DTYPE: opt-in 8-bit KV ring (B200_KV_FP8_E4M3 or B200_KV_INT8; 0 = bf16)
   float *dep_part0 = nullptr, *dep_part1 = nullptr;
   unsigned* dep_bar = nullptr;
@@ -106,6 +105,9 @@ struct b200_lm {
 };
 
 namespace {
+
+// slots per temporal KV ring: the reference's context unless b200_lm_set_kv_capacity shortened it
+inline int ring_cap(const b200_lm* h) { return h->kv_cap > 0 && h->kv_cap < h->cfg.context ? h->kv_cap : h->cfg.context; }
 
 int get_bf16(b200_lm* h, const std::string& name, std::vector<int64_t> shape, const bf16** out) {
   const Tensor* t = h->store.find(name);
@@ -257,12 +259,14 @@ int step_body(b200_lm* h) {
     const long long n = (long long)B * noise_per_row(h);
     B200_LAUNCH(lm_noise_kernel, (unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, st, h->noise, n, h->noise_seed, h->noise_ctr);
   }
+  if (ring_cap(h) < c.context)      // a shortened ring serves a session only until it is full: flag instead of silently forgetting
+    B200_LAUNCH(kv_capacity_check_kernel, ceil_div(MB, 128), 128, 0, st, h->pos, h->exec_mask_m, MB, ring_cap(h), h->err);
   for (auto& L : h->layers) {
     B200_TRY(norm_linear(h, h->x, L.n1, h->xn, L.in_w, h->qkv, 3 * d, MB, 3 * d, d, LIN_STORE, 0, L.in_s));
     if (h->kv_fp8) {
       AttnStepQ8 a;
       a.qkv = h->qkv; a.kc = L.kc8; a.vc = L.vc8; a.ks = L.ks; a.vs = L.vs; a.out = h->ao; a.part = h->attn_part;
-      a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask_m; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+      a.counters = h->attn_counters; a.pos = h->pos; a.exec_mask = h->exec_mask_m; a.H = H; a.cap = ring_cap(h); a.nsplit = h->nsplit;
       a.neg_log_period_2_over_d = nl;
       dim3 grid(MB * H, h->nsplit);
       if (h->kv_fp8 == B200_KV_INT8) B200_LAUNCH(attn_step_q8_kernel<KV_INT8>, grid, ATT_THREADS, 0, st, a);
@@ -270,7 +274,7 @@ int step_body(b200_lm* h) {
     } else {   // RoPE + ring append + split-KV attention + split merge in one launch
       AttnStep a;
       a.qkv = h->qkv; a.kc = L.kc; a.vc = L.vc; a.out = h->ao; a.part = h->attn_part; a.counters = h->attn_counters;
-      a.pos = h->pos; a.exec_mask = h->exec_mask_m; a.H = H; a.cap = c.context; a.nsplit = h->nsplit;
+      a.pos = h->pos; a.exec_mask = h->exec_mask_m; a.H = H; a.cap = ring_cap(h); a.nsplit = h->nsplit;
       a.neg_log_period_2_over_d = nl;
       dim3 grid(MB * H, h->nsplit);
       if (attn_group_keys() == 2) B200_LAUNCH(attn_step_kernel<2>, grid, ATT_THREADS, 0, st, a);
@@ -302,9 +306,7 @@ int step_body(b200_lm* h) {
     return check_launch("lm step (no depformer)");
   }
   B200_TRY(linear(h, h->tout, d, h->dep_in_all, h->din, (long long)c.dep_q * dd, nullptr, 0, MB, c.dep_q * dd, d, LIN_STORE, 0, h->dep_in_s));
-  if (h->depc) {
-    B200_TRY(tc::dep_cluster_launch(h->depc, st));
-  } else if (h->depf) {
+  if (h->depf) {
     B200_TRY(tc::dep_fused_launch(h->depf, st));
   } else {
     for (int k = 0; k < c.dep_q; ++k) {
@@ -522,7 +524,6 @@ int b200_lm_set_sampling(b200_lm* h, int use_sampling, float temp, float temp_te
     return B200_OK;
   h->use_sampling = use_sampling; h->temp = temp; h->temp_text = temp_text; h->top_k = top_k; h->top_k_text = top_k_text;
   tc::dep_fused_set_sampling(h->depf, use_sampling, temp, top_k);
-  tc::dep_cluster_set_sampling(h->depc, use_sampling, temp, top_k);
   drop_graph(h);         // the sampling parameters are kernel arguments of the captured step
   return B200_OK;
 }
@@ -578,7 +579,8 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   struct Cleanup { b200_lm* h; bool armed = true; ~Cleanup() { if (armed) { h->state.free_all(); h->cfg_until = nullptr; h->noise_ctr = nullptr; } } } cleanup{h};
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  const size_t kv_bytes = (size_t)c.num_layers * 2 * MB * H * c.context * (h->kv_fp8 ? (size_t)D + 4 : (size_t)D * 2);
+  const int cap = ring_cap(h);
+  const size_t kv_bytes = (size_t)c.num_layers * 2 * MB * H * cap * (h->kv_fp8 ? (size_t)D + 4 : (size_t)D * 2);
   if (kv_bytes + (1ull << 30) > free_b)
     B200_FAIL(B200_ERR_INVALID, "lm_streaming_begin: %d sessions need %.1f GB of KV ring, %.1f GB free", B, kv_bytes / 1e9,
               free_b / 1e9);
@@ -607,13 +609,13 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   h->offset_cpu = 0;
   for (auto& L : h->layers) {
     if (h->kv_fp8) {
-      B200_TRY(A.alloc_t(&L.kc8, (size_t)MB * H * c.context * D));
-      B200_TRY(A.alloc_t(&L.vc8, (size_t)MB * H * c.context * D));
-      B200_TRY(A.alloc_t(&L.ks, (size_t)MB * H * c.context));
-      B200_TRY(A.alloc_t(&L.vs, (size_t)MB * H * c.context));
+      B200_TRY(A.alloc_t(&L.kc8, (size_t)MB * H * cap * D));
+      B200_TRY(A.alloc_t(&L.vc8, (size_t)MB * H * cap * D));
+      B200_TRY(A.alloc_t(&L.ks, (size_t)MB * H * cap));
+      B200_TRY(A.alloc_t(&L.vs, (size_t)MB * H * cap));
     } else {
-      B200_TRY(A.alloc_t(&L.kc, (size_t)MB * H * c.context * D));
-      B200_TRY(A.alloc_t(&L.vc, (size_t)MB * H * c.context * D));
+      B200_TRY(A.alloc_t(&L.kc, (size_t)MB * H * cap * D));
+      B200_TRY(A.alloc_t(&L.vc, (size_t)MB * H * cap * D));
     }
   }
   for (auto& L : h->dlayers) {
@@ -656,7 +658,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   B200_TRY(A.alloc_t(&h->dep_logits, (size_t)MB * dq1 * c.card));
   B200_TRY(A.alloc(reinterpret_cast<void**>(&h->sk_ws), tc::sk_workspace_bytes(MB), false));
   B200_TRY(A.alloc_t(&h->sk_counters, tc::SK_MAX_TILES));
-  const int ns = attn_pick_splits(MB, H, c.context);
+  const int ns = attn_pick_splits(MB, H, cap);
   h->nsplit = ns;
   B200_TRY(A.alloc_t(&h->attn_part, (size_t)MB * H * ns * (ATT_D + 2)));
   B200_TRY(A.alloc_t(&h->attn_counters, (size_t)MB * H));
@@ -676,7 +678,6 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
   // Under classifier-free guidance the two halves of the batch meet before every sampler (lm.py:828-833): launch chain.
   const bool dep_small = B <= tc::sk_gemv_max_m() && h->dep_fused != 2;
   h->depf = nullptr;
-  h->depc = nullptr;
   if (c.dep_q > 0 && !cfg && !c.quantize && h->dep_fused && !dep_small && B <= 256 && dd <= 1024 && dd % 64 == 0) {
     tc::DepFusedConfig fc;
     memset(&fc, 0, sizeof(fc));
@@ -694,17 +695,9 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     fc.heads = heads.data(); fc.tables = tables.data(); fc.n1 = n1.data(); fc.n2 = n2.data(); fc.kc = kc.data(); fc.vc = vc.data();
     fc.din = h->din; fc.din_ld = (long long)c.dep_q * dd; fc.text_token = h->text_token;
     fc.x = h->dx; fc.xn = h->dxn; fc.ao = h->dao; fc.hbuf = h->dh;
-    int dep_kernel = 2;
-    if (const char* e = getenv("B200_DEP_KERNEL")) dep_kernel = atoi(e);
-    const bool use_cluster = dep_kernel == 2 && tc::dep_cluster_supported(fc);
-    if (!use_cluster) {
-      const size_t pf = tc::dep_fused_partial_floats(fc);
-      B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
-      B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
-    } else {
-      B200_TRY(A.alloc_t(&h->dep_ssq, (size_t)((dd + 127) / 128) * B));
-      fc.qkv = h->dqkv; fc.ssq = h->dep_ssq;
-    }
+    const size_t pf = tc::dep_fused_partial_floats(fc);
+    B200_TRY(A.alloc_t(&h->dep_part0, pf, false));
+    B200_TRY(A.alloc_t(&h->dep_part1, pf, false));
     B200_TRY(A.alloc_t(&h->dep_bar, 1));
     fc.part0 = h->dep_part0; fc.part1 = h->dep_part1; fc.bar = h->dep_bar;
     if (const char* e = getenv("B200_DEP_TRACE")) {
@@ -716,8 +709,7 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     fc.noise_off = h->top_k_text < c.text_card ? h->top_k_text : c.text_card;
     fc.ka = h->top_k < c.card ? h->top_k : c.card;
     fc.use_sampling = h->use_sampling; fc.top_k = h->top_k; fc.temp = h->temp;
-    if (use_cluster) B200_TRY(tc::dep_cluster_create(fc, &h->depc));
-    else B200_TRY(tc::dep_fused_create(fc, &h->depf));
+    B200_TRY(tc::dep_fused_create(fc, &h->depf));
   }
   // streaming-state snapshot (lm.py:527-542 _LMGenState + the temporal transformer's ring caches, transformer.py:196-288)
   A.mark_state(h->exec_mask, B, "exec_mask", B200_U8, {B});
@@ -730,13 +722,13 @@ int b200_lm_streaming_begin(b200_lm* h, int batch, void* stream) {
     auto& L = h->layers[l];
     const std::string p = "layers." + std::to_string(l);
     if (h->kv_fp8) {
-      A.mark_state(L.kc8, (size_t)MB * H * c.context * D, p + ".k8", B200_U8, {MB, H, c.context, D});
-      A.mark_state(L.vc8, (size_t)MB * H * c.context * D, p + ".v8", B200_U8, {MB, H, c.context, D});
-      A.mark_state(L.ks, (size_t)MB * H * c.context * 4, p + ".k_scale", B200_F32, {MB, H, c.context});
-      A.mark_state(L.vs, (size_t)MB * H * c.context * 4, p + ".v_scale", B200_F32, {MB, H, c.context});
+      A.mark_state(L.kc8, (size_t)MB * H * cap * D, p + ".k8", B200_U8, {MB, H, cap, D});
+      A.mark_state(L.vc8, (size_t)MB * H * cap * D, p + ".v8", B200_U8, {MB, H, cap, D});
+      A.mark_state(L.ks, (size_t)MB * H * cap * 4, p + ".k_scale", B200_F32, {MB, H, cap});
+      A.mark_state(L.vs, (size_t)MB * H * cap * 4, p + ".v_scale", B200_F32, {MB, H, cap});
     } else {
-      A.mark_state(L.kc, (size_t)MB * H * c.context * D * 2, p + ".k", B200_BF16, {MB, H, c.context, D});
-      A.mark_state(L.vc, (size_t)MB * H * c.context * D * 2, p + ".v", B200_BF16, {MB, H, c.context, D});
+      A.mark_state(L.kc, (size_t)MB * H * cap * D * 2, p + ".k", B200_BF16, {MB, H, cap, D});
+      A.mark_state(L.vc, (size_t)MB * H * cap * D * 2, p + ".v", B200_BF16, {MB, H, cap, D});
     }
   }
   B200_CUDA(cudaDeviceSynchronize());
@@ -810,8 +802,6 @@ int b200_lm_streaming_end(b200_lm* h) {
   h->gstream = nullptr; h->ev_in = h->ev_out = nullptr;
   h->plans.clear();
   tc::dep_fused_destroy(h->depf);
-  tc::dep_cluster_destroy(h->depc);
-  h->depc = nullptr;
   h->depf = nullptr;
   h->state.free_all();
   h->cfg_until = nullptr; h->noise_ctr = nullptr; h->err = nullptr; h->cond_sum = nullptr; h->cond_on = 0;
@@ -867,6 +857,14 @@ int b200_lm_set_kv_dtype(b200_lm* h, int kv_dtype) {
   if (kv_dtype != B200_KV_BF16 && kv_dtype != B200_KV_FP8_E4M3 && kv_dtype != B200_KV_INT8)
     B200_FAIL(B200_ERR_INVALID, "lm_set_kv_dtype: unknown dtype %d", kv_dtype);
   h->kv_fp8 = kv_dtype;
+  return B200_OK;
+}
+
+int b200_lm_set_kv_capacity(b200_lm* h, int slots) {
+  if (!h) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_capacity: null handle");
+  if (h->batch > 0) B200_FAIL(B200_ERR_STATE, "lm_set_kv_capacity: the rings are allocated at streaming_begin; set the capacity before it");
+  if (slots < 0) B200_FAIL(B200_ERR_INVALID, "lm_set_kv_capacity: negative capacity");
+  h->kv_cap = slots >= h->cfg.context ? 0 : slots;
   return B200_OK;
 }
 
@@ -989,6 +987,8 @@ int b200_lm_step_host(b200_lm* h, const int64_t* in_codes_host, int n_in, const 
   if (ready_host) *ready_host = (support_out_of_sync || h->offset_cpu > h->max_delay) ? 1 : 0;
   if (flags) {
     cudaMemsetAsync(h->err, 0, 4, h->stream);
+    if (flags & lm::ERR_KV_CAPACITY)
+      B200_FAIL(B200_ERR_STATE, "lm_step_host: a session stepped past its %d-slot KV ring (b200_lm_set_kv_capacity; flags %d)", ring_cap(h), flags);
     B200_FAIL(B200_ERR_INVALID, "lm_step_host: a token id outside its embedding table reached the model (flags %d)", flags);
   }
   return B200_OK;

@@ -48,7 +48,7 @@ struct TokenRing {
 
 // device error flags: raised instead of reading out of bounds; surfaced by b200_lm_error_flags / b200_mimi_error_flags and by
 // the host-synchronising entry points
-enum { ERR_TOKEN_RANGE = 1, ERR_CODE_RANGE = 2 };
+enum { ERR_TOKEN_RANGE = 1, ERR_CODE_RANGE = 2, ERR_KV_CAPACITY = 4 };
 
 // One thread per (b, k): write the user's codes, then build the model input row(s) [MB][Kc].
 static __global__ void lm_prepare_kernel(const TokenRing r, const long long* __restrict__ in_codes, int n_in,
@@ -768,6 +768,15 @@ static __global__ void replace_audio_kernel(const long long* __restrict__ given,
   if (i >= B * dep_q) return;
   const int b = i / dep_q, k = i - b * dep_q;
   audio_tokens[(long long)k * B + b] = given[i];
+}
+
+// rings shorter than the model's context (b200_lm_set_kv_capacity): a row about to write position >= cap would overwrite keys the
+// reference still attends to -> ERR_KV_CAPACITY (the step still runs, as a ring of `cap` slots)
+static __global__ void kv_capacity_check_kernel(const long long* __restrict__ pos, const uint8_t* __restrict__ exec_mask, int B, int cap,
+                                                int* err) {
+  pdl_trigger();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && exec_mask[b] && pos[b] >= cap && err != nullptr) atomicOr(err, ERR_KV_CAPACITY);
 }
 
 static __global__ void advance_pos_kernel(long long* pos, const uint8_t* exec_mask, int B) {

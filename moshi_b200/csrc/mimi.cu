@@ -487,8 +487,16 @@ int encode_body(b200_mimi* h) {
     p.B = h->batch; p.Cin = l.cin; p.Cout = l.cout; p.K = l.k; p.stride = l.stride; p.dil = 1; p.Tout = l.t_out;
     p.elu_in = 0;
     p.M = l.cout; p.N = h->batch * l.t_out; p.Kd = l.cin * l.k; p.cin_aligned = (l.cin % BK) == 0;
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
+    const int KS = ceil_div(p.Kd, DS_KP);
+    if ((size_t)KS * p.N * p.M * 4 <= h->splitk_bytes) {
+      // deep and skinny (2048 reduction steps, N = sessions): the reduction cut over KS CTAs per 64 outputs, slices added in order
+      dim3 g1(ceil_div(p.M, DS_CO), KS);
+      B200_LAUNCH(conv_splitk_kernel, g1, 256, 0, h->body, p, h->splitk_ws, KS);
+      B200_LAUNCH(conv_splitk_reduce_kernel, (unsigned)ceil_div64((long long)p.N * p.M, 256), 256, 0, h->body, p, h->splitk_ws, KS);
+    } else {
+      dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+      B200_LAUNCH((igemm_f32_kernel<ConvP, false>), grid, 256, 0, h->body, p);
+    }
   }
   B200_TRY(commit_states(h, true));
   return B200_OK;

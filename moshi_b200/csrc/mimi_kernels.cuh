@@ -68,6 +68,71 @@ struct ConvP {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Deep-and-skinny convolution (the learnt down-sampling conv, resample.py:14-65: Cin = Cout = 512, K = 4, one output step
+// per frame): N = sessions x T_out columns against K * Cin = 2048 reduction steps and 4 MB of weights.  As a plain tile
+// GEMM that is 16 CTAs walking 2048 k each (249 us at 104 sessions, 209 us at one); here the reduction is cut into KS
+// slices so that (Cout / 64) x KS CTAs stream the weights once, and a second pass adds the slices in slice order
+// (deterministic).  Same ext() semantics as ConvP (carried left context, replicate padding on a session's first frame).
+// ---------------------------------------------------------------------------------------------
+constexpr int DS_CO = 64, DS_KP = 64, DS_NC = 32;
+static __global__ void __launch_bounds__(256) conv_splitk_kernel(const ConvP p, float* __restrict__ part, int KS) {
+  __shared__ float ws[DS_KP][DS_CO + 1];
+  __shared__ float xs[DS_KP][DS_NC + 1];
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.x * DS_CO, k0 = blockIdx.y * DS_KP;
+  for (int idx = tid; idx < DS_CO * DS_KP; idx += 256) {
+    const int co = idx / DS_KP, kk = idx - co * DS_KP;
+    ws[kk][co] = (co0 + co < p.M && k0 + kk < p.Kd) ? p.w[(long long)(co0 + co) * p.Kd + k0 + kk] : 0.f;
+  }
+  const int co = tid & 63, ng = tid >> 6;
+  for (int n0 = 0; n0 < p.N; n0 += DS_NC) {
+    __syncthreads();
+    for (int idx = tid; idx < DS_KP * DS_NC; idx += 256) {
+      const int n = idx / DS_KP, kk = idx - n * DS_KP;
+      float v = 0.f;
+      if (n0 + n < p.N && k0 + kk < p.Kd) {
+        const int b = (n0 + n) / p.Tout, t = (n0 + n) - b * p.Tout;
+        const int kw = (k0 + kk) / p.Cin, ci = (k0 + kk) - kw * p.Cin;
+        v = p.ext(b, ci, t * p.stride + kw * p.dil);
+      }
+      xs[kk][n] = v;
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 8
+    for (int kk = 0; kk < DS_KP; ++kk) {
+      const float w = ws[kk][co];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, xs[kk][ng * 8 + j], acc[j]);
+    }
+    if (co0 + co < p.M) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = n0 + ng * 8 + j;
+        if (n < p.N) part[((long long)blockIdx.y * p.N + n) * p.M + co0 + co] = acc[j];
+      }
+    }
+  }
+  (void)KS;
+}
+static __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const ConvP p, const float* __restrict__ part, int KS) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)p.N * p.M) return;
+  const int n = (int)(i / p.M), m = (int)(i - (long long)n * p.M);
+  float a = 0.f;
+  for (int s0 = 0; s0 < KS; s0 += 8) {            // 8 independent loads in flight, added in slice order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = s0 + j < KS ? part[((long long)(s0 + j) * p.N + n) * p.M + m] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += v[j];
+  }
+  p.store(m, n, a);
+}
+
 template <class P, bool B_K_FAST>
 static __global__ void __launch_bounds__(256) igemm_f32_kernel(const P p) {
   __shared__ float As[2][BK][BM + 4];

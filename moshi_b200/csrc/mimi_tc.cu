@@ -1,4 +1,7 @@
 // mimi_tc_kernel: persistent TMA + tcgen05 kind::tf32 implicit GEMM with 3xTF32 split products (see mimi_tc.cuh).
+#include <cstdlib>
+#include <cstring>
+
 #include "mimi_tc.cuh"
 #include "tc_prims.cuh"
 
@@ -115,23 +118,40 @@ mimi_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tptr_generic;
+  pdl_trigger();                                 // the next kernel of the frame may begin its own prologue and weight prefetch
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== producer =====
+      // Programmatic dependent launch: the weights do not depend on the preceding kernel, so the first `stages` weight pairs of
+      // this CTA's first tile are requested before the dependency wait (their HBM latency overlaps the predecessor's tail and
+      // this kernel's own launch); the activation boxes, and everything the epilogue touches, come after it.
+      int pre = 0;
+      if ((int)blockIdx.x < n_tiles) {
+        const Tile t0 = tile_at(p, blockIdx.x);
+        const uint8_t* wsrc = p.wt + ((size_t)t0.n * p.num_kb + t0.kb0) * (size_t)(2 * w_bytes);
+        for (int kb = t0.kb0; kb < t0.kb1 && pre < p.stages; ++kb, wsrc += 2 * w_bytes, ++pre) {
+          mbar_expect_tx(full0 + 8 * pre, 2 * A_TILE_BYTES + 2 * w_bytes);
+          bulk_load(base + (uint32_t)pre * p.stage_bytes + 2 * A_TILE_BYTES, wsrc, 2 * w_bytes, full0 + 8 * pre);
+        }
+      }
+      pdl_wait();
       int s = 0; uint32_t ph = 0;
+      int item = 0;
       for (int id = blockIdx.x; id < n_tiles; id += gridDim.x) {
         const Tile tl = tile_at(p, id);
         const uint8_t* wsrc = p.wt + ((size_t)tl.n * p.num_kb + tl.kb0) * (size_t)(2 * w_bytes);
-        for (int kb = tl.kb0; kb < tl.kb1; ++kb, wsrc += 2 * w_bytes) {
+        for (int kb = tl.kb0; kb < tl.kb1; ++kb, wsrc += 2 * w_bytes, ++item) {
           const int tap = kb / cb_per_tap, cb = kb - tap * cb_per_tap;
           const uint32_t sa = base + (uint32_t)s * p.stage_bytes;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          mbar_expect_tx(full0 + 8 * s, 2 * A_TILE_BYTES + 2 * w_bytes);
+          if (item >= pre) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            mbar_expect_tx(full0 + 8 * s, 2 * A_TILE_BYTES + 2 * w_bytes);
+            bulk_load(sa + 2 * A_TILE_BYTES, wsrc, 2 * w_bytes, full0 + 8 * s);
+          }
           const int row = p.row0 + tl.t0 * p.stride + tap * p.dil;
           tma_load_3d(sa, &map_hi, full0 + 8 * s, cb * TC_KB, row, tl.b0);
           tma_load_3d(sa + A_TILE_BYTES, &map_lo, full0 + 8 * s, cb * TC_KB, row, tl.b0);
-          bulk_load(sa + 2 * A_TILE_BYTES, wsrc, 2 * w_bytes, full0 + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -175,6 +195,7 @@ mimi_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const int row = q * 32 + lane;
     const int bi = row / p.tt, ti = row - bi * p.tt;
     int acc = 0; uint32_t acc_bits = 0u;
+    pdl_wait();                                  // outputs / residuals / the split-K workspace may still be in use by the predecessor
     for (int id = blockIdx.x; id < n_tiles; id += gridDim.x) {
       const Tile tl = tile_at(p, id);
       const int b = tl.b0 + bi, t = tl.t0 + ti;
@@ -212,6 +233,7 @@ mimi_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 
 // split-K: sum the partials in split order (deterministic) and run the epilogue; one thread per (row, 4 features)
 __global__ void __launch_bounds__(256) mimi_tc_reduce_kernel(const TcParams p) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n4 = p.N / 4;
   const long long rows = (long long)p.m_tiles * TC_ROWS;
@@ -350,7 +372,18 @@ int tc_plan(TcLayer& L, int n_sessions, int T, int sms, size_t ws_bytes) {
 }
 
 int tc_launch(const TcLayer& L, cudaStream_t st) {
-  mimi_tc_kernel<<<L.grid, TC_THREADS, L.smem, st>>>(L.map_hi, L.map_lo, L.p);
+  // programmatic dependent launch (B200_MIMI_PDL=0: off): the kernel may start while its predecessor drains; it requests its
+  // first weight tiles, then waits (griddepcontrol.wait) before it reads an activation or writes anything
+  static const int pdl = [] { const char* e = getenv("B200_MIMI_PDL"); return e ? atoi(e) : 1; }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, mimi_tc_kernel, L.map_hi, L.map_lo, L.p);
+  if (le != cudaSuccess) B200_FAIL(B200_ERR_CUDA, "mimi_tc launch failed: %s", cudaGetErrorString(le));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (L.p.ksplit > 1) {
     const long long n = (long long)L.p.m_tiles * TC_ROWS * (L.p.N / 4);

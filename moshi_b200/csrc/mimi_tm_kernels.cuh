@@ -9,6 +9,10 @@
 namespace b200 {
 namespace mimi {
 
+// lets a following mimi_tc_kernel (launched with programmatic stream serialization) start its prologue and weight prefetch
+// while this kernel runs; that kernel waits (griddepcontrol.wait) before it touches activations
+__device__ __forceinline__ void pdl_trigger_next() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // First encoder conv (Cin = 1, K <= 8; seanet.py:170-178): memory-bound, one thread per (b, t) produces all Cout channels.
 //   in: ext[b][P + T] fp32 (carried samples | frame);  out: raw y[b][t][co] and the consumer's ELU(y) as a hi / lo pair
@@ -21,6 +25,7 @@ struct ConvFirst {
   int B, Cout, K, T;
 };
 static __global__ void __launch_bounds__(128) conv_first_tm_kernel(const ConvFirst p) {
+  pdl_trigger_next();
   extern __shared__ float sw[];              // [K][Cout] then bias [Cout]
   for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[(i % p.K) * p.Cout + i / p.K] = p.w[i];
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[p.Cout * p.K + i] = p.bias ? p.bias[i] : 0.f;
@@ -88,6 +93,7 @@ static __global__ void __launch_bounds__(128) conv_last_tm_kernel(const ConvLast
 // ---------------------------------------------------------------------------------------------
 struct TmCommit { float* hi; float* lo; int P, T, rowlen; long long sb; };       // rowlen = Cin floats per row
 static __global__ void tm_commit_kernel(const TmCommit* descs, const uint8_t* exec_mask, int B) {
+  pdl_trigger_next();
   const TmCommit d = descs[blockIdx.y];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, ci)
   if (i >= (long long)B * d.rowlen) return;
@@ -115,6 +121,7 @@ static __global__ void tm_zero_kernel(float* hi, float* lo, int P, int rowlen, l
 // LayerNorm (eps 1e-5, affine; transformer.py:126) -> the following linear's input as a hi / lo pair
 static __global__ void layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                                        float* __restrict__ y_hi, float* __restrict__ y_lo, int n_tok, int C, float eps) {
+  pdl_trigger_next();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_tok) return;
   const float* xr = x + (long long)warp * C;
@@ -142,6 +149,7 @@ static __global__ void __launch_bounds__(128) ring_attn_step_kernel(const float*
                                                              float* __restrict__ out_lo, const long long* __restrict__ offset,
                                                              const uint8_t* __restrict__ exec_mask, int T, int H, int cap,
                                                              int context, float neg_log_period_2_over_d) {
+  pdl_trigger_next();
   extern __shared__ float sm[];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int C = H * D;

@@ -75,9 +75,12 @@ int b200_op_linear_ns(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
   if (!tc::ns_supported(M, N, K, epi)) B200_FAIL(B200_ERR_SHAPE, "op_linear_ns: unsupported shape");
   static tc::GemmPlanCache cache;
   const int out_cols = epi == 2 ? gate_rows : N;
+  // cluster >= 100: single-tile units (N = 128 per instruction) with cluster - 100 K-splits
+  const int unit_tiles = cluster >= 100 ? 1 : (cluster > 0 ? 2 : 0);
+  if (cluster >= 100) cluster -= 100;
   return tc::ns_linear(cache, static_cast<const __nv_bfloat16*>(x_dev), K, w_tiles_dev, static_cast<__nv_bfloat16*>(y_dev), out_cols,
                        static_cast<const __nv_bfloat16*>(res_dev), out_cols, M, N, K, epi, gate_rows, cluster, 0,
-                       static_cast<cudaStream_t>(stream));
+                       static_cast<cudaStream_t>(stream), unit_tiles);
 }
 
 int b200_op_set_gemv_max_rows(int max_rows) { return tc::sk_set_gemv_max_m(max_rows); }

@@ -175,6 +175,9 @@ class LMGen:
         self.use_graph = True
         # "bf16" = the reference's ring; "fp8_e4m3" / "int8" = opt-in extensions outside the reference's numerics (half the ring)
         self.kv_dtype = "bf16"
+        # slots per temporal KV ring; None = the model's context (the reference's RingKVCache).  A pool of sessions younger than
+        # `kv_capacity` frames holds the same keys in kv_capacity / context of the memory; stepping past it raises error flag 4
+        self.kv_capacity: int | None = None
 
     # ---- plumbing ---------------------------------------------------------------------------------
     def _device(self):
@@ -222,6 +225,7 @@ class LMGen:
             if self.kv_dtype not in kinds:
                 raise ValueError(f"kv_dtype {self.kv_dtype!r}: expected one of {sorted(kinds)}")
             _lib.check(self._lib.b200_lm_set_kv_dtype(self._h, kinds[self.kv_dtype]))
+            _lib.check(self._lib.b200_lm_set_kv_capacity(self._h, int(self.kv_capacity or 0)))
             until = None
             if self.cfg_coef != 1. and self.cfg_is_masked_until is not None:
                 until = (C.c_int64 * len(self.cfg_is_masked_until))(*[int(v) for v in self.cfg_is_masked_until])
@@ -391,7 +395,8 @@ class LMGen:
         return out
 
     def error_flags(self) -> int:
-        """Synchronises and returns (and clears) the device error flags (1 = a token id outside its embedding table)."""
+        """Synchronises and returns (and clears) the device error flags (1 = a token id outside its embedding table, 4 = a session
+        stepped past a shortened KV ring, `kv_capacity`)."""
         v = C.c_int(0)
         with self._device():
             _lib.check(self._lib.b200_lm_error_flags(self._h, C.byref(v)))

@@ -77,7 +77,7 @@ class DialogueService:
     """
 
     def __init__(self, batch_size: int, lm, mimi, use_sampling: bool = True, temp: float = 0.8, temp_text: float = 0.7,
-                 top_k: int = 250, top_k_text: int = 25, kv_dtype: str = "bf16"):
+                 top_k: int = 250, top_k_text: int = 25, kv_dtype: str = "bf16", kv_capacity: int | None = None):
         import ctypes as C
 
         from . import _lib
@@ -87,6 +87,7 @@ class DialogueService:
         self.lm_gen = LMGen(lm, use_sampling=use_sampling, temp=temp, temp_text=temp_text, top_k=top_k, top_k_text=top_k_text,
                             support_out_of_sync=True)
         self.lm_gen.kv_dtype = kv_dtype
+        self.lm_gen.kv_capacity = kv_capacity
         self.lm_gen.streaming_forever(batch_size)
         self.mimi.streaming_forever(batch_size)
         self._lib = _lib.lib()

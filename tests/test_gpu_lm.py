@@ -154,6 +154,42 @@ def test_step_outside_streaming_raises(lm):
 
 
 @torch.no_grad()
+def test_shortened_kv_ring_is_the_reference_ring_until_it_is_full(lm, tiny):
+    """`kv_capacity` (b200_lm_set_kv_capacity; SURVEY 8f item 3, rings sized to live fill): a ring of 8 slots gives the same
+    logits and tokens as the model's own 12-slot ring for a session's first 8 frames (nothing is evicted before position
+    `context`), and the frame that would overwrite a live key raises error flag 4 instead of silently forgetting."""
+    from moshi_b200.models import LMGen
+    cfg, _ = tiny
+    B, cap = 4, 8
+    assert cap < cfg.context
+    g = torch.Generator().manual_seed(99)
+    codes = torch.randint(0, cfg.card, (cap + 1, B, 8, 1), generator=g).cuda()
+    outs = {}
+    for name, kv_capacity in (("full", None), ("short", cap)):
+        gen = LMGen(lm, use_sampling=False, check=False)
+        gen.kv_capacity = kv_capacity
+        rec = []
+        with gen.streaming(B):
+            for i in range(cap):
+                gen.step(codes[i])
+                rec.append((gen.read_buffer("text_logits", torch.bfloat16, (B, cfg.text_card)).cpu(),
+                            gen.read_buffer("audio_tokens", torch.int64, (cfg.dep_q, B)).cpu()))
+            assert gen.error_flags() == 0
+            if kv_capacity is not None:
+                gen.step(codes[cap])                       # position 8 of an 8-slot ring
+                assert gen.error_flags() == 4
+                assert gen.error_flags() == 0              # reading clears
+        outs[name] = rec
+    same = total = 0
+    for (tl_f, at_f), (tl_s, at_s) in zip(outs["full"], outs["short"]):
+        # the same keys in the same order: equal up to the fp32 summation order of the attention's key groups
+        torch.testing.assert_close(tl_s.float(), tl_f.float(), rtol=0, atol=LOGIT_ATOL)
+        same += int((at_f == at_s).sum())
+        total += at_f.numel()
+    assert same / total >= 0.97, (same, total)
+
+
+@torch.no_grad()
 def test_rows_independent_graph_invariant_and_host_path():
     """Mid-size member of the 7B family at a serving batch, full 3000-slot ring machinery:
     (1) graph replay == eager launches bit for bit, (2) a session's tokens do not depend on its slot or its neighbours

@@ -207,8 +207,9 @@ def test_ns_gemm(M, N, K, epi):
         h = acc.bfloat16()
         want = (F.silu(h[:, :gate_rows].float()).bfloat16() * h[:, gate_rows:]).float()
     n_kb = (K + 63) // 64
-    for cs in ((0, 1) if epi == GATE else (0, 1, 2, 3, 4, 8)):
-        if cs > n_kb:
+    # 100 + n: single-tile units (N = 128 per instruction) with n K-splits
+    for cs in ((0, 1) if epi == GATE else (0, 1, 2, 3, 4, 8, 101, 102, 104)):
+        if cs % 100 > n_kb:
             continue
         y = _run_ns(lib, x, wt, res, M, N, K, epi, gate_rows, cluster=cs)
         print(stats(f"ns {M}x{N}x{K} epi={epi} cluster={cs}", y, want))

@@ -18,15 +18,8 @@ import torch  # noqa: E402
 
 
 def phase_names(dep_q: int, L: int) -> list[str]:
-    """Phase that ENDS at barrier e (1-based), in the kernel's order (dep_cluster.cu; dep_fused.cu with B200_DEP_KERNEL=1)."""
+    """Phase that ENDS at barrier e (1-based), in the kernel's order (dep_fused.cu)."""
     names = []
-    if os.environ.get("B200_DEP_KERNEL", "2") == "2":
-        for k in range(dep_q):
-            names.append("input+norm" if k == 0 else "sample+input+norm")
-            for _ in range(L):
-                names += ["gemm.in_proj(norm folded)", "attn", "gemm.out_proj(+res,ssq)", "gemm.lin_in(norm folded, gate)", "gemm.lin_out(+res,ssq)"]
-            names.append("gemm.head")
-        return names
     for k in range(dep_q):
         names.append("input+norm" if k == 0 else "sample+input+norm")
         for _ in range(L):
@@ -61,7 +54,7 @@ def main():
     for nm, v in zip(names, d):
         a = agg.setdefault(nm, [0, 0.0, 1e9, 0.0])
         a[0] += 1; a[1] += v; a[2] = min(a[2], v); a[3] = max(a[3], v)
-    out = {"kernel": "dep_cluster" if os.environ.get("B200_DEP_KERNEL", "2") == "2" else "dep_fused", "B": args.B, "total_us": (ts[n] - ts[0]) / 1e3, "barriers": n,
+    out = {"kernel": "dep_fused", "B": args.B, "total_us": (ts[n] - ts[0]) / 1e3, "barriers": n,
            "phases": {k: {"count": a[0], "sum_us": round(a[1], 1), "avg_us": round(a[1] / a[0], 2), "min_us": round(a[2], 2), "max_us": round(a[3], 2)}
                       for k, a in agg.items()},
            "substep0_us": [round(v, 2) for v in d[:names.index("gemm.head") + 1]]}
