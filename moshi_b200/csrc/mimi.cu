@@ -432,7 +432,10 @@ int run_seanet(b200_mimi* h, std::vector<SeaLayer>& layers) {
       q.a_sb = (long long)(nx.P + nx.t_in) * nx.cin; q.a_elu = nx.elu_in;
       q.B = B; q.Cout = l.cout; q.K = l.k; q.T = l.t_out;
       const long long n = (long long)B * l.t_out;
-      B200_LAUNCH(conv_first_tm_kernel, (unsigned)ceil_div64(n, 128), 128, (size_t)(l.cout * l.k + l.cout) * 4, h->body, q);
+      if (l.cout % 4 || 128 % (l.cout / 4) || l.k > 8) B200_FAIL(B200_ERR_INVALID, "mimi: first conv with %d channels / %d taps", l.cout, l.k);
+      const int per_pass = 128 / (l.cout / 4);
+      q.tok_per_block = per_pass * 16;           // 16 passes per CTA: the 4 x K weights of a thread are loaded once
+      B200_LAUNCH(conv_first_tm_kernel, (unsigned)ceil_div64(n, q.tok_per_block), 128, 0, h->body, q);
     } else if (l.simt_last) {
       ConvLast q;
       q.ext = l.ext_hi; q.e_sb = (long long)(l.P + l.t_in) * l.cin; q.Cin = l.cin; q.w = l.w_simt; q.bias = l.bias;
@@ -539,9 +542,9 @@ int quantize_cols(b200_mimi* h, const float* lat, long long lb, long long lc, lo
   levels[0] = c.q_n_semantic < h->num_codebooks ? c.q_n_semantic : h->num_codebooks;
   levels[1] = h->num_codebooks - levels[0];
   {
-    dim3 grid(Q, 2);
-    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)c.dimension * 4, h->body, lat, lb, lc, lt, n_cols, h->wT[0], h->wT[1],
-                h->rvq_res[0], h->rvq_res[1], c.dimension, Dq);
+    dim3 grid(ceil_div(Q, RVQ_PQ), 2, ceil_div(Dq, 64));
+    B200_LAUNCH(rvq_project_kernel, grid, 256, (size_t)(RVQ_PQ * c.dimension + 4 * RVQ_PQ * 64) * 4, h->body, lat, lb, lc, lt, n_cols, Q,
+                h->wT[0], h->wT[1], h->rvq_res[0], h->rvq_res[1], c.dimension, Dq);
   }
   const int max_levels = levels[0] > levels[1] ? levels[0] : levels[1];
   const size_t per = (size_t)bins * Dq;

@@ -333,22 +333,47 @@ struct RvqLevelArgs {
 };
 
 // res[which][q][m] = sum_k Wt[k][m] * lat[q][k]   (vq.py:135: 1x1 conv, no bias)
+// A CTA projects RVQ_PQ queries onto 64 outputs: 256 threads = 64 outputs x 4 slices of the input channels, 8 independent FMA
+// chains per weight load (one per query), the slices added in slice order.  (One CTA per query with a 512-long dependent chain
+// per thread took 85-100 us and re-read the 512 KB weight matrix for every query.)
+constexpr int RVQ_PQ = 8;
 static __global__ void __launch_bounds__(256) rvq_project_kernel(const float* __restrict__ lat, long long lb, long long lc,
-                                                          long long lt, int n_frames, const float* __restrict__ wT0,
+                                                          long long lt, int n_frames, int n_query, const float* __restrict__ wT0,
                                                           const float* __restrict__ wT1, float* __restrict__ res0,
                                                           float* __restrict__ res1, int Cin, int Dq) {
-  extern __shared__ float s_lat[];           // [Cin]
-  const int q = blockIdx.x, which = blockIdx.y;
-  const int b = q / n_frames, f = q % n_frames;
-  for (int c = threadIdx.x; c < Cin; c += blockDim.x) s_lat[c] = lat[b * lb + c * lc + f * lt];
+  extern __shared__ float s_lat[];           // [RVQ_PQ][Cin], then [4][RVQ_PQ][64] partial sums
+  float* s_part = s_lat + RVQ_PQ * Cin;
+  const int q0 = blockIdx.x * RVQ_PQ, which = blockIdx.y, m0 = blockIdx.z * 64;
+  for (int i = threadIdx.x; i < RVQ_PQ * Cin; i += blockDim.x) {
+    const int j = i / Cin, c = i - j * Cin, q = q0 + j;
+    float v = 0.f;
+    if (q < n_query) { const int b = q / n_frames, f = q % n_frames; v = lat[b * lb + c * lc + f * lt]; }
+    s_lat[i] = v;
+  }
   __syncthreads();
   const float* wT = which ? wT1 : wT0;
   float* res = which ? res1 : res0;
-  for (int m = threadIdx.x; m < Dq; m += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < Cin; ++k) acc = fmaf(wT[(long long)k * Dq + m], s_lat[k], acc);
-    res[(long long)q * Dq + m] = acc;
+  const int m = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int kper = (Cin + 3) / 4, k0 = sl * kper, k1 = min(Cin, k0 + kper);
+  float acc[RVQ_PQ];
+#pragma unroll
+  for (int j = 0; j < RVQ_PQ; ++j) acc[j] = 0.f;
+  if (m0 + m < Dq) {
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      const float w = wT[(long long)k * Dq + m0 + m];
+#pragma unroll
+      for (int j = 0; j < RVQ_PQ; ++j) acc[j] = fmaf(w, s_lat[j * Cin + k], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RVQ_PQ; ++j) s_part[(sl * RVQ_PQ + j) * 64 + m] = acc[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < RVQ_PQ * 64; i += blockDim.x) {
+    const int j = i >> 6, mm = i & 63, q = q0 + j;
+    if (q < n_query && m0 + mm < Dq)
+      res[(long long)q * Dq + m0 + mm] = ((s_part[(0 * RVQ_PQ + j) * 64 + mm] + s_part[(1 * RVQ_PQ + j) * 64 + mm]) +
+                                          s_part[(2 * RVQ_PQ + j) * 64 + mm]) + s_part[(3 * RVQ_PQ + j) * 64 + mm];
   }
 }
 
@@ -372,12 +397,14 @@ static __global__ void __launch_bounds__(RVQ_CHUNK) rvq_search_kernel(const RvqL
   for (int q = 0; q < RVQ_QT; ++q) dots[q] = 0.f;
   const bool ok = code < a.bins;
   const float* col = a.cbT[which] + (ok ? code : 0);
-  for (int d0 = 0; d0 < a.Dq; d0 += 8) {
-    float cv[8];
+  // 32 codebook loads in flight per thread (8 made every batch of FMAs wait a full L2 round trip: 32 round trips per level)
+  for (int d0 = 0; d0 < a.Dq; d0 += 32) {
+    float cv[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cv[j] = col[(long long)(d0 + j) * a.bins];
+    for (int j = 0; j < 32; ++j) cv[j] = d0 + j < a.Dq ? col[(long long)(d0 + j) * a.bins] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 32; ++j) {
+      if (d0 + j >= a.Dq) break;
       const float4 r0 = *reinterpret_cast<const float4*>(&s_res[(d0 + j) * RVQ_QT]);
       const float4 r1 = *reinterpret_cast<const float4*>(&s_res[(d0 + j) * RVQ_QT + 4]);
       dots[0] = fmaf(cv[j], r0.x, dots[0]); dots[1] = fmaf(cv[j], r0.y, dots[1]);

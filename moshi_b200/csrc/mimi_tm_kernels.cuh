@@ -23,38 +23,44 @@ struct ConvFirst {
   float* y; long long y_sb;                  // [B][T][Cout]
   float *a_hi, *a_lo; long long a_sb; int a_elu;      // consumer ext (+ its carried rows), row stride Cout
   int B, Cout, K, T;
+  int tok_per_block;          // tokens a CTA walks (a multiple of 128 / (Cout / 4))
 };
 static __global__ void __launch_bounds__(128) conv_first_tm_kernel(const ConvFirst p) {
   pdl_trigger_next();
-  extern __shared__ float sw[];              // [K][Cout] then bias [Cout]
-  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[(i % p.K) * p.Cout + i / p.K] = p.w[i];
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[p.Cout * p.K + i] = p.bias ? p.bias[i] : 0.f;
-  __syncthreads();
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= (long long)p.B * p.T) return;
-  const int b = (int)(n / p.T), t = (int)(n - (long long)b * p.T);
-  float xin[8];
+  // A thread owns 4 consecutive channels of one token: the Cout / 4 threads of a token write its 3 x Cout floats as contiguous
+  // 16-byte pieces (a warp stores 512 contiguous bytes per instruction; one thread per token wrote 32 scattered sectors per
+  // instruction and ran at a sixth of the write bandwidth).  Weights of the 4 channels live in registers.
+  const int tpt = p.Cout >> 2;                                   // threads per token (host: Cout % 4 == 0, 128 % tpt == 0)
+  const int q = threadIdx.x % tpt, slot = threadIdx.x / tpt, tok_per_pass = 128 / tpt;
+  float w[8][4], bias[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) xin[k] = k < p.K ? p.ext[(long long)b * p.E + t + k] : 0.f;       // cat(previous, x)[t + k]
-  float* y = p.y + (long long)b * p.y_sb + (long long)t * p.Cout;
-  float* ah = p.a_hi + (long long)b * p.a_sb + (long long)t * p.Cout;
-  float* al = p.a_lo + (long long)b * p.a_sb + (long long)t * p.Cout;
-  for (int c0 = 0; c0 < p.Cout; c0 += 4) {
+  for (int j = 0; j < 4; ++j) {
+    bias[j] = p.bias ? p.bias[4 * q + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k][j] = k < p.K ? p.w[(4 * q + j) * p.K + k] : 0.f;
+  }
+  const long long total = (long long)p.B * p.T;
+  for (long long n = (long long)blockIdx.x * p.tok_per_block + slot; n < min(total, (long long)(blockIdx.x + 1) * p.tok_per_block); n += tok_per_pass) {
+    const int b = (int)(n / p.T), t = (int)(n - (long long)b * p.T);
+    float xin[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xin[k] = k < p.K ? p.ext[(long long)b * p.E + t + k] : 0.f;     // cat(previous, x)[t + k]
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float acc = sw[p.Cout * p.K + c0 + j];
+      float acc = bias[j];
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (k < p.K) acc = fmaf(sw[k * p.Cout + c0 + j], xin[k], acc);
+        if (k < p.K) acc = fmaf(w[k][j], xin[k], acc);
       v[j] = acc;
     }
-    *reinterpret_cast<float4*>(y + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    const long long o = (long long)t * p.Cout + 4 * q;
+    *reinterpret_cast<float4*>(p.y + (long long)b * p.y_sb + o) = make_float4(v[0], v[1], v[2], v[3]);
     float hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) mtc::split_tf32(p.a_elu ? elu1(v[j]) : v[j], hi[j], lo[j]);
-    *reinterpret_cast<float4*>(ah + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(al + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(p.a_hi + (long long)b * p.a_sb + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(p.a_lo + (long long)b * p.a_sb + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 

@@ -57,7 +57,8 @@ def get_moshi_lm(filename: str | Path | None, lm_kwargs: dict | None = None,
                  synth_device: str | torch.device | None = None) -> LMModel:
     """``loaders.get_moshi_lm`` (loaders.py:366-446).  Checkpoints: ``model.safetensors`` (bf16), ``model.q8.safetensors``
     (loaders.py:33: every nn.Linear stored as a QLinear, ``weight`` int8 + ``weight_scb`` float32; needs ``quantize=True`` in the
-    kwargs, like the reference) and legacy ``.pt`` packages; packed ``in_proj_weight`` names are split (transformer.py:422-446).
+    kwargs, like the reference), ``.gguf`` (the Rust stack's quantised form, F32 / F16 / BF16 / Q8_0 tensors under candle's names:
+    ``moshi_b200/models/gguf.py``) and legacy ``.pt`` packages; packed ``in_proj_weight`` names are split (transformer.py:422-446).
     LoRA adapters are fused offline (loaders.py:512-513)."""
     if lora_weights is not None:
         raise ValueError("LoRA checkpoints are fused offline (loaders.py:512-513); pass fused weights")
@@ -76,6 +77,10 @@ def get_moshi_lm(filename: str | Path | None, lm_kwargs: dict | None = None,
                 for key in f.keys():
                     yield key, f.get_tensor(key)
         tensors = _stream()
+    elif Path(filename).suffix == ".gguf":
+        # the Rust stack's quantised checkpoints (rust/moshi-core/src/nn.rs:9-116): candle tensor names, Q8_0 blocks dequantised
+        from .gguf import read_gguf
+        _, tensors = read_gguf(filename)
     else:
         tensors = torch.load(filename, "cpu")["fsdp_best_state"]["model"]
     return LMModel(cfg, tensors, device=device, dtype=dtype)

@@ -1,6 +1,7 @@
 """GPU: on-disk checkpoints through the reference-shaped loaders (``loaders.get_mimi(filename)`` / ``get_moshi_lm(filename)``,
 loaders.py:323-446): safetensors with the reference's key names incl. the legacy packed attention / codebook names, and the
-pre-quantised ``model.q8.safetensors`` layout (``weight`` int8 + ``weight_scb`` float32, utils/quantize.py:13-22)."""
+pre-quantised ``model.q8.safetensors`` layout (``weight`` int8 + ``weight_scb`` float32, utils/quantize.py:13-22), and the Rust
+stack's GGUF form (candle tensor names, Q8_0 blocks; rust/moshi-core/src/nn.rs:9-116)."""
 import pytest
 import torch
 from safetensors.torch import save_file
@@ -115,3 +116,36 @@ def test_mimi_safetensors_round_trip_with_legacy_names(tmp_path):
             outs.append((codes.cpu(), m.decode(codes).cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert from_disk.num_codebooks == 8 and from_disk.total_codebooks == 32
+
+
+def test_lm_gguf_checkpoint_in_the_candle_layout(tmp_path):
+    """A ``.gguf`` file as the Rust stack loads it: candle's tensor names (``scripts/import_rust.py``), every linear weight as
+    ``Q8_0`` blocks, norms and embeddings bf16.  ``get_moshi_lm`` dequantises the blocks and maps the names back: the model must be
+    bit-identical to one built directly from the dequantised weights under the reference's names."""
+    from moshi_b200.models import LMModel, gguf, loaders
+    from tests.util import to_candle_layout
+    cfg = tiny_lm_config()
+    sd = synth_lm_state_dict(cfg, seed=scenarios.LM_SEED)
+    candle = to_candle_layout(cfg, sd)
+    q8 = lambda k, t: t.dim() == 2 and "emb" not in k and t.shape[-1] % 32 == 0       # every nn.Linear weight; norms are [1, 1, C]
+    path = tmp_path / "model.q8_0.gguf"
+    gguf.write_gguf(path, candle, q8_0=q8, metadata={"general.architecture": "moshi"})
+    n_q8 = sum(1 for k, t in candle.items() if q8(k, t))
+    assert n_q8 > 20
+    # the same dequantised values under the reference's names
+    deq = {}
+    from moshi_b200.models.state_dict import normalize_lm_state_dict
+    back = {k2: k for k in candle for k2 in normalize_lm_state_dict({k: candle[k]})}
+    for name, t in sd.items():
+        src = back[name]
+        if q8(src, candle[src]):
+            t = torch.from_numpy(gguf.dequantize_q8_0(gguf.quantize_q8_0(t.float().numpy()), t.shape)).bfloat16()
+        deq[name] = t
+    from_disk = loaders.get_moshi_lm(path, cfg.to_reference_kwargs(), device="cuda")
+    direct = LMModel(cfg, deq, device="cuda")
+    a, b = _steps(from_disk, cfg), _steps(direct, cfg)
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert torch.equal(x, y)
+    # and close to the unquantised model (weight-only Q8_0: ~0.4 % relative error per weight)
+    c = _steps(LMModel(cfg, sd, device="cuda"), cfg)
+    assert max((x.float() - y.float()).abs().max().item() for x, y in zip(a[0], c[0])) < 0.25

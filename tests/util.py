@@ -87,3 +87,23 @@ def sample_is_stable(logits: torch.Tensor, temp: float, top_k: int, noise: torch
             continue
         out[n] = bool(worst_w > best_case.max())
     return out
+
+
+def to_candle_layout(cfg, sd: dict) -> dict:
+    """The Rust / candle checkpoint layout of the LM (``scripts/import_rust.py:45-113``, what ``rust/moshi-core`` loads): the
+    temporal transformer under the reference's names, the depformer per codebook step as ``depformer.<k>.*``."""
+    out = {k: v for k, v in sd.items() if k.startswith(("text_emb", "text_linear", "out_norm", "emb.", "transformer.", "extra_heads."))}
+    for k in range(cfg.dep_q):
+        base = f"depformer.{k}."
+        out[base + "linear_in.weight"] = sd[f"depformer_in.{k}.weight"]
+        out[base + "linear_out.weight"] = sd[f"linears.{k}.weight"]
+        out[base + "emb.weight"] = sd["depformer_text_emb.weight"] if k == 0 else sd[f"depformer_emb.{k - 1}.weight"]
+        for layer in range(cfg.depformer_num_layers):
+            src, dst = f"depformer.layers.{layer}.", base + f"transformer.layers.{layer}."
+            out[dst + "self_attn.in_proj_weight"] = sd[src + f"self_attn.in_projs.{k}.weight"]
+            out[dst + "self_attn.out_proj.weight"] = sd[src + f"self_attn.out_projs.{k}.weight"]
+            out[dst + "norm1.alpha"] = sd[src + "norm1.alpha"]
+            out[dst + "norm2.alpha"] = sd[src + "norm2.alpha"]
+            out[dst + "gating.linear_in.weight"] = sd[src + f"gating.{k}.linear_in.weight"]
+            out[dst + "gating.linear_out.weight"] = sd[src + f"gating.{k}.linear_out.weight"]
+    return out
