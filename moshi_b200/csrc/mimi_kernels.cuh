@@ -30,7 +30,7 @@ struct ConvP {
   const float* w; const float* bias;
   float* y; long long yb, yc, yt;
   const float* res; long long rb, rc, rt;
-  float* a = nullptr; long long ab = 0, ac = 0, at = 0; int a_elu = 0;   // activated copy for a mimi_gemm.cuh consumer
+  float* a = nullptr; long long ab = 0, ac = 0, at = 0; int a_elu = 0;   // activated copy for a following layer (unused by the down-sampling conv)
   int B, Cin, Cout, K, stride, dil, Tout, elu_in;
   int M, N, Kd, cin_aligned;
 
