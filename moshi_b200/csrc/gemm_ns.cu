@@ -11,9 +11,11 @@
 //     accumulator holds gate in columns 0..127 and value in 128..255 of the SAME thread and silu(g) * u needs no exchange;
 //   * D = [128 sessions (TMEM lanes) x 256 weight rows (columns)] fp32: an epilogue thread owns one session and writes 16
 //     consecutive outputs (32 bytes) per TMEM load.
-//   * few-unit shapes (in_proj 48 units, out_proj / linear_out 16) are cut along K over a cluster of 2..8 CTAs; the partial
-//     accumulators are reduce-scattered over distributed shared memory by output columns (the stage ring is dead by then and
-//     serves as the receive buffer), summed in rank order (deterministic) and stored by the owning rank: no workspace, no atomics.
+//   * shapes with fewer units than SMs are cut along K over a cluster of 2..4 CTAs (in_proj: 48 pairs x 2; out_proj / linear_out:
+//     32 single tiles x 4, N = 128 per instruction there so that 128 SMs pull on the weights); the partial accumulators are
+//     reduce-scattered over distributed shared memory by output columns (the stage ring is dead by then and serves as the
+//     receive buffer), summed in rank order (deterministic) and stored by the owning rank: no workspace, no atomics.
+//     ns_default_plan() holds the measured choice per shape.
 //
 // Same packed weights, same epilogues and cast points as gemm_sk.cu (residual add bf16(res + bf16(acc)), gated SiLU
 // bf16(bf16(silu(g)) * u), gating.py:18-20); same PDL protocol (weights requested before griddepcontrol.wait).
