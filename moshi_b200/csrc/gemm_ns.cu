@@ -325,7 +325,6 @@ bool ns_supported(int M, int N, int K, int epi) {
 
 int ns_prepare() { return ns_init(); }
 
-// K-splits for a shape: as many as keep every CTA of the grid resident at once (units * cs <= #SMs) with >= 4 k-blocks each
 // The LM's choice of unit and K-split for a shape, from measurements on B200 at 48 / 104 sessions
 // (profiles/r02_c_kbench_ns_sweep.jsonl, profiles/r02_d_kbench_ns_sweep_m104.jsonl):
 //   * >= 40 pairs of tiles (in_proj 48, the gated MLP's input 88, the text head 125): N = 256 units, two K-splits while both CTAs
@@ -333,7 +332,7 @@ int ns_prepare() { return ns_init(); }
 //   * fewer (out_proj / linear_out: 32 tiles, depformer_in: 64): single-tile units (N = 128) so that more SMs pull on the
 //     weights, K cut over the largest power of two <= 4 that keeps the grid resident (32 x 4, 64 x 2 = 128 CTAs).
 // Wider clusters lose more to the receive traffic (~10 B/clk per SM over DSMEM) and to cluster placement than they gain.
-void ns_default_plan(int n_tiles, int num_kb, int epi, int* unit_tiles, int* cs) {
+static void ns_default_plan(int n_tiles, int num_kb, int epi, int* unit_tiles, int* cs) {
   if (epi == EPI_GATE) { *unit_tiles = 2; *cs = 1; return; }
   const int pairs = (n_tiles + 1) / 2;
   if (pairs >= 40) {
