@@ -155,6 +155,33 @@ def test_golden_masked_rows_and_reset(gpu, sd, golden_dir):
     assert total_bad <= 3
 
 
+@torch.no_grad()
+def test_long_stream_ten_thousand_frames(gpu, sd):
+    """40 sessions x 260 frames = 10 400 session-frames of streaming encode + decode beside the oracle (the
+    3xTF32 tensor-core path must keep the RVQ indices exact over long streams): every code compared margin-aware (zero
+    unexcused flips), PCM within tolerance on every frame, and the 250-slot rings of both bottleneck transformers wrap on
+    the way (frames 250..259 overwrite the oldest keys)."""
+    cfg = MimiConfig()
+    B, frames = 40, 260
+    pcm = scenarios.mimi_noise(B, frames, seed=77)
+    orc = MimiOracle(sd, cfg)
+    orc.streaming(B)
+    bad = unexcused = total = 0
+    worst_pcm = 0.0
+    with gpu.streaming(B):
+        for f in range(frames):
+            x = pcm[..., f * 1920:(f + 1) * 1920]
+            want, margins = orc.quantize(orc.encode_to_latent(x), return_margins=True)
+            got = gpu.encode(x.cuda())
+            b_, u_ = rvq_mismatches(got, want, margins)
+            bad, unexcused, total = bad + b_, unexcused + u_, total + want.numel()
+            out = gpu.decode(want.cuda()).cpu()          # both decoders are fed the oracle's codes: their states stay comparable
+            worst_pcm = max(worst_pcm, (out - orc.decode(want)).abs().max().item())
+    print(f"long stream: {bad} code mismatches of {total} ({unexcused} unexcused) over {B * frames} session-frames; worst PCM |d| {worst_pcm:.2e}")
+    assert unexcused == 0 and bad <= total // 2000
+    assert worst_pcm <= PCM_ATOL
+
+
 def test_partial_frames_are_rejected(gpu):
     with gpu.streaming(1):
         with pytest.raises(RuntimeError):
