@@ -252,7 +252,7 @@ def _dominant_kernel_roofline(B: int, kv_fill: int, device, fp8: int = 0) -> dic
 
 def _gemm_roofline(B: int, device) -> dict:
     """Second kernel by time: the tcgen05 GEMM of the gated-MLP input projection (184.5 MB of weights) as the LM launches it at this
-    batch size (non-swapped N = 256 kernel for 33..128 sessions, swap-AB stream-K otherwise)."""
+    batch size (non-swapped N = 256 kernel for 33..256 sessions, swap-AB stream-K otherwise)."""
     import ctypes as C
     from moshi_b200 import _lib
     lib = _lib.lib()
@@ -279,7 +279,7 @@ def _gemm_roofline(B: int, device) -> dict:
     peak, src = _peaks()
     gbs = alg / (ms * 1e-3) / 1e9
     return {"kernel": "%s (gating.linear_in 22528x4096 bf16 with the fused gated-SiLU epilogue, M=%d: the kernel the LM launches at this batch)"
-                      % ("tc::gemm_ns_kernel<GATE>" if 32 < M <= 128 else "tc::gemm_sk_kernel<GATE>", M), "bound": "hbm",
+                      % ("tc::gemm_ns_kernel<GATE>" if 32 < M <= 256 else "tc::gemm_sk_kernel<GATE>", M), "bound": "hbm",
             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "ms_per_launch": ms,
             "algorithmic_bytes": alg, "launches_per_step": 32}
 

@@ -337,10 +337,10 @@ int64_t b200_op_packed_bytes(int N, int K, int epi, int gate_rows);
 int b200_op_pack_tiles(const void* w_dev, void* out_dev, int N, int K, int epi, int gate_rows, void* stream);
 int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N,
                       int K, int epi, int gate_rows, int grid, int smem_budget, int stream_only, void* stream);
-/* The LM's linear kernel for 33..128 sessions (csrc/gemm_ns.cu): activations as the UMMA A operand, two pre-tiled weight tiles
+/* The LM's linear kernel for 33..256 sessions (csrc/gemm_ns.cu): activations as the UMMA A operand, two pre-tiled weight tiles
  * as B (N = 256 per tcgen05.mma), K cut over a cluster of `cluster` CTAs and reduced over distributed shared memory
  * (0 = the LM's own choice; 100 + n = single-tile units, N = 128 per instruction, n K-splits); same packed weights and
- * epilogues as b200_op_linear_sk, any M <= 128.
+ * epilogues as b200_op_linear_sk, any M <= 256.
  * (b200_op_linear_sk with smem_budget = -1 keeps the swap-AB kernels at every M: the comparison row of tools/kbench.py.) */
 int b200_op_linear_ns(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N, int K,
                       int epi, int gate_rows, int cluster, void* stream);

@@ -1,11 +1,12 @@
-// tcgen05 GEMM for the LM linears at 33..128 sessions:  y[M][N] = epi(x[M][K] . w[N][K]^T), bf16 in, fp32 in TMEM, bf16 out.
+// tcgen05 GEMM for the LM linears at 33..256 sessions:  y[M][N] = epi(x[M][K] . w[N][K]^T), bf16 in, fp32 in TMEM, bf16 out.
 //
 // gemm_sk.cu feeds the 128-row weight tile as the UMMA *A* operand and the sessions as N ("swap-AB"): right while the batch is
 // tiny, but a tcgen05.mma with M = 128 occupies the tensor pipe for ~120-140 cycles whatever N <= 128 is (measured: the stream-K
 // kernel runs the same copy pipeline 1.8x slower with its MMAs switched on than with them off, and cuBLAS beats it on every LM
 // shape from 48 sessions up, profiles/r02_a_kbench_gemm_vs_cublas_mimi.jsonl).  Here the operands keep their textbook roles:
 //
-//   * A = the activations, one [128 sessions x 64 k] SWIZZLE_128B box per k-block (2-D TMA, rows beyond M zero-filled);
+//   * A = the activations, one [128 sessions x 64 k] SWIZZLE_128B box per k-block (2-D TMA, rows beyond M zero-filled; two such
+//     blocks and two accumulators above 128 sessions);
 //   * B = TWO pre-tiled 128-row weight tiles side by side (N = 256 per instruction: twice the weight bytes per tensor-pipe
 //     cycle); for the gated MLP the pair is (gate rows, value rows) of the same outputs, already stored back to back, so the
 //     accumulator holds gate in columns 0..127 and value in 128..255 of the SAME thread and silu(g) * u needs no exchange;
@@ -38,7 +39,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_CS = 8;
 
 struct NsParams {
-  int M, N, K, out_rows, gate_rows, CS, num_kb, kb_per, stages, n_tiles, ldw, unit_tiles;
+  int M, N, K, out_rows, gate_rows, CS, num_kb, kb_per, stages, n_tiles, ldw, unit_tiles, mblocks;
   const uint8_t* wt;
   __nv_bfloat16* y; long long ldy;
   const __nv_bfloat16* res; long long ldr;
@@ -98,7 +99,8 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_off = (uint32_t)p.unit_tiles * TILE_BYTES;             // stage = B (one or two weight tiles) | A (activation box)
-  const uint32_t stage_bytes = a_off + A_BYTES;
+  const uint32_t a_bytes = (uint32_t)p.mblocks * A_BYTES;                // one or two blocks of 128 sessions (M <= 256)
+  const uint32_t stage_bytes = a_off + a_bytes;
   const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;
   const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull = bars + 16 * MAX_STAGES;
   const uint32_t tptr = tfull + 8;
@@ -124,7 +126,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tptr, 256);
+  if (warp == 1) tmem_alloc(tptr, 256u * p.mblocks);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -146,7 +148,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
       // weights first (they do not depend on the preceding kernel), activations after the dependency wait
       const int pre = n_items < p.stages ? n_items : p.stages;
       for (int i = 0; i < pre; ++i) {
-        mbar_expect_tx(full0 + 8 * i, b_bytes + A_BYTES);
+        mbar_expect_tx(full0 + 8 * i, b_bytes + a_bytes);
         load_b(i, i);
       }
       pdl_wait();
@@ -154,7 +156,7 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
       for (int i = 0; i < n_items; ++i) {
         if (i >= pre) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          mbar_expect_tx(full0 + 8 * s, b_bytes + A_BYTES);
+          mbar_expect_tx(full0 + 8 * s, b_bytes + a_bytes);
           load_b(i, s);
         }
         tma_load_2d(base + (uint32_t)s * stage_bytes + a_off, &tmap_x, full0 + 8 * s, (kb0 + i) * BLOCK_K, 0);
@@ -171,9 +173,12 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
         tc_fence_after();
         const uint32_t sb = base + (uint32_t)s * stage_bytes;
         const uint32_t sa = sb + a_off;
+        for (int mb = 0; mb < p.mblocks; ++mb) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_bf16(tmem_base, make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc, (i == 0 && k == 0) ? 0u : 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_base + (uint32_t)(mb * 256), make_desc(sa + mb * A_BYTES + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2), idesc,
+                      (i == 0 && k == 0) ? 0u : 1u);
+        }
         umma_commit(empty0 + 8 * s);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -183,108 +188,106 @@ gemm_ns_kernel(const __grid_constant__ CUtensorMap tmap_x, const NsParams p) {
   }
 
   const int q4 = warp & 3;
-  const int m = q4 * 32 + lane;                 // session row of an epilogue thread = TMEM lane
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-  const bool m_ok = m < p.M;
   const int my_c0 = col_begin(width, p.CS, me), my_c1 = col_begin(width, p.CS, me + 1);
-
-  if (p.CS > 1) {
-    if (warp >= 2) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-    }
-    ns_cluster_sync();                          // every rank's MMAs have retired: the stage rings are free to receive
-    if (warp >= 2) {
-      for (int q = 0; q < p.CS; ++q) {
-        if (q == me) continue;
-        const int c0q = col_begin(width, p.CS, q), c1q = col_begin(width, p.CS, q + 1);
-        const int slot = me < q ? me : me - 1;
-        const uint32_t dst = ns_map_to_rank(base + (uint32_t)((slot * 128 + m) * p.ldw) * 4u, (uint32_t)q);
-        for (int c = c0q; c < c1q; c += 16) {
-          uint32_t r[16];
-          if (n_items > 0) {
-            tmem_ld16(lane_addr + (uint32_t)c, r);
-            tmem_ld_wait();
-          } else {
+  if (warp >= 2) {
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+  }
+  bool waited = false;
+  for (int mb = 0; mb < p.mblocks; ++mb) {      // blocks of 128 sessions: one accumulator each, the receive buffer is reused
+    const int m = mb * 128 + q4 * 32 + lane;    // session row of an epilogue thread (TMEM lane q4*32 + lane of accumulator mb)
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mb * 256);
+    const bool m_ok = m < p.M;
+    if (p.CS > 1) {
+      ns_cluster_sync();                        // every rank's MMAs have retired / has read the previous block: the rings are free to receive
+      if (warp >= 2) {
+        for (int q = 0; q < p.CS; ++q) {
+          if (q == me) continue;
+          const int c0q = col_begin(width, p.CS, q), c1q = col_begin(width, p.CS, q + 1);
+          const int slot = me < q ? me : me - 1;
+          const uint32_t dst = ns_map_to_rank(base + (uint32_t)((slot * 128 + q4 * 32 + lane) * p.ldw) * 4u, (uint32_t)q);
+          for (int c = c0q; c < c1q; c += 16) {
+            uint32_t r[16];
+            if (n_items > 0) {
+              tmem_ld16(lane_addr + (uint32_t)c, r);
+              tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = 0u;
+              for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            if (m_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) ns_st_cluster_v4(dst + (uint32_t)(c - c0q + j) * 4u, r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
           }
-          if (m_ok) {
+        }
+        tc_fence_before();
+      }
+      ns_cluster_sync();                        // every partial has landed in its owner's receive buffer
+    }
+    if (warp >= 2) {
+      if (!waited) { pdl_wait(); waited = true; }   // y / res may still be in use by the predecessor
+      if (EPI == EPI_GATE) {
+        // columns j (gate) and 128 + j (value) of the same output; CS == 1 (the pair never needs a split: 88 units at 7B)
+        const int nb = unit * BLOCK_ROWS;
+        for (int c = 0; c < 128; c += 16) {
+          uint32_t g[16], u[16];
+          tmem_ld16(lane_addr + (uint32_t)c, g);
+          tmem_ld16(lane_addr + (uint32_t)(128 + c), u);
+          tmem_ld_wait();
+          const int valid = p.out_rows - (nb + c);
+          if (m_ok && valid > 0) {
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) ns_st_cluster_v4(dst + (uint32_t)(c - c0q + j) * 4u, r[j], r[j + 1], r[j + 2], r[j + 3]);
+            for (int j = 0; j < 16; ++j) {
+              const float gt = ns_bf16_round(__uint_as_float(g[j])), ut = ns_bf16_round(__uint_as_float(u[j]));
+              v[j] = ns_bf16_round(gt / (1.f + expf(-gt))) * ut;
+            }
+            store16(p.y + (long long)m * p.ldy + nb + c, v, valid);
+          }
+        }
+      } else {
+        const int nb = tile0 * BLOCK_ROWS;
+        for (int c = my_c0; c < my_c1; c += 16) {
+          float acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+          const int valid = p.out_rows - (nb + c);
+          float rv[16];
+          if (EPI == EPI_RESADD && m_ok && valid > 0) load16(p.res + (long long)m * p.ldr + nb + c, rv, valid);
+          for (int r = 0; r < p.CS; ++r) {      // rank order: the sum does not depend on which rank does it
+            if (r == me) {
+              if (n_items > 0) {
+                uint32_t t[16];
+                tmem_ld16(lane_addr + (uint32_t)c, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(t[j]);
+              }
+            } else if (m_ok) {
+              const int slot = r < me ? r : r - 1;
+              const float4* src = reinterpret_cast<const float4*>(recv_generic + (size_t)(slot * 128 + q4 * 32 + lane) * p.ldw + (c - my_c0));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t = src[j];
+                acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
+              }
+            }
+          }
+          if (m_ok && valid > 0) {
+            if (EPI == EPI_RESADD) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = rv[j] + ns_bf16_round(acc[j]);
+            }
+            store16(p.y + (long long)m * p.ldy + nb + c, acc, valid);
           }
         }
       }
       tc_fence_before();
     }
-    ns_cluster_sync();                          // every partial has landed in its owner's receive buffer
-  } else if (warp >= 2) {
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-  }
-
-  if (warp >= 2) {
-    pdl_wait();                                 // y / res may still be in use by the predecessor
-    if (EPI == EPI_GATE) {
-      // columns j (gate) and 128 + j (value) of the same output; CS == 1 (the pair never needs a split: 88 units at 7B)
-      const int nb = unit * BLOCK_ROWS;
-      for (int c = 0; c < 128; c += 16) {
-        uint32_t g[16], u[16];
-        tmem_ld16(lane_addr + (uint32_t)c, g);
-        tmem_ld16(lane_addr + (uint32_t)(128 + c), u);
-        tmem_ld_wait();
-        const int valid = p.out_rows - (nb + c);
-        if (m_ok && valid > 0) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float gt = ns_bf16_round(__uint_as_float(g[j])), ut = ns_bf16_round(__uint_as_float(u[j]));
-            v[j] = ns_bf16_round(gt / (1.f + expf(-gt))) * ut;
-          }
-          store16(p.y + (long long)m * p.ldy + nb + c, v, valid);
-        }
-      }
-    } else {
-      const int nb = tile0 * BLOCK_ROWS;
-      for (int c = my_c0; c < my_c1; c += 16) {
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        const int valid = p.out_rows - (nb + c);
-        float rv[16];
-        if (EPI == EPI_RESADD && m_ok && valid > 0) load16(p.res + (long long)m * p.ldr + nb + c, rv, valid);
-        for (int r = 0; r < p.CS; ++r) {        // rank order: the sum does not depend on which rank does it
-          if (r == me) {
-            if (n_items > 0) {
-              uint32_t t[16];
-              tmem_ld16(lane_addr + (uint32_t)c, t);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(t[j]);
-            }
-          } else if (m_ok) {
-            const int slot = r < me ? r : r - 1;
-            const float4* src = reinterpret_cast<const float4*>(recv_generic + (size_t)(slot * 128 + m) * p.ldw + (c - my_c0));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 t = src[j];
-              acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
-            }
-          }
-        }
-        if (m_ok && valid > 0) {
-          if (EPI == EPI_RESADD) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = rv[j] + ns_bf16_round(acc[j]);
-          }
-          store16(p.y + (long long)m * p.ldy + nb + c, acc, valid);
-        }
-      }
-    }
-    tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 256u * p.mblocks);
   if (p.CS > 1) ns_cluster_sync();              // no CTA exits while a peer could still address its shared memory
 }
 
@@ -320,7 +323,7 @@ int ns_init() {
 
 bool ns_supported(int M, int N, int K, int epi) {
   (void)N; (void)epi;
-  return M >= 1 && M <= 128 && K >= 8 && K % 8 == 0;
+  return M >= 1 && M <= 256 && K >= 8 && K % 8 == 0;
 }
 
 int ns_prepare() { return ns_init(); }
@@ -363,7 +366,8 @@ int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   ns_default_plan(p.n_tiles, p.num_kb, epi, &def_ut, &def_cs);
   if (unit_tiles == 0) unit_tiles = cluster > 0 ? 2 : def_ut;
   p.unit_tiles = (unit_tiles == 1 && epi != EPI_GATE) ? 1 : 2;
-  const uint32_t stage_bytes = (uint32_t)p.unit_tiles * TILE_BYTES + A_BYTES;
+  p.mblocks = M > 128 ? 2 : 1;
+  const uint32_t stage_bytes = (uint32_t)p.unit_tiles * TILE_BYTES + (uint32_t)p.mblocks * A_BYTES;
   const int n_units = (epi == EPI_GATE || p.unit_tiles == 1) ? p.n_tiles : (p.n_tiles + 1) / 2;
   int cs = cluster > 0 ? cluster : def_cs;
   if (epi == EPI_GATE) cs = 1;
@@ -391,13 +395,13 @@ int ns_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
   p.wt = static_cast<const uint8_t*>(w_tiles);
   p.y = y; p.ldy = ldy; p.res = res; p.ldr = ldr;
   // activations x [M][K]: boxes of [128 rows x 64 k]; rows >= M are zero-filled by the TMA unit
-  PlanKey key{x, ldx, M, K, 128};
+  PlanKey key{x, ldx, M, K, 128 * p.mblocks};
   auto it = cache.maps.find(key);
   if (it == cache.maps.end()) {
     CUtensorMap mp;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, 128u};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(128 * p.mblocks)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_ns_encode(&mp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(x), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

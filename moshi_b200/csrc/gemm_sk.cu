@@ -1125,8 +1125,8 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
     }
   }
   if (tune.norm_alpha) B200_FAIL(B200_ERR_STATE, "sk GEMM: a fused RMSNorm input is only available on the GEMV path (M=%d)", M);
-  // 33..128 sessions: activations as the A operand, two weight tiles (N = 256) per tcgen05.mma (gemm_ns.cu)
-  if (!i8 && tune.ns >= 0 && (tune.ns > 0 || (g_use_ns && M > 32)) && M <= 128 && tune.grid == 0 && tune.cluster == 0 && !tune.stream_only &&
+  // 33..256 sessions: activations as the A operand, two weight tiles (N = 256) per tcgen05.mma (gemm_ns.cu)
+  if (!i8 && tune.ns >= 0 && (tune.ns > 0 || (g_use_ns && M > 32)) && M <= 256 && tune.grid == 0 && tune.cluster == 0 && !tune.stream_only &&
       !tune.force_split && ns_supported(M, N, K, epi) && ldy % 8 == 0 && (!res || ldr % 8 == 0))
     return ns_linear(cache, x, ldx, w_tiles, y, ldy, res, ldr, M, N, K, epi, gate_rows, 0, tune.pdl, stream);
   // more than 32 sessions and few row tiles: a cluster of CTAs per tile, split along K, reduced over DSMEM

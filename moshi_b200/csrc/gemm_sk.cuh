@@ -45,7 +45,7 @@ struct SkTuning {
   // int8 path (QLinear): row-wise absmax int8 activations [M][K] + their scales, and the weight-row scales [N]
   const void* xq = nullptr; const float* sa = nullptr; const float* sw = nullptr;
   int pdl = 0;           // launch with programmatic stream serialization (the kernel waits on its own)
-  int ns = 0;            // 33..128 sessions: 0 = the non-swapped kernel (gemm_ns.cu) unless B200_GEMM_NS=0, -1 = never, 1 = always (tests)
+  int ns = 0;            // 33..256 sessions: 0 = the non-swapped kernel (gemm_ns.cu) unless B200_GEMM_NS=0, -1 = never, 1 = always (tests)
   // GEMV path only (M <= sk_gemv_max_m()): x is the residual stream and the linear's input is rmsnorm(x, norm_alpha)
   const __nv_bfloat16* norm_alpha = nullptr;
 };
@@ -69,7 +69,7 @@ int sk_linear(GemmPlanCache& cache, const __nv_bfloat16* x, long long ldx, const
               long long ldy, const __nv_bfloat16* res, long long ldr, int M, int N, int K, int epi, int gate_rows,
               float* ws, int* counters, const SkTuning& tune, cudaStream_t stream);
 
-// ---- non-swapped kernel for 33..128 sessions (gemm_ns.cu): A = activations, B = two weight tiles (N = 256) ------------
+// ---- non-swapped kernel for 33..256 sessions (gemm_ns.cu): A = activations, B = two weight tiles (N = 256) ------------
 bool ns_supported(int M, int N, int K, int epi);
 int ns_prepare();
 // cluster: K-splits (0 = the measured choice for the shape); same packed weights and epilogues as sk_linear

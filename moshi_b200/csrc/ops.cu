@@ -68,7 +68,7 @@ int b200_op_linear_sk(const void* x_dev, const void* w_tiles_dev, void* y_dev, c
                        static_cast<cudaStream_t>(stream));
 }
 
-// the non-swapped kernel (33..128 sessions in the LM) at any M <= 128; cluster = K-splits (0 = the LM's own choice)
+// the non-swapped kernel (33..256 sessions in the LM) at any M <= 256; cluster = K-splits (0 = the LM's own choice)
 int b200_op_linear_ns(const void* x_dev, const void* w_tiles_dev, void* y_dev, const void* res_dev, int M, int N, int K, int epi,
                       int gate_rows, int cluster, void* stream) {
   if (!x_dev || !w_tiles_dev || !y_dev) B200_FAIL(B200_ERR_INVALID, "op_linear_ns: null pointer");

@@ -69,7 +69,7 @@ def bench_gemm(lib, Ms, legacy=True, only="", ns_sweep=False):
             y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             res = torch.zeros(M, cols, device="cuda", dtype=torch.bfloat16)
             alg = wbytes + M * K * 2 + M * cols * 2 * (2 if epi == 1 else 1)
-            # "lm": what the LM launches for this shape (GEMV <= 2 rows, swap-AB stream-K <= 32, non-swapped N=256 kernel 33..128);
+            # "lm": what the LM launches for this shape (GEMV <= 2 rows, swap-AB stream-K <= 32, non-swapped N=256 kernel 33..256);
             # "swapAB": the swap-AB kernels at any M; "ns.csN": the non-swapped kernel with K cut over N CTAs
             variants = [("lm", 0, 0, 0), ("swapAB", 0, -1, 0), ("swapAB.stream_only", 0, -1, 1)]
             if ns_sweep and M <= 128:
