@@ -4,6 +4,7 @@
     python tools/configs.py --config 2              # Mimi streaming encode+decode, B = 1 .. 256
     python tools/configs.py --config 3              # Moshi 7B LMGen.step, B = 1: p50/p90 latency, xRT (fill 200 and full ring)
     python tools/configs.py --config 4 [--sessions N]   # one GPU's shard of the 512-session config, all rows / 25 % masked
+    python tools/configs.py --config 4 --sessions -512  # 512 / N sessions on one GPU (N = 4, 2) with the rings sized to what fits
     python tools/configs.py --config 5 [--kv-dtype int8]   # int8 (QLinear) weights: sessions swept up to what HBM holds
 """
 from __future__ import annotations
@@ -130,6 +131,47 @@ def config4(sessions: int):
                               "ms_per_step": round(ms, 2), "p_max_ms": round(max(times), 2), "real_time": ms <= 80.0}), flush=True)
 
 
+def config4_shards():
+    """The 512-session configuration as written (512 / N sessions per GPU): which history the bf16 rings can hold when that many
+    sessions share one GPU ("the fill level at which 512 fit"), with the rings sized to it (`kv_capacity`,
+    reference numerics until a session is that old) — N = 2 (256 sessions per GPU) and N = 4 (128)."""
+    from moshi_b200.models import LMGen, loaders
+    lm, cfg = _lm()
+    mimi = loaders.get_mimi(None, device="cuda", num_codebooks=8)
+    free, _ = torch.cuda.mem_get_info()
+    for n_gpus in (4, 2):
+        B = 512 // n_gpus
+        slots = int(((free - 6e9) / B - 40e6) // 524288)
+        slots = min(slots, cfg.context)
+        fill = slots - 64
+        g = torch.Generator().manual_seed(4242)
+        pcm = (0.1 * torch.randn(B, 1, 1920, generator=g)).cuda()
+        gen = LMGen(lm, use_sampling=True, temp=0.8, temp_text=0.7)
+        gen.kv_capacity = slots if slots < cfg.context else None
+        with mimi.streaming(B), gen.streaming(B), torch.no_grad():
+            gen.assume_fill(fill)
+            times = []
+            for i in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                toks = gen.step(mimi.encode(pcm))
+                audio = toks[:, 1:].clamp(min=0) if toks is not None else torch.zeros(B, 8, 1, dtype=torch.int64, device="cuda")
+                mimi.decode(audio)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    times.append(e0.elapsed_time(e1))
+            flags = gen.error_flags()
+        ms = statistics.mean(times)
+        print(json.dumps({"config": 4, "what": "512 sessions on %d GPUs: one GPU's shard with the bf16 rings sized to what fits" % n_gpus,
+                          "n_gpus": n_gpus, "sessions_on_this_gpu": B, "kv_capacity_slots": slots,
+                          "history_each_session_can_hold_s": round(slots * 0.08, 1), "kv_fill": fill,
+                          "ms_per_step": round(ms, 2), "p_max_ms": round(max(times), 2), "real_time": ms <= 80.0,
+                          "stepped_past_capacity": bool(flags & 4)}), flush=True)
+        del gen
+        torch.cuda.empty_cache()
+
+
 def config5(kv_dtype: str):
     """int8 weights (row-wise absmax QLinear), 1 GPU: sweep the sessions upward until the step exceeds 80 ms or HBM is full."""
     from moshi_b200.config import MOSHI_7B
@@ -180,7 +222,10 @@ def main():
     elif args.config == 3:
         config3()
     elif args.config == 4:
-        config4(args.sessions)
+        if args.sessions == -512:
+            config4_shards()
+        else:
+            config4(args.sessions)
     elif args.config == 5:
         config5(args.kv_dtype)
 
