@@ -7,7 +7,6 @@ from moshi_b200.config import LMConfig, tiny_lm_config
 from moshi_b200.synth import synth_lm_state_dict
 from oracle import scenarios
 from oracle.lm import LMOracle, LMSpec, sample_token
-from tests.util import stats
 
 pytestmark = pytest.mark.gpu
 

@@ -223,7 +223,6 @@ def test_2b_shape_family_member_against_the_oracle():
     """``configs/moshi_dev_2b.json``'s shape of the step on a tiny member of the family: 32 codebooks of which 16 are
     generated, acoustic delay 2, RoPE period 100000: exercises 33-wide token rings, 16 depformer sub-steps and 16 keys in the
     depformer attention (the 7B model stops at 8)."""
-    import json
     from moshi_b200.config import tiny_lm_config
     delays = [0, 0] + [2] * 15 + [0] + [2] * 15
     cfg = tiny_lm_config(n_q=32, dep_q=16, delays=delays, depformer_context=16, max_period=100000.0)

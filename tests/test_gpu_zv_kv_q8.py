@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from oracle.transformer import kv_roundtrip
 from tests.test_gpu_ops import _rope_ref
-from tests.util import cptr, stats
+from tests.util import cptr
 
 pytestmark = pytest.mark.gpu
 

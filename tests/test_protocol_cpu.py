@@ -1,5 +1,4 @@
 """CPU: the wire protocol (rust/protocol.md) and the connection front-end over a fake frame service."""
-import json
 
 import numpy as np
 import pytest
