@@ -1,7 +1,6 @@
 """CPU: the margin-aware sampled-token comparison itself (tests/test_gpu_lm.py::_peaked_sampling_run), with a second oracle
 standing in for the device: identical logits, so every decision equals the teacher's, and every disagreement with the reference's
 recorded decisions must be one the stability test flags (exact bf16 ties ranked by token id instead of torch.topk's order)."""
-import torch
 from safetensors.torch import load_file
 
 from moshi_b200.config import tiny_lm_config
